@@ -1,0 +1,208 @@
+/*
+ * mntr_gpu.h -- C ABI of the B200 bound-propagation engine (libmntr_gpu.so).
+ *
+ * This is the drop-in boundary for Minotaur's activity-based FBBT hot path.  The
+ * reference has no C ABI for it: the path lives behind the C++ plugin class
+ * Minotaur::Handler (/root/reference/src/base/Handler.h:48-384).  The Minotaur-side
+ * adapter (minotaur_b200/handler/GpuBoundHandler.{h,cpp}) implements that class and
+ * calls the entry points below; INTEGRATION.md shows the wiring.  Each entry point
+ * names the reference routine(s) whose work it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a HOST pointer unless the name says "_dev";
+ *   - return 0 on success, <0 on error (MNTR_E_*); mntr_gpu_last_error() gives text;
+ *   - a context is used by one host thread at a time (the reference creates one
+ *     handler per B&B thread, examples/simple-bnb/McBnb.cpp:84-140) and owns its
+ *     device, stream and workspaces; there is no global mutable state;
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails.
+ *
+ * Arithmetic: IEEE fp64.  With MNTR_ROUND_DIRECTED (default) activities and implied
+ * bounds are rounded outward (__dadd_rd/_ru, __dmul_rd/_ru, __ddiv_rd/_ru) so no
+ * bound is ever tighter than exact arithmetic allows; MNTR_ROUND_NEAREST reproduces
+ * the reference's round-to-nearest, unfused arithmetic bit for bit where the
+ * evaluation order is also the reference's (MNTR_ORDER_REFERENCE).
+ */
+#ifndef MNTR_GPU_H
+#define MNTR_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNTR_GPU_ABI_VERSION 1
+
+typedef struct mntr_gpu_ctx mntr_gpu_ctx;
+
+/* error codes */
+enum {
+  MNTR_OK          = 0,
+  MNTR_E_ARG       = -1,   /* bad argument */
+  MNTR_E_CUDA      = -2,   /* CUDA runtime error (see mntr_gpu_last_error) */
+  MNTR_E_STATE     = -3,   /* call out of order (e.g. tighten before load) */
+  MNTR_E_NOMEM     = -4,
+  MNTR_E_UNSUPPORTED = -5,
+  MNTR_E_NCCL      = -6
+};
+
+/* variable types: Minotaur::VariableType, Types.h:83-89 */
+enum { MNTR_BINARY = 0, MNTR_INTEGER = 1, MNTR_IMPLBIN = 2, MNTR_IMPLINT = 3, MNTR_CONTINUOUS = 4 };
+
+/* per-box verdicts */
+enum {
+  MNTR_FEASIBLE      = 0,
+  MNTR_INFEAS_BOUNDS = 1,  /* lb > ub + 1e-8 : LinearHandler::checkBounds_, LinearHandler.cpp:328-359 */
+  MNTR_INFEAS_ROW    = 2,  /* activity-infeasible linear row : linBndTighten_, :994-1015.  The
+                              reference's node mode drops this status (:1631); it is still a
+                              valid proof of infeasibility. */
+  MNTR_INFEAS_NL     = 3,  /* CGraph: NlPresHandler::chkRed_ (:139-150) or CNode::propBounds_ */
+  MNTR_ERROR_NL      = 4   /* CGraph evaluation error (SolveError in the reference) */
+};
+
+/* rounding of activities / implied bounds */
+enum { MNTR_ROUND_DIRECTED = 0, MNTR_ROUND_NEAREST = 1 };
+
+/* sweep order of the linear rows */
+enum {
+  MNTR_ORDER_JACOBI    = 0,  /* all rows read the box of the round start; candidates merged
+                                with exact max/min.  Result is
+                                independent of row order and of the number of GPUs. */
+  MNTR_ORDER_REFERENCE = 1   /* the reference's in-place, index-ordered sweep
+                                (LinearHandler::varBndsFromCons_, :493-541) reproduced by
+                                wavefront scheduling: rows that share no variable run
+                                concurrently, levels run in order. */
+};
+
+/* loop control */
+enum {
+  MNTR_LOOP_FIXPOINT       = 0,  /* sweep until nothing changes (or max_rounds) */
+  MNTR_LOOP_SIMPLEPRESOLVE = 1   /* LinearHandler::simplePresolve's truncation: <=10 rounds,
+                                    rounds >=3 only while integer variables moved (:1625-1627);
+                                    NlPresHandler::simplePresolve: <=2 sweeps (:1034-1035) */
+};
+
+typedef struct {
+  int32_t rounding;     /* MNTR_ROUND_*  */
+  int32_t order;        /* MNTR_ORDER_*  */
+  int32_t loop;         /* MNTR_LOOP_*   */
+  int32_t max_rounds;   /* 0 = no extra cap */
+} mntr_gpu_options;
+
+/* per-call statistics (LinPresolveStats / NlPresStats counterparts, LinearHandler.h:22-36) */
+typedef struct {
+  int64_t nnz_updates;   /* sum over evaluated (row, box) pairs of the row's term count */
+  int64_t rows_evaluated;
+  int64_t n_infeasible;  /* boxes with verdict != MNTR_FEASIBLE */
+  int32_t max_rounds;    /* largest number of rounds any box took */
+  int32_t reserved;
+  double  kernel_ms;     /* device time of the tighten kernels (CUDA events) */
+  double  h2d_ms, d2h_ms;
+} mntr_gpu_stats;
+
+/* ---- lifetime -------------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device`.  Replaces: LinearHandler / NlPresHandler
+ * construction (LinearHandler.cpp:66-97, NlPresHandler.cpp:69-91). */
+int mntr_gpu_create(int device, mntr_gpu_ctx **out);
+void mntr_gpu_destroy(mntr_gpu_ctx *ctx);
+const char *mntr_gpu_last_error(const mntr_gpu_ctx *ctx);
+int mntr_gpu_abi_version(void);
+/* number of CUDA devices visible, <0 if the runtime is unusable */
+int mntr_gpu_device_count(void);
+
+/* ---- problem upload --------------------------------------------------------------- */
+
+/* Linear rows  row_lb <= A x <= row_ub  as CSR; columns strictly ascending inside a row
+ * (the term order of LinearFunction, Types.h:496).  Entries with |a| <= 1e-9 are dropped
+ * as LinearFunction::addTerm does (LinearFunction.cpp:20-23,89-95).  row_active may be
+ * NULL (all rows active); 0 marks a deleted row (Constraint state DeletedCons).
+ * Flattens: Problem / Constraint / LinearFunction / Variable::cons_ object graph. */
+int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t *row_ptr,
+                         const int32_t *col, const double *val, const double *row_lb,
+                         const double *row_ub, const uint8_t *var_type,
+                         const uint8_t *row_active);
+
+/* CGraph constraints  c_lb <= f_c(x) + lin_c.x <= c_ub  as expression tapes.  Node order
+ * inside a tape is the reference's evaluation order: variable nodes by ascending variable
+ * id (vq_), constants, then operator nodes in the post-order of CGraph::finalize (dq_,
+ * CGraph.cpp:557-644); the last node is the output.  op = Minotaur::OpCode (OpCode.h);
+ * arg0/arg1 = local node indices (OpVar: arg0 = variable; OpSumList: child[arg0..arg1)).
+ * Requires a previous mntr_gpu_load_linear (m may be 0) for n and the variable types.
+ * Flattens: CGraph / CNode. */
+int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_ptr,
+                         const uint8_t *op, const int32_t *arg0, const int32_t *arg1,
+                         const double *cnst, const int32_t *child, const int32_t *lin_ptr,
+                         const int32_t *lin_col, const double *lin_val, const double *c_lb,
+                         const double *c_ub);
+
+/* Objective cut-off row  c.x <= rhs  (rhs = incumbent value - objective constant);
+ * k = 0 removes it.  Replaces: LinearHandler::varBndsFromObj_ (LinearHandler.cpp:544-597). */
+int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *col, const double *val,
+                        double rhs);
+
+/* ---- the hot path ------------------------------------------------------------------ */
+
+/* Tightens n_boxes independent node boxes.  lb/ub are box-major [n_boxes][n] host arrays,
+ * updated in place.  Per box: verdict[b] (MNTR_FEASIBLE ...), rounds[b] (sweeps run) and
+ * nnz_updates[b]; any of the three output arrays may be NULL.  opts may be NULL (directed
+ * rounding; Jacobi order for a single box, reference order for a batch; fixpoint loop).
+ * Replaces: LinearHandler::simplePresolve / presolveNode (LinearHandler.cpp:1592-1653) and,
+ * when tapes are loaded, NlPresHandler::simplePresolve / presolveNode (:1009-1059), i.e. one
+ * PCBProcessor::presolveNode_ pass (PCBProcessor.cpp:134-175) per box. */
+int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
+                     const mntr_gpu_options *opts, int32_t *verdict, int32_t *rounds,
+                     int64_t *nnz_updates);
+
+/* Same work with boxes given as sparse branching deltas on a common root box and results
+ * returned as the bound changes to emit as VarBoundMods (VarBoundMod.cpp:27-43): the form in
+ * which B&B nodes actually differ (Node r_mods, NodeIncRelaxer.cpp:94-155).
+ *   root_lb/root_ub [n]; box b applies deltas delta_ptr[b] .. delta_ptr[b+1):
+ *   (delta_var, delta_is_upper, delta_val).
+ * Outputs: mod_ptr [n_boxes+1] offsets into (mod_var, mod_is_upper, mod_val), capacity
+ * mod_cap entries; *n_mods_out receives the total produced (may exceed mod_cap: call again
+ * with a larger buffer).  A mod is emitted for every (var, side) whose final bound differs
+ * from the box's initial bound. */
+int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *root_lb,
+                           const double *root_ub, const int64_t *delta_ptr,
+                           const int32_t *delta_var, const uint8_t *delta_is_upper,
+                           const double *delta_val, const mntr_gpu_options *opts,
+                           int32_t *verdict, int32_t *rounds, int64_t *mod_ptr,
+                           int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val,
+                           int64_t mod_cap, int64_t *n_mods_out);
+
+/* Device-resident variant for callers that keep boxes in HBM (bench "value" leg, and the
+ * multi-GPU drivers): boxes_dev is the engine's own layout, a double2 {lb,ub} array
+ * [n][ld] with ld = mntr_gpu_box_ld(n_boxes) (node-minor: the boxes of one variable are
+ * contiguous).  verdict_dev/rounds_dev/nnz_dev are device arrays of n_boxes entries. */
+int64_t mntr_gpu_box_ld(int32_t n_boxes);
+int mntr_gpu_tighten_dev(mntr_gpu_ctx *ctx, int32_t n_boxes, void *boxes_dev,
+                         const mntr_gpu_options *opts, int32_t *verdict_dev,
+                         int32_t *rounds_dev, int64_t *nnz_dev);
+/* box-major host arrays <-> engine layout in HBM (uses the context's stream) */
+int mntr_gpu_boxes_upload(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *lb,
+                          const double *ub, void *boxes_dev);
+int mntr_gpu_boxes_download(mntr_gpu_ctx *ctx, int32_t n_boxes, const void *boxes_dev,
+                            double *lb, double *ub);
+
+/* statistics of the last tighten call */
+int mntr_gpu_get_stats(const mntr_gpu_ctx *ctx, mntr_gpu_stats *out);
+
+/* ---- row-partitioned multi-GPU (one process per GPU) --------------------------------- */
+
+/* Every rank loads ITS row block with mntr_gpu_load_linear (all n columns) and holds a
+ * full replica of the box.  After this call mntr_gpu_tighten on a single box runs Jacobi
+ * rounds whose candidate bounds are merged across ranks each round with an NCCL
+ * all-reduce (MAX on lb, MIN on ub, riding as one MAX over [lb ; -ub]) plus the change /
+ * infeasible flags; integer rounding and the bound check run replicated after the merge,
+ * so every rank ends with bit-identical boxes, independent of the number of ranks.
+ * nccl_unique_id: 128 bytes from mntr_gpu_nccl_unique_id on rank 0, broadcast by the
+ * caller (MPI / torch.distributed / files). */
+int mntr_gpu_nccl_unique_id(void *id128);
+int mntr_gpu_comm_init(mntr_gpu_ctx *ctx, int32_t n_ranks, int32_t rank, const void *id128);
+int mntr_gpu_comm_destroy(mntr_gpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MNTR_GPU_H */

@@ -1,0 +1,57 @@
+// device_problem.cuh -- flattened problem data as the kernels see it (all device pointers).
+#pragma once
+#include "common.cuh"
+
+namespace mntr {
+
+// Linear rows.  CSR whose row starts are padded to an EVEN entry index so a lane can fetch
+// two (col,val) pairs with one 64-bit + one 128-bit load; padding entries have val == 0 and
+// a valid column, and are skipped by value.  CSC (var -> rows) replaces Variable::cons_
+// (Variable.h:164-191) for the bFlag propagation of LinearHandler::changeBFlag_ (:1229-1234).
+struct LinDev {
+  int32_t m, n;
+  const int32_t *row_ptr;   // [m+1] padded offsets (even)
+  const int32_t *col;       // [nnz_padded]
+  const double  *val;       // [nnz_padded]
+  const int32_t *row_nnz;   // [m] true term count
+  const double  *row_lb;    // [m]
+  const double  *row_ub;    // [m]
+  const uint8_t *var_type;  // [n]
+  const uint8_t *row_active;// [m] 1 = active
+  const int32_t *csc_ptr;   // [n+1]
+  const int32_t *csc_row;   // [nnz]
+  // wavefront schedule of the reference's index-ordered in-place sweep
+  int32_t n_levels;
+  const int32_t *level_ptr; // [n_levels+1]
+  const int32_t *level_row; // [m] rows sorted by (level, index)
+};
+
+// CGraph tapes (see include/mntr_gpu.h for the node order contract)
+struct NlDev {
+  int32_t n_cons;
+  const int32_t *tape_ptr;  // [n_cons+1]
+  const uint8_t *op;
+  const int32_t *arg0, *arg1;
+  const double  *cnst;
+  const int32_t *child;
+  const int32_t *lin_ptr, *lin_col;
+  const double  *lin_val;
+  const double  *c_lb, *c_ub;
+  int32_t max_nodes;        // longest tape
+  int32_t n_levels;
+  const int32_t *level_ptr; // [n_levels+1]
+  const int32_t *level_con; // [n_cons] constraints sorted by (level, index)
+};
+
+// workspace of the single-box Jacobi fixpoint kernel
+struct SingleWs {
+  double2 *box;    // [n] {lb, ub} of the round start
+  double2 *nbox;   // [n] candidates of the round (atomic max / min)
+  uint8_t *flag_a; // [m] row flags, current
+  uint8_t *flag_b; // [m] row flags, next
+  int32_t *ring;   // [8] per-round change flags: ring[r%3] changed, ring[3 + r%3] int moved
+  int32_t *status; // [0] verdict, [1] rounds
+  unsigned long long *counters;  // [0] nnz_updates, [1] rows evaluated
+};
+
+}  // namespace mntr

@@ -1,0 +1,53 @@
+// kernels.h -- host-callable launchers of the CUDA kernels (internal to libmntr_gpu.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_problem.cuh"
+
+namespace mntr {
+
+// K1 (linear_single.cu): single-box Jacobi fixpoint, one cooperative launch.
+// lb_dev/ub_dev [n] are read at the start and overwritten with the tightened box.
+cudaError_t launch_single_jacobi(const LinDev &P, const SingleWs &W, double *lb_dev, double *ub_dev,
+                                 int lanes_per_row, bool directed, int max_rounds, int loop_mode,
+                                 int sm_count, cudaStream_t stream);
+
+// per-box outputs / controls of the batched kernels
+struct BatchIo {
+  double2 *boxes;        // [n][ld] {lb,ub}, node-minor
+  int64_t ld;            // boxes per variable row (multiple of 32)
+  int32_t n_boxes;
+  uint32_t *rowflag;     // [tiles][m] bit b = row flagged for box tile*32+b   (bFlag)
+  int32_t *verdict;      // [n_boxes]
+  int32_t *rounds;       // [n_boxes]
+  long long *nnz;        // [n_boxes]
+};
+
+// K3 (linear_batch.cu): batched node boxes, the reference's in-place index-ordered sweep
+// reproduced by wavefront levels; one CTA per tile of 32 boxes.
+cudaError_t launch_batch_reference(const LinDev &P, const NlDev *N, const BatchIo &io, bool directed,
+                                   int loop_mode, int max_rounds, int lin_enabled, int nl_enabled,
+                                   cudaStream_t stream);
+
+// box-major [n_boxes][n] lb/ub (device staging) <-> node-minor double2 boxes
+cudaError_t launch_boxes_pack(const double *lb_bm, const double *ub_bm, int32_t n, int32_t box0,
+                              int32_t nb, double2 *boxes, int64_t ld, cudaStream_t stream);
+cudaError_t launch_boxes_unpack(const double2 *boxes, int64_t ld, int32_t n, int32_t box0, int32_t nb,
+                                double *lb_bm, double *ub_bm, cudaStream_t stream);
+// fill padding boxes [n_boxes, ld) with a harmless copy of box 0
+cudaError_t launch_boxes_pad(double2 *boxes, int64_t ld, int32_t n, int32_t n_boxes, cudaStream_t stream);
+
+// node form: boxes from root + deltas, and extraction of the resulting mods
+cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub, int32_t n,
+                                   int32_t n_boxes, double2 *boxes, int64_t ld, cudaStream_t stream);
+cudaError_t launch_apply_deltas(const long long *delta_ptr, const int32_t *delta_var,
+                                const uint8_t *delta_is_upper, const double *delta_val,
+                                int32_t n_boxes, double2 *boxes, int64_t ld, cudaStream_t stream);
+cudaError_t launch_count_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n,
+                              int32_t n_boxes, long long *mod_count, cudaStream_t stream);
+cudaError_t launch_emit_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n,
+                             int32_t n_boxes, const long long *mod_ptr, long long cap, int32_t *mod_var,
+                             uint8_t *mod_is_upper, double *mod_val, cudaStream_t stream);
+
+}  // namespace mntr

@@ -1,0 +1,440 @@
+// linear_batch.cu -- K3: thousands of B&B node boxes tightened in one launch, in the
+// REFERENCE'S sweep order.
+//
+// Layout: boxes are node-minor, double2 {lb,ub} [n][ld]: the 32 boxes of a tile are
+// contiguous for one variable, so a warp (lane = box) gathers a variable's bounds for its
+// whole tile with one coalesced 512-byte request of 128-bit loads, while the CSR entries
+// (col,val) are warp-uniform broadcast loads amortised over the 32 boxes.
+//
+// One CTA owns one tile of 32 boxes for the whole call.  Because boxes are independent, the
+// only ordering constraint of the reference's in-place, index-ordered Gauss-Seidel sweep
+// (LinearHandler::varBndsFromCons_, LinearHandler.cpp:493-541) is between rows that share a
+// variable; rows are therefore scheduled in wavefront levels (level = 1 + max level of an
+// earlier row sharing a variable, built at load time) and a level boundary is a plain
+// __syncthreads() -- no grid-wide synchronisation, no atomics on bounds, no second buffer.
+// Inside a level the warps of the CTA take rows round-robin.  With round-to-nearest
+// arithmetic every lane performs exactly the reference's operation sequence (ascending
+// column order, unfused mul/add), so results are bitwise those of the reference; with
+// directed rounding (default) they are outward-rounded versions of the same.
+//
+// Per sweep, per box (reference lines in brackets):
+//   rows   : linBndTighten_ [:952-1045] = getLfBnds_ [:1237-1258], getSingLfBnds_
+//            [:1261-1319] (the flag machine kept as coded), infeasibility [:994-1015],
+//            updateLfBoundsFromLb_ [:1048-1136], activity recomputation when the row changed
+//            something [:1027-1032], updateLfBoundsFromUb_ [:1139-1226]; bFlag set on every
+//            row of a changed variable [changeBFlag_ :1229-1234] through the CSC lists.
+//   ints   : tightenInts_ [:415-490]   bounds: checkBounds_ [:328-359]
+//   loop   : simplePresolve [:1605-1653] (<=10 rounds, rounds >=3 only while integer
+//            variables moved) or fixpoint.
+// Deviation, deliberate: an activity-infeasible row yields verdict MNTR_INFEAS_ROW and stops
+// that box; the reference's node mode drops that status (:1631).
+#include "device_problem.cuh"
+#include "kernels.h"
+
+namespace mntr {
+
+namespace {
+
+constexpr int kBatchWarps = 16;
+constexpr int kBatchThreads = kBatchWarps * 32;
+
+struct TileShared {
+  int changed[32];
+  int nint[32];
+  int verdict[32];
+  unsigned long long nnz[32];
+};
+
+// min / max activity of one row for this lane's box  [getLfBnds_]
+template <class R>
+__device__ __forceinline__ void row_activity(const LinDev &P, int beg, int end, const double2 *bx,
+                                             int64_t ld, bool mine, double &ll, double &uu)
+{
+  ll = 0.0; uu = 0.0;
+  for (int t = beg; t < end; ++t) {
+    const double a = __ldg(P.val + t);
+    if (a == 0.0) continue;                         // alignment padding (warp-uniform)
+    const int j = __ldg(P.col + t);
+    if (mine) {
+      const double2 b = bx[(int64_t)j * ld];
+      if (a > 0) { ll = R::add_lo(ll, R::mul_lo(a, b.x)); uu = R::add_hi(uu, R::mul_hi(a, b.y)); }
+      else       { ll = R::add_lo(ll, R::mul_lo(a, b.y)); uu = R::add_hi(uu, R::mul_hi(a, b.x)); }
+    }
+  }
+}
+
+// singleton-infinity activity [getSingLfBnds_], state machine as coded in the reference
+template <class R>
+__device__ __forceinline__ void row_sing_activity(const LinDev &P, int beg, int end, const double2 *bx,
+                                                  int64_t ld, bool need, double &slo, double &sup)
+{
+  double lb = 0.0, ub = 0.0;
+  bool lo_sing = false, up_sing = false, lo_fin = true, up_fin = true;
+  for (int t = beg; t < end; ++t) {
+    const double a = __ldg(P.val + t);
+    if (a == 0.0) continue;
+    const int j = __ldg(P.col + t);
+    if (!need) continue;
+    const double2 b = bx[(int64_t)j * ld];
+    if (a > kETol) {
+      if (b.y < kInf20 && up_fin) ub = R::add_hi(ub, R::mul_hi(a, b.y));
+      else if (up_sing) { up_sing = false; ub = INFINITY; up_fin = false; }
+      else up_sing = true;
+      if (b.x > -kInf20 && lo_fin) lb = R::add_lo(lb, R::mul_lo(a, b.x));
+      else if (lo_sing) { lo_sing = false; lb = -INFINITY; lo_fin = false; }
+      else lo_sing = true;
+    } else if (a < -kETol) {
+      if (b.y < kInf20 && lo_fin) lb = R::add_lo(lb, R::mul_lo(a, b.y));
+      else if (lo_sing) { lo_sing = false; lb = -INFINITY; lo_fin = false; }
+      else lo_sing = true;
+      if (b.x > -kInf20 && up_fin) ub = R::add_hi(ub, R::mul_hi(a, b.x));
+      else if (up_sing) { up_sing = false; ub = INFINITY; up_fin = false; }
+      else up_sing = true;
+    }
+  }
+  if (need) { slo = lb; sup = ub; }
+}
+
+// flag every row of variable j for the boxes in `mask`  [changeBFlag_]
+__device__ __forceinline__ void flag_rows_of(const LinDev &P, int j, unsigned mask, uint32_t *flags,
+                                             int lane)
+{
+  const int b = __ldg(P.csc_ptr + j), e = __ldg(P.csc_ptr + j + 1);
+  for (int q = b + lane; q < e; q += 32) atomicOr(flags + __ldg(P.csc_row + q), mask);
+}
+
+// updateLfBoundsFromLb_ (FROM_LB) / updateLfBoundsFromUb_ (!FROM_LB), in place.
+// returns the ballot of lanes that changed something.
+template <class R, bool FROM_LB>
+__device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int end, double2 *bx, int64_t ld,
+                                               bool doit, bool sing, double rbound, double act,
+                                               uint32_t *flags, TileShared &sh, int lane)
+{
+  unsigned any = 0;
+  // (row bound - activity): FromLb needs a lower estimate, FromUb an upper estimate
+  const double numer = FROM_LB ? R::sub_lo(rbound, act) : R::sub_hi(rbound, act);
+  for (int t = beg; t < end; ++t) {
+    const double a = __ldg(P.val + t);
+    if (a == 0.0) continue;
+    const int j = __ldg(P.col + t);
+    bool chg = false;
+    if (doit) {
+      double2 *pb = bx + (int64_t)j * ld;
+      const double2 b = *pb;
+      const double vl = b.x, vu = b.y;
+      // FromLb: a>0 raises lb, a<0 lowers ub.   FromUb: a>0 lowers ub, a<0 raises lb.
+      const bool raise_lb = FROM_LB ? (a > kETol) : (a < -kETol);
+      const bool lower_ub = FROM_LB ? (a < -kETol) : (a > kETol);
+      if (raise_lb && (!sing || vu >= kInf20)) {
+        const double base = (vu >= kInf20) ? 0.0 : vu;
+        double c = R::add_lo(R::div_lo(numer, a), base);
+        if (c > vl + kETol) {
+          if (c > vu - kETol) c = vu;
+          pb->x = c;
+          chg = true;
+        }
+      } else if (lower_ub && (!sing || vl <= -kInf20)) {
+        const double base = (vl <= -kInf20) ? 0.0 : vl;
+        double c = R::add_hi(R::div_hi(numer, a), base);
+        if (c < vu - kETol) {
+          if (c < vl + kETol) c = vl;
+          pb->y = c;
+          chg = true;
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, chg);
+    if (m) {
+      any |= m;
+      flag_rows_of(P, j, m, flags, lane);
+      if (chg) {
+        sh.changed[lane] = 1;
+        if (is_int_type(__ldg(P.var_type + j))) sh.nint[lane] = 1;
+      }
+    }
+  }
+  return any;
+}
+
+// one linear row for the 32 boxes of the tile  [linBndTighten_ with apply_to_prob == false]
+template <class R>
+__device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx, int64_t ld, bool mine,
+                                            uint32_t *flags, TileShared &sh, int lane,
+                                            unsigned long long &my_nnz)
+{
+  const int beg = __ldg(P.row_ptr + i), end = __ldg(P.row_ptr + i + 1);
+  const double rl = __ldg(P.row_lb + i), ru = __ldg(P.row_ub + i);
+  double ll, uu, sing_ll = -INFINITY, sing_uu = INFINITY;
+  row_activity<R>(P, beg, end, bx, ld, mine, ll, uu);
+  bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
+  if (__any_sync(0xffffffffu, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
+  if (mine) my_nnz += (unsigned long long)__ldg(P.row_nnz + i);
+  if (mine && (ll > ru + kETol || uu < rl - kETol)) {       // :994-1015
+    sh.verdict[lane] = 2;  /* MNTR_INFEAS_ROW */
+    mine = false;
+  }
+  // row lb side  (:1017-1025)
+  bool do_lb = false, s_lb = false; double act = 0.0;
+  if (mine && rl > -kInf20) {
+    if (uu < kInf20) { do_lb = true; act = uu; }
+    else if (sing_uu < kInf20) { do_lb = true; s_lb = true; act = sing_uu; }
+  }
+  unsigned chg = 0;
+  if (__any_sync(0xffffffffu, do_lb))
+    chg = row_update<R, true>(P, beg, end, bx, ld, do_lb, s_lb, rl, act, flags, sh, lane);
+  // recompute activities when FromLb changed something (:1027-1032); lanes that did not
+  // change would recompute identical values, so the decision is taken per warp
+  if (chg) {
+    const bool redo = mine && ((chg >> lane) & 1u);
+    double l2, u2;
+    row_activity<R>(P, beg, end, bx, ld, redo, l2, u2);
+    if (redo) { ll = l2; uu = u2; }
+    need_sing = redo && (ll < -kInf20 || uu > kInf20);
+    if (__any_sync(0xffffffffu, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
+  }
+  // row ub side  (:1035-1043)
+  bool do_ub = false, s_ub = false; act = 0.0;
+  if (mine && ru < kInf20) {
+    if (ll > -kInf20) { do_ub = true; act = ll; }
+    else if (sing_ll > -kInf20) { do_ub = true; s_ub = true; act = sing_ll; }
+  }
+  if (__any_sync(0xffffffffu, do_ub))
+    (void)row_update<R, false>(P, beg, end, bx, ld, do_ub, s_ub, ru, act, flags, sh, lane);
+}
+
+template <class R>
+__global__ void __launch_bounds__(kBatchThreads)
+fbbt_batch_reference_kernel(LinDev P, BatchIo io, int loop_mode, int max_rounds)
+{
+  __shared__ TileShared sh;
+  const int tile = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int box = tile * 32 + lane;
+  const bool active = box < io.n_boxes;
+  double2 *bx = io.boxes + box;             // + j*ld addresses variable j of this lane's box
+  const int64_t ld = io.ld;
+  uint32_t *flags = io.rowflag + (int64_t)tile * P.m;
+
+  // every row flagged for every box of the tile  (simplePresolve :1618-1622)
+  for (int i = threadIdx.x; i < P.m; i += kBatchThreads) __stcg(flags + i, __ldg(P.row_active + i) ? 0xffffffffu : 0u);
+  if (warp == 0) { sh.changed[lane] = 1; sh.nint[lane] = 0; sh.verdict[lane] = 0; sh.nnz[lane] = 0ull; }
+  // checkBounds_ rows part is static: a row with lb > ub + eTol makes every box infeasible
+  int bad_row = 0;
+  for (int i = threadIdx.x; i < P.m; i += kBatchThreads)
+    if (__ldg(P.row_active + i) && __ldg(P.row_lb + i) > __ldg(P.row_ub + i) + kETol) bad_row = 1;
+  bad_row = __syncthreads_or(bad_row);
+
+  unsigned long long my_nnz = 0ull;
+  int iters = 1;          // the reference's counter: starts at 1, ++ per sweep
+  int my_rounds = 0;
+  int my_verdict = 0;
+  for (;;) {
+    // ---- loop condition per box (registers are identical in every warp of the CTA) ----
+    const int changed = sh.changed[lane];
+    const int nint = sh.nint[lane];
+    if (my_verdict == 0) my_verdict = sh.verdict[lane];
+    bool run = active && my_verdict == 0 && changed;
+    if (max_rounds > 0 && my_rounds >= max_rounds) run = false;
+    if (loop_mode == 1) run = run && iters <= 10 && (iters <= 2 || nint > 0);   // :1625-1627
+    const unsigned runmask = __ballot_sync(0xffffffffu, run);
+    __syncthreads();                      // everybody has read the previous round's flags
+    if (runmask == 0) break;
+    if (warp == 0) { sh.changed[lane] = 0; sh.nint[lane] = 0; }
+    ++iters;
+    if (run) ++my_rounds;
+    __syncthreads();
+
+    // ---- rows, level by level ----
+    for (int lev = 0; lev < P.n_levels; ++lev) {
+      const int qb = __ldg(P.level_ptr + lev), qe = __ldg(P.level_ptr + lev + 1);
+      for (int q = qb + warp; q < qe; q += kBatchWarps) {
+        const int i = __ldg(P.level_row + q);
+        const uint32_t fw = __ldcg(flags + i);      // flags are updated by L2 atomics: bypass L1
+        // boxes already proven infeasible by a row stop sweeping (their result is final)
+        unsigned alive = __ballot_sync(0xffffffffu, sh.verdict[lane] == 0);
+        const uint32_t proc = fw & runmask & alive;
+        if (proc == 0) continue;
+        if (lane == 0) __stcg(flags + i, fw & ~proc);   // c_ptr->setBFlag(false), :513
+        __syncwarp();
+        process_row<R>(P, i, bx, ld, (proc >> lane) & 1u, flags, sh, lane, my_nnz);
+      }
+      __syncthreads();
+    }
+
+    // ---- integer rounding + bound check over all variables ----
+    for (int j = warp; j < P.n; j += kBatchWarps) {
+      bool chg = false;
+      const bool isint = is_int_type(__ldg(P.var_type + j));
+      if (run && sh.verdict[lane] == 0) {
+        double2 *pb = bx + (int64_t)j * ld;
+        double2 b = *pb;
+        if (isint) {
+          const double2 o = b;
+          tighten_int_bounds(b.x, b.y);
+          if (b.x != o.x || b.y != o.y) { *pb = b; chg = true; }
+        }
+        if (b.x > b.y + kETol) sh.verdict[lane] = 1;   /* MNTR_INFEAS_BOUNDS; benign race */
+      }
+      if (isint) {
+        const unsigned m = __ballot_sync(0xffffffffu, chg);
+        if (m) {
+          flag_rows_of(P, j, m, flags, lane);
+          if (chg) sh.changed[lane] = 1;
+        }
+      }
+    }
+    if (bad_row && run && warp == 0 && sh.verdict[lane] == 0) sh.verdict[lane] = 1;
+    __syncthreads();
+  }
+
+  // ---- per-box results ----
+  atomicAdd(&sh.nnz[lane], my_nnz);
+  __syncthreads();
+  if (warp == 0 && active) {
+    io.verdict[box] = sh.verdict[lane];
+    io.rounds[box] = my_rounds;
+    io.nnz[box] = (long long)sh.nnz[lane];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// layout kernels
+// ---------------------------------------------------------------------------------------
+
+// box-major lb/ub [nb][n]  ->  node-minor double2 [n][ld] at columns box0..box0+nb
+__global__ void boxes_pack_kernel(const double *__restrict__ lb, const double *__restrict__ ub, int n,
+                                  int box0, int nb, double2 *__restrict__ boxes, int64_t ld)
+{
+  __shared__ double tl[32][33], tu[32][33];
+  const int j0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {      // r = box inside the tile
+    const int b = b0 + r, j = j0 + threadIdx.x;
+    if (b < nb && j < n) {
+      tl[r][threadIdx.x] = lb[(int64_t)b * n + j];
+      tu[r][threadIdx.x] = ub[(int64_t)b * n + j];
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {      // r = variable inside the tile
+    const int j = j0 + r, b = b0 + threadIdx.x;
+    if (j < n && b < nb) boxes[(int64_t)j * ld + box0 + b] = make_double2(tl[threadIdx.x][r], tu[threadIdx.x][r]);
+  }
+}
+
+__global__ void boxes_unpack_kernel(const double2 *__restrict__ boxes, int64_t ld, int n, int box0,
+                                    int nb, double *__restrict__ lb, double *__restrict__ ub)
+{
+  __shared__ double tl[32][33], tu[32][33];
+  const int j0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {      // r = variable
+    const int j = j0 + r, b = b0 + threadIdx.x;
+    if (j < n && b < nb) {
+      const double2 v = boxes[(int64_t)j * ld + box0 + b];
+      tl[r][threadIdx.x] = v.x;
+      tu[r][threadIdx.x] = v.y;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {      // r = box
+    const int b = b0 + r, j = j0 + threadIdx.x;
+    if (b < nb && j < n) {
+      lb[(int64_t)b * n + j] = tl[threadIdx.x][r];
+      ub[(int64_t)b * n + j] = tu[threadIdx.x][r];
+    }
+  }
+}
+
+__global__ void boxes_pad_kernel(double2 *boxes, int64_t ld, int n, int n_boxes)
+{
+  const int pad = (int)(ld - n_boxes);
+  const int64_t total = (int64_t)n * pad;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = k / pad; const int p = (int)(k % pad);
+    boxes[j * ld + n_boxes + p] = boxes[j * ld];
+  }
+}
+
+__global__ void boxes_from_root_kernel(const double *__restrict__ rl, const double *__restrict__ ru, int n,
+                                       double2 *__restrict__ boxes, int64_t ld)
+{
+  const int64_t total = (int64_t)n * ld;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = k / ld;
+    boxes[k] = make_double2(rl[j], ru[j]);
+  }
+}
+
+__global__ void apply_deltas_kernel(const long long *__restrict__ dptr, const int32_t *__restrict__ dvar,
+                                    const uint8_t *__restrict__ dup, const double *__restrict__ dval,
+                                    int n_boxes, double2 *boxes, int64_t ld)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_boxes) return;
+  for (long long q = dptr[b]; q < dptr[b + 1]; ++q) {      // in order: a later delta overrides
+    double2 *p = boxes + (int64_t)dvar[q] * ld + b;
+    if (dup[q]) p->y = dval[q]; else p->x = dval[q];
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_batch_reference(const LinDev &P, const NlDev *N, const BatchIo &io, bool directed,
+                                   int loop_mode, int max_rounds, int lin_enabled, int nl_enabled,
+                                   cudaStream_t stream)
+{
+  (void)N; (void)lin_enabled; (void)nl_enabled;
+  const int tiles = (io.n_boxes + 31) / 32;
+  if (tiles <= 0) return cudaSuccess;
+  if (directed)
+    fbbt_batch_reference_kernel<RoundDirected><<<tiles, kBatchThreads, 0, stream>>>(P, io, loop_mode, max_rounds);
+  else
+    fbbt_batch_reference_kernel<RoundNearest><<<tiles, kBatchThreads, 0, stream>>>(P, io, loop_mode, max_rounds);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_boxes_pack(const double *lb_bm, const double *ub_bm, int32_t n, int32_t box0, int32_t nb,
+                              double2 *boxes, int64_t ld, cudaStream_t stream)
+{
+  if (n <= 0 || nb <= 0) return cudaSuccess;
+  dim3 grid((n + 31) / 32, (nb + 31) / 32), block(32, 8);
+  boxes_pack_kernel<<<grid, block, 0, stream>>>(lb_bm, ub_bm, n, box0, nb, boxes, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_boxes_unpack(const double2 *boxes, int64_t ld, int32_t n, int32_t box0, int32_t nb,
+                                double *lb_bm, double *ub_bm, cudaStream_t stream)
+{
+  if (n <= 0 || nb <= 0) return cudaSuccess;
+  dim3 grid((n + 31) / 32, (nb + 31) / 32), block(32, 8);
+  boxes_unpack_kernel<<<grid, block, 0, stream>>>(boxes, ld, n, box0, nb, lb_bm, ub_bm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_boxes_pad(double2 *boxes, int64_t ld, int32_t n, int32_t n_boxes, cudaStream_t stream)
+{
+  if (ld == n_boxes || n <= 0) return cudaSuccess;
+  boxes_pad_kernel<<<256, 256, 0, stream>>>(boxes, ld, n, n_boxes);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub, int32_t n, int32_t n_boxes,
+                                   double2 *boxes, int64_t ld, cudaStream_t stream)
+{
+  (void)n_boxes;
+  if (n <= 0) return cudaSuccess;
+  boxes_from_root_kernel<<<148 * 8, 256, 0, stream>>>(root_lb, root_ub, n, boxes, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_apply_deltas(const long long *delta_ptr, const int32_t *delta_var,
+                                const uint8_t *delta_is_upper, const double *delta_val, int32_t n_boxes,
+                                double2 *boxes, int64_t ld, cudaStream_t stream)
+{
+  if (n_boxes <= 0) return cudaSuccess;
+  apply_deltas_kernel<<<(n_boxes + 127) / 128, 128, 0, stream>>>(delta_ptr, delta_var, delta_is_upper,
+                                                                 delta_val, n_boxes, boxes, ld);
+  return cudaGetLastError();
+}
+
+}  // namespace mntr

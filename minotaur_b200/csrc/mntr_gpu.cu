@@ -1,0 +1,522 @@
+// mntr_gpu.cu -- C ABI of libmntr_gpu.so (include/mntr_gpu.h): context, problem upload
+// (CSR padding, CSC, wavefront levels), dispatch of the tighten kernels, result download.
+// Host C++ only orchestrates; all bound arithmetic runs in the CUDA kernels.  There is no CPU
+// fallback: every entry point fails when CUDA is unusable.
+#include "../../include/mntr_gpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "device_problem.cuh"
+#include "kernels.h"
+
+using namespace mntr;
+
+struct mntr_gpu_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  char err[512] = {0};
+
+  // ---- linear rows ----
+  bool lin_loaded = false;
+  int32_t m = 0, n = 0;
+  int64_t nnz = 0, nnz_padded = 0;
+  int lanes_per_row = 8;
+  LinDev lin{};
+  std::vector<void *> lin_allocs;
+
+  // ---- cgraph tapes ----
+  bool nl_loaded = false;
+  NlDev nl{};
+  std::vector<void *> nl_allocs;
+
+  // ---- single-box workspace ----
+  SingleWs sws{};
+  double *d_lb = nullptr, *d_ub = nullptr;   // [n] staging of one box
+  void *d_ctrl = nullptr;                    // ring[8] | status[2] | counters[2]
+  std::vector<void *> single_allocs;
+
+  // ---- batch workspace ----
+  int64_t batch_ld = 0;        // capacity in boxes (multiple of 32)
+  double2 *d_boxes = nullptr;
+  uint32_t *d_rowflag = nullptr;
+  int32_t *d_verdict = nullptr, *d_rounds = nullptr;
+  long long *d_nnzb = nullptr;
+  double *d_stage_lb = nullptr, *d_stage_ub = nullptr;
+  int64_t stage_boxes = 0;
+
+  mntr_gpu_stats stats{};
+};
+
+namespace {
+
+int fail(mntr_gpu_ctx *c, int code, const char *fmt, ...)
+{
+  if (c) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(c->err, sizeof(c->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(ctx, MNTR_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),  \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+template <class T>
+int dev_upload(mntr_gpu_ctx *ctx, std::vector<void *> &owner, const T *host, size_t count, const T **out)
+{
+  T *d = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CU(cudaMalloc((void **)&d, bytes));
+  owner.push_back(d);
+  if (count) CU(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *out = d;
+  return MNTR_OK;
+}
+
+void free_all(std::vector<void *> &v)
+{
+  for (void *p : v) cudaFree(p);
+  v.clear();
+}
+
+void free_stage(mntr_gpu_ctx *c)
+{
+  cudaFree(c->d_stage_lb); cudaFree(c->d_stage_ub);
+  c->d_stage_lb = nullptr; c->d_stage_ub = nullptr; c->stage_boxes = 0;
+}
+
+void free_batch(mntr_gpu_ctx *c)
+{
+  cudaFree(c->d_boxes); cudaFree(c->d_rowflag); cudaFree(c->d_verdict); cudaFree(c->d_rounds);
+  cudaFree(c->d_nnzb);
+  c->d_boxes = nullptr; c->d_rowflag = nullptr; c->d_verdict = nullptr; c->d_rounds = nullptr;
+  c->d_nnzb = nullptr;
+  c->batch_ld = 0;
+}
+
+int ensure_batch(mntr_gpu_ctx *ctx, int32_t n_boxes)
+{
+  const int64_t ld = mntr_gpu_box_ld(n_boxes);
+  if (ld <= ctx->batch_ld) return MNTR_OK;
+  free_batch(ctx);
+  const int64_t tiles = ld / 32;
+  CU(cudaMalloc((void **)&ctx->d_boxes, sizeof(double2) * (size_t)std::max<int64_t>(1, (int64_t)ctx->n * ld)));
+  CU(cudaMalloc((void **)&ctx->d_rowflag, sizeof(uint32_t) * (size_t)std::max<int64_t>(1, (int64_t)ctx->m * tiles)));
+  CU(cudaMalloc((void **)&ctx->d_verdict, sizeof(int32_t) * (size_t)ld));
+  CU(cudaMalloc((void **)&ctx->d_rounds, sizeof(int32_t) * (size_t)ld));
+  CU(cudaMalloc((void **)&ctx->d_nnzb, sizeof(long long) * (size_t)ld));
+  ctx->batch_ld = ld;
+  return MNTR_OK;
+}
+
+// box-major staging for host <-> engine-layout transposes: ~256 MiB per array
+int ensure_stage(mntr_gpu_ctx *ctx)
+{
+  if (ctx->stage_boxes > 0) return MNTR_OK;
+  int64_t sb = ((int64_t)256 << 20) / std::max<int64_t>(8, (int64_t)ctx->n * 8);
+  sb = std::max<int64_t>(1, std::min<int64_t>(sb, 1 << 20));
+  if (sb >= 32) sb = sb / 32 * 32;
+  CU(cudaMalloc((void **)&ctx->d_stage_lb, sizeof(double) * (size_t)std::max<int64_t>(1, sb * ctx->n)));
+  CU(cudaMalloc((void **)&ctx->d_stage_ub, sizeof(double) * (size_t)std::max<int64_t>(1, sb * ctx->n)));
+  ctx->stage_boxes = sb;
+  return MNTR_OK;
+}
+
+mntr_gpu_options resolve_opts(const mntr_gpu_options *o, int32_t n_boxes)
+{
+  mntr_gpu_options r;
+  r.rounding = MNTR_ROUND_DIRECTED;
+  r.order = (n_boxes == 1) ? MNTR_ORDER_JACOBI : MNTR_ORDER_REFERENCE;
+  r.loop = MNTR_LOOP_FIXPOINT;
+  r.max_rounds = 0;
+  if (o) {
+    r = *o;
+    if (r.order < 0) r.order = (n_boxes == 1) ? MNTR_ORDER_JACOBI : MNTR_ORDER_REFERENCE;
+  }
+  return r;
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b)
+{
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mntr_gpu_abi_version(void) { return MNTR_GPU_ABI_VERSION; }
+
+int mntr_gpu_device_count(void)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
+
+int64_t mntr_gpu_box_ld(int32_t n_boxes) { return ((int64_t)std::max(n_boxes, 1) + 31) / 32 * 32; }
+
+int mntr_gpu_create(int device, mntr_gpu_ctx **out)
+{
+  if (!out) return MNTR_E_ARG;
+  *out = nullptr;
+  mntr_gpu_ctx *ctx = new (std::nothrow) mntr_gpu_ctx();
+  if (!ctx) return MNTR_E_NOMEM;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    // no CPU fallback: the engine is unusable without a CUDA device
+    delete ctx;
+    return MNTR_E_CUDA;
+  }
+  ctx->device = device;
+  auto bail = [&](cudaError_t err) { (void)err; mntr_gpu_destroy(ctx); return MNTR_E_CUDA; };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e);
+  ctx->sm_count = prop.multiProcessorCount;
+  if (!prop.cooperativeLaunch) return bail(cudaErrorNotSupported);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+  for (auto &ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e);
+  *out = ctx;
+  return MNTR_OK;
+}
+
+void mntr_gpu_destroy(mntr_gpu_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_all(ctx->lin_allocs); free_all(ctx->nl_allocs); free_all(ctx->single_allocs);
+  free_batch(ctx); free_stage(ctx);
+  for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *mntr_gpu_last_error(const mntr_gpu_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int mntr_gpu_get_stats(const mntr_gpu_ctx *ctx, mntr_gpu_stats *out)
+{
+  if (!ctx || !out) return MNTR_E_ARG;
+  *out = ctx->stats;
+  return MNTR_OK;
+}
+
+int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t *row_ptr,
+                         const int32_t *col, const double *val, const double *row_lb,
+                         const double *row_ub, const uint8_t *var_type, const uint8_t *row_active)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (m < 0 || n < 0 || !row_ptr || (m > 0 && (!row_lb || !row_ub)) || (n > 0 && !var_type))
+    return fail(ctx, MNTR_E_ARG, "load_linear: null or negative argument");
+  if (row_ptr[0] != 0) return fail(ctx, MNTR_E_ARG, "load_linear: row_ptr[0] != 0");
+  CU(cudaSetDevice(ctx->device));
+  free_all(ctx->lin_allocs); free_all(ctx->single_allocs); free_batch(ctx); free_stage(ctx);
+  free_all(ctx->nl_allocs); ctx->nl_loaded = false;
+  ctx->lin_loaded = false;
+
+  // ---- host flattening: drop |a| <= 1e-9 (LinearFunction.cpp:89-95), pad rows to even starts ----
+  std::vector<int32_t> prow(m + 1, 0), pcol, rnnz(m, 0);
+  std::vector<double> pval;
+  std::vector<uint8_t> ract(m, 1);
+  pcol.reserve((size_t)row_ptr[m] + m); pval.reserve((size_t)row_ptr[m] + m);
+  int64_t nnz = 0;
+  for (int32_t i = 0; i < m; ++i) {
+    if (row_ptr[i + 1] < row_ptr[i]) return fail(ctx, MNTR_E_ARG, "load_linear: row_ptr not monotone at row %d", i);
+    prow[i] = (int32_t)pcol.size();
+    int32_t prev = -1;
+    for (int32_t t = row_ptr[i]; t < row_ptr[i + 1]; ++t) {
+      const int32_t j = col[t];
+      if (j < 0 || j >= n) return fail(ctx, MNTR_E_ARG, "load_linear: column %d out of range in row %d", j, i);
+      if (j <= prev) return fail(ctx, MNTR_E_ARG, "load_linear: columns not strictly ascending in row %d", i);
+      prev = j;
+      if (std::fabs(val[t]) <= kCoefDrop) continue;
+      pcol.push_back(j); pval.push_back(val[t]); ++rnnz[i]; ++nnz;
+    }
+    if (pcol.size() & 1) { pcol.push_back(pcol.back()); pval.push_back(0.0); }
+    if (row_active) ract[i] = row_active[i] ? 1 : 0;
+    if ((int64_t)pcol.size() > (int64_t)INT32_MAX - 4) return fail(ctx, MNTR_E_UNSUPPORTED, "load_linear: more than 2^31 entries");
+  }
+  prow[m] = (int32_t)pcol.size();
+
+  // ---- CSC: var -> rows (Variable::cons_) ----
+  std::vector<int32_t> cptr(n + 2, 0), crow((size_t)std::max<int64_t>(nnz, 1));
+  for (int32_t i = 0; i < m; ++i)
+    for (int32_t t = prow[i]; t < prow[i + 1]; ++t) if (pval[t] != 0.0) cptr[pcol[t] + 2]++;
+  for (int32_t j = 0; j < n; ++j) cptr[j + 2] += cptr[j + 1];
+  for (int32_t i = 0; i < m; ++i)
+    for (int32_t t = prow[i]; t < prow[i + 1]; ++t) if (pval[t] != 0.0) crow[cptr[pcol[t] + 1]++] = i;
+
+  // ---- wavefront levels of the index-ordered in-place sweep ----
+  std::vector<int32_t> last(n, -1), level(m, 0);
+  int32_t n_levels = 0;
+  for (int32_t i = 0; i < m; ++i) {
+    if (!ract[i]) { level[i] = -1; continue; }
+    int32_t lev = 0;
+    for (int32_t t = prow[i]; t < prow[i + 1]; ++t) if (pval[t] != 0.0) lev = std::max(lev, last[pcol[t]] + 1);
+    level[i] = lev;
+    for (int32_t t = prow[i]; t < prow[i + 1]; ++t) if (pval[t] != 0.0) last[pcol[t]] = lev;
+    n_levels = std::max(n_levels, lev + 1);
+  }
+  std::vector<int32_t> lptr(n_levels + 2, 0), lrow((size_t)std::max(m, 1));
+  for (int32_t i = 0; i < m; ++i) if (level[i] >= 0) lptr[level[i] + 2]++;
+  for (int32_t l = 0; l < n_levels; ++l) lptr[l + 2] += lptr[l + 1];
+  for (int32_t i = 0; i < m; ++i) if (level[i] >= 0) lrow[lptr[level[i] + 1]++] = i;
+
+  // ---- upload ----
+  LinDev &L = ctx->lin;
+  L = LinDev{};
+  L.m = m; L.n = n; L.n_levels = n_levels;
+  int rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, prow.data(), prow.size(), &L.row_ptr))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, pcol.data(), pcol.size(), &L.col))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, pval.data(), pval.size(), &L.val))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, rnnz.data(), rnnz.size(), &L.row_nnz))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, row_lb, (size_t)m, &L.row_lb))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, row_ub, (size_t)m, &L.row_ub))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, var_type, (size_t)n, &L.var_type))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, ract.data(), ract.size(), &L.row_active))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, cptr.data(), (size_t)n + 1, &L.csc_ptr))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, crow.data(), (size_t)nnz, &L.csc_row))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, lptr.data(), (size_t)n_levels + 1, &L.level_ptr))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, lrow.data(), (size_t)m, &L.level_row))) return rc;
+
+  // ---- single-box workspace ----
+  SingleWs &W = ctx->sws;
+  auto dalloc = [&](void **p, size_t bytes) -> int {
+    CU(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    ctx->single_allocs.push_back(*p);
+    return MNTR_OK;
+  };
+  if ((rc = dalloc((void **)&W.box, sizeof(double2) * (size_t)n))) return rc;
+  if ((rc = dalloc((void **)&W.nbox, sizeof(double2) * (size_t)n))) return rc;
+  if ((rc = dalloc((void **)&W.flag_a, (size_t)m))) return rc;
+  if ((rc = dalloc((void **)&W.flag_b, (size_t)m))) return rc;
+  if ((rc = dalloc((void **)&ctx->d_lb, sizeof(double) * (size_t)n))) return rc;
+  if ((rc = dalloc((void **)&ctx->d_ub, sizeof(double) * (size_t)n))) return rc;
+  if ((rc = dalloc(&ctx->d_ctrl, 64))) return rc;
+  W.ring = (int32_t *)ctx->d_ctrl;
+  W.status = W.ring + 8;
+  W.counters = (unsigned long long *)((char *)ctx->d_ctrl + 48);
+
+  // sub-warp group size from the mean row length (two entries per lane per step)
+  const double mean = m > 0 ? (double)nnz / m : 0.0;
+  int g = 2;
+  while (g < 32 && 2 * g < mean + 0.5) g *= 2;
+  ctx->lanes_per_row = g;
+  ctx->m = m; ctx->n = n; ctx->nnz = nnz; ctx->nnz_padded = (int64_t)pcol.size();
+  CU(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+  ctx->lin_loaded = true;
+  return MNTR_OK;
+}
+
+int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *, const uint8_t *, const int32_t *,
+                         const int32_t *, const double *, const int32_t *, const int32_t *, const int32_t *,
+                         const double *, const double *, const double *)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (n_cons == 0) return MNTR_OK;
+  return fail(ctx, MNTR_E_UNSUPPORTED, "load_cgraph: CGraph tapes are not implemented yet");
+}
+
+int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *, const double *, double)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (k == 0) return MNTR_OK;
+  return fail(ctx, MNTR_E_UNSUPPORTED, "set_cutoff: objective cut-off row is not implemented yet");
+}
+
+static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_gpu_options &o,
+                          int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
+{
+  const size_t bytes = sizeof(double) * (size_t)ctx->n;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_lb, lb, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_ub, ub, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_ctrl, 0, 64, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(launch_single_jacobi(ctx->lin, ctx->sws, ctx->d_lb, ctx->d_ub, ctx->lanes_per_row,
+                          o.rounding == MNTR_ROUND_DIRECTED, o.max_rounds, o.loop, ctx->sm_count, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(cudaMemcpyAsync(lb, ctx->d_lb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ub, ctx->d_ub, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  struct { int32_t ring[8]; int32_t status[2]; int32_t pad[2]; unsigned long long counters[2]; } ctrl;
+  static_assert(sizeof(ctrl) == 64, "control block layout");
+  CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (verdict) *verdict = ctrl.status[0];
+  if (rounds) *rounds = ctrl.status[1];
+  if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
+  ctx->stats.nnz_updates += (int64_t)ctrl.counters[0];
+  ctx->stats.rows_evaluated += (int64_t)ctrl.counters[1];
+  ctx->stats.n_infeasible += ctrl.status[0] != 0;
+  ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, ctrl.status[1]);
+  ctx->stats.h2d_ms += elapsed(ctx->ev[0], ctx->ev[1]);
+  ctx->stats.kernel_ms += elapsed(ctx->ev[1], ctx->ev[2]);
+  ctx->stats.d2h_ms += elapsed(ctx->ev[2], ctx->ev[3]);
+  return MNTR_OK;
+}
+
+int mntr_gpu_boxes_upload(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *lb, const double *ub, void *boxes_dev)
+{
+  if (!ctx || !ctx->lin_loaded || n_boxes <= 0 || !lb || !ub || !boxes_dev) return fail(ctx, MNTR_E_ARG, "boxes_upload: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx);
+  if (rc) return rc;
+  const int64_t ld = mntr_gpu_box_ld(n_boxes);
+  const int32_t n = ctx->n;
+  for (int64_t b0 = 0; b0 < n_boxes; b0 += ctx->stage_boxes) {
+    const int32_t nb = (int32_t)std::min<int64_t>(ctx->stage_boxes, n_boxes - b0);
+    CU(cudaMemcpyAsync(ctx->d_stage_lb, lb + b0 * n, sizeof(double) * (size_t)nb * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_stage_ub, ub + b0 * n, sizeof(double) * (size_t)nb * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_boxes_pack(ctx->d_stage_lb, ctx->d_stage_ub, n, (int32_t)b0, nb, (double2 *)boxes_dev, ld, ctx->stream));
+  }
+  CU(launch_boxes_pad((double2 *)boxes_dev, ld, n, n_boxes, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MNTR_OK;
+}
+
+int mntr_gpu_boxes_download(mntr_gpu_ctx *ctx, int32_t n_boxes, const void *boxes_dev, double *lb, double *ub)
+{
+  if (!ctx || !ctx->lin_loaded || n_boxes <= 0 || !lb || !ub || !boxes_dev) return fail(ctx, MNTR_E_ARG, "boxes_download: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx);
+  if (rc) return rc;
+  const int64_t ld = mntr_gpu_box_ld(n_boxes);
+  const int32_t n = ctx->n;
+  for (int64_t b0 = 0; b0 < n_boxes; b0 += ctx->stage_boxes) {
+    const int32_t nb = (int32_t)std::min<int64_t>(ctx->stage_boxes, n_boxes - b0);
+    CU(launch_boxes_unpack((const double2 *)boxes_dev, ld, n, (int32_t)b0, nb, ctx->d_stage_lb, ctx->d_stage_ub, ctx->stream));
+    CU(cudaMemcpyAsync(lb + b0 * n, ctx->d_stage_lb, sizeof(double) * (size_t)nb * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ub + b0 * n, ctx->d_stage_ub, sizeof(double) * (size_t)nb * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return MNTR_OK;
+}
+
+int mntr_gpu_tighten_dev(mntr_gpu_ctx *ctx, int32_t n_boxes, void *boxes_dev, const mntr_gpu_options *opts,
+                         int32_t *verdict_dev, int32_t *rounds_dev, int64_t *nnz_dev)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "tighten_dev: no problem loaded");
+  if (n_boxes <= 0 || !boxes_dev || !verdict_dev || !rounds_dev || !nnz_dev)
+    return fail(ctx, MNTR_E_ARG, "tighten_dev: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  const mntr_gpu_options o = resolve_opts(opts, n_boxes > 1 ? n_boxes : 2);
+  if (o.order != MNTR_ORDER_REFERENCE)
+    return fail(ctx, MNTR_E_UNSUPPORTED, "tighten_dev: device-resident boxes use MNTR_ORDER_REFERENCE");
+  const int64_t ld = mntr_gpu_box_ld(n_boxes);
+  const int64_t tiles = ld / 32;
+  // row flags are sized for the context's batch capacity
+  int rc = ensure_batch(ctx, n_boxes);
+  if (rc) return rc;
+  BatchIo io;
+  io.boxes = (double2 *)boxes_dev; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag;
+  io.verdict = verdict_dev; io.rounds = rounds_dev; io.nnz = (long long *)nnz_dev;
+  (void)tiles;
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
+                            o.loop, o.max_rounds, 1, ctx->nl_loaded ? 1 : 0, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stats = mntr_gpu_stats{};
+  ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  return MNTR_OK;
+}
+
+int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub, const mntr_gpu_options *opts,
+                     int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "tighten: no problem loaded");
+  if (n_boxes <= 0 || !lb || !ub) return fail(ctx, MNTR_E_ARG, "tighten: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  const mntr_gpu_options o = resolve_opts(opts, n_boxes);
+  if (o.rounding != MNTR_ROUND_DIRECTED && o.rounding != MNTR_ROUND_NEAREST) return fail(ctx, MNTR_E_ARG, "tighten: bad rounding");
+  if (o.loop != MNTR_LOOP_FIXPOINT && o.loop != MNTR_LOOP_SIMPLEPRESOLVE) return fail(ctx, MNTR_E_ARG, "tighten: bad loop mode");
+  ctx->stats = mntr_gpu_stats{};
+  const int32_t n = ctx->n;
+
+  if (o.order == MNTR_ORDER_JACOBI) {
+    if (ctx->nl_loaded) return fail(ctx, MNTR_E_UNSUPPORTED, "tighten: CGraph tapes need MNTR_ORDER_REFERENCE");
+    for (int32_t b = 0; b < n_boxes; ++b) {
+      int rc = tighten_single(ctx, lb + (int64_t)b * n, ub + (int64_t)b * n, o, verdict ? verdict + b : nullptr,
+                              rounds ? rounds + b : nullptr, nnz_updates ? nnz_updates + b : nullptr);
+      if (rc) return rc;
+    }
+    return MNTR_OK;
+  }
+  if (o.order != MNTR_ORDER_REFERENCE) return fail(ctx, MNTR_E_ARG, "tighten: bad order");
+
+  int rc = ensure_batch(ctx, n_boxes);
+  if (rc) return rc;
+  const int64_t ld = mntr_gpu_box_ld(n_boxes);
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if ((rc = mntr_gpu_boxes_upload(ctx, n_boxes, lb, ub, ctx->d_boxes))) return rc;
+  BatchIo io;
+  io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag;
+  io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb;
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
+                            o.loop, o.max_rounds, 1, ctx->nl_loaded ? 1 : 0, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if ((rc = mntr_gpu_boxes_download(ctx, n_boxes, ctx->d_boxes, lb, ub))) return rc;
+  std::vector<int32_t> hv(n_boxes), hr(n_boxes);
+  std::vector<long long> hn(n_boxes);
+  CU(cudaMemcpyAsync(hv.data(), ctx->d_verdict, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hr.data(), ctx->d_rounds, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hn.data(), ctx->d_nnzb, sizeof(long long) * (size_t)n_boxes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int32_t b = 0; b < n_boxes; ++b) {
+    if (verdict) verdict[b] = hv[b];
+    if (rounds) rounds[b] = hr[b];
+    if (nnz_updates) nnz_updates[b] = hn[b];
+    ctx->stats.nnz_updates += hn[b];
+    ctx->stats.n_infeasible += hv[b] != 0;
+    ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, hr[b]);
+  }
+  ctx->stats.h2d_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+  ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  ctx->stats.d2h_ms = elapsed(ctx->ev[2], ctx->ev[3]);
+  return MNTR_OK;
+}
+
+int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t, const double *, const double *, const int64_t *,
+                           const int32_t *, const uint8_t *, const double *, const mntr_gpu_options *, int32_t *,
+                           int32_t *, int64_t *, int32_t *, uint8_t *, double *, int64_t, int64_t *)
+{
+  if (!ctx) return MNTR_E_ARG;
+  return fail(ctx, MNTR_E_UNSUPPORTED, "tighten_nodes: not implemented yet");
+}
+
+int mntr_gpu_nccl_unique_id(void *) { return MNTR_E_UNSUPPORTED; }
+int mntr_gpu_comm_init(mntr_gpu_ctx *ctx, int32_t, int32_t, const void *)
+{
+  return fail(ctx, MNTR_E_UNSUPPORTED, "comm_init: not implemented yet");
+}
+int mntr_gpu_comm_destroy(mntr_gpu_ctx *ctx) { return ctx ? MNTR_OK : MNTR_E_ARG; }
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+"""Python host binding of the C ABI in include/mntr_gpu.h (libmntr_gpu.so), via ctypes.
+
+This is plumbing for tests, bench.py and multi-GPU drivers: it owns no algorithm.  It fails
+loudly when the CUDA library is missing or no CUDA device is usable -- there is no CPU path.
+
+Method names follow the reference handler they stand in for:
+``simple_presolve`` <-> LinearHandler::simplePresolve / NlPresHandler::simplePresolve
+(/root/reference/src/base/LinearHandler.cpp:1605-1653, NlPresHandler.cpp:1022-1059),
+``presolve_node`` <-> Handler::presolveNode (Handler.h:229-231; returns True = infeasible).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .instances import LinearRows, Tapes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmntr_gpu.so")
+
+# enums of include/mntr_gpu.h
+ROUND_DIRECTED, ROUND_NEAREST = 0, 1
+ORDER_JACOBI, ORDER_REFERENCE, ORDER_AUTO = 0, 1, -1
+LOOP_FIXPOINT, LOOP_SIMPLEPRESOLVE = 0, 1
+FEASIBLE, INFEAS_BOUNDS, INFEAS_ROW, INFEAS_NL, ERROR_NL = 0, 1, 2, 3, 4
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_bp = C.POINTER(C.c_uint8)
+
+ABI_SYMBOLS = [
+    "mntr_gpu_create", "mntr_gpu_destroy", "mntr_gpu_last_error", "mntr_gpu_abi_version",
+    "mntr_gpu_device_count", "mntr_gpu_load_linear", "mntr_gpu_load_cgraph", "mntr_gpu_set_cutoff",
+    "mntr_gpu_tighten", "mntr_gpu_tighten_nodes", "mntr_gpu_box_ld", "mntr_gpu_tighten_dev",
+    "mntr_gpu_boxes_upload", "mntr_gpu_boxes_download", "mntr_gpu_get_stats",
+    "mntr_gpu_nccl_unique_id", "mntr_gpu_comm_init", "mntr_gpu_comm_destroy",
+]
+
+
+class GpuOptions(C.Structure):
+    _fields_ = [("rounding", C.c_int32), ("order", C.c_int32), ("loop", C.c_int32), ("max_rounds", C.c_int32)]
+
+
+class GpuStats(C.Structure):
+    _fields_ = [("nnz_updates", C.c_int64), ("rows_evaluated", C.c_int64), ("n_infeasible", C.c_int64),
+                ("max_rounds", C.c_int32), ("reserved", C.c_int32), ("kernel_ms", C.c_double),
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libmntr_gpu.so and declare the ABI.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: run `python -m minotaur_b200.build` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.mntr_gpu_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.mntr_gpu_destroy.argtypes = [vp]
+    L.mntr_gpu_destroy.restype = None
+    L.mntr_gpu_last_error.argtypes = [vp]
+    L.mntr_gpu_last_error.restype = C.c_char_p
+    L.mntr_gpu_load_linear.argtypes = [vp, C.c_int32, C.c_int32, _ip, _ip, _dp, _dp, _dp, _bp, _bp]
+    L.mntr_gpu_load_cgraph.argtypes = [vp, C.c_int32, _ip, _bp, _ip, _ip, _dp, _ip, _ip, _ip, _dp, _dp, _dp]
+    L.mntr_gpu_set_cutoff.argtypes = [vp, C.c_int32, _ip, _dp, C.c_double]
+    L.mntr_gpu_tighten.argtypes = [vp, C.c_int32, _dp, _dp, C.POINTER(GpuOptions), _ip, _ip, _lp]
+    L.mntr_gpu_tighten_nodes.argtypes = [vp, C.c_int32, _dp, _dp, _lp, _ip, _bp, _dp, C.POINTER(GpuOptions),
+                                         _ip, _ip, _lp, _ip, _bp, _dp, C.c_int64, _lp]
+    L.mntr_gpu_box_ld.argtypes = [C.c_int32]
+    L.mntr_gpu_box_ld.restype = C.c_int64
+    L.mntr_gpu_tighten_dev.argtypes = [vp, C.c_int32, vp, C.POINTER(GpuOptions), vp, vp, vp]
+    L.mntr_gpu_boxes_upload.argtypes = [vp, C.c_int32, _dp, _dp, vp]
+    L.mntr_gpu_boxes_download.argtypes = [vp, C.c_int32, vp, _dp, _dp]
+    L.mntr_gpu_get_stats.argtypes = [vp, C.POINTER(GpuStats)]
+    L.mntr_gpu_nccl_unique_id.argtypes = [vp]
+    L.mntr_gpu_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    L.mntr_gpu_comm_destroy.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _d(a): return a.ctypes.data_as(_dp)
+def _i(a): return a.ctypes.data_as(_ip)
+def _l(a): return a.ctypes.data_as(_lp)
+def _b(a): return a.ctypes.data_as(_bp)
+
+
+@dataclass
+class TightenResult:
+    lb: np.ndarray
+    ub: np.ndarray
+    verdict: np.ndarray       # int32 per box
+    rounds: np.ndarray        # int32 per box
+    nnz_updates: np.ndarray   # int64 per box
+    kernel_ms: float = 0.0
+    h2d_ms: float = 0.0
+    d2h_ms: float = 0.0
+
+
+class GpuBoundEngine:
+    """One engine context = one handler instance of the reference (one per B&B thread)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.mntr_gpu_create(device, C.byref(self.h))
+        if rc != 0:
+            raise EngineError(f"mntr_gpu_create(device={device}) failed with {rc}: no usable CUDA device "
+                              "(the engine has no CPU fallback)")
+        self.n = 0
+        self.m = 0
+        self.nnz = 0
+
+    # -- lifetime --
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.mntr_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.L.mntr_gpu_last_error(self.h)
+            raise EngineError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # -- upload --
+    def load_linear(self, inst: LinearRows):
+        rp = np.ascontiguousarray(inst.row_ptr, np.int32); col = np.ascontiguousarray(inst.col, np.int32)
+        val = np.ascontiguousarray(inst.val, np.float64)
+        rl = np.ascontiguousarray(inst.row_lb, np.float64); ru = np.ascontiguousarray(inst.row_ub, np.float64)
+        vt = np.ascontiguousarray(inst.var_type, np.uint8)
+        ra = None if inst.row_active is None else np.ascontiguousarray(inst.row_active, np.uint8)
+        self._check(self.L.mntr_gpu_load_linear(self.h, inst.m, inst.n, _i(rp), _i(col), _d(val), _d(rl), _d(ru),
+                                                _b(vt), _b(ra) if ra is not None else None), "load_linear")
+        self.n, self.m, self.nnz = inst.n, inst.m, inst.nnz
+        if inst.cut_col is not None and len(inst.cut_col):
+            self.set_cutoff(inst.cut_col, inst.cut_val, inst.cut_rhs)
+
+    def load_cgraph(self, t: Tapes):
+        a = {k: np.ascontiguousarray(getattr(t, k), ty) for k, ty in (
+            ("tape_ptr", np.int32), ("op", np.uint8), ("arg0", np.int32), ("arg1", np.int32), ("cnst", np.float64),
+            ("child", np.int32), ("lin_ptr", np.int32), ("lin_col", np.int32), ("lin_val", np.float64),
+            ("c_lb", np.float64), ("c_ub", np.float64))}
+        self._check(self.L.mntr_gpu_load_cgraph(self.h, t.n_cons, _i(a["tape_ptr"]), _b(a["op"]), _i(a["arg0"]),
+                                                _i(a["arg1"]), _d(a["cnst"]), _i(a["child"]), _i(a["lin_ptr"]),
+                                                _i(a["lin_col"]), _d(a["lin_val"]), _d(a["c_lb"]), _d(a["c_ub"])),
+                    "load_cgraph")
+
+    def set_cutoff(self, col, val, rhs: float):
+        col = np.ascontiguousarray(col, np.int32); val = np.ascontiguousarray(val, np.float64)
+        self._check(self.L.mntr_gpu_set_cutoff(self.h, len(col), _i(col), _d(val), float(rhs)), "set_cutoff")
+
+    # -- the hot path --
+    def tighten(self, lb, ub, rounding=ROUND_DIRECTED, order=ORDER_AUTO, loop=LOOP_FIXPOINT, max_rounds=0,
+                inplace=False) -> TightenResult:
+        """lb/ub: [n] or box-major [n_boxes, n] float64 host arrays."""
+        lb = np.asarray(lb, np.float64); ub = np.asarray(ub, np.float64)
+        if not inplace or not lb.flags.c_contiguous or not ub.flags.c_contiguous:
+            lb = np.array(lb, np.float64, order="C", copy=True); ub = np.array(ub, np.float64, order="C", copy=True)
+        single = lb.ndim == 1
+        nb = 1 if single else lb.shape[0]
+        if lb.shape[-1] != self.n or ub.shape != lb.shape:
+            raise ValueError("box shape does not match the loaded problem")
+        o = GpuOptions(rounding, order, loop, max_rounds)
+        v = np.zeros(nb, np.int32); r = np.zeros(nb, np.int32); z = np.zeros(nb, np.int64)
+        self._check(self.L.mntr_gpu_tighten(self.h, nb, _d(lb), _d(ub), C.byref(o), _i(v), _i(r), _l(z)), "tighten")
+        st = self.stats()
+        return TightenResult(lb, ub, v, r, z, st.kernel_ms, st.h2d_ms, st.d2h_ms)
+
+    def tighten_raw(self, nb: int, lb_ptr: int, ub_ptr: int, opts: GpuOptions, v_ptr: int = 0, r_ptr: int = 0,
+                    z_ptr: int = 0):
+        """Pointer-level call for callers that own (pinned) host buffers."""
+        self._check(self.L.mntr_gpu_tighten(self.h, nb, C.cast(lb_ptr, _dp), C.cast(ub_ptr, _dp), C.byref(opts),
+                                            C.cast(v_ptr, _ip), C.cast(r_ptr, _ip), C.cast(z_ptr, _lp)), "tighten")
+
+    def simple_presolve(self, lb, ub, **kw) -> TightenResult:
+        """LinearHandler::simplePresolve semantics (loop truncation of the reference)."""
+        kw.setdefault("loop", LOOP_SIMPLEPRESOLVE)
+        return self.tighten(lb, ub, **kw)
+
+    def presolve_node(self, lb, ub, **kw) -> Tuple[bool, TightenResult]:
+        """Handler::presolveNode: returns (is_infeasible, result)."""
+        res = self.simple_presolve(lb, ub, **kw)
+        return bool(res.verdict[0] != FEASIBLE), res
+
+    # -- device-resident boxes --
+    def box_ld(self, n_boxes: int) -> int:
+        return int(self.L.mntr_gpu_box_ld(n_boxes))
+
+    def boxes_upload(self, lb, ub, boxes_dev_ptr: int):
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        self._check(self.L.mntr_gpu_boxes_upload(self.h, lb.shape[0], _d(lb), _d(ub), C.c_void_p(boxes_dev_ptr)),
+                    "boxes_upload")
+
+    def boxes_download(self, n_boxes: int, boxes_dev_ptr: int):
+        lb = np.zeros((n_boxes, self.n)); ub = np.zeros((n_boxes, self.n))
+        self._check(self.L.mntr_gpu_boxes_download(self.h, n_boxes, C.c_void_p(boxes_dev_ptr), _d(lb), _d(ub)),
+                    "boxes_download")
+        return lb, ub
+
+    def tighten_dev(self, n_boxes: int, boxes_dev_ptr: int, verdict_ptr: int, rounds_ptr: int, nnz_ptr: int,
+                    rounding=ROUND_DIRECTED, loop=LOOP_FIXPOINT, max_rounds=0):
+        o = GpuOptions(rounding, ORDER_REFERENCE, loop, max_rounds)
+        self._check(self.L.mntr_gpu_tighten_dev(self.h, n_boxes, C.c_void_p(boxes_dev_ptr), C.byref(o),
+                                                C.c_void_p(verdict_ptr), C.c_void_p(rounds_ptr),
+                                                C.c_void_p(nnz_ptr)), "tighten_dev")
+        return self.stats()
+
+    def stats(self) -> GpuStats:
+        s = GpuStats()
+        self._check(self.L.mntr_gpu_get_stats(self.h, C.byref(s)), "get_stats")
+        return s

@@ -1,0 +1,402 @@
+"""Flat problem descriptions and the synthetic instance generators of SURVEY.md section 8(d).
+
+The flat layout is what crosses the C ABI (include/mntr_gpu.h): a CSR matrix of the
+linear rows with columns in ascending variable id (the iteration order of the
+reference's ``LinearFunction`` terms, /root/reference/src/base/Types.h:496), row and
+variable bounds, Minotaur ``VariableType`` codes (Types.h:83-89), and one expression
+tape per CGraph constraint in the evaluation order ``CGraph::finalize`` produces
+(/root/reference/src/base/CGraph.cpp:557-644).
+
+Pure numpy: nothing here touches the GPU or the oracle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# Minotaur::VariableType (Types.h:83-89)
+BINARY, INTEGER, IMPLBIN, IMPLINT, CONTINUOUS = 0, 1, 2, 3, 4
+
+# Minotaur::OpCode (OpCode.h:17-53)
+(OpAbs, OpAcos, OpAcosh, OpAsin, OpAsinh, OpAtan, OpAtanh, OpCeil, OpCos, OpCosh, OpCPow, OpDiv,
+ OpExp, OpFloor, OpInt, OpIntDiv, OpLog, OpLog10, OpMinus, OpMult, OpNone, OpNum, OpPlus, OpPow,
+ OpPowK, OpRound, OpSin, OpSinh, OpSqr, OpSqrt, OpSumList, OpTan, OpTanh, OpUMinus, OpVar) = range(35)
+
+INF = float("inf")
+
+
+@dataclass
+class LinearRows:
+    """CSR linear rows  row_lb <= A x <= row_ub  plus variable types and the root box."""
+    m: int
+    n: int
+    row_ptr: np.ndarray   # int32 [m+1]
+    col: np.ndarray       # int32 [nnz], ascending inside a row
+    val: np.ndarray       # float64 [nnz]
+    row_lb: np.ndarray    # float64 [m]
+    row_ub: np.ndarray    # float64 [m]
+    var_type: np.ndarray  # uint8 [n]
+    lb: np.ndarray        # float64 [n] root box
+    ub: np.ndarray        # float64 [n]
+    row_active: Optional[np.ndarray] = None   # uint8 [m] or None
+    cut_col: Optional[np.ndarray] = None      # objective cut-off row  c.x <= cut_rhs
+    cut_val: Optional[np.ndarray] = None
+    cut_rhs: float = INF
+    name: str = ""
+    xstar: Optional[np.ndarray] = None        # planted feasible point of the generators
+
+    @property
+    def nnz(self) -> int:
+        return int(self.row_ptr[-1])
+
+    def validate(self) -> None:
+        assert self.row_ptr.dtype == np.int32 and self.col.dtype == np.int32
+        assert self.val.dtype == np.float64 and self.var_type.dtype == np.uint8
+        assert self.row_ptr.shape == (self.m + 1,) and self.row_ptr[0] == 0
+        assert self.col.shape == (self.nnz,) and self.val.shape == (self.nnz,)
+        assert self.lb.shape == (self.n,) and self.ub.shape == (self.n,)
+        if self.nnz:
+            assert self.col.min() >= 0 and self.col.max() < self.n
+        for i in range(min(self.m, 1000)):
+            c = self.col[self.row_ptr[i]:self.row_ptr[i + 1]]
+            assert np.all(np.diff(c) > 0), "columns must be strictly ascending inside a row"
+
+
+@dataclass
+class Tapes:
+    """Expression tapes of the CGraph constraints  c_lb <= f_c(x) + lin_c . x <= c_ub."""
+    n_cons: int
+    tape_ptr: np.ndarray   # int32 [n_cons+1]
+    op: np.ndarray         # uint8 [n_nodes]
+    arg0: np.ndarray       # int32 [n_nodes]
+    arg1: np.ndarray       # int32 [n_nodes]
+    cnst: np.ndarray       # float64 [n_nodes]
+    child: np.ndarray      # int32 [n_child]  SumList child lists
+    lin_ptr: np.ndarray    # int32 [n_cons+1]
+    lin_col: np.ndarray    # int32
+    lin_val: np.ndarray    # float64
+    c_lb: np.ndarray       # float64 [n_cons]
+    c_ub: np.ndarray       # float64 [n_cons]
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.tape_ptr[-1])
+
+
+# --------------------------------------------------------------------------------------
+# expression -> tape (mirrors the node order of CGraph::finalize)
+# --------------------------------------------------------------------------------------
+
+class Expr:
+    """Tiny expression DAG used to author CGraph constraints for tests and generators."""
+    __slots__ = ("op", "kids", "value", "var")
+
+    def __init__(self, op, kids=(), value=0.0, var=-1):
+        self.op, self.kids, self.value, self.var = op, tuple(kids), float(value), int(var)
+
+    @staticmethod
+    def v(j):
+        return Expr(OpVar, var=j)
+
+    @staticmethod
+    def c(x):
+        return Expr(OpNum, value=x)
+
+    @staticmethod
+    def i(x):
+        return Expr(OpInt, value=x)
+
+    def __add__(self, o): return Expr(OpPlus, (self, _e(o)))
+    def __sub__(self, o): return Expr(OpMinus, (self, _e(o)))
+    def __mul__(self, o): return Expr(OpMult, (self, _e(o)))
+    def __truediv__(self, o): return Expr(OpDiv, (self, _e(o)))
+    def __neg__(self): return Expr(OpUMinus, (self,))
+
+    def sqr(self): return Expr(OpSqr, (self,))
+    def sqrt(self): return Expr(OpSqrt, (self,))
+    def exp(self): return Expr(OpExp, (self,))
+    def log(self): return Expr(OpLog, (self,))
+    def abs(self): return Expr(OpAbs, (self,))
+    def powk(self, k): return Expr(OpPowK, (self, Expr.c(k)))
+
+    @staticmethod
+    def sumlist(kids): return Expr(OpSumList, tuple(_e(k) for k in kids))
+
+    @staticmethod
+    def unary(op, a): return Expr(op, (_e(a),))
+
+
+def _e(x):
+    return x if isinstance(x, Expr) else Expr.c(x)
+
+
+def flatten_expr(root: Expr) -> Tuple[list, list, list, list, list]:
+    """Return (op, arg0, arg1, cnst, child) of one constraint in reference order:
+    variable nodes by ascending variable id (``vq_``), then constants, then operator
+    nodes in the iterative left-to-right post-order of ``CGraph::finalize`` (``dq_``).
+    One node per variable (``CGraph::newNode(VariablePtr)`` de-duplicates,
+    CGraph.cpp:1247-1262); shared sub-expressions (same Expr object) are emitted once."""
+    var_nodes, consts, ops = {}, [], []
+    seen = {}
+
+    def visit(e):
+        stack = [(e, 0)]
+        while stack:
+            node, k = stack.pop()
+            if id(node) in seen:
+                continue
+            if node.op == OpVar:
+                var_nodes.setdefault(node.var, node)
+                seen[id(node)] = True
+                continue
+            if node.op in (OpNum, OpInt):
+                consts.append(node)
+                seen[id(node)] = True
+                continue
+            if k < len(node.kids):
+                stack.append((node, k + 1))
+                stack.append((node.kids[k], 0))
+            else:
+                seen[id(node)] = True
+                ops.append(node)
+
+    visit(root)
+    order, index = [], {}
+    for j in sorted(var_nodes):
+        index[("v", j)] = len(order)
+        order.append(var_nodes[j])
+    for cn in consts:
+        index[id(cn)] = len(order)
+        order.append(cn)
+    for on in ops:
+        index[id(on)] = len(order)
+        order.append(on)
+
+    def idx(e):
+        return index[("v", e.var)] if e.op == OpVar else index[id(e)]
+
+    op, a0, a1, cn, child = [], [], [], [], []
+    for e in order:
+        op.append(e.op)
+        cn.append(e.value if e.op in (OpNum, OpInt) else 0.0)
+        if e.op == OpVar:
+            a0.append(e.var); a1.append(-1)
+        elif e.op in (OpNum, OpInt):
+            a0.append(-1); a1.append(-1)
+        elif e.op == OpSumList:
+            a0.append(len(child))
+            child.extend(idx(k) for k in e.kids)
+            a1.append(len(child))
+        else:
+            a0.append(idx(e.kids[0]))
+            a1.append(idx(e.kids[1]) if len(e.kids) > 1 else -1)
+    if root.op in (OpVar, OpNum, OpInt):
+        raise ValueError("a CGraph constraint needs at least one operator node")
+    return op, a0, a1, cn, child
+
+
+def build_tapes(cons: Sequence[Tuple[Expr, Sequence[Tuple[int, float]], float, float]]) -> Tapes:
+    """cons: list of (expr, [(col, coef) ...] linear part, c_lb, c_ub)."""
+    tp, lp = [0], [0]
+    op, a0, a1, cn, child, lc, lv, clb, cub = [], [], [], [], [], [], [], [], []
+    for expr, lin, lo, hi in cons:
+        o, x0, x1, c, ch = flatten_expr(expr)
+        base_child = len(child)
+        for k, oo in enumerate(o):
+            if oo == OpSumList:
+                x0[k] += base_child
+                x1[k] += base_child
+        op += o; a0 += x0; a1 += x1; cn += c; child += ch
+        tp.append(len(op))
+        lin = sorted(lin)
+        lc += [j for j, _ in lin]; lv += [a for _, a in lin]
+        lp.append(len(lc))
+        clb.append(lo); cub.append(hi)
+    return Tapes(
+        n_cons=len(cons), tape_ptr=np.asarray(tp, np.int32), op=np.asarray(op, np.uint8),
+        arg0=np.asarray(a0, np.int32), arg1=np.asarray(a1, np.int32), cnst=np.asarray(cn, np.float64),
+        child=np.asarray(child if child else [0], np.int32), lin_ptr=np.asarray(lp, np.int32),
+        lin_col=np.asarray(lc if lc else [0], np.int32), lin_val=np.asarray(lv if lv else [0.0], np.float64),
+        c_lb=np.asarray(clb, np.float64), c_ub=np.asarray(cub, np.float64))
+
+
+# --------------------------------------------------------------------------------------
+# generators
+# --------------------------------------------------------------------------------------
+
+def _distinct_sorted_columns(rng: np.random.Generator, m: int, n: int, k: int) -> np.ndarray:
+    """m rows of k distinct columns out of n, each row ascending."""
+    cols = np.sort(rng.integers(0, n, size=(m, k), dtype=np.int64), axis=1)
+    for _ in range(100):
+        bad = np.nonzero((np.diff(cols, axis=1) == 0).any(axis=1))[0]
+        if bad.size == 0:
+            break
+        cols[bad] = np.sort(rng.integers(0, n, size=(bad.size, k), dtype=np.int64), axis=1)
+    else:
+        raise RuntimeError("could not draw distinct columns")
+    return cols.astype(np.int32)
+
+
+def make_sparse_milp(m: int, n: int, nnz_per_row: int = 10, seed: int = 12345, real_data: bool = False,
+                     inf_frac: Tuple[float, float, float] = (0.0, 0.0, 0.0),
+                     int_frac: float = 0.5, name: str = "sparse_milp") -> LinearRows:
+    """Config C2 / C4 shape: per row ``nnz_per_row`` distinct uniform columns,
+    integer coefficients in +-{1..9} (30 % negative), ``int_frac`` Integer variables in
+    [0, ub], ub in {1..10}, the rest Continuous; a planted feasible point x* and rows
+    ``a.x <= a.x* + s`` (s in {0..3}) with 20-40 % equality rows ``a.x = a.x*``.
+    ``inf_frac`` = fractions of continuous variables given (ub=+inf, lb=-inf, both)."""
+    rng = np.random.default_rng(seed)
+    k = min(nnz_per_row, n)
+    col = _distinct_sorted_columns(rng, m, n, k)
+    mag = rng.integers(1, 10, size=(m, k)).astype(np.float64)
+    if real_data:
+        mag = mag + rng.random((m, k))
+    sign = np.where(rng.random((m, k)) < 0.3, -1.0, 1.0)
+    val = mag * sign
+    is_int = rng.random(n) < int_frac
+    var_type = np.where(is_int, INTEGER, CONTINUOUS).astype(np.uint8)
+    lb = np.zeros(n)
+    ub = rng.integers(1, 11, size=n).astype(np.float64)
+    if real_data:
+        ub = np.where(is_int, ub, ub + rng.random(n))
+    xstar = np.where(is_int, np.floor(rng.random(n) * (ub + 1)).clip(0, ub), rng.random(n) * ub)
+    if not real_data:
+        xstar = np.where(is_int, xstar, np.round(xstar * 4) / 4)  # quarter grid: exact sums
+    act = (val * xstar[col]).sum(axis=1)
+    slack = rng.integers(0, 4, size=m).astype(np.float64)
+    eq_frac = 0.2 + 0.2 * rng.random()
+    is_eq = rng.random(m) < eq_frac
+    row_ub = np.where(is_eq, act, act + slack)
+    row_lb = np.where(is_eq, act, -INF)
+    f_ub, f_lb, f_both = inf_frac
+    if f_ub + f_lb + f_both > 0:
+        u = rng.random(n)
+        cont = ~is_int
+        ub = np.where(cont & (u < f_ub), INF, ub)
+        lb = np.where(cont & (u >= f_ub) & (u < f_ub + f_lb), -INF, lb)
+        both = cont & (u >= f_ub + f_lb) & (u < f_ub + f_lb + f_both)
+        ub = np.where(both, INF, ub)
+        lb = np.where(both, -INF, lb)
+    row_ptr = (np.arange(m + 1, dtype=np.int64) * k).astype(np.int32)
+    return LinearRows(m=m, n=n, row_ptr=row_ptr, col=col.reshape(-1), val=val.reshape(-1),
+                      row_lb=row_lb, row_ub=row_ub, var_type=var_type, lb=lb, ub=ub, name=name,
+                      xstar=xstar)
+
+
+def make_knapsack_setcover(m: int = 50_000, n: int = 50_000, nnz_per_row: int = 10, seed: int = 2024,
+                           name: str = "knapsack_setcover") -> LinearRows:
+    """Config C3 shape: half knapsack rows ``sum w_j x_j <= W`` (w in {1..20}, binaries and
+    small integers), half set-cover rows ``sum x_j >= 1`` over binaries; planted point."""
+    rng = np.random.default_rng(seed)
+    k = min(nnz_per_row, n)
+    col = _distinct_sorted_columns(rng, m, n, k)
+    is_bin = rng.random(n) < 0.7
+    var_type = np.where(is_bin, BINARY, INTEGER).astype(np.uint8)
+    lb = np.zeros(n)
+    ub = np.where(is_bin, 1.0, rng.integers(2, 6, size=n).astype(np.float64))
+    xstar = np.floor(rng.random(n) * (ub + 1)).clip(0, ub)
+    mk = m // 2
+    val = np.ones((m, k))
+    val[:mk] = rng.integers(1, 21, size=(mk, k)).astype(np.float64)
+    act = (val * xstar[col]).sum(axis=1)
+    row_lb = np.full(m, -INF)
+    row_ub = np.full(m, INF)
+    row_ub[:mk] = act[:mk] + rng.integers(0, 6, size=mk)
+    # set-cover rows: make sure the planted point covers each row
+    cover = slice(mk, m)
+    need = np.nonzero(act[cover] < 1.0)[0] + mk
+    xstar[col[need, 0]] = 1.0
+    row_lb[cover] = 1.0
+    # re-plant knapsack capacities after the fix-up so x* stays feasible
+    act = (val * xstar[col]).sum(axis=1)
+    row_ub[:mk] = np.maximum(row_ub[:mk], act[:mk])
+    row_ptr = (np.arange(m + 1, dtype=np.int64) * k).astype(np.int32)
+    return LinearRows(m=m, n=n, row_ptr=row_ptr, col=col.reshape(-1), val=val.reshape(-1),
+                      row_lb=row_lb, row_ub=row_ub, var_type=var_type, lb=lb, ub=ub, name=name,
+                      xstar=xstar)
+
+
+def branch_boxes(inst_lb: np.ndarray, inst_ub: np.ndarray, var_type: np.ndarray, n_boxes: int,
+                 seed: int = 2024, max_depth: int = 20, continuous_too: bool = False
+                 ) -> Tuple[np.ndarray, np.ndarray]:
+    """``n_boxes`` node boxes: the root box with d in {1..max_depth} random branching
+    perturbations, ``ub := floor(v)`` or ``lb := ceil(v)`` on random integer variables, as
+    ``IntVarHandler::getBranches`` creates them (/root/reference/src/base/IntVarHandler.cpp:133-190).
+    Returns box-major arrays [n_boxes, n]."""
+    rng = np.random.default_rng(seed)
+    n = inst_lb.shape[0]
+    lbs = np.repeat(inst_lb[None, :], n_boxes, axis=0)
+    ubs = np.repeat(inst_ub[None, :], n_boxes, axis=0)
+    is_int = (var_type == INTEGER) | (var_type == BINARY)
+    cand = np.nonzero((is_int | continuous_too) & np.isfinite(inst_lb) & np.isfinite(inst_ub)
+                      & (inst_ub > inst_lb))[0]
+    if cand.size == 0:
+        return lbs, ubs
+    for b in range(n_boxes):
+        d = int(rng.integers(1, max_depth + 1))
+        for j in rng.choice(cand, size=min(d, cand.size), replace=False):
+            lo, hi = lbs[b, j], ubs[b, j]
+            if hi - lo < 0.5:
+                continue
+            v = lo + (hi - lo) * rng.random()
+            if is_int[j]:
+                if v == np.floor(v):
+                    v += 0.5
+                if rng.random() < 0.5:
+                    ubs[b, j] = np.floor(v)
+                else:
+                    lbs[b, j] = np.ceil(v)
+            else:
+                if rng.random() < 0.5:
+                    ubs[b, j] = v
+                else:
+                    lbs[b, j] = v
+    return lbs, ubs
+
+
+def make_minlp(n: int, n_cons: int, m_lin: int, seed: int = 99, name: str = "minlp"
+               ) -> Tuple[LinearRows, Tapes]:
+    """Config C5 shape: variables in [l,u] within [-10,10]; 50 % constraints
+    ``c_lb <= x_i*x_j + a*x_k <= c_ub`` (tape Var,Var,Mult + linear part), 50 %
+    ``x_i^2 + x_j^2 <= r`` as SumList(Sqr,Sqr); plus ``m_lin`` linear rows; planted point."""
+    rng = np.random.default_rng(seed)
+    lo = -rng.integers(0, 11, size=n).astype(np.float64)
+    hi = rng.integers(1, 11, size=n).astype(np.float64)
+    is_int = rng.random(n) < 0.3
+    var_type = np.where(is_int, INTEGER, CONTINUOUS).astype(np.uint8)
+    xstar = lo + (hi - lo) * rng.random(n)
+    xstar = np.where(is_int, np.round(xstar), xstar).clip(lo, hi)
+    cons = []
+    for c in range(n_cons):
+        i, j, k = rng.choice(n, size=3, replace=False)
+        if c % 2 == 0:
+            a = float(rng.integers(1, 6)) * (1 if rng.random() < 0.5 else -1)
+            v = xstar[i] * xstar[j] + a * xstar[k]
+            w = float(rng.integers(0, 4))
+            if rng.random() < 0.3:
+                clb, cub = v - 0.5 * w, v + 0.5 * w
+            else:
+                clb, cub = -INF, v + w
+            cons.append((Expr.v(int(i)) * Expr.v(int(j)), [(int(k), a)], clb, cub))
+        else:
+            r = xstar[i] ** 2 + xstar[j] ** 2 + float(rng.integers(0, 10))
+            cons.append((Expr.sumlist([Expr.v(int(i)).sqr(), Expr.v(int(j)).sqr()]), [], -INF, r))
+    tapes = build_tapes(cons)
+    k = min(6, n)
+    if m_lin > 0:
+        col = _distinct_sorted_columns(rng, m_lin, n, k)
+        val = rng.integers(1, 10, size=(m_lin, k)).astype(np.float64) * np.where(rng.random((m_lin, k)) < 0.3, -1.0, 1.0)
+        act = (val * xstar[col]).sum(axis=1)
+        row_ub = act + rng.integers(0, 4, size=m_lin)
+        row_lb = np.where(rng.random(m_lin) < 0.3, act, -INF)
+        row_ub = np.where(np.isfinite(row_lb), act, row_ub)
+    else:
+        col = np.zeros((0, k), np.int32); val = np.zeros((0, k)); row_lb = np.zeros(0); row_ub = np.zeros(0)
+    row_ptr = (np.arange(m_lin + 1, dtype=np.int64) * k).astype(np.int32)
+    lin = LinearRows(m=m_lin, n=n, row_ptr=row_ptr, col=col.reshape(-1).astype(np.int32),
+                     val=val.reshape(-1).astype(np.float64), row_lb=row_lb.astype(np.float64),
+                     row_ub=row_ub.astype(np.float64), var_type=var_type, lb=lo, ub=hi, name=name,
+                     xstar=xstar)
+    return lin, tapes

@@ -1,0 +1,323 @@
+"""ctypes bindings of the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+* ``Oracle``    -> oracle/liboracle.so            (fbbt_oracle.c, our plain-C restatement)
+* ``Reference`` -> oracle/_ref/libminotaur_ref.so (the reference's own objects + ref_harness.cpp)
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl reference``
+legs may import this module; nothing under ``minotaur_b200/`` does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libminotaur_ref.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+
+
+def _d(a): return a.ctypes.data_as(_dp)
+def _i(a): return a.ctypes.data_as(_ip)
+def _b(a): return a.ctypes.data_as(_bp)
+
+
+class OrcLin(C.Structure):
+    _fields_ = [("m", C.c_int32), ("n", C.c_int32), ("row_ptr", _ip), ("col", _ip), ("val", _dp),
+                ("row_lb", _dp), ("row_ub", _dp), ("var_type", _bp), ("row_active", _bp),
+                ("cut_k", C.c_int32), ("cut_col", _ip), ("cut_val", _dp), ("cut_rhs", C.c_double)]
+
+
+class OrcNl(C.Structure):
+    _fields_ = [("n_cons", C.c_int32), ("tape_ptr", _ip), ("op", _bp), ("arg0", _ip), ("arg1", _ip),
+                ("cnst", _dp), ("child", _ip), ("lin_ptr", _ip), ("lin_col", _ip), ("lin_val", _dp),
+                ("c_lb", _dp), ("c_ub", _dp)]
+
+
+class OrcResult(C.Structure):
+    _fields_ = [("verdict", C.c_int32), ("rounds", C.c_int32), ("nnz_updates", C.c_int64),
+                ("n_mods", C.c_int64)]
+
+
+def build_oracle(force: bool = False) -> str:
+    """Compile oracle/liboracle.so (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(ORACLE_SO) or \
+            os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "fbbt_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    return ORACLE_SO
+
+
+def have_reference() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def _lin_struct(inst, keep):
+    s = OrcLin()
+    s.m, s.n = inst.m, inst.n
+    arrs = dict(row_ptr=np.ascontiguousarray(inst.row_ptr, np.int32), col=np.ascontiguousarray(inst.col, np.int32),
+                val=np.ascontiguousarray(inst.val, np.float64), row_lb=np.ascontiguousarray(inst.row_lb, np.float64),
+                row_ub=np.ascontiguousarray(inst.row_ub, np.float64),
+                var_type=np.ascontiguousarray(inst.var_type, np.uint8))
+    keep.update(arrs)
+    s.row_ptr, s.col, s.val = _i(arrs["row_ptr"]), _i(arrs["col"]), _d(arrs["val"])
+    s.row_lb, s.row_ub, s.var_type = _d(arrs["row_lb"]), _d(arrs["row_ub"]), _b(arrs["var_type"])
+    if inst.row_active is not None:
+        keep["row_active"] = np.ascontiguousarray(inst.row_active, np.uint8)
+        s.row_active = _b(keep["row_active"])
+    if inst.cut_col is not None and len(inst.cut_col):
+        keep["cut_col"] = np.ascontiguousarray(inst.cut_col, np.int32)
+        keep["cut_val"] = np.ascontiguousarray(inst.cut_val, np.float64)
+        s.cut_k, s.cut_col, s.cut_val, s.cut_rhs = len(keep["cut_col"]), _i(keep["cut_col"]), _d(keep["cut_val"]), inst.cut_rhs
+    return s
+
+
+def _nl_struct(t, keep):
+    s = OrcNl()
+    s.n_cons = t.n_cons
+    for name, typ in (("tape_ptr", np.int32), ("op", np.uint8), ("arg0", np.int32), ("arg1", np.int32),
+                      ("cnst", np.float64), ("child", np.int32), ("lin_ptr", np.int32), ("lin_col", np.int32),
+                      ("lin_val", np.float64), ("c_lb", np.float64), ("c_ub", np.float64)):
+        a = np.ascontiguousarray(getattr(t, name), typ)
+        keep["nl_" + name] = a
+        setattr(s, name, {np.int32: _i, np.uint8: _b, np.float64: _d}[typ](a))
+    return s
+
+
+class Oracle:
+    """The plain-C restatement (oracle/fbbt_oracle.c)."""
+
+    def __init__(self):
+        build_oracle()
+        self.lib = C.CDLL(ORACLE_SO)
+        L = self.lib
+        L.orc_lin_simple_presolve.argtypes = [C.POINTER(OrcLin), _dp, _dp, C.POINTER(OrcResult)]
+        L.orc_lin_fixpoint_inplace.argtypes = [C.POINTER(OrcLin), _dp, _dp, C.POINTER(OrcResult)]
+        L.orc_lin_fixpoint_jacobi.argtypes = [C.POINTER(OrcLin), _dp, _dp, C.c_int32, C.POINTER(OrcResult)]
+        L.orc_lin_row_activity.argtypes = [C.POINTER(OrcLin), C.c_int32, _dp, _dp, _dp]
+        L.orc_nl_compute_bounds.argtypes = [C.POINTER(OrcNl), C.c_int32, _dp, _dp, _dp, _dp]
+        L.orc_nl_compute_bounds.restype = C.c_int32
+        L.orc_nl_var_bound_mods.argtypes = [C.POINTER(OrcNl), C.c_int32, C.c_double, C.c_double, _dp, _dp, _ip]
+        L.orc_nl_var_bound_mods.restype = C.c_int32
+        L.orc_nl_simple_presolve.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(OrcResult)]
+        L.orc_nl_chk_red.argtypes = [C.POINTER(OrcNl), _dp, _dp]
+        L.orc_nl_chk_red.restype = C.c_int32
+        L.orc_nl_sweep.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(C.c_int64)]
+        L.orc_nl_sweep.restype = C.c_int32
+        L.orc_node_presolve.argtypes = [C.POINTER(OrcLin), C.POINTER(OrcNl), _dp, _dp, C.POINTER(OrcResult)]
+        for f in ("orc_bounds_on_product",):
+            getattr(L, f).argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp]
+        L.orc_bounds_on_div.argtypes = [C.c_double] * 4 + [_dp, _dp]
+        L.orc_bounds_on_recip.argtypes = [C.c_double] * 2 + [_dp, _dp]
+        L.orc_bounds_on_square.argtypes = [C.c_double] * 2 + [_dp, _dp]
+
+    # ---- linear ----
+    def _run_lin(self, fn, inst, lb, ub, *extra):
+        keep = {}
+        s = _lin_struct(inst, keep)
+        lb = np.array(lb, np.float64, copy=True); ub = np.array(ub, np.float64, copy=True)
+        r = OrcResult()
+        fn(C.byref(s), _d(lb), _d(ub), *extra, C.byref(r))
+        return lb, ub, dict(verdict=r.verdict, rounds=r.rounds, nnz_updates=r.nnz_updates, n_mods=r.n_mods)
+
+    def lin_simple_presolve(self, inst, lb=None, ub=None):
+        return self._run_lin(self.lib.orc_lin_simple_presolve, inst, inst.lb if lb is None else lb,
+                             inst.ub if ub is None else ub)
+
+    def lin_fixpoint_inplace(self, inst, lb=None, ub=None):
+        return self._run_lin(self.lib.orc_lin_fixpoint_inplace, inst, inst.lb if lb is None else lb,
+                             inst.ub if ub is None else ub)
+
+    def lin_fixpoint_jacobi(self, inst, lb=None, ub=None, max_rounds=0):
+        return self._run_lin(self.lib.orc_lin_fixpoint_jacobi, inst, inst.lb if lb is None else lb,
+                             inst.ub if ub is None else ub, C.c_int32(max_rounds))
+
+    def lin_row_activity(self, inst, row, lb, ub):
+        keep = {}
+        s = _lin_struct(inst, keep)
+        out = np.zeros(4)
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        self.lib.orc_lin_row_activity(C.byref(s), row, _d(lb), _d(ub), _d(out))
+        return out
+
+    # ---- nonlinear ----
+    def nl_compute_bounds(self, tapes, c, lb, ub):
+        keep = {}; s = _nl_struct(tapes, keep)
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        o = np.zeros(2)
+        err = self.lib.orc_nl_compute_bounds(C.byref(s), c, _d(lb), _d(ub), _d(o[0:1]), _d(o[1:2]))
+        return o[0], o[1], err
+
+    def nl_var_bound_mods(self, tapes, c, lb_in, ub_in, lb, ub):
+        keep = {}; s = _nl_struct(tapes, keep)
+        lb = np.array(lb, np.float64, copy=True); ub = np.array(ub, np.float64, copy=True)
+        nm = np.zeros(1, np.int32)
+        st = self.lib.orc_nl_var_bound_mods(C.byref(s), c, lb_in, ub_in, _d(lb), _d(ub), _i(nm))
+        return lb, ub, st, int(nm[0])
+
+    def nl_simple_presolve(self, tapes, lb, ub):
+        keep = {}; s = _nl_struct(tapes, keep)
+        lb = np.array(lb, np.float64, copy=True); ub = np.array(ub, np.float64, copy=True)
+        r = OrcResult()
+        self.lib.orc_nl_simple_presolve(C.byref(s), _d(lb), _d(ub), C.byref(r))
+        return lb, ub, dict(verdict=r.verdict, rounds=r.rounds, n_mods=r.n_mods)
+
+    def node_presolve(self, inst, tapes, lb, ub):
+        keep = {}
+        s = _lin_struct(inst, keep) if inst is not None and inst.m > 0 else None
+        g = _nl_struct(tapes, keep) if tapes is not None else None
+        lb = np.array(lb, np.float64, copy=True); ub = np.array(ub, np.float64, copy=True)
+        r = OrcResult()
+        self.lib.orc_node_presolve(C.byref(s) if s is not None else None, C.byref(g) if g is not None else None,
+                                   _d(lb), _d(ub), C.byref(r))
+        return lb, ub, dict(verdict=r.verdict, rounds=r.rounds, nnz_updates=r.nnz_updates, n_mods=r.n_mods)
+
+    def bounds_on_product(self, z, l0, u0, l1, u1):
+        o = np.zeros(2); self.lib.orc_bounds_on_product(int(z), l0, u0, l1, u1, _d(o[0:1]), _d(o[1:2])); return tuple(o)
+
+    def bounds_on_div(self, l0, u0, l1, u1):
+        o = np.zeros(2); self.lib.orc_bounds_on_div(l0, u0, l1, u1, _d(o[0:1]), _d(o[1:2])); return tuple(o)
+
+
+class Reference:
+    """A Minotaur::Problem built inside oracle/_ref/libminotaur_ref.so, driven by the
+    reference's own LinearHandler / NlPresHandler / CGraph code."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(REF_SO)
+            L.ref_create.restype = C.c_void_p
+            L.ref_create.argtypes = [C.c_int32, C.c_int32, _ip, _ip, _dp, _dp, _dp, _bp, _dp, _dp]
+            L.ref_add_nl.argtypes = [C.c_void_p, C.c_int32, _bp, _ip, _ip, _dp, _ip, C.c_int32, _ip, _dp,
+                                     C.c_double, C.c_double]
+            L.ref_add_nl.restype = C.c_int32
+            L.ref_finish.argtypes = [C.c_void_p]
+            L.ref_set_box.argtypes = [C.c_void_p, _dp, _dp]
+            L.ref_get_box.argtypes = [C.c_void_p, _dp, _dp]
+            L.ref_lin_fixpoint.argtypes = [C.c_void_p, _ip, C.POINTER(C.c_int64)]
+            L.ref_lin_fixpoint_counted.argtypes = [C.c_void_p, C.c_int32, _ip, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+            L.ref_lin_simple_presolve.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+            L.ref_nl_simple_presolve.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+            L.ref_node_presolve.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+            L.ref_nl_compute_bounds.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
+            L.ref_nl_var_bound_mods.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, _ip]
+            L.ref_nl_dq_ops.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _ip]
+            L.ref_row_activity.argtypes = [C.c_void_p, C.c_int32, _dp]
+            L.ref_time_boxes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+            L.ref_time_boxes.restype = C.c_double
+            L.ref_destroy.argtypes = [C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, inst, tapes=None):
+        L = self.lib()
+        self.n = inst.n
+        rp = np.ascontiguousarray(inst.row_ptr, np.int32); col = np.ascontiguousarray(inst.col, np.int32)
+        val = np.ascontiguousarray(inst.val, np.float64)
+        rl = np.ascontiguousarray(inst.row_lb, np.float64); ru = np.ascontiguousarray(inst.row_ub, np.float64)
+        vt = np.ascontiguousarray(inst.var_type, np.uint8)
+        lb = np.ascontiguousarray(inst.lb, np.float64); ub = np.ascontiguousarray(inst.ub, np.float64)
+        if inst.row_active is not None and not np.all(inst.row_active):
+            raise ValueError("Reference harness: deleted rows are not supported; drop them from the CSR")
+        self.h = L.ref_create(inst.m, inst.n, _i(rp), _i(col), _d(val), _d(rl), _d(ru), _b(vt), _d(lb), _d(ub))
+        if tapes is not None:
+            for c in range(tapes.n_cons):
+                b, e = int(tapes.tape_ptr[c]), int(tapes.tape_ptr[c + 1])
+                op = np.ascontiguousarray(tapes.op[b:e]); a0 = np.ascontiguousarray(tapes.arg0[b:e])
+                a1 = np.ascontiguousarray(tapes.arg1[b:e]); cn = np.ascontiguousarray(tapes.cnst[b:e])
+                lbeg, lend = int(tapes.lin_ptr[c]), int(tapes.lin_ptr[c + 1])
+                lc = np.ascontiguousarray(tapes.lin_col[lbeg:lend] if lend > lbeg else np.zeros(1, np.int32))
+                lv = np.ascontiguousarray(tapes.lin_val[lbeg:lend] if lend > lbeg else np.zeros(1))
+                L.ref_add_nl(self.h, e - b, _b(op), _i(a0), _i(a1), _d(cn), _i(tapes.child), lend - lbeg,
+                             _i(lc), _d(lv), float(tapes.c_lb[c]), float(tapes.c_ub[c]))
+        L.ref_finish(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib().ref_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_box(self, lb, ub):
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        self.lib().ref_set_box(self.h, _d(lb), _d(ub))
+
+    def get_box(self) -> Tuple[np.ndarray, np.ndarray]:
+        lb = np.zeros(self.n); ub = np.zeros(self.n)
+        self.lib().ref_get_box(self.h, _d(lb), _d(ub))
+        return lb, ub
+
+    def lin_fixpoint(self, lb, ub, counted=False, max_rounds=0):
+        self.set_box(lb, ub)
+        rounds = C.c_int32(0); nm = C.c_int64(0); nnz = C.c_int64(0)
+        if counted:
+            v = self.lib().ref_lin_fixpoint_counted(self.h, max_rounds, C.byref(rounds), C.byref(nm), C.byref(nnz))
+        else:
+            v = self.lib().ref_lin_fixpoint(self.h, C.byref(rounds), C.byref(nm))
+        l, u = self.get_box()
+        return l, u, dict(verdict=int(v), rounds=rounds.value, n_mods=nm.value, nnz_updates=nnz.value)
+
+    def lin_simple_presolve(self, lb, ub):
+        self.set_box(lb, ub)
+        nm = C.c_int64(0)
+        v = self.lib().ref_lin_simple_presolve(self.h, C.byref(nm))
+        l, u = self.get_box()
+        return l, u, dict(verdict=int(v), n_mods=nm.value)
+
+    def nl_simple_presolve(self, lb, ub):
+        self.set_box(lb, ub)
+        nm = C.c_int64(0)
+        v = self.lib().ref_nl_simple_presolve(self.h, C.byref(nm))
+        l, u = self.get_box()
+        return l, u, dict(verdict=int(v), n_mods=nm.value)
+
+    def node_presolve(self, lb, ub):
+        self.set_box(lb, ub)
+        nm = C.c_int64(0)
+        v = self.lib().ref_node_presolve(self.h, C.byref(nm))
+        l, u = self.get_box()
+        return l, u, dict(verdict=int(v), n_mods=nm.value)
+
+    def nl_compute_bounds(self, c, lb, ub):
+        self.set_box(lb, ub)
+        o = np.zeros(2)
+        err = self.lib().ref_nl_compute_bounds(self.h, c, _d(o[0:1]), _d(o[1:2]))
+        return o[0], o[1], err
+
+    def nl_var_bound_mods(self, c, lb_in, ub_in, lb, ub):
+        self.set_box(lb, ub)
+        nm = np.zeros(1, np.int32)
+        st = self.lib().ref_nl_var_bound_mods(self.h, c, lb_in, ub_in, _i(nm))
+        l, u = self.get_box()
+        return l, u, int(st), int(nm[0])
+
+    def nl_dq_ops(self, c):
+        ops = np.zeros(4096, np.int32)
+        k = self.lib().ref_nl_dq_ops(self.h, c, 4096, _i(ops))
+        return ops[:k].copy()
+
+    def row_activity(self, row, lb, ub):
+        self.set_box(lb, ub)
+        out = np.zeros(4)
+        self.lib().ref_row_activity(self.h, row, _d(out))
+        return out
+
+    def time_boxes(self, mode, lbs, ubs):
+        lbs = np.ascontiguousarray(lbs, np.float64); ubs = np.ascontiguousarray(ubs, np.float64)
+        nb = lbs.shape[0] if lbs.ndim == 2 else 1
+        nnz = C.c_int64(0); ninf = C.c_int64(0)
+        secs = self.lib().ref_time_boxes(self.h, mode, nb, _d(lbs), _d(ubs), C.byref(nnz), C.byref(ninf))
+        return secs, nnz.value, ninf.value

@@ -1,0 +1,322 @@
+/*
+ * ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A small C-ABI driver around the REFERENCE'S OWN objects (compiled by oracle/Makefile
+ * from /root/reference/src/base/*.cpp, never copied).  It builds a Minotaur::Problem
+ * from the same flat CSR / tape description the CUDA path takes and runs the
+ * reference's LinearHandler / NlPresHandler / CGraph code on it.  Output goes only to
+ * oracle/_ref/libminotaur_ref.so.
+ *
+ * Used (a) to pin oracle/fbbt_oracle.c, (b) to generate tests/golden/ fixtures,
+ * (c) as the "reference" CPU baseline of bench.py.
+ */
+#include "MinotaurConfig.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "CGraph.h"
+#include "CNode.h"
+#include "Constraint.h"
+#include "Environment.h"
+#include "Function.h"
+#include "LinearFunction.h"
+#include "LinearHandler.h"
+#include "Logger.h"
+#include "NlPresHandler.h"
+#include "NonlinearFunction.h"
+#include "Objective.h"
+#include "Option.h"
+#include "Problem.h"
+#include "Types.h"
+#include "VarBoundMod.h"
+#include "Variable.h"
+
+using namespace Minotaur;
+
+namespace {
+
+/* exposes the protected per-round routines of LinearHandler (LinearHandler.h:154-273) */
+class LinProbe : public LinearHandler {
+public:
+  LinProbe(EnvPtr env, ProblemPtr p) : LinearHandler(env, p) {}
+
+  void flagAll(ProblemPtr p)
+  {
+    for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it) (*it)->setBFlag(true);
+  }
+
+  /* SURVEY.md section 8c parity driver: the reference's sweeps, status honoured, to fixpoint */
+  int fixpoint(ProblemPtr p, int *rounds, int64_t *nmods)
+  {
+    ModQ mods; bool ch = true; UInt ni = 0; int inf = 0; *rounds = 0;
+    flagAll(p);
+    while (ch && !inf) {
+      ch = false; ++*rounds;
+      if (varBndsFromCons_(p, false, &ch, &mods, &ni) == SolvedInfeasible) { inf = 1; break; }
+      tightenInts_(p, false, &ch, &mods);
+      if (checkBounds_(p) == SolvedInfeasible) inf = 1;
+    }
+    *nmods = (int64_t)mods.size();
+    for (ModQ::iterator it = mods.begin(); it != mods.end(); ++it) delete *it;
+    return inf;
+  }
+
+  /* same driver with the row loop of varBndsFromCons_ (LinearHandler.cpp:506-539,
+   * apply_to_prob == false) unrolled here so the visited nnz can be counted */
+  int fixpointCounted(ProblemPtr p, int *rounds, int64_t *nmods, int64_t *nnz, int max_rounds)
+  {
+    ModQ mods; bool ch = true; UInt ni = 0; int inf = 0; *rounds = 0; *nnz = 0;
+    flagAll(p);
+    while (ch && !inf && (max_rounds <= 0 || *rounds < max_rounds)) {
+      ch = false; ++*rounds;
+      for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it) {
+        ConstraintPtr c = *it;
+        if (c->getBFlag() && c->getFunctionType() == Linear && c->getQuadraticFunction() == 0 &&
+            c->getNonlinearFunction() == 0 && DeletedCons != c->getState()) {
+          bool t = false;
+          c->setBFlag(false);
+          *nnz += c->getLinearFunction()->getNumTerms();
+          if (linBndTighten_(p, false, c, &t, &mods, &ni) == SolvedInfeasible) { inf = 1; break; }
+          if (t) ch = true;
+        }
+      }
+      if (inf) break;
+      tightenInts_(p, false, &ch, &mods);
+      if (checkBounds_(p) == SolvedInfeasible) inf = 1;
+    }
+    *nmods = (int64_t)mods.size();
+    for (ModQ::iterator it = mods.begin(); it != mods.end(); ++it) delete *it;
+    return inf;
+  }
+
+  void rowActivity(ConstraintPtr c, double out[4])
+  {
+    LinearFunctionPtr lf = c->getLinearFunction();
+    getLfBnds_(lf, &out[0], &out[1]);
+    out[2] = -INFINITY; out[3] = INFINITY;
+    getSingLfBnds_(lf, &out[2], &out[3]);
+  }
+};
+
+struct RefProblem {
+  EnvPtr env = 0;
+  ProblemPtr p = 0;
+  LinProbe *lh = 0;
+  NlPresHandler *nh = 0;
+  std::vector<VariablePtr> vars;
+  std::vector<ConstraintPtr> lin_rows;
+  std::vector<ConstraintPtr> nl_rows;
+  std::vector<CGraph *> graphs;
+};
+
+void freeMods(ModVector &mods)
+{
+  for (ModVector::iterator it = mods.begin(); it != mods.end(); ++it) delete *it;
+  mods.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+void *ref_create(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col,
+                 const double *val, const double *row_lb, const double *row_ub,
+                 const uint8_t *var_type, const double *lb, const double *ub)
+{
+  RefProblem *h = new RefProblem();
+  int err = 0;
+  h->env = (EnvPtr) new Environment();
+  h->env->startTimer(err);
+  h->env->setLogLevel(LogNone);
+  h->p = (ProblemPtr) new Problem(h->env);
+  h->vars.reserve(n);
+  for (int32_t j = 0; j < n; ++j)
+    h->vars.push_back(h->p->newVariable(lb[j], ub[j], (VariableType)var_type[j]));
+  h->lin_rows.reserve(m);
+  for (int32_t i = 0; i < m; ++i) {
+    LinearFunctionPtr lf = (LinearFunctionPtr) new LinearFunction();
+    for (int32_t t = row_ptr[i]; t < row_ptr[i + 1]; ++t) lf->addTerm(h->vars[col[t]], val[t]);
+    FunctionPtr f = (FunctionPtr) new Function(lf);
+    h->lin_rows.push_back(h->p->newConstraint(f, row_lb[i], row_ub[i]));
+  }
+  return h;
+}
+
+/* one nonlinear constraint  c_lb <= tape(x) + lin.x <= c_ub ; tape in the flat layout
+ * of fbbt_oracle.h (local indices).  Returns its index among nonlinear constraints. */
+int32_t ref_add_nl(void *hv, int32_t n_nodes, const uint8_t *op, const int32_t *arg0,
+                   const int32_t *arg1, const double *cnst, const int32_t *child, int32_t lin_k,
+                   const int32_t *lin_col, const double *lin_val, double c_lb, double c_ub)
+{
+  RefProblem *h = (RefProblem *)hv;
+  CGraph *cg = new CGraph();
+  std::vector<CNode *> nodes(n_nodes, (CNode *)0);
+  for (int32_t i = 0; i < n_nodes; ++i) {
+    OpCode o = (OpCode)op[i];
+    if (o == OpVar) nodes[i] = cg->newNode(h->vars[arg0[i]]);
+    else if (o == OpNum) nodes[i] = cg->newNode(cnst[i]);
+    else if (o == OpInt) nodes[i] = cg->newNode((int)cnst[i]);
+    else if (o == OpSumList) {
+      std::vector<CNode *> ch;
+      for (int32_t c = arg0[i]; c < arg1[i]; ++c) ch.push_back(nodes[child[c]]);
+      nodes[i] = cg->newNode(OpSumList, &ch[0], (UInt)ch.size());
+    } else {
+      nodes[i] = cg->newNode(o, nodes[arg0[i]], arg1[i] >= 0 ? nodes[arg1[i]] : (CNode *)0);
+    }
+  }
+  cg->setOut(nodes[n_nodes - 1]);
+  cg->finalize();
+  LinearFunctionPtr lf = 0;
+  if (lin_k > 0) {
+    lf = (LinearFunctionPtr) new LinearFunction();
+    for (int32_t t = 0; t < lin_k; ++t) lf->addTerm(h->vars[lin_col[t]], lin_val[t]);
+  }
+  FunctionPtr f = (FunctionPtr) new Function(lf, (NonlinearFunctionPtr)cg);
+  h->nl_rows.push_back(h->p->newConstraint(f, c_lb, c_ub));
+  h->graphs.push_back(cg);
+  return (int32_t)h->nl_rows.size() - 1;
+}
+
+void ref_finish(void *hv)
+{
+  RefProblem *h = (RefProblem *)hv;
+  h->p->calculateSize();
+  h->lh = new LinProbe(h->env, h->p);
+  h->nh = new NlPresHandler(h->env, h->p);
+}
+
+void ref_set_box(void *hv, const double *lb, const double *ub)
+{
+  RefProblem *h = (RefProblem *)hv;
+  for (size_t j = 0; j < h->vars.size(); ++j) h->p->changeBound(h->vars[j], lb[j], ub[j]);
+}
+
+void ref_get_box(void *hv, double *lb, double *ub)
+{
+  RefProblem *h = (RefProblem *)hv;
+  for (size_t j = 0; j < h->vars.size(); ++j) { lb[j] = h->vars[j]->getLb(); ub[j] = h->vars[j]->getUb(); }
+}
+
+int32_t ref_lin_fixpoint(void *hv, int32_t *rounds, int64_t *nmods)
+{
+  RefProblem *h = (RefProblem *)hv;
+  return h->lh->fixpoint(h->p, rounds, nmods);
+}
+
+int32_t ref_lin_fixpoint_counted(void *hv, int32_t max_rounds, int32_t *rounds, int64_t *nmods,
+                                 int64_t *nnz)
+{
+  RefProblem *h = (RefProblem *)hv;
+  return h->lh->fixpointCounted(h->p, rounds, nmods, nnz, max_rounds);
+}
+
+/* raw LinearHandler::simplePresolve (LinearHandler.cpp:1605-1653): what B&B pays per node */
+int32_t ref_lin_simple_presolve(void *hv, int64_t *nmods)
+{
+  RefProblem *h = (RefProblem *)hv;
+  ModVector mods; SolveStatus st = Started;
+  h->lh->simplePresolve(h->p, (SolutionPoolPtr)0, mods, st);
+  *nmods = (int64_t)mods.size();
+  freeMods(mods);
+  return st == SolvedInfeasible ? 1 : 0;
+}
+
+/* raw NlPresHandler::simplePresolve (NlPresHandler.cpp:1022-1059) */
+int32_t ref_nl_simple_presolve(void *hv, int64_t *nmods)
+{
+  RefProblem *h = (RefProblem *)hv;
+  ModVector mods; SolveStatus st = Started;
+  h->nh->simplePresolve(h->p, (SolutionPoolPtr)0, mods, st);
+  *nmods = (int64_t)mods.size();
+  freeMods(mods);
+  return st == SolvedInfeasible ? 1 : (st == SolveError ? 2 : 0);
+}
+
+/* LinearHandler then NlPresHandler, as PCBProcessor::presolveNode_ (PCBProcessor.cpp:134-175) */
+int32_t ref_node_presolve(void *hv, int64_t *nmods)
+{
+  int64_t a = 0, b = 0;
+  int32_t inf = ref_lin_simple_presolve(hv, &a);
+  if (!inf) inf = (ref_nl_simple_presolve(hv, &b) == 1);
+  *nmods = a + b;
+  return inf;
+}
+
+/* CGraph::computeBounds of nonlinear constraint c */
+int32_t ref_nl_compute_bounds(void *hv, int32_t c, double *lb, double *ub)
+{
+  RefProblem *h = (RefProblem *)hv; int err = 0;
+  h->graphs[c]->computeBounds(lb, ub, &err);
+  return err;
+}
+
+/* CGraph::varBoundMods(lb_in, ub_in) of constraint c, mods applied to the problem the way
+ * NlPresHandler::varBndsFromCons_ applies them (NlPresHandler.cpp:1787-1803) */
+int32_t ref_nl_var_bound_mods(void *hv, int32_t c, double lb_in, double ub_in, int32_t *n_mods)
+{
+  RefProblem *h = (RefProblem *)hv;
+  VarBoundModVector mods; SolveStatus st = Started;
+  h->graphs[c]->varBoundMods(lb_in, ub_in, mods, &st);
+  *n_mods = (int32_t)mods.size();
+  for (VarBoundModVector::iterator it = mods.begin(); it != mods.end(); ++it) {
+    if (st != SolvedInfeasible && st != SolveError) (*it)->applyToProblem(h->p);
+    delete *it;
+  }
+  return st == SolvedInfeasible ? 1 : (st == SolveError ? 2 : 0);
+}
+
+/* opcodes of the dependent nodes in the order CGraph::finalize produced (dq_) */
+int32_t ref_nl_dq_ops(void *hv, int32_t c, int32_t cap, int32_t *ops)
+{
+  RefProblem *h = (RefProblem *)hv;
+  CNodeQ dq = h->graphs[c]->dNodes();
+  int32_t k = 0;
+  for (CNodeQ::iterator it = dq.begin(); it != dq.end(); ++it, ++k) if (k < cap) ops[k] = (int32_t)(*it)->getOp();
+  return k;
+}
+
+void ref_row_activity(void *hv, int32_t row, double out[4])
+{
+  RefProblem *h = (RefProblem *)hv;
+  h->lh->rowActivity(h->lin_rows[row], out);
+}
+
+/* CPU baseline legs: repeat a call on a list of boxes, steady_clock around the
+ * tighten calls only (box reset excluded).  mode 0 = status-honouring fixpoint
+ * (counted), 1 = raw LinearHandler::simplePresolve, 2 = raw node presolve (lin + nl).
+ * Returns seconds; accumulates nnz / verdict counts. */
+double ref_time_boxes(void *hv, int32_t mode, int32_t n_boxes, const double *lbs, const double *ubs,
+                      int64_t *nnz_total, int64_t *n_infeasible)
+{
+  RefProblem *h = (RefProblem *)hv;
+  size_t n = h->vars.size();
+  double secs = 0; *nnz_total = 0; *n_infeasible = 0;
+  for (int32_t b = 0; b < n_boxes; ++b) {
+    ref_set_box(hv, lbs + (size_t)b * n, ubs + (size_t)b * n);
+    int32_t rounds = 0, inf = 0; int64_t nmods = 0, nnz = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    if (mode == 0) inf = h->lh->fixpointCounted(h->p, &rounds, &nmods, &nnz, 0);
+    else if (mode == 1) inf = ref_lin_simple_presolve(hv, &nmods);
+    else inf = ref_node_presolve(hv, &nmods);
+    auto t1 = std::chrono::steady_clock::now();
+    secs += std::chrono::duration<double>(t1 - t0).count();
+    *nnz_total += nnz; *n_infeasible += inf;
+  }
+  return secs;
+}
+
+void ref_destroy(void *hv)
+{
+  RefProblem *h = (RefProblem *)hv;
+  delete h->lh; delete h->nh;
+  delete h->p;
+  delete h->env;
+  delete h;
+}
+
+}  // extern "C"
