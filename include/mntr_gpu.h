@@ -94,6 +94,7 @@ typedef struct {
   int64_t nnz_updates;   /* sum over evaluated (row, box) pairs of the row's term count */
   int64_t rows_evaluated;
   int64_t n_infeasible;  /* boxes with verdict != MNTR_FEASIBLE */
+  int64_t n_changes;     /* (variable, round) pairs whose bounds moved (single-box path) */
   int32_t max_rounds;    /* largest number of rounds any box took */
   int32_t reserved;
   double  kernel_ms;     /* device time of the tighten kernels (CUDA events) */
@@ -184,6 +185,15 @@ int mntr_gpu_boxes_upload(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *lb,
                           const double *ub, void *boxes_dev);
 int mntr_gpu_boxes_download(mntr_gpu_ctx *ctx, int32_t n_boxes, const void *boxes_dev,
                             double *lb, double *ub);
+
+/* Single box already resident in HBM (lb_dev/ub_dev: device arrays of n doubles, tightened in
+ * place) with the Jacobi fixpoint kernel; verdict/rounds/nnz_updates are host outputs.  This is
+ * the whole hot path of a single-box call minus the host<->device copies. */
+int mntr_gpu_tighten_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev,
+                                const mntr_gpu_options *opts, int32_t *verdict, int32_t *rounds,
+                                int64_t *nnz_updates);
+/* the context's cudaStream_t, for callers that time or order work against it */
+void *mntr_gpu_stream(mntr_gpu_ctx *ctx);
 
 /* statistics of the last tighten call */
 int mntr_gpu_get_stats(const mntr_gpu_ctx *ctx, mntr_gpu_stats *out);

@@ -266,7 +266,9 @@ fbbt_batch_reference_kernel(LinDev P, BatchIo io, int loop_mode, int max_rounds)
     for (int j = warp; j < P.n; j += kBatchWarps) {
       bool chg = false;
       const bool isint = is_int_type(__ldg(P.var_type + j));
-      if (run && sh.verdict[lane] == 0) {
+      // a box found bound-infeasible by another warp still finishes its integer sweep (the
+      // reference completes tightenInts_ before checkBounds_); row-infeasible boxes are frozen
+      if (run && sh.verdict[lane] != 2) {
         double2 *pb = bx + (int64_t)j * ld;
         double2 b = *pb;
         if (isint) {

@@ -227,6 +227,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
 
     // ------------------------------ vars phase ------------------------------
     int changed = 0, int_moved = 0, bad = 0;
+    int n_changed = 0;
     for (int j = tid; j < P.n; j += nthreads) {
       const double2 o = W.box[j];
       double2 v = W.nbox[j];
@@ -238,11 +239,13 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
       if (v.x > v.y + kETol) bad = 1;
       if (v.x != o.x || v.y != o.y) {
         changed = 1;
+        ++n_changed;
         W.box[j] = v;
         W.nbox[j] = v;
         for (int q = P.csc_ptr[j]; q < P.csc_ptr[j + 1]; ++q) fnext[P.csc_row[q]] = 1;
       }
     }
+    if (n_changed) atomicAdd(&W.status[2], n_changed);
     changed = __syncthreads_or(changed);
     int_moved = __syncthreads_or(int_moved);
     bad = __syncthreads_or(bad);

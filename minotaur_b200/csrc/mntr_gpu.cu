@@ -347,37 +347,80 @@ int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *, const dou
   return fail(ctx, MNTR_E_UNSUPPORTED, "set_cutoff: objective cut-off row is not implemented yet");
 }
 
+struct SingleCtrl { int32_t ring[8]; int32_t status[2]; int32_t pad[2]; unsigned long long counters[2]; };
+static_assert(sizeof(SingleCtrl) == 64, "control block layout");
+
+// K1 on a device-resident box; leaves verdict/rounds/counters in the control block
+static int run_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, const mntr_gpu_options &o)
+{
+  CU(cudaMemsetAsync(ctx->d_ctrl, 0, 64, ctx->stream));
+  CU(launch_single_jacobi(ctx->lin, ctx->sws, lb_dev, ub_dev, ctx->lanes_per_row,
+                          o.rounding == MNTR_ROUND_DIRECTED, o.max_rounds, o.loop, ctx->sm_count, ctx->stream));
+  return MNTR_OK;
+}
+
+static void account_single(mntr_gpu_ctx *ctx, const SingleCtrl &ctrl)
+{
+  ctx->stats.nnz_updates += (int64_t)ctrl.counters[0];
+  ctx->stats.rows_evaluated += (int64_t)ctrl.counters[1];
+  ctx->stats.n_changes += (int64_t)ctrl.pad[0];
+  ctx->stats.n_infeasible += ctrl.status[0] != 0;
+  ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, ctrl.status[1]);
+}
+
 static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_gpu_options &o,
                           int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
 {
   const size_t bytes = sizeof(double) * (size_t)ctx->n;
+  int rc;
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_lb, lb, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_ub, ub, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_ctrl, 0, 64, ctx->stream));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-  CU(launch_single_jacobi(ctx->lin, ctx->sws, ctx->d_lb, ctx->d_ub, ctx->lanes_per_row,
-                          o.rounding == MNTR_ROUND_DIRECTED, o.max_rounds, o.loop, ctx->sm_count, ctx->stream));
+  if ((rc = run_single_dev(ctx, ctx->d_lb, ctx->d_ub, o))) return rc;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   CU(cudaMemcpyAsync(lb, ctx->d_lb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(ub, ctx->d_ub, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  struct { int32_t ring[8]; int32_t status[2]; int32_t pad[2]; unsigned long long counters[2]; } ctrl;
-  static_assert(sizeof(ctrl) == 64, "control block layout");
+  SingleCtrl ctrl;
   CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (verdict) *verdict = ctrl.status[0];
   if (rounds) *rounds = ctrl.status[1];
   if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
-  ctx->stats.nnz_updates += (int64_t)ctrl.counters[0];
-  ctx->stats.rows_evaluated += (int64_t)ctrl.counters[1];
-  ctx->stats.n_infeasible += ctrl.status[0] != 0;
-  ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, ctrl.status[1]);
+  account_single(ctx, ctrl);
   ctx->stats.h2d_ms += elapsed(ctx->ev[0], ctx->ev[1]);
   ctx->stats.kernel_ms += elapsed(ctx->ev[1], ctx->ev[2]);
   ctx->stats.d2h_ms += elapsed(ctx->ev[2], ctx->ev[3]);
   return MNTR_OK;
 }
+
+int mntr_gpu_tighten_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, const mntr_gpu_options *opts,
+                                int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "tighten_single_dev: no problem loaded");
+  if (!lb_dev || !ub_dev) return fail(ctx, MNTR_E_ARG, "tighten_single_dev: null box");
+  CU(cudaSetDevice(ctx->device));
+  mntr_gpu_options o = resolve_opts(opts, 1);
+  o.order = MNTR_ORDER_JACOBI;
+  int rc;
+  ctx->stats = mntr_gpu_stats{};
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if ((rc = run_single_dev(ctx, lb_dev, ub_dev, o))) return rc;
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  SingleCtrl ctrl;
+  CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (verdict) *verdict = ctrl.status[0];
+  if (rounds) *rounds = ctrl.status[1];
+  if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
+  account_single(ctx, ctrl);
+  ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  return MNTR_OK;
+}
+
+void *mntr_gpu_stream(mntr_gpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int mntr_gpu_boxes_upload(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *lb, const double *ub, void *boxes_dev)
 {

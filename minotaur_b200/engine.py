@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "mntr_gpu_device_count", "mntr_gpu_load_linear", "mntr_gpu_load_cgraph", "mntr_gpu_set_cutoff",
     "mntr_gpu_tighten", "mntr_gpu_tighten_nodes", "mntr_gpu_box_ld", "mntr_gpu_tighten_dev",
     "mntr_gpu_boxes_upload", "mntr_gpu_boxes_download", "mntr_gpu_get_stats",
+    "mntr_gpu_tighten_single_dev", "mntr_gpu_stream",
     "mntr_gpu_nccl_unique_id", "mntr_gpu_comm_init", "mntr_gpu_comm_destroy",
 ]
 
@@ -48,7 +49,7 @@ class GpuOptions(C.Structure):
 
 class GpuStats(C.Structure):
     _fields_ = [("nnz_updates", C.c_int64), ("rows_evaluated", C.c_int64), ("n_infeasible", C.c_int64),
-                ("max_rounds", C.c_int32), ("reserved", C.c_int32), ("kernel_ms", C.c_double),
+                ("n_changes", C.c_int64), ("max_rounds", C.c_int32), ("reserved", C.c_int32), ("kernel_ms", C.c_double),
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
 
 
@@ -86,6 +87,9 @@ def load_library() -> C.CDLL:
     L.mntr_gpu_boxes_upload.argtypes = [vp, C.c_int32, _dp, _dp, vp]
     L.mntr_gpu_boxes_download.argtypes = [vp, C.c_int32, vp, _dp, _dp]
     L.mntr_gpu_get_stats.argtypes = [vp, C.POINTER(GpuStats)]
+    L.mntr_gpu_tighten_single_dev.argtypes = [vp, vp, vp, C.POINTER(GpuOptions), _ip, _ip, _lp]
+    L.mntr_gpu_stream.argtypes = [vp]
+    L.mntr_gpu_stream.restype = vp
     L.mntr_gpu_nccl_unique_id.argtypes = [vp]
     L.mntr_gpu_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.mntr_gpu_comm_destroy.argtypes = [vp]
@@ -230,6 +234,19 @@ class GpuBoundEngine:
                                                 C.c_void_p(verdict_ptr), C.c_void_p(rounds_ptr),
                                                 C.c_void_p(nnz_ptr)), "tighten_dev")
         return self.stats()
+
+    def tighten_single_dev(self, lb_dev_ptr: int, ub_dev_ptr: int, rounding=ROUND_DIRECTED, loop=LOOP_FIXPOINT,
+                           max_rounds=0):
+        """Single box resident in HBM (device pointers), Jacobi fixpoint; returns (verdict, rounds, nnz)."""
+        o = GpuOptions(rounding, ORDER_JACOBI, loop, max_rounds)
+        v = C.c_int32(0); r = C.c_int32(0); z = C.c_int64(0)
+        self._check(self.L.mntr_gpu_tighten_single_dev(self.h, C.c_void_p(lb_dev_ptr), C.c_void_p(ub_dev_ptr),
+                                                       C.byref(o), C.byref(v), C.byref(r), C.byref(z)),
+                    "tighten_single_dev")
+        return v.value, r.value, z.value
+
+    def stream_handle(self) -> int:
+        return int(self.L.mntr_gpu_stream(self.h) or 0)
 
     def stats(self) -> GpuStats:
         s = GpuStats()

@@ -228,6 +228,14 @@ def build_tapes(cons: Sequence[Tuple[Expr, Sequence[Tuple[int, float]], float, f
 
 def _distinct_sorted_columns(rng: np.random.Generator, m: int, n: int, k: int) -> np.ndarray:
     """m rows of k distinct columns out of n, each row ascending."""
+    if k * k > n:   # rejection sampling would rarely succeed: draw by random permutation keys
+        out = np.empty((m, k), dtype=np.int32)
+        step = max(1, (1 << 24) // max(n, 1))
+        for r0 in range(0, m, step):
+            r1 = min(m, r0 + step)
+            keys = rng.random((r1 - r0, n))
+            out[r0:r1] = np.sort(np.argpartition(keys, k - 1, axis=1)[:, :k], axis=1)
+        return out
     cols = np.sort(rng.integers(0, n, size=(m, k), dtype=np.int64), axis=1)
     for _ in range(100):
         bad = np.nonzero((np.diff(cols, axis=1) == 0).any(axis=1))[0]

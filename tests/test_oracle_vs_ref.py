@@ -1,0 +1,68 @@
+"""Live pin: oracle/fbbt_oracle.c against the reference's own objects (oracle/_ref), on seeded random
+instances.  Skipped where the reference library was not built (it needs /root/reference)."""
+import numpy as np
+import pytest
+
+from minotaur_b200.instances import branch_boxes, make_knapsack_setcover, make_minlp, make_sparse_milp
+from helpers import assert_box_parity
+
+
+@pytest.fixture(scope="module")
+def Reference(have_ref):
+    if not have_ref:
+        pytest.skip("oracle/_ref/libminotaur_ref.so not built")
+    from oracle.pyoracle import Reference
+    return Reference
+
+
+@pytest.mark.parametrize("seed,real,inf", [(0, False, (0, 0, 0)), (1, True, (0, 0, 0)), (2, True, (0.1, 0.05, 0.02)),
+                                           (3, False, (0.2, 0.1, 0.1))])
+def test_linear_inplace_bitwise(oracle, Reference, seed, real, inf):
+    inst = make_sparse_milp(250, 220, 6, seed=seed, real_data=real, inf_frac=inf)
+    ref = Reference(inst)
+    lbs, ubs = branch_boxes(inst.lb, inst.ub, inst.var_type, 25, seed=seed, max_depth=10)
+    n_inf = 0
+    for b in range(lbs.shape[0]):
+        rl, ru, rr = ref.lin_simple_presolve(lbs[b], ubs[b])
+        ol, ou, orr = oracle.lin_simple_presolve(inst, lbs[b], ubs[b])
+        assert rr["verdict"] == orr["verdict"] and rr["n_mods"] == orr["n_mods"]
+        assert np.array_equal(rl, ol) and np.array_equal(ru, ou)
+        rl, ru, rr = ref.lin_fixpoint(lbs[b], ubs[b], counted=True)
+        ol, ou, orr = oracle.lin_fixpoint_inplace(inst, lbs[b], ubs[b])
+        assert rr["verdict"] == orr["verdict"] and rr["rounds"] == orr["rounds"]
+        assert rr["nnz_updates"] == orr["nnz_updates"]
+        n_inf += rr["verdict"]
+        if rr["verdict"] == 0:
+            assert np.array_equal(rl, ol) and np.array_equal(ru, ou)
+            jl, ju, jr = oracle.lin_fixpoint_jacobi(inst, lbs[b], ubs[b])
+            assert jr["verdict"] == 0
+            assert_box_parity(inst.var_type, jl, ju, rl, ru, rel_tol=5e-8, what=f"jacobi box {b}")
+        else:
+            assert oracle.lin_fixpoint_jacobi(inst, lbs[b], ubs[b])[2]["verdict"] != 0
+    ref.close()
+
+
+def test_knapsack_setcover_bitwise(oracle, Reference):
+    inst = make_knapsack_setcover(300, 200, 6, seed=4)
+    ref = Reference(inst)
+    lbs, ubs = branch_boxes(inst.lb, inst.ub, inst.var_type, 30, seed=9, max_depth=12)
+    for b in range(lbs.shape[0]):
+        rl, ru, rr = ref.lin_fixpoint(lbs[b], ubs[b], counted=True)
+        ol, ou, orr = oracle.lin_fixpoint_inplace(inst, lbs[b], ubs[b])
+        assert rr["verdict"] == orr["verdict"] and rr["nnz_updates"] == orr["nnz_updates"]
+        if rr["verdict"] == 0:
+            assert np.array_equal(rl, ol) and np.array_equal(ru, ou)
+    ref.close()
+
+
+def test_minlp_node_presolve_bitwise(oracle, Reference):
+    lin, tapes = make_minlp(n=60, n_cons=90, m_lin=30, seed=21)
+    lbs, ubs = branch_boxes(lin.lb, lin.ub, lin.var_type, 10, seed=5, max_depth=6, continuous_too=True)
+    for b in range(lbs.shape[0]):
+        ref = Reference(lin, tapes)                 # fresh graph: constant nodes keep state in the reference
+        rl, ru, rr = ref.node_presolve(lbs[b], ubs[b])
+        ol, ou, orr = oracle.node_presolve(lin, tapes, lbs[b], ubs[b])
+        assert (rr["verdict"] != 0) == (orr["verdict"] != 0)
+        if rr["verdict"] == 0:
+            assert np.array_equal(rl, ol) and np.array_equal(ru, ou)
+        ref.close()
