@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 node-batch extra measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch-boxes", type=int, default=8192)
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: no sustained pre-load loop")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -220,7 +221,8 @@ def main():
     def dev_step():
         with torch.cuda.stream(stream):
             w_lb.copy_(root_lb); w_ub.copy_(root_ub)
-            flush.zero_()                                              # evict L2 between steps
+            if not os.environ.get("MNTR_BENCH_NOFLUSH"):
+                flush.zero_()                                          # evict L2 between steps
         v, r, z = eng.tighten_single_dev(w_lb.data_ptr(), w_ub.data_ptr())   # synchronises the stream
         st = eng.stats()
         return st.kernel_ms, z, r, v, st
@@ -229,7 +231,7 @@ def main():
     if rank == 0:
         sampler.start()
     # sustained pre-load so the clock samples are taken under load, then the warm-up steps
-    t_end = time.perf_counter() + 1.5
+    t_end = time.perf_counter() + (0.0 if args.profile else 1.5)
     while time.perf_counter() < t_end:
         dev_step()
     for _ in range(args.warmup):

@@ -4,7 +4,8 @@
 
 namespace mntr {
 
-// Linear rows.  CSR whose row starts are padded to an EVEN entry index so a lane can fetch
+// Linear rows, stored in (wavefront level, original index) order with deleted rows last.
+// CSR whose row starts are padded to an EVEN entry index so a lane can fetch
 // two (col,val) pairs with one 64-bit + one 128-bit load; padding entries have val == 0 and
 // a valid column, and are skipped by value.  CSC (var -> rows) replaces Variable::cons_
 // (Variable.h:164-191) for the bFlag propagation of LinearHandler::changeBFlag_ (:1229-1234).
@@ -22,8 +23,7 @@ struct LinDev {
   const int32_t *csc_row;   // [nnz]
   // wavefront schedule of the reference's index-ordered in-place sweep
   int32_t n_levels;
-  const int32_t *level_ptr; // [n_levels+1]
-  const int32_t *level_row; // [m] rows sorted by (level, index)
+  const int32_t *level_ptr; // [n_levels+1] ranges of STORED rows (rows are stored in level order)
 };
 
 // CGraph tapes (see include/mntr_gpu.h for the node order contract)
@@ -47,11 +47,14 @@ struct NlDev {
 struct SingleWs {
   double2 *box;    // [n] {lb, ub} of the round start
   double2 *nbox;   // [n] candidates of the round (atomic max / min)
-  uint8_t *flag_a; // [m] row flags, current
-  uint8_t *flag_b; // [m] row flags, next
-  int32_t *ring;   // [8] per-round change flags: ring[r%3] changed, ring[3 + r%3] int moved
-  int32_t *status; // [0] verdict, [1] rounds
-  unsigned long long *counters;  // [0] nnz_updates, [1] rows evaluated
+  uint32_t *bits;  // [(m+31)/32] row-is-on-the-next-work-list bit set   (Constraint bFlag)
+  int32_t *list;   // [m] work list of flagged rows
+  // control block (128 bytes, zeroed before every launch)
+  int32_t *ring;   // [12] per-round words: ring[r%3] changed, ring[3+r%3] int moved, ring[6+r%3] list length
+  int32_t *status; // [4]  [0] verdict, [1] rounds, [2] changed (variable, round) pairs
+  unsigned long long *counters;  // [2] [0] nnz_updates, [1] rows evaluated
+  unsigned *bar;   // device-wide barrier arrive counter
+  unsigned long long *trace;     // [64] optional phase timestamps (globaltimer ns), or nullptr
 };
 
 }  // namespace mntr

@@ -19,6 +19,7 @@ struct BatchIo {
   int64_t ld;            // boxes per variable row (multiple of 32)
   int32_t n_boxes;
   uint32_t *rowflag;     // [tiles][m] bit b = row flagged for box tile*32+b   (bFlag)
+  uint32_t *varflag;     // [tiles][n] bit b = variable moved in the current sweep of box tile*32+b
   int32_t *verdict;      // [n_boxes]
   int32_t *rounds;       // [n_boxes]
   long long *nnz;        // [n_boxes]

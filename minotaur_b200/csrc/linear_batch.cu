@@ -10,7 +10,7 @@
 // only ordering constraint of the reference's in-place, index-ordered Gauss-Seidel sweep
 // (LinearHandler::varBndsFromCons_, LinearHandler.cpp:493-541) is between rows that share a
 // variable; rows are therefore scheduled in wavefront levels (level = 1 + max level of an
-// earlier row sharing a variable, built at load time) and a level boundary is a plain
+// earlier row sharing a variable; rows are stored in level order at load time) and a level boundary is a plain
 // __syncthreads() -- no grid-wide synchronisation, no atomics on bounds, no second buffer.
 // Inside a level the warps of the CTA take rows round-robin.  With round-to-nearest
 // arithmetic every lane performs exactly the reference's operation sequence (ascending
@@ -37,6 +37,8 @@ namespace {
 
 constexpr int kBatchWarps = 16;
 constexpr int kBatchThreads = kBatchWarps * 32;
+constexpr int kGather = 4;             // independent 512-byte gathers a warp keeps in flight
+constexpr unsigned kFull = 0xffffffffu;
 
 struct TileShared {
   int changed[32];
@@ -45,25 +47,54 @@ struct TileShared {
   unsigned long long nnz[32];
 };
 
+// A row is consumed in chunks of <= 32 entries: lane t fetches entry t (one coalesced request
+// for the whole chunk), entries are then broadcast with warp shuffles, and the {lb,ub} gathers of
+// kGather consecutive terms are issued back to back before any of them is consumed, so a warp has
+// kGather independent 512-byte requests in flight instead of one.  Terms are still CONSUMED in
+// ascending column order, one after the other, exactly like the reference's loop.
+struct Chunk {
+  int cj; double ca; int cnt;
+};
+
+__device__ __forceinline__ Chunk load_chunk(const LinDev &P, int c0, int end, int lane)
+{
+  Chunk c;
+  c.cnt = min(32, end - c0);
+  c.cj = 0; c.ca = 0.0;
+  if (lane < c.cnt) { c.cj = __ldg(P.col + c0 + lane); c.ca = __ldg(P.val + c0 + lane); }
+  return c;
+}
+
 // min / max activity of one row for this lane's box  [getLfBnds_]
 template <class R>
 __device__ __forceinline__ void row_activity(const LinDev &P, int beg, int end, const double2 *bx,
-                                             int64_t ld, bool mine, double &ll, double &uu)
+                                             int64_t ld, bool mine, int lane, double &ll, double &uu)
 {
   ll = 0.0; uu = 0.0;
-  for (int t = beg; t < end; ++t) {
-    const double a = __ldg(P.val + t);
-    if (a == 0.0) continue;                         // alignment padding (warp-uniform)
-    const int j = __ldg(P.col + t);
-    if (mine) {
-      const double2 b = bx[(int64_t)j * ld];
-      if (a > 0) { ll = R::add_lo(ll, R::mul_lo(a, b.x)); uu = R::add_hi(uu, R::mul_hi(a, b.y)); }
-      else       { ll = R::add_lo(ll, R::mul_lo(a, b.y)); uu = R::add_hi(uu, R::mul_hi(a, b.x)); }
+  for (int c0 = beg; c0 < end; c0 += 32) {
+    const Chunk c = load_chunk(P, c0, end, lane);
+    for (int t0 = 0; t0 < c.cnt; t0 += kGather) {
+      double a[kGather]; double2 b[kGather];
+#pragma unroll
+      for (int u = 0; u < kGather; ++u) {
+        a[u] = __shfl_sync(kFull, c.ca, (t0 + u) & 31);
+        const int j = __shfl_sync(kFull, c.cj, (t0 + u) & 31);
+        if (t0 + u >= c.cnt) a[u] = 0.0;
+        b[u] = make_double2(0.0, 0.0);
+        if (mine && a[u] != 0.0) b[u] = bx[(int64_t)j * ld];
+      }
+#pragma unroll
+      for (int u = 0; u < kGather; ++u) {
+        if (mine && a[u] != 0.0) {                   // a == 0: alignment padding / past the row
+          if (a[u] > 0) { ll = R::add_lo(ll, R::mul_lo(a[u], b[u].x)); uu = R::add_hi(uu, R::mul_hi(a[u], b[u].y)); }
+          else          { ll = R::add_lo(ll, R::mul_lo(a[u], b[u].y)); uu = R::add_hi(uu, R::mul_hi(a[u], b[u].x)); }
+        }
+      }
     }
   }
 }
 
-// singleton-infinity activity [getSingLfBnds_], state machine as coded in the reference
+// singleton-infinity activity [getSingLfBnds_], state machine as coded in the reference (rare path)
 template <class R>
 __device__ __forceinline__ void row_sing_activity(const LinDev &P, int beg, int end, const double2 *bx,
                                                   int64_t ld, bool need, double &slo, double &sup)
@@ -95,12 +126,14 @@ __device__ __forceinline__ void row_sing_activity(const LinDev &P, int beg, int 
   if (need) { slo = lb; sup = ub; }
 }
 
-// flag every row of variable j for the boxes in `mask`  [changeBFlag_]
+// flag every row of variable j for the boxes in `mask`  [changeBFlag_], and remember that the
+// variable moved (so the integer / bound sweep of this round only visits moved variables)
 __device__ __forceinline__ void flag_rows_of(const LinDev &P, int j, unsigned mask, uint32_t *flags,
-                                             int lane)
+                                             uint32_t *varflag, int lane)
 {
   const int b = __ldg(P.csc_ptr + j), e = __ldg(P.csc_ptr + j + 1);
   for (int q = b + lane; q < e; q += 32) atomicOr(flags + __ldg(P.csc_row + q), mask);
+  if (varflag != nullptr && lane == 0) atomicOr(varflag + j, mask);
 }
 
 // updateLfBoundsFromLb_ (FROM_LB) / updateLfBoundsFromUb_ (!FROM_LB), in place.
@@ -108,48 +141,75 @@ __device__ __forceinline__ void flag_rows_of(const LinDev &P, int j, unsigned ma
 template <class R, bool FROM_LB>
 __device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int end, double2 *bx, int64_t ld,
                                                bool doit, bool sing, double rbound, double act,
-                                               uint32_t *flags, TileShared &sh, int lane)
+                                               uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane)
 {
   unsigned any = 0;
   // (row bound - activity): FromLb needs a lower estimate, FromUb an upper estimate
   const double numer = FROM_LB ? R::sub_lo(rbound, act) : R::sub_hi(rbound, act);
-  for (int t = beg; t < end; ++t) {
-    const double a = __ldg(P.val + t);
-    if (a == 0.0) continue;
-    const int j = __ldg(P.col + t);
-    bool chg = false;
-    if (doit) {
-      double2 *pb = bx + (int64_t)j * ld;
-      const double2 b = *pb;
-      const double vl = b.x, vu = b.y;
-      // FromLb: a>0 raises lb, a<0 lowers ub.   FromUb: a>0 lowers ub, a<0 raises lb.
-      const bool raise_lb = FROM_LB ? (a > kETol) : (a < -kETol);
-      const bool lower_ub = FROM_LB ? (a < -kETol) : (a > kETol);
-      if (raise_lb && (!sing || vu >= kInf20)) {
-        const double base = (vu >= kInf20) ? 0.0 : vu;
-        double c = R::add_lo(R::div_lo(numer, a), base);
-        if (c > vl + kETol) {
-          if (c > vu - kETol) c = vu;
-          pb->x = c;
-          chg = true;
-        }
-      } else if (lower_ub && (!sing || vl <= -kInf20)) {
-        const double base = (vl <= -kInf20) ? 0.0 : vl;
-        double c = R::add_hi(R::div_hi(numer, a), base);
-        if (c < vu - kETol) {
-          if (c < vl + kETol) c = vl;
-          pb->y = c;
-          chg = true;
-        }
+  for (int c0 = beg; c0 < end; c0 += 32) {
+    const Chunk c = load_chunk(P, c0, end, lane);
+    for (int t0 = 0; t0 < c.cnt; t0 += kGather) {
+      double a[kGather]; double2 b[kGather]; int jj[kGather];
+#pragma unroll
+      for (int u = 0; u < kGather; ++u) {
+        a[u] = __shfl_sync(kFull, c.ca, (t0 + u) & 31);
+        jj[u] = __shfl_sync(kFull, c.cj, (t0 + u) & 31);
+        if (t0 + u >= c.cnt) a[u] = 0.0;
+        b[u] = make_double2(0.0, 0.0);
+        if (doit && a[u] != 0.0) b[u] = bx[(int64_t)jj[u] * ld];
       }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, chg);
-    if (m) {
-      any |= m;
-      flag_rows_of(P, j, m, flags, lane);
-      if (chg) {
-        sh.changed[lane] = 1;
-        if (is_int_type(__ldg(P.var_type + j))) sh.nint[lane] = 1;
+#pragma unroll
+      for (int u = 0; u < kGather; ++u) {
+        if (a[u] == 0.0) continue;                    // warp-uniform
+        bool chg = false;
+        const double av = a[u], aa = fabs(av);
+        if (doit && aa > kETol) {
+          double2 *pb = bx + (int64_t)jj[u] * ld;
+          const double vl = b[u].x, vu = b[u].y;
+          // FromLb: a>0 raises lb, a<0 lowers ub.   FromUb: a>0 lowers ub, a<0 raises lb.
+          const bool raise_lb = FROM_LB ? (av > 0.0) : (av < 0.0);
+          const bool inf_side = raise_lb ? (vu >= kInf20) : (vl <= -kInf20);
+          if (!sing || inf_side) {
+            const double base = inf_side ? 0.0 : (raise_lb ? vu : vl);
+            // ONE division by |a| per term: round_up(x/a) == -round_down(x/|a|) for a<0 (and x/a ==
+            // -(x/|a|) exactly in round-to-nearest), so the sign only selects the bound that moves.
+            // The candidate moves a bound of x_j towards the other by slack/|a| (slack = |numer|), so it
+            // can only be accepted when slack < |a|*(ub_j - lb_j): that product test rejects almost every
+            // term without the fp64 division (1e-9 relative margin; inf/NaN fall through to the exact path).
+            const double reach = aa * (vu - vl) * 1.000000001;
+            const bool maybe = !((FROM_LB ? -numer : numer) > reach);
+            if (maybe) {
+              if (raise_lb) {
+                // lower estimate of numer/a: FromLb (a>0) div_lo(numer,|a|); FromUb (a<0) -div_hi(numer,|a|)
+                const double q = FROM_LB ? R::div_lo(numer, aa) : -R::div_hi(numer, aa);
+                double cnd = R::add_lo(q, base);
+                if (cnd > vl + kETol) {
+                  if (cnd > vu - kETol) cnd = vu;
+                  pb->x = cnd;
+                  chg = true;
+                }
+              } else {
+                // upper estimate of numer/a: FromLb (a<0) -div_lo(numer,|a|); FromUb (a>0) div_hi(numer,|a|)
+                const double q = FROM_LB ? -R::div_lo(numer, aa) : R::div_hi(numer, aa);
+                double cnd = R::add_hi(q, base);
+                if (cnd < vu - kETol) {
+                  if (cnd < vl + kETol) cnd = vl;
+                  pb->y = cnd;
+                  chg = true;
+                }
+              }
+            }
+          }
+        }
+        const unsigned m = __ballot_sync(kFull, chg);
+        if (m) {
+          any |= m;
+          flag_rows_of(P, jj[u], m, flags, varflag, lane);
+          if (chg) {
+            sh.changed[lane] = 1;
+            if (is_int_type(__ldg(P.var_type + jj[u]))) sh.nint[lane] = 1;
+          }
+        }
       }
     }
   }
@@ -159,15 +219,15 @@ __device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int end
 // one linear row for the 32 boxes of the tile  [linBndTighten_ with apply_to_prob == false]
 template <class R>
 __device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx, int64_t ld, bool mine,
-                                            uint32_t *flags, TileShared &sh, int lane,
+                                            uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane,
                                             unsigned long long &my_nnz)
 {
   const int beg = __ldg(P.row_ptr + i), end = __ldg(P.row_ptr + i + 1);
   const double rl = __ldg(P.row_lb + i), ru = __ldg(P.row_ub + i);
   double ll, uu, sing_ll = -INFINITY, sing_uu = INFINITY;
-  row_activity<R>(P, beg, end, bx, ld, mine, ll, uu);
+  row_activity<R>(P, beg, end, bx, ld, mine, lane, ll, uu);
   bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
-  if (__any_sync(0xffffffffu, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
+  if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
   if (mine) my_nnz += (unsigned long long)__ldg(P.row_nnz + i);
   if (mine && (ll > ru + kETol || uu < rl - kETol)) {       // :994-1015
     sh.verdict[lane] = 2;  /* MNTR_INFEAS_ROW */
@@ -180,17 +240,17 @@ __device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx,
     else if (sing_uu < kInf20) { do_lb = true; s_lb = true; act = sing_uu; }
   }
   unsigned chg = 0;
-  if (__any_sync(0xffffffffu, do_lb))
-    chg = row_update<R, true>(P, beg, end, bx, ld, do_lb, s_lb, rl, act, flags, sh, lane);
+  if (__any_sync(kFull, do_lb))
+    chg = row_update<R, true>(P, beg, end, bx, ld, do_lb, s_lb, rl, act, flags, varflag, sh, lane);
   // recompute activities when FromLb changed something (:1027-1032); lanes that did not
   // change would recompute identical values, so the decision is taken per warp
   if (chg) {
     const bool redo = mine && ((chg >> lane) & 1u);
     double l2, u2;
-    row_activity<R>(P, beg, end, bx, ld, redo, l2, u2);
+    row_activity<R>(P, beg, end, bx, ld, redo, lane, l2, u2);
     if (redo) { ll = l2; uu = u2; }
     need_sing = redo && (ll < -kInf20 || uu > kInf20);
-    if (__any_sync(0xffffffffu, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
+    if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
   }
   // row ub side  (:1035-1043)
   bool do_ub = false, s_ub = false; act = 0.0;
@@ -198,12 +258,35 @@ __device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx,
     if (ll > -kInf20) { do_ub = true; act = ll; }
     else if (sing_ll > -kInf20) { do_ub = true; s_ub = true; act = sing_ll; }
   }
-  if (__any_sync(0xffffffffu, do_ub))
-    (void)row_update<R, false>(P, beg, end, bx, ld, do_ub, s_ub, ru, act, flags, sh, lane);
+  if (__any_sync(kFull, do_ub))
+    (void)row_update<R, false>(P, beg, end, bx, ld, do_ub, s_ub, ru, act, flags, varflag, sh, lane);
+}
+
+// integer rounding [tightenInts_] + lb>ub check [checkBounds_] of variable j for the lanes in `want`
+__device__ __forceinline__ void finish_var(const LinDev &P, int j, double2 b, bool want, double2 *bx, int64_t ld,
+                                           uint32_t *flags, TileShared &sh, int lane)
+{
+  const bool isint = is_int_type(__ldg(P.var_type + j));
+  bool chg = false;
+  if (want) {
+    if (isint) {
+      const double2 o = b;
+      tighten_int_bounds(b.x, b.y);
+      if (b.x != o.x || b.y != o.y) { bx[(int64_t)j * ld] = b; chg = true; }
+    }
+    if (b.x > b.y + kETol) sh.verdict[lane] = 1;       /* MNTR_INFEAS_BOUNDS; benign race */
+  }
+  if (isint) {
+    const unsigned m = __ballot_sync(kFull, chg);
+    if (m) {
+      flag_rows_of(P, j, m, flags, nullptr, lane);
+      if (chg) sh.changed[lane] = 1;
+    }
+  }
 }
 
 template <class R>
-__global__ void __launch_bounds__(kBatchThreads)
+__global__ void __launch_bounds__(kBatchThreads, 2)
 fbbt_batch_reference_kernel(LinDev P, BatchIo io, int loop_mode, int max_rounds)
 {
   __shared__ TileShared sh;
@@ -215,9 +298,11 @@ fbbt_batch_reference_kernel(LinDev P, BatchIo io, int loop_mode, int max_rounds)
   double2 *bx = io.boxes + box;             // + j*ld addresses variable j of this lane's box
   const int64_t ld = io.ld;
   uint32_t *flags = io.rowflag + (int64_t)tile * P.m;
+  uint32_t *varflag = io.varflag + (int64_t)tile * P.n;
 
   // every row flagged for every box of the tile  (simplePresolve :1618-1622)
-  for (int i = threadIdx.x; i < P.m; i += kBatchThreads) __stcg(flags + i, __ldg(P.row_active + i) ? 0xffffffffu : 0u);
+  for (int i = threadIdx.x; i < P.m; i += kBatchThreads) __stcg(flags + i, __ldg(P.row_active + i) ? kFull : 0u);
+  for (int j = threadIdx.x; j < P.n; j += kBatchThreads) __stcg(varflag + j, 0u);
   if (warp == 0) { sh.changed[lane] = 1; sh.nint[lane] = 0; sh.verdict[lane] = 0; sh.nnz[lane] = 0ull; }
   // checkBounds_ rows part is static: a row with lb > ub + eTol makes every box infeasible
   int bad_row = 0;
@@ -237,52 +322,74 @@ fbbt_batch_reference_kernel(LinDev P, BatchIo io, int loop_mode, int max_rounds)
     bool run = active && my_verdict == 0 && changed;
     if (max_rounds > 0 && my_rounds >= max_rounds) run = false;
     if (loop_mode == 1) run = run && iters <= 10 && (iters <= 2 || nint > 0);   // :1625-1627
-    const unsigned runmask = __ballot_sync(0xffffffffu, run);
+    const unsigned runmask = __ballot_sync(kFull, run);
     __syncthreads();                      // everybody has read the previous round's flags
     if (runmask == 0) break;
     if (warp == 0) { sh.changed[lane] = 0; sh.nint[lane] = 0; }
+    const bool first_sweep = (iters == 1);
     ++iters;
     if (run) ++my_rounds;
     __syncthreads();
 
-    // ---- rows, level by level ----
+    // ---- rows, level by level; inside a level each warp owns a contiguous run of rows ----
     for (int lev = 0; lev < P.n_levels; ++lev) {
       const int qb = __ldg(P.level_ptr + lev), qe = __ldg(P.level_ptr + lev + 1);
-      for (int q = qb + warp; q < qe; q += kBatchWarps) {
-        const int i = __ldg(P.level_row + q);
-        const uint32_t fw = __ldcg(flags + i);      // flags are updated by L2 atomics: bypass L1
+      const int per = (qe - qb + kBatchWarps - 1) / kBatchWarps;
+      const int q_lo = qb + warp * per, q_hi = min(qe, q_lo + per);
+      for (int q0 = q_lo; q0 < q_hi; q0 += 32) {
+        // 32 rows' flag words with one coalesced request (flags live in L2: they are updated by atomics)
+        const int q = q0 + lane;
+        const uint32_t raw = (q < q_hi) ? __ldcg(flags + q) : 0u;
         // boxes already proven infeasible by a row stop sweeping (their result is final)
-        unsigned alive = __ballot_sync(0xffffffffu, sh.verdict[lane] == 0);
-        const uint32_t proc = fw & runmask & alive;
-        if (proc == 0) continue;
-        if (lane == 0) __stcg(flags + i, fw & ~proc);   // c_ptr->setBFlag(false), :513
-        __syncwarp();
-        process_row<R>(P, i, bx, ld, (proc >> lane) & 1u, flags, sh, lane, my_nnz);
+        const unsigned alive = __ballot_sync(kFull, sh.verdict[lane] == 0);
+        const uint32_t fw = raw & runmask & alive;
+        unsigned rows = __ballot_sync(kFull, fw != 0u);
+        while (rows) {
+          const int t = __ffs(rows) - 1;
+          rows &= rows - 1;
+          const uint32_t proc = __shfl_sync(kFull, fw, t);
+          if (lane == t) __stcg(flags + q, raw & ~proc);     // c_ptr->setBFlag(false), :513
+          __syncwarp();
+          process_row<R>(P, q0 + t, bx, ld, (proc >> lane) & 1u, flags, varflag, sh, lane, my_nnz);
+        }
       }
       __syncthreads();
     }
 
-    // ---- integer rounding + bound check over all variables ----
-    for (int j = warp; j < P.n; j += kBatchWarps) {
-      bool chg = false;
-      const bool isint = is_int_type(__ldg(P.var_type + j));
-      // a box found bound-infeasible by another warp still finishes its integer sweep (the
-      // reference completes tightenInts_ before checkBounds_); row-infeasible boxes are frozen
-      if (run && sh.verdict[lane] != 2) {
-        double2 *pb = bx + (int64_t)j * ld;
-        double2 b = *pb;
-        if (isint) {
-          const double2 o = b;
-          tighten_int_bounds(b.x, b.y);
-          if (b.x != o.x || b.y != o.y) { *pb = b; chg = true; }
+    // ---- integer rounding + bound check ----
+    if (first_sweep) {
+      // every variable once: the incoming box may hold fractional integer bounds or crossed bounds
+      for (int j0 = warp * kGather; j0 < P.n; j0 += kBatchWarps * kGather) {
+        double2 b[kGather];
+        const bool want = run && sh.verdict[lane] != 2;     // row-infeasible boxes are frozen
+#pragma unroll
+        for (int u = 0; u < kGather; ++u) {
+          b[u] = make_double2(0.0, 0.0);
+          if (want && j0 + u < P.n) b[u] = bx[(int64_t)(j0 + u) * ld];
         }
-        if (b.x > b.y + kETol) sh.verdict[lane] = 1;   /* MNTR_INFEAS_BOUNDS; benign race */
+#pragma unroll
+        for (int u = 0; u < kGather; ++u)
+          if (j0 + u < P.n) finish_var(P, j0 + u, b[u], want, bx, ld, flags, sh, lane);
       }
-      if (isint) {
-        const unsigned m = __ballot_sync(0xffffffffu, chg);
-        if (m) {
-          flag_rows_of(P, j, m, flags, lane);
-          if (chg) sh.changed[lane] = 1;
+      for (int j = threadIdx.x; j < P.n; j += kBatchThreads) __stcg(varflag + j, 0u);
+    } else {
+      // later sweeps: only variables some row moved in this sweep can need rounding or can cross
+      const int per = (P.n + kBatchWarps - 1) / kBatchWarps;
+      const int j_lo = warp * per, j_hi = min(P.n, j_lo + per);
+      for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
+        const int j = j0 + lane;
+        const uint32_t vw = (j < j_hi) ? __ldcg(varflag + j) : 0u;
+        if (vw != 0u) __stcg(varflag + j, 0u);
+        const unsigned dead = __ballot_sync(kFull, sh.verdict[lane] == 2);
+        unsigned vars = __ballot_sync(kFull, (vw & runmask & ~dead) != 0u);
+        while (vars) {
+          const int t = __ffs(vars) - 1;
+          vars &= vars - 1;
+          const uint32_t who = __shfl_sync(kFull, vw, t) & runmask & ~dead;
+          const bool want = (who >> lane) & 1u;
+          double2 b = make_double2(0.0, 0.0);
+          if (want) b = bx[(int64_t)(j0 + t) * ld];
+          finish_var(P, j0 + t, b, want, bx, ld, flags, sh, lane);
         }
       }
     }

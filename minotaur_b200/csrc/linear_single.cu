@@ -1,5 +1,5 @@
 // linear_single.cu -- K1: single-box FBBT of the linear rows, Jacobi rounds to a fixpoint
-// inside ONE cooperative launch (device-side change flag, no host round trips).
+// inside ONE cooperative launch (device-side change flag and work list, no host round trips).
 //
 // Per round (reference lines in brackets):
 //   rows phase : sub-warp group per flagged CSR row -- 128-bit loads of (val,val) and
@@ -8,21 +8,56 @@
 //                infinity sums by finite-sum + infinity-count [getSingLfBnds_ :1261-1319];
 //                warp-shuffle butterfly reduction; activity infeasibility [:994-1015];
 //                implied bounds [updateLfBoundsFromLb_/Ub_ :1048-1226] merged with fp64
-//                atomic max/min into the next box.
+//                atomic max/min into the next box.  The loop over a group's rows is software
+//                pipelined three deep (row ids / CSR entries / gathers of three different rows
+//                are in flight together): at this size the phase is latency-, not bandwidth-bound.
 //   vars phase : integer rounding [tightenInts_ :415-490], lb>ub check [checkBounds_
-//                :328-359], change detection, CSC flagging of the rows to re-evaluate
-//                [changeBFlag_ :1229-1234], device-side change flag.
-// grid.sync() separates the phases; the loop condition is evaluated on the device.
-#include <cooperative_groups.h>
-
+//                :328-359], change detection; the rows of every changed variable
+//                [changeBFlag_ :1229-1234] are appended once (bit-set test-and-set) to the work
+//                list of the next round with warp-aggregated atomics.
+// A device-wide barrier (one arrive counter, acquire polling) separates the phases; the loop
+// condition is evaluated on the device from the round's change flags.
 #include "device_problem.cuh"
 #include "kernels.h"
-
-namespace cg = cooperative_groups;
 
 namespace mntr {
 
 namespace {
+
+constexpr int kSingleThreads = 1024;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// optional phase trace (MNTR_GPU_TRACE=1): thread 0 of block 0 stamps every phase boundary
+#define MNTR_TRACE() do { if (W.trace != nullptr && tid == 0 && tr < 64) W.trace[tr] = globaltimer_ns(); ++tr; } while (0)
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Device-wide barrier for a cooperative (co-resident) grid: a cumulative arrive counter, thread 0
+// of each block arrives with a release fence and polls with acquire loads; the trailing fence also
+// invalidates this SM's L1 so the block's ordinary loads see the other blocks' writes.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, unsigned &target)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += n_blocks;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire_gpu(bar) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
 
 // butterfly over the G lanes of a group; every lane ends with bitwise the same total
 template <int G, class R, bool LO>
@@ -51,56 +86,194 @@ struct RowCtx {
   bool do_lb, do_ub, sing_lb, sing_ub;
 };
 
-// one term of pass 2: candidates of updateLfBoundsFromLb_ / updateLfBoundsFromUb_
+// branch-free term of getLfBnds_: an absent entry has a == 0 and b == {0,0}, contributing +0
+template <class R>
+__device__ __forceinline__ void accumulate(double a, double2 b, double &ll, double &uu)
+{
+  const bool pos = a > 0.0;
+  const double blo = pos ? b.x : b.y, bhi = pos ? b.y : b.x;
+  ll = R::add_lo(ll, R::mul_lo(a, blo));
+  uu = R::add_hi(uu, R::mul_hi(a, bhi));
+}
+
+// one term of pass 2: candidates of updateLfBoundsFromLb_ / updateLfBoundsFromUb_.
+//
+// Both row sides and both coefficient signs obey one rule: the candidate moves ONE bound of x_j
+// towards the other by  slack/|a|,  slack = (max activity - row lb)  or  (row ub - min activity):
+//     a>0, lb side: new lb = ub_j - slack/a        a<0, lb side: new ub = lb_j + slack/|a|
+//     a>0, ub side: new ub = lb_j + slack/a        a<0, ub side: new lb = ub_j - slack/|a|
+// so it can only be accepted when slack < |a| * (ub_j - lb_j).  That product test (one DADD, one
+// DMUL, shared by both sides) rejects almost every term of a round without the fp64 division; it
+// is conservative (1e-9 relative margin, NaN/inf fall through), so results are unchanged.
+// With directed rounding the division is taken on |a| (round_up(x/a) == -round_down(x/|a|) for
+// a<0; in round-to-nearest x/a == -(x/|a|) exactly), so the sign only picks the bound that moves.
 template <class R>
 __device__ __forceinline__ void emit_candidates(const RowCtx &rc, double a, int j, double2 b,
                                                 double2 *nbox)
 {
   const double vl = b.x, vu = b.y;
-  if (rc.do_lb) {                                   // row lb side, activity = max activity
+  const double aa = fabs(a);
+  if (!(aa > kETol)) return;
+  const bool pos = a > 0.0;
+  const double reach = aa * (vu - vl) * 1.000000001;      // inf or NaN when a bound is infinite
+  if (rc.do_lb) {                                   // row lb side: numer = rl - max activity = -slack
     const double numer = R::sub_lo(rc.rl, rc.act_lb);
-    if (a > kETol && (!rc.sing_lb || vu >= kInf20)) {
-      const double base = (vu >= kInf20) ? 0.0 : vu;
-      double c = R::add_lo(R::div_lo(numer, a), base);
-      if (c > vl + kETol) {
-        if (c > vu - kETol) c = vu;
-        atomic_max_f64(&nbox[j].x, c);
-      }
-    } else if (a < -kETol && (!rc.sing_lb || vl <= -kInf20)) {
-      const double base = (vl <= -kInf20) ? 0.0 : vl;
-      double c = R::add_hi(R::div_hi(numer, a), base);
-      if (c < vu - kETol) {
-        if (c < vl + kETol) c = vl;
-        atomic_min_f64(&nbox[j].y, c);
+    const bool inf_side = pos ? (vu >= kInf20) : (vl <= -kInf20);
+    if ((!rc.sing_lb || inf_side) && !(-numer > reach)) {
+      const double base = inf_side ? 0.0 : (pos ? vu : vl);
+      const double t = R::div_lo(numer, aa);        // round_down((rl - act)/|a|)
+      if (pos) {
+        double c = R::add_lo(t, base);
+        if (c > vl + kETol) { if (c > vu - kETol) c = vu; atomic_max_f64(&nbox[j].x, c); }
+      } else {
+        double c = R::add_hi(-t, base);
+        if (c < vu - kETol) { if (c < vl + kETol) c = vl; atomic_min_f64(&nbox[j].y, c); }
       }
     }
   }
-  if (rc.do_ub) {                                   // row ub side, activity = min activity
+  if (rc.do_ub) {                                   // row ub side: numer = ru - min activity = slack
     const double numer = R::sub_hi(rc.ru, rc.act_ub);
-    if (a > kETol && (!rc.sing_ub || vl <= -kInf20)) {
-      const double base = (vl <= -kInf20) ? 0.0 : vl;
-      double c = R::add_hi(R::div_hi(numer, a), base);
-      if (c < vu - kETol) {
-        if (c < vl + kETol) c = vl;
-        atomic_min_f64(&nbox[j].y, c);
-      }
-    } else if (a < -kETol && (!rc.sing_ub || vu >= kInf20)) {
-      const double base = (vu >= kInf20) ? 0.0 : vu;
-      double c = R::add_lo(R::div_lo(numer, a), base);
-      if (c > vl + kETol) {
-        if (c > vu - kETol) c = vu;
-        atomic_max_f64(&nbox[j].x, c);
+    const bool inf_side = pos ? (vl <= -kInf20) : (vu >= kInf20);
+    if ((!rc.sing_ub || inf_side) && !(numer > reach)) {
+      const double base = inf_side ? 0.0 : (pos ? vl : vu);
+      const double sq = R::div_hi(numer, aa);       // round_up((ru - act)/|a|)
+      if (pos) {
+        double c = R::add_hi(sq, base);
+        if (c < vu - kETol) { if (c < vl + kETol) c = vl; atomic_min_f64(&nbox[j].y, c); }
+      } else {
+        double c = R::add_lo(-sq, base);
+        if (c > vl + kETol) { if (c > vu - kETol) c = vu; atomic_max_f64(&nbox[j].x, c); }
       }
     }
   }
 }
 
+// pipeline registers of one row
+struct RowMeta { int i, beg, end; };                  // i < 0: nothing to do
+struct RowData { double2 a2; int2 c2; };              // this lane's first entry pair (a == 0: none)
+
+__device__ __forceinline__ RowMeta load_meta(const LinDev &P, const SingleWs &W, int idx, int count, bool first)
+{
+  RowMeta r; r.i = -1; r.beg = 0; r.end = 0;
+  if (idx < count) {
+    const int i = first ? idx : W.list[idx];
+    if (!first || __ldg(P.row_active + i)) {
+      r.i = i;
+      r.beg = __ldg(P.row_ptr + i);
+      r.end = __ldg(P.row_ptr + i + 1);
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ RowData load_data(const LinDev &P, const RowMeta &r, int lane_g)
+{
+  RowData d; d.a2 = make_double2(0.0, 0.0); d.c2 = make_int2(0, 0);
+  const int t = r.beg + 2 * lane_g;
+  if (r.i >= 0 && t < r.end) {
+    d.a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
+    d.c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
+  }
+  return d;
+}
+
+// one flagged row: activities, infeasibility, candidates   [linBndTighten_, Jacobi form]
 template <int G, class R>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void process_row(const LinDev &P, const SingleWs &W, const RowMeta &r, const RowData &d,
+                                            int lane_g, unsigned gmask, unsigned long long &my_nnz,
+                                            unsigned long long &my_rows)
+{
+  const int i = r.i;
+  RowCtx rc;
+  rc.rl = __ldg(P.row_lb + i);
+  rc.ru = __ldg(P.row_ub + i);
+  if (lane_g == 0) {
+    my_nnz += (unsigned long long)__ldg(P.row_nnz + i); ++my_rows;
+    atomicAnd(W.bits + (i >> 5), ~(1u << (i & 31)));       // setBFlag(false), :513
+  }
+  // pass 1: the first entry pair is already in registers, its two gathers go out together
+  double2 b0 = make_double2(0.0, 0.0), b1 = b0;
+  if (d.a2.x != 0.0) b0 = W.box[d.c2.x];
+  if (d.a2.y != 0.0) b1 = W.box[d.c2.y];
+  double ll = 0.0, uu = 0.0;
+  accumulate<R>(d.a2.x, b0, ll, uu);
+  accumulate<R>(d.a2.y, b1, ll, uu);
+  const bool long_row = (r.end - r.beg) > 2 * G;           // group-uniform
+  if (long_row) {
+    for (int t = r.beg + 2 * lane_g + 2 * G; t < r.end; t += 2 * G) {
+      const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
+      const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
+      if (a2.x != 0.0) accumulate<R>(a2.x, W.box[c2.x], ll, uu);
+      if (a2.y != 0.0) accumulate<R>(a2.y, W.box[c2.y], ll, uu);
+    }
+  }
+  ll = group_reduce<G, R, true>(ll, gmask);
+  uu = group_reduce<G, R, false>(uu, gmask);
+
+  // singleton-infinity sums, only when an activity is beyond +-1e20 (:970-972)
+  double sing_ll = -INFINITY, sing_uu = INFINITY;
+  if (ll < -kInf20 || uu > kInf20) {
+    double fs_lo = 0.0, fs_hi = 0.0;
+    int ninf_lo = 0, ninf_hi = 0;
+    for (int t = r.beg + 2 * lane_g; t < r.end; t += 2 * G) {
+      const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
+      const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double a = h ? a2.y : a2.x;
+        const int j = h ? c2.y : c2.x;
+        if (a > kETol) {
+          const double2 b = W.box[j];
+          if (b.y < kInf20) fs_hi = R::add_hi(fs_hi, R::mul_hi(a, b.y)); else ++ninf_hi;
+          if (b.x > -kInf20) fs_lo = R::add_lo(fs_lo, R::mul_lo(a, b.x)); else ++ninf_lo;
+        } else if (a < -kETol) {
+          const double2 b = W.box[j];
+          if (b.y < kInf20) fs_lo = R::add_lo(fs_lo, R::mul_lo(a, b.y)); else ++ninf_lo;
+          if (b.x > -kInf20) fs_hi = R::add_hi(fs_hi, R::mul_hi(a, b.x)); else ++ninf_hi;
+        }
+      }
+    }
+    fs_lo = group_reduce<G, R, true>(fs_lo, gmask);
+    fs_hi = group_reduce<G, R, false>(fs_hi, gmask);
+    ninf_lo = group_reduce_int<G>(ninf_lo, gmask);
+    ninf_hi = group_reduce_int<G>(ninf_hi, gmask);
+    sing_ll = (ninf_lo >= 2) ? -INFINITY : fs_lo;
+    sing_uu = (ninf_hi >= 2) ? INFINITY : fs_hi;
+  }
+
+  if (ll > rc.ru + kETol || uu < rc.rl - kETol) {     // activity-infeasible row
+    if (lane_g == 0) W.status[0] = 2 /* MNTR_INFEAS_ROW */;
+    return;
+  }
+  rc.do_lb = rc.do_ub = rc.sing_lb = rc.sing_ub = false;
+  rc.act_lb = rc.act_ub = 0.0;
+  if (rc.rl > -kInf20) {
+    if (uu < kInf20) { rc.do_lb = true; rc.act_lb = uu; }
+    else if (sing_uu < kInf20) { rc.do_lb = true; rc.sing_lb = true; rc.act_lb = sing_uu; }
+  }
+  if (rc.ru < kInf20) {
+    if (ll > -kInf20) { rc.do_ub = true; rc.act_ub = ll; }
+    else if (sing_ll > -kInf20) { rc.do_ub = true; rc.sing_ub = true; rc.act_ub = sing_ll; }
+  }
+  if (!rc.do_lb && !rc.do_ub) return;
+  // pass 2: implied bounds; the first pair and its bounds are still in registers
+  if (d.a2.x != 0.0) emit_candidates<R>(rc, d.a2.x, d.c2.x, b0, W.nbox);
+  if (d.a2.y != 0.0) emit_candidates<R>(rc, d.a2.y, d.c2.y, b1, W.nbox);
+  if (long_row) {
+    for (int t = r.beg + 2 * lane_g + 2 * G; t < r.end; t += 2 * G) {
+      const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
+      const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
+      if (a2.x != 0.0) emit_candidates<R>(rc, a2.x, c2.x, W.box[c2.x], W.nbox);
+      if (a2.y != 0.0) emit_candidates<R>(rc, a2.y, c2.y, W.box[c2.y], W.nbox);
+    }
+  }
+}
+
+template <int G, class R>
+__global__ void __launch_bounds__(kSingleThreads, 1)
 fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, int max_rounds,
                           int loop_mode)
 {
-  cg::grid_group grid = cg::this_grid();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
@@ -108,157 +281,127 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
   const int group = tid / G;
   const int n_groups = nthreads / G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lane_g));
+  unsigned bar_target = 0;
+  __shared__ int s_count;
+  __shared__ unsigned long long s_nnz, s_rows;
+  if (threadIdx.x == 0) { s_count = 0; s_nnz = 0ull; s_rows = 0ull; }
+  int tr = 0;
+  MNTR_TRACE();
 
-  // ---- phase 0: build {lb,ub} boxes, flag every active row (simplePresolve :1618-1622) ----
+  // ---- phase 0: build {lb,ub} boxes; every active row is on round 1's work list
+  //      (simplePresolve :1618-1622), so the list is the identity and is not materialised ----
   int infeasible0 = 0;
   for (int j = tid; j < P.n; j += nthreads) {
     double2 b = make_double2(lb_io[j], ub_io[j]);
     W.box[j] = b;
     W.nbox[j] = b;
   }
-  for (int i = tid; i < P.m; i += nthreads) {
-    const bool act = P.row_active[i] != 0;
-    W.flag_a[i] = act ? 1 : 0;
-    W.flag_b[i] = 0;
-    if (act && P.row_lb[i] > P.row_ub[i] + kETol) infeasible0 = 1;   // checkBounds_, rows part
-  }
+  for (int i = tid; i < P.m; i += nthreads)
+    if (__ldg(P.row_active + i) && __ldg(P.row_lb + i) > __ldg(P.row_ub + i) + kETol) infeasible0 = 1;  // checkBounds_, rows
+  for (int w = tid; w < (P.m + 31) / 32; w += nthreads) W.bits[w] = 0u;
   if (infeasible0) W.status[0] = 1 /* MNTR_INFEAS_BOUNDS */;
-  grid.sync();
-  volatile int32_t *vstatus = W.status;   // control words are re-read after every grid.sync
+  MNTR_TRACE();
+  grid_barrier(W.bar, gridDim.x, bar_target);
+  MNTR_TRACE();
+  volatile int32_t *vstatus = W.status;   // control words are re-read after every barrier
   volatile int32_t *vring = W.ring;
 
-  uint8_t *fcur = W.flag_a, *fnext = W.flag_b;
   unsigned long long my_nnz = 0, my_rows = 0;
   int round = 0;
   int verdict = vstatus[0];
+  int count = P.m;                         // work items of the current round
 
   while (verdict == 0) {
     ++round;
     const int slot = round % 3;
-    if (tid == 0) { W.ring[(round + 1) % 3] = 0; W.ring[3 + (round + 1) % 3] = 0; }
+    // ring[slot]: changed, ring[3+slot]: int moved, ring[6+slot]: next round's list length
+    if (tid == 0) { const int nx = (round + 1) % 3; W.ring[nx] = 0; W.ring[3 + nx] = 0; W.ring[6 + nx] = 0; }
 
-    // ------------------------------ rows phase ------------------------------
-    for (int i = group; i < P.m; i += n_groups) {
-      int f = 0;
-      if (lane_g == 0) { f = fcur[i]; if (f) fcur[i] = 0; }
-      f = __shfl_sync(gmask, f, 0, G);
-      if (!f) continue;
-      const int beg = P.row_ptr[i], end = P.row_ptr[i + 1];
-      RowCtx rc;
-      rc.rl = P.row_lb[i];
-      rc.ru = P.row_ub[i];
-      // pass 1: min / max activity
-      double ll = 0.0, uu = 0.0;
-      for (int t = beg + 2 * lane_g; t < end; t += 2 * G) {
-        const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
-        const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
-        if (a2.x != 0.0) {
-          const double2 b = W.box[c2.x];
-          if (a2.x > 0) { ll = R::add_lo(ll, R::mul_lo(a2.x, b.x)); uu = R::add_hi(uu, R::mul_hi(a2.x, b.y)); }
-          else          { ll = R::add_lo(ll, R::mul_lo(a2.x, b.y)); uu = R::add_hi(uu, R::mul_hi(a2.x, b.x)); }
-        }
-        if (a2.y != 0.0) {
-          const double2 b = W.box[c2.y];
-          if (a2.y > 0) { ll = R::add_lo(ll, R::mul_lo(a2.y, b.x)); uu = R::add_hi(uu, R::mul_hi(a2.y, b.y)); }
-          else          { ll = R::add_lo(ll, R::mul_lo(a2.y, b.y)); uu = R::add_hi(uu, R::mul_hi(a2.y, b.x)); }
-        }
-      }
-      ll = group_reduce<G, R, true>(ll, gmask);
-      uu = group_reduce<G, R, false>(uu, gmask);
-      if (lane_g == 0) { my_nnz += (unsigned long long)P.row_nnz[i]; ++my_rows; }
-
-      // singleton-infinity sums, only when an activity is beyond +-1e20 (:970-972)
-      double sing_ll = -INFINITY, sing_uu = INFINITY;
-      if (ll < -kInf20 || uu > kInf20) {
-        double fs_lo = 0.0, fs_hi = 0.0;
-        int ninf_lo = 0, ninf_hi = 0;
-        for (int t = beg + 2 * lane_g; t < end; t += 2 * G) {
-          const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
-          const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const double a = h ? a2.y : a2.x;
-            const int j = h ? c2.y : c2.x;
-            if (a > kETol) {
-              const double2 b = W.box[j];
-              if (b.y < kInf20) fs_hi = R::add_hi(fs_hi, R::mul_hi(a, b.y)); else ++ninf_hi;
-              if (b.x > -kInf20) fs_lo = R::add_lo(fs_lo, R::mul_lo(a, b.x)); else ++ninf_lo;
-            } else if (a < -kETol) {
-              const double2 b = W.box[j];
-              if (b.y < kInf20) fs_lo = R::add_lo(fs_lo, R::mul_lo(a, b.y)); else ++ninf_lo;
-              if (b.x > -kInf20) fs_hi = R::add_hi(fs_hi, R::mul_hi(a, b.x)); else ++ninf_hi;
-            }
-          }
-        }
-        fs_lo = group_reduce<G, R, true>(fs_lo, gmask);
-        fs_hi = group_reduce<G, R, false>(fs_hi, gmask);
-        ninf_lo = group_reduce_int<G>(ninf_lo, gmask);
-        ninf_hi = group_reduce_int<G>(ninf_hi, gmask);
-        sing_ll = (ninf_lo >= 2) ? -INFINITY : fs_lo;
-        sing_uu = (ninf_hi >= 2) ? INFINITY : fs_hi;
-      }
-
-      if (ll > rc.ru + kETol || uu < rc.rl - kETol) {     // activity-infeasible row
-        if (lane_g == 0) W.status[0] = 2 /* MNTR_INFEAS_ROW */;
-        continue;
-      }
-      rc.do_lb = rc.do_ub = rc.sing_lb = rc.sing_ub = false;
-      rc.act_lb = rc.act_ub = 0.0;
-      if (rc.rl > -kInf20) {
-        if (uu < kInf20) { rc.do_lb = true; rc.act_lb = uu; }
-        else if (sing_uu < kInf20) { rc.do_lb = true; rc.sing_lb = true; rc.act_lb = sing_uu; }
-      }
-      if (rc.ru < kInf20) {
-        if (ll > -kInf20) { rc.do_ub = true; rc.act_ub = ll; }
-        else if (sing_ll > -kInf20) { rc.do_ub = true; rc.sing_ub = true; rc.act_ub = sing_ll; }
-      }
-      if (!rc.do_lb && !rc.do_ub) continue;
-      // pass 2: implied bounds (the row's entries are L1/L2 hits now)
-      for (int t = beg + 2 * lane_g; t < end; t += 2 * G) {
-        const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
-        const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
-        if (a2.x != 0.0) emit_candidates<R>(rc, a2.x, c2.x, W.box[c2.x], W.nbox);
-        if (a2.y != 0.0) emit_candidates<R>(rc, a2.y, c2.y, W.box[c2.y], W.nbox);
+    // ------------------------------ rows phase (software pipelined) ------------------------------
+    {
+      const bool first = (round == 1);
+      RowMeta mC = load_meta(P, W, group, count, first);
+      RowData dC = load_data(P, mC, lane_g);
+      RowMeta mB = load_meta(P, W, group + n_groups, count, first);
+      for (int idx = group; idx < count; idx += n_groups) {
+        const RowData dB = load_data(P, mB, lane_g);                          // entries of the next row
+        const RowMeta mA = load_meta(P, W, idx + 2 * n_groups, count, first); // ids of the one after
+        if (mC.i >= 0) process_row<G, R>(P, W, mC, dC, lane_g, gmask, my_nnz, my_rows);
+        mC = mB; dC = dB; mB = mA;
       }
     }
-    grid.sync();
+    MNTR_TRACE();
+    grid_barrier(W.bar, gridDim.x, bar_target);
+    MNTR_TRACE();
     verdict = vstatus[0];
     if (verdict != 0) break;
 
     // ------------------------------ vars phase ------------------------------
+    // a warp owns 32 consecutive variables; the rows of each changed variable are flagged by the
+    // whole warp (lane q takes CSC entry q), so the test-and-set atomics of a variable are all in
+    // flight together instead of one after the other
     int changed = 0, int_moved = 0, bad = 0;
     int n_changed = 0;
-    for (int j = tid; j < P.n; j += nthreads) {
-      const double2 o = W.box[j];
-      double2 v = W.nbox[j];
-      const bool isint = is_int_type(P.var_type[j]);
-      if (isint) {
-        if (v.x != o.x || v.y != o.y) int_moved = 1;      // row-derived mod on an int var (nintmods)
-        tighten_int_bounds(v.x, v.y);
-      }
-      if (v.x > v.y + kETol) bad = 1;
-      if (v.x != o.x || v.y != o.y) {
-        changed = 1;
-        ++n_changed;
-        W.box[j] = v;
-        W.nbox[j] = v;
-        for (int q = P.csc_ptr[j]; q < P.csc_ptr[j + 1]; ++q) fnext[P.csc_row[q]] = 1;
+    {
+      const int warp_g = tid >> 5, n_warps = nthreads >> 5;
+      for (int j0 = warp_g * 32; j0 < P.n; j0 += n_warps * 32) {
+        const int j = j0 + lane;
+        bool ch = false;
+        if (j < P.n) {
+          const double2 o = W.box[j];
+          double2 v = W.nbox[j];
+          if (is_int_type(__ldg(P.var_type + j))) {
+            if (v.x != o.x || v.y != o.y) int_moved = 1;    // row-derived mod on an int var (nintmods)
+            tighten_int_bounds(v.x, v.y);
+          }
+          if (v.x > v.y + kETol) bad = 1;
+          if (v.x != o.x || v.y != o.y) { ch = true; W.box[j] = v; W.nbox[j] = v; }
+        }
+        unsigned chm = __ballot_sync(0xffffffffu, ch);
+        if (ch) { changed = 1; ++n_changed; }
+        while (chm) {
+          const int t = __ffs(chm) - 1;
+          chm &= chm - 1;
+          const int qb = __ldg(P.csc_ptr + j0 + t), qe = __ldg(P.csc_ptr + j0 + t + 1);
+          for (int q0 = qb; q0 < qe; q0 += 32) {
+            const int q = q0 + lane;
+            bool fresh = false; int row = 0;
+            if (q < qe) {
+              row = __ldg(P.csc_row + q);
+              const unsigned bit = 1u << (row & 31);
+              fresh = (atomicOr(W.bits + (row >> 5), bit) & bit) == 0u;
+            }
+            const unsigned want = __ballot_sync(0xffffffffu, fresh);
+            if (want) {
+              int base = 0;
+              const int leader = __ffs(want) - 1;
+              if (lane == leader) base = atomicAdd(&W.ring[6 + slot], __popc(want));
+              base = __shfl_sync(0xffffffffu, base, leader);
+              if (fresh) W.list[base + __popc(want & ((1u << lane) - 1u))] = row;
+            }
+          }
+        }
       }
     }
-    if (n_changed) atomicAdd(&W.status[2], n_changed);
+    // block-level reduction of the counters: one global atomic per block, not per thread
+    n_changed = __reduce_add_sync(0xffffffffu, n_changed);
+    if (lane == 0 && n_changed) atomicAdd(&s_count, n_changed);
     changed = __syncthreads_or(changed);
     int_moved = __syncthreads_or(int_moved);
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
+      if (s_count) { atomicAdd(&W.status[2], s_count); s_count = 0; }
       if (changed) W.ring[slot] = 1;
       if (int_moved) W.ring[3 + slot] = 1;
       if (bad) W.status[0] = 1 /* MNTR_INFEAS_BOUNDS */;
     }
-    grid.sync();
+    MNTR_TRACE();
+    grid_barrier(W.bar, gridDim.x, bar_target);
+    MNTR_TRACE();
     verdict = vstatus[0];
     const int any_changed = vring[slot];
     const int any_int = vring[3 + slot];
-    { uint8_t *t = fcur; fcur = fnext; fnext = t; }
+    count = vring[6 + slot];
     if (verdict != 0 || !any_changed) break;
     if (max_rounds > 0 && round >= max_rounds) break;
     if (loop_mode == 1) {   // LinearHandler::simplePresolve truncation, :1625-1627
@@ -278,8 +421,11 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
     my_nnz += __shfl_xor_sync(0xffffffffu, my_nnz, off);
     my_rows += __shfl_xor_sync(0xffffffffu, my_rows, off);
   }
-  if (lane == 0 && my_rows) { atomicAdd(&W.counters[0], my_nnz); atomicAdd(&W.counters[1], my_rows); }
+  if (lane == 0 && my_rows) { atomicAdd(&s_nnz, my_nnz); atomicAdd(&s_rows, my_rows); }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_rows) { atomicAdd(&W.counters[0], s_nnz); atomicAdd(&W.counters[1], s_rows); }
   if (tid == 0) W.status[1] = round;
+  MNTR_TRACE();
 }
 
 template <int G, class R>
@@ -288,18 +434,19 @@ cudaError_t launch_g(const LinDev &P, const SingleWs &W, double *lb, double *ub,
 {
   auto kern = fbbt_single_jacobi_kernel<G, R>;
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSingleThreads, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   long long want_threads = (long long)P.m * G;
   if (want_threads < P.n) want_threads = P.n;
-  long long want_blocks = (want_threads + 255) / 256;
+  long long want_blocks = (want_threads + kSingleThreads - 1) / kSingleThreads;
   long long max_blocks = (long long)per_sm * sm_count;
   int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
   if (blocks < 1) blocks = 1;
   LinDev p = P; SingleWs w = W;
   void *args[] = { &p, &w, &lb, &ub, &max_rounds, &loop_mode };
-  return cudaLaunchCooperativeKernel((void *)kern, dim3(blocks), dim3(256), args, 0, stream);
+  // cooperative launch: guarantees that all blocks are co-resident, which the barrier relies on
+  return cudaLaunchCooperativeKernel((void *)kern, dim3(blocks), dim3(kSingleThreads), args, 0, stream);
 }
 
 template <class R>

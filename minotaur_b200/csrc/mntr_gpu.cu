@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -42,13 +43,13 @@ struct mntr_gpu_ctx {
   // ---- single-box workspace ----
   SingleWs sws{};
   double *d_lb = nullptr, *d_ub = nullptr;   // [n] staging of one box
-  void *d_ctrl = nullptr;                    // ring[8] | status[2] | counters[2]
+  void *d_ctrl = nullptr;                    // SingleCtrl
   std::vector<void *> single_allocs;
 
   // ---- batch workspace ----
   int64_t batch_ld = 0;        // capacity in boxes (multiple of 32)
   double2 *d_boxes = nullptr;
-  uint32_t *d_rowflag = nullptr;
+  uint32_t *d_rowflag = nullptr, *d_varflag = nullptr;
   int32_t *d_verdict = nullptr, *d_rounds = nullptr;
   long long *d_nnzb = nullptr;
   double *d_stage_lb = nullptr, *d_stage_ub = nullptr;
@@ -56,6 +57,10 @@ struct mntr_gpu_ctx {
 
   mntr_gpu_stats stats{};
 };
+
+// host mirror of the single-box kernel's control block (SingleWs::ring/status/counters/bar)
+struct SingleCtrl { int32_t ring[12]; int32_t status[4]; unsigned long long counters[2]; unsigned bar; unsigned pad[11]; };
+static_assert(sizeof(SingleCtrl) == 128, "control block layout");
 
 namespace {
 
@@ -103,21 +108,23 @@ void free_stage(mntr_gpu_ctx *c)
 
 void free_batch(mntr_gpu_ctx *c)
 {
-  cudaFree(c->d_boxes); cudaFree(c->d_rowflag); cudaFree(c->d_verdict); cudaFree(c->d_rounds);
+  cudaFree(c->d_boxes); cudaFree(c->d_rowflag); cudaFree(c->d_varflag); cudaFree(c->d_verdict); cudaFree(c->d_rounds);
   cudaFree(c->d_nnzb);
   c->d_boxes = nullptr; c->d_rowflag = nullptr; c->d_verdict = nullptr; c->d_rounds = nullptr;
-  c->d_nnzb = nullptr;
+  c->d_nnzb = nullptr; c->d_varflag = nullptr;
   c->batch_ld = 0;
 }
 
-int ensure_batch(mntr_gpu_ctx *ctx, int32_t n_boxes)
+int ensure_batch(mntr_gpu_ctx *ctx, int32_t n_boxes, bool need_boxes)
 {
   const int64_t ld = mntr_gpu_box_ld(n_boxes);
-  if (ld <= ctx->batch_ld) return MNTR_OK;
+  if (ld <= ctx->batch_ld && (!need_boxes || ctx->d_boxes)) return MNTR_OK;
   free_batch(ctx);
   const int64_t tiles = ld / 32;
-  CU(cudaMalloc((void **)&ctx->d_boxes, sizeof(double2) * (size_t)std::max<int64_t>(1, (int64_t)ctx->n * ld)));
+  if (need_boxes)
+    CU(cudaMalloc((void **)&ctx->d_boxes, sizeof(double2) * (size_t)std::max<int64_t>(1, (int64_t)ctx->n * ld)));
   CU(cudaMalloc((void **)&ctx->d_rowflag, sizeof(uint32_t) * (size_t)std::max<int64_t>(1, (int64_t)ctx->m * tiles)));
+  CU(cudaMalloc((void **)&ctx->d_varflag, sizeof(uint32_t) * (size_t)std::max<int64_t>(1, (int64_t)ctx->n * tiles)));
   CU(cudaMalloc((void **)&ctx->d_verdict, sizeof(int32_t) * (size_t)ld));
   CU(cudaMalloc((void **)&ctx->d_rounds, sizeof(int32_t) * (size_t)ld));
   CU(cudaMalloc((void **)&ctx->d_nnzb, sizeof(long long) * (size_t)ld));
@@ -236,15 +243,12 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   free_all(ctx->nl_allocs); ctx->nl_loaded = false;
   ctx->lin_loaded = false;
 
-  // ---- host flattening: drop |a| <= 1e-9 (LinearFunction.cpp:89-95), pad rows to even starts ----
-  std::vector<int32_t> prow(m + 1, 0), pcol, rnnz(m, 0);
-  std::vector<double> pval;
-  std::vector<uint8_t> ract(m, 1);
-  pcol.reserve((size_t)row_ptr[m] + m); pval.reserve((size_t)row_ptr[m] + m);
-  int64_t nnz = 0;
+  // ---- host flattening: drop |a| <= 1e-9 (LinearFunction.cpp:89-95) ----
+  std::vector<int32_t> cptr0(m + 1, 0), ccol;     // compact CSR in the caller's row order
+  std::vector<double> cval;
+  ccol.reserve((size_t)row_ptr[m]); cval.reserve((size_t)row_ptr[m]);
   for (int32_t i = 0; i < m; ++i) {
     if (row_ptr[i + 1] < row_ptr[i]) return fail(ctx, MNTR_E_ARG, "load_linear: row_ptr not monotone at row %d", i);
-    prow[i] = (int32_t)pcol.size();
     int32_t prev = -1;
     for (int32_t t = row_ptr[i]; t < row_ptr[i + 1]; ++t) {
       const int32_t j = col[t];
@@ -252,37 +256,62 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
       if (j <= prev) return fail(ctx, MNTR_E_ARG, "load_linear: columns not strictly ascending in row %d", i);
       prev = j;
       if (std::fabs(val[t]) <= kCoefDrop) continue;
-      pcol.push_back(j); pval.push_back(val[t]); ++rnnz[i]; ++nnz;
+      ccol.push_back(j); cval.push_back(val[t]);
     }
-    if (pcol.size() & 1) { pcol.push_back(pcol.back()); pval.push_back(0.0); }
-    if (row_active) ract[i] = row_active[i] ? 1 : 0;
-    if ((int64_t)pcol.size() > (int64_t)INT32_MAX - 4) return fail(ctx, MNTR_E_UNSUPPORTED, "load_linear: more than 2^31 entries");
+    cptr0[i + 1] = (int32_t)ccol.size();
   }
-  prow[m] = (int32_t)pcol.size();
+  const int64_t nnz = (int64_t)ccol.size();
+  if (nnz + m > (int64_t)INT32_MAX - 4) return fail(ctx, MNTR_E_UNSUPPORTED, "load_linear: more than 2^31 entries");
 
-  // ---- CSC: var -> rows (Variable::cons_) ----
-  std::vector<int32_t> cptr(n + 2, 0), crow((size_t)std::max<int64_t>(nnz, 1));
-  for (int32_t i = 0; i < m; ++i)
-    for (int32_t t = prow[i]; t < prow[i + 1]; ++t) if (pval[t] != 0.0) cptr[pcol[t] + 2]++;
-  for (int32_t j = 0; j < n; ++j) cptr[j + 2] += cptr[j + 1];
-  for (int32_t i = 0; i < m; ++i)
-    for (int32_t t = prow[i]; t < prow[i + 1]; ++t) if (pval[t] != 0.0) crow[cptr[pcol[t] + 1]++] = i;
-
-  // ---- wavefront levels of the index-ordered in-place sweep ----
+  // ---- wavefront levels of the reference's index-ordered in-place sweep: a row's level is one more
+  //      than the highest level of an EARLIER row sharing a variable; rows of one level are pairwise
+  //      variable-disjoint, so running levels in order reproduces the sequential sweep exactly ----
   std::vector<int32_t> last(n, -1), level(m, 0);
   int32_t n_levels = 0;
   for (int32_t i = 0; i < m; ++i) {
-    if (!ract[i]) { level[i] = -1; continue; }
+    if (row_active && !row_active[i]) { level[i] = -1; continue; }
     int32_t lev = 0;
-    for (int32_t t = prow[i]; t < prow[i + 1]; ++t) if (pval[t] != 0.0) lev = std::max(lev, last[pcol[t]] + 1);
+    for (int32_t t = cptr0[i]; t < cptr0[i + 1]; ++t) lev = std::max(lev, last[ccol[t]] + 1);
     level[i] = lev;
-    for (int32_t t = prow[i]; t < prow[i + 1]; ++t) if (pval[t] != 0.0) last[pcol[t]] = lev;
+    for (int32_t t = cptr0[i]; t < cptr0[i + 1]; ++t) last[ccol[t]] = lev;
     n_levels = std::max(n_levels, lev + 1);
   }
-  std::vector<int32_t> lptr(n_levels + 2, 0), lrow((size_t)std::max(m, 1));
-  for (int32_t i = 0; i < m; ++i) if (level[i] >= 0) lptr[level[i] + 2]++;
+  // rows are STORED in (level, index) order; deleted rows go last and are never scheduled
+  std::vector<int32_t> lptr(n_levels + 2, 0), perm((size_t)std::max(m, 1));
+  int32_t n_sched = 0;
+  for (int32_t i = 0; i < m; ++i) if (level[i] >= 0) { lptr[level[i] + 2]++; ++n_sched; }
   for (int32_t l = 0; l < n_levels; ++l) lptr[l + 2] += lptr[l + 1];
-  for (int32_t i = 0; i < m; ++i) if (level[i] >= 0) lrow[lptr[level[i] + 1]++] = i;
+  {
+    int32_t tail = n_sched;
+    for (int32_t i = 0; i < m; ++i) {
+      if (level[i] >= 0) perm[lptr[level[i] + 1]++] = i;
+      else perm[tail++] = i;
+    }
+  }
+
+  // ---- padded CSR in stored order: row starts at even entries (128-bit val / 64-bit col loads) ----
+  std::vector<int32_t> prow(m + 1, 0), pcol, rnnz(m, 0);
+  std::vector<double> pval, prl(m), pru(m);
+  std::vector<uint8_t> ract(m, 1);
+  pcol.reserve((size_t)nnz + m); pval.reserve((size_t)nnz + m);
+  for (int32_t q = 0; q < m; ++q) {
+    const int32_t i = perm[q];
+    prow[q] = (int32_t)pcol.size();
+    for (int32_t t = cptr0[i]; t < cptr0[i + 1]; ++t) { pcol.push_back(ccol[t]); pval.push_back(cval[t]); }
+    rnnz[q] = cptr0[i + 1] - cptr0[i];
+    if (pcol.size() & 1) { pcol.push_back(pcol.back()); pval.push_back(0.0); }
+    ract[q] = (row_active && !row_active[i]) ? 0 : 1;
+    prl[q] = row_lb[i]; pru[q] = row_ub[i];
+  }
+  prow[m] = (int32_t)pcol.size();
+
+  // ---- CSC: var -> stored rows (Variable::cons_) ----
+  std::vector<int32_t> cptr(n + 2, 0), crow((size_t)std::max<int64_t>(nnz, 1));
+  for (int32_t q = 0; q < m; ++q)
+    for (int32_t t = prow[q]; t < prow[q + 1]; ++t) if (pval[t] != 0.0) cptr[pcol[t] + 2]++;
+  for (int32_t j = 0; j < n; ++j) cptr[j + 2] += cptr[j + 1];
+  for (int32_t q = 0; q < m; ++q)
+    for (int32_t t = prow[q]; t < prow[q + 1]; ++t) if (pval[t] != 0.0) crow[cptr[pcol[t] + 1]++] = q;
 
   // ---- upload ----
   LinDev &L = ctx->lin;
@@ -293,14 +322,13 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pcol.data(), pcol.size(), &L.col))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pval.data(), pval.size(), &L.val))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, rnnz.data(), rnnz.size(), &L.row_nnz))) return rc;
-  if ((rc = dev_upload(ctx, ctx->lin_allocs, row_lb, (size_t)m, &L.row_lb))) return rc;
-  if ((rc = dev_upload(ctx, ctx->lin_allocs, row_ub, (size_t)m, &L.row_ub))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, prl.data(), (size_t)m, &L.row_lb))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, pru.data(), (size_t)m, &L.row_ub))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, var_type, (size_t)n, &L.var_type))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, ract.data(), ract.size(), &L.row_active))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, cptr.data(), (size_t)n + 1, &L.csc_ptr))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, crow.data(), (size_t)nnz, &L.csc_row))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, lptr.data(), (size_t)n_levels + 1, &L.level_ptr))) return rc;
-  if ((rc = dev_upload(ctx, ctx->lin_allocs, lrow.data(), (size_t)m, &L.level_row))) return rc;
 
   // ---- single-box workspace ----
   SingleWs &W = ctx->sws;
@@ -311,14 +339,19 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   };
   if ((rc = dalloc((void **)&W.box, sizeof(double2) * (size_t)n))) return rc;
   if ((rc = dalloc((void **)&W.nbox, sizeof(double2) * (size_t)n))) return rc;
-  if ((rc = dalloc((void **)&W.flag_a, (size_t)m))) return rc;
-  if ((rc = dalloc((void **)&W.flag_b, (size_t)m))) return rc;
+  if ((rc = dalloc((void **)&W.bits, sizeof(uint32_t) * (size_t)((m + 31) / 32 + 1)))) return rc;
+  if ((rc = dalloc((void **)&W.list, sizeof(int32_t) * (size_t)m))) return rc;
   if ((rc = dalloc((void **)&ctx->d_lb, sizeof(double) * (size_t)n))) return rc;
   if ((rc = dalloc((void **)&ctx->d_ub, sizeof(double) * (size_t)n))) return rc;
-  if ((rc = dalloc(&ctx->d_ctrl, 64))) return rc;
+  if ((rc = dalloc(&ctx->d_ctrl, sizeof(SingleCtrl)))) return rc;
   W.ring = (int32_t *)ctx->d_ctrl;
-  W.status = W.ring + 8;
-  W.counters = (unsigned long long *)((char *)ctx->d_ctrl + 48);
+  W.status = W.ring + 12;
+  W.counters = (unsigned long long *)((char *)ctx->d_ctrl + 64);
+  W.bar = (unsigned *)((char *)ctx->d_ctrl + 80);
+  W.trace = nullptr;
+  if (const char *tr = getenv("MNTR_GPU_TRACE")) {
+    if (tr[0] == '1') { if ((rc = dalloc((void **)&W.trace, 64 * sizeof(unsigned long long)))) return rc; }
+  }
 
   // sub-warp group size from the mean row length (two entries per lane per step)
   const double mean = m > 0 ? (double)nnz / m : 0.0;
@@ -347,13 +380,11 @@ int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *, const dou
   return fail(ctx, MNTR_E_UNSUPPORTED, "set_cutoff: objective cut-off row is not implemented yet");
 }
 
-struct SingleCtrl { int32_t ring[8]; int32_t status[2]; int32_t pad[2]; unsigned long long counters[2]; };
-static_assert(sizeof(SingleCtrl) == 64, "control block layout");
 
 // K1 on a device-resident box; leaves verdict/rounds/counters in the control block
 static int run_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, const mntr_gpu_options &o)
 {
-  CU(cudaMemsetAsync(ctx->d_ctrl, 0, 64, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(SingleCtrl), ctx->stream));
   CU(launch_single_jacobi(ctx->lin, ctx->sws, lb_dev, ub_dev, ctx->lanes_per_row,
                           o.rounding == MNTR_ROUND_DIRECTED, o.max_rounds, o.loop, ctx->sm_count, ctx->stream));
   return MNTR_OK;
@@ -363,7 +394,7 @@ static void account_single(mntr_gpu_ctx *ctx, const SingleCtrl &ctrl)
 {
   ctx->stats.nnz_updates += (int64_t)ctrl.counters[0];
   ctx->stats.rows_evaluated += (int64_t)ctrl.counters[1];
-  ctx->stats.n_changes += (int64_t)ctrl.pad[0];
+  ctx->stats.n_changes += (int64_t)ctrl.status[2];
   ctx->stats.n_infeasible += ctrl.status[0] != 0;
   ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, ctrl.status[1]);
 }
@@ -382,7 +413,7 @@ static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_
   CU(cudaMemcpyAsync(lb, ctx->d_lb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(ub, ctx->d_ub, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   SingleCtrl ctrl;
-  CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, sizeof(SingleCtrl), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (verdict) *verdict = ctrl.status[0];
@@ -410,13 +441,22 @@ int mntr_gpu_tighten_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_de
   if ((rc = run_single_dev(ctx, lb_dev, ub_dev, o))) return rc;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   SingleCtrl ctrl;
-  CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, sizeof(SingleCtrl), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (verdict) *verdict = ctrl.status[0];
   if (rounds) *rounds = ctrl.status[1];
   if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
   account_single(ctx, ctrl);
   ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  if (ctx->sws.trace) {     // debug: phase durations of the fixpoint kernel
+    unsigned long long t[64];
+    CU(cudaMemcpy(t, ctx->sws.trace, sizeof(t), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[mntr trace] rounds=%d kernel=%.1fus phases(us):", ctrl.status[1], ctx->stats.kernel_ms * 1e3);
+    const int np = 4 + 4 * ctrl.status[1];
+    for (int k = 1; k < np && k < 64; ++k) fprintf(stderr, " %.1f", (double)(t[k] - t[k - 1]) * 1e-3);
+    fprintf(stderr, "\n");
+    CU(cudaMemset(ctx->sws.trace, 0, sizeof(t)));
+  }
   return MNTR_OK;
 }
 
@@ -473,10 +513,10 @@ int mntr_gpu_tighten_dev(mntr_gpu_ctx *ctx, int32_t n_boxes, void *boxes_dev, co
   const int64_t ld = mntr_gpu_box_ld(n_boxes);
   const int64_t tiles = ld / 32;
   // row flags are sized for the context's batch capacity
-  int rc = ensure_batch(ctx, n_boxes);
+  int rc = ensure_batch(ctx, n_boxes, false);
   if (rc) return rc;
   BatchIo io;
-  io.boxes = (double2 *)boxes_dev; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag;
+  io.boxes = (double2 *)boxes_dev; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag;
   io.verdict = verdict_dev; io.rounds = rounds_dev; io.nnz = (long long *)nnz_dev;
   (void)tiles;
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -513,13 +553,13 @@ int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
   }
   if (o.order != MNTR_ORDER_REFERENCE) return fail(ctx, MNTR_E_ARG, "tighten: bad order");
 
-  int rc = ensure_batch(ctx, n_boxes);
+  int rc = ensure_batch(ctx, n_boxes, true);
   if (rc) return rc;
   const int64_t ld = mntr_gpu_box_ld(n_boxes);
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   if ((rc = mntr_gpu_boxes_upload(ctx, n_boxes, lb, ub, ctx->d_boxes))) return rc;
   BatchIo io;
-  io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag;
+  io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag;
   io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb;
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
