@@ -251,7 +251,7 @@ def main():
 
     # ---------------- e2e: C-ABI call with pinned host buffers ----------------
     h_lb = torch.empty(n, dtype=torch.float64).pin_memory(); h_ub = torch.empty(n, dtype=torch.float64).pin_memory()
-    opts = E.GpuOptions(E.ROUND_DIRECTED, E.ORDER_JACOBI, E.LOOP_FIXPOINT, 0)
+    opts = E.GpuOptions(E.ROUND_DIRECTED, E.ORDER_JACOBI, E.LOOP_FIXPOINT, 0, E.HANDLERS_ALL)
     vbuf = np.zeros(1, np.int32); rbuf = np.zeros(1, np.int32); zbuf = np.zeros(1, np.int64)
     root_l_h, root_u_h = torch.from_numpy(inst.lb), torch.from_numpy(inst.ub)
 

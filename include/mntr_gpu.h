@@ -82,11 +82,20 @@ enum {
                                     NlPresHandler::simplePresolve: <=2 sweeps (:1034-1035) */
 };
 
+/* which of the reference's presolve handlers a tighten call stands in for */
+enum {
+  MNTR_HANDLERS_ALL       = 0,  /* LinearHandler, then NlPresHandler when tapes are loaded */
+  MNTR_HANDLERS_LINEAR    = 1,  /* LinearHandler only */
+  MNTR_HANDLERS_NONLINEAR = 2   /* NlPresHandler only */
+};
+
 typedef struct {
   int32_t rounding;     /* MNTR_ROUND_*  */
-  int32_t order;        /* MNTR_ORDER_*  */
+  int32_t order;        /* MNTR_ORDER_*  (-1: Jacobi for one box, reference order for a batch) */
   int32_t loop;         /* MNTR_LOOP_*   */
   int32_t max_rounds;   /* 0 = no extra cap */
+  int32_t handlers;     /* MNTR_HANDLERS_* */
+  int32_t reserved[3];  /* must be 0 */
 } mntr_gpu_options;
 
 /* per-call statistics (LinPresolveStats / NlPresStats counterparts, LinearHandler.h:22-36) */

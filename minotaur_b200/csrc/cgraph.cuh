@@ -1,0 +1,413 @@
+// cgraph.cuh -- K4 device code: interval evaluation of CGraph expression tapes.
+//
+// One lane evaluates one (constraint, box) pair; all lanes of a warp walk the SAME tape, so the
+// opcode dispatch is warp-uniform and the tape entries are broadcast loads.  Node intervals live
+// in per-thread local arrays (indexed by the warp-uniform node index: coalesced local memory).
+//
+// Reference rules reproduced (file:line under /root/reference/src/base/):
+//   forward  CNode::updateBnd        CNode.cpp:1701-1904   (incl. the (-inf,inf) "TODO" opcodes)
+//   reverse  CNode::propBounds       CNode.cpp:1259-1501   (incl. the OpSqr / OpSqrt / OpPowK / OpSumList
+//            CNode::propBounds_      CNode.cpp:1504-1526    quirks listed in SURVEY.md section 7, hard part 3)
+//   helpers  BoundsOnProduct/Recip/Div/Square   Operations.cpp:100-246
+//   driver   CGraph::varBoundMods    CGraph.cpp:1605-1644  (1e-4 acceptance, 1e-5 relaxation)
+// With RoundNearest every lane performs the reference's operation sequence, so +,-,*,/,sqrt results are
+// bitwise the reference's; exp/log/log10/pow come from CUDA's libm (<= 2 ulp from glibc).  With
+// RoundDirected lower bounds are rounded down and upper bounds up (transcendentals widened by 2 ulp).
+#pragma once
+#include "device_problem.cuh"
+
+namespace mntr {
+
+constexpr int kMaxTape = 48;          // longest supported tape (nodes per constraint)
+constexpr double kMinfty = 1e25;      // CNode.cpp:26
+
+// Minotaur::OpCode (OpCode.h:17-53)
+enum : int {
+  OpAbs = 0, OpAcos, OpAcosh, OpAsin, OpAsinh, OpAtan, OpAtanh, OpCeil, OpCos, OpCosh, OpCPow, OpDiv, OpExp,
+  OpFloor, OpInt, OpIntDiv, OpLog, OpLog10, OpMinus, OpMult, OpNone, OpNum, OpPlus, OpPow, OpPowK, OpRound,
+  OpSin, OpSinh, OpSqr, OpSqrt, OpSumList, OpTan, OpTanh, OpUMinus, OpVar
+};
+
+// std::min / std::max as the reference uses them (first argument wins ties: zero signs preserved)
+__device__ __forceinline__ double std_min(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double std_max(double a, double b) { return (a < b) ? b : a; }
+
+__device__ __forceinline__ double widen_lo(double x, bool directed)
+{
+  // two representable steps down: adding the smallest subnormal with round-down moves one step
+  return (directed && isfinite(x)) ? __dadd_rd(__dadd_rd(x, -4.9406564584124654e-324), -4.9406564584124654e-324) : x;
+}
+__device__ __forceinline__ double widen_hi(double x, bool directed)
+{
+  return (directed && isfinite(x)) ? __dadd_ru(__dadd_ru(x, 4.9406564584124654e-324), 4.9406564584124654e-324) : x;
+}
+
+template <class R> struct RoundTraits { static constexpr bool directed = true; };
+template <> struct RoundTraits<RoundNearest> { static constexpr bool directed = false; };
+
+// BoundsOnProduct, Operations.cpp:117-179
+template <class R>
+__device__ __forceinline__ void bounds_on_product(bool zero_x_inf_zero, double l0, double u0, double l1, double u1,
+                                                  double &lb, double &ub)
+{
+  if (fabs(l1) <= 1e-10 && fabs(u1) <= 1e-10) {
+    double t = l1; l1 = l0; l0 = t;
+    t = u1; u1 = u0; u0 = t;
+  }
+  if (fabs(l0) <= 1e-10 && fabs(u0) <= 1e-10) {
+    if (zero_x_inf_zero) { lb = 0.0; ub = 0.0; }
+    else {
+      lb = (l1 == -INFINITY) ? -INFINITY : 0.0;
+      ub = (u1 == INFINITY) ? INFINITY : 0.0;
+    }
+  } else if ((l1 == -INFINITY && u1 == INFINITY) || (l0 == -INFINITY && u0 == INFINITY)) {
+    lb = -INFINITY; ub = INFINITY;
+  } else {
+    // four corner products; 0*inf (NaN) is mapped as the reference maps it
+    double pl = R::mul_lo(l0, l1), ph = R::mul_hi(l0, l1);
+    if (isnan(pl)) { pl = -INFINITY; ph = -INFINITY; }
+    double l = pl, u = ph;
+    pl = R::mul_lo(u0, l1); ph = R::mul_hi(u0, l1);
+    if (isnan(pl)) { pl = INFINITY; ph = INFINITY; }
+    l = std_min(l, pl); u = std_max(u, ph);
+    pl = R::mul_lo(u0, u1); ph = R::mul_hi(u0, u1);
+    if (isnan(pl)) { pl = -INFINITY; ph = -INFINITY; }
+    l = std_min(l, pl); u = std_max(u, ph);
+    pl = R::mul_lo(l0, u1); ph = R::mul_hi(l0, u1);
+    if (isnan(pl)) { pl = INFINITY; ph = INFINITY; }
+    l = std_min(l, pl); u = std_max(u, ph);
+    lb = l; ub = u;
+  }
+}
+
+// BoundsOnRecip, Operations.cpp:182-212
+template <class R>
+__device__ __forceinline__ void bounds_on_recip(double l0, double u0, double &lb, double &ub)
+{
+  if ((fabs(u0) < 1e-10) && (fabs(l0) < 1e-10)) { lb = -INFINITY; ub = INFINITY; }
+  else if (l0 < -1e-10 && u0 > 1e-10) { lb = -INFINITY; ub = INFINITY; }
+  else if ((fabs(u0) < 1e-10) && l0 < 0) { lb = -INFINITY; ub = R::div_hi(1.0, l0); }
+  else if ((fabs(l0) < 1e-10) && u0 < 0) { lb = R::div_lo(1.0, u0); ub = INFINITY; }
+  else { lb = R::div_lo(1.0, u0); ub = R::div_hi(1.0, l0); }
+}
+
+// BoundsOnDiv, Operations.cpp:100-106
+template <class R>
+__device__ __forceinline__ void bounds_on_div(double l0, double u0, double l1, double u1, double &lb, double &ub)
+{
+  double tl, tu;
+  bounds_on_recip<R>(l1, u1, tl, tu);
+  bounds_on_product<R>(false, l0, u0, tl, tu, lb, ub);
+}
+
+// BoundsOnSquare, Operations.cpp:233-246
+template <class R>
+__device__ __forceinline__ void bounds_on_square(double l1, double u1, double &lb, double &ub)
+{
+  if (u1 < 0.) { lb = R::mul_lo(u1, u1); ub = R::mul_hi(l1, l1); }
+  else if (l1 > 0.) { lb = R::mul_lo(l1, l1); ub = R::mul_hi(u1, u1); }
+  else { lb = 0.; ub = std_max(R::mul_hi(l1, l1), R::mul_hi(u1, u1)); }
+}
+
+// isInt(v, 1e-12), Operations.cpp:80-83
+__device__ __forceinline__ bool is_int_val(double v) { return fabs(floor(v + 0.5) - v) < 1e-12; }
+
+// libm calls with the errno behaviour the reference observes (domain / range errors make
+// CGraph::computeBounds / varBoundMods return SolveError)
+__device__ __forceinline__ double chk(double r, double x, int &error)
+{
+  if (isnan(r) && !isnan(x)) error = 33;                    // EDOM
+  else if (isinf(r) && isfinite(x)) error = 34;             // ERANGE (overflow / pole)
+  return r;
+}
+__device__ __forceinline__ double exp_chk(double x, int &error)
+{
+  const double r = exp(x);
+  if (isfinite(x) && (isinf(r) || r < 2.2250738585072014e-308)) error = 34;   // overflow / underflow
+  return r;
+}
+__device__ __forceinline__ double pow_chk(double x, double y, int &error)
+{
+  const double r = pow(x, y);
+  if (isnan(r) && !isnan(x) && !isnan(y)) error = 33;
+  else if (isinf(r) && isfinite(x) && isfinite(y)) error = 34;
+  else if (r == 0.0 && x != 0.0 && isfinite(x) && isfinite(y)) error = 34;
+  return r;
+}
+
+struct TapeView {
+  const uint8_t *op; const int32_t *a0; const int32_t *a1; const double *cn; const int32_t *child;
+  int nn;
+};
+
+// CNode::updateBnd for node i.  Constants: OpNum keeps [d,d] (CNode::setVal :1693-1699), OpInt keeps the
+// constructor's (-inf,inf) (CGraph.cpp:1238-1245); neither gets the 1e25 clamp (they are not in vq_/dq_).
+template <class R>
+__device__ __forceinline__ void node_forward(const TapeView &t, int i, double *nlb, double *nub, const double2 *bx,
+                                             int64_t ld, int &error)
+{
+  constexpr bool D = RoundTraits<R>::directed;
+  const int op = t.op[i];
+  if (op == OpNum) { nlb[i] = nub[i] = t.cn[i]; return; }
+  if (op == OpInt) { nlb[i] = -INFINITY; nub[i] = INFINITY; return; }
+  double llb = 0, lub = 0, rlb = 0, rub = 0;
+  if (op != OpVar && op != OpSumList) {
+    llb = nlb[t.a0[i]]; lub = nub[t.a0[i]];
+    if (t.a1[i] >= 0) { rlb = nlb[t.a1[i]]; rub = nub[t.a1[i]]; }
+  }
+  double lb, ub;
+  switch (op) {
+  case OpAbs:
+    if (lub < 0) { lb = -lub; ub = -llb; }
+    else if (llb < 0) { if (-llb > lub) { lb = 0.0; ub = -llb; } else { lb = 0.0; ub = lub; } }
+    else { lb = llb; ub = lub; }
+    break;
+  case OpAcos: lb = 0.0; ub = 3.141592653589793; break;
+  case OpAsin: case OpAtan: lb = -3.141592653589793 / 2; ub = 3.141592653589793 / 2; break;
+  case OpCeil: lb = ceil(llb); ub = ceil(lub); break;
+  case OpCos: case OpSin: lb = -1.0; ub = 1.0; break;
+  case OpDiv: bounds_on_div<R>(llb, lub, rlb, rub, lb, ub); break;
+  case OpExp:
+    lb = (llb == -INFINITY) ? 0.0 : widen_lo(exp_chk(llb, error), D);
+    ub = (lub == INFINITY) ? INFINITY : widen_hi(exp_chk(lub, error), D);
+    if (D && lb < 0.0) lb = 0.0;
+    break;
+  case OpFloor: lb = floor(llb); ub = floor(lub); break;
+  case OpLog:
+    lb = (llb <= 0.0) ? -INFINITY : widen_lo(chk(log(llb), llb, error), D);
+    ub = widen_hi(chk(log(lub), lub, error), D);
+    break;
+  case OpLog10:
+    lb = (llb <= 0.0) ? -INFINITY : widen_lo(chk(log10(llb), llb, error), D);
+    ub = widen_hi(chk(log10(lub), lub, error), D);
+    break;
+  case OpMinus: lb = R::sub_lo(llb, rub); ub = R::sub_hi(lub, rlb); break;
+  case OpMult: bounds_on_product<R>(true, llb, lub, rlb, rub, lb, ub); break;
+  case OpNone: return;
+  case OpPlus: lb = R::add_lo(llb, rlb); ub = R::add_hi(lub, rub); break;
+  case OpSqr: bounds_on_square<R>(llb, lub, lb, ub); break;
+  case OpSqrt:
+    lb = (llb < 1e-12) ? 0.0 : R::sqrt_lo(llb);
+    ub = R::sqrt_hi(lub);
+    if (isnan(ub) && !isnan(lub)) error = 33;
+    break;
+  case OpSumList: {
+    double l = 0.0, u = 0.0;
+    for (int c = t.a0[i]; c < t.a1[i]; ++c) { l = R::add_lo(l, nlb[t.child[c]]); u = R::add_hi(u, nub[t.child[c]]); }
+    lb = l; ub = u;
+  } break;
+  case OpUMinus: lb = -lub; ub = -llb; break;
+  case OpVar: { const double2 b = bx[(int64_t)t.a0[i] * ld]; lb = b.x; ub = b.y; } break;
+  default:   // Acosh Asinh Atanh Cosh CPow IntDiv Pow PowK Round Sinh Tan Tanh: "TODO" in the reference
+    lb = -INFINITY; ub = INFINITY; break;
+  }
+  if (lb < -kMinfty) lb = -INFINITY;
+  if (ub > kMinfty) ub = INFINITY;
+  nlb[i] = lb; nub[i] = ub;
+}
+
+// CNode::propBounds_, CNode.cpp:1504-1526 (a NaN trips an assert in the reference -> error)
+__device__ __forceinline__ void prop_child(int c, double lb, double ub, double *nlb, double *nub, bool &is_inf,
+                                           int &error)
+{
+  const double etol = 1e-7;
+  if (isnan(lb) || isnan(ub)) { error = 9999; return; }
+  if (lb < -kMinfty) lb = -INFINITY;
+  if (ub > kMinfty) ub = INFINITY;
+  if (lb > ub + etol || ub < nlb[c] - etol || lb > nub[c] + etol) is_inf = true;
+  else { if (lb > nlb[c]) nlb[c] = lb; if (ub < nub[c]) nub[c] = ub; }
+}
+
+// CNode::propBounds for node i, reference quirks kept (see header)
+template <class R>
+__device__ __forceinline__ void node_reverse(const TapeView &t, int i, double *nlb, double *nub, bool &is_inf,
+                                             int &error)
+{
+  constexpr bool D = RoundTraits<R>::directed;
+  const int op = t.op[i];
+  const int l = t.a0[i], r = t.a1[i];
+  const double lb_ = nlb[i], ub_ = nub[i];
+  double lb = -INFINITY, ub = INFINITY;
+  switch (op) {
+  case OpAbs: prop_child(l, -ub_, ub_, nlb, nub, is_inf, error); break;
+  case OpAcos: case OpAsin: prop_child(l, -1.0, 1.0, nlb, nub, is_inf, error); break;
+  case OpCeil: prop_child(l, floor(lb_), floor(ub_), nlb, nub, is_inf, error); break;
+  case OpDiv:
+    bounds_on_product<R>(false, nlb[r], nub[r], lb_, ub_, lb, ub);
+    prop_child(l, lb, ub, nlb, nub, is_inf, error);
+    bounds_on_div<R>(nlb[l], nub[l], lb_, ub_, lb, ub);
+    prop_child(r, lb, ub, nlb, nub, is_inf, error);
+    break;
+  case OpExp:
+    lb = widen_lo(chk(log(lb_), lb_, error), D); ub = widen_hi(chk(log(ub_), ub_, error), D);
+    prop_child(l, lb, ub, nlb, nub, is_inf, error);
+    break;
+  case OpFloor: prop_child(l, ceil(lb_), ceil(ub_), nlb, nub, is_inf, error); break;
+  case OpLog:
+    lb = widen_lo(exp_chk(lb_, error), D); ub = widen_hi(exp_chk(ub_, error), D);
+    prop_child(l, lb, ub, nlb, nub, is_inf, error);
+    break;
+  case OpLog10:
+    lb = widen_lo(pow_chk(10.0, lb_, error), D); ub = widen_hi(pow_chk(10.0, ub_, error), D);
+    prop_child(l, lb, ub, nlb, nub, is_inf, error);
+    break;
+  case OpMinus:
+    lb = R::add_lo(lb_, nlb[r]); ub = R::add_hi(ub_, nub[r]);
+    prop_child(l, lb, ub, nlb, nub, is_inf, error);
+    lb = R::sub_lo(nlb[l], ub_); ub = R::sub_hi(nub[l], lb_);
+    prop_child(r, lb, ub, nlb, nub, is_inf, error);
+    break;
+  case OpMult:
+    bounds_on_div<R>(lb_, ub_, nlb[r], nub[r], lb, ub);
+    prop_child(l, lb, ub, nlb, nub, is_inf, error);
+    bounds_on_div<R>(lb_, ub_, nlb[l], nub[l], lb, ub);
+    prop_child(r, lb, ub, nlb, nub, is_inf, error);
+    break;
+  case OpPlus:
+    lb = R::sub_lo(lb_, nub[r]); ub = R::sub_hi(ub_, nlb[r]);
+    prop_child(l, lb, ub, nlb, nub, is_inf, error);
+    lb = R::sub_lo(lb_, nub[l]); ub = R::sub_hi(ub_, nlb[l]);
+    prop_child(r, lb, ub, nlb, nub, is_inf, error);
+    break;
+  case OpPowK: {
+    const double k = t.cn[r];                       // r_->val_
+    if (k > 0) {
+      if (is_int_val(k / 2.0)) {
+        if (ub_ < -1e-12) error = 3141;
+        else {
+          ub = widen_hi(pow_chk(ub_, 1.0 / k, error), D); lb = -ub;
+          prop_child(l, lb, ub, nlb, nub, is_inf, error);
+        }
+      } else if (is_int_val((k + 1) / 2.0)) {
+        // the reference tests the LOCALS (lb = -inf, ub = +inf), CNode.cpp:1377-1386
+        lb = -pow_chk(-lb_, 1.0 / k, error);
+        ub = pow_chk(ub_, 1.0 / k, error);
+        lb = widen_lo(lb, D); ub = widen_hi(ub, D);
+        prop_child(l, lb, ub, nlb, nub, is_inf, error);
+      }
+    }
+  } break;
+  case OpSqr:    // local ub = +inf: a no-op in the reference, CNode.cpp:1399-1403
+    prop_child(l, -INFINITY, INFINITY, nlb, nub, is_inf, error);
+    break;
+  case OpSqrt:   // local lb = -inf: only child >= 0 is ever derived, CNode.cpp:1404-1412
+    if (ub_ < 0.0) is_inf = true;
+    else prop_child(l, 0.0, INFINITY, nlb, nub, is_inf, error);
+    break;
+  case OpSumList: {   // CNode.cpp:1413-1481, including the tub = -inf defect at :1471-1473
+    bool inf_lb = false, inf_ub = false;
+    const int c0 = t.a0[i], c1 = t.a1[i];
+    lb = 0.0;
+    for (int c = c0; c < c1; ++c) {
+      const double cl = nlb[t.child[c]];
+      if (cl > -INFINITY) lb = R::add_lo(lb, cl); else if (inf_lb) { lb = -INFINITY; break; } else inf_lb = true;
+    }
+    ub = 0.0;
+    for (int c = c0; c < c1; ++c) {
+      const double cu = nub[t.child[c]];
+      if (cu < INFINITY) ub = R::add_hi(ub, cu); else if (inf_ub) { ub = INFINITY; break; } else inf_ub = true;
+    }
+    if (lb > -INFINITY || ub < INFINITY) {
+      for (int c = c0; c < c1; ++c) {
+        const int ch = t.child[c];
+        double tlb, tub;
+        if (ub < INFINITY) {
+          if (!inf_ub) tlb = R::sub_lo(lb_, R::sub_hi(ub, nub[ch]));
+          else if (nub[ch] < INFINITY) tlb = -INFINITY;
+          else tlb = R::sub_lo(lb_, ub);
+        } else tlb = -INFINITY;
+        if (lb > -INFINITY) {
+          if (!inf_lb) tub = R::sub_hi(ub_, R::sub_lo(lb, nlb[ch]));
+          else if (nlb[ch] > -INFINITY) tub = INFINITY;
+          else tub = R::sub_hi(ub_, lb);
+        } else tub = -INFINITY;
+        prop_child(ch, tlb, tub, nlb, nub, is_inf, error);
+        if (is_inf) break;
+      }
+    }
+  } break;
+  case OpUMinus: prop_child(l, -ub_, -lb_, nlb, nub, is_inf, error); break;
+  default: break;      // unimplemented in the reference: no-op
+  }
+}
+
+__device__ __forceinline__ bool is_leaf_op(int op) { return op == OpVar || op == OpNum || op == OpInt; }
+
+__device__ __forceinline__ TapeView open_tape(const NlDev &N, int c)
+{
+  const int b = __ldg(N.tape_ptr + c);
+  TapeView t;
+  t.op = N.op + b; t.a0 = N.arg0 + b; t.a1 = N.arg1 + b; t.cn = N.cnst + b; t.child = N.child;
+  t.nn = __ldg(N.tape_ptr + c + 1) - b;
+  return t;
+}
+
+// LinearFunction::computeBounds of the constraint's linear part (LinearFunction.cpp:178-195)
+template <class R>
+__device__ __forceinline__ void lin_part_bounds(const NlDev &N, int c, const double2 *bx, int64_t ld, double &lo,
+                                                double &up)
+{
+  lo = 0.0; up = 0.0;
+  for (int q = __ldg(N.lin_ptr + c); q < __ldg(N.lin_ptr + c + 1); ++q) {
+    const double a = __ldg(N.lin_val + q);
+    const double2 b = bx[(int64_t)__ldg(N.lin_col + q) * ld];
+    if (a > 0) { lo = R::add_lo(lo, R::mul_lo(a, b.x)); up = R::add_hi(up, R::mul_hi(a, b.y)); }
+    else       { lo = R::add_lo(lo, R::mul_lo(a, b.y)); up = R::add_hi(up, R::mul_hi(a, b.x)); }
+  }
+}
+
+// NlPresHandler::chkRed_ for one constraint (NlPresHandler.cpp:101-208, nlf branch):
+// returns 0 ok, 3 infeasible, 4 evaluation error
+template <class R>
+__device__ __forceinline__ int nl_chk_red(const NlDev &N, int c, const double2 *bx, int64_t ld, double *nlb, double *nub)
+{
+  const TapeView t = open_tape(N, c);
+  int error = 0;
+  for (int i = 0; i < t.nn; ++i) node_forward<R>(t, i, nlb, nub, bx, ld, error);
+  if (error != 0) return 4;
+  double lfl, lfu;
+  lin_part_bounds<R>(N, c, bx, ld, lfl, lfu);
+  const double impl_lb = R::add_lo(nlb[t.nn - 1], lfl), impl_ub = R::add_hi(nub[t.nn - 1], lfu);
+  if (impl_ub + 1e-6 < __ldg(N.c_lb + c) || impl_lb - 1e-6 > __ldg(N.c_ub + c)) return 3;
+  return 0;
+}
+
+// NlPresHandler::varBndsFromCons_ for one constraint (NlPresHandler.cpp:1771-1803) = lf bounds +
+// CGraph::varBoundMods + in-place application of the mods.  returns 0 ok, 3 infeasible, 4 error;
+// n_mods receives the number of bound changes.
+template <class R>
+__device__ __forceinline__ int nl_var_bound_mods(const NlDev &N, int c, double2 *bx, int64_t ld, double *nlb,
+                                                 double *nub, int &n_mods, unsigned &moved_int)
+{
+  const double bslack = 1e-5, bslack10 = 1e-4;
+  const TapeView t = open_tape(N, c);
+  double lfl, lfu;
+  lin_part_bounds<R>(N, c, bx, ld, lfl, lfu);
+  const double ub_in = R::sub_hi(__ldg(N.c_ub + c), lfl), lb_in = R::sub_lo(__ldg(N.c_lb + c), lfu);
+  int error = 0;
+  for (int i = 0; i < t.nn; ++i) node_forward<R>(t, i, nlb, nub, bx, ld, error);
+  if (error > 0) return 4;
+  const int o = t.nn - 1;
+  nlb[o] = fmax(lb_in, nlb[o]); nub[o] = fmin(ub_in, nub[o]);
+  bool is_inf = false;
+  for (int i = t.nn - 1; i >= 0; --i) {
+    if (is_leaf_op(t.op[i])) continue;               // leaves are not in dq_
+    node_reverse<R>(t, i, nlb, nub, is_inf, error);
+    if (is_inf) return 3;
+    if (error > 0) return 4;
+  }
+  (void)moved_int;
+  for (int i = 0; i < t.nn; ++i) {
+    if (t.op[i] != OpVar) continue;
+    double2 *pb = bx + (int64_t)t.a0[i] * ld;
+    double2 b = *pb;
+    bool ch = false;
+    // both tests read the variable's bounds before any mod of this call is applied
+    if (nlb[i] > b.x + bslack10) { b.x = nlb[i] - bslack; ++n_mods; ch = true; }
+    if (nub[i] < pb->y - bslack10) { b.y = nub[i] + bslack; ++n_mods; ch = true; }
+    if (ch) *pb = b;
+  }
+  return 0;
+}
+
+}  // namespace mntr

@@ -11,20 +11,19 @@ namespace mntr {
 // (Variable.h:164-191) for the bFlag propagation of LinearHandler::changeBFlag_ (:1229-1234).
 struct LinDev {
   int32_t m, n;
-  const int32_t *row_ptr;   // [m+1] padded offsets (even)
-  const int32_t *col;       // [nnz_padded]
+  const int2    *row_info;  // [m] {first entry (even), true term count; count < 0 marks a deleted row}
+  const double2 *row_bnd;   // [m] {row lb, row ub}
+  const int32_t *col;       // [nnz_padded]  a row occupies entries [beg, beg + roundup2(count))
   const double  *val;       // [nnz_padded]
-  const int32_t *row_nnz;   // [m] true term count
-  const double  *row_lb;    // [m]
-  const double  *row_ub;    // [m]
   const uint8_t *var_type;  // [n]
-  const uint8_t *row_active;// [m] 1 = active
   const int32_t *csc_ptr;   // [n+1]
   const int32_t *csc_row;   // [nnz]
   // wavefront schedule of the reference's index-ordered in-place sweep
   int32_t n_levels;
   const int32_t *level_ptr; // [n_levels+1] ranges of STORED rows (rows are stored in level order)
 };
+
+__device__ __forceinline__ int row_end(int2 info) { return info.x + ((info.y + 1) & ~1); }
 
 // CGraph tapes (see include/mntr_gpu.h for the node order contract)
 struct NlDev {
@@ -39,8 +38,7 @@ struct NlDev {
   const double  *c_lb, *c_ub;
   int32_t max_nodes;        // longest tape
   int32_t n_levels;
-  const int32_t *level_ptr; // [n_levels+1]
-  const int32_t *level_con; // [n_cons] constraints sorted by (level, index)
+  const int32_t *level_ptr; // [n_levels+1] ranges of STORED constraints (stored in level order)
 };
 
 // workspace of the single-box Jacobi fixpoint kernel

@@ -28,6 +28,7 @@
 //            variables moved) or fixpoint.
 // Deviation, deliberate: an activity-infeasible row yields verdict MNTR_INFEAS_ROW and stops
 // that box; the reference's node mode drops that status (:1631).
+#include "cgraph.cuh"
 #include "device_problem.cuh"
 #include "kernels.h"
 
@@ -222,13 +223,15 @@ __device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx,
                                             uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane,
                                             unsigned long long &my_nnz)
 {
-  const int beg = __ldg(P.row_ptr + i), end = __ldg(P.row_ptr + i + 1);
-  const double rl = __ldg(P.row_lb + i), ru = __ldg(P.row_ub + i);
+  const int2 info = __ldg(P.row_info + i);
+  const int beg = info.x, end = row_end(info);
+  const double2 bnd = __ldg(P.row_bnd + i);
+  const double rl = bnd.x, ru = bnd.y;
   double ll, uu, sing_ll = -INFINITY, sing_uu = INFINITY;
   row_activity<R>(P, beg, end, bx, ld, mine, lane, ll, uu);
   bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
   if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
-  if (mine) my_nnz += (unsigned long long)__ldg(P.row_nnz + i);
+  if (mine) my_nnz += (unsigned long long)info.y;
   if (mine && (ll > ru + kETol || uu < rl - kETol)) {       // :994-1015
     sh.verdict[lane] = 2;  /* MNTR_INFEAS_ROW */
     mine = false;
@@ -285,41 +288,30 @@ __device__ __forceinline__ void finish_var(const LinDev &P, int j, double2 b, bo
   }
 }
 
+// LinearHandler::simplePresolve (loop_mode 1) or the status-honouring fixpoint (loop_mode 0) of the
+// linear rows for the 32 boxes of this tile.  sh.verdict carries each box's verdict in and out;
+// returns (per lane) the number of sweeps its box ran.
 template <class R>
-__global__ void __launch_bounds__(kBatchThreads, 2)
-fbbt_batch_reference_kernel(LinDev P, BatchIo io, int loop_mode, int max_rounds)
+__device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, int64_t ld, uint32_t *flags,
+                                                 uint32_t *varflag, TileShared &sh, bool active, int loop_mode,
+                                                 int max_rounds, int bad_row, unsigned long long &my_nnz,
+                                                 bool &any_change)
 {
-  __shared__ TileShared sh;
-  const int tile = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int box = tile * 32 + lane;
-  const bool active = box < io.n_boxes;
-  double2 *bx = io.boxes + box;             // + j*ld addresses variable j of this lane's box
-  const int64_t ld = io.ld;
-  uint32_t *flags = io.rowflag + (int64_t)tile * P.m;
-  uint32_t *varflag = io.varflag + (int64_t)tile * P.n;
-
   // every row flagged for every box of the tile  (simplePresolve :1618-1622)
-  for (int i = threadIdx.x; i < P.m; i += kBatchThreads) __stcg(flags + i, __ldg(P.row_active + i) ? kFull : 0u);
+  for (int i = threadIdx.x; i < P.m; i += kBatchThreads) __stcg(flags + i, __ldg(P.row_info + i).y >= 0 ? kFull : 0u);
   for (int j = threadIdx.x; j < P.n; j += kBatchThreads) __stcg(varflag + j, 0u);
-  if (warp == 0) { sh.changed[lane] = 1; sh.nint[lane] = 0; sh.verdict[lane] = 0; sh.nnz[lane] = 0ull; }
-  // checkBounds_ rows part is static: a row with lb > ub + eTol makes every box infeasible
-  int bad_row = 0;
-  for (int i = threadIdx.x; i < P.m; i += kBatchThreads)
-    if (__ldg(P.row_active + i) && __ldg(P.row_lb + i) > __ldg(P.row_ub + i) + kETol) bad_row = 1;
-  bad_row = __syncthreads_or(bad_row);
+  if (warp == 0) { sh.changed[lane] = 1; sh.nint[lane] = 0; }
+  __syncthreads();
 
-  unsigned long long my_nnz = 0ull;
   int iters = 1;          // the reference's counter: starts at 1, ++ per sweep
   int my_rounds = 0;
-  int my_verdict = 0;
   for (;;) {
     // ---- loop condition per box (registers are identical in every warp of the CTA) ----
     const int changed = sh.changed[lane];
     const int nint = sh.nint[lane];
-    if (my_verdict == 0) my_verdict = sh.verdict[lane];
-    bool run = active && my_verdict == 0 && changed;
+    bool run = active && sh.verdict[lane] == 0 && changed;
     if (max_rounds > 0 && my_rounds >= max_rounds) run = false;
     if (loop_mode == 1) run = run && iters <= 10 && (iters <= 2 || nint > 0);   // :1625-1627
     const unsigned runmask = __ballot_sync(kFull, run);
@@ -394,7 +386,102 @@ fbbt_batch_reference_kernel(LinDev P, BatchIo io, int loop_mode, int max_rounds)
       }
     }
     if (bad_row && run && warp == 0 && sh.verdict[lane] == 0) sh.verdict[lane] = 1;
+    if (run && sh.changed[lane]) any_change = true;          // benign: read again after the barrier below
     __syncthreads();
+    if (run && sh.changed[lane]) any_change = true;
+  }
+  return my_rounds;
+}
+
+// NlPresHandler::simplePresolve for the 32 boxes of this tile (NlPresHandler.cpp:1022-1059, no incumbent):
+// at most two sweeps of { chkRed_ over all CGraph constraints ; varBndsFromCons_ in constraint index
+// order, in place }.  The in-place order is reproduced by wavefront levels over the constraints
+// (built at load time from the variables each constraint reads and writes).
+template <class R>
+__device__ __forceinline__ int nl_tile_presolve(const NlDev &N, double2 *bx, int64_t ld, TileShared &sh, bool active,
+                                                bool &any_change)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double nlb[kMaxTape], nub[kMaxTape];
+  if (warp == 0) sh.changed[lane] = 1;
+  __syncthreads();
+  int iters = 1, my_rounds = 0;
+  for (;;) {
+    const bool run = active && sh.verdict[lane] == 0 && sh.changed[lane] && iters <= 2;    // :1034-1035
+    const unsigned runmask = __ballot_sync(kFull, run);
+    __syncthreads();
+    if (runmask == 0) break;
+    if (warp == 0) sh.changed[lane] = 0;
+    ++iters;
+    if (run) ++my_rounds;
+    __syncthreads();
+    // chkRed_: read-only, every constraint against the box of the sweep start
+    for (int c = warp; c < N.n_cons; c += kBatchWarps) {
+      if (run && sh.verdict[lane] == 0) {
+        const int st = nl_chk_red<R>(N, c, bx, ld, nlb, nub);
+        if (st != 0) sh.verdict[lane] = st;
+      }
+    }
+    __syncthreads();
+    // varBndsFromCons_: constraints of one level touch disjoint variables
+    for (int lev = 0; lev < N.n_levels; ++lev) {
+      const int qb = __ldg(N.level_ptr + lev), qe = __ldg(N.level_ptr + lev + 1);
+      for (int c = qb + warp; c < qe; c += kBatchWarps) {
+        if (run && sh.verdict[lane] == 0) {
+          int n_mods = 0; unsigned dummy = 0;
+          const int st = nl_var_bound_mods<R>(N, c, bx, ld, nlb, nub, n_mods, dummy);
+          if (st != 0) sh.verdict[lane] = st;
+          else if (n_mods > 0) sh.changed[lane] = 1;
+        }
+      }
+      __syncthreads();
+    }
+    if (run && sh.changed[lane]) any_change = true;
+  }
+  return my_rounds;
+}
+
+// One PCBProcessor::presolveNode_ pass per box (loop_mode 1): LinearHandler::presolveNode, then -- unless
+// the box is already infeasible -- NlPresHandler::presolveNode (PCBProcessor.cpp:134-175); or (loop_mode 0)
+// that pair repeated until neither handler changes a bound.
+template <class R>
+__global__ void __launch_bounds__(kBatchThreads, 2)
+fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int max_rounds, int lin_enabled,
+                            int nl_enabled)
+{
+  __shared__ TileShared sh;
+  const int tile = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int box = tile * 32 + lane;
+  const bool active = box < io.n_boxes;
+  double2 *bx = io.boxes + box;             // + j*ld addresses variable j of this lane's box
+  const int64_t ld = io.ld;
+  uint32_t *flags = io.rowflag + (int64_t)tile * P.m;
+  uint32_t *varflag = io.varflag + (int64_t)tile * P.n;
+
+  if (warp == 0) { sh.verdict[lane] = 0; sh.nnz[lane] = 0ull; }
+  // checkBounds_ rows part is static: a row with lb > ub + eTol makes every box infeasible
+  int bad_row = 0;
+  for (int i = threadIdx.x; i < P.m; i += kBatchThreads) {
+    const double2 bnd = __ldg(P.row_bnd + i);
+    if (__ldg(P.row_info + i).y >= 0 && bnd.x > bnd.y + kETol) bad_row = 1;
+  }
+  bad_row = __syncthreads_or(bad_row);
+
+  unsigned long long my_nnz = 0ull;
+  int my_rounds = 0;
+  for (int outer = 0;; ++outer) {
+    bool lin_changed = false, nl_changed = false;
+    if (lin_enabled)
+      my_rounds += lin_tile_presolve<R>(P, bx, ld, flags, varflag, sh, active, loop_mode, max_rounds, bad_row,
+                                        my_nnz, lin_changed);
+    if (nl_enabled) my_rounds += nl_tile_presolve<R>(N, bx, ld, sh, active, nl_changed);
+    // fixpoint mode with both handlers: go round again while the nonlinear sweeps still move bounds
+    const bool again = (loop_mode == 0) && lin_enabled && nl_enabled && nl_changed && sh.verdict[lane] == 0 &&
+                       (max_rounds <= 0 || my_rounds < max_rounds) && outer < 50;
+    if (!__syncthreads_or(again)) break;
   }
 
   // ---- per-box results ----
@@ -492,13 +579,16 @@ cudaError_t launch_batch_reference(const LinDev &P, const NlDev *N, const BatchI
                                    int loop_mode, int max_rounds, int lin_enabled, int nl_enabled,
                                    cudaStream_t stream)
 {
-  (void)N; (void)lin_enabled; (void)nl_enabled;
   const int tiles = (io.n_boxes + 31) / 32;
   if (tiles <= 0) return cudaSuccess;
+  NlDev nl{};
+  if (N != nullptr && nl_enabled) nl = *N; else nl_enabled = 0;
   if (directed)
-    fbbt_batch_reference_kernel<RoundDirected><<<tiles, kBatchThreads, 0, stream>>>(P, io, loop_mode, max_rounds);
+    fbbt_batch_reference_kernel<RoundDirected><<<tiles, kBatchThreads, 0, stream>>>(P, nl, io, loop_mode, max_rounds,
+                                                                                   lin_enabled, nl_enabled);
   else
-    fbbt_batch_reference_kernel<RoundNearest><<<tiles, kBatchThreads, 0, stream>>>(P, io, loop_mode, max_rounds);
+    fbbt_batch_reference_kernel<RoundNearest><<<tiles, kBatchThreads, 0, stream>>>(P, nl, io, loop_mode, max_rounds,
+                                                                                  lin_enabled, nl_enabled);
   return cudaGetLastError();
 }
 

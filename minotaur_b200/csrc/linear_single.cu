@@ -149,19 +149,16 @@ __device__ __forceinline__ void emit_candidates(const RowCtx &rc, double a, int 
 }
 
 // pipeline registers of one row
-struct RowMeta { int i, beg, end; };                  // i < 0: nothing to do
+struct RowMeta { int i, beg, cnt; };                  // i < 0: nothing to do; cnt = true term count
 struct RowData { double2 a2; int2 c2; };              // this lane's first entry pair (a == 0: none)
 
 __device__ __forceinline__ RowMeta load_meta(const LinDev &P, const SingleWs &W, int idx, int count, bool first)
 {
-  RowMeta r; r.i = -1; r.beg = 0; r.end = 0;
+  RowMeta r; r.i = -1; r.beg = 0; r.cnt = 0;
   if (idx < count) {
     const int i = first ? idx : W.list[idx];
-    if (!first || __ldg(P.row_active + i)) {
-      r.i = i;
-      r.beg = __ldg(P.row_ptr + i);
-      r.end = __ldg(P.row_ptr + i + 1);
-    }
+    const int2 info = __ldg(P.row_info + i);
+    if (info.y >= 0) { r.i = i; r.beg = info.x; r.cnt = info.y; }   // deleted rows are never evaluated
   }
   return r;
 }
@@ -169,10 +166,10 @@ __device__ __forceinline__ RowMeta load_meta(const LinDev &P, const SingleWs &W,
 __device__ __forceinline__ RowData load_data(const LinDev &P, const RowMeta &r, int lane_g)
 {
   RowData d; d.a2 = make_double2(0.0, 0.0); d.c2 = make_int2(0, 0);
-  const int t = r.beg + 2 * lane_g;
-  if (r.i >= 0 && t < r.end) {
-    d.a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
-    d.c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
+  const int t = 2 * lane_g;
+  if (r.i >= 0 && t < r.cnt) {
+    d.a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + r.beg + t));
+    d.c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + r.beg + t));
   }
   return d;
 }
@@ -180,16 +177,18 @@ __device__ __forceinline__ RowData load_data(const LinDev &P, const RowMeta &r, 
 // one flagged row: activities, infeasibility, candidates   [linBndTighten_, Jacobi form]
 template <int G, class R>
 __device__ __forceinline__ void process_row(const LinDev &P, const SingleWs &W, const RowMeta &r, const RowData &d,
-                                            int lane_g, unsigned gmask, unsigned long long &my_nnz,
+                                            int lane_g, unsigned gmask, bool first, unsigned long long &my_nnz,
                                             unsigned long long &my_rows)
 {
   const int i = r.i;
+  const int end = r.beg + ((r.cnt + 1) & ~1);
   RowCtx rc;
-  rc.rl = __ldg(P.row_lb + i);
-  rc.ru = __ldg(P.row_ub + i);
+  const double2 bnd = __ldg(P.row_bnd + i);
+  rc.rl = bnd.x;
+  rc.ru = bnd.y;
   if (lane_g == 0) {
-    my_nnz += (unsigned long long)__ldg(P.row_nnz + i); ++my_rows;
-    atomicAnd(W.bits + (i >> 5), ~(1u << (i & 31)));       // setBFlag(false), :513
+    my_nnz += (unsigned long long)r.cnt; ++my_rows;
+    if (!first) atomicAnd(W.bits + (i >> 5), ~(1u << (i & 31)));       // setBFlag(false), :513
   }
   // pass 1: the first entry pair is already in registers, its two gathers go out together
   double2 b0 = make_double2(0.0, 0.0), b1 = b0;
@@ -198,9 +197,9 @@ __device__ __forceinline__ void process_row(const LinDev &P, const SingleWs &W, 
   double ll = 0.0, uu = 0.0;
   accumulate<R>(d.a2.x, b0, ll, uu);
   accumulate<R>(d.a2.y, b1, ll, uu);
-  const bool long_row = (r.end - r.beg) > 2 * G;           // group-uniform
+  const bool long_row = r.cnt > 2 * G;                      // group-uniform
   if (long_row) {
-    for (int t = r.beg + 2 * lane_g + 2 * G; t < r.end; t += 2 * G) {
+    for (int t = r.beg + 2 * lane_g + 2 * G; t < end; t += 2 * G) {
       const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
       const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
       if (a2.x != 0.0) accumulate<R>(a2.x, W.box[c2.x], ll, uu);
@@ -215,7 +214,7 @@ __device__ __forceinline__ void process_row(const LinDev &P, const SingleWs &W, 
   if (ll < -kInf20 || uu > kInf20) {
     double fs_lo = 0.0, fs_hi = 0.0;
     int ninf_lo = 0, ninf_hi = 0;
-    for (int t = r.beg + 2 * lane_g; t < r.end; t += 2 * G) {
+    for (int t = r.beg + 2 * lane_g; t < end; t += 2 * G) {
       const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
       const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
 #pragma unroll
@@ -260,7 +259,7 @@ __device__ __forceinline__ void process_row(const LinDev &P, const SingleWs &W, 
   if (d.a2.x != 0.0) emit_candidates<R>(rc, d.a2.x, d.c2.x, b0, W.nbox);
   if (d.a2.y != 0.0) emit_candidates<R>(rc, d.a2.y, d.c2.y, b1, W.nbox);
   if (long_row) {
-    for (int t = r.beg + 2 * lane_g + 2 * G; t < r.end; t += 2 * G) {
+    for (int t = r.beg + 2 * lane_g + 2 * G; t < end; t += 2 * G) {
       const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
       const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
       if (a2.x != 0.0) emit_candidates<R>(rc, a2.x, c2.x, W.box[c2.x], W.nbox);
@@ -296,8 +295,10 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
     W.box[j] = b;
     W.nbox[j] = b;
   }
-  for (int i = tid; i < P.m; i += nthreads)
-    if (__ldg(P.row_active + i) && __ldg(P.row_lb + i) > __ldg(P.row_ub + i) + kETol) infeasible0 = 1;  // checkBounds_, rows
+  for (int i = tid; i < P.m; i += nthreads) {
+    const double2 bnd = __ldg(P.row_bnd + i);
+    if (__ldg(P.row_info + i).y >= 0 && bnd.x > bnd.y + kETol) infeasible0 = 1;   // checkBounds_, rows
+  }
   for (int w = tid; w < (P.m + 31) / 32; w += nthreads) W.bits[w] = 0u;
   if (infeasible0) W.status[0] = 1 /* MNTR_INFEAS_BOUNDS */;
   MNTR_TRACE();
@@ -326,7 +327,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
       for (int idx = group; idx < count; idx += n_groups) {
         const RowData dB = load_data(P, mB, lane_g);                          // entries of the next row
         const RowMeta mA = load_meta(P, W, idx + 2 * n_groups, count, first); // ids of the one after
-        if (mC.i >= 0) process_row<G, R>(P, W, mC, dC, lane_g, gmask, my_nnz, my_rows);
+        if (mC.i >= 0) process_row<G, R>(P, W, mC, dC, lane_g, gmask, first, my_nnz, my_rows);
         mC = mB; dC = dB; mB = mA;
       }
     }

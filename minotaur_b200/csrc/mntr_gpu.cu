@@ -15,6 +15,7 @@
 #include <new>
 #include <vector>
 
+#include "cgraph.cuh"
 #include "device_problem.cuh"
 #include "kernels.h"
 
@@ -152,6 +153,8 @@ mntr_gpu_options resolve_opts(const mntr_gpu_options *o, int32_t n_boxes)
   r.order = (n_boxes == 1) ? MNTR_ORDER_JACOBI : MNTR_ORDER_REFERENCE;
   r.loop = MNTR_LOOP_FIXPOINT;
   r.max_rounds = 0;
+  r.handlers = MNTR_HANDLERS_ALL;
+  r.reserved[0] = r.reserved[1] = r.reserved[2] = 0;
   if (o) {
     r = *o;
     if (r.order < 0) r.order = (n_boxes == 1) ? MNTR_ORDER_JACOBI : MNTR_ORDER_REFERENCE;
@@ -290,18 +293,20 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   }
 
   // ---- padded CSR in stored order: row starts at even entries (128-bit val / 64-bit col loads) ----
-  std::vector<int32_t> prow(m + 1, 0), pcol, rnnz(m, 0);
-  std::vector<double> pval, prl(m), pru(m);
-  std::vector<uint8_t> ract(m, 1);
+  std::vector<int32_t> prow(m + 1, 0), pcol;
+  std::vector<double> pval;
+  std::vector<int2> pinfo((size_t)std::max(m, 1));
+  std::vector<double2> pbnd((size_t)std::max(m, 1));
   pcol.reserve((size_t)nnz + m); pval.reserve((size_t)nnz + m);
   for (int32_t q = 0; q < m; ++q) {
     const int32_t i = perm[q];
     prow[q] = (int32_t)pcol.size();
     for (int32_t t = cptr0[i]; t < cptr0[i + 1]; ++t) { pcol.push_back(ccol[t]); pval.push_back(cval[t]); }
-    rnnz[q] = cptr0[i + 1] - cptr0[i];
+    const int32_t cnt = cptr0[i + 1] - cptr0[i];
     if (pcol.size() & 1) { pcol.push_back(pcol.back()); pval.push_back(0.0); }
-    ract[q] = (row_active && !row_active[i]) ? 0 : 1;
-    prl[q] = row_lb[i]; pru[q] = row_ub[i];
+    const bool deleted = row_active && !row_active[i];
+    pinfo[q] = make_int2(prow[q], deleted ? -1 : cnt);
+    pbnd[q] = make_double2(row_lb[i], row_ub[i]);
   }
   prow[m] = (int32_t)pcol.size();
 
@@ -318,14 +323,11 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   L = LinDev{};
   L.m = m; L.n = n; L.n_levels = n_levels;
   int rc;
-  if ((rc = dev_upload(ctx, ctx->lin_allocs, prow.data(), prow.size(), &L.row_ptr))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, pinfo.data(), (size_t)m, &L.row_info))) return rc;
+  if ((rc = dev_upload(ctx, ctx->lin_allocs, pbnd.data(), (size_t)m, &L.row_bnd))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pcol.data(), pcol.size(), &L.col))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pval.data(), pval.size(), &L.val))) return rc;
-  if ((rc = dev_upload(ctx, ctx->lin_allocs, rnnz.data(), rnnz.size(), &L.row_nnz))) return rc;
-  if ((rc = dev_upload(ctx, ctx->lin_allocs, prl.data(), (size_t)m, &L.row_lb))) return rc;
-  if ((rc = dev_upload(ctx, ctx->lin_allocs, pru.data(), (size_t)m, &L.row_ub))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, var_type, (size_t)n, &L.var_type))) return rc;
-  if ((rc = dev_upload(ctx, ctx->lin_allocs, ract.data(), ract.size(), &L.row_active))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, cptr.data(), (size_t)n + 1, &L.csc_ptr))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, crow.data(), (size_t)nnz, &L.csc_row))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, lptr.data(), (size_t)n_levels + 1, &L.level_ptr))) return rc;
@@ -364,13 +366,107 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   return MNTR_OK;
 }
 
-int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *, const uint8_t *, const int32_t *,
-                         const int32_t *, const double *, const int32_t *, const int32_t *, const int32_t *,
-                         const double *, const double *, const double *)
+int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_ptr, const uint8_t *op,
+                         const int32_t *arg0, const int32_t *arg1, const double *cnst, const int32_t *child,
+                         const int32_t *lin_ptr, const int32_t *lin_col, const double *lin_val, const double *c_lb,
+                         const double *c_ub)
 {
   if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "load_cgraph: call load_linear first (m may be 0)");
+  CU(cudaSetDevice(ctx->device));
+  free_all(ctx->nl_allocs);
+  ctx->nl_loaded = false;
   if (n_cons == 0) return MNTR_OK;
-  return fail(ctx, MNTR_E_UNSUPPORTED, "load_cgraph: CGraph tapes are not implemented yet");
+  if (n_cons < 0 || !tape_ptr || !op || !arg0 || !arg1 || !cnst || !lin_ptr || !c_lb || !c_ub)
+    return fail(ctx, MNTR_E_ARG, "load_cgraph: null or negative argument");
+  const int32_t n = ctx->n;
+
+  // ---- validate, and collect the variables each constraint reads / writes ----
+  std::vector<int32_t> level(n_cons, 0), lastW(n, -1), lastR(n, -1);
+  int32_t n_levels = 0, max_nodes = 0;
+  for (int32_t c = 0; c < n_cons; ++c) {
+    const int32_t b = tape_ptr[c], nn = tape_ptr[c + 1] - b;
+    if (nn < 1 || nn > kMaxTape)
+      return fail(ctx, MNTR_E_UNSUPPORTED, "load_cgraph: constraint %d has %d tape nodes (supported: 1..%d)", c, nn, kMaxTape);
+    max_nodes = std::max(max_nodes, nn);
+    int32_t lev = 0;
+    for (int32_t i = 0; i < nn; ++i) {
+      const int o = op[b + i];
+      if (o > OpVar) return fail(ctx, MNTR_E_ARG, "load_cgraph: bad opcode %d in constraint %d", o, c);
+      if (o == OpVar) {
+        const int32_t v = arg0[b + i];
+        if (v < 0 || v >= n) return fail(ctx, MNTR_E_ARG, "load_cgraph: variable %d out of range in constraint %d", v, c);
+        lev = std::max(lev, std::max(lastW[v], lastR[v]) + 1);     // the tape's variables are read AND written
+      } else if (o == OpNum || o == OpInt) {
+      } else if (o == OpSumList) {
+        if (!child || arg0[b + i] < 0 || arg1[b + i] < arg0[b + i])
+          return fail(ctx, MNTR_E_ARG, "load_cgraph: bad child list in constraint %d", c);
+        for (int32_t q = arg0[b + i]; q < arg1[b + i]; ++q)
+          if (child[q] < 0 || child[q] >= i) return fail(ctx, MNTR_E_ARG, "load_cgraph: child after parent in constraint %d", c);
+      } else {
+        if (arg0[b + i] < 0 || arg0[b + i] >= i || arg1[b + i] >= i)
+          return fail(ctx, MNTR_E_ARG, "load_cgraph: operand after operator in constraint %d", c);
+      }
+    }
+    if (op[b + nn - 1] == OpVar || op[b + nn - 1] == OpNum || op[b + nn - 1] == OpInt)
+      return fail(ctx, MNTR_E_ARG, "load_cgraph: constraint %d has no operator node", c);
+    for (int32_t q = lin_ptr[c]; q < lin_ptr[c + 1]; ++q) {
+      const int32_t v = lin_col[q];
+      if (v < 0 || v >= n) return fail(ctx, MNTR_E_ARG, "load_cgraph: linear column out of range in constraint %d", c);
+      lev = std::max(lev, lastW[v] + 1);                            // the linear part is only read
+    }
+    // wavefront level of the in-place, index-ordered sweep (NlPresHandler.cpp:1686-1806): after every
+    // earlier constraint that writes something this one touches, or reads something this one writes
+    level[c] = lev;
+    for (int32_t i = 0; i < nn; ++i)
+      if (op[b + i] == OpVar) { lastW[arg0[b + i]] = lev; lastR[arg0[b + i]] = std::max(lastR[arg0[b + i]], lev); }
+    for (int32_t q = lin_ptr[c]; q < lin_ptr[c + 1]; ++q) lastR[lin_col[q]] = std::max(lastR[lin_col[q]], lev);
+    n_levels = std::max(n_levels, lev + 1);
+  }
+
+  // ---- store the constraints in (level, index) order ----
+  std::vector<int32_t> lptr(n_levels + 2, 0), perm(n_cons);
+  for (int32_t c = 0; c < n_cons; ++c) lptr[level[c] + 2]++;
+  for (int32_t l = 0; l < n_levels; ++l) lptr[l + 2] += lptr[l + 1];
+  for (int32_t c = 0; c < n_cons; ++c) perm[lptr[level[c] + 1]++] = c;
+  std::vector<int32_t> tp(n_cons + 1, 0), lp(n_cons + 1, 0), a0v, a1v, chv, lcv;
+  std::vector<uint8_t> opv;
+  std::vector<double> cnv, lvv, clb(n_cons), cub(n_cons);
+  for (int32_t q = 0; q < n_cons; ++q) {
+    const int32_t c = perm[q], b = tape_ptr[c], nn = tape_ptr[c + 1] - b;
+    for (int32_t i = 0; i < nn; ++i) {
+      opv.push_back(op[b + i]); cnv.push_back(cnst[b + i]);
+      if (op[b + i] == OpSumList) {
+        a0v.push_back((int32_t)chv.size());
+        for (int32_t k = arg0[b + i]; k < arg1[b + i]; ++k) chv.push_back(child[k]);
+        a1v.push_back((int32_t)chv.size());
+      } else { a0v.push_back(arg0[b + i]); a1v.push_back(arg1[b + i]); }
+    }
+    tp[q + 1] = (int32_t)opv.size();
+    for (int32_t k = lin_ptr[c]; k < lin_ptr[c + 1]; ++k) { lcv.push_back(lin_col[k]); lvv.push_back(lin_val[k]); }
+    lp[q + 1] = (int32_t)lcv.size();
+    clb[q] = c_lb[c]; cub[q] = c_ub[c];
+  }
+
+  NlDev &N = ctx->nl;
+  N = NlDev{};
+  N.n_cons = n_cons; N.max_nodes = max_nodes; N.n_levels = n_levels;
+  int rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, tp.data(), tp.size(), &N.tape_ptr))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, opv.data(), opv.size(), &N.op))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, a0v.data(), a0v.size(), &N.arg0))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, a1v.data(), a1v.size(), &N.arg1))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, cnv.data(), cnv.size(), &N.cnst))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, chv.data(), chv.size(), &N.child))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, lp.data(), lp.size(), &N.lin_ptr))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, lcv.data(), lcv.size(), &N.lin_col))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, lvv.data(), lvv.size(), &N.lin_val))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, clb.data(), clb.size(), &N.c_lb))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, cub.data(), cub.size(), &N.c_ub))) return rc;
+  if ((rc = dev_upload(ctx, ctx->nl_allocs, lptr.data(), (size_t)n_levels + 1, &N.level_ptr))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->nl_loaded = true;
+  return MNTR_OK;
 }
 
 int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *, const double *, double)
@@ -521,7 +617,8 @@ int mntr_gpu_tighten_dev(mntr_gpu_ctx *ctx, int32_t n_boxes, void *boxes_dev, co
   (void)tiles;
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
-                            o.loop, o.max_rounds, 1, ctx->nl_loaded ? 1 : 0, ctx->stream));
+                            o.loop, o.max_rounds, o.handlers != MNTR_HANDLERS_NONLINEAR,
+                            (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR) ? 1 : 0, ctx->stream));
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->stats = mntr_gpu_stats{};
@@ -542,8 +639,10 @@ int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
   ctx->stats = mntr_gpu_stats{};
   const int32_t n = ctx->n;
 
+  if (o.handlers < 0 || o.handlers > 2) return fail(ctx, MNTR_E_ARG, "tighten: bad handlers");
   if (o.order == MNTR_ORDER_JACOBI) {
-    if (ctx->nl_loaded) return fail(ctx, MNTR_E_UNSUPPORTED, "tighten: CGraph tapes need MNTR_ORDER_REFERENCE");
+    if (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR)
+      return fail(ctx, MNTR_E_UNSUPPORTED, "tighten: CGraph tapes need MNTR_ORDER_REFERENCE");
     for (int32_t b = 0; b < n_boxes; ++b) {
       int rc = tighten_single(ctx, lb + (int64_t)b * n, ub + (int64_t)b * n, o, verdict ? verdict + b : nullptr,
                               rounds ? rounds + b : nullptr, nnz_updates ? nnz_updates + b : nullptr);
@@ -563,7 +662,8 @@ int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
   io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb;
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
-                            o.loop, o.max_rounds, 1, ctx->nl_loaded ? 1 : 0, ctx->stream));
+                            o.loop, o.max_rounds, o.handlers != MNTR_HANDLERS_NONLINEAR,
+                            (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR) ? 1 : 0, ctx->stream));
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   if ((rc = mntr_gpu_boxes_download(ctx, n_boxes, ctx->d_boxes, lb, ub))) return rc;
   std::vector<int32_t> hv(n_boxes), hr(n_boxes);

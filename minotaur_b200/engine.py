@@ -27,6 +27,7 @@ ROUND_DIRECTED, ROUND_NEAREST = 0, 1
 ORDER_JACOBI, ORDER_REFERENCE, ORDER_AUTO = 0, 1, -1
 LOOP_FIXPOINT, LOOP_SIMPLEPRESOLVE = 0, 1
 FEASIBLE, INFEAS_BOUNDS, INFEAS_ROW, INFEAS_NL, ERROR_NL = 0, 1, 2, 3, 4
+HANDLERS_ALL, HANDLERS_LINEAR, HANDLERS_NONLINEAR = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -44,7 +45,8 @@ ABI_SYMBOLS = [
 
 
 class GpuOptions(C.Structure):
-    _fields_ = [("rounding", C.c_int32), ("order", C.c_int32), ("loop", C.c_int32), ("max_rounds", C.c_int32)]
+    _fields_ = [("rounding", C.c_int32), ("order", C.c_int32), ("loop", C.c_int32), ("max_rounds", C.c_int32),
+                ("handlers", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class GpuStats(C.Structure):
@@ -181,7 +183,7 @@ class GpuBoundEngine:
 
     # -- the hot path --
     def tighten(self, lb, ub, rounding=ROUND_DIRECTED, order=ORDER_AUTO, loop=LOOP_FIXPOINT, max_rounds=0,
-                inplace=False) -> TightenResult:
+                inplace=False, handlers=HANDLERS_ALL) -> TightenResult:
         """lb/ub: [n] or box-major [n_boxes, n] float64 host arrays."""
         lb = np.asarray(lb, np.float64); ub = np.asarray(ub, np.float64)
         if not inplace or not lb.flags.c_contiguous or not ub.flags.c_contiguous:
@@ -190,7 +192,7 @@ class GpuBoundEngine:
         nb = 1 if single else lb.shape[0]
         if lb.shape[-1] != self.n or ub.shape != lb.shape:
             raise ValueError("box shape does not match the loaded problem")
-        o = GpuOptions(rounding, order, loop, max_rounds)
+        o = GpuOptions(rounding, order, loop, max_rounds, handlers)
         v = np.zeros(nb, np.int32); r = np.zeros(nb, np.int32); z = np.zeros(nb, np.int64)
         self._check(self.L.mntr_gpu_tighten(self.h, nb, _d(lb), _d(ub), C.byref(o), _i(v), _i(r), _l(z)), "tighten")
         st = self.stats()

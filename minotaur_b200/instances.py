@@ -370,7 +370,8 @@ def make_minlp(n: int, n_cons: int, m_lin: int, seed: int = 99, name: str = "min
     ``c_lb <= x_i*x_j + a*x_k <= c_ub`` (tape Var,Var,Mult + linear part), 50 %
     ``x_i^2 + x_j^2 <= r`` as SumList(Sqr,Sqr); plus ``m_lin`` linear rows; planted point."""
     rng = np.random.default_rng(seed)
-    lo = -rng.integers(0, 11, size=n).astype(np.float64)
+    lo = 0.0 - rng.integers(0, 11, size=n).astype(np.float64)   # 0.0 - 0 = +0.0 (a -0.0 lower bound trips the
+    # reference's BoundsOnRecip: 1/-0.0 = -inf, Operations.cpp:208-211)
     hi = rng.integers(1, 11, size=n).astype(np.float64)
     is_int = rng.random(n) < 0.3
     var_type = np.where(is_int, INTEGER, CONTINUOUS).astype(np.uint8)

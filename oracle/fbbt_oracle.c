@@ -420,6 +420,11 @@ void orc_lin_fixpoint_jacobi(const orc_lin_t *p, double *lb, double *ub, int32_t
  *                         interval helpers (Operations.cpp)
  * ========================================================================= */
 
+/* std::min / std::max exactly as the reference uses them (first argument wins ties, so the sign of
+ * a zero is preserved the way libstdc++ does) */
+#define STD_MIN(a, b) (((b) < (a)) ? (b) : (a))
+#define STD_MAX(a, b) (((a) < (b)) ? (b) : (a))
+
 /* ref: Operations.cpp:117-179 */
 void orc_bounds_on_product(int zero_x_inf_zero, double l0, double u0, double l1, double u1,
                            double *lb, double *ub)
@@ -442,11 +447,11 @@ void orc_bounds_on_product(int zero_x_inf_zero, double l0, double u0, double l1,
     prod = l0 * l1; if (isnan(prod)) prod = -INFINITY;
     l = prod; u = prod;
     prod = u0 * l1; if (isnan(prod)) prod = INFINITY;
-    l = fmin(l, prod) ; u = fmax(u, prod);
+    l = STD_MIN(l, prod); u = STD_MAX(u, prod);
     prod = u0 * u1; if (isnan(prod)) prod = -INFINITY;
-    l = fmin(l, prod); u = fmax(u, prod);
+    l = STD_MIN(l, prod); u = STD_MAX(u, prod);
     prod = l0 * u1; if (isnan(prod)) prod = INFINITY;
-    l = fmin(l, prod); u = fmax(u, prod);
+    l = STD_MIN(l, prod); u = STD_MAX(u, prod);
     *lb = l; *ub = u;
   }
 }
@@ -474,7 +479,7 @@ void orc_bounds_on_square(double l1, double u1, double *lb, double *ub)
 {
   if (u1 < 0.) { *lb = u1 * u1; *ub = l1 * l1; }
   else if (l1 > 0.) { *lb = l1 * l1; *ub = u1 * u1; }
-  else { *lb = 0.; *ub = fmax(l1 * l1, u1 * u1); }
+  else { double p = l1 * l1, q = u1 * u1; *lb = 0.; *ub = STD_MAX(p, q); }
 }
 
 /* ref: Operations.cpp:80-83 */
