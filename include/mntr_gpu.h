@@ -95,8 +95,14 @@ typedef struct {
   int32_t loop;         /* MNTR_LOOP_*   */
   int32_t max_rounds;   /* 0 = no extra cap */
   int32_t handlers;     /* MNTR_HANDLERS_* */
-  int32_t reserved[3];  /* must be 0 */
+  int32_t flags;        /* MNTR_FLAG_* */
+  int32_t reserved[2];  /* must be 0 */
 } mntr_gpu_options;
+
+/* Single-box Jacobi with one kernel launch per phase and the host reading the change flag between rounds
+ * (the kernels of the row-partitioned multi-GPU mode) instead of the single cooperative launch.  Always on
+ * when a communicator is attached; this flag selects it on one GPU too. */
+#define MNTR_FLAG_PER_ROUND_KERNELS 1
 
 /* per-call statistics (LinPresolveStats / NlPresStats counterparts, LinearHandler.h:22-36) */
 typedef struct {
@@ -108,6 +114,8 @@ typedef struct {
   int32_t reserved;
   double  kernel_ms;     /* device time of the tighten kernels (CUDA events) */
   double  h2d_ms, d2h_ms;
+  double  comm_ms;       /* device time of the per-round NCCL bound all-reduces (row-partitioned mode) */
+  double  rows_ms, vars_ms; /* per-round kernels of the row-partitioned mode */
 } mntr_gpu_stats;
 
 /* ---- lifetime -------------------------------------------------------------------- */

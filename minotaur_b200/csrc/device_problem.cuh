@@ -55,4 +55,15 @@ struct SingleWs {
   unsigned long long *trace;     // [64] optional phase timestamps (globaltimer ns), or nullptr
 };
 
+// workspace of the per-round kernels (row-partitioned multi-GPU mode)
+struct RoundsWs {
+  double2 *box;    // [n] {lb, ub} of the round start (replicated on every rank)
+  double *nlb;     // [n+1] lower-bound candidates (all-reduced with MAX); [n] = row-infeasible flag
+  double *nub;     // [n]   upper-bound candidates (all-reduced with MIN)
+  uint32_t *bits;  // [(m+31)/32] this rank's rows on the next work list
+  int32_t *list;   // [m] work list
+  int32_t *ctrl;   // [8] [0] changed [1] int moved [2] next list length [3] verdict [4] changed pairs
+  unsigned long long *counters;  // [2] nnz_updates, rows evaluated (this rank)
+};
+
 }  // namespace mntr

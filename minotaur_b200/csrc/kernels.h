@@ -13,6 +13,15 @@ cudaError_t launch_single_jacobi(const LinDev &P, const SingleWs &W, double *lb_
                                  int lanes_per_row, bool directed, int max_rounds, int loop_mode,
                                  int sm_count, cudaStream_t stream);
 
+// K5 (linear_rounds.cu): one Jacobi round as separate launches (row-partitioned multi-GPU mode)
+cudaError_t launch_rounds_init(const LinDev &P, const RoundsWs &W, const double *lb_dev, const double *ub_dev,
+                               int sm_count, cudaStream_t stream);
+cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per_row, bool directed, int count,
+                               int first, int sm_count, cudaStream_t stream);
+cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream);
+cudaError_t launch_rounds_finish(const LinDev &P, const RoundsWs &W, double *lb_dev, double *ub_dev, int sm_count,
+                                 cudaStream_t stream);
+
 // per-box outputs / controls of the batched kernels
 struct BatchIo {
   double2 *boxes;        // [n][ld] {lb,ub}, node-minor

@@ -1,0 +1,202 @@
+// linear_rounds.cu -- K5: one Jacobi round of the linear rows as separate launches, for the
+// row-partitioned multi-GPU mode.  Every rank holds ITS block of rows (all n columns) and a full
+// replica of the box:
+//   rows kernel  : this rank's flagged rows -> candidate bounds, atomically merged into nlb / nub
+//   (host)       : NCCL all-reduce over NVLink, MAX on nlb[0..n] and MIN on nub[0..n), grouped into one
+//                  operation; slot nlb[n] carries the "a row is activity-infeasible" flag
+//   vars kernel  : replicated on every rank over identical data: integer rounding, lb>ub check, change
+//                  detection, work list of this rank's rows for the next round
+// Because candidates are merged with exact max/min and everything after the merge is replicated, all
+// ranks finish with bit-identical boxes and the result does not depend on the number of ranks.
+// The row evaluation itself is the code of the single-launch kernel (linear_row.cuh).
+#include "device_problem.cuh"
+#include "kernels.h"
+#include "linear_row.cuh"
+
+namespace mntr {
+
+namespace {
+
+constexpr int kRoundsThreads = 256;
+
+__global__ void rounds_init_kernel(LinDev P, RoundsWs W, const double *lb_io, const double *ub_io)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  int bad = 0;
+  for (int j = tid; j < P.n; j += nthreads) {
+    const double l = lb_io[j], u = ub_io[j];
+    W.box[j] = make_double2(l, u);
+    W.nlb[j] = l;
+    W.nub[j] = u;
+  }
+  if (tid == 0) W.nlb[P.n] = 0.0;
+  for (int i = tid; i < P.m; i += nthreads) {
+    const double2 bnd = __ldg(P.row_bnd + i);
+    if (__ldg(P.row_info + i).y >= 0 && bnd.x > bnd.y + kETol) bad = 1;     // checkBounds_, rows part
+  }
+  for (int w = tid; w < (P.m + 31) / 32; w += nthreads) W.bits[w] = 0u;
+  if (bad) W.ctrl[3] = 1 /* MNTR_INFEAS_BOUNDS */;
+}
+
+template <int G, class R>
+__global__ void __launch_bounds__(kRoundsThreads)
+rounds_rows_kernel(LinDev P, RoundsWs W, int count, int first)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, lane_g = lane % G;
+  const int group = tid / G, n_groups = nthreads / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lane_g));
+  const SinkSplit sink{W.nlb, W.nub, P.n};
+  unsigned long long my_nnz = 0, my_rows = 0;
+  const bool f = first != 0;
+  RowMeta mC = load_meta(P, W.list, group, count, f);
+  RowData dC = load_data(P, mC, lane_g);
+  RowMeta mB = load_meta(P, W.list, group + n_groups, count, f);
+  for (int idx = group; idx < count; idx += n_groups) {
+    const RowData dB = load_data(P, mB, lane_g);
+    const RowMeta mA = load_meta(P, W.list, idx + 2 * n_groups, count, f);
+    if (mC.i >= 0) process_row<G, R>(P, W.box, W.bits, W.ctrl, sink, mC, dC, lane_g, gmask, f, my_nnz, my_rows);
+    mC = mB; dC = dB; mB = mA;
+  }
+  __shared__ unsigned long long s_nnz, s_rows;
+  if (threadIdx.x == 0) { s_nnz = 0ull; s_rows = 0ull; }
+  __syncthreads();
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    my_nnz += __shfl_xor_sync(0xffffffffu, my_nnz, off);
+    my_rows += __shfl_xor_sync(0xffffffffu, my_rows, off);
+  }
+  if (lane == 0 && my_rows) { atomicAdd(&s_nnz, my_nnz); atomicAdd(&s_rows, my_rows); }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_rows) { atomicAdd(&W.counters[0], s_nnz); atomicAdd(&W.counters[1], s_rows); }
+}
+
+// ctrl: [0] changed  [1] int moved  [2] next work-list length  [3] verdict  [4] changed (var,round) pairs
+__global__ void __launch_bounds__(kRoundsThreads)
+rounds_vars_kernel(LinDev P, RoundsWs W)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int warp_g = tid >> 5, n_warps = nthreads >> 5;
+  int changed = 0, int_moved = 0, bad = 0, n_changed = 0;
+  const bool row_inf = W.nlb[P.n] > 0.0;          // merged flag: some rank found an activity-infeasible row
+  if (!row_inf) {
+    for (int j0 = warp_g * 32; j0 < P.n; j0 += n_warps * 32) {
+      const int j = j0 + lane;
+      bool ch = false;
+      if (j < P.n) {
+        const double2 o = W.box[j];
+        double2 v = make_double2(W.nlb[j], W.nub[j]);
+        if (is_int_type(__ldg(P.var_type + j))) {
+          if (v.x != o.x || v.y != o.y) int_moved = 1;
+          tighten_int_bounds(v.x, v.y);
+        }
+        if (v.x > v.y + kETol) bad = 1;
+        if (v.x != o.x || v.y != o.y) { ch = true; W.box[j] = v; W.nlb[j] = v.x; W.nub[j] = v.y; }
+      }
+      unsigned chm = __ballot_sync(0xffffffffu, ch);
+      if (ch) { changed = 1; ++n_changed; }
+      while (chm) {
+        const int t = __ffs(chm) - 1;
+        chm &= chm - 1;
+        const int qb = __ldg(P.csc_ptr + j0 + t), qe = __ldg(P.csc_ptr + j0 + t + 1);
+        for (int q0 = qb; q0 < qe; q0 += 32) {
+          const int q = q0 + lane;
+          bool fresh = false; int row = 0;
+          if (q < qe) {
+            row = __ldg(P.csc_row + q);
+            const unsigned bit = 1u << (row & 31);
+            fresh = (atomicOr(W.bits + (row >> 5), bit) & bit) == 0u;
+          }
+          const unsigned want = __ballot_sync(0xffffffffu, fresh);
+          if (want) {
+            int base = 0;
+            const int leader = __ffs(want) - 1;
+            if (lane == leader) base = atomicAdd(&W.ctrl[2], __popc(want));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (fresh) W.list[base + __popc(want & ((1u << lane) - 1u))] = row;
+          }
+        }
+      }
+    }
+  }
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  n_changed = __reduce_add_sync(0xffffffffu, n_changed);
+  if (lane == 0 && n_changed) atomicAdd(&s_count, n_changed);
+  changed = __syncthreads_or(changed);
+  int_moved = __syncthreads_or(int_moved);
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) {
+    if (s_count) atomicAdd(&W.ctrl[4], s_count);
+    if (changed) W.ctrl[0] = 1;
+    if (int_moved) W.ctrl[1] = 1;
+    if (row_inf) W.ctrl[3] = 2 /* MNTR_INFEAS_ROW */;
+    else if (bad) W.ctrl[3] = 1 /* MNTR_INFEAS_BOUNDS */;
+  }
+}
+
+__global__ void rounds_finish_kernel(LinDev P, RoundsWs W, double *lb_io, double *ub_io)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  for (int j = tid; j < P.n; j += nthreads) {
+    const double2 b = W.box[j];
+    lb_io[j] = b.x;
+    ub_io[j] = b.y;
+  }
+}
+
+int grid_for(long long items, int sm_count)
+{
+  long long blocks = (items + kRoundsThreads - 1) / kRoundsThreads;
+  const long long cap = (long long)sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : (int)blocks;
+}
+
+template <class R>
+cudaError_t rows_r(int G, const LinDev &P, const RoundsWs &W, int count, int first, int sm_count, cudaStream_t s)
+{
+  if (count <= 0) return cudaSuccess;
+  const int blocks = grid_for((long long)count * G, sm_count);
+  switch (G) {
+  case 2:  rounds_rows_kernel<2, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
+  case 4:  rounds_rows_kernel<4, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
+  case 8:  rounds_rows_kernel<8, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
+  case 16: rounds_rows_kernel<16, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
+  default: rounds_rows_kernel<32, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_rounds_init(const LinDev &P, const RoundsWs &W, const double *lb_dev, const double *ub_dev,
+                               int sm_count, cudaStream_t stream)
+{
+  rounds_init_kernel<<<grid_for(P.n > P.m ? P.n : P.m, sm_count), kRoundsThreads, 0, stream>>>(P, W, lb_dev, ub_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per_row, bool directed, int count,
+                               int first, int sm_count, cudaStream_t stream)
+{
+  if (directed) return rows_r<RoundDirected>(lanes_per_row, P, W, count, first, sm_count, stream);
+  return rows_r<RoundNearest>(lanes_per_row, P, W, count, first, sm_count, stream);
+}
+
+cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream)
+{
+  rounds_vars_kernel<<<grid_for(P.n, sm_count), kRoundsThreads, 0, stream>>>(P, W);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rounds_finish(const LinDev &P, const RoundsWs &W, double *lb_dev, double *ub_dev, int sm_count,
+                                 cudaStream_t stream)
+{
+  rounds_finish_kernel<<<grid_for(P.n, sm_count), kRoundsThreads, 0, stream>>>(P, W, lb_dev, ub_dev);
+  return cudaGetLastError();
+}
+
+}  // namespace mntr

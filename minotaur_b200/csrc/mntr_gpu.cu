@@ -5,6 +5,8 @@
 #include "../../include/mntr_gpu.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -56,6 +58,15 @@ struct mntr_gpu_ctx {
   double *d_stage_lb = nullptr, *d_stage_ub = nullptr;
   int64_t stage_boxes = 0;
 
+  // ---- per-round workspace (row-partitioned multi-GPU mode) ----
+  RoundsWs rws{};
+  int32_t *h_ctrl = nullptr;          // pinned mirror of rws.ctrl + counters
+  bool force_rounds = false;          // MNTR_GPU_ROUNDS=1: per-round kernels even without a communicator
+
+  // ---- NCCL communicator (resolved at run time with dlopen: no link-time dependency) ----
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+
   mntr_gpu_stats stats{};
 };
 
@@ -64,6 +75,39 @@ struct SingleCtrl { int32_t ring[12]; int32_t status[4]; unsigned long long coun
 static_assert(sizeof(SingleCtrl) == 128, "control block layout");
 
 namespace {
+
+// NCCL entry points, bound with dlopen("libnccl.so.2") on first use.  In a process that already loaded an
+// NCCL (e.g. PyTorch's bundled one) the same library instance is reused.
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi &nccl_api()
+{
+  static NcclApi api;
+  if (api.handle) return api;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int k = 0; names[k] && !api.handle; ++k) api.handle = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
+  if (!api.handle) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+  api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GroupStart &&
+           api.GroupEnd && api.GetErrorString;
+  return api;
+}
 
 int fail(mntr_gpu_ctx *c, int code, const char *fmt, ...)
 {
@@ -74,6 +118,14 @@ int fail(mntr_gpu_ctx *c, int code, const char *fmt, ...)
   }
   return code;
 }
+
+#define NC(call)                                                                              \
+  do {                                                                                        \
+    ncclResult_t r__ = (call);                                                                \
+    if (r__ != ncclSuccess)                                                                   \
+      return fail(ctx, MNTR_E_NCCL, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r__), \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
 
 #define CU(call)                                                                              \
   do {                                                                                        \
@@ -154,7 +206,8 @@ mntr_gpu_options resolve_opts(const mntr_gpu_options *o, int32_t n_boxes)
   r.loop = MNTR_LOOP_FIXPOINT;
   r.max_rounds = 0;
   r.handlers = MNTR_HANDLERS_ALL;
-  r.reserved[0] = r.reserved[1] = r.reserved[2] = 0;
+  r.flags = 0;
+  r.reserved[0] = r.reserved[1] = 0;
   if (o) {
     r = *o;
     if (r.order < 0) r.order = (n_boxes == 1) ? MNTR_ORDER_JACOBI : MNTR_ORDER_REFERENCE;
@@ -217,6 +270,8 @@ void mntr_gpu_destroy(mntr_gpu_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  if (ctx->h_ctrl) { cudaFreeHost(ctx->h_ctrl); ctx->h_ctrl = nullptr; }
   free_all(ctx->lin_allocs); free_all(ctx->nl_allocs); free_all(ctx->single_allocs);
   free_batch(ctx); free_stage(ctx);
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -354,6 +409,16 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if (const char *tr = getenv("MNTR_GPU_TRACE")) {
     if (tr[0] == '1') { if ((rc = dalloc((void **)&W.trace, 64 * sizeof(unsigned long long)))) return rc; }
   }
+
+  // per-round workspace shares box / bits / list with the single-launch kernel
+  RoundsWs &RW = ctx->rws;
+  RW.box = W.box; RW.bits = W.bits; RW.list = W.list;
+  if ((rc = dalloc((void **)&RW.nlb, sizeof(double) * ((size_t)n + 1)))) return rc;
+  if ((rc = dalloc((void **)&RW.nub, sizeof(double) * ((size_t)n + 1)))) return rc;
+  if ((rc = dalloc((void **)&RW.ctrl, 64))) return rc;
+  RW.counters = (unsigned long long *)((char *)RW.ctrl + 32);
+  if (!ctx->h_ctrl) CU(cudaMallocHost((void **)&ctx->h_ctrl, 64));
+  if (const char *fr = getenv("MNTR_GPU_ROUNDS")) ctx->force_rounds = fr[0] == '1';
 
   // sub-warp group size from the mean row length (two entries per lane per step)
   const double mean = m > 0 ? (double)nnz / m : 0.0;
@@ -495,6 +560,77 @@ static void account_single(mntr_gpu_ctx *ctx, const SingleCtrl &ctrl)
   ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, ctrl.status[1]);
 }
 
+// Jacobi rounds as separate launches with the bound merge between rows and vars kernels: the
+// row-partitioned multi-GPU path (and, with MNTR_GPU_ROUNDS=1, the same kernels on one GPU).
+static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, const mntr_gpu_options &o,
+                          int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
+{
+  const LinDev &P = ctx->lin;
+  const RoundsWs &W = ctx->rws;
+  const bool directed = o.rounding == MNTR_ROUND_DIRECTED;
+  NcclApi &nc = nccl_api();
+  CU(cudaMemsetAsync(W.ctrl, 0, 64, ctx->stream));
+  CU(launch_rounds_init(P, W, lb_dev, ub_dev, ctx->sm_count, ctx->stream));
+  int count = P.m, round = 0, verd = 0;
+  double rows_ms = 0, comm_ms = 0, vars_ms = 0;
+  CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  verd = ctx->h_ctrl[3];
+  while (verd == 0) {
+    ++round;
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(launch_rounds_rows(P, W, ctx->lanes_per_row, directed, count, round == 1, ctx->sm_count, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (ctx->comm) {
+      NC(nc.GroupStart());
+      NC(nc.AllReduce(W.nlb, W.nlb, (size_t)P.n + 1, ncclDouble, ncclMax, ctx->comm, ctx->stream));
+      NC(nc.AllReduce(W.nub, W.nub, (size_t)P.n, ncclDouble, ncclMin, ctx->comm, ctx->stream));
+      NC(nc.GroupEnd());
+    }
+    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CU(cudaMemsetAsync(W.ctrl, 0, 12, ctx->stream));          // changed, int moved, next list length
+    CU(launch_rounds_vars(P, W, ctx->sm_count, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    rows_ms += elapsed(ctx->ev[2], ctx->ev[3]);
+    comm_ms += elapsed(ctx->ev[3], ctx->ev[4]);
+    vars_ms += elapsed(ctx->ev[4], ctx->ev[5]);
+    verd = ctx->h_ctrl[3];
+    const int changed = ctx->h_ctrl[0], int_moved = ctx->h_ctrl[1];
+    count = ctx->h_ctrl[2];
+    if (verd != 0 || !changed) break;
+    if (o.max_rounds > 0 && round >= o.max_rounds) break;
+    if (o.loop == MNTR_LOOP_SIMPLEPRESOLVE) {       // LinearHandler.cpp:1625-1627
+      if (round >= 10) break;
+      if (round >= 2 && !int_moved) break;
+    }
+  }
+  CU(launch_rounds_finish(P, W, lb_dev, ub_dev, ctx->sm_count, ctx->stream));
+  unsigned long long cnt[2];
+  memcpy(cnt, (char *)ctx->h_ctrl + 32, sizeof(cnt));
+  if (ctx->comm) {     // nnz-updates / rows are per rank: sum them so every rank reports the job total
+    NC(nc.AllReduce(W.counters, W.counters, 2, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+    CU(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (verdict) *verdict = verd;
+  if (rounds) *rounds = round;
+  if (nnz_updates) *nnz_updates = (int64_t)cnt[0];
+  ctx->stats.nnz_updates += (int64_t)cnt[0];
+  ctx->stats.rows_evaluated += (int64_t)cnt[1];
+  ctx->stats.n_changes += ctx->h_ctrl[4];
+  ctx->stats.n_infeasible += verd != 0;
+  ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, round);
+  ctx->stats.rows_ms += rows_ms; ctx->stats.comm_ms += comm_ms; ctx->stats.vars_ms += vars_ms;
+  return MNTR_OK;
+}
+
+static bool use_rounds(const mntr_gpu_ctx *ctx, const mntr_gpu_options &o)
+{
+  return ctx->comm != nullptr || ctx->force_rounds || (o.flags & MNTR_FLAG_PER_ROUND_KERNELS);
+}
+
 static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_gpu_options &o,
                           int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
 {
@@ -504,6 +640,18 @@ static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_
   CU(cudaMemcpyAsync(ctx->d_lb, lb, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_ub, ub, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (use_rounds(ctx, o)) {
+    if ((rc = run_rounds_dev(ctx, ctx->d_lb, ctx->d_ub, o, verdict, rounds, nnz_updates))) return rc;
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(cudaMemcpyAsync(lb, ctx->d_lb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ub, ctx->d_ub, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_ms += elapsed(ctx->ev[0], ctx->ev[1]);
+    ctx->stats.kernel_ms += ctx->stats.rows_ms + ctx->stats.comm_ms + ctx->stats.vars_ms;
+    ctx->stats.d2h_ms += elapsed(ctx->ev[2], ctx->ev[3]);
+    return MNTR_OK;
+  }
   if ((rc = run_single_dev(ctx, ctx->d_lb, ctx->d_ub, o))) return rc;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   CU(cudaMemcpyAsync(lb, ctx->d_lb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -533,6 +681,14 @@ int mntr_gpu_tighten_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_de
   o.order = MNTR_ORDER_JACOBI;
   int rc;
   ctx->stats = mntr_gpu_stats{};
+  if (use_rounds(ctx, o)) {
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if ((rc = run_rounds_dev(ctx, lb_dev, ub_dev, o, verdict, rounds, nnz_updates))) return rc;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.kernel_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+    return MNTR_OK;
+  }
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   if ((rc = run_single_dev(ctx, lb_dev, ub_dev, o))) return rc;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -695,11 +851,39 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t, const double *, const dou
   return fail(ctx, MNTR_E_UNSUPPORTED, "tighten_nodes: not implemented yet");
 }
 
-int mntr_gpu_nccl_unique_id(void *) { return MNTR_E_UNSUPPORTED; }
-int mntr_gpu_comm_init(mntr_gpu_ctx *ctx, int32_t, int32_t, const void *)
+int mntr_gpu_nccl_unique_id(void *id128)
 {
-  return fail(ctx, MNTR_E_UNSUPPORTED, "comm_init: not implemented yet");
+  if (!id128) return MNTR_E_ARG;
+  NcclApi &nc = nccl_api();
+  if (!nc.ok) return MNTR_E_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (nc.GetUniqueId(&id) != ncclSuccess) return MNTR_E_NCCL;
+  memcpy(id128, &id, sizeof(id));
+  return MNTR_OK;
 }
-int mntr_gpu_comm_destroy(mntr_gpu_ctx *ctx) { return ctx ? MNTR_OK : MNTR_E_ARG; }
+
+int mntr_gpu_comm_init(mntr_gpu_ctx *ctx, int32_t n_ranks, int32_t rank, const void *id128)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !id128) return fail(ctx, MNTR_E_ARG, "comm_init: bad argument");
+  NcclApi &nc = nccl_api();
+  if (!nc.ok) return fail(ctx, MNTR_E_NCCL, "comm_init: libnccl.so.2 could not be loaded");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->comm) { nc.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NC(nc.CommInitRank(&ctx->comm, n_ranks, id, rank));
+  ctx->n_ranks = n_ranks; ctx->rank = rank;
+  return MNTR_OK;
+}
+
+int mntr_gpu_comm_destroy(mntr_gpu_ctx *ctx)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ctx->n_ranks = 1; ctx->rank = 0;
+  return MNTR_OK;
+}
 
 }  // extern "C"

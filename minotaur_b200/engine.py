@@ -28,6 +28,7 @@ ORDER_JACOBI, ORDER_REFERENCE, ORDER_AUTO = 0, 1, -1
 LOOP_FIXPOINT, LOOP_SIMPLEPRESOLVE = 0, 1
 FEASIBLE, INFEAS_BOUNDS, INFEAS_ROW, INFEAS_NL, ERROR_NL = 0, 1, 2, 3, 4
 HANDLERS_ALL, HANDLERS_LINEAR, HANDLERS_NONLINEAR = 0, 1, 2
+FLAG_PER_ROUND_KERNELS = 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -46,13 +47,14 @@ ABI_SYMBOLS = [
 
 class GpuOptions(C.Structure):
     _fields_ = [("rounding", C.c_int32), ("order", C.c_int32), ("loop", C.c_int32), ("max_rounds", C.c_int32),
-                ("handlers", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("handlers", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class GpuStats(C.Structure):
     _fields_ = [("nnz_updates", C.c_int64), ("rows_evaluated", C.c_int64), ("n_infeasible", C.c_int64),
                 ("n_changes", C.c_int64), ("max_rounds", C.c_int32), ("reserved", C.c_int32), ("kernel_ms", C.c_double),
-                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("comm_ms", C.c_double), ("rows_ms", C.c_double),
+                ("vars_ms", C.c_double)]
 
 
 class EngineError(RuntimeError):
@@ -183,7 +185,7 @@ class GpuBoundEngine:
 
     # -- the hot path --
     def tighten(self, lb, ub, rounding=ROUND_DIRECTED, order=ORDER_AUTO, loop=LOOP_FIXPOINT, max_rounds=0,
-                inplace=False, handlers=HANDLERS_ALL) -> TightenResult:
+                inplace=False, handlers=HANDLERS_ALL, flags=0) -> TightenResult:
         """lb/ub: [n] or box-major [n_boxes, n] float64 host arrays."""
         lb = np.asarray(lb, np.float64); ub = np.asarray(ub, np.float64)
         if not inplace or not lb.flags.c_contiguous or not ub.flags.c_contiguous:
@@ -192,7 +194,7 @@ class GpuBoundEngine:
         nb = 1 if single else lb.shape[0]
         if lb.shape[-1] != self.n or ub.shape != lb.shape:
             raise ValueError("box shape does not match the loaded problem")
-        o = GpuOptions(rounding, order, loop, max_rounds, handlers)
+        o = GpuOptions(rounding, order, loop, max_rounds, handlers, flags)
         v = np.zeros(nb, np.int32); r = np.zeros(nb, np.int32); z = np.zeros(nb, np.int64)
         self._check(self.L.mntr_gpu_tighten(self.h, nb, _d(lb), _d(ub), C.byref(o), _i(v), _i(r), _l(z)), "tighten")
         st = self.stats()
@@ -246,6 +248,24 @@ class GpuBoundEngine:
                                                        C.byref(o), C.byref(v), C.byref(r), C.byref(z)),
                     "tighten_single_dev")
         return v.value, r.value, z.value
+
+    # -- row-partitioned multi-GPU mode --
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        """128-byte NCCL unique id (create on rank 0, hand to every rank's comm_init)."""
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        rc = L.mntr_gpu_nccl_unique_id(buf)
+        if rc != 0:
+            raise EngineError(f"mntr_gpu_nccl_unique_id failed ({rc}): NCCL unavailable")
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self.L.mntr_gpu_comm_init(self.h, n_ranks, rank, buf), "comm_init")
+
+    def comm_destroy(self):
+        self._check(self.L.mntr_gpu_comm_destroy(self.h), "comm_destroy")
 
     def stream_handle(self) -> int:
         return int(self.L.mntr_gpu_stream(self.h) or 0)

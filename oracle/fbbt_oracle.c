@@ -416,6 +416,39 @@ void orc_lin_fixpoint_jacobi(const orc_lin_t *p, double *lb, double *ub, int32_t
   free(NL); free(NU); free(flag); free(csc_ptr); free(csc_row);
 }
 
+/* One Jacobi round split at the point where the row-partitioned multi-GPU mode merges candidate
+ * bounds across ranks: (1) rows -> candidates NL/NU (combined with max/min, so per-block results can be
+ * merged with an element-wise MAX / MIN all-reduce), (2) integer rounding + bound check + commit.
+ * Used by the world_size-2 gloo test of the merge protocol. */
+int32_t orc_lin_jacobi_round_rows(const orc_lin_t *p, const double *lb, const double *ub, double *NL, double *NU)
+{
+  jac_t s = { lb, ub, NL, NU };
+  memcpy(NL, lb, sizeof(double) * (size_t)p->n);
+  memcpy(NU, ub, sizeof(double) * (size_t)p->n);
+  for (int32_t i = 0; i < p->m; ++i) {
+    if (p->row_active && !p->row_active[i]) continue;
+    int32_t b = p->row_ptr[i], k = p->row_ptr[i + 1] - b;
+    if (jac_row(&s, k, p->col + b, p->val + b, p->row_lb[i], p->row_ub[i])) return 1;
+  }
+  return 0;
+}
+
+int32_t orc_lin_jacobi_round_vars(const orc_lin_t *p, double *lb, double *ub, double *NL, double *NU,
+                                  int32_t *changed)
+{
+  *changed = 0;
+  for (int32_t j = 0; j < p->n; ++j) {
+    if (is_int_type(p->var_type[j])) {
+      if (NL[j] > -INF20 && fabs(NL[j] - floor(NL[j] + 0.5)) > INT_TOL) NL[j] = ceil(NL[j]);
+      if (NU[j] < INF20 && fabs(NU[j] - floor(NU[j] + 0.5)) > INT_TOL) NU[j] = floor(NU[j]);
+    }
+    if (NL[j] != lb[j] || NU[j] != ub[j]) *changed = 1;
+    lb[j] = NL[j]; ub[j] = NU[j];
+  }
+  for (int32_t j = 0; j < p->n; ++j) if (lb[j] > ub[j] + E_TOL) return 1;
+  return 0;
+}
+
 /* ===========================================================================
  *                         interval helpers (Operations.cpp)
  * ========================================================================= */

@@ -101,6 +101,10 @@ class Oracle:
         L.orc_lin_fixpoint_inplace.argtypes = [C.POINTER(OrcLin), _dp, _dp, C.POINTER(OrcResult)]
         L.orc_lin_fixpoint_jacobi.argtypes = [C.POINTER(OrcLin), _dp, _dp, C.c_int32, C.POINTER(OrcResult)]
         L.orc_lin_row_activity.argtypes = [C.POINTER(OrcLin), C.c_int32, _dp, _dp, _dp]
+        L.orc_lin_jacobi_round_rows.argtypes = [C.POINTER(OrcLin), _dp, _dp, _dp, _dp]
+        L.orc_lin_jacobi_round_rows.restype = C.c_int32
+        L.orc_lin_jacobi_round_vars.argtypes = [C.POINTER(OrcLin), _dp, _dp, _dp, _dp, _ip]
+        L.orc_lin_jacobi_round_vars.restype = C.c_int32
         L.orc_nl_compute_bounds.argtypes = [C.POINTER(OrcNl), C.c_int32, _dp, _dp, _dp, _dp]
         L.orc_nl_compute_bounds.restype = C.c_int32
         L.orc_nl_var_bound_mods.argtypes = [C.POINTER(OrcNl), C.c_int32, C.c_double, C.c_double, _dp, _dp, _ip]
@@ -137,6 +141,23 @@ class Oracle:
     def lin_fixpoint_jacobi(self, inst, lb=None, ub=None, max_rounds=0):
         return self._run_lin(self.lib.orc_lin_fixpoint_jacobi, inst, inst.lb if lb is None else lb,
                              inst.ub if ub is None else ub, C.c_int32(max_rounds))
+
+    def lin_jacobi_round_rows(self, inst, lb, ub):
+        keep = {}
+        s = _lin_struct(inst, keep)
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        nl = np.empty_like(lb); nu = np.empty_like(ub)
+        inf = self.lib.orc_lin_jacobi_round_rows(C.byref(s), _d(lb), _d(ub), _d(nl), _d(nu))
+        return nl, nu, int(inf)
+
+    def lin_jacobi_round_vars(self, inst, lb, ub, nl, nu):
+        keep = {}
+        s = _lin_struct(inst, keep)
+        lb = np.array(lb, np.float64, copy=True); ub = np.array(ub, np.float64, copy=True)
+        nl = np.array(nl, np.float64, copy=True); nu = np.array(nu, np.float64, copy=True)
+        ch = np.zeros(1, np.int32)
+        inf = self.lib.orc_lin_jacobi_round_vars(C.byref(s), _d(lb), _d(ub), _d(nl), _d(nu), _i(ch))
+        return lb, ub, int(inf), int(ch[0])
 
     def lin_row_activity(self, inst, row, lb, ub):
         keep = {}
