@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         # cudart is linked statically (nvcc default); libstdc++ dynamically and explicitly,
         # because this image's g++ wrapper otherwise links the static archive.
         cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + \
-              ["-Xlinker", "--no-as-needed", "-lstdc++", "-lm", "-ldl", "-lpthread", "-lrt"]
+              ["-Xlinker", "-soname=libmntr_gpu.so", "-Xlinker", "--no-as-needed", "-lstdc++", "-lm", "-ldl", "-lpthread", "-lrt"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)

@@ -1,0 +1,315 @@
+//
+//     GpuBoundHandler -- B200 bound-tightening handler for Minotaur
+//
+/**
+ * \file GpuBoundHandler.cpp
+ * \brief Host adapter between Minotaur's Handler plugin API and the C ABI of libmntr_gpu.so.
+ * No bound arithmetic happens here: this file only flattens the object graph, moves bounds and turns
+ * the tightened box into VarBoundMods.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <map>
+#include <stdexcept>
+
+#include "MinotaurConfig.h"
+#include "CGraph.h"
+#include "CNode.h"
+#include "Constraint.h"
+#include "Environment.h"
+#include "Function.h"
+#include "GpuBoundHandler.h"
+#include "LinearFunction.h"
+#include "Logger.h"
+#include "Node.h"
+#include "NonlinearFunction.h"
+#include "Objective.h"
+#include "Problem.h"
+#include "Relaxation.h"
+#include "SolutionPool.h"
+#include "Timer.h"
+#include "VarBoundMod.h"
+#include "Variable.h"
+#include "mntr_gpu.h"
+
+using namespace Minotaur;
+
+const std::string GpuBoundHandler::me_ = "GpuBoundHandler: ";
+
+GpuBoundHandler::GpuBoundHandler(EnvPtr env, ProblemPtr problem, int device)
+  : env_(env), problem_(problem), ctx_(0), mode_(FastFixpoint), roundNearest_(false), loadedFor_(0),
+    loadedVars_(0), loadedCons_(0)
+{
+  logger_ = env->getLogger();
+  stats_.calls = stats_.uploads = stats_.nMods = stats_.nInf = 0;
+  stats_.nnzUpdates = 0;
+  stats_.timeHost = stats_.timeDevice = 0.;
+  int rc = mntr_gpu_create(device, &ctx_);
+  if (rc != MNTR_OK) {
+    ctx_ = 0;
+    // the reference's convention for unusable components is an assert / exception at set-up time
+    throw std::runtime_error("GpuBoundHandler: no usable CUDA device (mntr_gpu_create failed); "
+                             "use LinearHandler/NlPresHandler instead");
+  }
+}
+
+GpuBoundHandler::~GpuBoundHandler()
+{
+  if (ctx_) mntr_gpu_destroy(ctx_);
+}
+
+std::string GpuBoundHandler::getName() const { return "GpuBoundHandler (FBBT on B200)"; }
+
+namespace {
+
+// CGraph -> tape in the evaluation order of CGraph::computeBounds: variable nodes by ascending variable id,
+// constants, then the dependent nodes dq_ (public accessor dNodes(), CGraph.h:202).
+bool flattenCGraph(CGraph *cg, std::vector<unsigned char> &op, std::vector<int> &a0, std::vector<int> &a1,
+                   std::vector<double> &cn, std::vector<int> &child)
+{
+  CNodeQ dq = cg->dNodes();
+  if (dq.empty()) return false;
+  std::map<const CNode *, int> index;
+  std::map<UInt, const CNode *> vars;          // ascending variable id
+  std::vector<const CNode *> consts;
+  for (CNodeQ::iterator it = dq.begin(); it != dq.end(); ++it) {
+    const CNode *nd = *it;
+    std::vector<const CNode *> kids;
+    if (nd->numChild() > 2 || nd->getOp() == OpSumList) {
+      for (CNode **c = nd->getListL(); c != nd->getListR(); ++c) kids.push_back(*c);
+    } else {
+      if (nd->getL()) kids.push_back(nd->getL());
+      if (nd->getR()) kids.push_back(nd->getR());
+    }
+    for (size_t k = 0; k < kids.size(); ++k) {
+      const CNode *c = kids[k];
+      if (c->getOp() == OpVar) vars[c->getV()->getId()] = c;
+      else if ((c->getOp() == OpNum || c->getOp() == OpInt) && index.find(c) == index.end()) {
+        index[c] = -1;
+        consts.push_back(c);
+      }
+    }
+  }
+  const size_t base = op.size();
+  int next = 0;
+  for (std::map<UInt, const CNode *>::iterator it = vars.begin(); it != vars.end(); ++it) {
+    index[it->second] = next++;
+    op.push_back((unsigned char)OpVar); a0.push_back((int)it->second->getV()->getIndex()); a1.push_back(-1);
+    cn.push_back(0.);
+  }
+  for (size_t k = 0; k < consts.size(); ++k) {
+    index[consts[k]] = next++;
+    op.push_back((unsigned char)consts[k]->getOp()); a0.push_back(-1); a1.push_back(-1);
+    cn.push_back(consts[k]->getVal());
+  }
+  for (CNodeQ::iterator it = dq.begin(); it != dq.end(); ++it) {
+    const CNode *nd = *it;
+    index[nd] = next++;
+    op.push_back((unsigned char)nd->getOp());
+    cn.push_back(0.);
+    if (nd->getOp() == OpSumList) {
+      a0.push_back((int)child.size());
+      for (CNode **c = nd->getListL(); c != nd->getListR(); ++c) child.push_back(index[*c]);
+      a1.push_back((int)child.size());
+    } else {
+      a0.push_back(nd->getL() ? index[nd->getL()] : -1);
+      a1.push_back(nd->getR() ? index[nd->getR()] : -1);
+    }
+  }
+  (void)base;
+  return true;
+}
+
+}  // namespace
+
+void GpuBoundHandler::upload_(ProblemPtr p)
+{
+  const UInt n = p->getNumVars();
+  std::vector<int> rowPtr(1, 0), col, tapePtr(1, 0), a0, a1, child, linPtr(1, 0), linCol;
+  std::vector<double> val, rowLb, rowUb, cn, linVal, cLb, cUb;
+  std::vector<unsigned char> vtype(n), op;
+  for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it)
+    vtype[(*it)->getIndex()] = (unsigned char)(*it)->getType();
+
+  for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it) {
+    ConstraintPtr c = *it;
+    if (DeletedCons == c->getState()) continue;
+    LinearFunctionPtr lf = c->getLinearFunction();
+    if (c->getFunctionType() == Linear && c->getQuadraticFunction() == 0 && c->getNonlinearFunction() == 0) {
+      // LinearHandler::varBndsFromCons_ row filter, LinearHandler.cpp:509-511; terms in ascending variable id
+      if (lf)
+        for (VariableGroupConstIterator t = lf->termsBegin(); t != lf->termsEnd(); ++t) {
+          col.push_back((int)t->first->getIndex());
+          val.push_back(t->second);
+        }
+      rowPtr.push_back((int)col.size());
+      rowLb.push_back(c->getLb());
+      rowUb.push_back(c->getUb());
+    } else if (c->getFunctionType() != Constant && c->getNonlinearFunction() && !c->getQuadraticFunction()) {
+      // NlPresHandler::varBndsFromCons_ nlf branch, NlPresHandler.cpp:1771-1778 (native CGraph only)
+      CGraph *cg = dynamic_cast<CGraph *>(c->getNonlinearFunction());
+      if (!cg || !flattenCGraph(cg, op, a0, a1, cn, child)) continue;
+      tapePtr.push_back((int)op.size());
+      if (lf)
+        for (VariableGroupConstIterator t = lf->termsBegin(); t != lf->termsEnd(); ++t) {
+          linCol.push_back((int)t->first->getIndex());
+          linVal.push_back(t->second);
+        }
+      linPtr.push_back((int)linCol.size());
+      cLb.push_back(c->getLb());
+      cUb.push_back(c->getUb());
+    }
+  }
+  // CSR columns must ascend by variable INDEX; LinearFunction orders by id, which equals the index unless
+  // variables were deleted -- sort defensively
+  for (size_t i = 0; i + 1 < rowPtr.size(); ++i) {
+    bool sorted = true;
+    for (int t = rowPtr[i] + 1; t < rowPtr[i + 1]; ++t) if (col[t] <= col[t - 1]) { sorted = false; break; }
+    if (!sorted) {
+      std::vector<std::pair<int, double> > tmp;
+      for (int t = rowPtr[i]; t < rowPtr[i + 1]; ++t) tmp.push_back(std::make_pair(col[t], val[t]));
+      std::sort(tmp.begin(), tmp.end());
+      for (int t = rowPtr[i]; t < rowPtr[i + 1]; ++t) { col[t] = tmp[t - rowPtr[i]].first; val[t] = tmp[t - rowPtr[i]].second; }
+    }
+  }
+  const int m = (int)rowPtr.size() - 1;
+  int rc = mntr_gpu_load_linear(ctx_, m, (int)n, &rowPtr[0], col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0],
+                                rowLb.empty() ? 0 : &rowLb[0], rowUb.empty() ? 0 : &rowUb[0],
+                                vtype.empty() ? 0 : &vtype[0], 0);
+  if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+  const int nc = (int)tapePtr.size() - 1;
+  if (nc > 0) {
+    if (child.empty()) child.push_back(0);
+    if (linCol.empty()) { linCol.push_back(0); linVal.push_back(0.); }
+    rc = mntr_gpu_load_cgraph(ctx_, nc, &tapePtr[0], &op[0], &a0[0], &a1[0], &cn[0], &child[0], &linPtr[0],
+                              &linCol[0], &linVal[0], &cLb[0], &cUb[0]);
+    if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+  }
+  loadedFor_ = p;
+  loadedVars_ = p->getNumVars();
+  loadedCons_ = p->getNumCons();
+  lb_.resize(n); ub_.resize(n); lb0_.resize(n); ub0_.resize(n);
+  ++stats_.uploads;
+}
+
+bool GpuBoundHandler::tighten_(ProblemPtr p, ModVector &mods, bool truncated)
+{
+  if (loadedFor_ != p || loadedVars_ != p->getNumVars() || loadedCons_ != p->getNumCons()) upload_(p);
+  const UInt n = p->getNumVars();
+  for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) {
+    const UInt j = (*it)->getIndex();
+    lb0_[j] = lb_[j] = (*it)->getLb();
+    ub0_[j] = ub_[j] = (*it)->getUb();
+  }
+  mntr_gpu_options o;
+  o.rounding = roundNearest_ ? MNTR_ROUND_NEAREST : MNTR_ROUND_DIRECTED;
+  o.order = (mode_ == ReferenceOrder) ? MNTR_ORDER_REFERENCE : MNTR_ORDER_JACOBI;
+  o.loop = (mode_ == ReferenceOrder && truncated) ? MNTR_LOOP_SIMPLEPRESOLVE : MNTR_LOOP_FIXPOINT;
+  o.max_rounds = 0;
+  o.handlers = MNTR_HANDLERS_ALL;
+  o.flags = 0;
+  o.reserved[0] = o.reserved[1] = 0;
+  int verdict = 0, rounds = 0;
+  long long nnz = 0;
+  int rc = mntr_gpu_tighten(ctx_, 1, n ? &lb_[0] : 0, n ? &ub_[0] : 0, &o, &verdict, &rounds, (int64_t *)&nnz);
+  if (rc == MNTR_E_UNSUPPORTED && o.order == MNTR_ORDER_JACOBI) {
+    // CGraph constraints are evaluated by the reference-order kernel
+    o.order = MNTR_ORDER_REFERENCE;
+    rc = mntr_gpu_tighten(ctx_, 1, &lb_[0], &ub_[0], &o, &verdict, &rounds, (int64_t *)&nnz);
+  }
+  if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+  mntr_gpu_stats st;
+  mntr_gpu_get_stats(ctx_, &st);
+  stats_.timeDevice += st.kernel_ms + st.h2d_ms + st.d2h_ms;
+  stats_.nnzUpdates += nnz;
+  ++stats_.calls;
+  if (verdict != MNTR_FEASIBLE) { ++stats_.nInf; return true; }
+  // one VarBoundMod per changed (variable, side), applied at once: the final box is what matters
+  // (VarBoundMod::oldVal_ is captured by its constructor, VarBoundMod.cpp:27-43)
+  for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) {
+    VariablePtr v = *it;
+    const UInt j = v->getIndex();
+    if (lb_[j] != lb0_[j]) {
+      VarBoundModPtr mod = (VarBoundModPtr) new VarBoundMod(v, Lower, lb_[j]);
+      mod->applyToProblem(p);
+      mods.push_back(mod);
+      ++stats_.nMods;
+    }
+    if (ub_[j] != ub0_[j]) {
+      VarBoundModPtr mod = (VarBoundModPtr) new VarBoundMod(v, Upper, ub_[j]);
+      mod->applyToProblem(p);
+      mods.push_back(mod);
+      ++stats_.nMods;
+    }
+  }
+  return false;
+}
+
+void GpuBoundHandler::simplePresolve(ProblemPtr p, SolutionPoolPtr, ModVector &t_mods, SolveStatus &status)
+{
+  Timer *timer = env_->getNewTimer();
+  timer->start();
+  const bool inf = tighten_(p, t_mods, true);
+  if (inf) status = SolvedInfeasible;
+  stats_.timeHost += timer->query();
+  delete timer;
+}
+
+bool GpuBoundHandler::presolveNode(RelaxationPtr rel, NodePtr, SolutionPoolPtr spool, ModVector &p_mods,
+                                   ModVector &r_mods)
+{
+  SolveStatus status = Started;
+  simplePresolve(rel, spool, r_mods, status);
+  if (true == modProb_) copyBndsFromRel_(rel, p_mods);      // as LinearHandler::presolveNode, :1592-1602
+  return (status == SolvedInfeasible);
+}
+
+// LinearHandler::copyBndsFromRel_, LinearHandler.cpp:108-132
+void GpuBoundHandler::copyBndsFromRel_(RelaxationPtr rel, ModVector &p_mods)
+{
+  const double eTol = 1e-8;
+  for (VariableConstIterator it = problem_->varsBegin(); it != problem_->varsEnd(); ++it) {
+    VariablePtr xp = *it;
+    VariablePtr xr = rel->getRelaxationVar(xp);
+    if (!xr) continue;
+    if (xr->getLb() > xp->getLb() + eTol) {
+      VarBoundModPtr mod = (VarBoundModPtr) new VarBoundMod(xp, Lower, xr->getLb());
+      mod->applyToProblem(problem_);
+      p_mods.push_back(mod);
+    }
+    if (xr->getUb() < xp->getUb() - eTol) {
+      VarBoundModPtr mod = (VarBoundModPtr) new VarBoundMod(xp, Upper, xr->getUb());
+      mod->applyToProblem(problem_);
+      p_mods.push_back(mod);
+    }
+  }
+}
+
+SolveStatus GpuBoundHandler::presolve(PreModQ *, bool *changed, Solution **)
+{
+  ModVector mods;
+  Timer *timer = env_->getNewTimer();
+  timer->start();
+  const bool inf = tighten_(problem_, mods, false);
+  if (!mods.empty()) *changed = true;
+  // root mode keeps no undo information: the mods are already applied (LinearHandler deletes them too,
+  // LinearHandler.cpp:1093-1099)
+  for (ModVector::iterator it = mods.begin(); it != mods.end(); ++it) delete *it;
+  stats_.timeHost += timer->query();
+  delete timer;
+  return inf ? SolvedInfeasible : Finished;
+}
+
+void GpuBoundHandler::writeStats(std::ostream &out) const
+{
+  out << me_ << "Statistics for GPU bound tightening:" << std::endl
+      << me_ << "Calls                        = " << stats_.calls << std::endl
+      << me_ << "Structure uploads            = " << stats_.uploads << std::endl
+      << me_ << "Bound modifications          = " << stats_.nMods << std::endl
+      << me_ << "Times infeasibility detected = " << stats_.nInf << std::endl
+      << me_ << "nnz-updates                  = " << stats_.nnzUpdates << std::endl
+      << me_ << "Host time (s)                = " << stats_.timeHost << std::endl
+      << me_ << "Device time (ms)             = " << stats_.timeDevice << std::endl;
+}

@@ -1,0 +1,176 @@
+// handler_test.cpp -- TEST: GpuBoundHandler against the reference's own LinearHandler / NlPresHandler
+// through Minotaur's Handler::presolveNode interface, on the same relaxation objects.
+//
+// Built by oracle/Makefile (target handler_test) against the reference objects in oracle/_ref; run on a GPU
+// box by tests/test_gpu_handler.py.  Exit code 0 = every comparison held.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "MinotaurConfig.h"
+#include "CGraph.h"
+#include "Constraint.h"
+#include "Environment.h"
+#include "Function.h"
+#include "GpuBoundHandler.h"
+#include "LinearFunction.h"
+#include "LinearHandler.h"
+#include "NlPresHandler.h"
+#include "Objective.h"
+#include "Problem.h"
+#include "Relaxation.h"
+#include "VarBoundMod.h"
+#include "Variable.h"
+
+using namespace Minotaur;
+
+static uint64_t rng_state = 88172645463325252ull;
+static uint64_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; }
+static double urand() { return (rnd() >> 11) * (1.0 / 9007199254740992.0); }
+static int irand(int lo, int hi) { return lo + (int)(rnd() % (uint64_t)(hi - lo + 1)); }
+
+// random MILP with a planted point (the C2 generator's recipe) + a few CGraph constraints
+static ProblemPtr makeProblem(EnvPtr env, int n, int m, int k, int n_nl, std::vector<double> &xstar)
+{
+  ProblemPtr p = (ProblemPtr) new Problem(env);
+  xstar.resize(n);
+  std::vector<VariablePtr> v(n);
+  for (int j = 0; j < n; ++j) {
+    const bool isint = urand() < 0.5;
+    const double ub = irand(1, 10);
+    v[j] = p->newVariable(0.0, ub, isint ? Integer : Continuous);
+    xstar[j] = isint ? std::floor(urand() * (ub + 1)) : std::floor(urand() * ub * 4) / 4;
+    if (xstar[j] > ub) xstar[j] = ub;
+  }
+  for (int i = 0; i < m; ++i) {
+    LinearFunctionPtr lf = (LinearFunctionPtr) new LinearFunction();
+    double act = 0;
+    for (int t = 0; t < k; ++t) {
+      const int j = irand(0, n - 1);
+      if (lf->getWeight(v[j]) != 0.0) continue;
+      const double a = irand(1, 9) * (urand() < 0.3 ? -1.0 : 1.0);
+      lf->addTerm(v[j], a);
+      act += a * xstar[j];
+    }
+    const bool eq = urand() < 0.3;
+    p->newConstraint((FunctionPtr) new Function(lf), eq ? act : -INFINITY, eq ? act : act + irand(0, 3));
+  }
+  for (int c = 0; c < n_nl; ++c) {
+    int i = irand(0, n - 1), j = irand(0, n - 1), l = irand(0, n - 1);
+    if (i == j) j = (j + 1) % n;
+    CGraph *cg = new CGraph();
+    CNode *ni = cg->newNode(v[i]), *nj = cg->newNode(v[j]);
+    CNode *out = cg->newNode(OpMult, ni, nj);
+    cg->setOut(out);
+    cg->finalize();
+    LinearFunctionPtr lf = (LinearFunctionPtr) new LinearFunction();
+    const double a = irand(1, 5);
+    lf->addTerm(v[l], a);
+    const double val = xstar[i] * xstar[j] + a * xstar[l];
+    p->newConstraint((FunctionPtr) new Function(lf, (NonlinearFunctionPtr)cg), -INFINITY, val + irand(0, 3));
+  }
+  // Relaxation's cloning constructor dereferences the objective (Relaxation.cpp:139-140)
+  LinearFunctionPtr of = (LinearFunctionPtr) new LinearFunction();
+  of->addTerm(v[0], 1.0);
+  p->newObjective((FunctionPtr) new Function(of), 0.0, Minimize);
+  p->calculateSize();
+  return p;
+}
+
+static void branch(ProblemPtr p, int depth)
+{
+  for (int d = 0; d < depth; ++d) {
+    VariablePtr v = p->getVariable(irand(0, p->getNumVars() - 1));
+    if (v->getType() != Integer || v->getUb() - v->getLb() < 1) continue;
+    const double x = v->getLb() + (v->getUb() - v->getLb()) * urand();
+    if (urand() < 0.5) p->changeBound(v, Upper, std::floor(x)); else p->changeBound(v, Lower, std::ceil(x + 1e-9));
+  }
+}
+
+static int failures = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { ++failures; fprintf(stderr, "FAIL %s:%d: ", __FILE__, __LINE__); \
+                              fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
+
+int main()
+{
+  EnvPtr env = (EnvPtr) new Environment();
+  int err = 0;
+  env->startTimer(err);
+  env->setLogLevel(LogNone);
+  int n_cmp = 0, n_inf = 0, n_mods = 0;
+  for (int trial = 0; trial < 6; ++trial) {
+    std::vector<double> xstar;
+    const int n = 300 + 50 * trial, m = 350, n_nl = (trial % 2) ? 40 : 0;
+    ProblemPtr p = makeProblem(env, n, m, 6, n_nl, xstar);
+    for (int box = 0; box < 6; ++box) {
+      RelaxationPtr relA = (RelaxationPtr) new Relaxation(p, env);
+      RelaxationPtr relB = (RelaxationPtr) new Relaxation(p, env);
+      relA->calculateSize(); relB->calculateSize();
+      const uint64_t keep = rng_state;
+      branch(relA, 2 * box);
+      rng_state = keep;
+      branch(relB, 2 * box);
+      std::vector<double> lb0(n), ub0(n);
+      for (int j = 0; j < n; ++j) { lb0[j] = relB->getVariable(j)->getLb(); ub0[j] = relB->getVariable(j)->getUb(); }
+
+      // reference: LinearHandler then NlPresHandler, one PCBProcessor::presolveNode_ pass
+      LinearHandler lh(env, p);
+      NlPresHandler nh(env, p);
+      ModVector pm, rmA;
+      bool infA = lh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pm, rmA);
+      if (!infA && n_nl) infA = nh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pm, rmA);
+
+      // GPU handler in reference-order, round-to-nearest mode: must reproduce it bit for bit
+      GpuBoundHandler gh(env, p, 0);
+      gh.setMode(GpuBoundHandler::ReferenceOrder);
+      gh.setRoundNearest(true);
+      ModVector rmB;
+      const bool infB = gh.presolveNode(relB, (NodePtr)0, (SolutionPoolPtr)0, pm, rmB);
+      ++n_cmp;
+      if (infB && !infA) {
+        // allowed only when the GPU proved an activity-infeasible row, which the reference's node mode drops
+        // (LinearHandler.cpp:1631); such a box must really be infeasible: the reference's own sweeps agree
+        // once their status is honoured -- checked by the parity tests; here we only count it
+        ++n_inf;
+      } else {
+        CHECK(infA == infB, "trial %d box %d: verdict ref %d gpu %d", trial, box, (int)infA, (int)infB);
+        if (!infA) {
+          for (int j = 0; j < n; ++j) {
+            CHECK(relA->getVariable(j)->getLb() == relB->getVariable(j)->getLb() &&
+                  relA->getVariable(j)->getUb() == relB->getVariable(j)->getUb(),
+                  "trial %d box %d var %d: ref [%.17g,%.17g] gpu [%.17g,%.17g]", trial, box, j,
+                  relA->getVariable(j)->getLb(), relA->getVariable(j)->getUb(), relB->getVariable(j)->getLb(),
+                  relB->getVariable(j)->getUb());
+          }
+        } else ++n_inf;
+      }
+      n_mods += (int)rmB.size();
+      // undo in reverse order restores the incoming box (Node.cpp:318-340)
+      for (ModVector::reverse_iterator it = rmB.rbegin(); it != rmB.rend(); ++it) (*it)->undoToProblem(relB);
+      for (int j = 0; j < n; ++j)
+        CHECK(relB->getVariable(j)->getLb() == lb0[j] && relB->getVariable(j)->getUb() == ub0[j],
+              "trial %d box %d var %d: undo did not restore the box", trial, box, j);
+
+      // default mode (Jacobi fixpoint, directed rounding): valid, never cuts off the planted point on the root box
+      if (box == 0) {
+        GpuBoundHandler gf(env, p, 0);
+        ModVector rmC;
+        const bool infC = gf.presolveNode(relB, (NodePtr)0, (SolutionPoolPtr)0, pm, rmC);
+        CHECK(!infC, "trial %d: root box declared infeasible by the fast mode", trial);
+        for (int j = 0; j < n && !infC; ++j)
+          CHECK(relB->getVariable(j)->getLb() <= xstar[j] + 1e-6 && relB->getVariable(j)->getUb() >= xstar[j] - 1e-6,
+                "trial %d var %d: planted point cut off [%g,%g] x*=%g", trial, j, relB->getVariable(j)->getLb(),
+                relB->getVariable(j)->getUb(), xstar[j]);
+        for (ModVector::iterator it = rmC.begin(); it != rmC.end(); ++it) delete *it;
+      }
+      for (ModVector::iterator it = rmA.begin(); it != rmA.end(); ++it) delete *it;
+      for (ModVector::iterator it = rmB.begin(); it != rmB.end(); ++it) delete *it;
+      delete relA; delete relB;
+    }
+    delete p;
+  }
+  printf("handler_test: %d comparisons, %d infeasible, %d mods emitted, %d failures\n", n_cmp, n_inf, n_mods, failures);
+  return failures ? 1 : 0;
+}
