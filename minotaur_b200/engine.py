@@ -240,9 +240,9 @@ class GpuBoundEngine:
         return self.stats()
 
     def tighten_single_dev(self, lb_dev_ptr: int, ub_dev_ptr: int, rounding=ROUND_DIRECTED, loop=LOOP_FIXPOINT,
-                           max_rounds=0):
+                           max_rounds=0, flags=0):
         """Single box resident in HBM (device pointers), Jacobi fixpoint; returns (verdict, rounds, nnz)."""
-        o = GpuOptions(rounding, ORDER_JACOBI, loop, max_rounds)
+        o = GpuOptions(rounding, ORDER_JACOBI, loop, max_rounds, HANDLERS_ALL, flags)
         v = C.c_int32(0); r = C.c_int32(0); z = C.c_int64(0)
         self._check(self.L.mntr_gpu_tighten_single_dev(self.h, C.c_void_p(lb_dev_ptr), C.c_void_p(ub_dev_ptr),
                                                        C.byref(o), C.byref(v), C.byref(r), C.byref(z)),

@@ -293,6 +293,31 @@ def make_sparse_milp(m: int, n: int, nnz_per_row: int = 10, seed: int = 12345, r
                       xstar=xstar)
 
 
+def make_sparse_milp_block(m_block: int, n: int, nnz_per_row: int = 10, seed: int = 777, block: int = 0,
+                           int_frac: float = 0.5, name: str = "sparse_milp_block") -> LinearRows:
+    """Config C4 shape, one ROW BLOCK of it: the variables (types, box, planted point) come from ``seed``
+    alone, so every rank of the row-partitioned mode derives the same n columns, while the block's rows come
+    from ``(seed, block)``.  Same distributions as ``make_sparse_milp`` (integer data)."""
+    vrng = np.random.default_rng(seed)
+    is_int = vrng.random(n) < int_frac
+    var_type = np.where(is_int, INTEGER, CONTINUOUS).astype(np.uint8)
+    lb = np.zeros(n)
+    ub = vrng.integers(1, 11, size=n).astype(np.float64)
+    xstar = np.where(is_int, np.floor(vrng.random(n) * (ub + 1)).clip(0, ub), np.round(vrng.random(n) * ub * 4) / 4)
+    rng = np.random.default_rng([seed, block + 1])
+    k = min(nnz_per_row, n)
+    col = _distinct_sorted_columns(rng, m_block, n, k)
+    val = rng.integers(1, 10, size=(m_block, k)).astype(np.float64) * np.where(rng.random((m_block, k)) < 0.3, -1.0, 1.0)
+    act = (val * xstar[col]).sum(axis=1)
+    slack = rng.integers(0, 4, size=m_block).astype(np.float64)
+    is_eq = rng.random(m_block) < 0.3
+    row_ub = np.where(is_eq, act, act + slack)
+    row_lb = np.where(is_eq, act, -INF)
+    row_ptr = (np.arange(m_block + 1, dtype=np.int64) * k).astype(np.int32)
+    return LinearRows(m=m_block, n=n, row_ptr=row_ptr, col=col.reshape(-1), val=val.reshape(-1), row_lb=row_lb,
+                      row_ub=row_ub, var_type=var_type, lb=lb, ub=ub, name=f"{name}[{block}]", xstar=xstar)
+
+
 def make_knapsack_setcover(m: int = 50_000, n: int = 50_000, nnz_per_row: int = 10, seed: int = 2024,
                            name: str = "knapsack_setcover") -> LinearRows:
     """Config C3 shape: half knapsack rows ``sum w_j x_j <= W`` (w in {1..20}, binaries and
