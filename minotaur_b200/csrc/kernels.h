@@ -32,13 +32,15 @@ struct BatchIo {
   int32_t *verdict;      // [n_boxes]
   int32_t *rounds;       // [n_boxes]
   long long *nnz;        // [n_boxes]
+  unsigned char *tstate; // [tiles][kTileStateBytes] per-tile control words (global: shared by a cluster)
 };
+constexpr int kTileStateBytes = 640;
 
 // K3 (linear_batch.cu): batched node boxes, the reference's in-place index-ordered sweep
 // reproduced by wavefront levels; one CTA per tile of 32 boxes.
 cudaError_t launch_batch_reference(const LinDev &P, const NlDev *N, const BatchIo &io, bool directed,
                                    int loop_mode, int max_rounds, int lin_enabled, int nl_enabled,
-                                   cudaStream_t stream);
+                                   int sm_count, cudaStream_t stream);
 
 // box-major [n_boxes][n] lb/ub (device staging) <-> node-minor double2 boxes
 cudaError_t launch_boxes_pack(const double *lb_bm, const double *ub_bm, int32_t n, int32_t box0,

@@ -6,7 +6,8 @@
 // whole tile with one coalesced 512-byte request of 128-bit loads, while the CSR entries
 // (col,val) are warp-uniform broadcast loads amortised over the 32 boxes.
 //
-// One CTA owns one tile of 32 boxes for the whole call.  Because boxes are independent, the
+// One CTA -- or, when tiles are scarce, one thread-block cluster of up to 8 CTAs -- owns one tile of 32 boxes
+// for the whole call.  Because boxes are independent, the
 // only ordering constraint of the reference's in-place, index-ordered Gauss-Seidel sweep
 // (LinearHandler::varBndsFromCons_, LinearHandler.cpp:493-541) is between rows that share a
 // variable; rows are therefore scheduled in wavefront levels (level = 1 + max level of an
@@ -28,9 +29,14 @@
 //            variables moved) or fixpoint.
 // Deviation, deliberate: an activity-infeasible row yields verdict MNTR_INFEAS_ROW and stops
 // that box; the reference's node mode drops that status (:1631).
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "cgraph.cuh"
 #include "device_problem.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace mntr {
 
@@ -41,12 +47,33 @@ constexpr int kBatchThreads = kBatchWarps * 32;
 constexpr int kGather = 4;             // independent 512-byte gathers a warp keeps in flight
 constexpr unsigned kFull = 0xffffffffu;
 
+// Per-tile control words.  They live in GLOBAL memory (BatchIo::tstate) because a tile may be worked on by a
+// whole thread-block cluster: volatile accesses go to L2, cluster.sync() orders them.
 struct TileShared {
-  int changed[32];
-  int nint[32];
-  int verdict[32];
+  volatile int changed[32];
+  volatile int nint[32];
+  volatile int verdict[32];
   unsigned long long nnz[32];
 };
+static_assert(sizeof(TileShared) == kTileStateBytes, "BatchIo::tstate stride");
+
+// the warps of ALL CTAs of the cluster that owns a tile, numbered consecutively
+struct TileTeam {
+  int gwarp, n_warps;       // this warp / warps in the cluster
+  int cthread, n_threads;   // this thread / threads in the cluster
+  __device__ __forceinline__ void sync() const { cg::this_cluster().sync(); }
+};
+__device__ __forceinline__ TileTeam make_team()
+{
+  cg::cluster_group cl = cg::this_cluster();
+  TileTeam t;
+  const int nb = (int)cl.num_blocks(), rk = (int)cl.block_rank();
+  t.gwarp = rk * kBatchWarps + (threadIdx.x >> 5);
+  t.n_warps = nb * kBatchWarps;
+  t.cthread = rk * kBatchThreads + threadIdx.x;
+  t.n_threads = nb * kBatchThreads;
+  return t;
+}
 
 // A row is consumed in chunks of <= 32 entries: lane t fetches entry t (one coalesced request
 // for the whole chunk), entries are then broadcast with warp shuffles, and the {lb,ub} gathers of
@@ -298,12 +325,13 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
                                                  bool &any_change)
 {
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const TileTeam team = make_team();
+  const int warp = team.gwarp;
   // every row flagged for every box of the tile  (simplePresolve :1618-1622)
-  for (int i = threadIdx.x; i < P.m; i += kBatchThreads) __stcg(flags + i, __ldg(P.row_info + i).y >= 0 ? kFull : 0u);
-  for (int j = threadIdx.x; j < P.n; j += kBatchThreads) __stcg(varflag + j, 0u);
+  for (int i = team.cthread; i < P.m; i += team.n_threads) __stcg(flags + i, __ldg(P.row_info + i).y >= 0 ? kFull : 0u);
+  for (int j = team.cthread; j < P.n; j += team.n_threads) __stcg(varflag + j, 0u);
   if (warp == 0) { sh.changed[lane] = 1; sh.nint[lane] = 0; }
-  __syncthreads();
+  team.sync();
 
   int iters = 1;          // the reference's counter: starts at 1, ++ per sweep
   int my_rounds = 0;
@@ -315,25 +343,25 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
     if (max_rounds > 0 && my_rounds >= max_rounds) run = false;
     if (loop_mode == 1) run = run && iters <= 10 && (iters <= 2 || nint > 0);   // :1625-1627
     const unsigned runmask = __ballot_sync(kFull, run);
-    __syncthreads();                      // everybody has read the previous round's flags
+    team.sync();                      // everybody has read the previous round's flags
     if (runmask == 0) break;
     if (warp == 0) { sh.changed[lane] = 0; sh.nint[lane] = 0; }
     const bool first_sweep = (iters == 1);
     ++iters;
     if (run) ++my_rounds;
-    __syncthreads();
+    team.sync();
 
     // ---- rows, level by level; inside a level each warp owns a contiguous run of rows ----
     for (int lev = 0; lev < P.n_levels; ++lev) {
       const int qb = __ldg(P.level_ptr + lev), qe = __ldg(P.level_ptr + lev + 1);
-      const int per = (qe - qb + kBatchWarps - 1) / kBatchWarps;
+      const int per = (qe - qb + team.n_warps - 1) / team.n_warps;
       const int q_lo = qb + warp * per, q_hi = min(qe, q_lo + per);
+      // boxes already proven infeasible by a row stop sweeping (their result is final); sampled per level
+      const unsigned alive = __ballot_sync(kFull, sh.verdict[lane] == 0);
       for (int q0 = q_lo; q0 < q_hi; q0 += 32) {
         // 32 rows' flag words with one coalesced request (flags live in L2: they are updated by atomics)
         const int q = q0 + lane;
         const uint32_t raw = (q < q_hi) ? __ldcg(flags + q) : 0u;
-        // boxes already proven infeasible by a row stop sweeping (their result is final)
-        const unsigned alive = __ballot_sync(kFull, sh.verdict[lane] == 0);
         const uint32_t fw = raw & runmask & alive;
         unsigned rows = __ballot_sync(kFull, fw != 0u);
         while (rows) {
@@ -345,13 +373,13 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
           process_row<R>(P, q0 + t, bx, ld, (proc >> lane) & 1u, flags, varflag, sh, lane, my_nnz);
         }
       }
-      __syncthreads();
+      team.sync();
     }
 
     // ---- integer rounding + bound check ----
     if (first_sweep) {
       // every variable once: the incoming box may hold fractional integer bounds or crossed bounds
-      for (int j0 = warp * kGather; j0 < P.n; j0 += kBatchWarps * kGather) {
+      for (int j0 = warp * kGather; j0 < P.n; j0 += team.n_warps * kGather) {
         double2 b[kGather];
         const bool want = run && sh.verdict[lane] != 2;     // row-infeasible boxes are frozen
 #pragma unroll
@@ -363,10 +391,10 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
         for (int u = 0; u < kGather; ++u)
           if (j0 + u < P.n) finish_var(P, j0 + u, b[u], want, bx, ld, flags, sh, lane);
       }
-      for (int j = threadIdx.x; j < P.n; j += kBatchThreads) __stcg(varflag + j, 0u);
+      for (int j = team.cthread; j < P.n; j += team.n_threads) __stcg(varflag + j, 0u);
     } else {
       // later sweeps: only variables some row moved in this sweep can need rounding or can cross
-      const int per = (P.n + kBatchWarps - 1) / kBatchWarps;
+      const int per = (P.n + team.n_warps - 1) / team.n_warps;
       const int j_lo = warp * per, j_hi = min(P.n, j_lo + per);
       for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
         const int j = j0 + lane;
@@ -387,7 +415,7 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
     }
     if (bad_row && run && warp == 0 && sh.verdict[lane] == 0) sh.verdict[lane] = 1;
     if (run && sh.changed[lane]) any_change = true;          // benign: read again after the barrier below
-    __syncthreads();
+    team.sync();
     if (run && sh.changed[lane]) any_change = true;
   }
   return my_rounds;
@@ -402,32 +430,33 @@ __device__ __forceinline__ int nl_tile_presolve(const NlDev &N, double2 *bx, int
                                                 bool &any_change)
 {
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const TileTeam team = make_team();
+  const int warp = team.gwarp;
   double nlb[kMaxTape], nub[kMaxTape];
   if (warp == 0) sh.changed[lane] = 1;
-  __syncthreads();
+  team.sync();
   int iters = 1, my_rounds = 0;
   for (;;) {
     const bool run = active && sh.verdict[lane] == 0 && sh.changed[lane] && iters <= 2;    // :1034-1035
     const unsigned runmask = __ballot_sync(kFull, run);
-    __syncthreads();
+    team.sync();
     if (runmask == 0) break;
     if (warp == 0) sh.changed[lane] = 0;
     ++iters;
     if (run) ++my_rounds;
-    __syncthreads();
+    team.sync();
     // chkRed_: read-only, every constraint against the box of the sweep start
-    for (int c = warp; c < N.n_cons; c += kBatchWarps) {
+    for (int c = warp; c < N.n_cons; c += team.n_warps) {
       if (run && sh.verdict[lane] == 0) {
         const int st = nl_chk_red<R>(N, c, bx, ld, nlb, nub);
         if (st != 0) sh.verdict[lane] = st;
       }
     }
-    __syncthreads();
+    team.sync();
     // varBndsFromCons_: constraints of one level touch disjoint variables
     for (int lev = 0; lev < N.n_levels; ++lev) {
       const int qb = __ldg(N.level_ptr + lev), qe = __ldg(N.level_ptr + lev + 1);
-      for (int c = qb + warp; c < qe; c += kBatchWarps) {
+      for (int c = qb + warp; c < qe; c += team.n_warps) {
         if (run && sh.verdict[lane] == 0) {
           int n_mods = 0; unsigned dummy = 0;
           const int st = nl_var_bound_mods<R>(N, c, bx, ld, nlb, nub, n_mods, dummy);
@@ -435,7 +464,7 @@ __device__ __forceinline__ int nl_tile_presolve(const NlDev &N, double2 *bx, int
           else if (n_mods > 0) sh.changed[lane] = 1;
         }
       }
-      __syncthreads();
+      team.sync();
     }
     if (run && sh.changed[lane]) any_change = true;
   }
@@ -450,10 +479,11 @@ __global__ void __launch_bounds__(kBatchThreads, 2)
 fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int max_rounds, int lin_enabled,
                             int nl_enabled)
 {
-  __shared__ TileShared sh;
-  const int tile = blockIdx.x;
+  const TileTeam team = make_team();
+  const int tile = blockIdx.x / (int)cg::this_cluster().num_blocks();
+  TileShared &sh = *reinterpret_cast<TileShared *>(io.tstate + (int64_t)tile * kTileStateBytes);
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const int warp = team.gwarp;
   const int box = tile * 32 + lane;
   const bool active = box < io.n_boxes;
   double2 *bx = io.boxes + box;             // + j*ld addresses variable j of this lane's box
@@ -463,12 +493,14 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
 
   if (warp == 0) { sh.verdict[lane] = 0; sh.nnz[lane] = 0ull; }
   // checkBounds_ rows part is static: a row with lb > ub + eTol makes every box infeasible
+  // (every CTA of the cluster scans all rows, so the flag is identical cluster-wide)
   int bad_row = 0;
   for (int i = threadIdx.x; i < P.m; i += kBatchThreads) {
     const double2 bnd = __ldg(P.row_bnd + i);
     if (__ldg(P.row_info + i).y >= 0 && bnd.x > bnd.y + kETol) bad_row = 1;
   }
   bad_row = __syncthreads_or(bad_row);
+  team.sync();
 
   unsigned long long my_nnz = 0ull;
   int my_rounds = 0;
@@ -485,8 +517,8 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
   }
 
   // ---- per-box results ----
-  atomicAdd(&sh.nnz[lane], my_nnz);
-  __syncthreads();
+  if (my_nnz) atomicAdd(&sh.nnz[lane], my_nnz);
+  team.sync();
   if (warp == 0 && active) {
     io.verdict[box] = sh.verdict[lane];
     io.rounds[box] = my_rounds;
@@ -575,21 +607,45 @@ __global__ void apply_deltas_kernel(const long long *__restrict__ dptr, const in
 
 }  // namespace
 
+namespace {
+template <class R>
+cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, int loop_mode, int max_rounds,
+                           int lin_enabled, int nl_enabled, int tiles, int cluster, cudaStream_t stream)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(tiles * cluster));
+  cfg.blockDim = dim3(kBatchThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R>, P, nl, io, loop_mode, max_rounds, lin_enabled,
+                            nl_enabled);
+}
+}  // namespace
+
 cudaError_t launch_batch_reference(const LinDev &P, const NlDev *N, const BatchIo &io, bool directed,
                                    int loop_mode, int max_rounds, int lin_enabled, int nl_enabled,
-                                   cudaStream_t stream)
+                                   int sm_count, cudaStream_t stream)
 {
   const int tiles = (io.n_boxes + 31) / 32;
   if (tiles <= 0) return cudaSuccess;
   NlDev nl{};
   if (N != nullptr && nl_enabled) nl = *N; else nl_enabled = 0;
-  if (directed)
-    fbbt_batch_reference_kernel<RoundDirected><<<tiles, kBatchThreads, 0, stream>>>(P, nl, io, loop_mode, max_rounds,
-                                                                                   lin_enabled, nl_enabled);
-  else
-    fbbt_batch_reference_kernel<RoundNearest><<<tiles, kBatchThreads, 0, stream>>>(P, nl, io, loop_mode, max_rounds,
-                                                                                  lin_enabled, nl_enabled);
-  return cudaGetLastError();
+  // A tile's level-ordered sweep is a chain of short, latency-bound steps; when there are fewer tiles than
+  // CTA slots, a thread-block CLUSTER of up to 8 CTAs (8 SMs) shares one tile and cluster.sync() is the
+  // level barrier.  Two CTAs of this kernel fit on an SM.
+  int cluster = 1;
+  const int slots = 2 * sm_count;
+  while (cluster < 8 && tiles * cluster * 2 <= slots) cluster *= 2;
+  if (const char *e = getenv("MNTR_GPU_CLUSTER")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8) cluster = c; }
+  return directed ? launch_cluster<RoundDirected>(P, nl, io, loop_mode, max_rounds, lin_enabled, nl_enabled, tiles, cluster, stream)
+                  : launch_cluster<RoundNearest>(P, nl, io, loop_mode, max_rounds, lin_enabled, nl_enabled, tiles, cluster, stream);
 }
 
 cudaError_t launch_boxes_pack(const double *lb_bm, const double *ub_bm, int32_t n, int32_t box0, int32_t nb,

@@ -53,6 +53,7 @@ struct mntr_gpu_ctx {
   int64_t batch_ld = 0;        // capacity in boxes (multiple of 32)
   double2 *d_boxes = nullptr;
   uint32_t *d_rowflag = nullptr, *d_varflag = nullptr;
+  unsigned char *d_tstate = nullptr;
   int32_t *d_verdict = nullptr, *d_rounds = nullptr;
   long long *d_nnzb = nullptr;
   double *d_stage_lb = nullptr, *d_stage_ub = nullptr;
@@ -161,10 +162,10 @@ void free_stage(mntr_gpu_ctx *c)
 
 void free_batch(mntr_gpu_ctx *c)
 {
-  cudaFree(c->d_boxes); cudaFree(c->d_rowflag); cudaFree(c->d_varflag); cudaFree(c->d_verdict); cudaFree(c->d_rounds);
+  cudaFree(c->d_boxes); cudaFree(c->d_rowflag); cudaFree(c->d_varflag); cudaFree(c->d_tstate); cudaFree(c->d_verdict); cudaFree(c->d_rounds);
   cudaFree(c->d_nnzb);
   c->d_boxes = nullptr; c->d_rowflag = nullptr; c->d_verdict = nullptr; c->d_rounds = nullptr;
-  c->d_nnzb = nullptr; c->d_varflag = nullptr;
+  c->d_nnzb = nullptr; c->d_varflag = nullptr; c->d_tstate = nullptr;
   c->batch_ld = 0;
 }
 
@@ -178,6 +179,7 @@ int ensure_batch(mntr_gpu_ctx *ctx, int32_t n_boxes, bool need_boxes)
     CU(cudaMalloc((void **)&ctx->d_boxes, sizeof(double2) * (size_t)std::max<int64_t>(1, (int64_t)ctx->n * ld)));
   CU(cudaMalloc((void **)&ctx->d_rowflag, sizeof(uint32_t) * (size_t)std::max<int64_t>(1, (int64_t)ctx->m * tiles)));
   CU(cudaMalloc((void **)&ctx->d_varflag, sizeof(uint32_t) * (size_t)std::max<int64_t>(1, (int64_t)ctx->n * tiles)));
+  CU(cudaMalloc((void **)&ctx->d_tstate, (size_t)kTileStateBytes * (size_t)tiles));
   CU(cudaMalloc((void **)&ctx->d_verdict, sizeof(int32_t) * (size_t)ld));
   CU(cudaMalloc((void **)&ctx->d_rounds, sizeof(int32_t) * (size_t)ld));
   CU(cudaMalloc((void **)&ctx->d_nnzb, sizeof(long long) * (size_t)ld));
@@ -768,13 +770,13 @@ int mntr_gpu_tighten_dev(mntr_gpu_ctx *ctx, int32_t n_boxes, void *boxes_dev, co
   int rc = ensure_batch(ctx, n_boxes, false);
   if (rc) return rc;
   BatchIo io;
-  io.boxes = (double2 *)boxes_dev; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag;
+  io.boxes = (double2 *)boxes_dev; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
   io.verdict = verdict_dev; io.rounds = rounds_dev; io.nnz = (long long *)nnz_dev;
   (void)tiles;
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
                             o.loop, o.max_rounds, o.handlers != MNTR_HANDLERS_NONLINEAR,
-                            (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR) ? 1 : 0, ctx->stream));
+                            (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR) ? 1 : 0, ctx->sm_count, ctx->stream));
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->stats = mntr_gpu_stats{};
@@ -814,12 +816,12 @@ int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   if ((rc = mntr_gpu_boxes_upload(ctx, n_boxes, lb, ub, ctx->d_boxes))) return rc;
   BatchIo io;
-  io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag;
+  io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
   io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb;
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
                             o.loop, o.max_rounds, o.handlers != MNTR_HANDLERS_NONLINEAR,
-                            (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR) ? 1 : 0, ctx->stream));
+                            (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR) ? 1 : 0, ctx->sm_count, ctx->stream));
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   if ((rc = mntr_gpu_boxes_download(ctx, n_boxes, ctx->d_boxes, lb, ub))) return rc;
   std::vector<int32_t> hv(n_boxes), hr(n_boxes);
