@@ -5,15 +5,15 @@
 namespace mntr {
 
 // Linear rows, stored in (wavefront level, original index) order with deleted rows last.
-// CSR whose row starts are padded to an EVEN entry index so a lane can fetch
-// two (col,val) pairs with one 64-bit + one 128-bit load; padding entries have val == 0 and
+// CSR whose rows are padded to a multiple of FOUR entries so a lane can fetch four (col,val) pairs
+// with one 128-bit column load and two 128-bit value loads; padding entries have val == 0 and
 // a valid column, and are skipped by value.  CSC (var -> rows) replaces Variable::cons_
 // (Variable.h:164-191) for the bFlag propagation of LinearHandler::changeBFlag_ (:1229-1234).
 struct LinDev {
   int32_t m, n;
-  const int2    *row_info;  // [m] {first entry (even), true term count; count < 0 marks a deleted row}
+  const int2    *row_info;  // [m] {first entry (multiple of 4), true term count; count < 0 marks a deleted row}
   const double2 *row_bnd;   // [m] {row lb, row ub}
-  const int32_t *col;       // [nnz_padded]  a row occupies entries [beg, beg + roundup2(count))
+  const int32_t *col;       // [nnz_padded]  a row occupies entries [beg, beg + roundup4(count))
   const double  *val;       // [nnz_padded]
   const uint8_t *var_type;  // [n]
   const int32_t *csc_ptr;   // [n+1]
@@ -23,7 +23,9 @@ struct LinDev {
   const int32_t *level_ptr; // [n_levels+1] ranges of STORED rows (rows are stored in level order)
 };
 
-__device__ __forceinline__ int row_end(int2 info) { return info.x + ((info.y + 1) & ~1); }
+// rows are padded to a multiple of kRowPad entries (padding: val == 0, a valid column)
+constexpr int kRowPad = 4;
+__host__ __device__ __forceinline__ int row_end(int2 info) { return info.x + ((info.y + kRowPad - 1) & ~(kRowPad - 1)); }
 
 // CGraph tapes (see include/mntr_gpu.h for the node order contract)
 struct NlDev {

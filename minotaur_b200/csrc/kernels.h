@@ -16,7 +16,7 @@ cudaError_t launch_single_jacobi(const LinDev &P, const SingleWs &W, double *lb_
 // K5 (linear_rounds.cu): one Jacobi round as separate launches (row-partitioned multi-GPU mode)
 cudaError_t launch_rounds_init(const LinDev &P, const RoundsWs &W, const double *lb_dev, const double *ub_dev,
                                int sm_count, cudaStream_t stream);
-cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per_row, bool directed, int count,
+cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per_row, bool directed,
                                int first, int sm_count, cudaStream_t stream);
 cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream);
 cudaError_t launch_rounds_finish(const LinDev &P, const RoundsWs &W, double *lb_dev, double *ub_dev, int sm_count,

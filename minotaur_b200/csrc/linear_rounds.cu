@@ -39,25 +39,14 @@ __global__ void rounds_init_kernel(LinDev P, RoundsWs W, const double *lb_io, co
 }
 
 template <int G, class R>
-__global__ void __launch_bounds__(kRoundsThreads)
-rounds_rows_kernel(LinDev P, RoundsWs W, int count, int first)
+__global__ void __launch_bounds__(kRoundsThreads, 4)
+rounds_rows_kernel(LinDev P, RoundsWs W, int first)
 {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31, lane_g = lane % G;
-  const int group = tid / G, n_groups = nthreads / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lane_g));
+  const int lane = threadIdx.x & 31;
   const SinkSplit sink{W.nlb, W.nub, P.n};
   unsigned long long my_nnz = 0, my_rows = 0;
-  const bool f = first != 0;
-  RowMeta mC = load_meta(P, W.list, group, count, f);
-  RowData dC = load_data(P, mC, lane_g);
-  RowMeta mB = load_meta(P, W.list, group + n_groups, count, f);
-  for (int idx = group; idx < count; idx += n_groups) {
-    const RowData dB = load_data(P, mB, lane_g);
-    const RowMeta mA = load_meta(P, W.list, idx + 2 * n_groups, count, f);
-    if (mC.i >= 0) process_row<G, R>(P, W.box, W.bits, W.ctrl, sink, mC, dC, lane_g, gmask, f, my_nnz, my_rows);
-    mC = mB; dC = dB; mB = mA;
-  }
+  process_rows<G, R>(P, W.box, W.bits, W.ctrl, sink, tid >> 5, nthreads >> 5, first != 0, my_nnz, my_rows);
   __shared__ unsigned long long s_nnz, s_rows;
   if (threadIdx.x == 0) { s_nnz = 0ull; s_rows = 0ull; }
   __syncthreads();
@@ -71,7 +60,7 @@ rounds_rows_kernel(LinDev P, RoundsWs W, int count, int first)
   if (threadIdx.x == 0 && s_rows) { atomicAdd(&W.counters[0], s_nnz); atomicAdd(&W.counters[1], s_rows); }
 }
 
-// ctrl: [0] changed  [1] int moved  [2] next work-list length  [3] verdict  [4] changed (var,round) pairs
+// ctrl: [0] changed  [1] int moved  [3] verdict  [4] changed (var,round) pairs
 __global__ void __launch_bounds__(kRoundsThreads)
 rounds_vars_kernel(LinDev P, RoundsWs W)
 {
@@ -100,22 +89,9 @@ rounds_vars_kernel(LinDev P, RoundsWs W)
         const int t = __ffs(chm) - 1;
         chm &= chm - 1;
         const int qb = __ldg(P.csc_ptr + j0 + t), qe = __ldg(P.csc_ptr + j0 + t + 1);
-        for (int q0 = qb; q0 < qe; q0 += 32) {
-          const int q = q0 + lane;
-          bool fresh = false; int row = 0;
-          if (q < qe) {
-            row = __ldg(P.csc_row + q);
-            const unsigned bit = 1u << (row & 31);
-            fresh = (atomicOr(W.bits + (row >> 5), bit) & bit) == 0u;
-          }
-          const unsigned want = __ballot_sync(0xffffffffu, fresh);
-          if (want) {
-            int base = 0;
-            const int leader = __ffs(want) - 1;
-            if (lane == leader) base = atomicAdd(&W.ctrl[2], __popc(want));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (fresh) W.list[base + __popc(want & ((1u << lane) - 1u))] = row;
-          }
+        for (int q = qb + lane; q < qe; q += 32) {       // fire-and-forget OR into this rank's row bit set
+          const int row = __ldg(P.csc_row + q);
+          atomicOr(W.bits + (row >> 5), 1u << (row & 31));
         }
       }
     }
@@ -156,16 +132,16 @@ int grid_for(long long items, int sm_count)
 }
 
 template <class R>
-cudaError_t rows_r(int G, const LinDev &P, const RoundsWs &W, int count, int first, int sm_count, cudaStream_t s)
+cudaError_t rows_r(int G, const LinDev &P, const RoundsWs &W, int first, int sm_count, cudaStream_t s)
 {
-  if (count <= 0) return cudaSuccess;
-  const int blocks = grid_for((long long)count * G, sm_count);
+  if (P.m <= 0) return cudaSuccess;
+  const int blocks = grid_for((long long)P.m * G, sm_count);
   switch (G) {
-  case 2:  rounds_rows_kernel<2, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
-  case 4:  rounds_rows_kernel<4, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
-  case 8:  rounds_rows_kernel<8, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
-  case 16: rounds_rows_kernel<16, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
-  default: rounds_rows_kernel<32, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, count, first); break;
+  case 2:  rounds_rows_kernel<2, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
+  case 4:  rounds_rows_kernel<4, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
+  case 8:  rounds_rows_kernel<8, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
+  case 16: rounds_rows_kernel<16, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
+  default: rounds_rows_kernel<32, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
   }
   return cudaGetLastError();
 }
@@ -179,11 +155,11 @@ cudaError_t launch_rounds_init(const LinDev &P, const RoundsWs &W, const double 
   return cudaGetLastError();
 }
 
-cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per_row, bool directed, int count,
+cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per_row, bool directed,
                                int first, int sm_count, cudaStream_t stream)
 {
-  if (directed) return rows_r<RoundDirected>(lanes_per_row, P, W, count, first, sm_count, stream);
-  return rows_r<RoundNearest>(lanes_per_row, P, W, count, first, sm_count, stream);
+  if (directed) return rows_r<RoundDirected>(lanes_per_row, P, W, first, sm_count, stream);
+  return rows_r<RoundNearest>(lanes_per_row, P, W, first, sm_count, stream);
 }
 
 cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream)

@@ -46,11 +46,12 @@ __device__ __forceinline__ int group_reduce_int(int v, unsigned mask)
   return v;
 }
 
+// What a row offers its terms once its activities are known.  slack_* = +inf means "this side yields
+// nothing", so the per-term product test below rejects without looking at the side at all.
 struct RowCtx {
-  double rl, ru;       // row bounds
-  double act_lb;       // activity used by FromLb (uu or sing_uu)
-  double act_ub;       // activity used by FromUb (ll or sing_ll)
-  bool do_lb, do_ub, sing_lb, sing_ub;
+  double slack_lb;     // max activity - row lb   (>= -eTol)        [updateLfBoundsFromLb_]
+  double slack_ub;     // row ub - min activity   (>= -eTol)        [updateLfBoundsFromUb_]
+  bool sing_lb, sing_ub;   // singleton-infinity mode of that side
 };
 
 // branch-free term of getLfBnds_: an absent entry has a == 0 and b == {0,0}, contributing +0
@@ -63,30 +64,26 @@ __device__ __forceinline__ void accumulate(double a, double2 b, double &ll, doub
   uu = R::add_hi(uu, R::mul_hi(a, bhi));
 }
 
-// one term of pass 2: candidates of updateLfBoundsFromLb_ / updateLfBoundsFromUb_.
+// Exact candidates of one term (rare path, taken only when the product test cannot rule them out).
 //
 // Both row sides and both coefficient signs obey one rule: the candidate moves ONE bound of x_j
-// towards the other by  slack/|a|,  slack = (max activity - row lb)  or  (row ub - min activity):
+// towards the other by slack/|a|:
 //     a>0, lb side: new lb = ub_j - slack/a        a<0, lb side: new ub = lb_j + slack/|a|
 //     a>0, ub side: new ub = lb_j + slack/a        a<0, ub side: new lb = ub_j - slack/|a|
-// so it can only be accepted when slack < |a| * (ub_j - lb_j).  That product test (one DADD, one
-// DMUL, shared by both sides) rejects almost every term of a round without the fp64 division; it
-// is conservative (1e-9 relative margin, NaN/inf fall through), so results are unchanged.
 // With directed rounding the division is taken on |a| (round_up(x/a) == -round_down(x/|a|) for
 // a<0; in round-to-nearest x/a == -(x/|a|) exactly), so the sign only picks the bound that moves.
+// numer = rl - act (lb side, rounded down) / ru - act (ub side, rounded up) as the reference forms it.
 template <class R, class Sink>
-__device__ __forceinline__ void emit_candidates(const RowCtx &rc, double a, int j, double2 b,
-                                                const Sink &sink)
+__device__ __forceinline__ void emit_exact(const RowCtx rc, double a, int j, double2 b, const Sink sink)
 {
   const double vl = b.x, vu = b.y;
   const double aa = fabs(a);
   if (!(aa > kETol)) return;
   const bool pos = a > 0.0;
-  const double reach = aa * (vu - vl) * 1.000000001;      // inf or NaN when a bound is infinite
-  if (rc.do_lb) {                                   // row lb side: numer = rl - max activity = -slack
-    const double numer = R::sub_lo(rc.rl, rc.act_lb);
+  if (rc.slack_lb < INFINITY) {
+    const double numer = -rc.slack_lb;
     const bool inf_side = pos ? (vu >= kInf20) : (vl <= -kInf20);
-    if ((!rc.sing_lb || inf_side) && !(-numer > reach)) {
+    if (!rc.sing_lb || inf_side) {
       const double base = inf_side ? 0.0 : (pos ? vu : vl);
       const double t = R::div_lo(numer, aa);        // round_down((rl - act)/|a|)
       if (pos) {
@@ -98,10 +95,10 @@ __device__ __forceinline__ void emit_candidates(const RowCtx &rc, double a, int 
       }
     }
   }
-  if (rc.do_ub) {                                   // row ub side: numer = ru - min activity = slack
-    const double numer = R::sub_hi(rc.ru, rc.act_ub);
+  if (rc.slack_ub < INFINITY) {
+    const double numer = rc.slack_ub;
     const bool inf_side = pos ? (vl <= -kInf20) : (vu >= kInf20);
-    if ((!rc.sing_ub || inf_side) && !(numer > reach)) {
+    if (!rc.sing_ub || inf_side) {
       const double base = inf_side ? 0.0 : (pos ? vl : vu);
       const double sq = R::div_hi(numer, aa);       // round_up((ru - act)/|a|)
       if (pos) {
@@ -115,63 +112,94 @@ __device__ __forceinline__ void emit_candidates(const RowCtx &rc, double a, int 
   }
 }
 
-// pipeline registers of one row
-struct RowMeta { int i, beg, cnt; };                  // i < 0: nothing to do; cnt = true term count
-struct RowData { double2 a2; int2 c2; };              // this lane's first entry pair (a == 0: none)
-
-__device__ __forceinline__ RowMeta load_meta(const LinDev &P, const int32_t *list, int idx, int count, bool first)
+// Product test: a candidate can only be accepted when slack < |a| * (ub_j - lb_j).  One DADD and two
+// DMULs shared by both sides reject almost every term of a round without the fp64 division; the test
+// is conservative (1e-9 relative margin; an infinite or NaN reach falls through to the exact path), so
+// results are unchanged.
+template <class R, class Sink>
+__device__ __forceinline__ void emit_candidates(const RowCtx &rc, double a, int j, double2 b, const Sink &sink)
 {
-  RowMeta r; r.i = -1; r.beg = 0; r.cnt = 0;
-  if (idx < count) {
-    const int i = first ? idx : list[idx];
-    const int2 info = __ldg(P.row_info + i);
-    if (info.y >= 0) { r.i = i; r.beg = info.x; r.cnt = info.y; }   // deleted rows are never evaluated
-  }
-  return r;
+  const double reach = fabs(a) * (b.y - b.x) * 1.000000001;
+  if (!(rc.slack_lb > reach) || !(rc.slack_ub > reach)) emit_exact<R, Sink>(rc, a, j, b, sink);
 }
 
-__device__ __forceinline__ RowData load_data(const LinDev &P, const RowMeta &r, int lane_g)
+// this lane's first four entries of a row (a == 0: none)
+struct RowData { double2 a01, a23; int4 c; };
+
+__device__ __forceinline__ RowData load_data(const LinDev &P, int beg, int cnt, int lane_g)
 {
-  RowData d; d.a2 = make_double2(0.0, 0.0); d.c2 = make_int2(0, 0);
-  const int t = 2 * lane_g;
-  if (r.i >= 0 && t < r.cnt) {
-    d.a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + r.beg + t));
-    d.c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + r.beg + t));
+  RowData d;
+  d.a01 = make_double2(0.0, 0.0); d.a23 = d.a01; d.c = make_int4(0, 0, 0, 0);
+  const int t = 4 * lane_g;
+  if (t < cnt) {       // rows are padded to a multiple of 4 entries: the three 128-bit loads stay inside the row
+    d.a01 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + beg + t));
+    d.a23 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + beg + t + 2));
+    d.c = __ldg(reinterpret_cast<const int4 *>(P.col + beg + t));
   }
   return d;
 }
 
-// one flagged row: activities, infeasibility, candidates   [linBndTighten_, Jacobi form]
-template <int G, class R, class Sink>
-__device__ __forceinline__ void process_row(const LinDev &P, const double2 *box, uint32_t *bits, int32_t *status,
-                                            const Sink &sink, const RowMeta &r, const RowData &d,
-                                            int lane_g, unsigned gmask, bool first, unsigned long long &my_nnz,
-                                            unsigned long long &my_rows)
+// singleton-infinity sums (getSingLfBnds_, LinearHandler.cpp:1261-1319) as finite-sum + infinity-count
+// per side; rare path
+template <int G, class R>
+__device__ __noinline__ void sing_activity(const LinDev &P, const double2 *box, int beg, int end, int lane_g,
+                                           unsigned gmask, double &sing_ll, double &sing_uu)
 {
-  const int i = r.i;
-  const int end = r.beg + ((r.cnt + 1) & ~1);
-  RowCtx rc;
-  const double2 bnd = __ldg(P.row_bnd + i);
-  rc.rl = bnd.x;
-  rc.ru = bnd.y;
-  if (lane_g == 0) {
-    my_nnz += (unsigned long long)r.cnt; ++my_rows;
-    if (!first) atomicAnd(bits + (i >> 5), ~(1u << (i & 31)));       // setBFlag(false), :513
+  double fs_lo = 0.0, fs_hi = 0.0;
+  int ninf_lo = 0, ninf_hi = 0;
+  for (int t = beg + lane_g; t < end; t += G) {
+    {
+      const double a = __ldg(P.val + t);
+      const int j = __ldg(P.col + t);
+      if (a > kETol) {
+        const double2 b = box[j];
+        if (b.y < kInf20) fs_hi = R::add_hi(fs_hi, R::mul_hi(a, b.y)); else ++ninf_hi;
+        if (b.x > -kInf20) fs_lo = R::add_lo(fs_lo, R::mul_lo(a, b.x)); else ++ninf_lo;
+      } else if (a < -kETol) {
+        const double2 b = box[j];
+        if (b.y < kInf20) fs_lo = R::add_lo(fs_lo, R::mul_lo(a, b.y)); else ++ninf_lo;
+        if (b.x > -kInf20) fs_hi = R::add_hi(fs_hi, R::mul_hi(a, b.x)); else ++ninf_hi;
+      }
+    }
   }
-  // pass 1: the first entry pair is already in registers, its two gathers go out together
-  double2 b0 = make_double2(0.0, 0.0), b1 = b0;
-  if (d.a2.x != 0.0) b0 = box[d.c2.x];
-  if (d.a2.y != 0.0) b1 = box[d.c2.y];
+  fs_lo = group_reduce<G, R, true>(fs_lo, gmask);
+  fs_hi = group_reduce<G, R, false>(fs_hi, gmask);
+  ninf_lo = group_reduce_int<G>(ninf_lo, gmask);
+  ninf_hi = group_reduce_int<G>(ninf_hi, gmask);
+  sing_ll = (ninf_lo >= 2) ? -INFINITY : fs_lo;
+  sing_uu = (ninf_hi >= 2) ? INFINITY : fs_hi;
+}
+
+// one flagged row: activities, infeasibility, candidates   [linBndTighten_, Jacobi form]
+// Row i has `cnt` terms starting at entry `beg`; each lane owns four consecutive entries (two 128-bit
+// value loads + one 128-bit column load), so a group of G lanes covers 4G entries per step and most rows
+// take a single step.  The four {lb,ub} gathers of a lane are issued together.
+template <int G, class R, class Sink>
+__device__ __forceinline__ void process_row(const LinDev &P, const double2 *box, int32_t *status,
+                                            const Sink &sink, int i, int beg, int cnt, int lane_g, unsigned gmask,
+                                            unsigned long long &my_nnz, unsigned long long &my_rows)
+{
+  const RowData d = load_data(P, beg, cnt, lane_g);
+  const double2 bnd = __ldg(P.row_bnd + i);
+  const double rl = bnd.x, ru = bnd.y;
+  if (lane_g == 0) { my_nnz += (unsigned long long)cnt; ++my_rows; }
+  // pass 1: an absent entry (a == 0) reads a zero box so that it contributes exactly +0
+  const double2 zero = make_double2(0.0, 0.0);
+  const double2 b0 = (d.a01.x != 0.0) ? box[d.c.x] : zero;
+  const double2 b1 = (d.a01.y != 0.0) ? box[d.c.y] : zero;
+  const double2 b2 = (d.a23.x != 0.0) ? box[d.c.z] : zero;
+  const double2 b3 = (d.a23.y != 0.0) ? box[d.c.w] : zero;
   double ll = 0.0, uu = 0.0;
-  accumulate<R>(d.a2.x, b0, ll, uu);
-  accumulate<R>(d.a2.y, b1, ll, uu);
-  const bool long_row = r.cnt > 2 * G;                      // group-uniform
+  accumulate<R>(d.a01.x, b0, ll, uu);
+  accumulate<R>(d.a01.y, b1, ll, uu);
+  accumulate<R>(d.a23.x, b2, ll, uu);
+  accumulate<R>(d.a23.y, b3, ll, uu);
+  const bool long_row = cnt > 4 * G;                        // group-uniform
+  const int end = row_end(make_int2(beg, cnt));
   if (long_row) {
-    for (int t = r.beg + 2 * lane_g + 2 * G; t < end; t += 2 * G) {
-      const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
-      const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
-      if (a2.x != 0.0) accumulate<R>(a2.x, box[c2.x], ll, uu);
-      if (a2.y != 0.0) accumulate<R>(a2.y, box[c2.y], ll, uu);
+    for (int t = beg + 4 * G + lane_g; t < end; t += G) {
+      const double a = __ldg(P.val + t);
+      if (a != 0.0) accumulate<R>(a, box[__ldg(P.col + t)], ll, uu);
     }
   }
   ll = group_reduce<G, R, true>(ll, gmask);
@@ -179,59 +207,76 @@ __device__ __forceinline__ void process_row(const LinDev &P, const double2 *box,
 
   // singleton-infinity sums, only when an activity is beyond +-1e20 (:970-972)
   double sing_ll = -INFINITY, sing_uu = INFINITY;
-  if (ll < -kInf20 || uu > kInf20) {
-    double fs_lo = 0.0, fs_hi = 0.0;
-    int ninf_lo = 0, ninf_hi = 0;
-    for (int t = r.beg + 2 * lane_g; t < end; t += 2 * G) {
-      const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
-      const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const double a = h ? a2.y : a2.x;
-        const int j = h ? c2.y : c2.x;
-        if (a > kETol) {
-          const double2 b = box[j];
-          if (b.y < kInf20) fs_hi = R::add_hi(fs_hi, R::mul_hi(a, b.y)); else ++ninf_hi;
-          if (b.x > -kInf20) fs_lo = R::add_lo(fs_lo, R::mul_lo(a, b.x)); else ++ninf_lo;
-        } else if (a < -kETol) {
-          const double2 b = box[j];
-          if (b.y < kInf20) fs_lo = R::add_lo(fs_lo, R::mul_lo(a, b.y)); else ++ninf_lo;
-          if (b.x > -kInf20) fs_hi = R::add_hi(fs_hi, R::mul_hi(a, b.x)); else ++ninf_hi;
-        }
-      }
-    }
-    fs_lo = group_reduce<G, R, true>(fs_lo, gmask);
-    fs_hi = group_reduce<G, R, false>(fs_hi, gmask);
-    ninf_lo = group_reduce_int<G>(ninf_lo, gmask);
-    ninf_hi = group_reduce_int<G>(ninf_hi, gmask);
-    sing_ll = (ninf_lo >= 2) ? -INFINITY : fs_lo;
-    sing_uu = (ninf_hi >= 2) ? INFINITY : fs_hi;
-  }
+  if (ll < -kInf20 || uu > kInf20) sing_activity<G, R>(P, box, beg, end, lane_g, gmask, sing_ll, sing_uu);
 
-  if (ll > rc.ru + kETol || uu < rc.rl - kETol) {     // activity-infeasible row
+  if (ll > ru + kETol || uu < rl - kETol) {     // activity-infeasible row (:994-1015)
     if (lane_g == 0) sink.row_infeasible(status);
     return;
   }
-  rc.do_lb = rc.do_ub = rc.sing_lb = rc.sing_ub = false;
-  rc.act_lb = rc.act_ub = 0.0;
-  if (rc.rl > -kInf20) {
-    if (uu < kInf20) { rc.do_lb = true; rc.act_lb = uu; }
-    else if (sing_uu < kInf20) { rc.do_lb = true; rc.sing_lb = true; rc.act_lb = sing_uu; }
+  RowCtx rc;
+  rc.slack_lb = INFINITY; rc.slack_ub = INFINITY;
+  rc.sing_lb = false; rc.sing_ub = false;
+  if (rl > -kInf20) {                            // :1017-1025
+    if (uu < kInf20) rc.slack_lb = -R::sub_lo(rl, uu);
+    else if (sing_uu < kInf20) { rc.slack_lb = -R::sub_lo(rl, sing_uu); rc.sing_lb = true; }
   }
-  if (rc.ru < kInf20) {
-    if (ll > -kInf20) { rc.do_ub = true; rc.act_ub = ll; }
-    else if (sing_ll > -kInf20) { rc.do_ub = true; rc.sing_ub = true; rc.act_ub = sing_ll; }
+  if (ru < kInf20) {                             // :1035-1043
+    if (ll > -kInf20) rc.slack_ub = R::sub_hi(ru, ll);
+    else if (sing_ll > -kInf20) { rc.slack_ub = R::sub_hi(ru, sing_ll); rc.sing_ub = true; }
   }
-  if (!rc.do_lb && !rc.do_ub) return;
-  // pass 2: implied bounds; the first pair and its bounds are still in registers
-  if (d.a2.x != 0.0) emit_candidates<R>(rc, d.a2.x, d.c2.x, b0, sink);
-  if (d.a2.y != 0.0) emit_candidates<R>(rc, d.a2.y, d.c2.y, b1, sink);
+  // pass 2: implied bounds; the lane's entries and their bounds are still in registers
+  emit_candidates<R>(rc, d.a01.x, d.c.x, b0, sink);
+  emit_candidates<R>(rc, d.a01.y, d.c.y, b1, sink);
+  emit_candidates<R>(rc, d.a23.x, d.c.z, b2, sink);
+  emit_candidates<R>(rc, d.a23.y, d.c.w, b3, sink);
   if (long_row) {
-    for (int t = r.beg + 2 * lane_g + 2 * G; t < end; t += 2 * G) {
-      const double2 a2 = ldg_f64x2(reinterpret_cast<const double2 *>(P.val + t));
-      const int2 c2 = ldg_i32x2(reinterpret_cast<const int2 *>(P.col + t));
-      if (a2.x != 0.0) emit_candidates<R>(rc, a2.x, c2.x, box[c2.x], sink);
-      if (a2.y != 0.0) emit_candidates<R>(rc, a2.y, c2.y, box[c2.y], sink);
+    for (int t = beg + 4 * G + lane_g; t < end; t += G) {
+      const double a = __ldg(P.val + t);
+      const int j = __ldg(P.col + t);
+      if (a != 0.0) emit_candidates<R>(rc, a, j, box[j], sink);
+    }
+  }
+}
+
+// The rows of one phase.  A warp holds 32/G groups and takes the rows in chunks of 32/G consecutive rows:
+// group g of the warp gets row chunk*(32/G)+g.  Which rows are due is a BIT SET (one bit per row, the
+// reference's Constraint bFlag): the warp reads its chunk's bits from one word, clears them with a
+// fire-and-forget atomic, and each group whose bit is set evaluates its row.  In the first round every
+// stored row is due and the bit set is not consulted.
+template <int G, class R, class Sink>
+__device__ __forceinline__ void process_rows(const LinDev &P, const double2 *box, uint32_t *bits, int32_t *status,
+                                             const Sink &sink, int warp_global, int n_warps, bool first,
+                                             unsigned long long &my_nnz, unsigned long long &my_rows)
+{
+  constexpr int GPW = 32 / G;                    // groups (= rows) per warp step
+  const int lane = threadIdx.x & 31;
+  const int lane_g = lane % G, g = lane / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lane_g));
+  const int n_chunks = (P.m + GPW - 1) / GPW;
+  const unsigned full = (GPW == 32) ? 0xffffffffu : ((1u << GPW) - 1u);
+  // the warp's chunks are warp_global, warp_global + n_warps, ...; the due-bits of 32 of them are fetched
+  // at once (lane l looks at the l-th), so chunks with nothing due cost no dependent load
+  for (int it0 = 0; warp_global + (long long)it0 * n_warps < n_chunks; it0 += 32) {
+    const long long cl = warp_global + (long long)(it0 + lane) * n_warps;
+    unsigned due_l = 0u;
+    if (cl < n_chunks) {
+      if (first) due_l = full;
+      else {
+        const int row0 = (int)cl * GPW;
+        due_l = (__ldcg(bits + (row0 >> 5)) >> (row0 & 31)) & full;     // bits are set by L2 atomics: bypass L1
+        if (due_l) atomicAnd(bits + (row0 >> 5), ~(due_l << (row0 & 31)));   // setBFlag(false), :513
+      }
+    }
+    unsigned active = __ballot_sync(0xffffffffu, due_l != 0u);
+    while (active) {
+      const int l = __ffs(active) - 1;
+      active &= active - 1;
+      const unsigned due = __shfl_sync(0xffffffffu, due_l, l);
+      const int i = (warp_global + (it0 + l) * n_warps) * GPW + g;
+      if (!((due >> g) & 1u) || i >= P.m) continue;             // group-uniform
+      const int2 info = __ldg(P.row_info + i);
+      if (info.y < 0) continue;                                 // deleted rows are never evaluated
+      process_row<G, R>(P, box, status, sink, i, info.x, info.y, lane_g, gmask, my_nnz, my_rows);
     }
   }
 }

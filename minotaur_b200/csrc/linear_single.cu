@@ -2,19 +2,18 @@
 // inside ONE cooperative launch (device-side change flag and work list, no host round trips).
 //
 // Per round (reference lines in brackets):
-//   rows phase : sub-warp group per flagged CSR row -- 128-bit loads of (val,val) and
-//                64-bit loads of (col,col), 128-bit gathers of {lb,ub}; min/max activity
+//   rows phase : sub-warp group per flagged CSR row, four entries per lane -- two 128-bit value
+//                loads, one 128-bit column load, four 128-bit gathers of {lb,ub}; min/max activity
 //                with outward rounding [getLfBnds_ LinearHandler.cpp:1237-1258]; singleton-
 //                infinity sums by finite-sum + infinity-count [getSingLfBnds_ :1261-1319];
 //                warp-shuffle butterfly reduction; activity infeasibility [:994-1015];
 //                implied bounds [updateLfBoundsFromLb_/Ub_ :1048-1226] merged with fp64
-//                atomic max/min into the next box.  The loop over a group's rows is software
-//                pipelined three deep (row ids / CSR entries / gathers of three different rows
-//                are in flight together): at this size the phase is latency-, not bandwidth-bound.
+//                atomic max/min into the next box.  A product test skips the fp64 division for terms
+//                that cannot tighten anything.
 //   vars phase : integer rounding [tightenInts_ :415-490], lb>ub check [checkBounds_
 //                :328-359], change detection; the rows of every changed variable
-//                [changeBFlag_ :1229-1234] are appended once (bit-set test-and-set) to the work
-//                list of the next round with warp-aggregated atomics.
+//                [changeBFlag_ :1229-1234] are flagged in a bit set with fire-and-forget atomics
+//                (a warp walks a changed variable's CSC list with one entry per lane).
 // A device-wide barrier (one arrive counter, acquire polling) separates the phases; the loop
 // condition is evaluated on the device from the round's change flags.
 #include "device_problem.cuh"
@@ -68,10 +67,6 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  const int lane_g = lane % G;
-  const int group = tid / G;
-  const int n_groups = nthreads / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lane_g));
   unsigned bar_target = 0;
   __shared__ int s_count;
   __shared__ unsigned long long s_nnz, s_rows;
@@ -102,28 +97,17 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
   unsigned long long my_nnz = 0, my_rows = 0;
   int round = 0;
   int verdict = vstatus[0];
-  int count = P.m;                         // work items of the current round
 
   while (verdict == 0) {
     ++round;
     const int slot = round % 3;
-    // ring[slot]: changed, ring[3+slot]: int moved, ring[6+slot]: next round's list length
-    if (tid == 0) { const int nx = (round + 1) % 3; W.ring[nx] = 0; W.ring[3 + nx] = 0; W.ring[6 + nx] = 0; }
+    // ring[slot]: changed, ring[3+slot]: int moved
+    if (tid == 0) { const int nx = (round + 1) % 3; W.ring[nx] = 0; W.ring[3 + nx] = 0; }
 
-    // ------------------------------ rows phase (software pipelined) ------------------------------
+    // ------------------------------ rows phase ------------------------------
     {
-      const bool first = (round == 1);
       const SinkBox sink{W.nbox};
-      RowMeta mC = load_meta(P, W.list, group, count, first);
-      RowData dC = load_data(P, mC, lane_g);
-      RowMeta mB = load_meta(P, W.list, group + n_groups, count, first);
-      for (int idx = group; idx < count; idx += n_groups) {
-        const RowData dB = load_data(P, mB, lane_g);                          // entries of the next row
-        const RowMeta mA = load_meta(P, W.list, idx + 2 * n_groups, count, first); // ids of the one after
-        if (mC.i >= 0)
-          process_row<G, R>(P, W.box, W.bits, W.status, sink, mC, dC, lane_g, gmask, first, my_nnz, my_rows);
-        mC = mB; dC = dB; mB = mA;
-      }
+      process_rows<G, R>(P, W.box, W.bits, W.status, sink, tid >> 5, nthreads >> 5, round == 1, my_nnz, my_rows);
     }
     MNTR_TRACE();
     grid_barrier(W.bar, gridDim.x, bar_target);
@@ -158,22 +142,10 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
           const int t = __ffs(chm) - 1;
           chm &= chm - 1;
           const int qb = __ldg(P.csc_ptr + j0 + t), qe = __ldg(P.csc_ptr + j0 + t + 1);
-          for (int q0 = qb; q0 < qe; q0 += 32) {
-            const int q = q0 + lane;
-            bool fresh = false; int row = 0;
-            if (q < qe) {
-              row = __ldg(P.csc_row + q);
-              const unsigned bit = 1u << (row & 31);
-              fresh = (atomicOr(W.bits + (row >> 5), bit) & bit) == 0u;
-            }
-            const unsigned want = __ballot_sync(0xffffffffu, fresh);
-            if (want) {
-              int base = 0;
-              const int leader = __ffs(want) - 1;
-              if (lane == leader) base = atomicAdd(&W.ring[6 + slot], __popc(want));
-              base = __shfl_sync(0xffffffffu, base, leader);
-              if (fresh) W.list[base + __popc(want & ((1u << lane) - 1u))] = row;
-            }
+          // lane q flags CSC entry q: fire-and-forget OR into the row bit set
+          for (int q = qb + lane; q < qe; q += 32) {
+            const int row = __ldg(P.csc_row + q);
+            atomicOr(W.bits + (row >> 5), 1u << (row & 31));
           }
         }
       }
@@ -196,7 +168,6 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
     verdict = vstatus[0];
     const int any_changed = vring[slot];
     const int any_int = vring[3 + slot];
-    count = vring[6 + slot];
     if (verdict != 0 || !any_changed) break;
     if (max_rounds > 0 && round >= max_rounds) break;
     if (loop_mode == 1) {   // LinearHandler::simplePresolve truncation, :1625-1627

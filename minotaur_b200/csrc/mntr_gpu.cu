@@ -321,7 +321,7 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
     cptr0[i + 1] = (int32_t)ccol.size();
   }
   const int64_t nnz = (int64_t)ccol.size();
-  if (nnz + m > (int64_t)INT32_MAX - 4) return fail(ctx, MNTR_E_UNSUPPORTED, "load_linear: more than 2^31 entries");
+  if (nnz + 3 * (int64_t)m > (int64_t)INT32_MAX - 4) return fail(ctx, MNTR_E_UNSUPPORTED, "load_linear: more than 2^31 entries");
 
   // ---- wavefront levels of the reference's index-ordered in-place sweep: a row's level is one more
   //      than the highest level of an EARLIER row sharing a variable; rows of one level are pairwise
@@ -349,18 +349,18 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
     }
   }
 
-  // ---- padded CSR in stored order: row starts at even entries (128-bit val / 64-bit col loads) ----
+  // ---- padded CSR in stored order: rows padded to 4 entries (128-bit val and col loads) ----
   std::vector<int32_t> prow(m + 1, 0), pcol;
   std::vector<double> pval;
   std::vector<int2> pinfo((size_t)std::max(m, 1));
   std::vector<double2> pbnd((size_t)std::max(m, 1));
-  pcol.reserve((size_t)nnz + m); pval.reserve((size_t)nnz + m);
+  pcol.reserve((size_t)nnz + 3 * (size_t)m); pval.reserve((size_t)nnz + 3 * (size_t)m);
   for (int32_t q = 0; q < m; ++q) {
     const int32_t i = perm[q];
     prow[q] = (int32_t)pcol.size();
     for (int32_t t = cptr0[i]; t < cptr0[i + 1]; ++t) { pcol.push_back(ccol[t]); pval.push_back(cval[t]); }
     const int32_t cnt = cptr0[i + 1] - cptr0[i];
-    if (pcol.size() & 1) { pcol.push_back(pcol.back()); pval.push_back(0.0); }
+    while (pcol.size() % kRowPad) { pcol.push_back(pcol.empty() ? 0 : pcol.back()); pval.push_back(0.0); }
     const bool deleted = row_active && !row_active[i];
     pinfo[q] = make_int2(prow[q], deleted ? -1 : cnt);
     pbnd[q] = make_double2(row_lb[i], row_ub[i]);
@@ -422,10 +422,10 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if (!ctx->h_ctrl) CU(cudaMallocHost((void **)&ctx->h_ctrl, 64));
   if (const char *fr = getenv("MNTR_GPU_ROUNDS")) ctx->force_rounds = fr[0] == '1';
 
-  // sub-warp group size from the mean row length (two entries per lane per step)
+  // sub-warp group size from the mean row length (four entries per lane per step)
   const double mean = m > 0 ? (double)nnz / m : 0.0;
   int g = 2;
-  while (g < 32 && 2 * g < mean + 0.5) g *= 2;
+  while (g < 32 && 4 * g < mean + 0.5) g *= 2;
   ctx->lanes_per_row = g;
   ctx->m = m; ctx->n = n; ctx->nnz = nnz; ctx->nnz_padded = (int64_t)pcol.size();
   CU(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
@@ -573,7 +573,7 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
   NcclApi &nc = nccl_api();
   CU(cudaMemsetAsync(W.ctrl, 0, 64, ctx->stream));
   CU(launch_rounds_init(P, W, lb_dev, ub_dev, ctx->sm_count, ctx->stream));
-  int count = P.m, round = 0, verd = 0;
+  int round = 0, verd = 0;
   double rows_ms = 0, comm_ms = 0, vars_ms = 0;
   CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -581,7 +581,7 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
   while (verd == 0) {
     ++round;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CU(launch_rounds_rows(P, W, ctx->lanes_per_row, directed, count, round == 1, ctx->sm_count, ctx->stream));
+    CU(launch_rounds_rows(P, W, ctx->lanes_per_row, directed, round == 1, ctx->sm_count, ctx->stream));
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     if (ctx->comm) {
       NC(nc.GroupStart());
@@ -600,7 +600,6 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
     vars_ms += elapsed(ctx->ev[4], ctx->ev[5]);
     verd = ctx->h_ctrl[3];
     const int changed = ctx->h_ctrl[0], int_moved = ctx->h_ctrl[1];
-    count = ctx->h_ctrl[2];
     if (verd != 0 || !changed) break;
     if (o.max_rounds > 0 && round >= o.max_rounds) break;
     if (o.loop == MNTR_LOOP_SIMPLEPRESOLVE) {       // LinearHandler.cpp:1625-1627
