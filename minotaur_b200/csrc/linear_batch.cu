@@ -75,50 +75,54 @@ __device__ __forceinline__ TileTeam make_team()
   return t;
 }
 
-// A row is consumed in chunks of <= 32 entries: lane t fetches entry t (one coalesced request
-// for the whole chunk), entries are then broadcast with warp shuffles, and the {lb,ub} gathers of
-// kGather consecutive terms are issued back to back before any of them is consumed, so a warp has
-// kGather independent 512-byte requests in flight instead of one.  Terms are still CONSUMED in
-// ascending column order, one after the other, exactly like the reference's loop.
-struct Chunk {
-  int cj; double ca; int cnt;
+// A row is consumed in chunks of <= 32 entries: lane t fetches entry t (one coalesced request for the whole
+// chunk) into this warp's slice of shared memory; every lane then reads entry after entry back as a
+// broadcast (one LDS each for the coefficient and the column).  The {lb,ub} gathers of kGather consecutive
+// terms are issued back to back before any of them is consumed, so a warp keeps kGather independent
+// 512-byte requests in flight.  Terms are CONSUMED in ascending column order, one after the other,
+// exactly like the reference's loop.  Only the row's true entries are visited (no padding), so the inner
+// loops carry no per-term predicates.
+struct RowStage {
+  double *val;    // [32] this warp's slice
+  int *col;       // [32]
 };
 
-__device__ __forceinline__ Chunk load_chunk(const LinDev &P, int c0, int end, int lane)
+__device__ __forceinline__ int stage_chunk(const LinDev &P, int c0, int cnt_left, const RowStage &st, int lane)
 {
-  Chunk c;
-  c.cnt = min(32, end - c0);
-  c.cj = 0; c.ca = 0.0;
-  if (lane < c.cnt) { c.cj = __ldg(P.col + c0 + lane); c.ca = __ldg(P.val + c0 + lane); }
-  return c;
+  const int cnt = min(32, cnt_left);
+  __syncwarp();                                   // the previous chunk has been consumed
+  if (lane < cnt) { st.col[lane] = __ldg(P.col + c0 + lane); st.val[lane] = __ldg(P.val + c0 + lane); }
+  __syncwarp();
+  return cnt;
 }
 
-// min / max activity of one row for this lane's box  [getLfBnds_]
 template <class R>
-__device__ __forceinline__ void row_activity(const LinDev &P, int beg, int end, const double2 *bx,
-                                             int64_t ld, bool mine, int lane, double &ll, double &uu)
+__device__ __forceinline__ void acc_term(double a, double2 b, double &ll, double &uu)
+{
+  const bool pos = a > 0.0;
+  const double blo = pos ? b.x : b.y, bhi = pos ? b.y : b.x;
+  ll = R::add_lo(ll, R::mul_lo(a, blo));
+  uu = R::add_hi(uu, R::mul_hi(a, bhi));
+}
+
+// min / max activity of one row for this lane's box  [getLfBnds_].  Computed by every lane (lanes whose box
+// is not due simply discard the result): no predication in the loop.
+template <class R>
+__device__ __forceinline__ void row_activity(const LinDev &P, int beg, int cnt_row, const double2 *bx,
+                                             int64_t ld, const RowStage &st, int lane, double &ll, double &uu)
 {
   ll = 0.0; uu = 0.0;
-  for (int c0 = beg; c0 < end; c0 += 32) {
-    const Chunk c = load_chunk(P, c0, end, lane);
-    for (int t0 = 0; t0 < c.cnt; t0 += kGather) {
+  for (int c0 = 0; c0 < cnt_row; c0 += 32) {
+    const int cnt = stage_chunk(P, beg + c0, cnt_row - c0, st, lane);
+    int t = 0;
+    for (; t + kGather <= cnt; t += kGather) {
       double a[kGather]; double2 b[kGather];
 #pragma unroll
-      for (int u = 0; u < kGather; ++u) {
-        a[u] = __shfl_sync(kFull, c.ca, (t0 + u) & 31);
-        const int j = __shfl_sync(kFull, c.cj, (t0 + u) & 31);
-        if (t0 + u >= c.cnt) a[u] = 0.0;
-        b[u] = make_double2(0.0, 0.0);
-        if (mine && a[u] != 0.0) b[u] = bx[(int64_t)j * ld];
-      }
+      for (int u = 0; u < kGather; ++u) { a[u] = st.val[t + u]; b[u] = bx[(int64_t)st.col[t + u] * ld]; }
 #pragma unroll
-      for (int u = 0; u < kGather; ++u) {
-        if (mine && a[u] != 0.0) {                   // a == 0: alignment padding / past the row
-          if (a[u] > 0) { ll = R::add_lo(ll, R::mul_lo(a[u], b[u].x)); uu = R::add_hi(uu, R::mul_hi(a[u], b[u].y)); }
-          else          { ll = R::add_lo(ll, R::mul_lo(a[u], b[u].y)); uu = R::add_hi(uu, R::mul_hi(a[u], b[u].x)); }
-        }
-      }
+      for (int u = 0; u < kGather; ++u) acc_term<R>(a[u], b[u], ll, uu);
     }
+    for (; t < cnt; ++t) acc_term<R>(st.val[t], bx[(int64_t)st.col[t] * ld], ll, uu);
   }
 }
 
@@ -164,101 +168,101 @@ __device__ __forceinline__ void flag_rows_of(const LinDev &P, int j, unsigned ma
   if (varflag != nullptr && lane == 0) atomicOr(varflag + j, mask);
 }
 
+// exact candidate of one term for this lane's box (rare path); returns true when a bound moved
+template <class R, bool FROM_LB>
+__device__ __forceinline__ bool update_exact(double av, double numer, bool sing, double2 b, double2 *pb)
+{
+  const double aa = fabs(av);
+  if (!(aa > kETol)) return false;
+  const double vl = b.x, vu = b.y;
+  // FromLb: a>0 raises lb, a<0 lowers ub.   FromUb: a>0 lowers ub, a<0 raises lb.
+  const bool raise_lb = FROM_LB ? (av > 0.0) : (av < 0.0);
+  const bool inf_side = raise_lb ? (vu >= kInf20) : (vl <= -kInf20);
+  if (sing && !inf_side) return false;
+  const double base = inf_side ? 0.0 : (raise_lb ? vu : vl);
+  // ONE division by |a|: round_up(x/a) == -round_down(x/|a|) for a<0 (and x/a == -(x/|a|) exactly in
+  // round-to-nearest), so the sign only selects the bound that moves
+  if (raise_lb) {
+    const double q = FROM_LB ? R::div_lo(numer, aa) : -R::div_hi(numer, aa);
+    double cnd = R::add_lo(q, base);
+    if (cnd > vl + kETol) {
+      if (cnd > vu - kETol) cnd = vu;
+      pb->x = cnd;
+      return true;
+    }
+  } else {
+    const double q = FROM_LB ? -R::div_lo(numer, aa) : R::div_hi(numer, aa);
+    double cnd = R::add_hi(q, base);
+    if (cnd < vu - kETol) {
+      if (cnd < vl + kETol) cnd = vl;
+      pb->y = cnd;
+      return true;
+    }
+  }
+  return false;
+}
+
 // updateLfBoundsFromLb_ (FROM_LB) / updateLfBoundsFromUb_ (!FROM_LB), in place.
 // returns the ballot of lanes that changed something.
+// slack = |row bound - activity| for lanes that take part, +inf for the others.  A candidate moves a bound of
+// x_j towards the other by slack/|a|, so it can only be accepted when slack < |a|*(ub_j - lb_j): that product
+// test (1e-9 relative margin; inf/NaN fall through) lets the warp skip the fp64 division for almost every term.
 template <class R, bool FROM_LB>
-__device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int end, double2 *bx, int64_t ld,
-                                               bool doit, bool sing, double rbound, double act,
+__device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int cnt_row, double2 *bx, int64_t ld,
+                                               const RowStage &st, bool doit, bool sing, double rbound, double act,
                                                uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane)
 {
   unsigned any = 0;
   // (row bound - activity): FromLb needs a lower estimate, FromUb an upper estimate
   const double numer = FROM_LB ? R::sub_lo(rbound, act) : R::sub_hi(rbound, act);
-  for (int c0 = beg; c0 < end; c0 += 32) {
-    const Chunk c = load_chunk(P, c0, end, lane);
-    for (int t0 = 0; t0 < c.cnt; t0 += kGather) {
-      double a[kGather]; double2 b[kGather]; int jj[kGather];
-#pragma unroll
-      for (int u = 0; u < kGather; ++u) {
-        a[u] = __shfl_sync(kFull, c.ca, (t0 + u) & 31);
-        jj[u] = __shfl_sync(kFull, c.cj, (t0 + u) & 31);
-        if (t0 + u >= c.cnt) a[u] = 0.0;
-        b[u] = make_double2(0.0, 0.0);
-        if (doit && a[u] != 0.0) b[u] = bx[(int64_t)jj[u] * ld];
-      }
-#pragma unroll
-      for (int u = 0; u < kGather; ++u) {
-        if (a[u] == 0.0) continue;                    // warp-uniform
-        bool chg = false;
-        const double av = a[u], aa = fabs(av);
-        if (doit && aa > kETol) {
-          double2 *pb = bx + (int64_t)jj[u] * ld;
-          const double vl = b[u].x, vu = b[u].y;
-          // FromLb: a>0 raises lb, a<0 lowers ub.   FromUb: a>0 lowers ub, a<0 raises lb.
-          const bool raise_lb = FROM_LB ? (av > 0.0) : (av < 0.0);
-          const bool inf_side = raise_lb ? (vu >= kInf20) : (vl <= -kInf20);
-          if (!sing || inf_side) {
-            const double base = inf_side ? 0.0 : (raise_lb ? vu : vl);
-            // ONE division by |a| per term: round_up(x/a) == -round_down(x/|a|) for a<0 (and x/a ==
-            // -(x/|a|) exactly in round-to-nearest), so the sign only selects the bound that moves.
-            // The candidate moves a bound of x_j towards the other by slack/|a| (slack = |numer|), so it
-            // can only be accepted when slack < |a|*(ub_j - lb_j): that product test rejects almost every
-            // term without the fp64 division (1e-9 relative margin; inf/NaN fall through to the exact path).
-            const double reach = aa * (vu - vl) * 1.000000001;
-            const bool maybe = !((FROM_LB ? -numer : numer) > reach);
-            if (maybe) {
-              if (raise_lb) {
-                // lower estimate of numer/a: FromLb (a>0) div_lo(numer,|a|); FromUb (a<0) -div_hi(numer,|a|)
-                const double q = FROM_LB ? R::div_lo(numer, aa) : -R::div_hi(numer, aa);
-                double cnd = R::add_lo(q, base);
-                if (cnd > vl + kETol) {
-                  if (cnd > vu - kETol) cnd = vu;
-                  pb->x = cnd;
-                  chg = true;
-                }
-              } else {
-                // upper estimate of numer/a: FromLb (a<0) -div_lo(numer,|a|); FromUb (a>0) div_hi(numer,|a|)
-                const double q = FROM_LB ? -R::div_lo(numer, aa) : R::div_hi(numer, aa);
-                double cnd = R::add_hi(q, base);
-                if (cnd < vu - kETol) {
-                  if (cnd < vl + kETol) cnd = vl;
-                  pb->y = cnd;
-                  chg = true;
-                }
-              }
-            }
-          }
-        }
-        const unsigned m = __ballot_sync(kFull, chg);
-        if (m) {
-          any |= m;
-          flag_rows_of(P, jj[u], m, flags, varflag, lane);
-          if (chg) {
-            sh.changed[lane] = 1;
-            if (is_int_type(__ldg(P.var_type + jj[u]))) sh.nint[lane] = 1;
-          }
-        }
+  const double slack = doit ? (FROM_LB ? -numer : numer) : INFINITY;
+  // one term: product test, then (rarely) the exact candidate, the in-place store and the bFlag propagation
+  auto term = [&](double av, int j, double2 b) {
+    const double reach = fabs(av) * (b.y - b.x) * 1.000000001;
+    const bool maybe = !(slack > reach);
+    if (!__any_sync(kFull, maybe)) return;            // nobody in the tile can move this variable
+    bool chg = false;
+    if (maybe && doit) chg = update_exact<R, FROM_LB>(av, numer, sing, b, bx + (int64_t)j * ld);
+    const unsigned m = __ballot_sync(kFull, chg);
+    if (m) {
+      any |= m;
+      flag_rows_of(P, j, m, flags, varflag, lane);
+      if (chg) {
+        sh.changed[lane] = 1;
+        if (is_int_type(__ldg(P.var_type + j))) sh.nint[lane] = 1;
       }
     }
+  };
+  for (int c0 = 0; c0 < cnt_row; c0 += 32) {
+    const int cnt = stage_chunk(P, beg + c0, cnt_row - c0, st, lane);
+    int t = 0;
+    for (; t + kGather <= cnt; t += kGather) {
+      double a[kGather]; double2 b[kGather]; int jj[kGather];
+#pragma unroll
+      for (int u = 0; u < kGather; ++u) { a[u] = st.val[t + u]; jj[u] = st.col[t + u]; b[u] = bx[(int64_t)jj[u] * ld]; }
+#pragma unroll
+      for (int u = 0; u < kGather; ++u) term(a[u], jj[u], b[u]);
+    }
+    for (; t < cnt; ++t) { const int j = st.col[t]; term(st.val[t], j, bx[(int64_t)j * ld]); }
   }
   return any;
 }
 
 // one linear row for the 32 boxes of the tile  [linBndTighten_ with apply_to_prob == false]
 template <class R>
-__device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx, int64_t ld, bool mine,
-                                            uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane,
+__device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx, int64_t ld, const RowStage &st,
+                                            bool mine, uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane,
                                             unsigned long long &my_nnz)
 {
   const int2 info = __ldg(P.row_info + i);
-  const int beg = info.x, end = row_end(info);
+  const int beg = info.x, cnt = info.y, end = beg + cnt;
   const double2 bnd = __ldg(P.row_bnd + i);
   const double rl = bnd.x, ru = bnd.y;
   double ll, uu, sing_ll = -INFINITY, sing_uu = INFINITY;
-  row_activity<R>(P, beg, end, bx, ld, mine, lane, ll, uu);
+  row_activity<R>(P, beg, cnt, bx, ld, st, lane, ll, uu);
   bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
   if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
-  if (mine) my_nnz += (unsigned long long)info.y;
+  if (mine) my_nnz += (unsigned long long)cnt;
   if (mine && (ll > ru + kETol || uu < rl - kETol)) {       // :994-1015
     sh.verdict[lane] = 2;  /* MNTR_INFEAS_ROW */
     mine = false;
@@ -271,13 +275,13 @@ __device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx,
   }
   unsigned chg = 0;
   if (__any_sync(kFull, do_lb))
-    chg = row_update<R, true>(P, beg, end, bx, ld, do_lb, s_lb, rl, act, flags, varflag, sh, lane);
+    chg = row_update<R, true>(P, beg, cnt, bx, ld, st, do_lb, s_lb, rl, act, flags, varflag, sh, lane);
   // recompute activities when FromLb changed something (:1027-1032); lanes that did not
   // change would recompute identical values, so the decision is taken per warp
   if (chg) {
     const bool redo = mine && ((chg >> lane) & 1u);
     double l2, u2;
-    row_activity<R>(P, beg, end, bx, ld, redo, lane, l2, u2);
+    row_activity<R>(P, beg, cnt, bx, ld, st, lane, l2, u2);
     if (redo) { ll = l2; uu = u2; }
     need_sing = redo && (ll < -kInf20 || uu > kInf20);
     if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
@@ -289,7 +293,7 @@ __device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx,
     else if (sing_ll > -kInf20) { do_ub = true; s_ub = true; act = sing_ll; }
   }
   if (__any_sync(kFull, do_ub))
-    (void)row_update<R, false>(P, beg, end, bx, ld, do_ub, s_ub, ru, act, flags, varflag, sh, lane);
+    (void)row_update<R, false>(P, beg, cnt, bx, ld, st, do_ub, s_ub, ru, act, flags, varflag, sh, lane);
 }
 
 // integer rounding [tightenInts_] + lb>ub check [checkBounds_] of variable j for the lanes in `want`
@@ -319,8 +323,8 @@ __device__ __forceinline__ void finish_var(const LinDev &P, int j, double2 b, bo
 // linear rows for the 32 boxes of this tile.  sh.verdict carries each box's verdict in and out;
 // returns (per lane) the number of sweeps its box ran.
 template <class R>
-__device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, int64_t ld, uint32_t *flags,
-                                                 uint32_t *varflag, TileShared &sh, bool active, int loop_mode,
+__device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, int64_t ld, const RowStage &st,
+                                                 uint32_t *flags, uint32_t *varflag, TileShared &sh, bool active, int loop_mode,
                                                  int max_rounds, int bad_row, unsigned long long &my_nnz,
                                                  bool &any_change)
 {
@@ -370,7 +374,7 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
           const uint32_t proc = __shfl_sync(kFull, fw, t);
           if (lane == t) __stcg(flags + q, raw & ~proc);     // c_ptr->setBFlag(false), :513
           __syncwarp();
-          process_row<R>(P, q0 + t, bx, ld, (proc >> lane) & 1u, flags, varflag, sh, lane, my_nnz);
+          process_row<R>(P, q0 + t, bx, ld, st, (proc >> lane) & 1u, flags, varflag, sh, lane, my_nnz);
         }
       }
       team.sync();
@@ -479,6 +483,9 @@ __global__ void __launch_bounds__(kBatchThreads, 2)
 fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int max_rounds, int lin_enabled,
                             int nl_enabled)
 {
+  __shared__ double s_val[kBatchWarps][32];
+  __shared__ int s_col[kBatchWarps][32];
+  const RowStage st{s_val[threadIdx.x >> 5], s_col[threadIdx.x >> 5]};
   const TileTeam team = make_team();
   const int tile = blockIdx.x / (int)cg::this_cluster().num_blocks();
   TileShared &sh = *reinterpret_cast<TileShared *>(io.tstate + (int64_t)tile * kTileStateBytes);
@@ -507,7 +514,7 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
   for (int outer = 0;; ++outer) {
     bool lin_changed = false, nl_changed = false;
     if (lin_enabled)
-      my_rounds += lin_tile_presolve<R>(P, bx, ld, flags, varflag, sh, active, loop_mode, max_rounds, bad_row,
+      my_rounds += lin_tile_presolve<R>(P, bx, ld, st, flags, varflag, sh, active, loop_mode, max_rounds, bad_row,
                                         my_nnz, lin_changed);
     if (nl_enabled) my_rounds += nl_tile_presolve<R>(N, bx, ld, sh, active, nl_changed);
     // fixpoint mode with both handlers: go round again while the nonlinear sweeps still move bounds
