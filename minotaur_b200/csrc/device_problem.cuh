@@ -14,6 +14,7 @@ struct LinDev {
   const int2    *row_info;  // [m] {first entry (multiple of 4), true term count; count < 0 marks a deleted row}
   const double2 *row_bnd;   // [m] {row lb, row ub}
   const int32_t *col;       // [nnz_padded]  a row occupies entries [beg, beg + roundup4(count))
+  const int32_t *colx;      // [nnz_padded]  col with bit 31 set when the variable is integer (single-box fixpoint kernel)
   const double  *val;       // [nnz_padded]
   const uint8_t *var_type;  // [n]
   const int32_t *csc_ptr;   // [n+1]
@@ -21,6 +22,13 @@ struct LinDev {
   // wavefront schedule of the reference's index-ordered in-place sweep
   int32_t n_levels;
   const int32_t *level_ptr; // [n_levels+1] ranges of STORED rows (rows are stored in level order)
+  // objective cut-off row  c.x <= rhs  (LinearHandler::varBndsFromObj_, LinearHandler.cpp:544-597); cut_cnt 0 = none
+  int32_t cut_cnt;
+  const int32_t *cut_col;   // [roundup4(cut_cnt)]
+  const int32_t *cut_colx;  // same with the integer bit
+  const double  *cut_val;
+  const double2 *cut_bnd;   // [1] {-inf, rhs}
+  double cut_rhs;
 };
 
 // rows are padded to a multiple of kRowPad entries (padding: val == 0, a valid column)
@@ -43,15 +51,17 @@ struct NlDev {
   const int32_t *level_ptr; // [n_levels+1] ranges of STORED constraints (stored in level order)
 };
 
-// workspace of the single-box Jacobi fixpoint kernel
+// workspace of the single-box Jacobi fixpoint kernel (linear_single.cu).  Everything is double-buffered by round
+// parity: round r reads box[r&1] / due[r&1] and writes box[(r+1)&1] / due[(r+1)&1] / touched[r&1].
 struct SingleWs {
-  double2 *box;    // [n] {lb, ub} of the round start
-  double2 *nbox;   // [n] candidates of the round (atomic max / min)
-  uint32_t *bits;  // [(m+31)/32] row-is-on-the-next-work-list bit set   (Constraint bFlag)
-  int32_t *list;   // [m] work list of flagged rows
+  double2 *box[2];      // [n] {lb, ub}: merged candidates, integer bounds not yet rounded
+  uint32_t *due[2];     // [(m+31)/32] row-is-due bit sets   (Constraint bFlag)
+  uint32_t *touched[2]; // [(n+31)/32] variable-moved-in-the-round bit sets
   // control block (128 bytes, zeroed before every launch)
-  int32_t *ring;   // [12] per-round words: ring[r%3] changed, ring[3+r%3] int moved, ring[6+r%3] list length
-  int32_t *status; // [4]  [0] verdict, [1] rounds, [2] changed (variable, round) pairs
+  int32_t *ring;   // [12] per-round words: ring[r%3] changed, ring[3+r%3] int moved, 
+  int32_t *status; // [8]  [0] a row is activity-infeasible  [1] rounds  [2] changed (variable, round) pairs
+                   //      [3] a moved variable's bounds cross  [4] a row's bounds cross  [5] incoming bounds cross
+                   //      [6] verdict of the loop
   unsigned long long *counters;  // [2] [0] nnz_updates, [1] rows evaluated
   unsigned *bar;   // device-wide barrier arrive counter
   unsigned long long *trace;     // [64] optional phase timestamps (globaltimer ns), or nullptr
@@ -62,8 +72,7 @@ struct RoundsWs {
   double2 *box;    // [n] {lb, ub} of the round start (replicated on every rank)
   double *nlb;     // [n+1] lower-bound candidates (all-reduced with MAX); [n] = row-infeasible flag
   double *nub;     // [n]   upper-bound candidates (all-reduced with MIN)
-  uint32_t *bits;  // [(m+31)/32] this rank's rows on the next work list
-  int32_t *list;   // [m] work list
+  uint32_t *bits;  // [(m+31)/32] this rank's due rows   (Constraint bFlag)
   int32_t *ctrl;   // [8] [0] changed [1] int moved [2] next list length [3] verdict [4] changed pairs
   unsigned long long *counters;  // [2] nnz_updates, rows evaluated (this rank)
 };

@@ -8,7 +8,7 @@
 //                  detection, work list of this rank's rows for the next round
 // Because candidates are merged with exact max/min and everything after the merge is replicated, all
 // ranks finish with bit-identical boxes and the result does not depend on the number of ranks.
-// The row evaluation itself is the code of the single-launch kernel (linear_row.cuh).
+// The row evaluation is the throughput form in linear_row.cuh (sub-warp group per row, registers and shuffles only).
 #include "device_problem.cuh"
 #include "kernels.h"
 #include "linear_row.cuh"

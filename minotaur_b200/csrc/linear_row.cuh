@@ -1,20 +1,12 @@
 // linear_row.cuh -- evaluation of ONE linear row against ONE box by a sub-warp group of G lanes
-// (Jacobi form of LinearHandler::linBndTighten_, LinearHandler.cpp:952-1045).  Shared by the
-// cooperative single-launch fixpoint kernel (linear_single.cu) and the per-round kernels of the
-// row-partitioned multi-GPU path (linear_rounds.cu); they differ only in where candidate bounds go
-// (the Sink).
+// (Jacobi form of LinearHandler::linBndTighten_, LinearHandler.cpp:952-1045), registers and shuffles only.
+// This is the THROUGHPUT form, used by the per-round kernels of the row-partitioned multi-GPU path
+// (linear_rounds.cu), where every warp has hundreds of rows to stream through; the single-launch fixpoint
+// kernel uses the latency form in row_batch.cuh (one staged batch of rows per warp per round).
 #pragma once
 #include "device_problem.cuh"
 
 namespace mntr {
-
-// candidates merged into an interleaved {lb,ub} box
-struct SinkBox {
-  double2 *nbox;
-  __device__ __forceinline__ void raise_lb(int j, double c) const { atomic_max_f64(&nbox[j].x, c); }
-  __device__ __forceinline__ void lower_ub(int j, double c) const { atomic_min_f64(&nbox[j].y, c); }
-  __device__ __forceinline__ void row_infeasible(int32_t *status) const { status[0] = 2; /* MNTR_INFEAS_ROW */ }
-};
 
 // candidates merged into separate lb / ub arrays: each is contiguous, so the cross-GPU merge is one
 // NCCL MAX all-reduce on nlb and one MIN all-reduce on nub.  Slot n carries the row-infeasible flag.
@@ -278,6 +270,13 @@ __device__ __forceinline__ void process_rows(const LinDev &P, const double2 *box
       if (info.y < 0) continue;                                 // deleted rows are never evaluated
       process_row<G, R>(P, box, status, sink, i, info.x, info.y, lane_g, gmask, my_nnz, my_rows);
     }
+  }
+  // the objective cut-off row is evaluated in every round (the reference loops it to its own fixpoint in
+  // every sweep, LinearHandler.cpp:1636-1640); one group takes it
+  if (P.cut_cnt > 0 && warp_global == 0 && g == 0) {
+    LinDev C = P;
+    C.col = P.cut_col; C.val = P.cut_val; C.row_bnd = P.cut_bnd;
+    process_row<G, R>(C, box, status, sink, 0, 0, P.cut_cnt, lane_g, gmask, my_nnz, my_rows);
   }
 }
 

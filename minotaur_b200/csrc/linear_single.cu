@@ -1,30 +1,31 @@
-// linear_single.cu -- K1: single-box FBBT of the linear rows, Jacobi rounds to a fixpoint
-// inside ONE cooperative launch (device-side change flag and work list, no host round trips).
+// linear_single.cu -- K1: single-box FBBT of the linear rows, Jacobi rounds to a fixpoint inside ONE
+// cooperative launch with ONE device-wide barrier per round (device-side change flag, no host round trips).
 //
-// Per round (reference lines in brackets):
-//   rows phase : sub-warp group per flagged CSR row, four entries per lane -- two 128-bit value
-//                loads, one 128-bit column load, four 128-bit gathers of {lb,ub}; min/max activity
-//                with outward rounding [getLfBnds_ LinearHandler.cpp:1237-1258]; singleton-
-//                infinity sums by finite-sum + infinity-count [getSingLfBnds_ :1261-1319];
-//                warp-shuffle butterfly reduction; activity infeasibility [:994-1015];
-//                implied bounds [updateLfBoundsFromLb_/Ub_ :1048-1226] merged with fp64
-//                atomic max/min into the next box.  A product test skips the fp64 division for terms
-//                that cannot tighten anything.
-//   vars phase : integer rounding [tightenInts_ :415-490], lb>ub check [checkBounds_
-//                :328-359], change detection; the rows of every changed variable
-//                [changeBFlag_ :1229-1234] are flagged in a bit set with fire-and-forget atomics
-//                (a warp walks a changed variable's CSC list with one entry per lane).
-// A device-wide barrier (one arrive counter, acquire polling) separates the phases; the loop
-// condition is evaluated on the device from the round's change flags.
+// Round r reads the box A = box[r&1] and merges candidate bounds into Z = box[(r+1)&1] with fp64 atomic max/min.
+// Three things make a single barrier per round enough (SURVEY.md Appendix A gives the round; reference lines in
+// brackets):
+//   * max/min are commutative, so Z need not be a copy of A when the round starts: the variables that moved in round
+//     r-1 (the only ones where Z lags behind A) are on a list, and round r brings Z up to date with the same atomics,
+//     concurrently with the candidates of round r ("fix-up");
+//   * integer rounding [tightenInts_ LinearHandler.cpp:415-490] is applied by the READER of a bound (bit 31 of the
+//     stored column marks an integer variable), so the stored boxes hold merged, unrounded values and nobody has to
+//     rewrite a box between rounds; the bound check [checkBounds_ :328-359] of a moved variable is part of its fix-up;
+//   * the rows of a moved variable are flagged for the next round [changeBFlag_ :1229-1234] by the warp whose
+//     candidate moved it first, through the CSC lists, into the next round's row bit set.
+// The row evaluation itself (activities with outward rounding, singleton-infinity rule, implied bounds) is
+// row_batch.cuh: entry-parallel, one warp per batch of up to 32 due rows.
+// The result is exactly the two-phase Jacobi round: rows against the box of the round start, candidates merged with
+// max/min, integers rounded, bounds checked, rows of changed variables flagged.
 #include "device_problem.cuh"
 #include "kernels.h"
-#include "linear_row.cuh"
+#include "row_batch.cuh"
 
 namespace mntr {
 
 namespace {
 
-constexpr int kSingleThreads = 1024;
+constexpr int kSingleThreads = 768;      // 24 warps x 85 registers: the row evaluation must not spill (L1 is small)
+constexpr int kSingleWarps = kSingleThreads / 32;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
@@ -34,7 +35,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 
 // optional phase trace (MNTR_GPU_TRACE=1): thread 0 of block 0 stamps every phase boundary
-#define MNTR_TRACE() do { if (W.trace != nullptr && tid == 0 && tr < 64) W.trace[tr] = globaltimer_ns(); ++tr; } while (0)
+#define MNTR_TRACE() do { if (W.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tr < 32) W.trace[tr] = globaltimer_ns(); ++tr; } while (0)
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
 {
@@ -44,199 +45,285 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
 }
 
 // Device-wide barrier for a cooperative (co-resident) grid: a cumulative arrive counter, thread 0
-// of each block arrives with a release fence and polls with acquire loads; the trailing fence also
-// invalidates this SM's L1 so the block's ordinary loads see the other blocks' writes.
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, unsigned &target)
+// of each block arrives with a release fence and polls with acquire loads.  Thread 0 then takes a snapshot of
+// the control words (ring[12] + status[8]) into shared memory: ONE reader per block -- if every warp read them
+// from global memory, thousands of requests would queue on a single L2 line after every barrier.
+constexpr int kCtlWords = 20;
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, unsigned &target, const int32_t *ctl,
+                                             int *s_ctl, unsigned long long *arrive)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (arrive != nullptr) *arrive = globaltimer_ns();      // debug: when this block reached the barrier
     target += n_blocks;
     __threadfence();
     atomicAdd(bar, 1u);
     while (ld_acquire_gpu(bar) < target) { }
     __threadfence();
+    int4 v[kCtlWords / 4];
+#pragma unroll
+    for (int k = 0; k < kCtlWords / 4; ++k) v[k] = __ldcg(reinterpret_cast<const int4 *>(ctl) + k);
+#pragma unroll
+    for (int k = 0; k < kCtlWords / 4; ++k) reinterpret_cast<int4 *>(s_ctl)[k] = v[k];
   }
   __syncthreads();
 }
 
-template <int G, class R>
-__global__ void __launch_bounds__(kSingleThreads, 1)
-fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, int max_rounds,
-                          int loop_mode)
+// flag the rows of variable j (one thread; used for the few integer variables whose INCOMING bounds are fractional)
+__device__ __forceinline__ void flag_rows_serial(const LinDev &P, int j, uint32_t *due)
 {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nthreads = gridDim.x * blockDim.x;
+  const int qb = __ldg(P.csc_ptr + j), qe = __ldg(P.csc_ptr + j + 1);
+  for (int q = qb; q < qe; ++q) {
+    const int row = __ldg(P.csc_row + q);
+    atomicOr(due + (row >> 5), 1u << (row & 31));
+  }
+}
+
+template <class R>
+__global__ void __launch_bounds__(kSingleThreads, 1)
+fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, int max_rounds, int loop_mode)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ FixRound s_round;
+  __shared__ __align__(16) int s_ctl[kCtlWords];      // ring[0..11], status[0..7] as of the last barrier
+  const int *s_ring = s_ctl, *s_stat = s_ctl + 12;
+  WarpStage &S = reinterpret_cast<WarpStage *>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
+  const int nthreads = gridDim.x * blockDim.x;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;       // linear: coalesced sweeps over arrays
+  // block-interleaved numbering: consecutive work-list items and row ranges go to different SMs
+  const int tid = threadIdx.x * gridDim.x + blockIdx.x;
+  const int warp_g = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, n_warps = gridDim.x * kSingleWarps;
   unsigned bar_target = 0;
-  __shared__ int s_count;
-  __shared__ unsigned long long s_nnz, s_rows;
-  if (threadIdx.x == 0) { s_count = 0; s_nnz = 0ull; s_rows = 0ull; }
   int tr = 0;
   MNTR_TRACE();
+  if (lane == 0) { S.tcount = 0; S.pad_[0] = 0; }
 
-  // ---- phase 0: build {lb,ub} boxes; every active row is on round 1's work list
-  //      (simplePresolve :1618-1622), so the list is the identity and is not materialised ----
-  int infeasible0 = 0;
-  for (int j = tid; j < P.n; j += nthreads) {
-    double2 b = make_double2(lb_io[j], ub_io[j]);
-    W.box[j] = b;
-    W.nbox[j] = b;
+
+  // contiguous row range of this warp
+  const int rpw = (P.m + n_warps - 1) / n_warps;
+  const int r0 = min(P.m, warp_g * rpw), r1 = min(P.m, r0 + rpw);
+
+  // ---- phase 0: both boxes = incoming box; round 1's rows all due; moved-variable bit sets empty, except that
+  //      integer variables whose INCOMING bounds are fractional move in round 1 by rounding alone: they are
+  //      marked in touched[0], which round 1's fix-up scans ----
+  {
+    int cross0 = 0;
+    for (int j0 = gtid - lane; j0 < P.n; j0 += nthreads) {     // warp-uniform trip count: lanes = 32 consecutive j
+      const int j = j0 + lane;
+      bool frac = false;
+      if (j < P.n) {
+        const double2 b = make_double2(lb_io[j], ub_io[j]);
+        W.box[0][j] = b;
+        W.box[1][j] = b;
+        double2 r = b;
+        if (is_int_type(__ldg(P.var_type + j))) {
+          tighten_int_bounds(r.x, r.y);
+          frac = r.x != b.x || r.y != b.y;
+        }
+        if (r.x > r.y + kETol) cross0 = 1;       // still crossed after any round: reported after round 1
+      }
+      const unsigned fm = __ballot_sync(kFullMask, frac);
+      if (lane == 0) { W.touched[0][j0 >> 5] = fm; W.touched[1][j0 >> 5] = 0u; }
+    }
+    // round 1 takes every row without looking at its bit set (:1618-1622)
+    const int nw_rows = (P.m + 31) / 32;
+    for (int w = gtid; w < nw_rows; w += nthreads) { W.due[0][w] = 0u; W.due[1][w] = 0u; }
+    if (cross0) W.status[5] = 1;
   }
-  for (int i = tid; i < P.m; i += nthreads) {
-    const double2 bnd = __ldg(P.row_bnd + i);
-    if (__ldg(P.row_info + i).y >= 0 && bnd.x > bnd.y + kETol) infeasible0 = 1;   // checkBounds_, rows
-  }
-  for (int w = tid; w < (P.m + 31) / 32; w += nthreads) W.bits[w] = 0u;
-  if (infeasible0) W.status[0] = 1 /* MNTR_INFEAS_BOUNDS */;
   MNTR_TRACE();
-  grid_barrier(W.bar, gridDim.x, bar_target);
+  grid_barrier(W.bar, gridDim.x, bar_target, W.ring, s_ctl, nullptr);
   MNTR_TRACE();
-  volatile int32_t *vstatus = W.status;   // control words are re-read after every barrier
-  volatile int32_t *vring = W.ring;
 
   unsigned long long my_nnz = 0, my_rows = 0;
-  int round = 0;
-  int verdict = vstatus[0];
+  int round = 0, rounds_out = 0;
+  int verdict = 0;
+  int out_buf = 1;            // box to hand back
+  bool out_round = false;     // ... with integer rounding applied
+  bool final_check = false;   // the last round moved bounds that no later fix-up will check
+  int my_changes = 0;         // (variable, round) pairs this thread found in the moved bit sets
+  // contiguous range of words of the moved-variable bit sets this warp scans
+  const int nw_vars = (P.n + 31) / 32;
+  const int wpw = (nw_vars + n_warps - 1) / n_warps;
+  const int fw0 = min(nw_vars, warp_g * wpw), fw1 = min(nw_vars, fw0 + wpw);
 
   while (verdict == 0) {
     ++round;
-    const int slot = round % 3;
-    // ring[slot]: changed, ring[3+slot]: int moved
-    if (tid == 0) { const int nx = (round + 1) % 3; W.ring[nx] = 0; W.ring[3 + nx] = 0; }
-
-    // ------------------------------ rows phase ------------------------------
-    {
-      const SinkBox sink{W.nbox};
-      process_rows<G, R>(P, W.box, W.bits, W.status, sink, tid >> 5, nthreads >> 5, round == 1, my_nnz, my_rows);
+    const int cur = round & 1, slot = round % 3;
+    const double2 *A = W.box[cur];
+    double2 *Z = W.box[cur ^ 1];
+    if (threadIdx.x == 0) {
+      if (blockIdx.x == 0) { const int nx = (round + 1) % 3; W.ring[nx] = 0; W.ring[3 + nx] = 0; }
+      s_round = FixRound{Z, W.touched[cur], W.due[cur ^ 1], &W.ring[slot], &W.ring[3 + slot], &W.status[0],
+                         P.csc_ptr, P.csc_row};
     }
-    MNTR_TRACE();
-    grid_barrier(W.bar, gridDim.x, bar_target);
-    MNTR_TRACE();
-    verdict = vstatus[0];
-    if (verdict != 0) break;
+    __syncthreads();
 
-    // ------------------------------ vars phase ------------------------------
-    // a warp owns 32 consecutive variables; the rows of each changed variable are flagged by the
-    // whole warp (lane q takes CSC entry q), so the test-and-set atomics of a variable are all in
-    // flight together instead of one after the other
-    int changed = 0, int_moved = 0, bad = 0;
-    int n_changed = 0;
+    // the fix-up (below) scans the previous round's moved-variable bit set: fetch this warp's first words now, so
+    // the load is in flight while the rows are evaluated
+    uint32_t *Tp = W.touched[cur ^ 1];
+    unsigned fw = (fw0 + lane < fw1) ? __ldcg(Tp + fw0 + lane) : 0u;
+
+    // ---- rows due in this round ----
     {
-      const int warp_g = tid >> 5, n_warps = nthreads >> 5;
-      for (int j0 = warp_g * 32; j0 < P.n; j0 += n_warps * 32) {
-        const int j = j0 + lane;
-        bool ch = false;
-        if (j < P.n) {
-          const double2 o = W.box[j];
-          double2 v = W.nbox[j];
-          if (is_int_type(__ldg(P.var_type + j))) {
-            if (v.x != o.x || v.y != o.y) int_moved = 1;    // row-derived mod on an int var (nintmods)
-            tighten_int_bounds(v.x, v.y);
-          }
-          if (v.x > v.y + kETol) bad = 1;
-          if (v.x != o.x || v.y != o.y) { ch = true; W.box[j] = v; W.nbox[j] = v; }
+      const ReadPending rd{A, P.colx, round > 1};
+      const SinkFix sink{&s_round, (W.trace != nullptr && blockIdx.x == 0 && threadIdx.x < 32) ? W.trace + 32 : nullptr};
+      eval_due_range<R>(P, rd, sink, S, W.due[cur], r0, r1, round == 1, lane, my_nnz, my_rows);
+      // the objective cut-off row is evaluated in every round (the reference loops it to its own fixpoint in
+      // every sweep, LinearHandler.cpp:1636-1640); the last warp takes it
+      if (P.cut_cnt > 0 && warp_g == n_warps - 1) {
+        const ReadPending rdc{A, P.cut_colx, round > 1};
+        eval_long<R>(P.cut_val, rdc, sink, S, lane, 0, P.cut_cnt, -INFINITY, P.cut_rhs);
+        if (lane == 0) { my_nnz += (unsigned long long)P.cut_cnt; ++my_rows; }
+      }
+    }
+    // ---- fix-up: the variables that moved in the previous round.  It runs AFTER the rows (nothing in this round's
+    //      evaluation depends on it; it only has to land before the barrier); the set bits of 32 words are spread
+    //      over the lanes, so every moved variable is an independent chain ----
+    {
+      int bad = 0;
+      for (int wb = fw0; wb < fw1; wb += 32) {
+        const int w = wb + lane;
+        unsigned word = wb == fw0 ? fw : ((w < fw1) ? __ldcg(Tp + w) : 0u);
+        if (word) Tp[w] = 0u;
+        int incl = __popc(word);
+        my_changes += incl;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(kFullMask, incl, d);
+          if (lane >= d) incl += v;
         }
-        unsigned chm = __ballot_sync(0xffffffffu, ch);
-        if (ch) { changed = 1; ++n_changed; }
-        while (chm) {
-          const int t = __ffs(chm) - 1;
-          chm &= chm - 1;
-          const int qb = __ldg(P.csc_ptr + j0 + t), qe = __ldg(P.csc_ptr + j0 + t + 1);
-          // lane q flags CSC entry q: fire-and-forget OR into the row bit set
-          for (int q = qb + lane; q < qe; q += 32) {
-            const int row = __ldg(P.csc_row + q);
-            atomicOr(W.bits + (row >> 5), 1u << (row & 31));
+        const int total = __shfl_sync(kFullMask, incl, 31);
+        for (int base = 0; base < total; base += 32) {
+          const int x = base + lane;
+          int lo = 0;
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(kFullMask, incl, lo + step - 1);
+            if (v <= x) lo += step;
+          }
+          const unsigned wword = __shfl_sync(kFullMask, word, lo);
+          const int wincl = __shfl_sync(kFullMask, incl, lo);
+          if (x < total) {
+            const int j = (wb + lo) * 32 + (int)__fns(wword, 0, x - (wincl - __popc(wword)) + 1);
+            if (round == 1) {                      // moved by rounding alone: only its rows need flagging
+              flag_rows_serial(P, j, W.due[0]);
+              W.ring[slot] = 1;
+            } else {
+              double2 v = __ldcg(A + j);
+              atomic_max_f64(&Z[j].x, v.x);        // Z lags behind A exactly where A moved last round
+              atomic_min_f64(&Z[j].y, v.y);
+              if (is_int_type(__ldg(P.var_type + j))) tighten_int_bounds(v.x, v.y);
+              if (v.x > v.y + kETol) bad = 1;      // checkBounds_ of the box this round reads
+            }
           }
         }
       }
-    }
-    // block-level reduction of the counters: one global atomic per block, not per thread
-    n_changed = __reduce_add_sync(0xffffffffu, n_changed);
-    if (lane == 0 && n_changed) atomicAdd(&s_count, n_changed);
-    changed = __syncthreads_or(changed);
-    int_moved = __syncthreads_or(int_moved);
-    bad = __syncthreads_or(bad);
-    if (threadIdx.x == 0) {
-      if (s_count) { atomicAdd(&W.status[2], s_count); s_count = 0; }
-      if (changed) W.ring[slot] = 1;
-      if (int_moved) W.ring[3 + slot] = 1;
-      if (bad) W.status[0] = 1 /* MNTR_INFEAS_BOUNDS */;
+      if (bad) W.status[3] = 1;
     }
     MNTR_TRACE();
-    grid_barrier(W.bar, gridDim.x, bar_target);
+    grid_barrier(W.bar, gridDim.x, bar_target, W.ring, s_ctl,
+                 (W.trace != nullptr && round < 16) ? W.trace + 64 + blockIdx.x * 16 + round : nullptr);
     MNTR_TRACE();
-    verdict = vstatus[0];
-    const int any_changed = vring[slot];
-    const int any_int = vring[3 + slot];
-    if (verdict != 0 || !any_changed) break;
+
+    if (s_stat[3]) {                      // the box this round read was already crossed: found after round-1
+      verdict = 1; rounds_out = round - 1; out_buf = cur; out_round = true;
+      break;
+    }
+    rounds_out = round;
+    if (s_stat[0]) {                      // activity-infeasible row: the box of the round start is handed back
+      verdict = 2 /* MNTR_INFEAS_ROW */; out_buf = cur; out_round = round > 1;
+      break;
+    }
+    out_buf = cur ^ 1; out_round = true;
+    if (round == 1 && (s_stat[4] || s_stat[5])) { verdict = 1; break; }    // checkBounds_ after round 1
+    const int any_changed = s_ring[slot];
+    const int any_int = s_ring[3 + slot];
+    if (!any_changed) break;
+    final_check = true;
     if (max_rounds > 0 && round >= max_rounds) break;
     if (loop_mode == 1) {   // LinearHandler::simplePresolve truncation, :1625-1627
       if (round >= 10) break;
       if (round >= 2 && !any_int) break;
     }
+    final_check = false;
   }
 
   // ---- epilogue: hand the box back, publish counters ----
-  for (int j = tid; j < P.n; j += nthreads) {
-    const double2 b = W.box[j];
-    lb_io[j] = b.x;
-    ub_io[j] = b.y;
+  {
+    const double2 *O = W.box[out_buf];
+    for (int j = gtid; j < P.n; j += nthreads) {
+      double2 b = __ldcg(O + j);
+      if (out_round && is_int_type(__ldg(P.var_type + j))) tighten_int_bounds(b.x, b.y);
+      lb_io[j] = b.x;
+      ub_io[j] = b.y;
+    }
+    if (final_check) {                   // bound check of the variables the last round moved
+      const uint32_t *Tl = W.touched[round & 1];
+      int bad = 0;
+      for (int w = tid; w < nw_vars; w += nthreads) {
+        unsigned word = __ldcg(Tl + w);
+        my_changes += __popc(word);
+        while (word) {
+          const int j = w * 32 + __ffs(word) - 1;
+          word &= word - 1;
+          double2 v = __ldcg(O + j);
+          if (is_int_type(__ldg(P.var_type + j))) tighten_int_bounds(v.x, v.y);
+          if (v.x > v.y + kETol) bad = 1;
+        }
+      }
+      if (bad) W.status[3] = 1;
+    }
   }
+  __shared__ unsigned long long s_nnz, s_rows;
+  __shared__ int s_changes;
+  if (threadIdx.x == 0) { s_nnz = 0ull; s_rows = 0ull; s_changes = 0; }
+  __syncthreads();
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     my_nnz += __shfl_xor_sync(0xffffffffu, my_nnz, off);
     my_rows += __shfl_xor_sync(0xffffffffu, my_rows, off);
   }
+  my_changes = __reduce_add_sync(0xffffffffu, my_changes);
   if (lane == 0 && my_rows) { atomicAdd(&s_nnz, my_nnz); atomicAdd(&s_rows, my_rows); }
+  if (lane == 0 && my_changes) atomicAdd(&s_changes, my_changes);
   __syncthreads();
-  if (threadIdx.x == 0 && s_rows) { atomicAdd(&W.counters[0], s_nnz); atomicAdd(&W.counters[1], s_rows); }
-  if (tid == 0) W.status[1] = round;
+  if (threadIdx.x == 0) {
+    if (s_rows) { atomicAdd(&W.counters[0], s_nnz); atomicAdd(&W.counters[1], s_rows); }
+    if (s_changes) atomicAdd(&W.status[2], s_changes);
+    if (blockIdx.x == 0) { W.status[1] = rounds_out; W.status[6] = verdict; }
+  }
   MNTR_TRACE();
 }
 
-template <int G, class R>
-cudaError_t launch_g(const LinDev &P, const SingleWs &W, double *lb, double *ub, int max_rounds,
+template <class R>
+cudaError_t launch_r(const LinDev &P, const SingleWs &W, double *lb, double *ub, int max_rounds,
                      int loop_mode, int sm_count, cudaStream_t stream)
 {
-  auto kern = fbbt_single_jacobi_kernel<G, R>;
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSingleThreads, 0);
+  auto kern = fbbt_single_jacobi_kernel<R>;
+  const size_t smem = sizeof(WarpStage) * kSingleWarps;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-  long long want_threads = (long long)P.m * G;
-  if (want_threads < P.n) want_threads = P.n;
-  long long want_blocks = (want_threads + kSingleThreads - 1) / kSingleThreads;
-  long long max_blocks = (long long)per_sm * sm_count;
-  int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
+  // at least 8 rows per warp: small problems run on few blocks and pay a cheaper barrier
+  long long want_warps = ((long long)P.m + 7) / 8;
+  const long long var_warps = ((long long)P.n + 255) / 256;
+  if (want_warps < var_warps) want_warps = var_warps;
+  long long blocks = (want_warps + kSingleWarps - 1) / kSingleWarps;
+  if (blocks > sm_count) blocks = sm_count;
   if (blocks < 1) blocks = 1;
   LinDev p = P; SingleWs w = W;
   void *args[] = { &p, &w, &lb, &ub, &max_rounds, &loop_mode };
   // cooperative launch: guarantees that all blocks are co-resident, which the barrier relies on
-  return cudaLaunchCooperativeKernel((void *)kern, dim3(blocks), dim3(kSingleThreads), args, 0, stream);
-}
-
-template <class R>
-cudaError_t launch_r(int G, const LinDev &P, const SingleWs &W, double *lb, double *ub,
-                     int max_rounds, int loop_mode, int sm_count, cudaStream_t stream)
-{
-  switch (G) {
-  case 2:  return launch_g<2, R>(P, W, lb, ub, max_rounds, loop_mode, sm_count, stream);
-  case 4:  return launch_g<4, R>(P, W, lb, ub, max_rounds, loop_mode, sm_count, stream);
-  case 8:  return launch_g<8, R>(P, W, lb, ub, max_rounds, loop_mode, sm_count, stream);
-  case 16: return launch_g<16, R>(P, W, lb, ub, max_rounds, loop_mode, sm_count, stream);
-  default: return launch_g<32, R>(P, W, lb, ub, max_rounds, loop_mode, sm_count, stream);
-  }
+  return cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)blocks), dim3(kSingleThreads), args, smem, stream);
 }
 
 }  // namespace
 
 cudaError_t launch_single_jacobi(const LinDev &P, const SingleWs &W, double *lb_dev, double *ub_dev,
-                                 int lanes_per_row, bool directed, int max_rounds, int loop_mode,
-                                 int sm_count, cudaStream_t stream)
+                                 bool directed, int max_rounds, int loop_mode, int sm_count, cudaStream_t stream)
 {
-  if (directed)
-    return launch_r<RoundDirected>(lanes_per_row, P, W, lb_dev, ub_dev, max_rounds, loop_mode, sm_count, stream);
-  return launch_r<RoundNearest>(lanes_per_row, P, W, lb_dev, ub_dev, max_rounds, loop_mode, sm_count, stream);
+  if (directed) return launch_r<RoundDirected>(P, W, lb_dev, ub_dev, max_rounds, loop_mode, sm_count, stream);
+  return launch_r<RoundNearest>(P, W, lb_dev, ub_dev, max_rounds, loop_mode, sm_count, stream);
 }
 
 }  // namespace mntr

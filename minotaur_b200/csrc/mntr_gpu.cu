@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -34,9 +35,10 @@ struct mntr_gpu_ctx {
   bool lin_loaded = false;
   int32_t m = 0, n = 0;
   int64_t nnz = 0, nnz_padded = 0;
-  int lanes_per_row = 8;
+  std::vector<uint8_t> h_var_type;   // host copy: integer bit of the stored columns
+  int lanes_per_row = 8;             // sub-warp group size of the per-round kernels
   LinDev lin{};
-  std::vector<void *> lin_allocs;
+  std::vector<void *> lin_allocs, cut_allocs;
 
   // ---- cgraph tapes ----
   bool nl_loaded = false;
@@ -72,7 +74,12 @@ struct mntr_gpu_ctx {
 };
 
 // host mirror of the single-box kernel's control block (SingleWs::ring/status/counters/bar)
-struct SingleCtrl { int32_t ring[12]; int32_t status[4]; unsigned long long counters[2]; unsigned bar; unsigned pad[11]; };
+constexpr int kTraceWords = 64 + 256 * 16;   // MNTR_GPU_TRACE buffer: phases, one warp's passes, barrier arrivals
+struct SingleCtrl {
+  int32_t ring[12]; int32_t status[8]; unsigned long long counters[2]; unsigned bar; unsigned pad[7];
+  // the loop's verdict, or MNTR_INFEAS_BOUNDS when the bound check of the last round's moved variables failed
+  int verdict() const { return status[6] ? status[6] : (status[3] ? 1 : 0); }
+};
 static_assert(sizeof(SingleCtrl) == 128, "control block layout");
 
 namespace {
@@ -274,7 +281,7 @@ void mntr_gpu_destroy(mntr_gpu_ctx *ctx)
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
   if (ctx->h_ctrl) { cudaFreeHost(ctx->h_ctrl); ctx->h_ctrl = nullptr; }
-  free_all(ctx->lin_allocs); free_all(ctx->nl_allocs); free_all(ctx->single_allocs);
+  free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->nl_allocs); free_all(ctx->single_allocs);
   free_batch(ctx); free_stage(ctx);
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -299,7 +306,7 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
     return fail(ctx, MNTR_E_ARG, "load_linear: null or negative argument");
   if (row_ptr[0] != 0) return fail(ctx, MNTR_E_ARG, "load_linear: row_ptr[0] != 0");
   CU(cudaSetDevice(ctx->device));
-  free_all(ctx->lin_allocs); free_all(ctx->single_allocs); free_batch(ctx); free_stage(ctx);
+  free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->single_allocs); free_batch(ctx); free_stage(ctx);
   free_all(ctx->nl_allocs); ctx->nl_loaded = false;
   ctx->lin_loaded = false;
 
@@ -383,6 +390,12 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pinfo.data(), (size_t)m, &L.row_info))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pbnd.data(), (size_t)m, &L.row_bnd))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pcol.data(), pcol.size(), &L.col))) return rc;
+  {
+    std::vector<int32_t> pcolx(pcol);           // bit 31: the variable is integer (rounded by the reader)
+    for (auto &c : pcolx) if (is_int_type(var_type[c])) c |= INT32_MIN;
+    if ((rc = dev_upload(ctx, ctx->lin_allocs, pcolx.data(), pcolx.size(), &L.colx))) return rc;
+  }
+  ctx->h_var_type.assign(var_type, var_type + n);
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pval.data(), pval.size(), &L.val))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, var_type, (size_t)n, &L.var_type))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, cptr.data(), (size_t)n + 1, &L.csc_ptr))) return rc;
@@ -396,25 +409,26 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
     ctx->single_allocs.push_back(*p);
     return MNTR_OK;
   };
-  if ((rc = dalloc((void **)&W.box, sizeof(double2) * (size_t)n))) return rc;
-  if ((rc = dalloc((void **)&W.nbox, sizeof(double2) * (size_t)n))) return rc;
-  if ((rc = dalloc((void **)&W.bits, sizeof(uint32_t) * (size_t)((m + 31) / 32 + 1)))) return rc;
-  if ((rc = dalloc((void **)&W.list, sizeof(int32_t) * (size_t)m))) return rc;
+  for (int k = 0; k < 2; ++k) {
+    if ((rc = dalloc((void **)&W.box[k], sizeof(double2) * (size_t)n))) return rc;
+    if ((rc = dalloc((void **)&W.due[k], sizeof(uint32_t) * (size_t)((m + 31) / 32 + 1)))) return rc;
+    if ((rc = dalloc((void **)&W.touched[k], sizeof(uint32_t) * (size_t)((n + 31) / 32 + 1)))) return rc;
+  }
   if ((rc = dalloc((void **)&ctx->d_lb, sizeof(double) * (size_t)n))) return rc;
   if ((rc = dalloc((void **)&ctx->d_ub, sizeof(double) * (size_t)n))) return rc;
   if ((rc = dalloc(&ctx->d_ctrl, sizeof(SingleCtrl)))) return rc;
   W.ring = (int32_t *)ctx->d_ctrl;
   W.status = W.ring + 12;
-  W.counters = (unsigned long long *)((char *)ctx->d_ctrl + 64);
-  W.bar = (unsigned *)((char *)ctx->d_ctrl + 80);
+  W.counters = (unsigned long long *)((char *)ctx->d_ctrl + offsetof(SingleCtrl, counters));
+  W.bar = (unsigned *)((char *)ctx->d_ctrl + offsetof(SingleCtrl, bar));
   W.trace = nullptr;
   if (const char *tr = getenv("MNTR_GPU_TRACE")) {
-    if (tr[0] == '1') { if ((rc = dalloc((void **)&W.trace, 64 * sizeof(unsigned long long)))) return rc; }
+    if (tr[0] == '1') { if ((rc = dalloc((void **)&W.trace, kTraceWords * sizeof(unsigned long long)))) return rc; }
   }
 
   // per-round workspace shares box / bits / list with the single-launch kernel
   RoundsWs &RW = ctx->rws;
-  RW.box = W.box; RW.bits = W.bits; RW.list = W.list;
+  RW.box = W.box[0]; RW.bits = W.due[0];
   if ((rc = dalloc((void **)&RW.nlb, sizeof(double) * ((size_t)n + 1)))) return rc;
   if ((rc = dalloc((void **)&RW.nub, sizeof(double) * ((size_t)n + 1)))) return rc;
   if ((rc = dalloc((void **)&RW.ctrl, 64))) return rc;
@@ -422,11 +436,12 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if (!ctx->h_ctrl) CU(cudaMallocHost((void **)&ctx->h_ctrl, 64));
   if (const char *fr = getenv("MNTR_GPU_ROUNDS")) ctx->force_rounds = fr[0] == '1';
 
-  // sub-warp group size from the mean row length (four entries per lane per step)
-  const double mean = m > 0 ? (double)nnz / m : 0.0;
-  int g = 2;
-  while (g < 32 && 4 * g < mean + 0.5) g *= 2;
-  ctx->lanes_per_row = g;
+  {   // sub-warp group size of the per-round kernels from the mean row length (four entries per lane per step)
+    const double mean = m > 0 ? (double)nnz / m : 0.0;
+    int g = 2;
+    while (g < 32 && 4 * g < mean + 0.5) g *= 2;
+    ctx->lanes_per_row = g;
+  }
   ctx->m = m; ctx->n = n; ctx->nnz = nnz; ctx->nnz_padded = (int64_t)pcol.size();
   CU(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
   ctx->lin_loaded = true;
@@ -536,20 +551,47 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
   return MNTR_OK;
 }
 
-int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *, const double *, double)
+int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *col, const double *val, double rhs)
 {
   if (!ctx) return MNTR_E_ARG;
-  if (k == 0) return MNTR_OK;
-  return fail(ctx, MNTR_E_UNSUPPORTED, "set_cutoff: objective cut-off row is not implemented yet");
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "set_cutoff: call load_linear first");
+  CU(cudaSetDevice(ctx->device));
+  free_all(ctx->cut_allocs);
+  ctx->lin.cut_cnt = 0; ctx->lin.cut_col = nullptr; ctx->lin.cut_colx = nullptr; ctx->lin.cut_val = nullptr;
+  ctx->lin.cut_bnd = nullptr; ctx->lin.cut_rhs = INFINITY;
+  if (k <= 0) return MNTR_OK;
+  if (!col || !val) return fail(ctx, MNTR_E_ARG, "set_cutoff: null argument");
+  std::vector<int32_t> c; std::vector<double> v;
+  int32_t prev = -1;
+  for (int32_t t = 0; t < k; ++t) {
+    if (col[t] < 0 || col[t] >= ctx->n) return fail(ctx, MNTR_E_ARG, "set_cutoff: column %d out of range", col[t]);
+    if (col[t] <= prev) return fail(ctx, MNTR_E_ARG, "set_cutoff: columns not strictly ascending");
+    prev = col[t];
+    if (std::fabs(val[t]) <= kCoefDrop) continue;       // LinearFunction drops these, LinearFunction.cpp:89-95
+    c.push_back(col[t]); v.push_back(val[t]);
+  }
+  const int32_t cnt = (int32_t)c.size();
+  if (cnt == 0) return MNTR_OK;
+  while (c.size() % kRowPad) { c.push_back(c.back()); v.push_back(0.0); }
+  std::vector<int32_t> cx(c);
+  for (auto &j : cx) if (is_int_type(ctx->h_var_type[j])) j |= INT32_MIN;
+  int rc;
+  if ((rc = dev_upload(ctx, ctx->cut_allocs, c.data(), c.size(), &ctx->lin.cut_col))) return rc;
+  if ((rc = dev_upload(ctx, ctx->cut_allocs, cx.data(), cx.size(), &ctx->lin.cut_colx))) return rc;
+  if ((rc = dev_upload(ctx, ctx->cut_allocs, v.data(), v.size(), &ctx->lin.cut_val))) return rc;
+  const double2 bnd = make_double2(-INFINITY, rhs);
+  if ((rc = dev_upload(ctx, ctx->cut_allocs, &bnd, 1, &ctx->lin.cut_bnd))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->lin.cut_rhs = rhs;
+  ctx->lin.cut_cnt = cnt;
+  return MNTR_OK;
 }
-
 
 // K1 on a device-resident box; leaves verdict/rounds/counters in the control block
 static int run_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, const mntr_gpu_options &o)
 {
   CU(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(SingleCtrl), ctx->stream));
-  CU(launch_single_jacobi(ctx->lin, ctx->sws, lb_dev, ub_dev, ctx->lanes_per_row,
-                          o.rounding == MNTR_ROUND_DIRECTED, o.max_rounds, o.loop, ctx->sm_count, ctx->stream));
+  CU(launch_single_jacobi(ctx->lin, ctx->sws, lb_dev, ub_dev, o.rounding == MNTR_ROUND_DIRECTED, o.max_rounds, o.loop, ctx->sm_count, ctx->stream));
   return MNTR_OK;
 }
 
@@ -558,7 +600,7 @@ static void account_single(mntr_gpu_ctx *ctx, const SingleCtrl &ctrl)
   ctx->stats.nnz_updates += (int64_t)ctrl.counters[0];
   ctx->stats.rows_evaluated += (int64_t)ctrl.counters[1];
   ctx->stats.n_changes += (int64_t)ctrl.status[2];
-  ctx->stats.n_infeasible += ctrl.status[0] != 0;
+  ctx->stats.n_infeasible += ctrl.verdict() != 0;
   ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, ctrl.status[1]);
 }
 
@@ -661,7 +703,7 @@ static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_
   CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, sizeof(SingleCtrl), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (verdict) *verdict = ctrl.status[0];
+  if (verdict) *verdict = ctrl.verdict();
   if (rounds) *rounds = ctrl.status[1];
   if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
   account_single(ctx, ctrl);
@@ -696,17 +738,27 @@ int mntr_gpu_tighten_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_de
   SingleCtrl ctrl;
   CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, sizeof(SingleCtrl), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (verdict) *verdict = ctrl.status[0];
+  if (verdict) *verdict = ctrl.verdict();
   if (rounds) *rounds = ctrl.status[1];
   if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
   account_single(ctx, ctrl);
   ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
   if (ctx->sws.trace) {     // debug: phase durations of the fixpoint kernel
-    unsigned long long t[64];
+    static unsigned long long t[kTraceWords];
     CU(cudaMemcpy(t, ctx->sws.trace, sizeof(t), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[mntr trace] rounds=%d kernel=%.1fus phases(us):", ctrl.status[1], ctx->stats.kernel_ms * 1e3);
-    const int np = 4 + 4 * ctrl.status[1];
-    for (int k = 1; k < np && k < 64; ++k) fprintf(stderr, " %.1f", (double)(t[k] - t[k - 1]) * 1e-3);
+    const int np = 4 + 2 * (ctrl.status[1] + 1);
+    for (int k = 1; k < np && k < 64 && t[k] != 0; ++k) fprintf(stderr, " %.1f", (double)(t[k] - t[k - 1]) * 1e-3);
+    fprintf(stderr, "\n[mntr probe] warp 0 (us since kernel start):");
+    for (int k = 32; k < 64 && t[k] != 0; ++k) fprintf(stderr, " %.1f", (double)(t[k] - t[0]) * 1e-3);
+    fprintf(stderr, "\n[mntr arrive] per round: first / median / last block at the barrier (us since kernel start):");
+    for (int r = 1; r < 16; ++r) {
+      std::vector<double> a;
+      for (int b = 0; b < 256; ++b) if (t[64 + b * 16 + r] != 0) a.push_back((double)(t[64 + b * 16 + r] - t[0]) * 1e-3);
+      if (a.empty()) break;
+      std::sort(a.begin(), a.end());
+      fprintf(stderr, "  r%d %.1f/%.1f/%.1f", r, a.front(), a[a.size() / 2], a.back());
+    }
     fprintf(stderr, "\n");
     CU(cudaMemset(ctx->sws.trace, 0, sizeof(t)));
   }
