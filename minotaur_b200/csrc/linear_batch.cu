@@ -210,7 +210,8 @@ __device__ __forceinline__ bool update_exact(double av, double numer, bool sing,
 template <class R, bool FROM_LB>
 __device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int cnt_row, double2 *bx, int64_t ld,
                                                const RowStage &st, bool doit, bool sing, double rbound, double act,
-                                               uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane)
+                                               uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane,
+                                               bool count_int = true)
 {
   unsigned any = 0;
   // (row bound - activity): FromLb needs a lower estimate, FromUb an upper estimate
@@ -229,7 +230,7 @@ __device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int cnt
       flag_rows_of(P, j, m, flags, varflag, lane);
       if (chg) {
         sh.changed[lane] = 1;
-        if (is_int_type(__ldg(P.var_type + j))) sh.nint[lane] = 1;
+        if (count_int && is_int_type(__ldg(P.var_type + j))) sh.nint[lane] = 1;
       }
     }
   };
@@ -294,6 +295,39 @@ __device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx,
   }
   if (__any_sync(kFull, do_ub))
     (void)row_update<R, false>(P, beg, cnt, bx, ld, st, do_ub, s_ub, ru, act, flags, varflag, sh, lane);
+}
+
+// Objective cut-off row  c.x <= rhs  for the 32 boxes of the tile  [varBndsFromObj_, :544-597]: evaluated after
+// the row sweep, by ONE warp (it may share variables with any row), and looped until it moves nothing more.
+// Its modifications of integer variables do not count towards nintmods (the reference counts them into a local
+// it never reads, :554), and an infeasible cut-off stops the box like an activity-infeasible row.
+template <class R>
+__device__ __noinline__ void cutoff_row(const LinDev &P, double2 *bx, int64_t ld, const RowStage &st, bool run,
+                                        uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane,
+                                        unsigned long long &my_nnz)
+{
+  LinDev C = P;
+  C.col = P.cut_col; C.val = P.cut_val;
+  const int cnt = P.cut_cnt;
+  bool mine = run && sh.verdict[lane] == 0;
+  while (__any_sync(kFull, mine)) {
+    double ll, uu, sing_ll = INFINITY, sing_uu = INFINITY;
+    row_activity<R>(C, 0, cnt, bx, ld, st, lane, ll, uu);
+    const bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
+    if (__any_sync(kFull, need_sing)) row_sing_activity<R>(C, 0, cnt, bx, ld, need_sing, sing_ll, sing_uu);
+    if (mine) my_nnz += (unsigned long long)cnt;
+    if (mine && ll > P.cut_rhs + kETol) { sh.verdict[lane] = 2; /* MNTR_INFEAS_ROW */ mine = false; }
+    bool doit = false, sing = false;
+    double act = 0.0;
+    if (mine) {
+      if (ll > -kInf20) { doit = true; act = ll; }
+      else if (sing_ll > -kInf20) { doit = true; sing = true; act = sing_ll; }
+    }
+    unsigned chg = 0;
+    if (__any_sync(kFull, doit))
+      chg = row_update<R, false>(C, 0, cnt, bx, ld, st, doit, sing, P.cut_rhs, act, flags, varflag, sh, lane, false);
+    mine = mine && ((chg >> lane) & 1u);
+  }
 }
 
 // integer rounding [tightenInts_] + lb>ub check [checkBounds_] of variable j for the lanes in `want`
@@ -377,6 +411,12 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
           process_row<R>(P, q0 + t, bx, ld, st, (proc >> lane) & 1u, flags, varflag, sh, lane, my_nnz);
         }
       }
+      team.sync();
+    }
+
+    // ---- objective cut-off row (only with an incumbent), :1636-1640 ----
+    if (P.cut_cnt > 0) {
+      if (warp == 0) cutoff_row<R>(P, bx, ld, st, run, flags, varflag, sh, lane, my_nnz);
       team.sync();
     }
 

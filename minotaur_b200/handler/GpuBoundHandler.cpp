@@ -40,7 +40,7 @@ const std::string GpuBoundHandler::me_ = "GpuBoundHandler: ";
 
 GpuBoundHandler::GpuBoundHandler(EnvPtr env, ProblemPtr problem, int device)
   : env_(env), problem_(problem), ctx_(0), mode_(FastFixpoint), roundNearest_(false), loadedFor_(0),
-    loadedVars_(0), loadedCons_(0)
+    loadedVars_(0), loadedCons_(0), cutoffOn_(false)
 {
   logger_ = env->getLogger();
   stats_.calls = stats_.uploads = stats_.nMods = stats_.nInf = 0;
@@ -194,9 +194,37 @@ void GpuBoundHandler::upload_(ProblemPtr p)
   ++stats_.uploads;
 }
 
-bool GpuBoundHandler::tighten_(ProblemPtr p, ModVector &mods, bool truncated)
+// The incumbent's cut-off row  c.x <= best - constant  (LinearHandler::simplePresolve, LinearHandler.cpp:1636-1640,
+// varBndsFromObj_ :544-597): only for a linear objective, only when the pool holds a solution.
+void GpuBoundHandler::setCutoff_(ProblemPtr p, SolutionPoolPtr spool)
 {
-  if (loadedFor_ != p || loadedVars_ != p->getNumVars() || loadedCons_ != p->getNumCons()) upload_(p);
+  ObjectivePtr o = p->getObjective();
+  LinearFunctionPtr lf = o ? o->getLinearFunction() : LinearFunctionPtr();
+  const bool on = spool && spool->getNumSols() > 0 && lf && o->getFunctionType() == Linear;
+  if (!on) {
+    if (cutoffOn_) {
+      if (mntr_gpu_set_cutoff(ctx_, 0, 0, 0, 0.0) != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+      cutoffOn_ = false;
+    }
+    return;
+  }
+  std::vector<std::pair<int, double> > terms;
+  for (VariableGroupConstIterator t = lf->termsBegin(); t != lf->termsEnd(); ++t)
+    terms.push_back(std::make_pair((int)t->first->getIndex(), t->second));
+  std::sort(terms.begin(), terms.end());
+  std::vector<int> col(terms.size());
+  std::vector<double> val(terms.size());
+  for (size_t t = 0; t < terms.size(); ++t) { col[t] = terms[t].first; val[t] = terms[t].second; }
+  const double rhs = spool->getBestSolutionValue() - o->getConstant();
+  if (mntr_gpu_set_cutoff(ctx_, (int)col.size(), col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0], rhs) != MNTR_OK)
+    throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+  cutoffOn_ = !col.empty();
+}
+
+bool GpuBoundHandler::tighten_(ProblemPtr p, SolutionPoolPtr spool, ModVector &mods, bool truncated)
+{
+  if (loadedFor_ != p || loadedVars_ != p->getNumVars() || loadedCons_ != p->getNumCons()) { upload_(p); cutoffOn_ = false; }
+  setCutoff_(p, spool);
   const UInt n = p->getNumVars();
   for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) {
     const UInt j = (*it)->getIndex();
@@ -247,11 +275,11 @@ bool GpuBoundHandler::tighten_(ProblemPtr p, ModVector &mods, bool truncated)
   return false;
 }
 
-void GpuBoundHandler::simplePresolve(ProblemPtr p, SolutionPoolPtr, ModVector &t_mods, SolveStatus &status)
+void GpuBoundHandler::simplePresolve(ProblemPtr p, SolutionPoolPtr spool, ModVector &t_mods, SolveStatus &status)
 {
   Timer *timer = env_->getNewTimer();
   timer->start();
-  const bool inf = tighten_(p, t_mods, true);
+  const bool inf = tighten_(p, spool, t_mods, true);
   if (inf) status = SolvedInfeasible;
   stats_.timeHost += timer->query();
   delete timer;
@@ -292,7 +320,7 @@ SolveStatus GpuBoundHandler::presolve(PreModQ *, bool *changed, Solution **)
   ModVector mods;
   Timer *timer = env_->getNewTimer();
   timer->start();
-  const bool inf = tighten_(problem_, mods, false);
+  const bool inf = tighten_(problem_, SolutionPoolPtr(), mods, false);     // root presolve: no incumbent yet
   if (!mods.empty()) *changed = true;
   // root mode keeps no undo information: the mods are already applied (LinearHandler deletes them too,
   // LinearHandler.cpp:1093-1099)

@@ -101,12 +101,14 @@ private:
   // identity of the structure currently on the device
   const Problem *loadedFor_;
   UInt loadedVars_, loadedCons_;
+  bool cutoffOn_;      // an objective cut-off row is installed on the device
   std::vector<double> lb_, ub_, lb0_, ub0_;
 
   /// Flatten p (linear rows -> CSR, CGraph constraints -> tapes) and upload it.
   void upload_(ProblemPtr p);
   /// One tighten call on the current bounds of p; emits applied VarBoundMods.  Returns infeasible?
-  bool tighten_(ProblemPtr p, ModVector &mods, bool truncated);
+  bool tighten_(ProblemPtr p, SolutionPoolPtr spool, ModVector &mods, bool truncated);
+  void setCutoff_(ProblemPtr p, SolutionPoolPtr spool);
   void copyBndsFromRel_(RelaxationPtr rel, ModVector &p_mods);
 };
 

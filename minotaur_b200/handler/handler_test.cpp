@@ -21,6 +21,7 @@
 #include "Objective.h"
 #include "Problem.h"
 #include "Relaxation.h"
+#include "SolutionPool.h"
 #include "VarBoundMod.h"
 #include "Variable.h"
 
@@ -72,9 +73,14 @@ static ProblemPtr makeProblem(EnvPtr env, int n, int m, int k, int n_nl, std::ve
     p->newConstraint((FunctionPtr) new Function(lf, (NonlinearFunctionPtr)cg), -INFINITY, val + irand(0, 3));
   }
   // Relaxation's cloning constructor dereferences the objective (Relaxation.cpp:139-140)
+  // a linear objective over ~30 variables: with an incumbent it becomes the cut-off row of varBndsFromObj_
   LinearFunctionPtr of = (LinearFunctionPtr) new LinearFunction();
   of->addTerm(v[0], 1.0);
-  p->newObjective((FunctionPtr) new Function(of), 0.0, Minimize);
+  for (int t = 0; t < 30; ++t) {
+    const int j = irand(1, n - 1);
+    if (of->getWeight(v[j]) == 0.0) of->addTerm(v[j], (double)irand(1, 5));
+  }
+  p->newObjective((FunctionPtr) new Function(of), 2.5, Minimize);
   p->calculateSize();
   return p;
 }
@@ -99,7 +105,7 @@ int main()
   int err = 0;
   env->startTimer(err);
   env->setLogLevel(LogNone);
-  int n_cmp = 0, n_inf = 0, n_mods = 0;
+  int n_cmp = 0, n_inf = 0, n_mods = 0, n_cut = 0;
   for (int trial = 0; trial < 6; ++trial) {
     std::vector<double> xstar;
     const int n = 300 + 50 * trial, m = 350, n_nl = (trial % 2) ? 40 : 0;
@@ -115,11 +121,21 @@ int main()
       std::vector<double> lb0(n), ub0(n);
       for (int j = 0; j < n; ++j) { lb0[j] = relB->getVariable(j)->getLb(); ub0[j] = relB->getVariable(j)->getUb(); }
 
+      // every other box of the purely linear trials has an incumbent: the objective becomes the cut-off row
+      // (the nonlinear handler's own incumbent rule, fixObjBins_, is not built: DESIGN.md section 2)
+      SolutionPool *spool = 0;
+      if (n_nl == 0 && (box & 1)) {
+        std::vector<double> x(n, 0.0);
+        spool = new SolutionPool(env, p, 10);
+        spool->addSolution(&x[0], 2.5 + irand(15, 45));
+        ++n_cut;
+      }
+
       // reference: LinearHandler then NlPresHandler, one PCBProcessor::presolveNode_ pass
       LinearHandler lh(env, p);
       NlPresHandler nh(env, p);
       ModVector pm, rmA;
-      bool infA = lh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pm, rmA);
+      bool infA = lh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)spool, pm, rmA);
       if (!infA && n_nl) infA = nh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pm, rmA);
 
       // GPU handler in reference-order, round-to-nearest mode: must reproduce it bit for bit
@@ -127,7 +143,7 @@ int main()
       gh.setMode(GpuBoundHandler::ReferenceOrder);
       gh.setRoundNearest(true);
       ModVector rmB;
-      const bool infB = gh.presolveNode(relB, (NodePtr)0, (SolutionPoolPtr)0, pm, rmB);
+      const bool infB = gh.presolveNode(relB, (NodePtr)0, (SolutionPoolPtr)spool, pm, rmB);
       ++n_cmp;
       if (infB && !infA) {
         // allowed only when the GPU proved an activity-infeasible row, which the reference's node mode drops
@@ -168,9 +184,11 @@ int main()
       for (ModVector::iterator it = rmA.begin(); it != rmA.end(); ++it) delete *it;
       for (ModVector::iterator it = rmB.begin(); it != rmB.end(); ++it) delete *it;
       delete relA; delete relB;
+      delete spool;
     }
     delete p;
   }
-  printf("handler_test: %d comparisons, %d infeasible, %d mods emitted, %d failures\n", n_cmp, n_inf, n_mods, failures);
+  printf("handler_test: %d comparisons (%d with an incumbent cut-off), %d infeasible, %d mods emitted, %d failures\n",
+         n_cmp, n_cut, n_inf, n_mods, failures);
   return failures ? 1 : 0;
 }

@@ -351,6 +351,21 @@ def make_knapsack_setcover(m: int = 50_000, n: int = 50_000, nnz_per_row: int = 
                       xstar=xstar)
 
 
+def attach_cutoff(inst: LinearRows, k: int, seed: int, slack: float, box=None) -> LinearRows:
+    """Gives ``inst`` an objective cut-off row  c.x <= rhs  (LinearHandler::varBndsFromObj_,
+    /root/reference/src/base/LinearHandler.cpp:544-597): k random variables with finite root bounds, random
+    coefficients, rhs = minimum activity over ``box`` (default: the root box; tests pass the tightened root box,
+    which makes a small slack bite) + slack, so the row moves bounds without making the box trivially infeasible."""
+    blb, bub = (inst.lb, inst.ub) if box is None else box
+    rng = np.random.default_rng(seed)
+    finite = np.nonzero(np.isfinite(inst.lb) & np.isfinite(inst.ub) & (np.abs(inst.lb) < 1e19) & (np.abs(inst.ub) < 1e19))[0]
+    cols = np.sort(rng.choice(finite, min(k, len(finite)), replace=False)).astype(np.int32)
+    vals = rng.uniform(0.5, 3.0, len(cols)) * rng.choice([-1.0, 1.0], len(cols))
+    lo = float(np.sum(np.where(vals > 0, vals * blb[cols], vals * bub[cols])))
+    inst.cut_col, inst.cut_val, inst.cut_rhs = cols, vals, lo + slack
+    return inst
+
+
 def branch_boxes(inst_lb: np.ndarray, inst_ub: np.ndarray, var_type: np.ndarray, n_boxes: int,
                  seed: int = 2024, max_depth: int = 20, continuous_too: bool = False
                  ) -> Tuple[np.ndarray, np.ndarray]:

@@ -217,6 +217,8 @@ static int gs_cutoff(gs_t *s, int *changed)
   const orc_lin_t *p = s->p;
   if (p->cut_k <= 0) return 0;
   int t_changed = 1;
+  const uint32_t nintmods_keep = s->nintmods;  /* varBndsFromObj_ counts into a local it never reads (:554) */
+  int status = 0;
   while (t_changed) {
     double ll, uu, sing_ll = INFINITY, sing_uu = INFINITY;
     t_changed = 0;
@@ -224,13 +226,14 @@ static int gs_cutoff(gs_t *s, int *changed)
     if (ll < -INF20 || uu > INF20)
       lf_sing_bnds(p->cut_k, p->cut_col, p->cut_val, s->lb, s->ub, &sing_ll, &sing_uu);
     s->nnz_updates += p->cut_k;
-    if (ll > p->cut_rhs + E_TOL) return 1;
+    if (ll > p->cut_rhs + E_TOL) { status = 1; break; }
     if (ll > -INF20) gs_from_ub(s, p->cut_k, p->cut_col, p->cut_val, p->cut_rhs, ll, 0, &t_changed);
     else if (sing_ll > -INF20)
       gs_from_ub(s, p->cut_k, p->cut_col, p->cut_val, p->cut_rhs, sing_ll, 1, &t_changed);
     if (t_changed) *changed = 1;
   }
-  return 0;
+  s->nintmods = nintmods_keep;
+  return status;
 }
 
 /* ref: LinearHandler.cpp:415-490 tightenInts_ with apply_to_prob == false */

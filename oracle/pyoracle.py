@@ -222,6 +222,8 @@ class Reference:
                                      C.c_double, C.c_double]
             L.ref_add_nl.restype = C.c_int32
             L.ref_finish.argtypes = [C.c_void_p]
+            L.ref_set_objective.argtypes = [C.c_void_p, C.c_int32, _ip, _dp, C.c_double]
+            L.ref_set_incumbent.argtypes = [C.c_void_p, C.c_int32, C.c_double]
             L.ref_set_box.argtypes = [C.c_void_p, _dp, _dp]
             L.ref_get_box.argtypes = [C.c_void_p, _dp, _dp]
             L.ref_lin_fixpoint.argtypes = [C.c_void_p, _ip, C.POINTER(C.c_int64)]
@@ -260,7 +262,17 @@ class Reference:
                 lv = np.ascontiguousarray(tapes.lin_val[lbeg:lend] if lend > lbeg else np.zeros(1))
                 L.ref_add_nl(self.h, e - b, _b(op), _i(a0), _i(a1), _d(cn), _i(tapes.child), lend - lbeg,
                              _i(lc), _d(lv), float(tapes.c_lb[c]), float(tapes.c_ub[c]))
+        if inst.cut_col is not None and len(inst.cut_col):
+            # the cut-off row c.x <= cut_rhs as the reference meets it: a linear objective (constant 0) and an
+            # incumbent of value cut_rhs in the solution pool (LinearHandler.cpp:1636-1640)
+            cc = np.ascontiguousarray(inst.cut_col, np.int32); cv = np.ascontiguousarray(inst.cut_val, np.float64)
+            L.ref_set_objective(self.h, len(cc), _i(cc), _d(cv), 0.0)
+            L.ref_set_incumbent(self.h, 1, float(inst.cut_rhs))
         L.ref_finish(self.h)
+
+    def set_incumbent(self, value=None):
+        """value None removes the incumbent (no cut-off row)."""
+        self.lib().ref_set_incumbent(self.h, 0 if value is None else 1, 0.0 if value is None else float(value))
 
     def close(self):
         if self.h:

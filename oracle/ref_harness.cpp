@@ -32,6 +32,7 @@
 #include "Objective.h"
 #include "Option.h"
 #include "Problem.h"
+#include "SolutionPool.h"
 #include "Types.h"
 #include "VarBoundMod.h"
 #include "Variable.h"
@@ -50,14 +51,24 @@ public:
     for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it) (*it)->setBFlag(true);
   }
 
+  /* cut-off value of the incumbent, as simplePresolve forms it (LinearHandler.cpp:1636-1640) */
+  static bool cutoff(ProblemPtr p, SolutionPool *spool, double *ub)
+  {
+    if (!spool || spool->getNumSols() == 0 || !p->getObjective()) return false;
+    *ub = spool->getBestSolutionValue() - p->getObjective()->getConstant();
+    return true;
+  }
+
   /* SURVEY.md section 8c parity driver: the reference's sweeps, status honoured, to fixpoint */
-  int fixpoint(ProblemPtr p, int *rounds, int64_t *nmods)
+  int fixpoint(ProblemPtr p, SolutionPool *spool, int *rounds, int64_t *nmods)
   {
     ModQ mods; bool ch = true; UInt ni = 0; int inf = 0; *rounds = 0;
+    double cut = 0;
     flagAll(p);
     while (ch && !inf) {
       ch = false; ++*rounds;
       if (varBndsFromCons_(p, false, &ch, &mods, &ni) == SolvedInfeasible) { inf = 1; break; }
+      if (cutoff(p, spool, &cut) && varBndsFromObj_(p, cut, false, &ch, &mods) == SolvedInfeasible) { inf = 1; break; }
       tightenInts_(p, false, &ch, &mods);
       if (checkBounds_(p) == SolvedInfeasible) inf = 1;
     }
@@ -68,9 +79,10 @@ public:
 
   /* same driver with the row loop of varBndsFromCons_ (LinearHandler.cpp:506-539,
    * apply_to_prob == false) unrolled here so the visited nnz can be counted */
-  int fixpointCounted(ProblemPtr p, int *rounds, int64_t *nmods, int64_t *nnz, int max_rounds)
+  int fixpointCounted(ProblemPtr p, SolutionPool *spool, int *rounds, int64_t *nmods, int64_t *nnz, int max_rounds)
   {
     ModQ mods; bool ch = true; UInt ni = 0; int inf = 0; *rounds = 0; *nnz = 0;
+    double cut = 0;
     flagAll(p);
     while (ch && !inf && (max_rounds <= 0 || *rounds < max_rounds)) {
       ch = false; ++*rounds;
@@ -83,6 +95,27 @@ public:
           *nnz += c->getLinearFunction()->getNumTerms();
           if (linBndTighten_(p, false, c, &t, &mods, &ni) == SolvedInfeasible) { inf = 1; break; }
           if (t) ch = true;
+        }
+      }
+      if (inf) break;
+      if (cutoff(p, spool, &cut)) {
+        /* the loop of varBndsFromObj_ (LinearHandler.cpp:565-593) spelled out with the reference's own
+         * pieces, so that the terms it visits can be counted */
+        ObjectivePtr o = p->getObjective();
+        LinearFunctionPtr lf = o->getLinearFunction();
+        if (lf && o->getFunctionType() == Linear) {
+          bool t = true; UInt unused = 0;
+          while (t && !inf) {
+            double ll, uu, sll = INFINITY, suu = INFINITY;
+            t = false;
+            getLfBnds_(lf, &ll, &uu);
+            if (ll < -1e20 || uu > 1e20) getSingLfBnds_(lf, &sll, &suu);
+            *nnz += lf->getNumTerms();
+            if (ll > cut + 1e-8) { inf = 1; break; }
+            if (ll > -1e20) updateLfBoundsFromUb_(p, false, lf, cut, ll, false, &t, &mods, &unused);
+            else if (sll > -1e20) updateLfBoundsFromUb_(p, false, lf, cut, sll, true, &t, &mods, &unused);
+            if (t) ch = true;
+          }
         }
       }
       if (inf) break;
@@ -108,6 +141,7 @@ struct RefProblem {
   ProblemPtr p = 0;
   LinProbe *lh = 0;
   NlPresHandler *nh = 0;
+  SolutionPool *spool = 0;       /* holds the incumbent when a cut-off is set */
   std::vector<VariablePtr> vars;
   std::vector<ConstraintPtr> lin_rows;
   std::vector<ConstraintPtr> nl_rows;
@@ -182,6 +216,28 @@ int32_t ref_add_nl(void *hv, int32_t n_nodes, const uint8_t *op, const int32_t *
   return (int32_t)h->nl_rows.size() - 1;
 }
 
+/* linear objective  min c.x + constant  (the cut-off row of LinearHandler::varBndsFromObj_) */
+void ref_set_objective(void *hv, int32_t k, const int32_t *col, const double *val, double constant)
+{
+  RefProblem *h = (RefProblem *)hv;
+  LinearFunctionPtr lf = (LinearFunctionPtr) new LinearFunction();
+  for (int32_t t = 0; t < k; ++t) lf->addTerm(h->vars[col[t]], val[t]);
+  FunctionPtr f = (FunctionPtr) new Function(lf);
+  h->p->newObjective(f, constant, Minimize);
+}
+
+/* an incumbent of objective value `value`; has_incumbent == 0 removes it */
+void ref_set_incumbent(void *hv, int32_t has_incumbent, double value)
+{
+  RefProblem *h = (RefProblem *)hv;
+  delete h->spool; h->spool = 0;
+  if (has_incumbent) {
+    std::vector<double> x(h->vars.size(), 0.0);
+    h->spool = new SolutionPool(h->env, h->p, 10);
+    h->spool->addSolution(x.empty() ? 0 : &x[0], value);
+  }
+}
+
 void ref_finish(void *hv)
 {
   RefProblem *h = (RefProblem *)hv;
@@ -205,14 +261,14 @@ void ref_get_box(void *hv, double *lb, double *ub)
 int32_t ref_lin_fixpoint(void *hv, int32_t *rounds, int64_t *nmods)
 {
   RefProblem *h = (RefProblem *)hv;
-  return h->lh->fixpoint(h->p, rounds, nmods);
+  return h->lh->fixpoint(h->p, h->spool, rounds, nmods);
 }
 
 int32_t ref_lin_fixpoint_counted(void *hv, int32_t max_rounds, int32_t *rounds, int64_t *nmods,
                                  int64_t *nnz)
 {
   RefProblem *h = (RefProblem *)hv;
-  return h->lh->fixpointCounted(h->p, rounds, nmods, nnz, max_rounds);
+  return h->lh->fixpointCounted(h->p, h->spool, rounds, nmods, nnz, max_rounds);
 }
 
 /* raw LinearHandler::simplePresolve (LinearHandler.cpp:1605-1653): what B&B pays per node */
@@ -220,7 +276,7 @@ int32_t ref_lin_simple_presolve(void *hv, int64_t *nmods)
 {
   RefProblem *h = (RefProblem *)hv;
   ModVector mods; SolveStatus st = Started;
-  h->lh->simplePresolve(h->p, (SolutionPoolPtr)0, mods, st);
+  h->lh->simplePresolve(h->p, (SolutionPoolPtr)h->spool, mods, st);
   *nmods = (int64_t)mods.size();
   freeMods(mods);
   return st == SolvedInfeasible ? 1 : 0;
@@ -300,7 +356,7 @@ double ref_time_boxes(void *hv, int32_t mode, int32_t n_boxes, const double *lbs
     ref_set_box(hv, lbs + (size_t)b * n, ubs + (size_t)b * n);
     int32_t rounds = 0, inf = 0; int64_t nmods = 0, nnz = 0;
     auto t0 = std::chrono::steady_clock::now();
-    if (mode == 0) inf = h->lh->fixpointCounted(h->p, &rounds, &nmods, &nnz, 0);
+    if (mode == 0) inf = h->lh->fixpointCounted(h->p, h->spool, &rounds, &nmods, &nnz, 0);
     else if (mode == 1) inf = ref_lin_simple_presolve(hv, &nmods);
     else inf = ref_node_presolve(hv, &nmods);
     auto t1 = std::chrono::steady_clock::now();
@@ -313,7 +369,7 @@ double ref_time_boxes(void *hv, int32_t mode, int32_t n_boxes, const double *lbs
 void ref_destroy(void *hv)
 {
   RefProblem *h = (RefProblem *)hv;
-  delete h->lh; delete h->nh;
+  delete h->lh; delete h->nh; delete h->spool;
   delete h->p;
   delete h->env;
   delete h;

@@ -22,7 +22,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from minotaur_b200.instances import (Expr, OpAbs, OpCeil, OpFloor, OpLog10, branch_boxes, build_tapes,  # noqa: E402
+from minotaur_b200.instances import (Expr, OpAbs, OpCeil, OpFloor, OpLog10, attach_cutoff, branch_boxes, build_tapes,  # noqa: E402
                                      make_knapsack_setcover, make_minlp, make_sparse_milp, LinearRows, INF)
 from oracle.pyoracle import Reference  # noqa: E402
 
@@ -45,6 +45,16 @@ def linear_cases():
     inst = make_knapsack_setcover(m=80, n=60, nnz_per_row=6, seed=15)
     names.append("knap")
     _emit_linear(out, "knap", inst, n_boxes=10, seed=15)
+    # objective cut-off row (LinearHandler::varBndsFromObj_): a linear objective plus an incumbent in the pool
+    for name, kw, k, slack in (("cut_int", dict(m=60, n=60, nnz_per_row=5, seed=16, real_data=False), 25, 30.0),
+                               ("cut_real", dict(m=70, n=60, nnz_per_row=6, seed=17, real_data=True), 40, 30.0)):
+        inst = make_sparse_milp(**kw)
+        ref = Reference(inst)
+        tl, tu, _ = ref.lin_fixpoint(inst.lb, inst.ub)
+        ref.close()
+        inst = attach_cutoff(inst, k, kw["seed"], slack, box=(tl, tu))
+        names.append(name)
+        _emit_linear(out, name, inst, n_boxes=10, seed=kw["seed"])
     out["names"] = np.array(names)
     return out
 
@@ -56,6 +66,9 @@ def _emit_linear(out, name, inst, n_boxes, seed):
     for k in ("row_ptr", "col", "val", "row_lb", "row_ub", "var_type"):
         out[f"{name}.{k}"] = getattr(inst, k)
     out[f"{name}.shape"] = np.array([inst.m, inst.n])
+    if inst.cut_col is not None:
+        out[f"{name}.cut_col"], out[f"{name}.cut_val"] = inst.cut_col, inst.cut_val
+        out[f"{name}.cut_rhs"] = np.array([inst.cut_rhs])
     out[f"{name}.lbs"], out[f"{name}.ubs"] = lbs, ubs
     raw_lb, raw_ub, raw_v, raw_nm = [], [], [], []
     fix_lb, fix_ub, fix_v, fix_r, fix_nnz = [], [], [], [], []

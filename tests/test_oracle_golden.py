@@ -12,9 +12,13 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def load_linear(z, name):
     m, n = z[f"{name}.shape"]
-    return LinearRows(m=int(m), n=int(n), row_ptr=z[f"{name}.row_ptr"], col=z[f"{name}.col"], val=z[f"{name}.val"],
+    inst = LinearRows(m=int(m), n=int(n), row_ptr=z[f"{name}.row_ptr"], col=z[f"{name}.col"], val=z[f"{name}.val"],
                       row_lb=z[f"{name}.row_lb"], row_ub=z[f"{name}.row_ub"], var_type=z[f"{name}.var_type"],
                       lb=z[f"{name}.lbs"][0], ub=z[f"{name}.ubs"][0], name=name)
+    if f"{name}.cut_col" in z.files:       # objective cut-off row  c.x <= cut_rhs
+        inst.cut_col, inst.cut_val = z[f"{name}.cut_col"], z[f"{name}.cut_val"]
+        inst.cut_rhs = float(z[f"{name}.cut_rhs"][0])
+    return inst
 
 
 def load_tapes(z, prefix):

@@ -3,7 +3,7 @@ instances.  Skipped where the reference library was not built (it needs /root/re
 import numpy as np
 import pytest
 
-from minotaur_b200.instances import branch_boxes, make_knapsack_setcover, make_minlp, make_sparse_milp
+from minotaur_b200.instances import attach_cutoff, branch_boxes, make_knapsack_setcover, make_minlp, make_sparse_milp
 from helpers import assert_box_parity
 
 
@@ -40,6 +40,40 @@ def test_linear_inplace_bitwise(oracle, Reference, seed, real, inf):
         else:
             assert oracle.lin_fixpoint_jacobi(inst, lbs[b], ubs[b])[2]["verdict"] != 0
     ref.close()
+
+
+@pytest.mark.parametrize("seed,real,inf,k,slack", [(10, False, (0, 0, 0), 40, 20.0), (11, True, (0, 0, 0), 90, 30.0),
+                                                   (12, True, (0.1, 0.05, 0.02), 60, 20.0), (13, False, (0, 0, 0), 220, 30.0)])
+def test_linear_cutoff_row_bitwise(oracle, Reference, seed, real, inf, k, slack):
+    """Objective cut-off row (LinearHandler::varBndsFromObj_, :544-597): the reference meets it as a linear objective
+    plus an incumbent in the solution pool; raw simplePresolve and the status-honouring fixpoint, bit for bit."""
+    inst = make_sparse_milp(250, 220, 6, seed=seed, real_data=real, inf_frac=inf)
+    tl, tu, _ = oracle.lin_fixpoint_inplace(inst, inst.lb, inst.ub)
+    inst = attach_cutoff(inst, k, seed, slack, box=(tl, tu))
+    ref = Reference(inst)
+    lbs, ubs = branch_boxes(inst.lb, inst.ub, inst.var_type, 16, seed=seed, max_depth=8)
+    lbs[0], ubs[0] = inst.lb, inst.ub
+    n_feas = moved = 0
+    for b in range(lbs.shape[0]):
+        rl, ru, rr = ref.lin_simple_presolve(lbs[b], ubs[b])
+        ol, ou, orr = oracle.lin_simple_presolve(inst, lbs[b], ubs[b])
+        assert rr["verdict"] == orr["verdict"] and rr["n_mods"] == orr["n_mods"], b
+        assert np.array_equal(rl, ol) and np.array_equal(ru, ou), b
+        rl, ru, rr = ref.lin_fixpoint(lbs[b], ubs[b], counted=True)
+        ul, uu, ur = ref.lin_fixpoint(lbs[b], ubs[b], counted=False)         # the reference's own varBndsFromObj_
+        ol, ou, orr = oracle.lin_fixpoint_inplace(inst, lbs[b], ubs[b])
+        assert rr["verdict"] == ur["verdict"] == orr["verdict"] and rr["rounds"] == ur["rounds"] == orr["rounds"], b
+        assert rr["nnz_updates"] == orr["nnz_updates"], b
+        if rr["verdict"] == 0:
+            n_feas += 1
+            assert np.array_equal(rl, ol) and np.array_equal(ru, ou) and np.array_equal(ul, ol) and np.array_equal(uu, ou), b
+            # what the row did: the same box without an incumbent
+            ref.set_incumbent(None)
+            nl, nu, nr = ref.lin_fixpoint(lbs[b], ubs[b])
+            ref.set_incumbent(inst.cut_rhs)
+            moved += int(np.sum(rl > nl) + np.sum(ru < nu))
+    ref.close()
+    assert n_feas > 0 and moved > 0, "the cut-off row never moved a bound: vacuous"
 
 
 def test_knapsack_setcover_bitwise(oracle, Reference):
