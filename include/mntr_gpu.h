@@ -159,6 +159,14 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
 int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *col, const double *val,
                         double rhs);
 
+/* The incumbent's objective value as NlPresHandler::fixObjBins_ compares it: the RAW pool value -- that rule
+ * does not subtract the objective constant (NlPresHandler.cpp:1030,1045-1050).  The objective's linear function
+ * is the cut-off row's (col,val), so this only has an effect after mntr_gpu_set_cutoff with k > 0, in the
+ * reference-order kernel with CGraph tapes loaded and the nonlinear handler enabled; +inf (the state after
+ * mntr_gpu_set_cutoff) switches the rule off.  Nonlinear objectives are not supported.
+ * Replaces: NlPresHandler::fixObjBins_ (NlPresHandler.cpp:1062-1121). */
+int mntr_gpu_set_incumbent(mntr_gpu_ctx *ctx, double best_value);
+
 /* ---- the hot path ------------------------------------------------------------------ */
 
 /* Tightens n_boxes independent node boxes.  lb/ub are box-major [n_boxes][n] host arrays,

@@ -29,6 +29,7 @@ struct LinDev {
   const double  *cut_val;
   const double2 *cut_bnd;   // [1] {-inf, rhs}
   double cut_rhs;
+  double obj_ub;            // raw incumbent value for NlPresHandler::fixObjBins_ (+inf: none)
 };
 
 // rows are padded to a multiple of kRowPad entries (padding: val == 0, a valid column)

@@ -469,9 +469,40 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
 // at most two sweeps of { chkRed_ over all CGraph constraints ; varBndsFromCons_ in constraint index
 // order, in place }.  The in-place order is reproduced by wavefront levels over the constraints
 // (built at load time from the variables each constraint reads and writes).
+// NlPresHandler::fixObjBins_ (NlPresHandler.cpp:1062-1121) for a LINEAR objective, for this lane's box: with olb the
+// objective's lower bound over the box (LinearFunction::computeBounds, taken once), a binary with coefficient a0
+// is fixed to 0 if a0>0 && olb+a0>ub, to 1 if a0<0 && olb-a0>ub; ub is the RAW incumbent value.  One warp per tile.
 template <class R>
-__device__ __forceinline__ int nl_tile_presolve(const NlDev &N, double2 *bx, int64_t ld, TileShared &sh, bool active,
-                                                bool &any_change)
+__device__ __noinline__ void fix_obj_bins(const LinDev &P, double2 *bx, int64_t ld, bool run, TileShared &sh, int lane)
+{
+  const bool mine = run && sh.verdict[lane] == 0;
+  if (!__any_sync(kFull, mine)) return;
+  const double best = P.obj_ub;
+  double olb = 0.0;
+  for (int t = 0; t < P.cut_cnt; ++t) {
+    const double a = __ldg(P.cut_val + t);
+    const double2 b = bx[(int64_t)__ldg(P.cut_col + t) * ld];
+    olb = R::add_lo(olb, R::mul_lo(a, a > 0.0 ? b.x : b.y));
+  }
+  if (!mine || olb <= -INFINITY) return;
+  if (olb > best) { sh.verdict[lane] = 1; /* MNTR_INFEAS_BOUNDS */ return; }
+  for (int t = 0; t < P.cut_cnt; ++t) {
+    const int j = __ldg(P.cut_col + t);
+    const uint8_t ty = __ldg(P.var_type + j);
+    if (ty != 0 && ty != 2) continue;                    // Binary, ImplBin
+    double2 *pb = bx + (int64_t)j * ld;
+    const double2 b = *pb;
+    if (!((b.y - b.x) > 1e-6)) continue;                 // NlPresHandler::eTol_
+    const double a0 = __ldg(P.cut_val + t);
+    // (olb + a0 > best) must hold in exact arithmetic for the fix to be valid: round the sum down
+    if (a0 > 0.0 && R::add_lo(olb, a0) > best) { pb->y = 0.0; sh.changed[lane] = 1; }
+    else if (a0 < 0.0 && R::add_lo(olb, -a0) > best) { pb->x = 1.0; sh.changed[lane] = 1; }
+  }
+}
+
+template <class R>
+__device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N, double2 *bx, int64_t ld, TileShared &sh,
+                                                bool active, bool &any_change)
 {
   const int lane = threadIdx.x & 31;
   const TileTeam team = make_team();
@@ -508,6 +539,11 @@ __device__ __forceinline__ int nl_tile_presolve(const NlDev &N, double2 *bx, int
           else if (n_mods > 0) sh.changed[lane] = 1;
         }
       }
+      team.sync();
+    }
+    // fixObjBins_: only with an incumbent and a linear objective (:1045-1050)
+    if (P.cut_cnt > 0 && P.obj_ub < INFINITY) {
+      if (warp == 0) fix_obj_bins<R>(P, bx, ld, run, sh, lane);
       team.sync();
     }
     if (run && sh.changed[lane]) any_change = true;
@@ -556,7 +592,7 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
     if (lin_enabled)
       my_rounds += lin_tile_presolve<R>(P, bx, ld, st, flags, varflag, sh, active, loop_mode, max_rounds, bad_row,
                                         my_nnz, lin_changed);
-    if (nl_enabled) my_rounds += nl_tile_presolve<R>(N, bx, ld, sh, active, nl_changed);
+    if (nl_enabled) my_rounds += nl_tile_presolve<R>(P, N, bx, ld, sh, active, nl_changed);
     // fixpoint mode with both handlers: go round again while the nonlinear sweeps still move bounds
     const bool again = (loop_mode == 0) && lin_enabled && nl_enabled && nl_changed && sh.verdict[lane] == 0 &&
                        (max_rounds <= 0 || my_rounds < max_rounds) && outer < 50;

@@ -385,6 +385,7 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   // ---- upload ----
   LinDev &L = ctx->lin;
   L = LinDev{};
+  L.cut_rhs = INFINITY; L.obj_ub = INFINITY;
   L.m = m; L.n = n; L.n_levels = n_levels;
   int rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pinfo.data(), (size_t)m, &L.row_info))) return rc;
@@ -558,7 +559,7 @@ int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *col, const 
   CU(cudaSetDevice(ctx->device));
   free_all(ctx->cut_allocs);
   ctx->lin.cut_cnt = 0; ctx->lin.cut_col = nullptr; ctx->lin.cut_colx = nullptr; ctx->lin.cut_val = nullptr;
-  ctx->lin.cut_bnd = nullptr; ctx->lin.cut_rhs = INFINITY;
+  ctx->lin.cut_bnd = nullptr; ctx->lin.cut_rhs = INFINITY; ctx->lin.obj_ub = INFINITY;
   if (k <= 0) return MNTR_OK;
   if (!col || !val) return fail(ctx, MNTR_E_ARG, "set_cutoff: null argument");
   std::vector<int32_t> c; std::vector<double> v;
@@ -584,6 +585,15 @@ int mntr_gpu_set_cutoff(mntr_gpu_ctx *ctx, int32_t k, const int32_t *col, const 
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->lin.cut_rhs = rhs;
   ctx->lin.cut_cnt = cnt;
+  return MNTR_OK;
+}
+
+int mntr_gpu_set_incumbent(mntr_gpu_ctx *ctx, double best_value)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "set_incumbent: call load_linear first");
+  if (best_value != best_value) return fail(ctx, MNTR_E_ARG, "set_incumbent: NaN");
+  ctx->lin.obj_ub = best_value;
   return MNTR_OK;
 }
 

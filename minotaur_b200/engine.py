@@ -38,6 +38,7 @@ _bp = C.POINTER(C.c_uint8)
 ABI_SYMBOLS = [
     "mntr_gpu_create", "mntr_gpu_destroy", "mntr_gpu_last_error", "mntr_gpu_abi_version",
     "mntr_gpu_device_count", "mntr_gpu_load_linear", "mntr_gpu_load_cgraph", "mntr_gpu_set_cutoff",
+    "mntr_gpu_set_incumbent",
     "mntr_gpu_tighten", "mntr_gpu_tighten_nodes", "mntr_gpu_box_ld", "mntr_gpu_tighten_dev",
     "mntr_gpu_boxes_upload", "mntr_gpu_boxes_download", "mntr_gpu_get_stats",
     "mntr_gpu_tighten_single_dev", "mntr_gpu_stream",
@@ -82,6 +83,7 @@ def load_library() -> C.CDLL:
     L.mntr_gpu_load_linear.argtypes = [vp, C.c_int32, C.c_int32, _ip, _ip, _dp, _dp, _dp, _bp, _bp]
     L.mntr_gpu_load_cgraph.argtypes = [vp, C.c_int32, _ip, _bp, _ip, _ip, _dp, _ip, _ip, _ip, _dp, _dp, _dp]
     L.mntr_gpu_set_cutoff.argtypes = [vp, C.c_int32, _ip, _dp, C.c_double]
+    L.mntr_gpu_set_incumbent.argtypes = [vp, C.c_double]
     L.mntr_gpu_tighten.argtypes = [vp, C.c_int32, _dp, _dp, C.POINTER(GpuOptions), _ip, _ip, _lp]
     L.mntr_gpu_tighten_nodes.argtypes = [vp, C.c_int32, _dp, _dp, _lp, _ip, _bp, _dp, C.POINTER(GpuOptions),
                                          _ip, _ip, _lp, _ip, _bp, _dp, C.c_int64, _lp]
@@ -168,6 +170,7 @@ class GpuBoundEngine:
         self.n, self.m, self.nnz = inst.n, inst.m, inst.nnz
         if inst.cut_col is not None and len(inst.cut_col):
             self.set_cutoff(inst.cut_col, inst.cut_val, inst.cut_rhs)
+            self.set_incumbent(inst.cut_rhs + getattr(inst, "obj_const", 0.0))
 
     def load_cgraph(self, t: Tapes):
         a = {k: np.ascontiguousarray(getattr(t, k), ty) for k, ty in (
@@ -182,6 +185,10 @@ class GpuBoundEngine:
     def set_cutoff(self, col, val, rhs: float):
         col = np.ascontiguousarray(col, np.int32); val = np.ascontiguousarray(val, np.float64)
         self._check(self.L.mntr_gpu_set_cutoff(self.h, len(col), _i(col), _d(val), float(rhs)), "set_cutoff")
+
+    def set_incumbent(self, best_value: float):
+        """Raw incumbent value for NlPresHandler::fixObjBins_ (needs a cut-off row; inf switches the rule off)."""
+        self._check(self.L.mntr_gpu_set_incumbent(self.h, float(best_value)), "set_incumbent")
 
     # -- the hot path --
     def tighten(self, lb, ub, rounding=ROUND_DIRECTED, order=ORDER_AUTO, loop=LOOP_FIXPOINT, max_rounds=0,

@@ -219,6 +219,9 @@ void GpuBoundHandler::setCutoff_(ProblemPtr p, SolutionPoolPtr spool)
   if (mntr_gpu_set_cutoff(ctx_, (int)col.size(), col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0], rhs) != MNTR_OK)
     throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
   cutoffOn_ = !col.empty();
+  // NlPresHandler::fixObjBins_ compares against the raw pool value (NlPresHandler.cpp:1030)
+  if (mntr_gpu_set_incumbent(ctx_, spool->getBestSolutionValue()) != MNTR_OK)
+    throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
 }
 
 bool GpuBoundHandler::tighten_(ProblemPtr p, SolutionPoolPtr spool, ModVector &mods, bool truncated)

@@ -41,7 +41,7 @@ static ProblemPtr makeProblem(EnvPtr env, int n, int m, int k, int n_nl, std::ve
   for (int j = 0; j < n; ++j) {
     const bool isint = urand() < 0.5;
     const double ub = irand(1, 10);
-    v[j] = p->newVariable(0.0, ub, isint ? Integer : Continuous);
+    v[j] = p->newVariable(0.0, ub, isint ? (ub == 1.0 ? Binary : Integer) : Continuous);
     xstar[j] = isint ? std::floor(urand() * (ub + 1)) : std::floor(urand() * ub * 4) / 4;
     if (xstar[j] > ub) xstar[j] = ub;
   }
@@ -89,7 +89,7 @@ static void branch(ProblemPtr p, int depth)
 {
   for (int d = 0; d < depth; ++d) {
     VariablePtr v = p->getVariable(irand(0, p->getNumVars() - 1));
-    if (v->getType() != Integer || v->getUb() - v->getLb() < 1) continue;
+    if ((v->getType() != Integer && v->getType() != Binary) || v->getUb() - v->getLb() < 1) continue;
     const double x = v->getLb() + (v->getUb() - v->getLb()) * urand();
     if (urand() < 0.5) p->changeBound(v, Upper, std::floor(x)); else p->changeBound(v, Lower, std::ceil(x + 1e-9));
   }
@@ -121,10 +121,10 @@ int main()
       std::vector<double> lb0(n), ub0(n);
       for (int j = 0; j < n; ++j) { lb0[j] = relB->getVariable(j)->getLb(); ub0[j] = relB->getVariable(j)->getUb(); }
 
-      // every other box of the purely linear trials has an incumbent: the objective becomes the cut-off row
-      // (the nonlinear handler's own incumbent rule, fixObjBins_, is not built: DESIGN.md section 2)
+      // every other box has an incumbent: the objective becomes the cut-off row of LinearHandler::varBndsFromObj_
+      // and NlPresHandler::fixObjBins_ fixes binaries of the objective
       SolutionPool *spool = 0;
-      if (n_nl == 0 && (box & 1)) {
+      if (box & 1) {
         std::vector<double> x(n, 0.0);
         spool = new SolutionPool(env, p, 10);
         spool->addSolution(&x[0], 2.5 + irand(15, 45));
@@ -136,7 +136,7 @@ int main()
       NlPresHandler nh(env, p);
       ModVector pm, rmA;
       bool infA = lh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)spool, pm, rmA);
-      if (!infA && n_nl) infA = nh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pm, rmA);
+      if (!infA && n_nl) infA = nh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)spool, pm, rmA);
 
       // GPU handler in reference-order, round-to-nearest mode: must reproduce it bit for bit
       GpuBoundHandler gh(env, p, 0);

@@ -44,6 +44,7 @@ class LinearRows:
     cut_col: Optional[np.ndarray] = None      # objective cut-off row  c.x <= cut_rhs
     cut_val: Optional[np.ndarray] = None
     cut_rhs: float = INF
+    obj_const: float = 0.0                    # objective constant: the incumbent's value is cut_rhs + obj_const
     name: str = ""
     xstar: Optional[np.ndarray] = None        # planted feasible point of the generators
 
@@ -363,6 +364,33 @@ def attach_cutoff(inst: LinearRows, k: int, seed: int, slack: float, box=None) -
     vals = rng.uniform(0.5, 3.0, len(cols)) * rng.choice([-1.0, 1.0], len(cols))
     lo = float(np.sum(np.where(vals > 0, vals * blb[cols], vals * bub[cols])))
     inst.cut_col, inst.cut_val, inst.cut_rhs = cols, vals, lo + slack
+    return inst
+
+
+def attach_binary_objective(inst: LinearRows, n_bin: int, n_other: int, seed: int, slack: float,
+                            const: float = 0.0, coef_hi: int = 9) -> LinearRows:
+    """Turns ``n_bin`` integer variables whose planted value is 0 or 1 into binaries and gives ``inst`` a linear
+    objective over them and ``n_other`` further variables (coefficient +-1), with an incumbent ``slack`` above the
+    planted point's objective value.  A binary's coefficient is positive where the planted value is 0 and negative
+    where it is 1, so the planted point sits at the binaries' minimum: the setting in which
+    NlPresHandler::fixObjBins_ (/root/reference/src/base/NlPresHandler.cpp:1062-1121) fixes the binaries whose
+    coefficient alone exceeds the remaining slack, while LinearHandler's cut-off row keeps the planted point.
+    ``const`` is the objective's constant term."""
+    rng = np.random.default_rng(seed)
+    elig = np.nonzero((inst.var_type == INTEGER) & ((inst.xstar == 0) | (inst.xstar == 1)) & (inst.lb <= 0) & (inst.ub >= 1))[0]
+    bins = rng.choice(elig, min(n_bin, len(elig)), replace=False)
+    rest = np.setdiff1d(np.arange(inst.n), bins)
+    others = rng.choice(rest, n_other, replace=False)
+    inst.var_type = inst.var_type.copy(); inst.lb = inst.lb.copy(); inst.ub = inst.ub.copy()
+    inst.var_type[bins] = BINARY
+    inst.lb[bins], inst.ub[bins] = 0.0, 1.0
+    coef = np.zeros(inst.n)
+    coef[bins] = rng.integers(1, coef_hi, len(bins)) * np.where(inst.xstar[bins] == 0, 1.0, -1.0)
+    coef[others] = rng.choice([-1.0, 1.0], len(others))
+    cols = np.sort(np.concatenate([bins, others])).astype(np.int32)
+    vals = coef[cols]
+    inst.cut_col, inst.cut_val = cols, vals
+    inst.cut_rhs, inst.obj_const = float(vals @ inst.xstar[cols]) + slack, float(const)
     return inst
 
 

@@ -788,8 +788,34 @@ int32_t orc_nl_sweep(const orc_nl_t *g, double *lb, double *ub, int64_t *n_mods)
   return ORC_OK;
 }
 
-/* ref: NlPresHandler.cpp:1022-1059 simplePresolve without incumbent */
-void orc_nl_simple_presolve(const orc_nl_t *g, double *lb, double *ub, orc_result_t *res)
+/* ref: NlPresHandler.cpp:1062-1121 fixObjBins_ for a LINEAR objective (obj = the cut-off row's coefficients):
+ * with olb the objective's lower bound over the box (LinearFunction::computeBounds, LinearFunction.cpp:178-195,
+ * taken ONCE), a binary z with coefficient a0 is fixed to 0 if a0>0 && olb+a0>ub, to 1 if a0<0 && olb-a0>ub. */
+int32_t orc_nl_fix_obj_bins(const orc_lin_t *obj, double *lb, double *ub, int64_t *n_mods)
+{
+  if (!obj || obj->cut_k <= 0 || !(obj->obj_ub < INFINITY)) return ORC_OK;
+  const double best = obj->obj_ub;
+  double olb = 0.0;
+  for (int32_t t = 0; t < obj->cut_k; ++t) {
+    double a = obj->cut_val[t];
+    olb += (a > 0) ? a * lb[obj->cut_col[t]] : a * ub[obj->cut_col[t]];
+  }
+  if (olb <= -INFINITY) return ORC_OK;
+  if (olb > best) return ORC_INFEASIBLE;
+  for (int32_t t = 0; t < obj->cut_k; ++t) {
+    int32_t j = obj->cut_col[t];
+    uint8_t ty = obj->var_type[j];
+    if ((ty == 0 /* Binary */ || ty == 2 /* ImplBin */) && (ub[j] - lb[j]) > 1e-6) {
+      double a0 = obj->cut_val[t];
+      if (a0 > 0 && olb + a0 > best) { ub[j] = 0.0; ++*n_mods; }
+      else if (a0 < 0 && olb - a0 > best) { lb[j] = 1.0; ++*n_mods; }
+    }
+  }
+  return ORC_OK;
+}
+
+/* ref: NlPresHandler.cpp:1022-1059 simplePresolve; obj (may be NULL) carries the objective and the incumbent */
+void orc_nl_simple_presolve_obj(const orc_nl_t *g, const orc_lin_t *obj, double *lb, double *ub, orc_result_t *res)
 {
   int changed = 1; uint32_t iters = 1; const uint32_t max_iters = 4, min_iters = 2;
   int32_t verdict = ORC_OK, rounds = 0; int64_t n_mods = 0;
@@ -802,8 +828,17 @@ void orc_nl_simple_presolve(const orc_nl_t *g, double *lb, double *ub, orc_resul
     n_mods += nm; if (nm > 0) changed = 1;
     if (st == ORC_INFEASIBLE) { verdict = ORC_INFEASIBLE; break; }
     /* SolveError: the sweep stopped early; the loop condition only tests Infeasible */
+    nm = 0;
+    st = orc_nl_fix_obj_bins(obj, lb, ub, &nm);      /* :1045-1050, only with an incumbent */
+    n_mods += nm; if (nm > 0) changed = 1;
+    if (st == ORC_INFEASIBLE) { verdict = ORC_INFEASIBLE; break; }
   }
   res->verdict = verdict; res->rounds = rounds; res->n_mods = n_mods; res->nnz_updates = 0;
+}
+
+void orc_nl_simple_presolve(const orc_nl_t *g, double *lb, double *ub, orc_result_t *res)
+{
+  orc_nl_simple_presolve_obj(g, NULL, lb, ub, res);
 }
 
 /* ref: PCBProcessor.cpp:134-175 presolveNode_: handlers in order, stop at first infeasible */
@@ -812,7 +847,7 @@ void orc_node_presolve(const orc_lin_t *p, const orc_nl_t *g, double *lb, double
 {
   orc_result_t a = {0, 0, 0, 0}, b = {0, 0, 0, 0};
   if (p) orc_lin_simple_presolve(p, lb, ub, &a);
-  if (a.verdict == ORC_OK && g) orc_nl_simple_presolve(g, lb, ub, &b);
+  if (a.verdict == ORC_OK && g) orc_nl_simple_presolve_obj(g, p, lb, ub, &b);
   res->verdict = (a.verdict != ORC_OK) ? a.verdict : b.verdict;
   res->rounds = a.rounds + b.rounds;
   res->nnz_updates = a.nnz_updates; res->n_mods = a.n_mods + b.n_mods;

@@ -32,7 +32,8 @@ def _b(a): return a.ctypes.data_as(_bp)
 class OrcLin(C.Structure):
     _fields_ = [("m", C.c_int32), ("n", C.c_int32), ("row_ptr", _ip), ("col", _ip), ("val", _dp),
                 ("row_lb", _dp), ("row_ub", _dp), ("var_type", _bp), ("row_active", _bp),
-                ("cut_k", C.c_int32), ("cut_col", _ip), ("cut_val", _dp), ("cut_rhs", C.c_double)]
+                ("cut_k", C.c_int32), ("cut_col", _ip), ("cut_val", _dp), ("cut_rhs", C.c_double),
+                ("obj_ub", C.c_double)]
 
 
 class OrcNl(C.Structure):
@@ -71,7 +72,9 @@ def _lin_struct(inst, keep):
     if inst.row_active is not None:
         keep["row_active"] = np.ascontiguousarray(inst.row_active, np.uint8)
         s.row_active = _b(keep["row_active"])
+    s.obj_ub = float("inf")
     if inst.cut_col is not None and len(inst.cut_col):
+        s.obj_ub = inst.cut_rhs + getattr(inst, "obj_const", 0.0)      # the raw incumbent value (fixObjBins_)
         keep["cut_col"] = np.ascontiguousarray(inst.cut_col, np.int32)
         keep["cut_val"] = np.ascontiguousarray(inst.cut_val, np.float64)
         s.cut_k, s.cut_col, s.cut_val, s.cut_rhs = len(keep["cut_col"]), _i(keep["cut_col"]), _d(keep["cut_val"]), inst.cut_rhs
@@ -110,6 +113,7 @@ class Oracle:
         L.orc_nl_var_bound_mods.argtypes = [C.POINTER(OrcNl), C.c_int32, C.c_double, C.c_double, _dp, _dp, _ip]
         L.orc_nl_var_bound_mods.restype = C.c_int32
         L.orc_nl_simple_presolve.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(OrcResult)]
+        L.orc_nl_simple_presolve_obj.argtypes = [C.POINTER(OrcNl), C.POINTER(OrcLin), _dp, _dp, C.POINTER(OrcResult)]
         L.orc_nl_chk_red.argtypes = [C.POINTER(OrcNl), _dp, _dp]
         L.orc_nl_chk_red.restype = C.c_int32
         L.orc_nl_sweep.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(C.c_int64)]
@@ -182,11 +186,16 @@ class Oracle:
         st = self.lib.orc_nl_var_bound_mods(C.byref(s), c, lb_in, ub_in, _d(lb), _d(ub), _i(nm))
         return lb, ub, st, int(nm[0])
 
-    def nl_simple_presolve(self, tapes, lb, ub):
+    def nl_simple_presolve(self, tapes, lb, ub, obj=None):
+        """obj: a LinearRows whose cut-off row is the (linear) objective, with an incumbent -> fixObjBins_ runs."""
         keep = {}; s = _nl_struct(tapes, keep)
         lb = np.array(lb, np.float64, copy=True); ub = np.array(ub, np.float64, copy=True)
         r = OrcResult()
-        self.lib.orc_nl_simple_presolve(C.byref(s), _d(lb), _d(ub), C.byref(r))
+        if obj is not None:
+            o = _lin_struct(obj, keep)
+            self.lib.orc_nl_simple_presolve_obj(C.byref(s), C.byref(o), _d(lb), _d(ub), C.byref(r))
+        else:
+            self.lib.orc_nl_simple_presolve(C.byref(s), _d(lb), _d(ub), C.byref(r))
         return lb, ub, dict(verdict=r.verdict, rounds=r.rounds, n_mods=r.n_mods)
 
     def node_presolve(self, inst, tapes, lb, ub):
@@ -263,11 +272,12 @@ class Reference:
                 L.ref_add_nl(self.h, e - b, _b(op), _i(a0), _i(a1), _d(cn), _i(tapes.child), lend - lbeg,
                              _i(lc), _d(lv), float(tapes.c_lb[c]), float(tapes.c_ub[c]))
         if inst.cut_col is not None and len(inst.cut_col):
-            # the cut-off row c.x <= cut_rhs as the reference meets it: a linear objective (constant 0) and an
-            # incumbent of value cut_rhs in the solution pool (LinearHandler.cpp:1636-1640)
+            # the cut-off row c.x <= cut_rhs as the reference meets it: a linear objective c.x + obj_const and an
+            # incumbent of value cut_rhs + obj_const in the solution pool (LinearHandler.cpp:1636-1640)
             cc = np.ascontiguousarray(inst.cut_col, np.int32); cv = np.ascontiguousarray(inst.cut_val, np.float64)
-            L.ref_set_objective(self.h, len(cc), _i(cc), _d(cv), 0.0)
-            L.ref_set_incumbent(self.h, 1, float(inst.cut_rhs))
+            const = float(getattr(inst, "obj_const", 0.0))
+            L.ref_set_objective(self.h, len(cc), _i(cc), _d(cv), const)
+            L.ref_set_incumbent(self.h, 1, float(inst.cut_rhs) + const)
         L.ref_finish(self.h)
 
     def set_incumbent(self, value=None):

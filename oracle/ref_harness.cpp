@@ -287,7 +287,7 @@ int32_t ref_nl_simple_presolve(void *hv, int64_t *nmods)
 {
   RefProblem *h = (RefProblem *)hv;
   ModVector mods; SolveStatus st = Started;
-  h->nh->simplePresolve(h->p, (SolutionPoolPtr)0, mods, st);
+  h->nh->simplePresolve(h->p, (SolutionPoolPtr)h->spool, mods, st);
   *nmods = (int64_t)mods.size();
   freeMods(mods);
   return st == SolvedInfeasible ? 1 : (st == SolveError ? 2 : 0);

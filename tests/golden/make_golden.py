@@ -22,7 +22,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from minotaur_b200.instances import (Expr, OpAbs, OpCeil, OpFloor, OpLog10, attach_cutoff, branch_boxes, build_tapes,  # noqa: E402
+from minotaur_b200.instances import (Expr, OpAbs, OpCeil, OpFloor, OpLog10, attach_binary_objective, attach_cutoff,  # noqa: E402
+                                     branch_boxes, build_tapes,
                                      make_knapsack_setcover, make_minlp, make_sparse_milp, LinearRows, INF)
 from oracle.pyoracle import Reference  # noqa: E402
 
@@ -183,6 +184,32 @@ def nl_cases():
         ref.close()
     out["minlp.nl_lb"], out["minlp.nl_ub"], out["minlp.nl_verdict"] = np.array(nl_l), np.array(nl_u), np.array(nl_v, np.int32)
     out["minlp.node_lb"], out["minlp.node_ub"], out["minlp.node_verdict"] = np.array(nd_l), np.array(nd_u), np.array(nd_v, np.int32)
+
+    # the same two runs with a linear objective over binaries and an incumbent: LinearHandler adds the cut-off row
+    # (varBndsFromObj_), NlPresHandler adds fixObjBins_ (which compares against the raw incumbent value)
+    lin, tp = make_minlp(n=300, n_cons=200, m_lin=60, seed=35)
+    lin = attach_binary_objective(lin, n_bin=14, n_other=2, seed=35, slack=3.0, const=2.25, coef_hi=40)
+    for k in ("row_ptr", "col", "val", "row_lb", "row_ub", "var_type", "cut_col", "cut_val"):
+        out[f"minlp_obj.{k}"] = getattr(lin, k)
+    out["minlp_obj.shape"] = np.array([lin.m, lin.n])
+    out["minlp_obj.cut_rhs_const"] = np.array([lin.cut_rhs, lin.obj_const])
+    for k in ("tape_ptr", "op", "arg0", "arg1", "cnst", "child", "lin_ptr", "lin_col", "lin_val", "c_lb", "c_ub"):
+        out[f"minlp_obj.t.{k}"] = getattr(tp, k)
+    lbs, ubs = branch_boxes(lin.lb, lin.ub, lin.var_type, 10, seed=35, max_depth=5, continuous_too=True)
+    lbs[0], ubs[0] = lin.lb, lin.ub
+    out["minlp_obj.lbs"], out["minlp_obj.ubs"] = lbs, ubs
+    nl_l, nl_u, nl_v, nd_l, nd_u, nd_v = [], [], [], [], [], []
+    for b in range(lbs.shape[0]):
+        ref = Reference(lin, tp)
+        l, u, r = ref.nl_simple_presolve(lbs[b], ubs[b])
+        nl_l.append(l); nl_u.append(u); nl_v.append(r["verdict"])
+        ref.close()
+        ref = Reference(lin, tp)
+        l, u, r = ref.node_presolve(lbs[b], ubs[b])
+        nd_l.append(l); nd_u.append(u); nd_v.append(r["verdict"])
+        ref.close()
+    out["minlp_obj.nl_lb"], out["minlp_obj.nl_ub"], out["minlp_obj.nl_verdict"] = np.array(nl_l), np.array(nl_u), np.array(nl_v, np.int32)
+    out["minlp_obj.node_lb"], out["minlp_obj.node_ub"], out["minlp_obj.node_verdict"] = np.array(nd_l), np.array(nd_u), np.array(nd_v, np.int32)
     return out
 
 

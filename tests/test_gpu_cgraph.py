@@ -14,7 +14,7 @@ from helpers import assert_box_parity, never_tighter, rel_diff
 from minotaur_b200 import engine as E
 from minotaur_b200.instances import (CONTINUOUS, Expr, INTEGER, LinearRows, OpExp, OpLog, OpLog10, OpPowK,
                                      branch_boxes, build_tapes, make_minlp)
-from test_oracle_golden import GOLD, load_tapes
+from test_oracle_golden import GOLD, load_minlp, load_tapes
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 LIBM_OPS = {OpExp, OpLog, OpLog10, OpPowK}
@@ -70,16 +70,14 @@ def test_every_opcode_single_constraint(engine, oracle):
     assert changed > 30
 
 
-def test_golden_minlp_bitwise(engine):
+@pytest.mark.parametrize("name", ["minlp", "minlp_obj"])
+def test_golden_minlp_bitwise(engine, name):
     """tests/golden/nl_cases.npz 'minlp.*': outputs of the reference's NlPresHandler::simplePresolve and of
-    LinearHandler + NlPresHandler (one PCBProcessor::presolveNode_ pass)."""
+    LinearHandler + NlPresHandler (one PCBProcessor::presolveNode_ pass).  'minlp_obj.*': the same with a linear
+    objective over binaries and an incumbent (varBndsFromObj_ cut-off row + fixObjBins_)."""
     z = np.load(os.path.join(GOLD, "nl_cases.npz"))
-    m, n = z["minlp.shape"]
-    lin = LinearRows(m=int(m), n=int(n), row_ptr=z["minlp.row_ptr"], col=z["minlp.col"], val=z["minlp.val"],
-                     row_lb=z["minlp.row_lb"], row_ub=z["minlp.row_ub"], var_type=z["minlp.var_type"],
-                     lb=z["minlp.lbs"][0], ub=z["minlp.ubs"][0])
-    t = load_tapes(z, "minlp.t")
-    lbs, ubs = z["minlp.lbs"], z["minlp.ubs"]
+    lin, t = load_minlp(z, name)
+    lbs, ubs = z[f"{name}.lbs"], z[f"{name}.ubs"]
     engine.load_linear(lin)
     engine.load_cgraph(t)
     nl = engine.tighten(lbs, ubs, rounding=E.ROUND_NEAREST, order=E.ORDER_REFERENCE, loop=E.LOOP_SIMPLEPRESOLVE,
@@ -87,16 +85,16 @@ def test_golden_minlp_bitwise(engine):
     node = engine.tighten(lbs, ubs, rounding=E.ROUND_NEAREST, order=E.ORDER_REFERENCE, loop=E.LOOP_SIMPLEPRESOLVE)
     n_feas = 0
     for b in range(lbs.shape[0]):
-        assert (nl.verdict[b] != 0) == (z["minlp.nl_verdict"][b] != 0), b
+        assert (nl.verdict[b] != 0) == (z[f"{name}.nl_verdict"][b] != 0), b
         if nl.verdict[b] == 0:
-            assert np.array_equal(nl.lb[b], z["minlp.nl_lb"][b]) and np.array_equal(nl.ub[b], z["minlp.nl_ub"][b]), b
+            assert np.array_equal(nl.lb[b], z[f"{name}.nl_lb"][b]) and np.array_equal(nl.ub[b], z[f"{name}.nl_ub"][b]), b
         if node.verdict[b] == E.INFEAS_ROW:
             continue
-        assert (node.verdict[b] != 0) == (z["minlp.node_verdict"][b] != 0), b
+        assert (node.verdict[b] != 0) == (z[f"{name}.node_verdict"][b] != 0), b
         if node.verdict[b] == 0:
             n_feas += 1
-            assert np.array_equal(node.lb[b], z["minlp.node_lb"][b]), b
-            assert np.array_equal(node.ub[b], z["minlp.node_ub"][b]), b
+            assert np.array_equal(node.lb[b], z[f"{name}.node_lb"][b]), b
+            assert np.array_equal(node.ub[b], z[f"{name}.node_ub"][b]), b
     assert n_feas > 0
 
 

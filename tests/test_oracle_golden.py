@@ -130,22 +130,34 @@ def test_cgraph_var_bound_mods_bitwise(oracle, nl_gold):
     assert n_mods > 20
 
 
-def test_nl_simple_presolve_bitwise(oracle, nl_gold):
+def load_minlp(z, name):
+    """(LinearRows, Tapes) of a 'minlp*' fixture; the objective / incumbent when the fixture has one."""
+    m, n = z[f"{name}.shape"]
+    lin = LinearRows(m=int(m), n=int(n), row_ptr=z[f"{name}.row_ptr"], col=z[f"{name}.col"], val=z[f"{name}.val"],
+                     row_lb=z[f"{name}.row_lb"], row_ub=z[f"{name}.row_ub"], var_type=z[f"{name}.var_type"],
+                     lb=z[f"{name}.lbs"][0], ub=z[f"{name}.ubs"][0])
+    if f"{name}.cut_col" in z.files:
+        lin.cut_col, lin.cut_val = z[f"{name}.cut_col"], z[f"{name}.cut_val"]
+        lin.cut_rhs, lin.obj_const = (float(x) for x in z[f"{name}.cut_rhs_const"])
+    return lin, load_tapes(z, f"{name}.t")
+
+
+@pytest.mark.parametrize("name", ["minlp", "minlp_obj"])
+def test_nl_simple_presolve_bitwise(oracle, nl_gold, name):
+    """'minlp_obj' has a linear objective over binaries and an incumbent: LinearHandler::varBndsFromObj_ and
+    NlPresHandler::fixObjBins_ take part."""
     z = nl_gold
-    m, n = z["minlp.shape"]
-    lin = LinearRows(m=int(m), n=int(n), row_ptr=z["minlp.row_ptr"], col=z["minlp.col"], val=z["minlp.val"],
-                     row_lb=z["minlp.row_lb"], row_ub=z["minlp.row_ub"], var_type=z["minlp.var_type"],
-                     lb=z["minlp.lbs"][0], ub=z["minlp.ubs"][0])
-    t = load_tapes(z, "minlp.t")
+    lin, t = load_minlp(z, name)
+    has_obj = lin.cut_col is not None
     changed = 0
-    for b in range(z["minlp.lbs"].shape[0]):
-        l, u, r = oracle.nl_simple_presolve(t, z["minlp.lbs"][b], z["minlp.ubs"][b])
-        assert (r["verdict"] == 1) == (z["minlp.nl_verdict"][b] == 1), b
+    for b in range(z[f"{name}.lbs"].shape[0]):
+        l, u, r = oracle.nl_simple_presolve(t, z[f"{name}.lbs"][b], z[f"{name}.ubs"][b], obj=lin if has_obj else None)
+        assert (r["verdict"] == 1) == (z[f"{name}.nl_verdict"][b] == 1), b
         if r["verdict"] == 0:
-            assert np.array_equal(l, z["minlp.nl_lb"][b]) and np.array_equal(u, z["minlp.nl_ub"][b]), b
+            assert np.array_equal(l, z[f"{name}.nl_lb"][b]) and np.array_equal(u, z[f"{name}.nl_ub"][b]), b
             changed += r["n_mods"]
-        l, u, r = oracle.node_presolve(lin, t, z["minlp.lbs"][b], z["minlp.ubs"][b])
-        assert (r["verdict"] != 0) == (z["minlp.node_verdict"][b] != 0), b
+        l, u, r = oracle.node_presolve(lin, t, z[f"{name}.lbs"][b], z[f"{name}.ubs"][b])
+        assert (r["verdict"] != 0) == (z[f"{name}.node_verdict"][b] != 0), b
         if r["verdict"] == 0:
-            assert np.array_equal(l, z["minlp.node_lb"][b]) and np.array_equal(u, z["minlp.node_ub"][b]), b
+            assert np.array_equal(l, z[f"{name}.node_lb"][b]) and np.array_equal(u, z[f"{name}.node_ub"][b]), b
     assert changed > 0

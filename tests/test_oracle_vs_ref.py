@@ -3,7 +3,7 @@ instances.  Skipped where the reference library was not built (it needs /root/re
 import numpy as np
 import pytest
 
-from minotaur_b200.instances import attach_cutoff, branch_boxes, make_knapsack_setcover, make_minlp, make_sparse_milp
+from minotaur_b200.instances import attach_binary_objective, attach_cutoff, branch_boxes, make_knapsack_setcover, make_minlp, make_sparse_milp
 from helpers import assert_box_parity
 
 
@@ -100,3 +100,34 @@ def test_minlp_node_presolve_bitwise(oracle, Reference):
         if rr["verdict"] == 0:
             assert np.array_equal(rl, ol) and np.array_equal(ru, ou)
         ref.close()
+
+
+@pytest.mark.parametrize("seed,slack,const", [(31, 4.0, 0.0), (35, 3.0, 2.25), (36, 9.0, -4.5)])
+def test_fix_obj_bins_bitwise(oracle, Reference, seed, slack, const):
+    """NlPresHandler::fixObjBins_ (NlPresHandler.cpp:1062-1121): with an incumbent, binaries of the linear
+    objective whose coefficient alone exceeds the slack are fixed.  The rule compares against the RAW incumbent
+    value (the objective constant is not subtracted, :1030), hence the cases with a constant."""
+    lin, tapes = make_minlp(n=300, n_cons=200, m_lin=60, seed=seed)
+    lin = attach_binary_objective(lin, n_bin=14, n_other=2, seed=seed, slack=slack, const=const, coef_hi=40)
+    lbs, ubs = branch_boxes(lin.lb, lin.ub, lin.var_type, 8, seed=seed, max_depth=5, continuous_too=True)
+    lbs[0], ubs[0] = lin.lb, lin.ub
+    fixed = 0
+    for b in range(lbs.shape[0]):
+        ref = Reference(lin, tapes)                 # fresh graph: constant nodes keep state in the reference
+        rl, ru, rr = ref.nl_simple_presolve(lbs[b], ubs[b])
+        ol, ou, orr = oracle.nl_simple_presolve(tapes, lbs[b], ubs[b], obj=lin)
+        assert (rr["verdict"] == 1) == (orr["verdict"] == 1), b
+        if rr["verdict"] == 0:
+            assert np.array_equal(rl, ol) and np.array_equal(ru, ou), b
+            assert rr["n_mods"] == orr["n_mods"], b
+            nl, nu, _ = oracle.nl_simple_presolve(tapes, lbs[b], ubs[b])       # without the incumbent
+            fixed += int(np.sum(ol > nl) + np.sum(ou < nu))
+        ref.close()
+        ref = Reference(lin, tapes)
+        rl, ru, rr = ref.node_presolve(lbs[b], ubs[b])
+        ol, ou, orr = oracle.node_presolve(lin, tapes, lbs[b], ubs[b])
+        assert (rr["verdict"] != 0) == (orr["verdict"] != 0), b
+        if rr["verdict"] == 0:
+            assert np.array_equal(rl, ol) and np.array_equal(ru, ou), b
+        ref.close()
+    assert fixed > 0, "fixObjBins_ never fixed a binary: vacuous"
