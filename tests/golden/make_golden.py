@@ -213,7 +213,59 @@ def nl_cases():
     return out
 
 
+def _emit_minlp(out, name, lin, tp, lbs, ubs):
+    """NlPresHandler::simplePresolve, LinearHandler::simplePresolve, the linear fixpoint driver and the node
+    presolve (LinearHandler then NlPresHandler) of the reference on every box."""
+    for k in ("row_ptr", "col", "val", "row_lb", "row_ub", "var_type"):
+        out[f"{name}.{k}"] = getattr(lin, k)
+    out[f"{name}.shape"] = np.array([lin.m, lin.n])
+    if lin.cut_col is not None:
+        out[f"{name}.cut_col"], out[f"{name}.cut_val"] = lin.cut_col, lin.cut_val
+        out[f"{name}.cut_rhs_const"] = np.array([lin.cut_rhs, lin.obj_const])
+    for k in ("tape_ptr", "op", "arg0", "arg1", "cnst", "child", "lin_ptr", "lin_col", "lin_val", "c_lb", "c_ub"):
+        out[f"{name}.t.{k}"] = getattr(tp, k)
+    out[f"{name}.lbs"], out[f"{name}.ubs"] = lbs, ubs
+    acc = {k: [] for k in ("nl_lb", "nl_ub", "nl_verdict", "node_lb", "node_ub", "node_verdict", "raw_lb", "raw_ub",
+                           "raw_verdict", "fix_lb", "fix_ub", "fix_verdict", "fix_rounds", "fix_nnz")}
+    for b in range(lbs.shape[0]):
+        for key, call in (("nl", "nl_simple_presolve"), ("node", "node_presolve"), ("raw", "lin_simple_presolve")):
+            ref = Reference(lin, tp)            # fresh graphs: constant nodes keep state in the reference
+            l, u, r = getattr(ref, call)(lbs[b], ubs[b])
+            acc[f"{key}_lb"].append(l); acc[f"{key}_ub"].append(u); acc[f"{key}_verdict"].append(r["verdict"])
+            ref.close()
+        ref = Reference(lin, tp)
+        l, u, r = ref.lin_fixpoint(lbs[b], ubs[b], counted=True)
+        acc["fix_lb"].append(l); acc["fix_ub"].append(u); acc["fix_verdict"].append(r["verdict"])
+        acc["fix_rounds"].append(r["rounds"]); acc["fix_nnz"].append(r["nnz_updates"])
+        ref.close()
+    for k, v in acc.items():
+        out[f"{name}.{k}"] = np.array(v, np.int64 if k.endswith(("verdict", "rounds", "nnz")) else np.float64)
+
+
+def tls4_cases():
+    """BASELINE config 1: test_instances/tls4.nl of the reference, read by minotaur_b200/nl_reader.py (the .nl file
+    itself is not copied: the fixture holds the flattened instance), node boxes by branching on its integer
+    variables; once as read, once with an incumbent of value 10 (the optimum is 8.3)."""
+    from minotaur_b200.nl_reader import read_nl
+    out = {}
+    P = read_nl("/root/reference/test_instances/tls4.nl")
+    lin, tp = P.lin, P.tapes
+    assert (P.n_var, P.n_con, tp.n_cons, lin.m) == (105, 64, 4, 60)
+    lbs, ubs = branch_boxes(lin.lb, lin.ub, lin.var_type, 12, seed=4, max_depth=6)
+    lbs[0], ubs[0] = lin.lb, lin.ub
+    obj = (lin.cut_col, lin.cut_val)
+    lin.cut_col = lin.cut_val = None
+    _emit_minlp(out, "tls4", lin, tp, lbs, ubs)
+    lin.cut_col, lin.cut_val = obj
+    lin.cut_rhs = 10.0 - lin.obj_const
+    _emit_minlp(out, "tls4_inc", lin, tp, lbs, ubs)
+    return out
+
+
 if __name__ == "__main__":
+    t4 = tls4_cases()
+    np.savez_compressed(os.path.join(HERE, "tls4_cases.npz"), **t4)
+    print("tls4_cases.npz", os.path.getsize(os.path.join(HERE, "tls4_cases.npz")), "bytes")
     lin = linear_cases()
     np.savez_compressed(os.path.join(HERE, "linear_cases.npz"), **lin)
     nl = nl_cases()

@@ -174,3 +174,45 @@ def test_c5_shape_reduced(engine, oracle):
         assert (ex.verdict[b] != 0) == (r["verdict"] != 0), b
         if r["verdict"] == 0:
             assert np.array_equal(ex.lb[b], ol) and np.array_equal(ex.ub[b], ou), b
+
+
+@pytest.mark.parametrize("name", ["tls4", "tls4_inc"])
+def test_c1_tls4_bitwise(engine, name):
+    """BASELINE config 1, tests/golden/tls4_cases.npz: the reference's own handlers on test_instances/tls4.nl (root
+    box and branched boxes; 'tls4_inc' with an incumbent: cut-off row + fixObjBins_), bit for bit in the
+    reference-order kernel; the default Jacobi / directed mode on the linear rows within tolerance."""
+    z = np.load(os.path.join(GOLD, "tls4_cases.npz"))
+    lin, t = load_minlp(z, name)
+    lbs, ubs = z[f"{name}.lbs"], z[f"{name}.ubs"]
+    engine.load_linear(lin)
+    engine.load_cgraph(t)
+    exact = dict(rounding=E.ROUND_NEAREST, order=E.ORDER_REFERENCE)
+    nl = engine.tighten(lbs, ubs, loop=E.LOOP_SIMPLEPRESOLVE, handlers=E.HANDLERS_NONLINEAR, **exact)
+    node = engine.tighten(lbs, ubs, loop=E.LOOP_SIMPLEPRESOLVE, **exact)
+    raw = engine.tighten(lbs, ubs, loop=E.LOOP_SIMPLEPRESOLVE, handlers=E.HANDLERS_LINEAR, **exact)
+    fix = engine.tighten(lbs, ubs, loop=E.LOOP_FIXPOINT, handlers=E.HANDLERS_LINEAR, **exact)
+    n_node = 0
+    for b in range(lbs.shape[0]):
+        assert (nl.verdict[b] != 0) == (z[f"{name}.nl_verdict"][b] != 0), b
+        if nl.verdict[b] == 0:
+            assert np.array_equal(nl.lb[b], z[f"{name}.nl_lb"][b]) and np.array_equal(nl.ub[b], z[f"{name}.nl_ub"][b]), b
+        assert (fix.verdict[b] != 0) == (z[f"{name}.fix_verdict"][b] != 0), b
+        if fix.verdict[b] == 0:
+            assert np.array_equal(fix.lb[b], z[f"{name}.fix_lb"][b]) and np.array_equal(fix.ub[b], z[f"{name}.fix_ub"][b]), b
+            assert fix.rounds[b] == z[f"{name}.fix_rounds"][b] and fix.nnz_updates[b] == z[f"{name}.fix_nnz"][b], b
+        if raw.verdict[b] != E.INFEAS_ROW:
+            assert (raw.verdict[b] != 0) == (z[f"{name}.raw_verdict"][b] != 0), b
+            assert np.array_equal(raw.lb[b], z[f"{name}.raw_lb"][b]) and np.array_equal(raw.ub[b], z[f"{name}.raw_ub"][b]), b
+        if node.verdict[b] != E.INFEAS_ROW:
+            assert (node.verdict[b] != 0) == (z[f"{name}.node_verdict"][b] != 0), b
+            if node.verdict[b] == 0:
+                n_node += 1
+                assert np.array_equal(node.lb[b], z[f"{name}.node_lb"][b]), b
+                assert np.array_equal(node.ub[b], z[f"{name}.node_ub"][b]), b
+    assert n_node >= 6
+    # default mode (single box, Jacobi rounds, directed rounding) on the linear rows of the root box
+    engine.load_linear(lin)
+    res = engine.tighten(lbs[0], ubs[0])
+    assert res.verdict[0] == 0
+    assert_box_parity(lin.var_type, res.lb, res.ub, z[f"{name}.fix_lb"][0], z[f"{name}.fix_ub"][0], rel_tol=5e-8, what="jacobi")
+    assert never_tighter(res.lb, res.ub, z[f"{name}.fix_lb"][0], z[f"{name}.fix_ub"][0], rel_tol=5e-8)

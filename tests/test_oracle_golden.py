@@ -161,3 +161,61 @@ def test_nl_simple_presolve_bitwise(oracle, nl_gold, name):
         if r["verdict"] == 0:
             assert np.array_equal(l, z[f"{name}.node_lb"][b]) and np.array_equal(u, z[f"{name}.node_ub"][b]), b
     assert changed > 0
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE config 1: test_instances/tls4.nl (105 vars, 60 linear rows + 4 CGraph rows -sum sqrt(x_i*y_i))
+# ----------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def tls4_gold():
+    return np.load(os.path.join(GOLD, "tls4_cases.npz"))
+
+
+@pytest.mark.parametrize("name", ["tls4", "tls4_inc"])
+def test_tls4_bitwise(oracle, tls4_gold, name):
+    """The reference's LinearHandler / NlPresHandler on tls4 (as read by minotaur_b200/nl_reader.py), root box and
+    11 branched boxes; 'tls4_inc' with an incumbent of value 10 (cut-off row + fixObjBins_)."""
+    z = tls4_gold
+    lin, t = load_minlp(z, name)
+    has_obj = lin.cut_col is not None
+    assert (lin.n, lin.m, t.n_cons) == (105, 60, 4)
+    n_mods = 0
+    for b in range(z[f"{name}.lbs"].shape[0]):
+        lb, ub = z[f"{name}.lbs"][b], z[f"{name}.ubs"][b]
+        l, u, r = oracle.lin_simple_presolve(lin, lb, ub)
+        assert r["verdict"] == z[f"{name}.raw_verdict"][b], b
+        assert np.array_equal(l, z[f"{name}.raw_lb"][b]) and np.array_equal(u, z[f"{name}.raw_ub"][b]), b
+        l, u, r = oracle.lin_fixpoint_inplace(lin, lb, ub)
+        assert r["verdict"] == z[f"{name}.fix_verdict"][b] and r["rounds"] == z[f"{name}.fix_rounds"][b], b
+        assert r["nnz_updates"] == z[f"{name}.fix_nnz"][b], b
+        if r["verdict"] == 0:
+            assert np.array_equal(l, z[f"{name}.fix_lb"][b]) and np.array_equal(u, z[f"{name}.fix_ub"][b]), b
+        l, u, r = oracle.nl_simple_presolve(t, lb, ub, obj=lin if has_obj else None)
+        assert (r["verdict"] == 1) == (z[f"{name}.nl_verdict"][b] == 1), b
+        if r["verdict"] == 0:
+            assert np.array_equal(l, z[f"{name}.nl_lb"][b]) and np.array_equal(u, z[f"{name}.nl_ub"][b]), b
+        l, u, r = oracle.node_presolve(lin, t, lb, ub)
+        assert (r["verdict"] != 0) == (z[f"{name}.node_verdict"][b] != 0), b
+        if r["verdict"] == 0:
+            assert np.array_equal(l, z[f"{name}.node_lb"][b]) and np.array_equal(u, z[f"{name}.node_ub"][b]), b
+            n_mods += int(np.sum(l > lb) + np.sum(u < ub))
+    assert n_mods >= 18          # the root box alone gets 18 tightenings
+
+
+def test_nl_reader_reads_the_reference_instance():
+    """Only where the reference tree is present: the reader reproduces the fixture's flattened tls4."""
+    path = "/root/reference/test_instances/tls4.nl"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    from minotaur_b200.nl_reader import read_nl
+    z = np.load(os.path.join(GOLD, "tls4_cases.npz"))
+    P = read_nl(path)
+    assert (P.n_var, P.n_con) == (105, 64)
+    for k in ("row_ptr", "col", "val", "row_lb", "row_ub", "var_type"):
+        assert np.array_equal(getattr(P.lin, k), z[f"tls4.{k}"]), k
+    for k in ("tape_ptr", "op", "arg0", "arg1", "cnst", "child", "lin_ptr", "lin_col", "lin_val", "c_lb", "c_ub"):
+        assert np.array_equal(getattr(P.tapes, k), z[f"tls4.t.{k}"]), k
+    assert np.array_equal(P.lin.cut_col, z["tls4_inc.cut_col"]) and np.array_equal(P.lin.cut_val, z["tls4_inc.cut_val"])
+    # Jacobian non-zeros of the header: linear rows + linear parts and variable leaves of the 4 nonlinear rows
+    assert P.lin.nnz + int(P.tapes.lin_ptr[-1]) + int(np.sum(P.tapes.op == 34)) == 588
