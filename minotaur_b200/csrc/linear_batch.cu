@@ -61,7 +61,12 @@ static_assert(sizeof(TileShared) == kTileStateBytes, "BatchIo::tstate stride");
 struct TileTeam {
   int gwarp, n_warps;       // this warp / warps in the cluster
   int cthread, n_threads;   // this thread / threads in the cluster
-  __device__ __forceinline__ void sync() const { cg::this_cluster().sync(); }
+  // bounds written with ordinary stores in this phase are read by bulk async copies (async proxy) in the next
+  __device__ __forceinline__ void sync() const
+  {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    cg::this_cluster().sync();
+  }
 };
 __device__ __forceinline__ TileTeam make_team()
 {
@@ -85,6 +90,59 @@ __device__ __forceinline__ TileTeam make_team()
 struct RowStage {
   double *val;    // [32] this warp's slice
   int *col;       // [32]
+  double2 *seg;   // [kSegEntries][32] {lb,ub} of the row's variables for the 32 boxes of the tile (TMA destination)
+  uint64_t *bar;  // mbarrier of the bulk copies into seg
+};
+
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared, completion on an mbarrier ----
+constexpr int kSegEntries = 12;                      // rows of up to this many terms are staged
+constexpr int kSegBytes = kTile * (int)sizeof(double2);   // 512 B: one variable, the 32 boxes of the tile
+constexpr int kSegSmemBytes = kBatchWarps * kSegEntries * kSegBytes;   // dynamic shared memory of a CTA
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+               "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+               ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Where a row's {lb,ub} come from.  BoxGlobal gathers them from the node-minor box array; BoxStaged reads the copy
+// a bulk async copy put into shared memory (one 512-byte segment per term), writes a changed bound into that copy
+// and through to global memory.
+struct BoxGlobal {
+  static constexpr int kBatch = kGather;     // independent 512-byte gathers kept in flight
+  double2 *bx; int64_t ld;
+  __device__ __forceinline__ double2 load(int, int j) const { return bx[(int64_t)j * ld]; }
+  __device__ __forceinline__ double2 *slot(int, int j) const { return bx + (int64_t)j * ld; }
+  __device__ __forceinline__ void commit(int, int) const {}
+};
+struct BoxStaged {
+  static constexpr int kBatch = 2;           // shared-memory reads: no need to batch deeply, keep registers free
+  double2 *seg;            // this lane's column of the staged segments: entry t at seg[t * 32]
+  double2 *bx; int64_t ld;
+  __device__ __forceinline__ double2 load(int t, int) const { return seg[t * kTile]; }
+  __device__ __forceinline__ double2 *slot(int t, int) const { return seg + t * kTile; }
+  // write-through; the fence orders this lane's store into seg before the next bulk copy into the same buffer
+  __device__ __forceinline__ void commit(int t, int j) const
+  {
+    bx[(int64_t)j * ld] = seg[t * kTile];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
 };
 
 __device__ __forceinline__ int stage_chunk(const LinDev &P, int c0, int cnt_left, const RowStage &st, int lane)
@@ -94,6 +152,17 @@ __device__ __forceinline__ int stage_chunk(const LinDev &P, int c0, int cnt_left
   if (lane < cnt) { st.col[lane] = __ldg(P.col + c0 + lane); st.val[lane] = __ldg(P.val + c0 + lane); }
   __syncwarp();
   return cnt;
+}
+
+// A row of at most 32 entries is staged ONCE by its caller (stage_short) and stays staged for all passes over it
+// (activity, FromLb, activity again, FromUb); longer rows are re-staged chunk by chunk.
+__device__ __forceinline__ void stage_short(const LinDev &P, int beg, int cnt_row, const RowStage &st, int lane)
+{
+  if (cnt_row <= 32) (void)stage_chunk(P, beg, cnt_row, st, lane);
+}
+__device__ __forceinline__ int next_chunk(const LinDev &P, int beg, int c0, int cnt_row, const RowStage &st, int lane)
+{
+  return cnt_row <= 32 ? cnt_row : stage_chunk(P, beg + c0, cnt_row - c0, st, lane);
 }
 
 template <class R>
@@ -107,22 +176,23 @@ __device__ __forceinline__ void acc_term(double a, double2 b, double &ll, double
 
 // min / max activity of one row for this lane's box  [getLfBnds_].  Computed by every lane (lanes whose box
 // is not due simply discard the result): no predication in the loop.
-template <class R>
-__device__ __forceinline__ void row_activity(const LinDev &P, int beg, int cnt_row, const double2 *bx,
-                                             int64_t ld, const RowStage &st, int lane, double &ll, double &uu)
+template <class R, class Box>
+__device__ __forceinline__ void row_activity(const LinDev &P, int beg, int cnt_row, const Box &box,
+                                             const RowStage &st, int lane, double &ll, double &uu)
 {
   ll = 0.0; uu = 0.0;
   for (int c0 = 0; c0 < cnt_row; c0 += 32) {
-    const int cnt = stage_chunk(P, beg + c0, cnt_row - c0, st, lane);
+    const int cnt = next_chunk(P, beg, c0, cnt_row, st, lane);
     int t = 0;
-    for (; t + kGather <= cnt; t += kGather) {
-      double a[kGather]; double2 b[kGather];
+    constexpr int kB = Box::kBatch;
+    for (; t + kB <= cnt; t += kB) {
+      double a[kB]; double2 b[kB];
 #pragma unroll
-      for (int u = 0; u < kGather; ++u) { a[u] = st.val[t + u]; b[u] = bx[(int64_t)st.col[t + u] * ld]; }
+      for (int u = 0; u < kB; ++u) { a[u] = st.val[t + u]; b[u] = box.load(t + u, st.col[t + u]); }
 #pragma unroll
-      for (int u = 0; u < kGather; ++u) acc_term<R>(a[u], b[u], ll, uu);
+      for (int u = 0; u < kB; ++u) acc_term<R>(a[u], b[u], ll, uu);
     }
-    for (; t < cnt; ++t) acc_term<R>(st.val[t], bx[(int64_t)st.col[t] * ld], ll, uu);
+    for (; t < cnt; ++t) acc_term<R>(st.val[t], box.load(t, st.col[t]), ll, uu);
   }
 }
 
@@ -207,8 +277,8 @@ __device__ __forceinline__ bool update_exact(double av, double numer, bool sing,
 // slack = |row bound - activity| for lanes that take part, +inf for the others.  A candidate moves a bound of
 // x_j towards the other by slack/|a|, so it can only be accepted when slack < |a|*(ub_j - lb_j): that product
 // test (1e-9 relative margin; inf/NaN fall through) lets the warp skip the fp64 division for almost every term.
-template <class R, bool FROM_LB>
-__device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int cnt_row, double2 *bx, int64_t ld,
+template <class R, bool FROM_LB, class Box>
+__device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int cnt_row, const Box &box,
                                                const RowStage &st, bool doit, bool sing, double rbound, double act,
                                                uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane,
                                                bool count_int = true)
@@ -218,12 +288,13 @@ __device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int cnt
   const double numer = FROM_LB ? R::sub_lo(rbound, act) : R::sub_hi(rbound, act);
   const double slack = doit ? (FROM_LB ? -numer : numer) : INFINITY;
   // one term: product test, then (rarely) the exact candidate, the in-place store and the bFlag propagation
-  auto term = [&](double av, int j, double2 b) {
+  auto term = [&](int t, double av, int j, double2 b) {
     const double reach = fabs(av) * (b.y - b.x) * 1.000000001;
     const bool maybe = !(slack > reach);
     if (!__any_sync(kFull, maybe)) return;            // nobody in the tile can move this variable
     bool chg = false;
-    if (maybe && doit) chg = update_exact<R, FROM_LB>(av, numer, sing, b, bx + (int64_t)j * ld);
+    if (maybe && doit) chg = update_exact<R, FROM_LB>(av, numer, sing, b, box.slot(t, j));
+    if (chg) box.commit(t, j);
     const unsigned m = __ballot_sync(kFull, chg);
     if (m) {
       any |= m;
@@ -235,32 +306,32 @@ __device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int cnt
     }
   };
   for (int c0 = 0; c0 < cnt_row; c0 += 32) {
-    const int cnt = stage_chunk(P, beg + c0, cnt_row - c0, st, lane);
+    const int cnt = next_chunk(P, beg, c0, cnt_row, st, lane);
     int t = 0;
-    for (; t + kGather <= cnt; t += kGather) {
-      double a[kGather]; double2 b[kGather]; int jj[kGather];
+    constexpr int kB = Box::kBatch;
+    for (; t + kB <= cnt; t += kB) {
+      double a[kB]; double2 b[kB]; int jj[kB];
 #pragma unroll
-      for (int u = 0; u < kGather; ++u) { a[u] = st.val[t + u]; jj[u] = st.col[t + u]; b[u] = bx[(int64_t)jj[u] * ld]; }
+      for (int u = 0; u < kB; ++u) { a[u] = st.val[t + u]; jj[u] = st.col[t + u]; b[u] = box.load(t + u, jj[u]); }
 #pragma unroll
-      for (int u = 0; u < kGather; ++u) term(a[u], jj[u], b[u]);
+      for (int u = 0; u < kB; ++u) term(t + u, a[u], jj[u], b[u]);
     }
-    for (; t < cnt; ++t) { const int j = st.col[t]; term(st.val[t], j, bx[(int64_t)j * ld]); }
+    for (; t < cnt; ++t) { const int j = st.col[t]; term(t, st.val[t], j, box.load(t, j)); }
   }
   return any;
 }
 
 // one linear row for the 32 boxes of the tile  [linBndTighten_ with apply_to_prob == false]
-template <class R>
-__device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx, int64_t ld, const RowStage &st,
-                                            bool mine, uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane,
-                                            unsigned long long &my_nnz)
+// (rows of at most 32 entries have been staged by the caller; `box` says where their {lb,ub} are)
+template <class R, class Box>
+__device__ __forceinline__ void process_row(const LinDev &P, int2 info, double2 bnd, const Box &box, double2 *bx,
+                                            int64_t ld, const RowStage &st, bool mine, uint32_t *flags,
+                                            uint32_t *varflag, TileShared &sh, int lane, unsigned long long &my_nnz)
 {
-  const int2 info = __ldg(P.row_info + i);
   const int beg = info.x, cnt = info.y, end = beg + cnt;
-  const double2 bnd = __ldg(P.row_bnd + i);
   const double rl = bnd.x, ru = bnd.y;
   double ll, uu, sing_ll = -INFINITY, sing_uu = INFINITY;
-  row_activity<R>(P, beg, cnt, bx, ld, st, lane, ll, uu);
+  row_activity<R>(P, beg, cnt, box, st, lane, ll, uu);
   bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
   if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
   if (mine) my_nnz += (unsigned long long)cnt;
@@ -276,13 +347,13 @@ __device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx,
   }
   unsigned chg = 0;
   if (__any_sync(kFull, do_lb))
-    chg = row_update<R, true>(P, beg, cnt, bx, ld, st, do_lb, s_lb, rl, act, flags, varflag, sh, lane);
+    chg = row_update<R, true>(P, beg, cnt, box, st, do_lb, s_lb, rl, act, flags, varflag, sh, lane);
   // recompute activities when FromLb changed something (:1027-1032); lanes that did not
   // change would recompute identical values, so the decision is taken per warp
   if (chg) {
     const bool redo = mine && ((chg >> lane) & 1u);
     double l2, u2;
-    row_activity<R>(P, beg, cnt, bx, ld, st, lane, l2, u2);
+    row_activity<R>(P, beg, cnt, box, st, lane, l2, u2);
     if (redo) { ll = l2; uu = u2; }
     need_sing = redo && (ll < -kInf20 || uu > kInf20);
     if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
@@ -294,7 +365,7 @@ __device__ __forceinline__ void process_row(const LinDev &P, int i, double2 *bx,
     else if (sing_ll > -kInf20) { do_ub = true; s_ub = true; act = sing_ll; }
   }
   if (__any_sync(kFull, do_ub))
-    (void)row_update<R, false>(P, beg, cnt, bx, ld, st, do_ub, s_ub, ru, act, flags, varflag, sh, lane);
+    (void)row_update<R, false>(P, beg, cnt, box, st, do_ub, s_ub, ru, act, flags, varflag, sh, lane);
 }
 
 // Objective cut-off row  c.x <= rhs  for the 32 boxes of the tile  [varBndsFromObj_, :544-597]: evaluated after
@@ -312,7 +383,9 @@ __device__ __noinline__ void cutoff_row(const LinDev &P, double2 *bx, int64_t ld
   bool mine = run && sh.verdict[lane] == 0;
   while (__any_sync(kFull, mine)) {
     double ll, uu, sing_ll = INFINITY, sing_uu = INFINITY;
-    row_activity<R>(C, 0, cnt, bx, ld, st, lane, ll, uu);
+    const BoxGlobal box{bx, ld};
+    stage_short(C, 0, cnt, st, lane);
+    row_activity<R>(C, 0, cnt, box, st, lane, ll, uu);
     const bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
     if (__any_sync(kFull, need_sing)) row_sing_activity<R>(C, 0, cnt, bx, ld, need_sing, sing_ll, sing_uu);
     if (mine) my_nnz += (unsigned long long)cnt;
@@ -325,7 +398,7 @@ __device__ __noinline__ void cutoff_row(const LinDev &P, double2 *bx, int64_t ld
     }
     unsigned chg = 0;
     if (__any_sync(kFull, doit))
-      chg = row_update<R, false>(C, 0, cnt, bx, ld, st, doit, sing, P.cut_rhs, act, flags, varflag, sh, lane, false);
+      chg = row_update<R, false>(C, 0, cnt, box, st, doit, sing, P.cut_rhs, act, flags, varflag, sh, lane, false);
     mine = mine && ((chg >> lane) & 1u);
   }
 }
@@ -360,9 +433,10 @@ template <class R>
 __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, int64_t ld, const RowStage &st,
                                                  uint32_t *flags, uint32_t *varflag, TileShared &sh, bool active, int loop_mode,
                                                  int max_rounds, int bad_row, unsigned long long &my_nnz,
-                                                 bool &any_change)
+                                                 bool &any_change, unsigned &seg_phase)
 {
   const int lane = threadIdx.x & 31;
+  const double2 *tile_base = bx - lane;          // box 0 of the tile: + j*ld is variable j's 512-byte segment
   const TileTeam team = make_team();
   const int warp = team.gwarp;
   // every row flagged for every box of the tile  (simplePresolve :1618-1622)
@@ -402,13 +476,34 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
         const uint32_t raw = (q < q_hi) ? __ldcg(flags + q) : 0u;
         const uint32_t fw = raw & runmask & alive;
         unsigned rows = __ballot_sync(kFull, fw != 0u);
+        if (rows == 0u) continue;
+        // the heads {first entry, count} / {lb, ub} of the chunk's rows come with one coalesced request each
+        int2 myinfo = make_int2(0, 0);
+        double2 mybnd = make_double2(0.0, 0.0);
+        if (fw != 0u) { myinfo = __ldg(P.row_info + q); mybnd = __ldg(P.row_bnd + q); }
         while (rows) {
           const int t = __ffs(rows) - 1;
           rows &= rows - 1;
+          const int2 info = make_int2(__shfl_sync(kFull, myinfo.x, t), __shfl_sync(kFull, myinfo.y, t));
+          const double2 bnd = make_double2(__shfl_sync(kFull, mybnd.x, t), __shfl_sync(kFull, mybnd.y, t));
           const uint32_t proc = __shfl_sync(kFull, fw, t);
           if (lane == t) __stcg(flags + q, raw & ~proc);     // c_ptr->setBFlag(false), :513
-          __syncwarp();
-          process_row<R>(P, q0 + t, bx, ld, st, (proc >> lane) & 1u, flags, varflag, sh, lane, my_nnz);
+          stage_short(P, info.x, info.y, st, lane);
+          const bool mine = (proc >> lane) & 1u;
+          if (info.y <= kSegEntries) {
+            // TMA: one 512-byte bulk copy per term brings the {lb,ub} of that variable for the tile's 32 boxes into
+            // shared memory; all copies of the row are in flight at once and land on the warp's mbarrier
+            if (lane == 0) mbar_expect_tx(st.bar, (uint32_t)(info.y * kSegBytes));
+            __syncwarp();
+            if (lane < info.y) bulk_g2s(st.seg + lane * kTile, tile_base + (int64_t)st.col[lane] * ld, kSegBytes, st.bar);
+            mbar_wait(st.bar, seg_phase);
+            seg_phase ^= 1u;
+            const BoxStaged box{st.seg + lane, bx, ld};
+            process_row<R>(P, info, bnd, box, bx, ld, st, mine, flags, varflag, sh, lane, my_nnz);
+          } else {
+            const BoxGlobal box{bx, ld};
+            process_row<R>(P, info, bnd, box, bx, ld, st, mine, flags, varflag, sh, lane, my_nnz);
+          }
         }
       }
       team.sync();
@@ -561,7 +656,14 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
 {
   __shared__ double s_val[kBatchWarps][32];
   __shared__ int s_col[kBatchWarps][32];
-  const RowStage st{s_val[threadIdx.x >> 5], s_col[threadIdx.x >> 5]};
+  __shared__ __align__(8) uint64_t s_bar[kBatchWarps];
+  extern __shared__ __align__(128) unsigned char s_seg[];       // [kBatchWarps][kSegEntries][32] double2: TMA destination
+  const int wl = threadIdx.x >> 5;
+  const RowStage st{s_val[wl], s_col[wl], reinterpret_cast<double2 *>(s_seg) + (size_t)wl * kSegEntries * kTile, &s_bar[wl]};
+  if ((threadIdx.x & 31) == 0) mbar_init(st.bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  unsigned seg_phase = 0u;
   const TileTeam team = make_team();
   const int tile = blockIdx.x / (int)cg::this_cluster().num_blocks();
   TileShared &sh = *reinterpret_cast<TileShared *>(io.tstate + (int64_t)tile * kTileStateBytes);
@@ -591,7 +693,7 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
     bool lin_changed = false, nl_changed = false;
     if (lin_enabled)
       my_rounds += lin_tile_presolve<R>(P, bx, ld, st, flags, varflag, sh, active, loop_mode, max_rounds, bad_row,
-                                        my_nnz, lin_changed);
+                                        my_nnz, lin_changed, seg_phase);
     if (nl_enabled) my_rounds += nl_tile_presolve<R>(P, N, bx, ld, sh, active, nl_changed);
     // fixpoint mode with both handlers: go round again while the nonlinear sweeps still move bounds
     const bool again = (loop_mode == 0) && lin_enabled && nl_enabled && nl_changed && sh.verdict[lane] == 0 &&
@@ -698,7 +800,7 @@ cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(tiles * cluster));
   cfg.blockDim = dim3(kBatchThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = kSegSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -707,6 +809,9 @@ cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSegSmemBytes);
+  if (e != cudaSuccess) return e;
   return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R>, P, nl, io, loop_mode, max_rounds, lin_enabled,
                             nl_enabled);
 }
