@@ -58,15 +58,19 @@ struct SingleWs {
   double2 *box[2];      // [n] {lb, ub}: merged candidates, integer bounds not yet rounded
   uint32_t *due[2];     // [(m+31)/32] row-is-due bit sets   (Constraint bFlag)
   uint32_t *touched[2]; // [(n+31)/32] variable-moved-in-the-round bit sets
-  // control block (128 bytes, zeroed before every launch)
+  uint32_t *ever;       // [(n+31)/32] variable moved in some round: the only entries the epilogue writes back
+  // control block (128 bytes; zero when a launch starts: the previous launch's last block resets it)
   int32_t *ring;   // [12] per-round words: ring[r%3] changed, ring[3+r%3] int moved, 
   int32_t *status; // [8]  [0] a row is activity-infeasible  [1] rounds  [2] changed (variable, round) pairs
                    //      [3] a moved variable's bounds cross  [4] a row's bounds cross  [5] incoming bounds cross
                    //      [6] verdict of the loop
   unsigned long long *counters;  // [2] [0] nnz_updates, [1] rows evaluated
   unsigned *bar;   // device-wide barrier arrive counter
+  unsigned *done;  // blocks that have left the kernel: the last one publishes and resets the control block
+  int32_t *result; // [kCtrlWords] pinned, mapped host copy of the control block, written by the last block
   unsigned long long *trace;     // [64] optional phase timestamps (globaltimer ns), or nullptr
 };
+constexpr int kCtrlWords = 32;   // the control block: 128 bytes
 
 // workspace of the per-round kernels (row-partitioned multi-GPU mode)
 struct RoundsWs {

@@ -79,6 +79,32 @@ __device__ __forceinline__ void flag_rows_serial(const LinDev &P, int j, uint32_
   }
 }
 
+// The set bits of up to 32 words (lane l holds word wb + l) are spread over the lanes, 32 at a time, and f(j) is
+// called for each: every marked variable is an independent chain, whatever word it sits in.  Convergent.
+template <class F>
+__device__ __forceinline__ void for_each_marked(unsigned word, int wb, int lane, F f)
+{
+  int incl = __popc(word);
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(kFullMask, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int total = __shfl_sync(kFullMask, incl, 31);
+  for (int base = 0; base < total; base += 32) {
+    const int x = base + lane;
+    int lo = 0;                                      // first lane whose inclusive count exceeds x
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(kFullMask, incl, lo + step - 1);
+      if (v <= x) lo += step;
+    }
+    const unsigned wword = __shfl_sync(kFullMask, word, lo);
+    const int wincl = __shfl_sync(kFullMask, incl, lo);
+    if (x < total) f((wb + lo) * 32 + (int)__fns(wword, 0, x - (wincl - __popc(wword)) + 1));
+  }
+}
+
 template <class R>
 __global__ void __launch_bounds__(kSingleThreads, 1)
 fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, int max_rounds, int loop_mode)
@@ -124,7 +150,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
         if (r.x > r.y + kETol) cross0 = 1;       // still crossed after any round: reported after round 1
       }
       const unsigned fm = __ballot_sync(kFullMask, frac);
-      if (lane == 0) { W.touched[0][j0 >> 5] = fm; W.touched[1][j0 >> 5] = 0u; }
+      if (lane == 0) { W.touched[0][j0 >> 5] = fm; W.touched[1][j0 >> 5] = 0u; W.ever[j0 >> 5] = 0u; }
     }
     // round 1 takes every row without looking at its bit set (:1618-1622)
     const int nw_rows = (P.m + 31) / 32;
@@ -184,40 +210,21 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
       int bad = 0;
       for (int wb = fw0; wb < fw1; wb += 32) {
         const int w = wb + lane;
-        unsigned word = wb == fw0 ? fw : ((w < fw1) ? __ldcg(Tp + w) : 0u);
-        if (word) Tp[w] = 0u;
-        int incl = __popc(word);
-        my_changes += incl;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(kFullMask, incl, d);
-          if (lane >= d) incl += v;
-        }
-        const int total = __shfl_sync(kFullMask, incl, 31);
-        for (int base = 0; base < total; base += 32) {
-          const int x = base + lane;
-          int lo = 0;
-#pragma unroll
-          for (int step = 16; step > 0; step >>= 1) {
-            const int v = __shfl_sync(kFullMask, incl, lo + step - 1);
-            if (v <= x) lo += step;
+        const unsigned word = wb == fw0 ? fw : ((w < fw1) ? __ldcg(Tp + w) : 0u);
+        if (word) { Tp[w] = 0u; __stcg(W.ever + w, __ldcg(W.ever + w) | word); }     // this lane owns word w in every round
+        my_changes += __popc(word);
+        for_each_marked(word, wb, lane, [&](int j) {
+          if (round == 1) {                      // moved by rounding alone: only its rows need flagging
+            flag_rows_serial(P, j, W.due[0]);
+            W.ring[slot] = 1;
+          } else {
+            double2 v = __ldcg(A + j);
+            atomic_max_f64(&Z[j].x, v.x);        // Z lags behind A exactly where A moved last round
+            atomic_min_f64(&Z[j].y, v.y);
+            if (is_int_type(__ldg(P.var_type + j))) tighten_int_bounds(v.x, v.y);
+            if (v.x > v.y + kETol) bad = 1;      // checkBounds_ of the box this round reads
           }
-          const unsigned wword = __shfl_sync(kFullMask, word, lo);
-          const int wincl = __shfl_sync(kFullMask, incl, lo);
-          if (x < total) {
-            const int j = (wb + lo) * 32 + (int)__fns(wword, 0, x - (wincl - __popc(wword)) + 1);
-            if (round == 1) {                      // moved by rounding alone: only its rows need flagging
-              flag_rows_serial(P, j, W.due[0]);
-              W.ring[slot] = 1;
-            } else {
-              double2 v = __ldcg(A + j);
-              atomic_max_f64(&Z[j].x, v.x);        // Z lags behind A exactly where A moved last round
-              atomic_min_f64(&Z[j].y, v.y);
-              if (is_int_type(__ldg(P.var_type + j))) tighten_int_bounds(v.x, v.y);
-              if (v.x > v.y + kETol) bad = 1;      // checkBounds_ of the box this round reads
-            }
-          }
-        }
+        });
       }
       if (bad) W.status[3] = 1;
     }
@@ -249,31 +256,26 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
     final_check = false;
   }
 
-  // ---- epilogue: hand the box back, publish counters ----
-  {
+  // ---- epilogue: hand the box back -- lb_io / ub_io already hold the bounds of every variable that never moved,
+  //      so only the variables marked in `ever` (or moved in the last round) are written; publish counters ----
+  if (out_round) {
     const double2 *O = W.box[out_buf];
-    for (int j = gtid; j < P.n; j += nthreads) {
-      double2 b = __ldcg(O + j);
-      if (out_round && is_int_type(__ldg(P.var_type + j))) tighten_int_bounds(b.x, b.y);
-      lb_io[j] = b.x;
-      ub_io[j] = b.y;
+    const uint32_t *Tl = W.touched[round & 1];
+    int bad = 0;
+    for (int wb = fw0; wb < fw1; wb += 32) {
+      const int w = wb + lane;
+      const unsigned last = (w < fw1) ? __ldcg(Tl + w) : 0u;
+      const unsigned word = (w < fw1) ? (__ldcg(W.ever + w) | last) : 0u;
+      if (final_check) my_changes += __popc(last);
+      for_each_marked(word, wb, lane, [&](int j) {
+        double2 b = __ldcg(O + j);
+        if (is_int_type(__ldg(P.var_type + j))) tighten_int_bounds(b.x, b.y);
+        lb_io[j] = b.x;
+        ub_io[j] = b.y;
+        if (b.x > b.y + kETol) bad = 1;            // bound check of what the last round moved (no fix-up follows)
+      });
     }
-    if (final_check) {                   // bound check of the variables the last round moved
-      const uint32_t *Tl = W.touched[round & 1];
-      int bad = 0;
-      for (int w = tid; w < nw_vars; w += nthreads) {
-        unsigned word = __ldcg(Tl + w);
-        my_changes += __popc(word);
-        while (word) {
-          const int j = w * 32 + __ffs(word) - 1;
-          word &= word - 1;
-          double2 v = __ldcg(O + j);
-          if (is_int_type(__ldg(P.var_type + j))) tighten_int_bounds(v.x, v.y);
-          if (v.x > v.y + kETol) bad = 1;
-        }
-      }
-      if (bad) W.status[3] = 1;
-    }
+    if (bad && final_check) W.status[3] = 1;
   }
   __shared__ unsigned long long s_nnz, s_rows;
   __shared__ int s_changes;
@@ -292,6 +294,18 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
     if (s_rows) { atomicAdd(&W.counters[0], s_nnz); atomicAdd(&W.counters[1], s_rows); }
     if (s_changes) atomicAdd(&W.status[2], s_changes);
     if (blockIdx.x == 0) { W.status[1] = rounds_out; W.status[6] = verdict; }
+    // last block out: publish the control block to the host (pinned, mapped: no copy operation follows the
+    // kernel) and zero it for the next launch (no memset precedes the kernel)
+    __threadfence();
+    if (atomicAdd(W.done, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const int32_t *src = W.ring;                 // the control block starts with ring[]
+      int32_t v[kCtrlWords];
+#pragma unroll
+      for (int k = 0; k < kCtrlWords; ++k) v[k] = __ldcg(src + k);
+#pragma unroll
+      for (int k = 0; k < kCtrlWords; ++k) { W.result[k] = v[k]; W.ring[k] = 0; }
+    }
   }
   MNTR_TRACE();
 }

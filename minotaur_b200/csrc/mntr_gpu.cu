@@ -24,6 +24,15 @@
 
 using namespace mntr;
 
+// host mirror of the single-box kernel's control block (SingleWs::ring/status/counters/bar)
+constexpr int kTraceWords = 64 + 256 * 16;   // MNTR_GPU_TRACE buffer: phases, one warp's passes, barrier arrivals
+struct SingleCtrl {
+  int32_t ring[12]; int32_t status[8]; unsigned long long counters[2]; unsigned bar; unsigned done; unsigned pad[6];
+  // the loop's verdict, or MNTR_INFEAS_BOUNDS when the bound check of the last round's moved variables failed
+  int verdict() const { return status[6] ? status[6] : (status[3] ? 1 : 0); }
+};
+static_assert(sizeof(SingleCtrl) == 128, "control block layout");
+
 struct mntr_gpu_ctx {
   int device = 0;
   int sm_count = 0;
@@ -37,6 +46,7 @@ struct mntr_gpu_ctx {
   int64_t nnz = 0, nnz_padded = 0;
   std::vector<uint8_t> h_var_type;   // host copy: integer bit of the stored columns
   int lanes_per_row = 8;             // sub-warp group size of the per-round kernels
+  bool no_zero_copy = false;         // MNTR_GPU_NO_ZEROCOPY=1: always stage pinned host boxes through device copies
   LinDev lin{};
   std::vector<void *> lin_allocs, cut_allocs;
 
@@ -64,6 +74,8 @@ struct mntr_gpu_ctx {
   // ---- per-round workspace (row-partitioned multi-GPU mode) ----
   RoundsWs rws{};
   int32_t *h_ctrl = nullptr;          // pinned mirror of rws.ctrl + counters
+  SingleCtrl *h_single = nullptr;     // pinned, mapped: the fixpoint kernel's last block writes its control block here
+  bool ctrl_clean = false;            // the device control block is zero (left so by the previous launch)
   bool force_rounds = false;          // MNTR_GPU_ROUNDS=1: per-round kernels even without a communicator
 
   // ---- NCCL communicator (resolved at run time with dlopen: no link-time dependency) ----
@@ -73,14 +85,6 @@ struct mntr_gpu_ctx {
   mntr_gpu_stats stats{};
 };
 
-// host mirror of the single-box kernel's control block (SingleWs::ring/status/counters/bar)
-constexpr int kTraceWords = 64 + 256 * 16;   // MNTR_GPU_TRACE buffer: phases, one warp's passes, barrier arrivals
-struct SingleCtrl {
-  int32_t ring[12]; int32_t status[8]; unsigned long long counters[2]; unsigned bar; unsigned pad[7];
-  // the loop's verdict, or MNTR_INFEAS_BOUNDS when the bound check of the last round's moved variables failed
-  int verdict() const { return status[6] ? status[6] : (status[3] ? 1 : 0); }
-};
-static_assert(sizeof(SingleCtrl) == 128, "control block layout");
 
 namespace {
 
@@ -281,6 +285,7 @@ void mntr_gpu_destroy(mntr_gpu_ctx *ctx)
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
   if (ctx->h_ctrl) { cudaFreeHost(ctx->h_ctrl); ctx->h_ctrl = nullptr; }
+  if (ctx->h_single) { cudaFreeHost(ctx->h_single); ctx->h_single = nullptr; }
   free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->nl_allocs); free_all(ctx->single_allocs);
   free_batch(ctx); free_stage(ctx);
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -414,6 +419,7 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
     if ((rc = dalloc((void **)&W.box[k], sizeof(double2) * (size_t)n))) return rc;
     if ((rc = dalloc((void **)&W.due[k], sizeof(uint32_t) * (size_t)((m + 31) / 32 + 1)))) return rc;
     if ((rc = dalloc((void **)&W.touched[k], sizeof(uint32_t) * (size_t)((n + 31) / 32 + 1)))) return rc;
+    if (k == 0 && (rc = dalloc((void **)&W.ever, sizeof(uint32_t) * (size_t)((n + 31) / 32 + 1)))) return rc;
   }
   if ((rc = dalloc((void **)&ctx->d_lb, sizeof(double) * (size_t)n))) return rc;
   if ((rc = dalloc((void **)&ctx->d_ub, sizeof(double) * (size_t)n))) return rc;
@@ -422,6 +428,14 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   W.status = W.ring + 12;
   W.counters = (unsigned long long *)((char *)ctx->d_ctrl + offsetof(SingleCtrl, counters));
   W.bar = (unsigned *)((char *)ctx->d_ctrl + offsetof(SingleCtrl, bar));
+  W.done = (unsigned *)((char *)ctx->d_ctrl + offsetof(SingleCtrl, done));
+  if (!ctx->h_single) CU(cudaHostAlloc((void **)&ctx->h_single, sizeof(SingleCtrl), cudaHostAllocMapped));
+  {
+    void *mapped = nullptr;
+    CU(cudaHostGetDevicePointer(&mapped, ctx->h_single, 0));
+    W.result = (int32_t *)mapped;
+  }
+  ctx->ctrl_clean = false;
   W.trace = nullptr;
   if (const char *tr = getenv("MNTR_GPU_TRACE")) {
     if (tr[0] == '1') { if ((rc = dalloc((void **)&W.trace, kTraceWords * sizeof(unsigned long long)))) return rc; }
@@ -436,6 +450,7 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   RW.counters = (unsigned long long *)((char *)RW.ctrl + 32);
   if (!ctx->h_ctrl) CU(cudaMallocHost((void **)&ctx->h_ctrl, 64));
   if (const char *fr = getenv("MNTR_GPU_ROUNDS")) ctx->force_rounds = fr[0] == '1';
+  if (const char *zc = getenv("MNTR_GPU_NO_ZEROCOPY")) ctx->no_zero_copy = zc[0] == '1';
 
   {   // sub-warp group size of the per-round kernels from the mean row length (four entries per lane per step)
     const double mean = m > 0 ? (double)nnz / m : 0.0;
@@ -600,7 +615,8 @@ int mntr_gpu_set_incumbent(mntr_gpu_ctx *ctx, double best_value)
 // K1 on a device-resident box; leaves verdict/rounds/counters in the control block
 static int run_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, const mntr_gpu_options &o)
 {
-  CU(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(SingleCtrl), ctx->stream));
+  if (!ctx->ctrl_clean) CU(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(SingleCtrl), ctx->stream));
+  ctx->ctrl_clean = false;          // until the launch has been seen to complete
   CU(launch_single_jacobi(ctx->lin, ctx->sws, lb_dev, ub_dev, o.rounding == MNTR_ROUND_DIRECTED, o.max_rounds, o.loop, ctx->sm_count, ctx->stream));
   return MNTR_OK;
 }
@@ -684,11 +700,19 @@ static bool use_rounds(const mntr_gpu_ctx *ctx, const mntr_gpu_options &o)
   return ctx->comm != nullptr || ctx->force_rounds || (o.flags & MNTR_FLAG_PER_ROUND_KERNELS);
 }
 
+static double *mapped_host_ptr(const double *p);
+static int tighten_single_zero_copy(mntr_gpu_ctx *ctx, double *lb_map, double *ub_map, const mntr_gpu_options &o,
+                                    int32_t *verdict, int32_t *rounds, int64_t *nnz_updates);
+
 static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_gpu_options &o,
                           int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
 {
   const size_t bytes = sizeof(double) * (size_t)ctx->n;
   int rc;
+  if (!use_rounds(ctx, o) && !ctx->no_zero_copy) {
+    double *lb_map = mapped_host_ptr(lb), *ub_map = mapped_host_ptr(ub);
+    if (lb_map && ub_map) return tighten_single_zero_copy(ctx, lb_map, ub_map, o, verdict, rounds, nnz_updates);
+  }
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_lb, lb, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_ub, ub, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -709,10 +733,10 @@ static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   CU(cudaMemcpyAsync(lb, ctx->d_lb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(ub, ctx->d_ub, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  SingleCtrl ctrl;
-  CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, sizeof(SingleCtrl), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  const SingleCtrl ctrl = *ctx->h_single;      // written by the kernel's last block
+  ctx->ctrl_clean = true;
   if (verdict) *verdict = ctrl.verdict();
   if (rounds) *rounds = ctrl.status[1];
   if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
@@ -720,6 +744,36 @@ static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_
   ctx->stats.h2d_ms += elapsed(ctx->ev[0], ctx->ev[1]);
   ctx->stats.kernel_ms += elapsed(ctx->ev[1], ctx->ev[2]);
   ctx->stats.d2h_ms += elapsed(ctx->ev[2], ctx->ev[3]);
+  return MNTR_OK;
+}
+
+// Device pointer of a PINNED (page-locked, mapped) host buffer, or nullptr for pageable memory.
+static double *mapped_host_ptr(const double *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return nullptr;
+  return static_cast<double *>(a.devicePointer);
+}
+
+// Single box whose host buffers are pinned: the fixpoint kernel reads the incoming bounds straight from host memory
+// (one coalesced pass over PCIe in its first phase) and writes back ONLY the bounds that moved, so the call is one
+// launch plus the 128-byte control block -- no staging copies of the whole box in either direction.
+static int tighten_single_zero_copy(mntr_gpu_ctx *ctx, double *lb_map, double *ub_map, const mntr_gpu_options &o,
+                                    int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
+{
+  int rc;
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if ((rc = run_single_dev(ctx, lb_map, ub_map, o))) return rc;
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const SingleCtrl ctrl = *ctx->h_single;      // written by the kernel's last block
+  ctx->ctrl_clean = true;
+  if (verdict) *verdict = ctrl.verdict();
+  if (rounds) *rounds = ctrl.status[1];
+  if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
+  account_single(ctx, ctrl);
+  ctx->stats.kernel_ms += elapsed(ctx->ev[1], ctx->ev[2]);       // includes the PCIe reads / writes of the box
   return MNTR_OK;
 }
 
@@ -745,9 +799,9 @@ int mntr_gpu_tighten_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_de
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   if ((rc = run_single_dev(ctx, lb_dev, ub_dev, o))) return rc;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-  SingleCtrl ctrl;
-  CU(cudaMemcpyAsync(&ctrl, ctx->d_ctrl, sizeof(SingleCtrl), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  const SingleCtrl ctrl = *ctx->h_single;      // written by the kernel's last block
+  ctx->ctrl_clean = true;
   if (verdict) *verdict = ctrl.verdict();
   if (rounds) *rounds = ctrl.status[1];
   if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
