@@ -140,6 +140,117 @@ struct TapeView {
   int nn;
 };
 
+// One warp's staging area for a BATCH of consecutive constraints.  All lanes of a warp walk the same tapes, so the
+// nodes, linear parts and bounds of up to 31 constraints are fetched ONCE, cooperatively (coalesced requests), the
+// interpreter reads them from shared memory, and the {lb,ub} segments of every variable the batch touches are
+// prefetched into L2 before the first constraint is evaluated: a constraint costs L2 hits instead of a chain of
+// DRAM round trips.
+constexpr int kStageNodes = 128;
+constexpr int kStageChild = 64;
+constexpr int kStageLin = 64;
+struct BatchStage {
+  double cn[kStageNodes];
+  double lin_val[kStageLin];
+  double c_lb[32], c_ub[32];
+  int32_t a0[kStageNodes], a1[kStageNodes];
+  int32_t child[kStageChild];
+  int32_t lin_col[kStageLin];
+  int32_t tape_off[33], lin_off[33];     // offsets of the batch's constraints inside the staged arrays
+  uint8_t op[kStageNodes];
+};
+
+// a staged constraint: tape view (pointers into the BatchStage), linear part, bounds
+struct ConsView {
+  TapeView t;
+  const int32_t *lin_col; const double *lin_val;   // [n_lin]
+  int n_lin;
+  int n_lead_vars;          // leading OpVar nodes (the tape starts with the variable nodes, ascending id)
+  double c_lb, c_ub;
+};
+
+struct BatchInfo {
+  int n;                    // constraints staged (1..32)
+  const int32_t *child;     // child list base to index with the tape's absolute offsets
+  const int32_t *lin_col; const double *lin_val; int lin_base;   // linear terms: staged arrays (lin_base = first term)
+};
+
+__device__ __forceinline__ void prefetch_segment(const double2 *tile_base, int64_t ld, int var)
+{
+  const char *p = reinterpret_cast<const char *>(tile_base + (int64_t)var * ld);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128 * k));
+}
+
+// Stages constraints c0, c0+1, ... (at most 31, at most c_end - c0, as many as fit the staging arrays) and prefetches
+// their variables' segments.  Convergent.
+__device__ __forceinline__ BatchInfo stage_batch(const NlDev &N, int c0, int c_end, BatchStage &S, const double2 *tile_base,
+                                                 int64_t ld, int lane)
+{
+  const int avail = min(31, c_end - c0);               // lane `avail` carries the end markers
+  // heads: lane l holds the offsets of constraint c0 + l (lane `avail` the end markers)
+  int tp = 0, lp = 0;
+  if (lane <= avail) { tp = __ldg(N.tape_ptr + c0 + lane); lp = __ldg(N.lin_ptr + c0 + lane); }
+  double clb = 0.0, cub = 0.0;
+  if (lane < avail) { clb = __ldg(N.c_lb + c0 + lane); cub = __ldg(N.c_ub + c0 + lane); }
+  const int tp0 = __shfl_sync(0xffffffffu, tp, 0), lp0 = __shfl_sync(0xffffffffu, lp, 0);
+  // the largest k with nodes(c0..c0+k) and lin terms within capacity; a single constraint always fits its nodes
+  // (kMaxTape <= kStageNodes); its linear part may not, then it is read from global memory
+  const bool fits = lane >= 1 && lane <= avail && tp - tp0 <= kStageNodes && lp - lp0 <= kStageLin;
+  const unsigned fm = __ballot_sync(0xffffffffu, fits);
+  const unsigned gaps = ~(fm | 1u);
+  int n = (fm & 2u) ? (gaps ? __ffs(gaps) - 2 : 31) : 1;     // length of the run of set bits starting at bit 1
+  if (n > avail) n = avail;
+  const int tp_end = __shfl_sync(0xffffffffu, tp, n), lp_end = __shfl_sync(0xffffffffu, lp, n);
+  const int nn = tp_end - tp0, nl = lp_end - lp0;
+  __syncwarp();                                        // the previous batch has been consumed
+  if (lane <= n) { S.tape_off[lane] = tp - tp0; S.lin_off[lane] = lp - lp0; }
+  if (lane < n) { S.c_lb[lane] = clb; S.c_ub[lane] = cub; }
+  int clo = 0x7fffffff, chi = 0;
+  for (int i = lane; i < nn; i += 32) {
+    const int op = __ldg(N.op + tp0 + i);
+    const int x0 = __ldg(N.arg0 + tp0 + i), x1 = __ldg(N.arg1 + tp0 + i);
+    S.op[i] = (uint8_t)op; S.a0[i] = x0; S.a1[i] = x1; S.cn[i] = __ldg(N.cnst + tp0 + i);
+    if (op == OpSumList) { clo = min(clo, x0); chi = max(chi, x1); }
+    if (op == OpVar) prefetch_segment(tile_base, ld, x0);
+  }
+  BatchInfo B;
+  B.n = n;
+  B.lin_col = N.lin_col; B.lin_val = N.lin_val; B.lin_base = 0;       // global fallback: absolute offsets
+  if (nl <= kStageLin) {
+    for (int q = lane; q < nl; q += 32) {
+      const int col = __ldg(N.lin_col + lp0 + q);
+      S.lin_col[q] = col; S.lin_val[q] = __ldg(N.lin_val + lp0 + q);
+      prefetch_segment(tile_base, ld, col);
+    }
+    B.lin_col = S.lin_col; B.lin_val = S.lin_val; B.lin_base = lp0;
+  }
+  clo = __reduce_min_sync(0xffffffffu, clo); chi = __reduce_max_sync(0xffffffffu, chi);
+  B.child = N.child;
+  if (chi > clo && chi - clo <= kStageChild) {         // the SumList child lists of consecutive constraints are contiguous
+    for (int k = lane; k < chi - clo; k += 32) S.child[k] = __ldg(N.child + clo + k);
+    B.child = S.child - clo;
+  }
+  __syncwarp();
+  return B;
+}
+
+// constraint k of the staged batch (k < B.n); c = its global index.  Warp-uniform.
+__device__ __forceinline__ ConsView batch_constraint(const NlDev &N, const BatchStage &S, const BatchInfo &B, int k, int c)
+{
+  ConsView V;
+  const int o = S.tape_off[k];
+  V.t.op = S.op + o; V.t.a0 = S.a0 + o; V.t.a1 = S.a1 + o; V.t.cn = S.cn + o; V.t.child = B.child;
+  V.t.nn = S.tape_off[k + 1] - o;
+  V.n_lin = S.lin_off[k + 1] - S.lin_off[k];
+  if (B.lin_col == S.lin_col) { V.lin_col = S.lin_col + S.lin_off[k]; V.lin_val = S.lin_val + S.lin_off[k]; }
+  else { const int q0 = __ldg(N.lin_ptr + c); V.lin_col = N.lin_col + q0; V.lin_val = N.lin_val + q0; }
+  V.c_lb = S.c_lb[k]; V.c_ub = S.c_ub[k];
+  int nv = 0;
+  while (nv < V.t.nn && V.t.op[nv] == OpVar) ++nv;
+  V.n_lead_vars = nv;
+  return V;
+}
+
 // CNode::updateBnd for node i.  Constants: OpNum keeps [d,d] (CNode::setVal :1693-1699), OpInt keeps the
 // constructor's (-inf,inf) (CGraph.cpp:1238-1245); neither gets the 1e25 clamp (they are not in vq_/dq_).
 template <class R>
@@ -333,42 +444,60 @@ __device__ __forceinline__ void node_reverse(const TapeView &t, int i, double *n
 
 __device__ __forceinline__ bool is_leaf_op(int op) { return op == OpVar || op == OpNum || op == OpInt; }
 
-__device__ __forceinline__ TapeView open_tape(const NlDev &N, int c)
-{
-  const int b = __ldg(N.tape_ptr + c);
-  TapeView t;
-  t.op = N.op + b; t.a0 = N.arg0 + b; t.a1 = N.arg1 + b; t.cn = N.cnst + b; t.child = N.child;
-  t.nn = __ldg(N.tape_ptr + c + 1) - b;
-  return t;
-}
-
 // LinearFunction::computeBounds of the constraint's linear part (LinearFunction.cpp:178-195)
 template <class R>
-__device__ __forceinline__ void lin_part_bounds(const NlDev &N, int c, const double2 *bx, int64_t ld, double &lo,
-                                                double &up)
+__device__ __forceinline__ void lin_part_bounds(const ConsView &V, const double2 *bx, int64_t ld, double &lo, double &up)
 {
   lo = 0.0; up = 0.0;
-  for (int q = __ldg(N.lin_ptr + c); q < __ldg(N.lin_ptr + c + 1); ++q) {
-    const double a = __ldg(N.lin_val + q);
-    const double2 b = bx[(int64_t)__ldg(N.lin_col + q) * ld];
-    if (a > 0) { lo = R::add_lo(lo, R::mul_lo(a, b.x)); up = R::add_hi(up, R::mul_hi(a, b.y)); }
-    else       { lo = R::add_lo(lo, R::mul_lo(a, b.y)); up = R::add_hi(up, R::mul_hi(a, b.x)); }
+  for (int q0 = 0; q0 < V.n_lin; q0 += 2) {             // two gathers in flight
+    const double a0 = V.lin_val[q0];
+    const double2 b0 = bx[(int64_t)V.lin_col[q0] * ld];
+    const bool two = q0 + 1 < V.n_lin;
+    const double a1 = two ? V.lin_val[q0 + 1] : 0.0;
+    const double2 b1 = two ? bx[(int64_t)V.lin_col[q0 + 1] * ld] : make_double2(0.0, 0.0);
+    if (a0 > 0) { lo = R::add_lo(lo, R::mul_lo(a0, b0.x)); up = R::add_hi(up, R::mul_hi(a0, b0.y)); }
+    else        { lo = R::add_lo(lo, R::mul_lo(a0, b0.y)); up = R::add_hi(up, R::mul_hi(a0, b0.x)); }
+    if (two) {
+      if (a1 > 0) { lo = R::add_lo(lo, R::mul_lo(a1, b1.x)); up = R::add_hi(up, R::mul_hi(a1, b1.y)); }
+      else        { lo = R::add_lo(lo, R::mul_lo(a1, b1.y)); up = R::add_hi(up, R::mul_hi(a1, b1.x)); }
+    }
   }
+}
+
+// CGraph::computeBounds forward sweep.  The leading variable nodes are gathered four at a time (independent
+// requests in flight together) before the operator nodes are interpreted.
+template <class R>
+__device__ __forceinline__ void tape_forward(const ConsView &V, double *nlb, double *nub, const double2 *bx, int64_t ld,
+                                             int &error)
+{
+  const TapeView &t = V.t;
+  for (int i0 = 0; i0 < V.n_lead_vars; i0 += 4) {
+    double2 b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (i0 + u < V.n_lead_vars) b[u] = bx[(int64_t)t.a0[i0 + u] * ld];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < V.n_lead_vars) {
+        nlb[i0 + u] = (b[u].x < -kMinfty) ? -INFINITY : b[u].x;        // the clamp of updateBnd, :1898-1903
+        nub[i0 + u] = (b[u].y > kMinfty) ? INFINITY : b[u].y;
+      }
+  }
+  for (int i = V.n_lead_vars; i < t.nn; ++i) node_forward<R>(t, i, nlb, nub, bx, ld, error);
 }
 
 // NlPresHandler::chkRed_ for one constraint (NlPresHandler.cpp:101-208, nlf branch):
 // returns 0 ok, 3 infeasible, 4 evaluation error
 template <class R>
-__device__ __forceinline__ int nl_chk_red(const NlDev &N, int c, const double2 *bx, int64_t ld, double *nlb, double *nub)
+__device__ __forceinline__ int nl_chk_red(const ConsView &V, const double2 *bx, int64_t ld, double *nlb, double *nub)
 {
-  const TapeView t = open_tape(N, c);
+  const TapeView &t = V.t;
   int error = 0;
-  for (int i = 0; i < t.nn; ++i) node_forward<R>(t, i, nlb, nub, bx, ld, error);
+  tape_forward<R>(V, nlb, nub, bx, ld, error);
   if (error != 0) return 4;
   double lfl, lfu;
-  lin_part_bounds<R>(N, c, bx, ld, lfl, lfu);
+  lin_part_bounds<R>(V, bx, ld, lfl, lfu);
   const double impl_lb = R::add_lo(nlb[t.nn - 1], lfl), impl_ub = R::add_hi(nub[t.nn - 1], lfu);
-  if (impl_ub + 1e-6 < __ldg(N.c_lb + c) || impl_lb - 1e-6 > __ldg(N.c_ub + c)) return 3;
+  if (impl_ub + 1e-6 < V.c_lb || impl_lb - 1e-6 > V.c_ub) return 3;
   return 0;
 }
 
@@ -376,16 +505,16 @@ __device__ __forceinline__ int nl_chk_red(const NlDev &N, int c, const double2 *
 // CGraph::varBoundMods + in-place application of the mods.  returns 0 ok, 3 infeasible, 4 error;
 // n_mods receives the number of bound changes.
 template <class R>
-__device__ __forceinline__ int nl_var_bound_mods(const NlDev &N, int c, double2 *bx, int64_t ld, double *nlb,
+__device__ __forceinline__ int nl_var_bound_mods(const ConsView &V, double2 *bx, int64_t ld, double *nlb,
                                                  double *nub, int &n_mods, unsigned &moved_int)
 {
   const double bslack = 1e-5, bslack10 = 1e-4;
-  const TapeView t = open_tape(N, c);
+  const TapeView &t = V.t;
   double lfl, lfu;
-  lin_part_bounds<R>(N, c, bx, ld, lfl, lfu);
-  const double ub_in = R::sub_hi(__ldg(N.c_ub + c), lfl), lb_in = R::sub_lo(__ldg(N.c_lb + c), lfu);
+  lin_part_bounds<R>(V, bx, ld, lfl, lfu);
+  const double ub_in = R::sub_hi(V.c_ub, lfl), lb_in = R::sub_lo(V.c_lb, lfu);
   int error = 0;
-  for (int i = 0; i < t.nn; ++i) node_forward<R>(t, i, nlb, nub, bx, ld, error);
+  tape_forward<R>(V, nlb, nub, bx, ld, error);
   if (error > 0) return 4;
   const int o = t.nn - 1;
   nlb[o] = fmax(lb_in, nlb[o]); nub[o] = fmin(ub_in, nub[o]);

@@ -490,7 +490,7 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
           if (lane == t) __stcg(flags + q, raw & ~proc);     // c_ptr->setBFlag(false), :513
           stage_short(P, info.x, info.y, st, lane);
           const bool mine = (proc >> lane) & 1u;
-          if (info.y <= kSegEntries) {
+          if (st.seg != nullptr && info.y <= kSegEntries) {
             // TMA: one 512-byte bulk copy per term brings the {lb,ub} of that variable for the tile's 32 boxes into
             // shared memory; all copies of the row are in flight at once and land on the warp's mbarrier
             if (lane == 0) mbar_expect_tx(st.bar, (uint32_t)(info.y * kSegBytes));
@@ -597,11 +597,12 @@ __device__ __noinline__ void fix_obj_bins(const LinDev &P, double2 *bx, int64_t 
 
 template <class R>
 __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N, double2 *bx, int64_t ld, TileShared &sh,
-                                                bool active, bool &any_change)
+                                                bool active, bool &any_change, BatchStage &TS)
 {
   const int lane = threadIdx.x & 31;
   const TileTeam team = make_team();
   const int warp = team.gwarp;
+  const double2 *tile_base = bx - lane;
   double nlb[kMaxTape], nub[kMaxTape];
   if (warp == 0) sh.changed[lane] = 1;
   team.sync();
@@ -616,23 +617,40 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
     if (run) ++my_rounds;
     team.sync();
     // chkRed_: read-only, every constraint against the box of the sweep start
-    for (int c = warp; c < N.n_cons; c += team.n_warps) {
-      if (run && sh.verdict[lane] == 0) {
-        const int st = nl_chk_red<R>(N, c, bx, ld, nlb, nub);
-        if (st != 0) sh.verdict[lane] = st;
+    {
+      // each warp takes a contiguous range of constraints, in staged batches
+      const int per = (N.n_cons + team.n_warps - 1) / team.n_warps;
+      const int c_lo = min(N.n_cons, warp * per), c_hi = min(N.n_cons, c_lo + per);
+      for (int c0 = c_lo; c0 < c_hi;) {
+        const BatchInfo B = stage_batch(N, c0, c_hi, TS, tile_base, ld, lane);
+        for (int k = 0; k < B.n; ++k) {
+          const ConsView V = batch_constraint(N, TS, B, k, c0 + k);
+          if (run && sh.verdict[lane] == 0) {
+            const int st = nl_chk_red<R>(V, bx, ld, nlb, nub);
+            if (st != 0) sh.verdict[lane] = st;
+          }
+        }
+        c0 += B.n;
       }
     }
     team.sync();
     // varBndsFromCons_: constraints of one level touch disjoint variables
     for (int lev = 0; lev < N.n_levels; ++lev) {
       const int qb = __ldg(N.level_ptr + lev), qe = __ldg(N.level_ptr + lev + 1);
-      for (int c = qb + warp; c < qe; c += team.n_warps) {
-        if (run && sh.verdict[lane] == 0) {
-          int n_mods = 0; unsigned dummy = 0;
-          const int st = nl_var_bound_mods<R>(N, c, bx, ld, nlb, nub, n_mods, dummy);
-          if (st != 0) sh.verdict[lane] = st;
-          else if (n_mods > 0) sh.changed[lane] = 1;
+      const int per = (qe - qb + team.n_warps - 1) / team.n_warps;
+      const int c_lo = min(qe, qb + warp * per), c_hi = min(qe, c_lo + per);
+      for (int c0 = c_lo; c0 < c_hi;) {
+        const BatchInfo B = stage_batch(N, c0, c_hi, TS, tile_base, ld, lane);
+        for (int k = 0; k < B.n; ++k) {
+          const ConsView V = batch_constraint(N, TS, B, k, c0 + k);
+          if (run && sh.verdict[lane] == 0) {
+            int n_mods = 0; unsigned dummy = 0;
+            const int st = nl_var_bound_mods<R>(V, bx, ld, nlb, nub, n_mods, dummy);
+            if (st != 0) sh.verdict[lane] = st;
+            else if (n_mods > 0) sh.changed[lane] = 1;
+          }
         }
+        c0 += B.n;
       }
       team.sync();
     }
@@ -649,17 +667,24 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
 // One PCBProcessor::presolveNode_ pass per box (loop_mode 1): LinearHandler::presolveNode, then -- unless
 // the box is already infeasible -- NlPresHandler::presolveNode (PCBProcessor.cpp:134-175); or (loop_mode 0)
 // that pair repeated until neither handler changes a bound.
-template <class R>
+// Two instantiations.  HAS_NL = false, the pure linear one, stages the rows' {lb,ub} segments with TMA (96 KB of
+// dynamic shared memory per CTA) and carries no tape interpreter.  HAS_NL = true gathers the linear rows' bounds
+// directly (use_tma == 0: no dynamic shared memory), which leaves the L1 to the interpreter's per-thread node
+// intervals, and stages the tapes instead.
+template <class R, bool HAS_NL>
 __global__ void __launch_bounds__(kBatchThreads, 2)
 fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int max_rounds, int lin_enabled,
-                            int nl_enabled)
+                            int nl_enabled_arg, int use_tma)
 {
+  const int nl_enabled = HAS_NL ? nl_enabled_arg : 0;
   __shared__ double s_val[kBatchWarps][32];
   __shared__ int s_col[kBatchWarps][32];
   __shared__ __align__(8) uint64_t s_bar[kBatchWarps];
+
   extern __shared__ __align__(128) unsigned char s_seg[];       // [kBatchWarps][kSegEntries][32] double2: TMA destination
   const int wl = threadIdx.x >> 5;
-  const RowStage st{s_val[wl], s_col[wl], reinterpret_cast<double2 *>(s_seg) + (size_t)wl * kSegEntries * kTile, &s_bar[wl]};
+  const RowStage st{s_val[wl], s_col[wl],
+                    use_tma ? reinterpret_cast<double2 *>(s_seg) + (size_t)wl * kSegEntries * kTile : nullptr, &s_bar[wl]};
   if ((threadIdx.x & 31) == 0) mbar_init(st.bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -694,7 +719,10 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
     if (lin_enabled)
       my_rounds += lin_tile_presolve<R>(P, bx, ld, st, flags, varflag, sh, active, loop_mode, max_rounds, bad_row,
                                         my_nnz, lin_changed, seg_phase);
-    if (nl_enabled) my_rounds += nl_tile_presolve<R>(P, N, bx, ld, sh, active, nl_changed);
+    if constexpr (HAS_NL) {
+      // the NL instantiation uses the dynamic shared memory for the tape batches (no TMA segments: use_tma == 0)
+      if (nl_enabled) my_rounds += nl_tile_presolve<R>(P, N, bx, ld, sh, active, nl_changed, reinterpret_cast<BatchStage *>(s_seg)[wl]);
+    }
     // fixpoint mode with both handlers: go round again while the nonlinear sweeps still move bounds
     const bool again = (loop_mode == 0) && lin_enabled && nl_enabled && nl_changed && sh.verdict[lane] == 0 &&
                        (max_rounds <= 0 || my_rounds < max_rounds) && outer < 50;
@@ -809,11 +837,19 @@ cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSegSmemBytes);
+  if (nl_enabled) {
+    cfg.dynamicSmemBytes = kBatchWarps * sizeof(BatchStage);
+    cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, true>, P, nl, io, loop_mode, max_rounds, lin_enabled,
+                              nl_enabled, 0);
+  }
+  cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSegSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R>, P, nl, io, loop_mode, max_rounds, lin_enabled,
-                            nl_enabled);
+  return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, false>, P, nl, io, loop_mode, max_rounds, lin_enabled,
+                            nl_enabled, 1);
 }
 }  // namespace
 

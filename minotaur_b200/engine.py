@@ -239,8 +239,8 @@ class GpuBoundEngine:
         return lb, ub
 
     def tighten_dev(self, n_boxes: int, boxes_dev_ptr: int, verdict_ptr: int, rounds_ptr: int, nnz_ptr: int,
-                    rounding=ROUND_DIRECTED, loop=LOOP_FIXPOINT, max_rounds=0):
-        o = GpuOptions(rounding, ORDER_REFERENCE, loop, max_rounds)
+                    rounding=ROUND_DIRECTED, loop=LOOP_FIXPOINT, max_rounds=0, handlers=HANDLERS_ALL):
+        o = GpuOptions(rounding, ORDER_REFERENCE, loop, max_rounds, handlers)
         self._check(self.L.mntr_gpu_tighten_dev(self.h, n_boxes, C.c_void_p(boxes_dev_ptr), C.byref(o),
                                                 C.c_void_p(verdict_ptr), C.c_void_p(rounds_ptr),
                                                 C.c_void_p(nnz_ptr)), "tighten_dev")
