@@ -58,7 +58,7 @@ cudaError_t launch_apply_deltas(const long long *delta_ptr, const int32_t *delta
 cudaError_t launch_count_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n,
                               int32_t n_boxes, long long *mod_count, cudaStream_t stream);
 cudaError_t launch_emit_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n,
-                             int32_t n_boxes, const long long *mod_ptr, long long cap, int32_t *mod_var,
-                             uint8_t *mod_is_upper, double *mod_val, cudaStream_t stream);
+                             int32_t n_boxes, const long long *mod_ptr, long long *cursor, long long cap,
+                             int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val, cudaStream_t stream);
 
 }  // namespace mntr

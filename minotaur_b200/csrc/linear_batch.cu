@@ -818,6 +818,39 @@ __global__ void apply_deltas_kernel(const long long *__restrict__ dptr, const in
   }
 }
 
+// mods of box b = every (variable, side) whose bound differs from the box's initial bound.  A block takes a strip
+// of variables for one tile of 32 boxes (lane = box: coalesced 512-byte segments).
+__global__ void count_mods_kernel(const double2 *__restrict__ boxes, const double2 *__restrict__ boxes0, int64_t ld,
+                                  int n, int n_boxes, long long *mod_count)
+{
+  const int b = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int j0 = blockIdx.x * 256 + (threadIdx.x >> 5), j1 = min(n, (blockIdx.x + 1) * 256);
+  int cnt = 0;
+  if (b < n_boxes)
+    for (int j = j0; j < j1; j += blockDim.x >> 5) {
+      const double2 v = boxes[(int64_t)j * ld + b], o = boxes0[(int64_t)j * ld + b];
+      cnt += (v.x != o.x) + (v.y != o.y);
+    }
+  if (cnt) atomicAdd(reinterpret_cast<unsigned long long *>(mod_count + b), (unsigned long long)cnt);
+}
+
+__global__ void emit_mods_kernel(const double2 *__restrict__ boxes, const double2 *__restrict__ boxes0, int64_t ld,
+                                 int n, int n_boxes, const long long *__restrict__ mod_ptr, long long *cursor,
+                                 long long cap, int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val)
+{
+  const int b = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int j0 = blockIdx.x * 256 + (threadIdx.x >> 5), j1 = min(n, (blockIdx.x + 1) * 256);
+  if (b >= n_boxes) return;
+  for (int j = j0; j < j1; j += blockDim.x >> 5) {
+    const double2 v = boxes[(int64_t)j * ld + b], o = boxes0[(int64_t)j * ld + b];
+    const int k = (v.x != o.x) + (v.y != o.y);
+    if (k == 0) continue;
+    long long at = mod_ptr[b] + (long long)atomicAdd(reinterpret_cast<unsigned long long *>(cursor + b), (unsigned long long)k);
+    if (v.x != o.x) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 0; mod_val[at] = v.x; } ++at; }
+    if (v.y != o.y) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 1; mod_val[at] = v.y; } }
+  }
+}
+
 }  // namespace
 
 namespace {
@@ -903,6 +936,26 @@ cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub,
   (void)n_boxes;
   if (n <= 0) return cudaSuccess;
   boxes_from_root_kernel<<<148 * 8, 256, 0, stream>>>(root_lb, root_ub, n, boxes, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_count_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n, int32_t n_boxes,
+                              long long *mod_count, cudaStream_t stream)
+{
+  if (n <= 0 || n_boxes <= 0) return cudaSuccess;
+  dim3 grid((n + 255) / 256, (n_boxes + 31) / 32);
+  count_mods_kernel<<<grid, 256, 0, stream>>>(boxes, boxes0, ld, n, n_boxes, mod_count);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_emit_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n, int32_t n_boxes,
+                             const long long *mod_ptr, long long *cursor, long long cap, int32_t *mod_var,
+                             uint8_t *mod_is_upper, double *mod_val, cudaStream_t stream)
+{
+  if (n <= 0 || n_boxes <= 0) return cudaSuccess;
+  dim3 grid((n + 255) / 256, (n_boxes + 31) / 32);
+  emit_mods_kernel<<<grid, 256, 0, stream>>>(boxes, boxes0, ld, n, n_boxes, mod_ptr, cursor, cap, mod_var, mod_is_upper,
+                                             mod_val);
   return cudaGetLastError();
 }
 

@@ -960,12 +960,142 @@ int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
   return MNTR_OK;
 }
 
-int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t, const double *, const double *, const int64_t *,
-                           const int32_t *, const uint8_t *, const double *, const mntr_gpu_options *, int32_t *,
-                           int32_t *, int64_t *, int32_t *, uint8_t *, double *, int64_t, int64_t *)
+// Node batch given as branching deltas on a common root box; results as the VarBoundMod tuples to emit.
+int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *root_lb, const double *root_ub,
+                           const int64_t *delta_ptr, const int32_t *delta_var, const uint8_t *delta_is_upper,
+                           const double *delta_val, const mntr_gpu_options *opts, int32_t *verdict, int32_t *rounds,
+                           int64_t *mod_ptr, int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val, int64_t mod_cap,
+                           int64_t *n_mods_out)
 {
   if (!ctx) return MNTR_E_ARG;
-  return fail(ctx, MNTR_E_UNSUPPORTED, "tighten_nodes: not implemented yet");
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "tighten_nodes: no problem loaded");
+  if (n_boxes <= 0 || !root_lb || !root_ub || !delta_ptr || !mod_ptr || mod_cap < 0 ||
+      (mod_cap > 0 && (!mod_var || !mod_is_upper || !mod_val)))
+    return fail(ctx, MNTR_E_ARG, "tighten_nodes: bad argument");
+  const int64_t n_delta = delta_ptr[n_boxes];
+  if (delta_ptr[0] != 0 || n_delta < 0 || (n_delta > 0 && (!delta_var || !delta_is_upper || !delta_val)))
+    return fail(ctx, MNTR_E_ARG, "tighten_nodes: bad delta lists");
+  for (int32_t b = 0; b < n_boxes; ++b)
+    if (delta_ptr[b + 1] < delta_ptr[b]) return fail(ctx, MNTR_E_ARG, "tighten_nodes: delta_ptr not monotone at box %d", b);
+  for (int64_t q = 0; q < n_delta; ++q)
+    if (delta_var[q] < 0 || delta_var[q] >= ctx->n) return fail(ctx, MNTR_E_ARG, "tighten_nodes: delta variable %d out of range", delta_var[q]);
+  CU(cudaSetDevice(ctx->device));
+  mntr_gpu_options o = resolve_opts(opts, n_boxes);
+  o.order = MNTR_ORDER_REFERENCE;      // a node batch always runs the reference-order kernel
+  if (o.rounding != MNTR_ROUND_DIRECTED && o.rounding != MNTR_ROUND_NEAREST) return fail(ctx, MNTR_E_ARG, "tighten_nodes: bad rounding");
+  if (o.loop != MNTR_LOOP_FIXPOINT && o.loop != MNTR_LOOP_SIMPLEPRESOLVE) return fail(ctx, MNTR_E_ARG, "tighten_nodes: bad loop mode");
+  if (o.handlers < 0 || o.handlers > 2) return fail(ctx, MNTR_E_ARG, "tighten_nodes: bad handlers");
+  ctx->stats = mntr_gpu_stats{};
+  const int32_t n = ctx->n;
+  int rc = ensure_batch(ctx, n_boxes, true);
+  if (rc) return rc;
+  const int64_t ld = mntr_gpu_box_ld(n_boxes);
+
+  // device scratch of this call: the initial boxes, root, deltas, mod counts / offsets / tuples
+  std::vector<void *> scratch;
+  auto dalloc = [&](void **p, size_t bytes) -> int {
+    if (cudaMalloc(p, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+      (void)cudaGetLastError(); free_all(scratch);
+      return fail(ctx, MNTR_E_NOMEM, "tighten_nodes: out of device memory");
+    }
+    scratch.push_back(*p);
+    return MNTR_OK;
+  };
+  double2 *boxes0 = nullptr; double *d_rl = nullptr, *d_ru = nullptr, *d_dval = nullptr, *d_mval = nullptr;
+  long long *d_dptr = nullptr, *d_cnt = nullptr, *d_mptr = nullptr, *d_cur = nullptr;
+  int32_t *d_dvar = nullptr, *d_mvar = nullptr; uint8_t *d_dup = nullptr, *d_mup = nullptr;
+  if ((rc = dalloc((void **)&boxes0, sizeof(double2) * (size_t)n * (size_t)ld))) return rc;
+  if ((rc = dalloc((void **)&d_rl, sizeof(double) * (size_t)n))) return rc;
+  if ((rc = dalloc((void **)&d_ru, sizeof(double) * (size_t)n))) return rc;
+  if ((rc = dalloc((void **)&d_dptr, sizeof(long long) * ((size_t)n_boxes + 1)))) return rc;
+  if ((rc = dalloc((void **)&d_dvar, sizeof(int32_t) * (size_t)n_delta))) return rc;
+  if ((rc = dalloc((void **)&d_dup, (size_t)n_delta))) return rc;
+  if ((rc = dalloc((void **)&d_dval, sizeof(double) * (size_t)n_delta))) return rc;
+  if ((rc = dalloc((void **)&d_cnt, sizeof(long long) * (size_t)n_boxes))) return rc;
+  if ((rc = dalloc((void **)&d_mptr, sizeof(long long) * ((size_t)n_boxes + 1)))) return rc;
+  if ((rc = dalloc((void **)&d_cur, sizeof(long long) * (size_t)n_boxes))) return rc;
+  if ((rc = dalloc((void **)&d_mvar, sizeof(int32_t) * (size_t)mod_cap))) return rc;
+  if ((rc = dalloc((void **)&d_mup, (size_t)mod_cap))) return rc;
+  if ((rc = dalloc((void **)&d_mval, sizeof(double) * (size_t)mod_cap))) return rc;
+  auto done = [&](int code) { free_all(scratch); return code; };
+#define CUN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_all(scratch); return fail(ctx, MNTR_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  static_assert(sizeof(long long) == sizeof(int64_t), "delta_ptr / mod_ptr are copied as long long");
+  cudaStream_t s = ctx->stream;
+  CUN(cudaEventRecord(ctx->ev[0], s));
+  CUN(cudaMemcpyAsync(d_rl, root_lb, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CUN(cudaMemcpyAsync(d_ru, root_ub, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CUN(cudaMemcpyAsync(d_dptr, delta_ptr, sizeof(long long) * ((size_t)n_boxes + 1), cudaMemcpyHostToDevice, s));
+  if (n_delta > 0) {
+    CUN(cudaMemcpyAsync(d_dvar, delta_var, sizeof(int32_t) * (size_t)n_delta, cudaMemcpyHostToDevice, s));
+    CUN(cudaMemcpyAsync(d_dup, delta_is_upper, (size_t)n_delta, cudaMemcpyHostToDevice, s));
+    CUN(cudaMemcpyAsync(d_dval, delta_val, sizeof(double) * (size_t)n_delta, cudaMemcpyHostToDevice, s));
+  }
+  CUN(launch_boxes_from_root(d_rl, d_ru, n, n_boxes, ctx->d_boxes, ld, s));
+  CUN(launch_apply_deltas(d_dptr, d_dvar, d_dup, d_dval, n_boxes, ctx->d_boxes, ld, s));
+  CUN(cudaMemcpyAsync(boxes0, ctx->d_boxes, sizeof(double2) * (size_t)n * (size_t)ld, cudaMemcpyDeviceToDevice, s));
+  BatchIo io;
+  io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
+  io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb;
+  CUN(cudaEventRecord(ctx->ev[1], s));
+  CUN(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
+                             o.loop, o.max_rounds, o.handlers != MNTR_HANDLERS_NONLINEAR,
+                             (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR) ? 1 : 0, ctx->sm_count, s));
+  CUN(cudaEventRecord(ctx->ev[2], s));
+  // mods: count per box, offsets on the host (n_boxes numbers), then emit
+  CUN(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * (size_t)n_boxes, s));
+  CUN(cudaMemsetAsync(d_cur, 0, sizeof(long long) * (size_t)n_boxes, s));
+  CUN(launch_count_mods(ctx->d_boxes, boxes0, ld, n, n_boxes, d_cnt, s));
+  std::vector<long long> cnt((size_t)n_boxes), ptr((size_t)n_boxes + 1, 0);
+  std::vector<int32_t> hv((size_t)n_boxes), hr((size_t)n_boxes);
+  CUN(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(long long) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  CUN(cudaMemcpyAsync(hv.data(), ctx->d_verdict, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  CUN(cudaMemcpyAsync(hr.data(), ctx->d_rounds, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  CUN(cudaStreamSynchronize(s));
+  // an infeasible box reports no mods (the node is pruned; its box is not meaningful)
+  for (int32_t b = 0; b < n_boxes; ++b) ptr[(size_t)b + 1] = ptr[(size_t)b] + (hv[(size_t)b] == MNTR_FEASIBLE ? cnt[(size_t)b] : 0);
+  const long long total = ptr[(size_t)n_boxes];
+  if (n_mods_out) *n_mods_out = (int64_t)total;
+  for (int32_t b = 0; b <= n_boxes; ++b) mod_ptr[b] = (int64_t)ptr[(size_t)b];
+  if (verdict) memcpy(verdict, hv.data(), sizeof(int32_t) * (size_t)n_boxes);
+  if (rounds) memcpy(rounds, hr.data(), sizeof(int32_t) * (size_t)n_boxes);
+  if (total > 0 && total <= mod_cap) {
+    // boxes that are infeasible get an empty range [ptr, ptr): give them a cursor that is already past any capacity
+    std::vector<long long> cur((size_t)n_boxes, 0);
+    for (int32_t b = 0; b < n_boxes; ++b) if (hv[(size_t)b] != MNTR_FEASIBLE) cur[(size_t)b] = (long long)1 << 60;
+    CUN(cudaMemcpyAsync(d_cur, cur.data(), sizeof(long long) * (size_t)n_boxes, cudaMemcpyHostToDevice, s));
+    CUN(cudaMemcpyAsync(d_mptr, ptr.data(), sizeof(long long) * ((size_t)n_boxes + 1), cudaMemcpyHostToDevice, s));
+    CUN(launch_emit_mods(ctx->d_boxes, boxes0, ld, n, n_boxes, d_mptr, d_cur, (long long)mod_cap, d_mvar, d_mup, d_mval, s));
+    CUN(cudaMemcpyAsync(mod_var, d_mvar, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    CUN(cudaMemcpyAsync(mod_is_upper, d_mup, (size_t)total, cudaMemcpyDeviceToHost, s));
+    CUN(cudaMemcpyAsync(mod_val, d_mval, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  }
+  CUN(cudaEventRecord(ctx->ev[3], s));
+  CUN(cudaStreamSynchronize(s));
+#undef CUN
+  // deterministic order inside a box: ascending (variable, side)
+  if (total > 0 && total <= mod_cap) {
+    std::vector<size_t> idx;
+    std::vector<int32_t> tv; std::vector<uint8_t> tu; std::vector<double> tx;
+    for (int32_t b = 0; b < n_boxes; ++b) {
+      const size_t lo = (size_t)ptr[(size_t)b], hi = (size_t)ptr[(size_t)b + 1];
+      if (hi - lo < 2) continue;
+      idx.resize(hi - lo);
+      for (size_t k = 0; k < idx.size(); ++k) idx[k] = lo + k;
+      std::sort(idx.begin(), idx.end(), [&](size_t x, size_t y) {
+        return mod_var[x] != mod_var[y] ? mod_var[x] < mod_var[y] : mod_is_upper[x] < mod_is_upper[y]; });
+      tv.resize(idx.size()); tu.resize(idx.size()); tx.resize(idx.size());
+      for (size_t k = 0; k < idx.size(); ++k) { tv[k] = mod_var[idx[k]]; tu[k] = mod_is_upper[idx[k]]; tx[k] = mod_val[idx[k]]; }
+      for (size_t k = 0; k < idx.size(); ++k) { mod_var[lo + k] = tv[k]; mod_is_upper[lo + k] = tu[k]; mod_val[lo + k] = tx[k]; }
+    }
+  }
+  ctx->stats.h2d_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+  ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  ctx->stats.d2h_ms = elapsed(ctx->ev[2], ctx->ev[3]);
+  for (int32_t b = 0; b < n_boxes; ++b) {
+    ctx->stats.n_infeasible += hv[(size_t)b] != MNTR_FEASIBLE;
+    ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, hr[(size_t)b]);
+  }
+  return done(MNTR_OK);
 }
 
 int mntr_gpu_nccl_unique_id(void *id128)

@@ -238,6 +238,31 @@ class GpuBoundEngine:
                     "boxes_download")
         return lb, ub
 
+    def tighten_nodes(self, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val, rounding=ROUND_DIRECTED,
+                      loop=LOOP_FIXPOINT, max_rounds=0, handlers=HANDLERS_ALL, mod_cap=None):
+        """Node batch as branching deltas on a root box; returns (verdict, rounds, mod_ptr, mod_var, mod_is_upper,
+        mod_val): the VarBoundMod tuples of every feasible box, ascending (variable, side) inside a box."""
+        rl = np.ascontiguousarray(root_lb, np.float64); ru = np.ascontiguousarray(root_ub, np.float64)
+        dp = np.ascontiguousarray(delta_ptr, np.int64); dv = np.ascontiguousarray(delta_var, np.int32)
+        du = np.ascontiguousarray(delta_is_upper, np.uint8); dx = np.ascontiguousarray(delta_val, np.float64)
+        nb = len(dp) - 1
+        if len(dv) == 0:
+            dv = np.zeros(1, np.int32); du = np.zeros(1, np.uint8); dx = np.zeros(1)
+        o = GpuOptions(rounding, ORDER_REFERENCE, loop, max_rounds, handlers)
+        v = np.zeros(nb, np.int32); r = np.zeros(nb, np.int32); mp = np.zeros(nb + 1, np.int64)
+        cap = int(mod_cap) if mod_cap is not None else max(1024, 4 * nb)
+        while True:
+            mv = np.zeros(max(cap, 1), np.int32); mu = np.zeros(max(cap, 1), np.uint8); mx = np.zeros(max(cap, 1))
+            total = C.c_int64(0)
+            self._check(self.L.mntr_gpu_tighten_nodes(self.h, nb, _d(rl), _d(ru), _l(dp), _i(dv), _b(du), _d(dx), C.byref(o),
+                                                      _i(v), _i(r), _l(mp), _i(mv), _b(mu), _d(mx), cap, C.byref(total)),
+                        "tighten_nodes")
+            if total.value <= cap or mod_cap is not None:
+                break
+            cap = int(total.value)             # the buffer was too small: call again (documented contract)
+        k = min(int(total.value), cap)
+        return v, r, mp, mv[:k], mu[:k], mx[:k], int(total.value)
+
     def tighten_dev(self, n_boxes: int, boxes_dev_ptr: int, verdict_ptr: int, rounds_ptr: int, nnz_ptr: int,
                     rounding=ROUND_DIRECTED, loop=LOOP_FIXPOINT, max_rounds=0, handlers=HANDLERS_ALL):
         o = GpuOptions(rounding, ORDER_REFERENCE, loop, max_rounds, handlers)

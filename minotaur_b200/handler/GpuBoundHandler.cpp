@@ -278,6 +278,73 @@ bool GpuBoundHandler::tighten_(ProblemPtr p, SolutionPoolPtr spool, ModVector &m
   return false;
 }
 
+void GpuBoundHandler::tightenCandidates(RelaxationPtr rel, SolutionPoolPtr spool,
+                                        const std::vector<std::vector<BoundChange> > &deltas,
+                                        std::vector<BoxOutcome> &out)
+{
+  ProblemPtr p = rel;
+  if (loadedFor_ != p || loadedVars_ != p->getNumVars() || loadedCons_ != p->getNumCons()) { upload_(p); cutoffOn_ = false; }
+  setCutoff_(p, spool);
+  const UInt n = p->getNumVars();
+  const int nb = (int)deltas.size();
+  out.assign(deltas.size(), BoxOutcome());
+  if (nb == 0) return;
+  for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) {
+    const UInt j = (*it)->getIndex();
+    lb_[j] = (*it)->getLb();
+    ub_[j] = (*it)->getUb();
+  }
+  std::vector<int64_t> dptr(1, 0);
+  std::vector<int> dvar;
+  std::vector<unsigned char> dup;
+  std::vector<double> dval;
+  for (int b = 0; b < nb; ++b) {
+    for (size_t k = 0; k < deltas[b].size(); ++k) {
+      dvar.push_back((int)deltas[b][k].var);
+      dup.push_back(deltas[b][k].lu == Upper ? 1 : 0);
+      dval.push_back(deltas[b][k].val);
+    }
+    dptr.push_back((int64_t)dvar.size());
+  }
+  if (dvar.empty()) { dvar.push_back(0); dup.push_back(0); dval.push_back(0.); }
+  mntr_gpu_options o;
+  o.rounding = roundNearest_ ? MNTR_ROUND_NEAREST : MNTR_ROUND_DIRECTED;
+  o.order = MNTR_ORDER_REFERENCE;
+  o.loop = (mode_ == ReferenceOrder) ? MNTR_LOOP_SIMPLEPRESOLVE : MNTR_LOOP_FIXPOINT;
+  o.max_rounds = 0;
+  o.handlers = MNTR_HANDLERS_ALL;
+  o.flags = 0;
+  o.reserved[0] = o.reserved[1] = 0;
+  std::vector<int> verdict(nb), rounds(nb);
+  std::vector<int64_t> mptr(nb + 1, 0);
+  int64_t cap = std::max<int64_t>(1024, 8 * (int64_t)nb), total = 0;
+  std::vector<int> mvar;
+  std::vector<unsigned char> mup;
+  std::vector<double> mval;
+  for (int attempt = 0; attempt < 2; ++attempt) {          // second trip only when the tuple buffer was too small
+    mvar.assign((size_t)cap, 0); mup.assign((size_t)cap, 0); mval.assign((size_t)cap, 0.);
+    const int rc = mntr_gpu_tighten_nodes(ctx_, nb, n ? &lb_[0] : 0, n ? &ub_[0] : 0, &dptr[0], &dvar[0], &dup[0], &dval[0],
+                                          &o, &verdict[0], &rounds[0], &mptr[0], &mvar[0], &mup[0], &mval[0], cap, &total);
+    if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+    if (total <= cap) break;
+    cap = total;
+  }
+  mntr_gpu_stats st;
+  mntr_gpu_get_stats(ctx_, &st);
+  stats_.timeDevice += st.kernel_ms + st.h2d_ms + st.d2h_ms;
+  stats_.calls += nb;
+  for (int b = 0; b < nb; ++b) {
+    out[b].infeasible = verdict[b] != MNTR_FEASIBLE;
+    if (out[b].infeasible) { ++stats_.nInf; continue; }
+    for (int64_t q = mptr[b]; q < mptr[b + 1]; ++q) {
+      BoundChange c;
+      c.var = (UInt)mvar[(size_t)q]; c.lu = mup[(size_t)q] ? Upper : Lower; c.val = mval[(size_t)q];
+      out[b].changes.push_back(c);
+      ++stats_.nMods;
+    }
+  }
+}
+
 void GpuBoundHandler::simplePresolve(ProblemPtr p, SolutionPoolPtr spool, ModVector &t_mods, SolveStatus &status)
 {
   Timer *timer = env_->getNewTimer();

@@ -76,6 +76,21 @@ public:
   /// Same entry LinearHandler offers to heuristics (not virtual in Handler, Handler.h:356-361).
   void simplePresolve(ProblemPtr p, SolutionPoolPtr spool, ModVector &t_mods, SolveStatus &status);
 
+  // ---- batch form: all candidate boxes of a node in ONE device call ----
+  /// A bound change that distinguishes a candidate box from the current box of the relaxation.
+  struct BoundChange { UInt var; BoundType lu; double val; };
+  /// What FBBT makes of one candidate box: infeasible, or the bound changes it derives (NOT applied anywhere).
+  struct BoxOutcome { bool infeasible; std::vector<BoundChange> changes; };
+  /**
+   * Strong(er)-branching producers (StrongBrancher::strongBranch_, StrongBrancher.cpp:505-585;
+   * WeakBrancher::getStrongerMods loops, WeakBrancher.cpp:317-341) tighten 2 boxes per candidate one after the
+   * other through Handler::getStrongerMods.  This call takes all of them at once: box b = the current bounds of
+   * `rel` with deltas[b] applied (mntr_gpu_tighten_nodes: branching deltas in, VarBoundMod tuples out).  `rel` is
+   * not modified.  out[b] is what presolveNode would have produced on box b.
+   */
+  void tightenCandidates(RelaxationPtr rel, SolutionPoolPtr spool,
+                         const std::vector<std::vector<BoundChange> > &deltas, std::vector<BoxOutcome> &out);
+
   std::string getName() const;
   void writeStats(std::ostream &out) const;
 

@@ -188,7 +188,59 @@ int main()
     }
     delete p;
   }
-  printf("handler_test: %d comparisons (%d with an incumbent cut-off), %d infeasible, %d mods emitted, %d failures\n",
-         n_cmp, n_cut, n_inf, n_mods, failures);
+  // ---- batch form: all strong-branching candidates of a node in one call (StrongBrancher.cpp:505-585) ----
+  int n_cand = 0, n_cand_inf = 0;
+  {
+    std::vector<double> xstar;
+    const int n = 400;
+    ProblemPtr p = makeProblem(env, n, 350, 6, 30, xstar);
+    RelaxationPtr rel = (RelaxationPtr) new Relaxation(p, env);
+    rel->calculateSize();
+    branch(rel, 4);
+    GpuBoundHandler gh(env, p, 0);
+    gh.setMode(GpuBoundHandler::ReferenceOrder);
+    gh.setRoundNearest(true);
+    // candidates: down and up branch of 40 integer variables
+    std::vector<std::vector<GpuBoundHandler::BoundChange> > deltas;
+    for (int j = 0; j < n && (int)deltas.size() < 80; ++j) {
+      VariablePtr v = rel->getVariable(j);
+      if ((v->getType() != Integer && v->getType() != Binary) || v->getUb() - v->getLb() < 1) continue;
+      const double x = std::floor(v->getLb() + 0.5 * (v->getUb() - v->getLb()));
+      GpuBoundHandler::BoundChange dn = { (UInt)j, Upper, x }, up = { (UInt)j, Lower, x + 1 };
+      deltas.push_back(std::vector<GpuBoundHandler::BoundChange>(1, dn));
+      deltas.push_back(std::vector<GpuBoundHandler::BoundChange>(1, up));
+    }
+    std::vector<GpuBoundHandler::BoxOutcome> outc;
+    gh.tightenCandidates(rel, (SolutionPoolPtr)0, deltas, outc);
+    ModVector pm;
+    for (size_t b = 0; b < deltas.size(); ++b) {
+      // the same box the way StrongBrancher does it: apply the branching mod, presolveNode, undo
+      VariablePtr bv = rel->getVariable(deltas[b][0].var);
+      VarBoundMod br(bv, deltas[b][0].lu, deltas[b][0].val);
+      br.applyToProblem(rel);
+      std::vector<double> l0(n), u0(n);
+      for (int j = 0; j < n; ++j) { l0[j] = rel->getVariable(j)->getLb(); u0[j] = rel->getVariable(j)->getUb(); }
+      ModVector rm;
+      const bool inf = gh.presolveNode(rel, (NodePtr)0, (SolutionPoolPtr)0, pm, rm);
+      ++n_cand;
+      CHECK(inf == outc[b].infeasible, "candidate %d: verdict single %d batch %d", (int)b, (int)inf, (int)outc[b].infeasible);
+      if (!inf && !outc[b].infeasible) {
+        std::vector<double> l(l0), u(u0);
+        for (size_t k = 0; k < outc[b].changes.size(); ++k)
+          (outc[b].changes[k].lu == Upper ? u : l)[outc[b].changes[k].var] = outc[b].changes[k].val;
+        for (int j = 0; j < n; ++j)
+          CHECK(rel->getVariable(j)->getLb() == l[j] && rel->getVariable(j)->getUb() == u[j],
+                "candidate %d var %d: single [%.17g,%.17g] batch [%.17g,%.17g]", (int)b, j,
+                rel->getVariable(j)->getLb(), rel->getVariable(j)->getUb(), l[j], u[j]);
+      } else ++n_cand_inf;
+      for (ModVector::reverse_iterator it = rm.rbegin(); it != rm.rend(); ++it) { (*it)->undoToProblem(rel); delete *it; }
+      br.undoToProblem(rel);
+    }
+    delete rel;
+    delete p;
+  }
+  printf("handler_test: %d comparisons (%d with an incumbent cut-off), %d infeasible, %d mods emitted; "
+         "%d strong-branching candidates in one batch (%d infeasible); %d failures\n",
+         n_cmp, n_cut, n_inf, n_mods, n_cand, n_cand_inf, failures);
   return failures ? 1 : 0;
 }

@@ -432,6 +432,20 @@ def branch_boxes(inst_lb: np.ndarray, inst_ub: np.ndarray, var_type: np.ndarray,
     return lbs, ubs
 
 
+def boxes_to_deltas(root_lb: np.ndarray, root_ub: np.ndarray, lbs: np.ndarray, ubs: np.ndarray):
+    """Node boxes as sparse branching deltas on the root box, the form in which B&B nodes differ (Node r_mods):
+    (delta_ptr [n_boxes+1] int64, delta_var int32, delta_is_upper uint8, delta_val float64)."""
+    ptr, var, up, val = [0], [], [], []
+    for b in range(lbs.shape[0]):
+        jl = np.nonzero(lbs[b] != root_lb)[0]
+        ju = np.nonzero(ubs[b] != root_ub)[0]
+        var += list(jl) + list(ju)
+        up += [0] * len(jl) + [1] * len(ju)
+        val += list(lbs[b, jl]) + list(ubs[b, ju])
+        ptr.append(len(var))
+    return (np.asarray(ptr, np.int64), np.asarray(var, np.int32), np.asarray(up, np.uint8), np.asarray(val, np.float64))
+
+
 def make_minlp(n: int, n_cons: int, m_lin: int, seed: int = 99, name: str = "minlp"
                ) -> Tuple[LinearRows, Tapes]:
     """Config C5 shape: variables in [l,u] within [-10,10]; 50 % constraints
