@@ -103,6 +103,10 @@ typedef struct {
  * (the kernels of the row-partitioned multi-GPU mode) instead of the single cooperative launch.  Always on
  * when a communicator is attached; this flag selects it on one GPU too. */
 #define MNTR_FLAG_PER_ROUND_KERNELS 1
+/* Single-box cooperative launch: always stream the rows from the CSR in global memory (staged, entry-parallel
+ * batches) instead of keeping them resident in shared memory, which is the default whenever every warp of the grid
+ * owns at most 32 rows.  Same results; for testing the streaming form on small instances. */
+#define MNTR_FLAG_STAGED_ROWS 2
 
 /* per-call statistics (LinPresolveStats / NlPresStats counterparts, LinearHandler.h:22-36) */
 typedef struct {

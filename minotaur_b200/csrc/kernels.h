@@ -8,9 +8,11 @@
 namespace mntr {
 
 // K1 (linear_single.cu): single-box Jacobi fixpoint, one cooperative launch.
-// lb_dev/ub_dev [n] are read at the start and overwritten with the tightened box.
+// lb_dev/ub_dev [n] are read at the start and overwritten with the tightened box.  staged_only: never take the
+// resident-rows form (rows in shared memory, row_resident.cuh), even when the instance is small enough.
 cudaError_t launch_single_jacobi(const LinDev &P, const SingleWs &W, double *lb_dev, double *ub_dev,
-                                 bool directed, int max_rounds, int loop_mode, int sm_count, cudaStream_t stream);
+                                 bool directed, int max_rounds, int loop_mode, int sm_count, bool staged_only,
+                                 cudaStream_t stream);
 
 // K5 (linear_rounds.cu): one Jacobi round as separate launches (row-partitioned multi-GPU mode)
 cudaError_t launch_rounds_init(const LinDev &P, const RoundsWs &W, const double *lb_dev, const double *ub_dev,

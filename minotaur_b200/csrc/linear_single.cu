@@ -12,13 +12,18 @@
 //     rewrite a box between rounds; the bound check [checkBounds_ :328-359] of a moved variable is part of its fix-up;
 //   * the rows of a moved variable are flagged for the next round [changeBFlag_ :1229-1234] by the warp whose
 //     candidate moved it first, through the CSC lists, into the next round's row bit set.
-// The row evaluation itself (activities with outward rounding, singleton-infinity rule, implied bounds) is
-// row_batch.cuh: entry-parallel, one warp per batch of up to 32 due rows.
+// The row evaluation itself (activities with outward rounding, singleton-infinity rule, implied bounds) comes in two
+// forms.  RES (row_resident.cuh): every warp owns at most 32 rows, one per lane, whose heads stay in registers and
+// whose entries stay in shared memory for the whole launch -- taken whenever m <= 32 x warps of the grid.  Otherwise
+// row_batch.cuh: entry-parallel, one warp per staged batch of up to 32 due rows, streamed from the CSR.
 // The result is exactly the two-phase Jacobi round: rows against the box of the round start, candidates merged with
 // max/min, integers rounded, bounds checked, rows of changed variables flagged.
 #include "device_problem.cuh"
 #include "kernels.h"
 #include "row_batch.cuh"
+#include "row_resident.cuh"
+
+#include <type_traits>
 
 namespace mntr {
 
@@ -49,6 +54,7 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
 // the control words (ring[12] + status[8]) into shared memory: ONE reader per block -- if every warp read them
 // from global memory, thousands of requests would queue on a single L2 line after every barrier.
 constexpr int kCtlWords = 20;
+constexpr int kTraceBlk = 64 + 256 * 16;   // trace buffer: per-block phase maxima start here
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, unsigned &target, const int32_t *ctl,
                                              int *s_ctl, unsigned long long *arrive)
 {
@@ -105,20 +111,20 @@ __device__ __forceinline__ void for_each_marked(unsigned word, int wb, int lane,
   }
 }
 
-template <class R>
+template <class R, bool RES>
 __global__ void __launch_bounds__(kSingleThreads, 1)
 fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, int max_rounds, int loop_mode)
 {
+  using Stage = typename std::conditional<RES, ResidentStage, WarpStage>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ FixRound s_round;
   __shared__ __align__(16) int s_ctl[kCtlWords];      // ring[0..11], status[0..7] as of the last barrier
   const int *s_ring = s_ctl, *s_stat = s_ctl + 12;
-  WarpStage &S = reinterpret_cast<WarpStage *>(smem_raw)[threadIdx.x >> 5];
+  Stage &S = reinterpret_cast<Stage *>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int nthreads = gridDim.x * blockDim.x;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;       // linear: coalesced sweeps over arrays
-  // block-interleaved numbering: consecutive work-list items and row ranges go to different SMs
-  const int tid = threadIdx.x * gridDim.x + blockIdx.x;
+  // block-interleaved numbering: consecutive row ranges go to different SMs
   const int warp_g = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, n_warps = gridDim.x * kSingleWarps;
   unsigned bar_target = 0;
   int tr = 0;
@@ -129,6 +135,9 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
   // contiguous row range of this warp
   const int rpw = (P.m + n_warps - 1) / n_warps;
   const int r0 = min(P.m, warp_g * rpw), r1 = min(P.m, r0 + rpw);
+  // RES: the lane's row head stays in registers, the row's entries in the warp's slice of shared memory
+  RowHead head{0, -1, 0.0, 0.0};
+  if constexpr (RES) head = resident_load(P, S, lane, r0 + lane < r1 ? r0 + lane : -1);
 
   // ---- phase 0: both boxes = incoming box; round 1's rows all due; moved-variable bit sets empty, except that
   //      integer variables whose INCOMING bounds are fractional move in round 1 by rounding alone: they are
@@ -193,8 +202,10 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
     // ---- rows due in this round ----
     {
       const ReadPending rd{A, P.colx, round > 1};
-      const SinkFix sink{&s_round, (W.trace != nullptr && blockIdx.x == 0 && threadIdx.x < 32) ? W.trace + 32 : nullptr};
-      eval_due_range<R>(P, rd, sink, S, W.due[cur], r0, r1, round == 1, lane, my_nnz, my_rows);
+      const SinkFix sink{&s_round, (W.trace != nullptr && blockIdx.x == 0 && threadIdx.x < 32) ? W.trace + 32 : nullptr,
+                         (W.trace != nullptr && round < 16) ? W.trace + kTraceBlk + (blockIdx.x * 16 + round) * 8 : nullptr};
+      if constexpr (RES) eval_due_resident<R>(P, rd, sink, S, W.due[cur], r0, r1, head, round == 1, lane, my_nnz, my_rows);
+      else eval_due_range<R>(P, rd, sink, S, W.due[cur], r0, r1, round == 1, lane, my_nnz, my_rows);
       // the objective cut-off row is evaluated in every round (the reference loops it to its own fixpoint in
       // every sweep, LinearHandler.cpp:1636-1640); the last warp takes it
       if (P.cut_cnt > 0 && warp_g == n_warps - 1) {
@@ -228,6 +239,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
       }
       if (bad) W.status[3] = 1;
     }
+    if (W.trace != nullptr && round < 16 && lane == 0) atomicMax(W.trace + kTraceBlk + (blockIdx.x * 16 + round) * 8 + 6, globaltimer_ns());
     MNTR_TRACE();
     grid_barrier(W.bar, gridDim.x, bar_target, W.ring, s_ctl,
                  (W.trace != nullptr && round < 16) ? W.trace + 64 + blockIdx.x * 16 + round : nullptr);
@@ -312,12 +324,8 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
 
 template <class R>
 cudaError_t launch_r(const LinDev &P, const SingleWs &W, double *lb, double *ub, int max_rounds,
-                     int loop_mode, int sm_count, cudaStream_t stream)
+                     int loop_mode, int sm_count, bool staged_only, cudaStream_t stream)
 {
-  auto kern = fbbt_single_jacobi_kernel<R>;
-  const size_t smem = sizeof(WarpStage) * kSingleWarps;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   // at least 8 rows per warp: small problems run on few blocks and pay a cheaper barrier
   long long want_warps = ((long long)P.m + 7) / 8;
   const long long var_warps = ((long long)P.n + 255) / 256;
@@ -325,6 +333,13 @@ cudaError_t launch_r(const LinDev &P, const SingleWs &W, double *lb, double *ub,
   long long blocks = (want_warps + kSingleWarps - 1) / kSingleWarps;
   if (blocks > sm_count) blocks = sm_count;
   if (blocks < 1) blocks = 1;
+  // resident rows: every warp owns at most 32 rows (one per lane)
+  const long long n_warps = blocks * kSingleWarps;
+  const bool resident = !staged_only && ((long long)P.m + n_warps - 1) / n_warps <= 32;
+  auto kern = resident ? fbbt_single_jacobi_kernel<R, true> : fbbt_single_jacobi_kernel<R, false>;
+  const size_t smem = (resident ? sizeof(ResidentStage) : sizeof(WarpStage)) * kSingleWarps;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   LinDev p = P; SingleWs w = W;
   void *args[] = { &p, &w, &lb, &ub, &max_rounds, &loop_mode };
   // cooperative launch: guarantees that all blocks are co-resident, which the barrier relies on
@@ -334,10 +349,11 @@ cudaError_t launch_r(const LinDev &P, const SingleWs &W, double *lb, double *ub,
 }  // namespace
 
 cudaError_t launch_single_jacobi(const LinDev &P, const SingleWs &W, double *lb_dev, double *ub_dev,
-                                 bool directed, int max_rounds, int loop_mode, int sm_count, cudaStream_t stream)
+                                 bool directed, int max_rounds, int loop_mode, int sm_count, bool staged_only,
+                                 cudaStream_t stream)
 {
-  if (directed) return launch_r<RoundDirected>(P, W, lb_dev, ub_dev, max_rounds, loop_mode, sm_count, stream);
-  return launch_r<RoundNearest>(P, W, lb_dev, ub_dev, max_rounds, loop_mode, sm_count, stream);
+  if (directed) return launch_r<RoundDirected>(P, W, lb_dev, ub_dev, max_rounds, loop_mode, sm_count, staged_only, stream);
+  return launch_r<RoundNearest>(P, W, lb_dev, ub_dev, max_rounds, loop_mode, sm_count, staged_only, stream);
 }
 
 }  // namespace mntr

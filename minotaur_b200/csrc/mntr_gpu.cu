@@ -25,7 +25,7 @@
 using namespace mntr;
 
 // host mirror of the single-box kernel's control block (SingleWs::ring/status/counters/bar)
-constexpr int kTraceWords = 64 + 256 * 16;   // MNTR_GPU_TRACE buffer: phases, one warp's passes, barrier arrivals
+constexpr int kTraceWords = 64 + 256 * 16 + 256 * 16 * 8;   // MNTR_GPU_TRACE buffer: phases, one warp's passes, barrier arrivals
 struct SingleCtrl {
   int32_t ring[12]; int32_t status[8]; unsigned long long counters[2]; unsigned bar; unsigned done; unsigned pad[6];
   // the loop's verdict, or MNTR_INFEAS_BOUNDS when the bound check of the last round's moved variables failed
@@ -617,7 +617,8 @@ static int run_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
 {
   if (!ctx->ctrl_clean) CU(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(SingleCtrl), ctx->stream));
   ctx->ctrl_clean = false;          // until the launch has been seen to complete
-  CU(launch_single_jacobi(ctx->lin, ctx->sws, lb_dev, ub_dev, o.rounding == MNTR_ROUND_DIRECTED, o.max_rounds, o.loop, ctx->sm_count, ctx->stream));
+  CU(launch_single_jacobi(ctx->lin, ctx->sws, lb_dev, ub_dev, o.rounding == MNTR_ROUND_DIRECTED, o.max_rounds, o.loop, ctx->sm_count,
+                           (o.flags & MNTR_FLAG_STAGED_ROWS) != 0, ctx->stream));
   return MNTR_OK;
 }
 
@@ -823,7 +824,23 @@ int mntr_gpu_tighten_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_de
       std::sort(a.begin(), a.end());
       fprintf(stderr, "  r%d %.1f/%.1f/%.1f", r, a.front(), a[a.size() / 2], a.back());
     }
-    fprintf(stderr, "\n");
+    fprintf(stderr, "\n[mntr blocks] per round, phase k: median / max over blocks of the latest warp (us since kernel start)\n");
+    for (int r = 1; r < 16; ++r) {
+      bool any = false;
+      for (int k = 0; k < 8; ++k) {
+        std::vector<double> a;
+        for (int b = 0; b < 256; ++b) {
+          const unsigned long long v = t[64 + 256 * 16 + (b * 16 + r) * 8 + k];
+          if (v != 0) a.push_back((double)(v - t[0]) * 1e-3);
+        }
+        if (a.empty()) continue;
+        std::sort(a.begin(), a.end());
+        if (!any) fprintf(stderr, "  r%d:", r);
+        any = true;
+        fprintf(stderr, "  k%d %.1f/%.1f(n=%d)", k, a[a.size() / 2], a.back(), (int)a.size());
+      }
+      if (any) fprintf(stderr, "\n");
+    }
     CU(cudaMemset(ctx->sws.trace, 0, sizeof(t)));
   }
   return MNTR_OK;

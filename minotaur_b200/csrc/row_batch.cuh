@@ -28,7 +28,6 @@ constexpr int kGroup = 4;                 // gathers a lane issues back to back
 static_assert(kPerLane % kGroup == 0, "pass A runs in groups");
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kColMask = 0x7fffffff;
-constexpr int kLongList = 64;             // CSC lists longer than this are walked by the whole warp
 
 constexpr uint8_t kLoInf = 1, kHiInf = 2, kTiny = 4;   // per-entry bits of the singleton-infinity rule
 
@@ -45,6 +44,9 @@ struct __align__(16) WarpStage {
   uint8_t slot[kCap];      // staged entry -> row slot (= lane of the row)
   uint8_t flag[kCap];      // kLoInf | kHiInf | kTiny
   uint8_t sing[32];        // bit 0: lb side runs in singleton-infinity mode, bit 1: ub side
+  // the Sink's list of moved variables lives in plo[] once pass B has consumed the products
+  static constexpr int kListCap = 2 * kCap;
+  __device__ __forceinline__ int *list() { return reinterpret_cast<int *>(plo); }
 };
 static_assert(sizeof(WarpStage) % 16 == 0, "slices are laid out back to back");
 
@@ -59,15 +61,16 @@ struct ReadPending {
   const double2 *box;
   const int32_t *colx;
   bool round_ints;
-  __device__ __forceinline__ double2 get(int src, int &j, bool &isint) const
+  // bounds of the variable of a packed column (bit 31: integer)
+  __device__ __forceinline__ double2 fetch(int cx, int &j, bool &isint) const
   {
-    const int cx = __ldg(colx + src);
     j = cx & kColMask;
     isint = cx < 0;
     double2 b = __ldcg(box + j);
     if (round_ints && isint) tighten_int_bounds(b.x, b.y);
     return b;
   }
+  __device__ __forceinline__ double2 get(int src, int &j, bool &isint) const { return fetch(__ldg(colx + src), j, isint); }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -75,7 +78,7 @@ struct ReadPending {
 // ---------------------------------------------------------------------------------------------------------------
 
 struct FixRound;
-static __device__ void flush_moved(WarpStage &S, int lane, const FixRound *rc);
+template <class Stage> static __device__ __noinline__ void flush_moved(Stage &S, int lane, const FixRound *rc);
 
 // One-barrier fixpoint kernel: candidates are merged into the NEXT round's box; a moved variable is marked in the
 // round's bit set (the next round's fix-up scans it) and its rows are flagged for the next round [changeBFlag_
@@ -95,8 +98,17 @@ struct FixRound {
 struct SinkFix {
   const FixRound *rc;          // in shared memory
   unsigned long long *probe;   // debug (MNTR_GPU_TRACE): time stamps of one warp's passes, or nullptr
+  unsigned long long *blk;     // debug: per-block, per-round latest time any warp passed phase k, or nullptr
+  __device__ __forceinline__ void phase(int lane, int k) const
+  {
+    if (blk != nullptr && lane == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMax(blk + k, t);
+    }
+  }
 
-  __device__ __forceinline__ void mark(WarpStage &S, int lane) const
+  template <class Stage> __device__ __forceinline__ void mark(Stage &S, int lane) const
   {
     if (probe != nullptr && lane == 0 && S.pad_[0] < 32) {
       unsigned long long t;
@@ -104,20 +116,21 @@ struct SinkFix {
       probe[S.pad_[0]++] = t;
     }
   }
-  __device__ __forceinline__ void raise_lb(WarpStage &, int j, bool, double c) const { atomic_max_f64(&rc->next_box[j].x, c); }
-  __device__ __forceinline__ void lower_ub(WarpStage &, int j, bool, double c) const { atomic_min_f64(&rc->next_box[j].y, c); }
+  template <class Stage> __device__ __forceinline__ void raise_lb(Stage &, int j, bool, double c) const { atomic_max_f64(&rc->next_box[j].x, c); }
+  template <class Stage> __device__ __forceinline__ void lower_ub(Stage &, int j, bool, double c) const { atomic_min_f64(&rc->next_box[j].y, c); }
   // the moved variable goes on the warp's list; flush() walks the lists of 32 variables at a time
-  __device__ __forceinline__ void moved(WarpStage &S, int j, bool isint) const
+  template <class Stage> __device__ __forceinline__ void moved(Stage &S, int j, bool isint) const
   {
-    reinterpret_cast<int *>(S.plo)[atomicAdd(&S.tcount, 1)] = j;
+    S.list()[atomicAdd(&S.tcount, 1)] = j;
     if (isint) *rc->int_moved = 1;       // a row moved an integer variable (nintmods, :1070-1133)
   }
   __device__ __forceinline__ void row_infeasible() const { *rc->row_inf = 1; }
   __device__ __forceinline__ void row_bounds_cross() const { rc->row_inf[4] = 1; }     // status[4]
-  __device__ __forceinline__ bool near_full(const WarpStage &S) const { return S.tcount + 32 > 2 * kCap; }
+  // no room for `room` more entries?
+  template <class Stage> __device__ __forceinline__ bool near_full(const Stage &S, int room = 32) const { return S.tcount + room > Stage::kListCap; }
 
   // convergent: mark the warp's moved variables and flag their rows
-  __device__ __forceinline__ void flush(WarpStage &S, int lane) const
+  template <class Stage> __device__ __forceinline__ void flush(Stage &S, int lane) const
   {
     __syncwarp();
     if (S.tcount != 0) flush_moved(S, lane, rc);
@@ -125,38 +138,42 @@ struct SinkFix {
 };
 
 // out of line: rare, and called from several places
-static __device__ __noinline__ void flush_moved(WarpStage &S, int lane, const FixRound *rc)
+template <class Stage>
+static __device__ void flush_moved(Stage &S, int lane, const FixRound *rc)
 {
   uint32_t *due_next = rc->due_next, *touched = rc->touched;
   const int32_t *csc_ptr = rc->csc_ptr, *csc_row = rc->csc_row;
   const int n = S.tcount;
-  const int *tl = reinterpret_cast<const int *>(S.plo);
+  const int *tl = S.list();
   if (lane == 0) *rc->changed = 1;
   for (int base = 0; base < n; base += 32) {
     const int idx = base + lane;
-    int qb = 0, qe = 0;
+    int qb = 0, len = 0;
     if (idx < n) {
       const int j = tl[idx];
-      qb = __ldg(csc_ptr + j); qe = __ldg(csc_ptr + j + 1);
+      qb = __ldg(csc_ptr + j); len = __ldg(csc_ptr + j + 1) - qb;
       atomicOr(touched + (j >> 5), 1u << (j & 31));
     }
-    const int len = qe - qb;
-    const int mine = len <= kLongList ? len : 0;          // short lists: one lane each, four entries in flight
-    const int longest = __reduce_max_sync(kFullMask, mine);
-    for (int t = 0; t < longest; t += 4) {
-      int r[4];
+    // the CSC lists of these (up to 32) variables laid end to end, taken ENTRY-PARALLEL: one trip per 32 rows to flag
+    int incl = len;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) r[u] = (t + u < mine) ? __ldg(csc_row + qb + t + u) : -1;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) if (r[u] >= 0) atomicOr(due_next + (r[u] >> 5), 1u << (r[u] & 31));
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(kFullMask, incl, d);
+      if (lane >= d) incl += v;
     }
-    unsigned lm = __ballot_sync(kFullMask, len > kLongList);   // long lists: the whole warp walks one list
-    while (lm) {
-      const int s = __ffs(lm) - 1;
-      lm &= lm - 1;
-      const int b = __shfl_sync(kFullMask, qb, s), e = __shfl_sync(kFullMask, qe, s);
-      for (int q = b + lane; q < e; q += 32) {
-        const int row = __ldg(csc_row + q);
+    const int total = __shfl_sync(kFullMask, incl, 31);
+    for (int e0 = 0; e0 < total; e0 += 32) {
+      const int x = e0 + lane;
+      int lo = 0;                                      // first lane whose inclusive count exceeds x
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(kFullMask, incl, lo + step - 1);
+        if (v <= x) lo += step;
+      }
+      const int oqb = __shfl_sync(kFullMask, qb, lo), oincl = __shfl_sync(kFullMask, incl, lo);
+      const int olen = __shfl_sync(kFullMask, len, lo);
+      if (x < total) {
+        const int row = __ldg(csc_row + oqb + (x - (oincl - olen)));
         atomicOr(due_next + (row >> 5), 1u << (row & 31));
       }
     }
@@ -217,9 +234,9 @@ __device__ __noinline__ double2 exact_candidates(double slack_lb, double slack_u
 }
 
 // A candidate is handed to the sink only when it really moves the bound (after the clamp it may not).
-template <class R, class Sink>
+template <class R, class Sink, class Stage>
 __device__ __forceinline__ void emit_exact(double slack_lb, double slack_ub, int sing, double a, int j, bool isint,
-                                           double2 b, WarpStage &S, const Sink &sink)
+                                           double2 b, Stage &S, const Sink &sink)
 {
   const double2 c = exact_candidates<R>(slack_lb, slack_ub, sing, a, b.x, b.y);
   const bool up = c.x > b.x, down = c.y < b.y;
@@ -375,8 +392,8 @@ __device__ __forceinline__ double warp_sum(double v)
   return v;
 }
 
-template <class R, class Reader, class Sink>
-__device__ __forceinline__ void eval_long(const double *val, const Reader &rd, const Sink &sink, WarpStage &S, int lane,
+template <class R, class Reader, class Sink, class Stage>
+__device__ __forceinline__ void eval_long(const double *val, const Reader &rd, const Sink &sink, Stage &S, int lane,
                                           int beg, int cnt, double rl, double ru)
 {
   double ll = 0.0, uu = 0.0, fs_lo = 0.0, fs_hi = 0.0;

@@ -29,6 +29,7 @@ LOOP_FIXPOINT, LOOP_SIMPLEPRESOLVE = 0, 1
 FEASIBLE, INFEAS_BOUNDS, INFEAS_ROW, INFEAS_NL, ERROR_NL = 0, 1, 2, 3, 4
 HANDLERS_ALL, HANDLERS_LINEAR, HANDLERS_NONLINEAR = 0, 1, 2
 FLAG_PER_ROUND_KERNELS = 1
+FLAG_STAGED_ROWS = 2
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
