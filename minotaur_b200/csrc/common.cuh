@@ -76,6 +76,18 @@ __device__ __forceinline__ void atomic_min_f64(double *addr, double v)
 __device__ __forceinline__ double2 ldg_f64x2(const double2 *p) { return __ldg(p); }
 __device__ __forceinline__ int2 ldg_i32x2(const int2 *p) { return __ldg(p); }
 
+// Product test of the Jacobi kernels.  A term a*x_j of a row with slack s (row bound minus the activity of the OTHER
+// bound side) moves a bound of x_j towards the other by s/|a|, and updateLfBoundsFromLb_/Ub_ accept the new bound only
+// if it improves by more than eTol (LinearHandler.cpp:1070): in exact arithmetic iff  s < |a| (ub - lb - eTol).
+// term_reach() is an upper bound of that threshold with room for the rounding of the exact path (half of eTol
+// absolute, 1e-9 relative; bounds beyond 1e6 in magnitude, infinities and NaN always pass): a term with
+// s >= term_reach() cannot be accepted, so the fp64 divisions are skipped for it.  Test it as  !(s >= reach).
+__device__ __forceinline__ double term_reach(double a, double2 b)
+{
+  const double w = fabs(a) * ((b.y - b.x) - 0.5 * kETol) * 1.000000001;
+  return (fmax(fabs(b.x), fabs(b.y)) > 1e6) ? INFINITY : w;
+}
+
 // integer rounding of one bound pair: LinearHandler::tightenInts_, LinearHandler.cpp:415-490
 __device__ __forceinline__ void tighten_int_bounds(double &lb, double &ub)
 {

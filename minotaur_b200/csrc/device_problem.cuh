@@ -19,6 +19,7 @@ struct LinDev {
   const uint8_t *var_type;  // [n]
   const int32_t *csc_ptr;   // [n+1]
   const int32_t *csc_row;   // [nnz]
+  int32_t csc_nnz;          // length of csc_row
   // wavefront schedule of the reference's index-ordered in-place sweep
   int32_t n_levels;
   const int32_t *level_ptr; // [n_levels+1] ranges of STORED rows (rows are stored in level order)
@@ -60,17 +61,23 @@ struct SingleWs {
   uint32_t *touched[2]; // [(n+31)/32] variable-moved-in-the-round bit sets
   uint32_t *ever;       // [(n+31)/32] variable moved in some round: the only entries the epilogue writes back
   // control block (128 bytes; zero when a launch starts: the previous launch's last block resets it)
-  int32_t *ring;   // [12] per-round words: ring[r%3] changed, ring[3+r%3] int moved, 
-  int32_t *status; // [8]  [0] a row is activity-infeasible  [1] rounds  [2] changed (variable, round) pairs
-                   //      [3] a moved variable's bounds cross  [4] a row's bounds cross  [5] incoming bounds cross
-                   //      [6] verdict of the loop
+  unsigned *sync;  // [4]  ONE 16-byte line, read with one load by the barrier's poller:
+                   //      [0] device-wide barrier arrive counter
+                   //      [1] last round in which a bound moved          (atomicMax; "changed" of that round)
+                   //      [2] last round in which a row moved an integer variable   (nintmods > 0, :1625-1627)
+                   //      [3] sticky flag bits kCtl*
+  int32_t *status; // [8]  results: [1] rounds  [2] changed (variable, round) pairs  [6] verdict of the loop
   unsigned long long *counters;  // [2] [0] nnz_updates, [1] rows evaluated
-  unsigned *bar;   // device-wide barrier arrive counter
   unsigned *done;  // blocks that have left the kernel: the last one publishes and resets the control block
   int32_t *result; // [kCtrlWords] pinned, mapped host copy of the control block, written by the last block
   unsigned long long *trace;     // [64] optional phase timestamps (globaltimer ns), or nullptr
 };
 constexpr int kCtrlWords = 32;   // the control block: 128 bytes
+// sticky flags in sync[3]
+constexpr unsigned kCtlRowInf = 1u;      // a row is activity-infeasible
+constexpr unsigned kCtlVarCross = 2u;    // a moved variable's bounds cross
+constexpr unsigned kCtlRowCross = 4u;    // a row's bounds cross
+constexpr unsigned kCtlInCross = 8u;     // the incoming bounds cross
 
 // workspace of the per-round kernels (row-partitioned multi-GPU mode)
 struct RoundsWs {

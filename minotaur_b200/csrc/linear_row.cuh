@@ -111,8 +111,8 @@ __device__ __forceinline__ void emit_exact(const RowCtx rc, double a, int j, dou
 template <class R, class Sink>
 __device__ __forceinline__ void emit_candidates(const RowCtx &rc, double a, int j, double2 b, const Sink &sink)
 {
-  const double reach = fabs(a) * (b.y - b.x) * 1.000000001;
-  if (!(rc.slack_lb > reach) || !(rc.slack_ub > reach)) emit_exact<R, Sink>(rc, a, j, b, sink);
+  const double reach = term_reach(a, b);
+  if (!(rc.slack_lb >= reach) || !(rc.slack_ub >= reach)) emit_exact<R, Sink>(rc, a, j, b, sink);
 }
 
 // this lane's first four entries of a row (a == 0: none)

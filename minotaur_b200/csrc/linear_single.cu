@@ -42,35 +42,31 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 // optional phase trace (MNTR_GPU_TRACE=1): thread 0 of block 0 stamps every phase boundary
 #define MNTR_TRACE() do { if (W.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tr < 32) W.trace[tr] = globaltimer_ns(); ++tr; } while (0)
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+// Device-wide barrier for a cooperative (co-resident) grid: a cumulative arrive counter; thread 0 of each block
+// arrives with a release fence and polls.  The poll is ONE 16-byte acquire load of the line {arrive counter, last
+// round that moved a bound, last round that moved an integer, sticky flags}: the load that sees the last arrival
+// also carries the control words every block needs to decide what comes next (all of them were written, with
+// atomics performed at L2, before their writers arrived), so no second trip to L2 follows the barrier.  Thread 0
+// leaves the snapshot in shared memory: ONE reader per block.
+constexpr int kTraceBlk = 64 + 256 * 16;   // trace buffer: per-block phase maxima start here
+__device__ __forceinline__ uint4 ld_acquire_gpu_v4(const unsigned *p)
 {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  uint4 v;
+  asm volatile("ld.acquire.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-
-// Device-wide barrier for a cooperative (co-resident) grid: a cumulative arrive counter, thread 0
-// of each block arrives with a release fence and polls with acquire loads.  Thread 0 then takes a snapshot of
-// the control words (ring[12] + status[8]) into shared memory: ONE reader per block -- if every warp read them
-// from global memory, thousands of requests would queue on a single L2 line after every barrier.
-constexpr int kCtlWords = 20;
-constexpr int kTraceBlk = 64 + 256 * 16;   // trace buffer: per-block phase maxima start here
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, unsigned &target, const int32_t *ctl,
-                                             int *s_ctl, unsigned long long *arrive)
+__device__ __forceinline__ void grid_barrier(unsigned *sync, unsigned n_blocks, unsigned &target, unsigned *s_ctl,
+                                             unsigned long long *arrive)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
     if (arrive != nullptr) *arrive = globaltimer_ns();      // debug: when this block reached the barrier
     target += n_blocks;
     __threadfence();
-    atomicAdd(bar, 1u);
-    while (ld_acquire_gpu(bar) < target) { }
-    __threadfence();
-    int4 v[kCtlWords / 4];
-#pragma unroll
-    for (int k = 0; k < kCtlWords / 4; ++k) v[k] = __ldcg(reinterpret_cast<const int4 *>(ctl) + k);
-#pragma unroll
-    for (int k = 0; k < kCtlWords / 4; ++k) reinterpret_cast<int4 *>(s_ctl)[k] = v[k];
+    atomicAdd(sync, 1u);
+    uint4 v;
+    do { v = ld_acquire_gpu_v4(sync); } while (v.x < target);
+    *reinterpret_cast<uint4 *>(s_ctl) = v;
   }
   __syncthreads();
 }
@@ -88,7 +84,7 @@ __device__ __forceinline__ void flag_rows_serial(const LinDev &P, int j, uint32_
 // The set bits of up to 32 words (lane l holds word wb + l) are spread over the lanes, 32 at a time, and f(j) is
 // called for each: every marked variable is an independent chain, whatever word it sits in.  Convergent.
 template <class F>
-__device__ __forceinline__ void for_each_marked(unsigned word, int wb, int lane, F f)
+__device__ __forceinline__ void for_each_marked(unsigned word, int wb, int lane, F f, int first = 0)
 {
   int incl = __popc(word);
 #pragma unroll
@@ -97,7 +93,7 @@ __device__ __forceinline__ void for_each_marked(unsigned word, int wb, int lane,
     if (lane >= d) incl += v;
   }
   const int total = __shfl_sync(kFullMask, incl, 31);
-  for (int base = 0; base < total; base += 32) {
+  for (int base = first; base < total; base += 32) {
     const int x = base + lane;
     int lo = 0;                                      // first lane whose inclusive count exceeds x
 #pragma unroll
@@ -117,9 +113,8 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
 {
   using Stage = typename std::conditional<RES, ResidentStage, WarpStage>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ FixRound s_round;
-  __shared__ __align__(16) int s_ctl[kCtlWords];      // ring[0..11], status[0..7] as of the last barrier
-  const int *s_ring = s_ctl, *s_stat = s_ctl + 12;
+  __shared__ FixRound s_fix[2];                       // by round parity
+  __shared__ __align__(16) unsigned s_ctl[4];         // SingleWs::sync as of the last barrier
   Stage &S = reinterpret_cast<Stage *>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int nthreads = gridDim.x * blockDim.x;
@@ -130,14 +125,19 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
   int tr = 0;
   MNTR_TRACE();
   if (lane == 0) { S.tcount = 0; S.pad_[0] = 0; }
+  if (threadIdx.x < 2) {      // round r (parity c = r & 1) merges into box[c ^ 1], marks touched[c], flags due[c ^ 1]
+    const int c = threadIdx.x;
+    s_fix[c] = FixRound{0u, 0u, W.box[c ^ 1], W.touched[c], W.due[c ^ 1], W.sync, P.csc_ptr, P.csc_row};
+  }
 
 
   // contiguous row range of this warp
   const int rpw = (P.m + n_warps - 1) / n_warps;
   const int r0 = min(P.m, warp_g * rpw), r1 = min(P.m, r0 + rpw);
   // RES: the lane's row head stays in registers, the row's entries in the warp's slice of shared memory
+  // (the head's loads are issued here and first used after the box has been set up: the trips overlap)
   RowHead head{0, -1, 0.0, 0.0};
-  if constexpr (RES) head = resident_load(P, S, lane, r0 + lane < r1 ? r0 + lane : -1);
+  if constexpr (RES) head = load_head(P, r0 + lane < r1 ? r0 + lane : -1);
 
   // ---- phase 0: both boxes = incoming box; round 1's rows all due; moved-variable bit sets empty, except that
   //      integer variables whose INCOMING bounds are fractional move in round 1 by rounding alone: they are
@@ -164,10 +164,18 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
     // round 1 takes every row without looking at its bit set (:1618-1622)
     const int nw_rows = (P.m + 31) / 32;
     for (int w = gtid; w < nw_rows; w += nthreads) { W.due[0][w] = 0u; W.due[1][w] = 0u; }
-    if (cross0) W.status[5] = 1;
+    if (cross0) atomicOr(W.sync + 3, kCtlInCross);
+    // the CSC lists (rows to flag when a variable moves) are first needed at the end of round 1, on its critical
+    // path: pull them into L2 now
+    const char *cp = reinterpret_cast<const char *>(P.csc_ptr), *cr = reinterpret_cast<const char *>(P.csc_row);
+    for (long long o = (long long)gtid * 128; o < (long long)(P.n + 1) * 4; o += (long long)nthreads * 128)
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(cp + o));
+    for (long long o = (long long)gtid * 128; o < (long long)P.csc_nnz * 4; o += (long long)nthreads * 128)
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(cr + o));
   }
+  if constexpr (RES) resident_fill(P, S, lane, head);
   MNTR_TRACE();
-  grid_barrier(W.bar, gridDim.x, bar_target, W.ring, s_ctl, nullptr);
+  grid_barrier(W.sync, gridDim.x, bar_target, s_ctl, nullptr);
   MNTR_TRACE();
 
   unsigned long long my_nnz = 0, my_rows = 0;
@@ -184,25 +192,54 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
 
   while (verdict == 0) {
     ++round;
-    const int cur = round & 1, slot = round % 3;
+    const int cur = round & 1;
     const double2 *A = W.box[cur];
     double2 *Z = W.box[cur ^ 1];
-    if (threadIdx.x == 0) {
-      if (blockIdx.x == 0) { const int nx = (round + 1) % 3; W.ring[nx] = 0; W.ring[3 + nx] = 0; }
-      s_round = FixRound{Z, W.touched[cur], W.due[cur ^ 1], &W.ring[slot], &W.ring[3 + slot], &W.status[0],
-                         P.csc_ptr, P.csc_row};
-    }
-    __syncthreads();
 
     // the fix-up (below) scans the previous round's moved-variable bit set: fetch this warp's first words now, so
     // the load is in flight while the rows are evaluated
     uint32_t *Tp = W.touched[cur ^ 1];
     unsigned fw = (fw0 + lane < fw1) ? __ldcg(Tp + fw0 + lane) : 0u;
 
+    // ---- fix-up, first half: the variables that moved in the previous round (Z lags behind A exactly there).  The
+    //      first 32 of this warp's words -- one variable per lane -- have their loads issued NOW, ahead of the rows, and
+    //      are merged after them: the trip to L2 rides along with the rows' own ----
+    int fj = -1;
+    double2 fv = make_double2(0.0, 0.0);
+    uint8_t fty = 4;
+    bool fmore = false;         // more than 32 marks in the first 32 words (rare)
+    if (round > 1) {
+      if (fw) { Tp[fw0 + lane] = 0u; atomicOr(W.ever + fw0 + lane, fw); }     // this lane owns word fw0 + lane in every round
+      my_changes += __popc(fw);
+      if (__any_sync(kFullMask, fw != 0u)) {
+        int incl = __popc(fw);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(kFullMask, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const int total = __shfl_sync(kFullMask, incl, 31);
+        fmore = total > 32;
+        int lo = 0;                                      // first lane whose inclusive count exceeds `lane`
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int v = __shfl_sync(kFullMask, incl, lo + step - 1);
+          if (v <= lane) lo += step;
+        }
+        const unsigned wword = __shfl_sync(kFullMask, fw, lo);
+        const int wincl = __shfl_sync(kFullMask, incl, lo);
+        if (lane < total) {
+          fj = (fw0 + lo) * 32 + (int)__fns(wword, 0, lane - (wincl - __popc(wword)) + 1);
+          fv = __ldcg(A + fj);
+          fty = __ldg(P.var_type + fj);
+        }
+      }
+    }
+
     // ---- rows due in this round ----
     {
       const ReadPending rd{A, P.colx, round > 1};
-      const SinkFix sink{&s_round, (W.trace != nullptr && blockIdx.x == 0 && threadIdx.x < 32) ? W.trace + 32 : nullptr,
+      const SinkFix sink{&s_fix[cur], (unsigned)round, (W.trace != nullptr && blockIdx.x == 0 && threadIdx.x < 32) ? W.trace + 32 : nullptr,
                          (W.trace != nullptr && round < 16) ? W.trace + kTraceBlk + (blockIdx.x * 16 + round) * 8 : nullptr};
       if constexpr (RES) eval_due_resident<R>(P, rd, sink, S, W.due[cur], r0, r1, head, round == 1, lane, my_nnz, my_rows);
       else eval_due_range<R>(P, rd, sink, S, W.due[cur], r0, r1, round == 1, lane, my_nnz, my_rows);
@@ -214,50 +251,60 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
         if (lane == 0) { my_nnz += (unsigned long long)P.cut_cnt; ++my_rows; }
       }
     }
-    // ---- fix-up: the variables that moved in the previous round.  It runs AFTER the rows (nothing in this round's
-    //      evaluation depends on it; it only has to land before the barrier); the set bits of 32 words are spread
-    //      over the lanes, so every moved variable is an independent chain ----
+    // ---- fix-up, second half.  It only has to land before the barrier; the set bits of 32 words are spread over
+    //      the lanes, so every moved variable is an independent chain ----
     {
       int bad = 0;
-      for (int wb = fw0; wb < fw1; wb += 32) {
-        const int w = wb + lane;
-        const unsigned word = wb == fw0 ? fw : ((w < fw1) ? __ldcg(Tp + w) : 0u);
-        if (word) { Tp[w] = 0u; __stcg(W.ever + w, __ldcg(W.ever + w) | word); }     // this lane owns word w in every round
-        my_changes += __popc(word);
-        for_each_marked(word, wb, lane, [&](int j) {
-          if (round == 1) {                      // moved by rounding alone: only its rows need flagging
-            flag_rows_serial(P, j, W.due[0]);
-            W.ring[slot] = 1;
-          } else {
-            double2 v = __ldcg(A + j);
-            atomic_max_f64(&Z[j].x, v.x);        // Z lags behind A exactly where A moved last round
-            atomic_min_f64(&Z[j].y, v.y);
-            if (is_int_type(__ldg(P.var_type + j))) tighten_int_bounds(v.x, v.y);
-            if (v.x > v.y + kETol) bad = 1;      // checkBounds_ of the box this round reads
-          }
-        });
+      auto fix = [&](int j, double2 v, uint8_t ty) {
+        atomic_max_f64(&Z[j].x, v.x);
+        atomic_min_f64(&Z[j].y, v.y);
+        if (is_int_type(ty)) tighten_int_bounds(v.x, v.y);
+        if (v.x > v.y + kETol) bad = 1;          // checkBounds_ of the box this round reads
+      };
+      if (round == 1) {
+        // integer variables whose INCOMING bounds are fractional moved by rounding alone: only their rows need flagging
+        for (int wb = fw0; wb < fw1; wb += 32) {
+          const int w = wb + lane;
+          const unsigned word = wb == fw0 ? fw : ((w < fw1) ? __ldcg(Tp + w) : 0u);
+          if (word) { Tp[w] = 0u; atomicOr(W.ever + w, word); }
+          my_changes += __popc(word);
+          for_each_marked(word, wb, lane, [&](int j) { flag_rows_serial(P, j, W.due[0]); atomicMax(W.sync + 1, 1u); });
+        }
+      } else {
+        if (fj >= 0) fix(fj, fv, fty);
+        if (fmore) {
+          for_each_marked(fw, fw0, lane, [&](int j) { fix(j, __ldcg(A + j), __ldg(P.var_type + j)); }, 32);
+        }
+        for (int wb = fw0 + 32; wb < fw1; wb += 32) {
+          const int w = wb + lane;
+          const unsigned word = (w < fw1) ? __ldcg(Tp + w) : 0u;
+          if (word) { Tp[w] = 0u; atomicOr(W.ever + w, word); }
+          my_changes += __popc(word);
+          for_each_marked(word, wb, lane, [&](int j) { fix(j, __ldcg(A + j), __ldg(P.var_type + j)); });
+        }
       }
-      if (bad) W.status[3] = 1;
+      if (bad) atomicOr(W.sync + 3, kCtlVarCross);
     }
     if (W.trace != nullptr && round < 16 && lane == 0) atomicMax(W.trace + kTraceBlk + (blockIdx.x * 16 + round) * 8 + 6, globaltimer_ns());
     MNTR_TRACE();
-    grid_barrier(W.bar, gridDim.x, bar_target, W.ring, s_ctl,
+    grid_barrier(W.sync, gridDim.x, bar_target, s_ctl,
                  (W.trace != nullptr && round < 16) ? W.trace + 64 + blockIdx.x * 16 + round : nullptr);
     MNTR_TRACE();
 
-    if (s_stat[3]) {                      // the box this round read was already crossed: found after round-1
+    const unsigned ctl_flags = s_ctl[3];
+    if (ctl_flags & kCtlVarCross) {                      // the box this round read was already crossed: found after round-1
       verdict = 1; rounds_out = round - 1; out_buf = cur; out_round = true;
       break;
     }
     rounds_out = round;
-    if (s_stat[0]) {                      // activity-infeasible row: the box of the round start is handed back
+    if (ctl_flags & kCtlRowInf) {                      // activity-infeasible row: the box of the round start is handed back
       verdict = 2 /* MNTR_INFEAS_ROW */; out_buf = cur; out_round = round > 1;
       break;
     }
     out_buf = cur ^ 1; out_round = true;
-    if (round == 1 && (s_stat[4] || s_stat[5])) { verdict = 1; break; }    // checkBounds_ after round 1
-    const int any_changed = s_ring[slot];
-    const int any_int = s_ring[3 + slot];
+    if (round == 1 && (ctl_flags & (kCtlRowCross | kCtlInCross))) { verdict = 1; break; }    // checkBounds_ after round 1
+    const bool any_changed = s_ctl[1] == (unsigned)round;
+    const bool any_int = s_ctl[2] == (unsigned)round;
     if (!any_changed) break;
     final_check = true;
     if (max_rounds > 0 && round >= max_rounds) break;
@@ -287,7 +334,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
         if (b.x > b.y + kETol) bad = 1;            // bound check of what the last round moved (no fix-up follows)
       });
     }
-    if (bad && final_check) W.status[3] = 1;
+    if (bad && final_check) atomicOr(W.sync + 3, kCtlVarCross);
   }
   __shared__ unsigned long long s_nnz, s_rows;
   __shared__ int s_changes;
@@ -311,12 +358,12 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
     __threadfence();
     if (atomicAdd(W.done, 1u) == gridDim.x - 1) {
       __threadfence();
-      const int32_t *src = W.ring;                 // the control block starts with ring[]
+      const int32_t *src = reinterpret_cast<const int32_t *>(W.sync);      // the control block starts with sync[]
       int32_t v[kCtrlWords];
 #pragma unroll
       for (int k = 0; k < kCtrlWords; ++k) v[k] = __ldcg(src + k);
 #pragma unroll
-      for (int k = 0; k < kCtrlWords; ++k) { W.result[k] = v[k]; W.ring[k] = 0; }
+      for (int k = 0; k < kCtrlWords; ++k) { W.result[k] = v[k]; reinterpret_cast<int32_t *>(W.sync)[k] = 0; }
     }
   }
   MNTR_TRACE();

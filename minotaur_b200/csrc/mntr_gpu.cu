@@ -27,9 +27,9 @@ using namespace mntr;
 // host mirror of the single-box kernel's control block (SingleWs::ring/status/counters/bar)
 constexpr int kTraceWords = 64 + 256 * 16 + 256 * 16 * 8;   // MNTR_GPU_TRACE buffer: phases, one warp's passes, barrier arrivals
 struct SingleCtrl {
-  int32_t ring[12]; int32_t status[8]; unsigned long long counters[2]; unsigned bar; unsigned done; unsigned pad[6];
+  unsigned sync[4]; int32_t status[8]; unsigned long long counters[2]; unsigned done; unsigned pad[15];
   // the loop's verdict, or MNTR_INFEAS_BOUNDS when the bound check of the last round's moved variables failed
-  int verdict() const { return status[6] ? status[6] : (status[3] ? 1 : 0); }
+  int verdict() const { return status[6] ? status[6] : ((sync[3] & mntr::kCtlVarCross) ? 1 : 0); }
 };
 static_assert(sizeof(SingleCtrl) == 128, "control block layout");
 
@@ -406,6 +406,7 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if ((rc = dev_upload(ctx, ctx->lin_allocs, var_type, (size_t)n, &L.var_type))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, cptr.data(), (size_t)n + 1, &L.csc_ptr))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, crow.data(), (size_t)nnz, &L.csc_row))) return rc;
+  L.csc_nnz = (int32_t)nnz;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, lptr.data(), (size_t)n_levels + 1, &L.level_ptr))) return rc;
 
   // ---- single-box workspace ----
@@ -424,10 +425,9 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if ((rc = dalloc((void **)&ctx->d_lb, sizeof(double) * (size_t)n))) return rc;
   if ((rc = dalloc((void **)&ctx->d_ub, sizeof(double) * (size_t)n))) return rc;
   if ((rc = dalloc(&ctx->d_ctrl, sizeof(SingleCtrl)))) return rc;
-  W.ring = (int32_t *)ctx->d_ctrl;
-  W.status = W.ring + 12;
+  W.sync = (unsigned *)ctx->d_ctrl;
+  W.status = (int32_t *)((char *)ctx->d_ctrl + offsetof(SingleCtrl, status));
   W.counters = (unsigned long long *)((char *)ctx->d_ctrl + offsetof(SingleCtrl, counters));
-  W.bar = (unsigned *)((char *)ctx->d_ctrl + offsetof(SingleCtrl, bar));
   W.done = (unsigned *)((char *)ctx->d_ctrl + offsetof(SingleCtrl, done));
   if (!ctx->h_single) CU(cudaHostAlloc((void **)&ctx->h_single, sizeof(SingleCtrl), cudaHostAllocMapped));
   {

@@ -77,8 +77,37 @@ struct ReadPending {
 // Sinks: where accepted candidates go.
 // ---------------------------------------------------------------------------------------------------------------
 
+// The rows of up to 32 moved variables, one per lane (len == 0: none), are flagged for the next round [changeBFlag_
+// :1229-1234]: their CSC lists [qb, qb + len) are laid end to end and taken ENTRY-PARALLEL, one trip to L2 per 32
+// rows to flag.  Convergent.
+__device__ __forceinline__ void flag_lists(int qb, int len, int lane, const int32_t *csc_row, uint32_t *due_next)
+{
+  int incl = len;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(kFullMask, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int total = __shfl_sync(kFullMask, incl, 31);
+  for (int e0 = 0; e0 < total; e0 += 32) {
+    const int x = e0 + lane;
+    int lo = 0;                                      // first lane whose inclusive count exceeds x
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(kFullMask, incl, lo + step - 1);
+      if (v <= x) lo += step;
+    }
+    const int oqb = __shfl_sync(kFullMask, qb, lo), oincl = __shfl_sync(kFullMask, incl, lo);
+    const int olen = __shfl_sync(kFullMask, len, lo);
+    if (x < total) {
+      const int row = __ldg(csc_row + oqb + (x - (oincl - olen)));
+      atomicOr(due_next + (row >> 5), 1u << (row & 31));
+    }
+  }
+}
+
 struct FixRound;
-template <class Stage> static __device__ __noinline__ void flush_moved(Stage &S, int lane, const FixRound *rc);
+template <class Stage> static __device__ __noinline__ void flush_moved(Stage &S, int lane, const FixRound *rc, unsigned round);
 
 // One-barrier fixpoint kernel: candidates are merged into the NEXT round's box; a moved variable is marked in the
 // round's bit set (the next round's fix-up scans it) and its rows are flagged for the next round [changeBFlag_
@@ -88,15 +117,17 @@ template <class Stage> static __device__ __noinline__ void flush_moved(Stage &S,
 // The round's pointers live in shared memory (one copy per block): they are needed on rare paths only and must
 // not occupy registers during the row evaluation.
 struct FixRound {
+  unsigned seen_changed, seen_int;   // last round for which THIS BLOCK has already reported a move / an integer move
   double2 *next_box;
   uint32_t *touched;       // bit set: variable moved in this round
   uint32_t *due_next;      // row bit set of the next round   (Constraint bFlag)
-  int32_t *changed, *int_moved, *row_inf;
+  unsigned *sync;          // SingleWs::sync
   const int32_t *csc_ptr, *csc_row;
 };
 
 struct SinkFix {
-  const FixRound *rc;          // in shared memory
+  const FixRound *rc;          // in shared memory (one record per round parity, built once)
+  unsigned round;
   unsigned long long *probe;   // debug (MNTR_GPU_TRACE): time stamps of one warp's passes, or nullptr
   unsigned long long *blk;     // debug: per-block, per-round latest time any warp passed phase k, or nullptr
   __device__ __forceinline__ void phase(int lane, int k) const
@@ -122,10 +153,29 @@ struct SinkFix {
   template <class Stage> __device__ __forceinline__ void moved(Stage &S, int j, bool isint) const
   {
     S.list()[atomicAdd(&S.tcount, 1)] = j;
-    if (isint) *rc->int_moved = 1;       // a row moved an integer variable (nintmods, :1070-1133)
+    if (isint) int_moved();      // a row moved an integer variable (nintmods, :1070-1133)
   }
-  __device__ __forceinline__ void row_infeasible() const { *rc->row_inf = 1; }
-  __device__ __forceinline__ void row_bounds_cross() const { rc->row_inf[4] = 1; }     // status[4]
+  // without the list: mark a moved variable now; its rows are flagged by flag_lists()
+  // "a bound moved in this round" / "a row moved an integer variable in this round" are device-wide words that every
+  // block reads after the barrier; thousands of warps would report the same thing to the same address, and
+  // same-address atomics are served one after the other: a block reports each once per round
+  __device__ __forceinline__ void int_moved() const
+  {
+    FixRound *w = const_cast<FixRound *>(rc);
+    if (w->seen_int != round && atomicExch(&w->seen_int, round) != round) atomicMax(rc->sync + 2, round);
+  }
+  __device__ __forceinline__ void changed() const
+  {
+    FixRound *w = const_cast<FixRound *>(rc);
+    if (w->seen_changed != round && atomicExch(&w->seen_changed, round) != round) atomicMax(rc->sync + 1, round);
+  }
+  __device__ __forceinline__ void touch(int j, bool isint) const
+  {
+    atomicOr(rc->touched + (j >> 5), 1u << (j & 31));
+    if (isint) int_moved();      // nintmods, :1070-1133
+  }
+  __device__ __forceinline__ void row_infeasible() const { atomicOr(rc->sync + 3, kCtlRowInf); }
+  __device__ __forceinline__ void row_bounds_cross() const { atomicOr(rc->sync + 3, kCtlRowCross); }
   // no room for `room` more entries?
   template <class Stage> __device__ __forceinline__ bool near_full(const Stage &S, int room = 32) const { return S.tcount + room > Stage::kListCap; }
 
@@ -133,19 +183,19 @@ struct SinkFix {
   template <class Stage> __device__ __forceinline__ void flush(Stage &S, int lane) const
   {
     __syncwarp();
-    if (S.tcount != 0) flush_moved(S, lane, rc);
+    if (S.tcount != 0) flush_moved(S, lane, rc, round);
   }
 };
 
 // out of line: rare, and called from several places
 template <class Stage>
-static __device__ void flush_moved(Stage &S, int lane, const FixRound *rc)
+static __device__ void flush_moved(Stage &S, int lane, const FixRound *rc, unsigned round)
 {
   uint32_t *due_next = rc->due_next, *touched = rc->touched;
   const int32_t *csc_ptr = rc->csc_ptr, *csc_row = rc->csc_row;
   const int n = S.tcount;
   const int *tl = S.list();
-  if (lane == 0) *rc->changed = 1;
+  if (lane == 0) SinkFix{rc, round, nullptr, nullptr}.changed();
   for (int base = 0; base < n; base += 32) {
     const int idx = base + lane;
     int qb = 0, len = 0;
@@ -154,29 +204,7 @@ static __device__ void flush_moved(Stage &S, int lane, const FixRound *rc)
       qb = __ldg(csc_ptr + j); len = __ldg(csc_ptr + j + 1) - qb;
       atomicOr(touched + (j >> 5), 1u << (j & 31));
     }
-    // the CSC lists of these (up to 32) variables laid end to end, taken ENTRY-PARALLEL: one trip per 32 rows to flag
-    int incl = len;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(kFullMask, incl, d);
-      if (lane >= d) incl += v;
-    }
-    const int total = __shfl_sync(kFullMask, incl, 31);
-    for (int e0 = 0; e0 < total; e0 += 32) {
-      const int x = e0 + lane;
-      int lo = 0;                                      // first lane whose inclusive count exceeds x
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const int v = __shfl_sync(kFullMask, incl, lo + step - 1);
-        if (v <= x) lo += step;
-      }
-      const int oqb = __shfl_sync(kFullMask, qb, lo), oincl = __shfl_sync(kFullMask, incl, lo);
-      const int olen = __shfl_sync(kFullMask, len, lo);
-      if (x < total) {
-        const int row = __ldg(csc_row + oqb + (x - (oincl - olen)));
-        atomicOr(due_next + (row >> 5), 1u << (row & 31));
-      }
-    }
+    flag_lists(qb, len, lane, csc_row, due_next);
   }
   __syncwarp();
   if (lane == 0) S.tcount = 0;
@@ -314,8 +342,8 @@ __device__ __forceinline__ void eval_staged(const LinDev &P, const Reader &rd, c
         if (pos ? (b[u].y >= kInf20) : (b[u].x <= -kInf20)) f |= kHiInf;
         if (!(fabs(a[u]) > kETol)) f |= kTiny;
         S.flag[e] = f;
-        // |a|(ub-lb) with a 1e-9 relative margin, rounded UP to a float: conservative, inf/NaN fall through
-        reach[k] = __double2float_ru(fabs(a[u]) * (b[u].y - b[u].x) * 1.000000001);
+        // term_reach rounded UP to a float: conservative, inf falls through
+        reach[k] = __double2float_ru(term_reach(a[u], b[u]));
       }
     }
   }
@@ -359,7 +387,7 @@ __device__ __forceinline__ void eval_staged(const LinDev &P, const Reader &rd, c
     if (e < T) {
       const int s = S.slot[e];
       const double rch = (double)reach[k];
-      if (!(S.slack_lb[s] > rch) || !(S.slack_ub[s] > rch)) need |= 1u << k;
+      if (!(S.slack_lb[s] >= rch) || !(S.slack_ub[s] >= rch)) need |= 1u << k;
     }
   }
   while (need) {                          // one copy of the exact path, whatever the entry
@@ -434,8 +462,8 @@ __device__ __forceinline__ void eval_long(const double *val, const Reader &rd, c
       int j; bool isint;
       const double a = __ldg(val + beg + t);
       const double2 b = rd.get(beg + t, j, isint);
-      const double rch = fabs(a) * (b.y - b.x) * 1.000000001;
-      if (!(slb > rch) || !(sub > rch)) emit_exact<R>(slb, sub, sg, a, j, isint, b, S, sink);
+      const double rch = term_reach(a, b);
+      if (!(slb >= rch) || !(sub >= rch)) emit_exact<R>(slb, sub, sg, a, j, isint, b, S, sink);
     }
   }
   sink.flush(S, lane);

@@ -7,31 +7,28 @@
 //   * the row head {first entry, term count, row lb, row ub} stays in the lane's registers;
 //   * the first kRes entries {column | integer bit, coefficient} of the row stay in the warp's slice of shared memory,
 //     transposed (entry t of the row of lane l at [t][l]: conflict-free); the 148 SMs together hold the matrix.
-// A round then is, per due row, ONE dependent trip to L2 (the {lb,ub} gathers, up to four in flight per lane, all
-// lanes of all warps at once) followed by register arithmetic:
-//   pass 1  products a*blo (rounded down) / a*bhi (rounded up) added IN ASCENDING COLUMN ORDER [getLfBnds_ :1237-1258],
-//           |a|(ub-lb) of every entry kept as a float rounded up; the singleton-infinity sums [getSingLfBnds_
-//           :1261-1319] are a second, rare pass (only rows with an infinite activity)
-//   pass 2  product test slack < |a|(ub-lb) per entry from registers; only entries that can move a bound re-derive the
-//           exact candidate [updateLfBoundsFromLb_/Ub_ :1048-1226] and hand it to the Sink.
+// A round then takes one of two forms, picked per warp and round:
+//   * lane = ROW (dense rounds, eval_resident): pass 1 gathers {lb,ub} four at a time per lane and adds the products
+//     a*blo (rounded down) / a*bhi (rounded up) IN ASCENDING COLUMN ORDER [getLfBnds_ :1237-1258], keeping
+//     term_reach() of every entry as a float rounded up; the singleton-infinity sums [getSingLfBnds_ :1261-1319] are a
+//     second, rare pass; pass 2 is the product test from registers.  The entries that pass it are few and spread
+//     unevenly over the rows, and the exact path [updateLfBoundsFromLb_/Ub_ :1048-1226] is long (two directed fp64
+//     divisions), so the (row lane, entry) pairs of the whole warp are compacted into a work list and taken
+//     ENTRY-PARALLEL, 32 per trip;
+//   * lane = ENTRY (sparse rounds: at most 32 due entries in the warp, eval_packed): one gather per lane, the row's own
+//     lane adds the products in column order through shuffles, and an entry derives its exact candidate from the
+//     bounds it already holds.  A sparse round is bound by the instructions on this path, not by bandwidth.
+// In both, the CSC list of an entry's variable is looked up speculatively with the gather, so a moved variable's rows
+// are flagged [changeBFlag_ :1229-1234] one trip later (flag_lists: the lists laid end to end, entry-parallel).
 // Entries beyond kRes of a row are read from the CSR in global memory by the same lane; rows longer than kLaneMax are
-// evaluated by the whole warp (eval_long in row_batch.cuh).  Compared with the staged, entry-parallel form
-// (row_batch.cuh) there is no staging of products, no slot indirection, and a sparse round costs a warp a few
-// hundred instructions instead of a few thousand -- sparse rounds are bound by exactly that serial path.
+// evaluated by the whole warp (eval_long in row_batch.cuh).
 #pragma once
 #include "row_batch.cuh"
 
 namespace mntr {
 
 constexpr int kRes = 12;        // resident entries per row
-#ifndef MNTR_K1_GROUP
-#define MNTR_K1_GROUP 4
-#endif
-#ifndef MNTR_K1_REACH_SMEM
-#define MNTR_K1_REACH_SMEM 0
-#endif
-constexpr int kPassGroup = MNTR_K1_GROUP;   // gathers a lane has in flight in pass 1
-constexpr int kResGroup = 4;    // exact candidates a lane derives per trip
+constexpr int kPassGroup = 4;    // gathers a lane has in flight in pass 1
 constexpr int kLaneMax = 32;    // rows longer than this are evaluated by the whole warp
 static_assert(kRes % kPassGroup == 0, "pass 1 runs in groups");
 static_assert(kLaneMax <= 32, "pass 2 keeps one bit per entry");
@@ -45,17 +42,13 @@ struct __align__(16) ResidentStage {
   static constexpr int kListCap = 256;
   int items[kListCap];
   uint16_t work[32 * kLaneMax];     // (row lane | entry << 5) of the entries whose exact candidates are due
-#if MNTR_K1_REACH_SMEM
-  float reach[kRes][32];   // |a|(ub-lb) of the resident entries, rounded up (pass 1 -> pass 2)
-#endif
   __device__ __forceinline__ int *list() { return items; }
 };
 static_assert(sizeof(ResidentStage) % 16 == 0, "slices are laid out back to back");
 
-// phase 0: the lane's row head into registers, its first kRes entries into the slice
-__device__ __forceinline__ RowHead resident_load(const LinDev &P, ResidentStage &S, int lane, int row)
+// phase 0: the lane's row head is in registers (load_head); its first kRes entries go into the slice
+__device__ __forceinline__ void resident_fill(const LinDev &P, ResidentStage &S, int lane, const RowHead h)
 {
-  const RowHead h = load_head(P, row);
   if (h.cnt > 0) {
     const int keep = h.cnt < kRes ? h.cnt : kRes;
     // rows start at a multiple of four entries and are padded to one (val == 0): 128-bit loads
@@ -69,7 +62,6 @@ __device__ __forceinline__ RowHead resident_load(const LinDev &P, ResidentStage 
       S.val[t][lane] = v0.x; S.val[t + 1][lane] = v0.y; S.val[t + 2][lane] = v1.x; S.val[t + 3][lane] = v1.y;
     }
   }
-  return h;
 }
 
 // entry t of the lane's row
@@ -78,6 +70,27 @@ __device__ __forceinline__ void resident_entry(const LinDev &P, const ResidentSt
 {
   if (t < kRes) { a = S.val[t][lane]; cx = S.colx[t][lane]; }
   else { a = __ldg(P.val + beg + t); cx = __ldg(P.colx + beg + t); }
+}
+
+// singleton-infinity sums of the lane's row [getSingLfBnds_ :1261-1319]: finite sum + infinity count per side.  Rare
+// (only rows with an infinite activity), serial, out of line.
+template <class R>
+__device__ __noinline__ void singleton_sums(const LinDev &P, const ReadPending &rd, const ResidentStage &S, int lane,
+                                            const RowHead h, double &sing_ll, double &sing_uu)
+{
+  double fs_lo = 0.0, fs_hi = 0.0;
+  int ninf_lo = 0, ninf_hi = 0;
+  for (int t = 0; t < h.cnt; ++t) {
+    double a; int cx, j; bool isint;
+    resident_entry(P, S, lane, h.beg, t, a, cx);
+    if (!(fabs(a) > kETol)) continue;
+    const double2 bt = rd.fetch(cx, j, isint);
+    const bool pos = a > 0.0;
+    if (pos ? (bt.x <= -kInf20) : (bt.y >= kInf20)) ++ninf_lo; else fs_lo = R::add_lo(fs_lo, R::mul_lo(a, pos ? bt.x : bt.y));
+    if (pos ? (bt.y >= kInf20) : (bt.x <= -kInf20)) ++ninf_hi; else fs_hi = R::add_hi(fs_hi, R::mul_hi(a, pos ? bt.y : bt.x));
+  }
+  sing_ll = (ninf_lo >= 2) ? -INFINITY : fs_lo;
+  sing_uu = (ninf_hi >= 2) ? INFINITY : fs_hi;
 }
 
 // One round of the rows of this warp: lane = row.  `due`: the lane's row is evaluated in this round (h.cnt >= 0).
@@ -100,16 +113,12 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
   double slb = INFINITY, sub = INFINITY;
   uint8_t sg = 0;
   {
-#if !MNTR_K1_REACH_SMEM
     float reach[kRes];
-#endif
 #pragma unroll
     for (int g = 0; g < kRes / kPassGroup; ++g) {
       if (g * kPassGroup >= maxc) {            // warp-uniform: no row of the warp reaches this group
-#if !MNTR_K1_REACH_SMEM
 #pragma unroll
         for (int u = 0; u < kPassGroup; ++u) reach[g * kPassGroup + u] = 0.f;
-#endif
         continue;
       }
       double2 b[kPassGroup];
@@ -122,22 +131,15 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
 #pragma unroll
       for (int u = 0; u < kPassGroup; ++u) {
         const int t = g * kPassGroup + u;
-#if !MNTR_K1_REACH_SMEM
         reach[t] = 0.f;
-#endif
         if (t < cnt) {
           const double a = S.val[t][lane];
           if (rd.round_ints && S.colx[t][lane] < 0) tighten_int_bounds(b[u].x, b[u].y);
           const bool pos = a > 0.0;
           ll = R::add_lo(ll, R::mul_lo(a, pos ? b[u].x : b[u].y));
           uu = R::add_hi(uu, R::mul_hi(a, pos ? b[u].y : b[u].x));
-          // |a|(ub-lb) with a 1e-9 relative margin, rounded UP to a float: conservative, inf/NaN fall through
-          const float rch = __double2float_ru(fabs(a) * (b[u].y - b[u].x) * 1.000000001);
-#if MNTR_K1_REACH_SMEM
-          S.reach[t][lane] = rch;
-#else
-          reach[t] = rch;
-#endif
+          // term_reach rounded UP to a float: conservative, inf falls through
+          reach[t] = __double2float_ru(term_reach(a, b[u]));
         }
       }
     }
@@ -156,21 +158,7 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
     // ---- what the row offers its terms ----
     if (mine) {
       double sing_ll = -INFINITY, sing_uu = INFINITY;
-      if (ll < -kInf20 || uu > kInf20) {          // singleton-infinity sums: finite sum + infinity count per side (rare)
-        double fs_lo = 0.0, fs_hi = 0.0;
-        int ninf_lo = 0, ninf_hi = 0;
-        for (int t = 0; t < cnt; ++t) {
-          double a; int cx, j; bool isint;
-          resident_entry(P, S, lane, h.beg, t, a, cx);
-          if (!(fabs(a) > kETol)) continue;
-          const double2 bt = rd.fetch(cx, j, isint);
-          const bool pos = a > 0.0;
-          if (pos ? (bt.x <= -kInf20) : (bt.y >= kInf20)) ++ninf_lo; else fs_lo = R::add_lo(fs_lo, R::mul_lo(a, pos ? bt.x : bt.y));
-          if (pos ? (bt.y >= kInf20) : (bt.x <= -kInf20)) ++ninf_hi; else fs_hi = R::add_hi(fs_hi, R::mul_hi(a, pos ? bt.y : bt.x));
-        }
-        sing_ll = (ninf_lo >= 2) ? -INFINITY : fs_lo;
-        sing_uu = (ninf_hi >= 2) ? INFINITY : fs_hi;
-      }
+      if (ll < -kInf20 || uu > kInf20) singleton_sums<R>(P, rd, S, lane, h, sing_ll, sing_uu);     // rare
       if (ll > h.ru + kETol || uu < h.rl - kETol) sink.row_infeasible();     // :994-1015
       else row_offers<R>(h.rl, h.ru, ll, uu, sing_ll, sing_uu, slb, sub, sg);
     }
@@ -179,12 +167,8 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
 #pragma unroll
     for (int t = 0; t < kRes; ++t) {
       if (t < cnt) {
-#if MNTR_K1_REACH_SMEM
-        const double rch = (double)S.reach[t][lane];
-#else
         const double rch = (double)reach[t];
-#endif
-        if (!(slb > rch) || !(sub > rch)) need |= 1u << t;
+        if (!(slb >= rch) || !(sub >= rch)) need |= 1u << t;
       }
     }
   }
@@ -193,8 +177,8 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
       int j; bool isint;
       const double a = __ldg(P.val + h.beg + t);
       const double2 bt = rd.get(h.beg + t, j, isint);
-      const double rch = fabs(a) * (bt.y - bt.x) * 1.000000001;
-      if (!(slb > rch) || !(sub > rch)) need |= 1u << t;
+      const double rch = term_reach(a, bt);
+      if (!(slb >= rch) || !(sub >= rch)) need |= 1u << t;
     }
   }
   sink.mark(S, lane); sink.phase(lane, 2);
@@ -217,19 +201,29 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
       for (unsigned nd = need; nd; nd &= nd - 1) S.work[pos++] = (uint16_t)(lane | ((__ffs(nd) - 1) << 5));
       __syncwarp();
       for (int base = 0; base < total; base += 32) {
-        if (sink.near_full(S, 32)) sink.flush(S, lane);          // warp-uniform (tcount is read behind a barrier)
         const bool on = base + lane < total;
         const int item = on ? S.work[base + lane] : 0;
         const int rl = item & 31, t = item >> 5;
         const double o_slb = __shfl_sync(kFullMask, slb, rl), o_sub = __shfl_sync(kFullMask, sub, rl);
         const int o_sg = __shfl_sync(kFullMask, (int)sg, rl), o_beg = __shfl_sync(kFullMask, h.beg, rl);
+        int qb = 0, len = 0;
         if (on) {
           double a; int cx, j; bool isint;
           resident_entry(P, S, rl, o_beg, t, a, cx);
           const double2 bt = rd.fetch(cx, j, isint);
-          emit_exact<R>(o_slb, o_sub, o_sg, a, j, isint, bt, S, sink);
+          // speculative: where the variable's row list is, should it move (rides along with the gather)
+          qb = __ldg(P.csc_ptr + j);
+          const int qe = __ldg(P.csc_ptr + j + 1);
+          const double2 c = exact_candidates<R>(o_slb, o_sub, o_sg, a, bt.x, bt.y);
+          const bool up = c.x > bt.x, down = c.y < bt.y;
+          if (up) sink.raise_lb(S, j, isint, c.x);
+          if (down) sink.lower_ub(S, j, isint, c.y);
+          if (up || down) { sink.touch(j, isint); len = qe - qb; }
         }
-        __syncwarp();
+        if (__any_sync(kFullMask, len != 0)) {
+          if (lane == 0) sink.changed();
+          flag_lists(qb, len, lane, P.csc_row, sink.rc->due_next);
+        }
       }
     }
   }
@@ -244,6 +238,87 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
     eval_long<R>(P.val, rd, sink, S, lane, bg, c, l, u);
   }
   sink.flush(S, lane);
+  sink.mark(S, lane); sink.phase(lane, 4);
+}
+
+// SPARSE rounds: the due rows of the warp have at most 32 entries in all, every one of them resident.  The entries are
+// laid end to end over the lanes (lane = ENTRY: one gather per lane, each entry's arithmetic done once instead of once
+// per unrolled slot), the row's own lane adds the products in ascending column order through shuffles, and an entry
+// that can move a bound derives its exact candidate from the bounds it already holds: one trip to L2 for the whole
+// evaluation, one more for the rows to flag.  A sparse round is bound by the instructions on this path, not by
+// bandwidth -- it is a third of the lane = row form's.
+template <class R, class Sink>
+__device__ __forceinline__ void eval_packed(const LinDev &P, const ReadPending &rd, const Sink &sink, ResidentStage &S,
+                                            int lane, bool due, const RowHead h, bool first, int incl, int total)
+{
+  if (first && due && h.rl > h.ru + kETol) sink.row_bounds_cross();     // checkBounds_, rows part (:328-359)
+  sink.mark(S, lane); sink.phase(lane, 0);
+  const int cnt = due ? h.cnt : 0;
+  const int off = incl - cnt;
+  // ---- lane = entry ----
+  int rl = 0;                                      // the row lane of entry `lane`: first lane whose inclusive count exceeds it
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const int v = __shfl_sync(kFullMask, incl, rl + step - 1);
+    if (v <= lane) rl += step;
+  }
+  const int roff = __shfl_sync(kFullMask, off, rl);
+  const bool on = lane < total;
+  double a = 0.0, plo = 0.0, phi = 0.0, rch = 0.0;
+  double2 b = make_double2(0.0, 0.0);
+  int j = 0, qb = 0, qe = 0;
+  bool isint = false;
+  if (on) {
+    const int t = lane - roff;
+    a = S.val[t][rl];
+    b = rd.fetch(S.colx[t][rl], j, isint);
+    qb = __ldg(P.csc_ptr + j);                     // speculative: the variable's row list, should it move
+    qe = __ldg(P.csc_ptr + j + 1);
+    const bool pos = a > 0.0;
+    plo = R::mul_lo(a, pos ? b.x : b.y);
+    phi = R::mul_hi(a, pos ? b.y : b.x);
+    rch = term_reach(a, b);
+  }
+  // ---- lane = row: products added in ascending column order ----
+  double ll = 0.0, uu = 0.0;
+  const int maxc = __reduce_max_sync(kFullMask, cnt);
+  for (int t = 0; t < maxc; ++t) {
+    const double vlo = __shfl_sync(kFullMask, plo, off + t), vhi = __shfl_sync(kFullMask, phi, off + t);
+    if (t < cnt) { ll = R::add_lo(ll, vlo); uu = R::add_hi(uu, vhi); }
+  }
+  sink.mark(S, lane); sink.phase(lane, 1);
+  double slb = INFINITY, sub = INFINITY;
+  int sg = 0;
+  if (due) {
+    double sing_ll = -INFINITY, sing_uu = INFINITY;
+    if (ll < -kInf20 || uu > kInf20) singleton_sums<R>(P, rd, S, lane, h, sing_ll, sing_uu);     // rare
+    uint8_t sg8 = 0;
+    if (ll > h.ru + kETol || uu < h.rl - kETol) sink.row_infeasible();     // :994-1015
+    else row_offers<R>(h.rl, h.ru, ll, uu, sing_ll, sing_uu, slb, sub, sg8);
+    sg = sg8;
+  }
+  // ---- lane = entry: product test, rarely the exact candidate [updateLfBoundsFromLb_/Ub_ :1048-1226] ----
+  const double o_slb = __shfl_sync(kFullMask, slb, rl), o_sub = __shfl_sync(kFullMask, sub, rl);
+  const int o_sg = __shfl_sync(kFullMask, sg, rl);
+  const bool need = on && (!(o_slb >= rch) || !(o_sub >= rch));
+  sink.mark(S, lane); sink.phase(lane, 2);
+  int len = 0;
+  if (__any_sync(kFullMask, need)) {
+    if (need) {
+      const double2 c = exact_candidates<R>(o_slb, o_sub, o_sg, a, b.x, b.y);
+      const bool up = c.x > b.x, down = c.y < b.y;
+      if (up) sink.raise_lb(S, j, isint, c.x);
+      if (down) sink.lower_ub(S, j, isint, c.y);
+      if (up || down) { sink.touch(j, isint); len = qe - qb; }
+    }
+    sink.mark(S, lane); sink.phase(lane, 3);
+    if (__any_sync(kFullMask, len != 0)) {
+      if (lane == 0) sink.changed();
+      flag_lists(qb, len, lane, P.csc_row, sink.rc->due_next);
+    }
+  } else {
+    sink.mark(S, lane); sink.phase(lane, 3);
+  }
   sink.mark(S, lane); sink.phase(lane, 4);
 }
 
@@ -270,7 +345,17 @@ __device__ __forceinline__ void eval_due_resident(const LinDev &P, const ReadPen
   }
   const bool is_due = ((m >> lane) & 1u) && h.cnt >= 0;      // deleted rows (term count < 0) are never evaluated
   if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
-  eval_resident<R>(P, rd, sink, S, lane, is_due, h, first);
+  // few entries in all, every one resident: the entry-parallel form (sparse rounds); else lane = row
+  const int c = is_due ? h.cnt : 0;
+  int incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(kFullMask, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int total = __shfl_sync(kFullMask, incl, 31);
+  if (total <= 32 && !__any_sync(kFullMask, c > kRes)) eval_packed<R>(P, rd, sink, S, lane, is_due, h, first, incl, total);
+  else eval_resident<R>(P, rd, sink, S, lane, is_due, h, first);
 }
 
 }  // namespace mntr
