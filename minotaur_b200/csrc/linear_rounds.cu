@@ -12,12 +12,109 @@
 #include "device_problem.cuh"
 #include "kernels.h"
 #include "linear_row.cuh"
+#include "row_resident.cuh"
 
 namespace mntr {
 
 namespace {
 
 constexpr int kRoundsThreads = 256;
+
+// ---- dense 32-row blocks: lane = row straight from the CSR (eval_resident of row_resident.cuh, streaming form) ----
+// one warp's slice of shared memory: the queue of deferred exact candidates and, for a block with more candidates
+// than the queue holds, the work list
+struct __align__(16) StreamStage {
+  int tcount;
+  int pad_[3];             // [1] length of the candidate queue
+  CandItem q[kQueueCap];
+  uint16_t work[32 * kLaneMax];
+  static constexpr bool kSlab = false;
+  __device__ __forceinline__ uint16_t *work_list() { return work; }
+  __device__ __forceinline__ CandItem *queue() { return q; }
+};
+
+// candidates go into the split arrays nlb / nub; moved variables are found, rounded and their rows flagged by the vars
+// kernel after the cross-GPU merge, so nothing is marked here
+struct SinkRounds {
+  static constexpr bool kFlagsRows = false;
+  double *nlb, *nub;
+  int n;
+  template <class Stage> __device__ __forceinline__ void mark(Stage &, int) const {}
+  __device__ __forceinline__ void phase(int, int) const {}
+  template <class Stage> __device__ __forceinline__ void raise_lb(Stage &, int j, bool, double c) const { atomic_max_f64(&nlb[j], c); }
+  template <class Stage> __device__ __forceinline__ void lower_ub(Stage &, int j, bool, double c) const { atomic_min_f64(&nub[j], c); }
+  template <class Stage> __device__ __forceinline__ void moved(Stage &, int, bool) const {}
+  __device__ __forceinline__ void touch(int, bool) const {}
+  __device__ __forceinline__ void row_infeasible() const { nlb[n] = 2.0; }
+  __device__ __forceinline__ void row_bounds_cross() const {}      // checked by the init kernel
+  template <class Stage> __device__ __forceinline__ bool near_full(const Stage &, int = 32) const { return false; }
+  template <class Stage> __device__ __forceinline__ void flush(Stage &, int) const {}
+};
+
+// The rows of one phase, in blocks of 32 (one word of the bit set -- the reference's Constraint bFlag): blocks
+// bk = warp, warp + n_warps, ...; the due words of 32 of them are fetched at once (lane l looks at the l-th) and
+// cleared with a fire-and-forget atomic [setBFlag(false), :513].  Blocks with at least kDenseRows due rows (all blocks
+// in the first round) are evaluated lane = row; the due rows of a sparse block are taken 32/G at a time by sub-warp
+// groups of G lanes (process_row of linear_row.cuh).
+template <int G, class R>
+__device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W, StreamStage &S, int warp_global, int n_warps,
+                                              bool first, unsigned long long &my_nnz, unsigned long long &my_rows)
+{
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int lane_g = lane % G, g = lane / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lane_g));
+  const ReadPending rd{W.box, P.colx, false};          // the vars kernel stores rounded integer bounds
+  const SinkRounds sink{W.nlb, W.nub, P.n};
+  const SinkSplit split{W.nlb, W.nub, P.n};
+  const int n_blk = (P.m + 31) / 32;
+  for (int it0 = 0; warp_global + (long long)it0 * n_warps < n_blk; it0 += 32) {
+    const long long bl = warp_global + (long long)(it0 + lane) * n_warps;
+    unsigned word = 0u;
+    if (bl < n_blk) {
+      word = first ? kFullMask : __ldcg(W.bits + bl);                 // bits are set by L2 atomics: bypass L1
+      if (P.m - (int)bl * 32 < 32) word &= (1u << (P.m - (int)bl * 32)) - 1u;
+      if (!first && word) atomicAnd(W.bits + bl, ~word);
+    }
+    const bool dense = first ? word != 0u : __popc(word) >= kDenseRows;
+    unsigned dm = __ballot_sync(kFullMask, dense);
+    unsigned sm = __ballot_sync(kFullMask, word != 0u && !dense);
+    while (dm) {
+      const int k = __ffs(dm) - 1;
+      dm &= dm - 1;
+      const unsigned wk = __shfl_sync(kFullMask, word, k);
+      const int row = (warp_global + (it0 + k) * n_warps) * 32 + lane;
+      const bool bit = (wk >> lane) & 1u;
+      const RowHead h = load_head(P, bit ? row : -1);
+      const bool is_due = bit && h.cnt >= 0;                          // deleted rows are never evaluated
+      if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
+      eval_resident<R>(P, rd, sink, S, lane, is_due, h, false);
+    }
+    while (sm) {
+      const int k = __ffs(sm) - 1;
+      sm &= sm - 1;
+      const unsigned wk = __shfl_sync(kFullMask, word, k);
+      const int base = (warp_global + (it0 + k) * n_warps) * 32, nd = __popc(wk);
+      for (int x0 = 0; x0 < nd; x0 += GPW) {
+        const int x = x0 + g;
+        if (x >= nd) continue;                                        // group-uniform
+        const int i = base + (int)__fns(wk, 0, x + 1);
+        const int2 info = __ldg(P.row_info + i);
+        if (info.y < 0) continue;
+        process_row<G, R>(P, W.box, W.ctrl, split, i, info.x, info.y, lane_g, gmask, my_nnz, my_rows);
+      }
+      __syncwarp();
+    }
+  }
+  drain_queue<R>(P, rd, sink, S, lane);
+  // the objective cut-off row is evaluated in every round (the reference loops it to its own fixpoint in every
+  // sweep, LinearHandler.cpp:1636-1640); one group takes it
+  if (P.cut_cnt > 0 && warp_global == 0 && g == 0) {
+    LinDev C = P;
+    C.col = P.cut_col; C.val = P.cut_val; C.row_bnd = P.cut_bnd;
+    process_row<G, R>(C, W.box, W.ctrl, split, 0, 0, P.cut_cnt, lane_g, gmask, my_nnz, my_rows);
+  }
+}
 
 __global__ void rounds_init_kernel(LinDev P, RoundsWs W, const double *lb_io, const double *ub_io)
 {
@@ -44,9 +141,12 @@ rounds_rows_kernel(LinDev P, RoundsWs W, int first)
 {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  const SinkSplit sink{W.nlb, W.nub, P.n};
   unsigned long long my_nnz = 0, my_rows = 0;
-  process_rows<G, R>(P, W.box, W.bits, W.ctrl, sink, tid >> 5, nthreads >> 5, first != 0, my_nnz, my_rows);
+  __shared__ StreamStage s_stage[kRoundsThreads / 32];
+  StreamStage &S = s_stage[threadIdx.x >> 5];
+  if (lane == 0) { S.tcount = 0; S.pad_[0] = 0; S.pad_[1] = 0; }
+  __syncwarp();
+  rows_of_phase<G, R>(P, W, S, tid >> 5, nthreads >> 5, first != 0, my_nnz, my_rows);
   __shared__ unsigned long long s_nnz, s_rows;
   if (threadIdx.x == 0) { s_nnz = 0ull; s_rows = 0ull; }
   __syncthreads();

@@ -1,8 +1,7 @@
 // linear_row.cuh -- evaluation of ONE linear row against ONE box by a sub-warp group of G lanes
 // (Jacobi form of LinearHandler::linBndTighten_, LinearHandler.cpp:952-1045), registers and shuffles only.
-// This is the THROUGHPUT form, used by the per-round kernels of the row-partitioned multi-GPU path
-// (linear_rounds.cu), where every warp has hundreds of rows to stream through; the single-launch fixpoint
-// kernel uses the latency form in row_batch.cuh (one staged batch of rows per warp per round).
+// Used by the per-round kernels of the row-partitioned multi-GPU path (linear_rounds.cu) for the due rows of SPARSE
+// 32-row blocks and the cut-off row; dense blocks are evaluated lane = row (row_resident.cuh, streaming form).
 #pragma once
 #include "device_problem.cuh"
 
@@ -227,56 +226,6 @@ __device__ __forceinline__ void process_row(const LinDev &P, const double2 *box,
       const int j = __ldg(P.col + t);
       if (a != 0.0) emit_candidates<R>(rc, a, j, box[j], sink);
     }
-  }
-}
-
-// The rows of one phase.  A warp holds 32/G groups and takes the rows in chunks of 32/G consecutive rows:
-// group g of the warp gets row chunk*(32/G)+g.  Which rows are due is a BIT SET (one bit per row, the
-// reference's Constraint bFlag): the warp reads its chunk's bits from one word, clears them with a
-// fire-and-forget atomic, and each group whose bit is set evaluates its row.  In the first round every
-// stored row is due and the bit set is not consulted.
-template <int G, class R, class Sink>
-__device__ __forceinline__ void process_rows(const LinDev &P, const double2 *box, uint32_t *bits, int32_t *status,
-                                             const Sink &sink, int warp_global, int n_warps, bool first,
-                                             unsigned long long &my_nnz, unsigned long long &my_rows)
-{
-  constexpr int GPW = 32 / G;                    // groups (= rows) per warp step
-  const int lane = threadIdx.x & 31;
-  const int lane_g = lane % G, g = lane / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lane_g));
-  const int n_chunks = (P.m + GPW - 1) / GPW;
-  const unsigned full = (GPW == 32) ? 0xffffffffu : ((1u << GPW) - 1u);
-  // the warp's chunks are warp_global, warp_global + n_warps, ...; the due-bits of 32 of them are fetched
-  // at once (lane l looks at the l-th), so chunks with nothing due cost no dependent load
-  for (int it0 = 0; warp_global + (long long)it0 * n_warps < n_chunks; it0 += 32) {
-    const long long cl = warp_global + (long long)(it0 + lane) * n_warps;
-    unsigned due_l = 0u;
-    if (cl < n_chunks) {
-      if (first) due_l = full;
-      else {
-        const int row0 = (int)cl * GPW;
-        due_l = (__ldcg(bits + (row0 >> 5)) >> (row0 & 31)) & full;     // bits are set by L2 atomics: bypass L1
-        if (due_l) atomicAnd(bits + (row0 >> 5), ~(due_l << (row0 & 31)));   // setBFlag(false), :513
-      }
-    }
-    unsigned active = __ballot_sync(0xffffffffu, due_l != 0u);
-    while (active) {
-      const int l = __ffs(active) - 1;
-      active &= active - 1;
-      const unsigned due = __shfl_sync(0xffffffffu, due_l, l);
-      const int i = (warp_global + (it0 + l) * n_warps) * GPW + g;
-      if (!((due >> g) & 1u) || i >= P.m) continue;             // group-uniform
-      const int2 info = __ldg(P.row_info + i);
-      if (info.y < 0) continue;                                 // deleted rows are never evaluated
-      process_row<G, R>(P, box, status, sink, i, info.x, info.y, lane_g, gmask, my_nnz, my_rows);
-    }
-  }
-  // the objective cut-off row is evaluated in every round (the reference loops it to its own fixpoint in
-  // every sweep, LinearHandler.cpp:1636-1640); one group takes it
-  if (P.cut_cnt > 0 && warp_global == 0 && g == 0) {
-    LinDev C = P;
-    C.col = P.cut_col; C.val = P.cut_val; C.row_bnd = P.cut_bnd;
-    process_row<G, R>(C, box, status, sink, 0, 0, P.cut_cnt, lane_g, gmask, my_nnz, my_rows);
   }
 }
 

@@ -124,7 +124,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
   unsigned bar_target = 0;
   int tr = 0;
   MNTR_TRACE();
-  if (lane == 0) { S.tcount = 0; S.pad_[0] = 0; }
+  if (lane == 0) { S.tcount = 0; S.pad_[0] = 0; S.pad_[1] = 0; }
   if (threadIdx.x < 2) {      // round r (parity c = r & 1) merges into box[c ^ 1], marks touched[c], flags due[c ^ 1]
     const int c = threadIdx.x;
     s_fix[c] = FixRound{0u, 0u, W.box[c ^ 1], W.touched[c], W.due[c ^ 1], W.sync, P.csc_ptr, P.csc_row};
@@ -242,7 +242,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
       const SinkFix sink{&s_fix[cur], (unsigned)round, (W.trace != nullptr && blockIdx.x == 0 && threadIdx.x < 32) ? W.trace + 32 : nullptr,
                          (W.trace != nullptr && round < 16) ? W.trace + kTraceBlk + (blockIdx.x * 16 + round) * 8 : nullptr};
       if constexpr (RES) eval_due_resident<R>(P, rd, sink, S, W.due[cur], r0, r1, head, round == 1, lane, my_nnz, my_rows);
-      else eval_due_range<R>(P, rd, sink, S, W.due[cur], r0, r1, round == 1, lane, my_nnz, my_rows);
+      else eval_due_stream<R>(P, rd, sink, S, W.due[cur], r0, r1, round == 1, lane, my_nnz, my_rows);
       // the objective cut-off row is evaluated in every round (the reference loops it to its own fixpoint in
       // every sweep, LinearHandler.cpp:1636-1640); the last warp takes it
       if (P.cut_cnt > 0 && warp_g == n_warps - 1) {

@@ -31,6 +31,10 @@ constexpr int kColMask = 0x7fffffff;
 
 constexpr uint8_t kLoInf = 1, kHiInf = 2, kTiny = 4;   // per-entry bits of the singleton-infinity rule
 
+// a deferred exact candidate of the streaming form (row_resident.cuh): what its row offers, the entry
+struct __align__(16) CandItem { double slb, sub, a; int cx, sg; };
+constexpr int kQueueCap = 96;
+
 // one warp's slice of shared memory
 struct __align__(16) WarpStage {
   double plo[kCap];        // a * blo, rounded down   (after pass B: first-touch list of the Sink)
@@ -40,14 +44,21 @@ struct __align__(16) WarpStage {
   int beg[32];             // first CSR entry of the row in slot s
   int off[32];             // first staged entry of the row in slot s
   int tcount;              // length of the first-touch list
-  int pad_[3];
+  int pad_[3];             // [0] debug mark counter  [1] length of the candidate queue
   uint8_t slot[kCap];      // staged entry -> row slot (= lane of the row)
   uint8_t flag[kCap];      // kLoInf | kHiInf | kTiny
   uint8_t sing[32];        // bit 0: lb side runs in singleton-infinity mode, bit 1: ub side
   // the Sink's list of moved variables lives in plo[] once pass B has consumed the products
   static constexpr int kListCap = 2 * kCap;
   __device__ __forceinline__ int *list() { return reinterpret_cast<int *>(plo); }
+  // the lane = row form of dense 32-row blocks (row_resident.cuh) streams its rows from the CSR and only needs a
+  // work list of (row lane, entry) pairs: it lives in phi[]
+  static constexpr bool kSlab = false;
+  __device__ __forceinline__ uint16_t *work_list() { return reinterpret_cast<uint16_t *>(phi); }
+  __device__ __forceinline__ CandItem *queue() { return reinterpret_cast<CandItem *>(phi); }
 };
+static_assert(sizeof(double) * kCap >= sizeof(CandItem) * kQueueCap, "the candidate queue fits phi[]");
+static_assert(sizeof(double) * kCap >= sizeof(uint16_t) * 32 * 32, "the work list of a 32-row block fits phi[]");
 static_assert(sizeof(WarpStage) % 16 == 0, "slices are laid out back to back");
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -126,6 +137,8 @@ struct FixRound {
 };
 
 struct SinkFix {
+  static constexpr bool kFlagsRows = true;      // a moved variable's rows are flagged by the emitting warp
+  __device__ __forceinline__ uint32_t *due_next() const { return rc->due_next; }
   const FixRound *rc;          // in shared memory (one record per round parity, built once)
   unsigned round;
   unsigned long long *probe;   // debug (MNTR_GPU_TRACE): time stamps of one warp's passes, or nullptr

@@ -42,7 +42,10 @@ struct __align__(16) ResidentStage {
   static constexpr int kListCap = 256;
   int items[kListCap];
   uint16_t work[32 * kLaneMax];     // (row lane | entry << 5) of the entries whose exact candidates are due
+  static constexpr bool kSlab = true;
   __device__ __forceinline__ int *list() { return items; }
+  __device__ __forceinline__ uint16_t *work_list() { return work; }
+  __device__ __forceinline__ CandItem *queue() { return nullptr; }      // (resident rows take their candidates at once)
 };
 static_assert(sizeof(ResidentStage) % 16 == 0, "slices are laid out back to back");
 
@@ -64,18 +67,21 @@ __device__ __forceinline__ void resident_fill(const LinDev &P, ResidentStage &S,
   }
 }
 
-// entry t of the lane's row
-__device__ __forceinline__ void resident_entry(const LinDev &P, const ResidentStage &S, int lane, int beg, int t,
+// entry t of the lane's row: from the slice when the stage keeps the rows resident, else from the CSR
+template <class Stage>
+__device__ __forceinline__ void resident_entry(const LinDev &P, const Stage &S, int lane, int beg, int t,
                                                double &a, int &cx)
 {
-  if (t < kRes) { a = S.val[t][lane]; cx = S.colx[t][lane]; }
-  else { a = __ldg(P.val + beg + t); cx = __ldg(P.colx + beg + t); }
+  if constexpr (Stage::kSlab) {
+    if (t < kRes) { a = S.val[t][lane]; cx = S.colx[t][lane]; return; }
+  }
+  a = __ldg(P.val + beg + t); cx = __ldg(P.colx + beg + t);
 }
 
 // singleton-infinity sums of the lane's row [getSingLfBnds_ :1261-1319]: finite sum + infinity count per side.  Rare
 // (only rows with an infinite activity), serial, out of line.
-template <class R>
-__device__ __noinline__ void singleton_sums(const LinDev &P, const ReadPending &rd, const ResidentStage &S, int lane,
+template <class R, class Stage>
+__device__ __noinline__ void singleton_sums(const LinDev &P, const ReadPending &rd, const Stage &S, int lane,
                                             const RowHead h, double &sing_ll, double &sing_uu)
 {
   double fs_lo = 0.0, fs_hi = 0.0;
@@ -93,11 +99,58 @@ __device__ __noinline__ void singleton_sums(const LinDev &P, const ReadPending &
   sing_uu = (ninf_hi >= 2) ? INFINITY : fs_hi;
 }
 
+// One trip of the exact path, lane = entry: bounds of the entry's variable and (speculatively, riding along with the
+// gather) the position of its CSC list; exact candidates; a moved variable is marked and its rows are flagged for the
+// next round [changeBFlag_ :1229-1234].  Convergent.
+template <class R, class Sink, class Stage>
+__device__ __forceinline__ void exact_and_flag(const LinDev &P, const ReadPending &rd, const Sink &sink, Stage &S, int lane,
+                                               bool on, double slb, double sub, int sg, double a, int cx)
+{
+  int qb = 0, len = 0;
+  if (on) {
+    int j; bool isint;
+    const double2 bt = rd.fetch(cx, j, isint);
+    int qe = 0;
+    if constexpr (Sink::kFlagsRows) { qb = __ldg(P.csc_ptr + j); qe = __ldg(P.csc_ptr + j + 1); }
+    const double2 c = exact_candidates<R>(slb, sub, sg, a, bt.x, bt.y);
+    const bool up = c.x > bt.x, down = c.y < bt.y;
+    if (up) sink.raise_lb(S, j, isint, c.x);
+    if (down) sink.lower_ub(S, j, isint, c.y);
+    if (up || down) { sink.touch(j, isint); len = qe - qb; }
+  }
+  if constexpr (Sink::kFlagsRows) {
+    if (__any_sync(kFullMask, len != 0)) {
+      if (lane == 0) sink.changed();
+      flag_lists(qb, len, lane, P.csc_row, sink.due_next());
+    }
+  }
+}
+
+// queue of deferred exact candidates (streaming form)
+template <class R, class Sink, class Stage>
+__device__ __noinline__ void drain_queue(const LinDev &P, const ReadPending &rd, const Sink &sink, Stage &S, int lane)
+{
+  __syncwarp();
+  const int n = S.pad_[1];
+  for (int base = 0; base < n; base += 32) {
+    const bool on = base + lane < n;
+    CandItem it{0.0, 0.0, 0.0, 0, 0};
+    if (on) it = S.queue()[base + lane];
+    exact_and_flag<R>(P, rd, sink, S, lane, on, it.slb, it.sub, it.sg, it.a, it.cx);
+  }
+  __syncwarp();
+  if (lane == 0) S.pad_[1] = 0;
+  __syncwarp();
+}
+
 // One round of the rows of this warp: lane = row.  `due`: the lane's row is evaluated in this round (h.cnt >= 0).
 // Both passes issue ALL the gathers of the resident entries before the first one is consumed: a round costs a row one
 // trip to L2 for its activities and, if any of its entries can move a bound, one more for the exact candidates.
-template <class R, class Sink>
-__device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending &rd, const Sink &sink, ResidentStage &S,
+// With a stage that does not keep rows resident (Stage::kSlab false: the streaming form of large instances) the lane
+// reads its row's entries from the CSR, four at a time with 128-bit loads (rows start at and are padded to a multiple
+// of four entries); the lines are shared by neighbouring lanes and consecutive groups through L1.
+template <class R, class Sink, class Stage>
+__device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending &rd, const Sink &sink, Stage &S,
                                               int lane, bool due, const RowHead h, bool first)
 {
   if (first && due && h.rl > h.ru + kETol) sink.row_bounds_cross();     // checkBounds_, rows part (:328-359)
@@ -122,19 +175,40 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
         continue;
       }
       double2 b[kPassGroup];
+      double av[kPassGroup];
+      int cv[kPassGroup];
+      if constexpr (Stage::kSlab) {
+#pragma unroll
+        for (int u = 0; u < kPassGroup; ++u) {
+          const int t = g * kPassGroup + u;
+          av[u] = 0.0; cv[u] = 0;
+          if (t < cnt) { av[u] = S.val[t][lane]; cv[u] = S.colx[t][lane]; }
+        }
+      } else {
+        static_assert(kPassGroup == 4, "one 128-bit column load and two 128-bit value loads per group");
+        int4 c = make_int4(0, 0, 0, 0);
+        double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+        if (g * kPassGroup < cnt) {
+          c = __ldg(reinterpret_cast<const int4 *>(P.colx + h.beg + g * kPassGroup));
+          v0 = __ldg(reinterpret_cast<const double2 *>(P.val + h.beg + g * kPassGroup));
+          v1 = __ldg(reinterpret_cast<const double2 *>(P.val + h.beg + g * kPassGroup + 2));
+        }
+        cv[0] = c.x; cv[1] = c.y; cv[2] = c.z; cv[3] = c.w;
+        av[0] = v0.x; av[1] = v0.y; av[2] = v1.x; av[3] = v1.y;
+      }
 #pragma unroll
       for (int u = 0; u < kPassGroup; ++u) {
         const int t = g * kPassGroup + u;
         b[u] = make_double2(0.0, 0.0);
-        if (t < cnt) b[u] = __ldcg(rd.box + (S.colx[t][lane] & kColMask));
+        if (t < cnt) b[u] = __ldcg(rd.box + (cv[u] & kColMask));
       }
 #pragma unroll
       for (int u = 0; u < kPassGroup; ++u) {
         const int t = g * kPassGroup + u;
         reach[t] = 0.f;
         if (t < cnt) {
-          const double a = S.val[t][lane];
-          if (rd.round_ints && S.colx[t][lane] < 0) tighten_int_bounds(b[u].x, b[u].y);
+          const double a = av[u];
+          if (rd.round_ints && cv[u] < 0) tighten_int_bounds(b[u].x, b[u].y);
           const bool pos = a > 0.0;
           ll = R::add_lo(ll, R::mul_lo(a, pos ? b[u].x : b[u].y));
           uu = R::add_hi(uu, R::mul_hi(a, pos ? b[u].y : b[u].x));
@@ -158,7 +232,7 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
     // ---- what the row offers its terms ----
     if (mine) {
       double sing_ll = -INFINITY, sing_uu = INFINITY;
-      if (ll < -kInf20 || uu > kInf20) singleton_sums<R>(P, rd, S, lane, h, sing_ll, sing_uu);     // rare
+      if (ll < -kInf20 || uu > kInf20) singleton_sums<R, Stage>(P, rd, S, lane, h, sing_ll, sing_uu);     // rare
       if (ll > h.ru + kETol || uu < h.rl - kETol) sink.row_infeasible();     // :994-1015
       else row_offers<R>(h.rl, h.ru, ll, uu, sing_ll, sing_uu, slb, sub, sg);
     }
@@ -184,9 +258,11 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
   sink.mark(S, lane); sink.phase(lane, 2);
 
   // ---- exact candidates [updateLfBoundsFromLb_/Ub_] of the entries that passed the test.  They are few and spread
-  //      unevenly over the rows, and the exact path is long (two directed fp64 divisions): the (row lane, entry)
-  //      pairs of the whole warp are compacted into a work list and taken ENTRY-PARALLEL, 32 per trip, so the exact
-  //      path runs with full lanes once or twice per warp instead of once per row and entry ----
+  //      unevenly over the rows, and the exact path is long (two directed fp64 divisions): the entries of the whole
+  //      warp are compacted and taken ENTRY-PARALLEL, 32 per trip, so the exact path runs with full lanes.
+  //      Resident rows: a work list of (row lane, entry) pairs, taken at once.  Streamed rows: the items go on a
+  //      queue that is drained when it is full or the range is done, so the chain of dependent trips (bounds and
+  //      CSC pointers, division, CSC rows) is paid once per ~96 candidates instead of once per 32-row block ----
   {
     const int mine_n = __popc(need);
     int incl = mine_n;
@@ -196,35 +272,40 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
       if (lane >= d) incl += v;
     }
     const int total = __shfl_sync(kFullMask, incl, 31);
-    if (total > 0) {
+    bool queued = false;
+    if constexpr (!Stage::kSlab) {
+      if (total > 0 && total <= kQueueCap) {
+        __syncwarp();
+        if (S.pad_[1] + total > kQueueCap) drain_queue<R>(P, rd, sink, S, lane);
+        int pos = S.pad_[1] + incl - mine_n;
+        for (unsigned nd = need; nd; nd &= nd - 1) {
+          double a; int cx;
+          resident_entry(P, S, lane, h.beg, __ffs(nd) - 1, a, cx);
+          S.queue()[pos++] = CandItem{slb, sub, a, cx, (int)sg};
+        }
+        __syncwarp();
+        if (lane == 0) S.pad_[1] += total;
+        __syncwarp();
+        queued = true;
+      } else if (total > 0) {
+        drain_queue<R>(P, rd, sink, S, lane);      // the work list below shares the queue's storage
+      }
+    }
+    if (total > 0 && !queued) {
       int pos = incl - mine_n;
-      for (unsigned nd = need; nd; nd &= nd - 1) S.work[pos++] = (uint16_t)(lane | ((__ffs(nd) - 1) << 5));
+      for (unsigned nd = need; nd; nd &= nd - 1) S.work_list()[pos++] = (uint16_t)(lane | ((__ffs(nd) - 1) << 5));
       __syncwarp();
       for (int base = 0; base < total; base += 32) {
         const bool on = base + lane < total;
-        const int item = on ? S.work[base + lane] : 0;
+        const int item = on ? S.work_list()[base + lane] : 0;
         const int rl = item & 31, t = item >> 5;
         const double o_slb = __shfl_sync(kFullMask, slb, rl), o_sub = __shfl_sync(kFullMask, sub, rl);
         const int o_sg = __shfl_sync(kFullMask, (int)sg, rl), o_beg = __shfl_sync(kFullMask, h.beg, rl);
-        int qb = 0, len = 0;
-        if (on) {
-          double a; int cx, j; bool isint;
-          resident_entry(P, S, rl, o_beg, t, a, cx);
-          const double2 bt = rd.fetch(cx, j, isint);
-          // speculative: where the variable's row list is, should it move (rides along with the gather)
-          qb = __ldg(P.csc_ptr + j);
-          const int qe = __ldg(P.csc_ptr + j + 1);
-          const double2 c = exact_candidates<R>(o_slb, o_sub, o_sg, a, bt.x, bt.y);
-          const bool up = c.x > bt.x, down = c.y < bt.y;
-          if (up) sink.raise_lb(S, j, isint, c.x);
-          if (down) sink.lower_ub(S, j, isint, c.y);
-          if (up || down) { sink.touch(j, isint); len = qe - qb; }
-        }
-        if (__any_sync(kFullMask, len != 0)) {
-          if (lane == 0) sink.changed();
-          flag_lists(qb, len, lane, P.csc_row, sink.rc->due_next);
-        }
+        double a = 0.0; int cx = 0;
+        if (on) resident_entry(P, S, rl, o_beg, t, a, cx);
+        exact_and_flag<R>(P, rd, sink, S, lane, on, o_slb, o_sub, o_sg, a, cx);
       }
+      __syncwarp();
     }
   }
   sink.mark(S, lane); sink.phase(lane, 3);
@@ -247,7 +328,7 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
 // that can move a bound derives its exact candidate from the bounds it already holds: one trip to L2 for the whole
 // evaluation, one more for the rows to flag.  A sparse round is bound by the instructions on this path, not by
 // bandwidth -- it is a third of the lane = row form's.
-template <class R, class Sink>
+template <class R, class Sink, class Stage = ResidentStage>
 __device__ __forceinline__ void eval_packed(const LinDev &P, const ReadPending &rd, const Sink &sink, ResidentStage &S,
                                             int lane, bool due, const RowHead h, bool first, int incl, int total)
 {
@@ -291,7 +372,7 @@ __device__ __forceinline__ void eval_packed(const LinDev &P, const ReadPending &
   int sg = 0;
   if (due) {
     double sing_ll = -INFINITY, sing_uu = INFINITY;
-    if (ll < -kInf20 || uu > kInf20) singleton_sums<R>(P, rd, S, lane, h, sing_ll, sing_uu);     // rare
+    if (ll < -kInf20 || uu > kInf20) singleton_sums<R, Stage>(P, rd, S, lane, h, sing_ll, sing_uu);     // rare
     uint8_t sg8 = 0;
     if (ll > h.ru + kETol || uu < h.rl - kETol) sink.row_infeasible();     // :994-1015
     else row_offers<R>(h.rl, h.ru, ll, uu, sing_ll, sing_uu, slb, sub, sg8);
@@ -314,12 +395,56 @@ __device__ __forceinline__ void eval_packed(const LinDev &P, const ReadPending &
     sink.mark(S, lane); sink.phase(lane, 3);
     if (__any_sync(kFullMask, len != 0)) {
       if (lane == 0) sink.changed();
-      flag_lists(qb, len, lane, P.csc_row, sink.rc->due_next);
+      flag_lists(qb, len, lane, P.csc_row, sink.due_next());
     }
   } else {
     sink.mark(S, lane); sink.phase(lane, 3);
   }
   sink.mark(S, lane); sink.phase(lane, 4);
+}
+
+// STREAMING form (rows not resident: large instances).  The due rows of [r0, r1): 32-row blocks (one word of the bit
+// set) in which at least kDenseRows rows are due are evaluated lane = row straight from the CSR (eval_resident with a
+// non-resident stage): in the dense rounds, which carry almost all the work of a large instance, that costs about two
+// warp instructions per nonzero where the staged, entry-parallel batches of row_batch.cuh cost about twelve.  The
+// bits taken are cleared; what remains (sparse blocks) goes to the packing path of eval_due_range.
+constexpr int kDenseRows = 6;
+template <class R, class Sink>
+__device__ __forceinline__ void eval_due_stream(const LinDev &P, const ReadPending &rd, const Sink &sink, WarpStage &S,
+                                                uint32_t *due, int r0, int r1, bool first, int lane,
+                                                unsigned long long &my_nnz, unsigned long long &my_rows)
+{
+  if (r0 >= r1) return;
+  if (r1 - r0 > 32) {
+    bool rest = false;
+    for (int wb = r0 >> 5; wb * 32 < r1; wb += 32) {
+      const int w = wb + lane;
+      unsigned word = 0u;
+      if (w * 32 < r1) {
+        word = first ? kFullMask : __ldcg(due + w);
+        if (w * 32 < r0) word &= ~0u << (r0 - w * 32);
+        if (r1 - w * 32 < 32) word &= (1u << (r1 - w * 32)) - 1u;
+      }
+      const bool dense = first ? word != 0u : __popc(word) >= kDenseRows;
+      if (dense && !first) atomicAnd(due + w, ~word);            // setBFlag(false), :513
+      if (word != 0u && !dense) rest = true;
+      unsigned dm = __ballot_sync(kFullMask, dense);
+      while (dm) {
+        const int k = __ffs(dm) - 1;
+        dm &= dm - 1;
+        const unsigned wk = __shfl_sync(kFullMask, word, k);
+        const int row = (wb + k) * 32 + lane;
+        const bool bit = (wk >> lane) & 1u;
+        const RowHead h = load_head(P, bit ? row : -1);
+        const bool is_due = bit && h.cnt >= 0;                     // deleted rows (term count < 0) are never evaluated
+        if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
+        eval_resident<R>(P, rd, sink, S, lane, is_due, h, first);
+      }
+    }
+    drain_queue<R>(P, rd, sink, S, lane);
+    if (first || !__any_sync(kFullMask, rest)) return;
+  }
+  eval_due_range<R>(P, rd, sink, S, due, r0, r1, first, lane, my_nnz, my_rows);
 }
 
 // The due rows of this warp's range [r0, r0 + 32): lane l owns row r0 + l.  Which rows are due is a BIT SET (the

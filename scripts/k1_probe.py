@@ -7,6 +7,7 @@ if os.environ.get("MNTR_GPU_LIB"):          # dev: a variant build (scripts/buil
     E.LIB_PATH = os.path.abspath(os.environ["MNTR_GPU_LIB"])
 from minotaur_b200.instances import make_sparse_milp
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0     # 1: per-round kernels (K5), 2: staged rows
 inst = make_sparse_milp(m, m, 10, seed=12345)
 eng = E.GpuBoundEngine(0); eng.load_linear(inst)
 dev = torch.device('cuda', 0)
@@ -20,8 +21,8 @@ for do_flush in (True, False):
         with torch.cuda.stream(stream):
             w_lb.copy_(root_lb); w_ub.copy_(root_ub)
             if do_flush: flush.zero_()
-        v, r, z = eng.tighten_single_dev(w_lb.data_ptr(), w_ub.data_ptr())
-        us.append(eng.stats().kernel_ms * 1e3)
+        v, r, z = eng.tighten_single_dev(w_lb.data_ptr(), w_ub.data_ptr(), flags=flags)
+        st = eng.stats(); us.append(st.kernel_ms * 1e3)
     us = np.array(us[4:])
-    print(f"K1 {os.path.basename(E.LIB_PATH)} m={m} flush={do_flush}: {us.mean():.1f} us (min {us.min():.1f})  rounds={r} nnz={z} verdict={v} "
-          f"checksum={float(w_lb.sum() + w_ub.sum()):.6f}", flush=True)
+    print(f"K1 {os.path.basename(E.LIB_PATH)} flags={flags} m={m} flush={do_flush}: {us.mean():.1f} us (min {us.min():.1f})  rounds={r} nnz={z} verdict={v} "
+          f"checksum={float(w_lb.sum() + w_ub.sum()):.6f} rows_ms={st.rows_ms:.3f} vars_ms={st.vars_ms:.3f}", flush=True)
