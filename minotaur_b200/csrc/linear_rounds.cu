@@ -24,14 +24,19 @@ constexpr int kRoundsThreads = 256;
 // one warp's slice of shared memory: the queue of deferred exact candidates and, for a block with more candidates
 // than the queue holds, the work list
 struct __align__(16) StreamStage {
+  double sval[kStageEntries];      // the block's entries, staged by cp.async
+  int32_t scol[kStageEntries];
+  static constexpr int kQueueCap = 96;
+  CandItem q[kQueueCap];           // (the work list is only used with an empty queue and shares its storage)
   int tcount;
-  int pad_[3];             // [1] length of the candidate queue
-  CandItem q[kQueueCap];
-  uint16_t work[32 * kLaneMax];
+  int pad_[3];                     // [1] length of the candidate queue
   static constexpr bool kSlab = false;
-  __device__ __forceinline__ uint16_t *work_list() { return work; }
+  __device__ __forceinline__ double *stage_val() { return sval; }
+  __device__ __forceinline__ int32_t *stage_col() { return scol; }
+  __device__ __forceinline__ uint16_t *work_list() { return reinterpret_cast<uint16_t *>(q); }
   __device__ __forceinline__ CandItem *queue() { return q; }
 };
+static_assert(sizeof(CandItem) * StreamStage::kQueueCap >= sizeof(uint16_t) * 32 * kLaneMax, "work list fits the queue's storage");
 
 // candidates go into the split arrays nlb / nub; moved variables are found, rounded and their rows flagged by the vars
 // kernel after the cross-GPU merge, so nothing is marked here
@@ -88,7 +93,9 @@ __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W
       const RowHead h = load_head(P, bit ? row : -1);
       const bool is_due = bit && h.cnt >= 0;                          // deleted rows are never evaluated
       if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
-      eval_resident<R>(P, rd, sink, S, lane, is_due, h, false);
+      const int32_t *gcol; const double *gval;
+      stage_block(P, S, lane, is_due, h, gcol, gval);
+      eval_resident<R>(P, rd, sink, S, lane, is_due, h, false, gcol, gval);
     }
     while (sm) {
       const int k = __ffs(sm) - 1;
@@ -142,8 +149,8 @@ rounds_rows_kernel(LinDev P, RoundsWs W, int first)
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   unsigned long long my_nnz = 0, my_rows = 0;
-  __shared__ StreamStage s_stage[kRoundsThreads / 32];
-  StreamStage &S = s_stage[threadIdx.x >> 5];
+  extern __shared__ __align__(16) unsigned char smem_raw[];       // one StreamStage per warp
+  StreamStage &S = reinterpret_cast<StreamStage *>(smem_raw)[threadIdx.x >> 5];
   if (lane == 0) { S.tcount = 0; S.pad_[0] = 0; S.pad_[1] = 0; }
   __syncwarp();
   rows_of_phase<G, R>(P, W, S, tid >> 5, nthreads >> 5, first != 0, my_nnz, my_rows);
@@ -236,14 +243,20 @@ cudaError_t rows_r(int G, const LinDev &P, const RoundsWs &W, int first, int sm_
 {
   if (P.m <= 0) return cudaSuccess;
   const int blocks = grid_for((long long)P.m * G, sm_count);
+  const size_t smem = sizeof(StreamStage) * (kRoundsThreads / 32);
+  auto launch = [&](auto kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<blocks, kRoundsThreads, smem, s>>>(P, W, first);
+    return cudaGetLastError();
+  };
   switch (G) {
-  case 2:  rounds_rows_kernel<2, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
-  case 4:  rounds_rows_kernel<4, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
-  case 8:  rounds_rows_kernel<8, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
-  case 16: rounds_rows_kernel<16, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
-  default: rounds_rows_kernel<32, R><<<blocks, kRoundsThreads, 0, s>>>(P, W, first); break;
+  case 2:  return launch(rounds_rows_kernel<2, R>);
+  case 4:  return launch(rounds_rows_kernel<4, R>);
+  case 8:  return launch(rounds_rows_kernel<8, R>);
+  case 16: return launch(rounds_rows_kernel<16, R>);
+  default: return launch(rounds_rows_kernel<32, R>);
   }
-  return cudaGetLastError();
 }
 
 }  // namespace

@@ -33,7 +33,7 @@ constexpr uint8_t kLoInf = 1, kHiInf = 2, kTiny = 4;   // per-entry bits of the 
 
 // a deferred exact candidate of the streaming form (row_resident.cuh): what its row offers, the entry
 struct __align__(16) CandItem { double slb, sub, a; int cx, sg; };
-constexpr int kQueueCap = 96;
+constexpr int kStageEntries = 384;      // entries of a 32-row block staged in shared memory (streaming form)
 
 // one warp's slice of shared memory
 struct __align__(16) WarpStage {
@@ -51,15 +51,20 @@ struct __align__(16) WarpStage {
   // the Sink's list of moved variables lives in plo[] once pass B has consumed the products
   static constexpr int kListCap = 2 * kCap;
   __device__ __forceinline__ int *list() { return reinterpret_cast<int *>(plo); }
-  // the lane = row form of dense 32-row blocks (row_resident.cuh) streams its rows from the CSR and only needs a
-  // work list of (row lane, entry) pairs: it lives in phi[]
+  // The lane = row form of dense 32-row blocks (row_resident.cuh, streaming form) reuses the slice: the block's
+  // entries staged by cp.async (values in plo[], columns in the first half of phi[]), the queue of deferred exact
+  // candidates in the second half of phi[]; the work list of a block with more candidates than the queue holds
+  // overwrites the staged values (they have been consumed by then).
   static constexpr bool kSlab = false;
-  __device__ __forceinline__ uint16_t *work_list() { return reinterpret_cast<uint16_t *>(phi); }
-  __device__ __forceinline__ CandItem *queue() { return reinterpret_cast<CandItem *>(phi); }
+  static constexpr int kQueueCap = 48;
+  __device__ __forceinline__ double *stage_val() { return plo; }
+  __device__ __forceinline__ int32_t *stage_col() { return reinterpret_cast<int32_t *>(phi); }
+  __device__ __forceinline__ CandItem *queue() { return reinterpret_cast<CandItem *>(phi + kCap / 2); }
+  __device__ __forceinline__ uint16_t *work_list() { return reinterpret_cast<uint16_t *>(plo); }
 };
-static_assert(sizeof(double) * kCap >= sizeof(CandItem) * kQueueCap, "the candidate queue fits phi[]");
-static_assert(sizeof(double) * kCap >= sizeof(uint16_t) * 32 * 32, "the work list of a 32-row block fits phi[]");
-static_assert(sizeof(WarpStage) % 16 == 0, "slices are laid out back to back");
+static_assert(kCap >= kStageEntries && sizeof(double) * (kCap / 2) >= sizeof(int32_t) * kStageEntries, "staged block fits");
+static_assert(sizeof(double) * (kCap / 2) >= sizeof(CandItem) * WarpStage::kQueueCap, "the candidate queue fits phi[]");
+static_assert(sizeof(double) * kCap >= sizeof(uint16_t) * 32 * 32, "the work list of a 32-row block fits plo[]");
 
 // ---------------------------------------------------------------------------------------------------------------
 // Readers: how an entry's column and the bounds of its variable are fetched.  Boxes are read with ld.global.cg

@@ -45,7 +45,8 @@ struct __align__(16) ResidentStage {
   static constexpr bool kSlab = true;
   __device__ __forceinline__ int *list() { return items; }
   __device__ __forceinline__ uint16_t *work_list() { return work; }
-  __device__ __forceinline__ CandItem *queue() { return nullptr; }      // (resident rows take their candidates at once)
+  static constexpr int kQueueCap = 0;                                   // (resident rows take their candidates at once)
+  __device__ __forceinline__ CandItem *queue() { return nullptr; }
 };
 static_assert(sizeof(ResidentStage) % 16 == 0, "slices are laid out back to back");
 
@@ -151,8 +152,10 @@ __device__ __noinline__ void drain_queue(const LinDev &P, const ReadPending &rd,
 // of four entries); the lines are shared by neighbouring lanes and consecutive groups through L1.
 template <class R, class Sink, class Stage>
 __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending &rd, const Sink &sink, Stage &S,
-                                              int lane, bool due, const RowHead h, bool first)
+                                              int lane, bool due, const RowHead h, bool first,
+                                              const int32_t *gcol = nullptr, const double *gval = nullptr)
 {
+  // gcol / gval (streaming form): where the lane's row starts -- in the CSR, or in the block staged in shared memory
   if (first && due && h.rl > h.ru + kETol) sink.row_bounds_cross();     // checkBounds_, rows part (:328-359)
   const bool mine = due && h.cnt <= kLaneMax;
   unsigned longm = __ballot_sync(kFullMask, due && h.cnt > kLaneMax);
@@ -189,9 +192,9 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
         int4 c = make_int4(0, 0, 0, 0);
         double2 v0 = make_double2(0.0, 0.0), v1 = v0;
         if (g * kPassGroup < cnt) {
-          c = __ldg(reinterpret_cast<const int4 *>(P.colx + h.beg + g * kPassGroup));
-          v0 = __ldg(reinterpret_cast<const double2 *>(P.val + h.beg + g * kPassGroup));
-          v1 = __ldg(reinterpret_cast<const double2 *>(P.val + h.beg + g * kPassGroup + 2));
+          c = *reinterpret_cast<const int4 *>(gcol + g * kPassGroup);
+          v0 = *reinterpret_cast<const double2 *>(gval + g * kPassGroup);
+          v1 = *reinterpret_cast<const double2 *>(gval + g * kPassGroup + 2);
         }
         cv[0] = c.x; cv[1] = c.y; cv[2] = c.z; cv[3] = c.w;
         av[0] = v0.x; av[1] = v0.y; av[2] = v1.x; av[3] = v1.y;
@@ -274,9 +277,9 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
     const int total = __shfl_sync(kFullMask, incl, 31);
     bool queued = false;
     if constexpr (!Stage::kSlab) {
-      if (total > 0 && total <= kQueueCap) {
+      if (total > 0 && total <= Stage::kQueueCap) {
         __syncwarp();
-        if (S.pad_[1] + total > kQueueCap) drain_queue<R>(P, rd, sink, S, lane);
+        if (S.pad_[1] + total > Stage::kQueueCap) drain_queue<R>(P, rd, sink, S, lane);
         int pos = S.pad_[1] + incl - mine_n;
         for (unsigned nd = need; nd; nd &= nd - 1) {
           double a; int cx;
@@ -403,6 +406,36 @@ __device__ __forceinline__ void eval_packed(const LinDev &P, const ReadPending &
   sink.mark(S, lane); sink.phase(lane, 4);
 }
 
+// Streaming form: the rows of a 32-row block lie back to back in the CSR.  When most of them are due and the block is
+// not too long, its entries are copied to shared memory in ONE coalesced, asynchronous burst (cp.async, 16 bytes per
+// lane and instruction, no registers held), so pass 1 starts from shared memory with one trip to DRAM behind it instead
+// of one per group of four entries.  Returns where the lane's row starts (staged or in the CSR).
+// (Measured and dropped: pulling the NEXT block's entries into L2 with prefetch.global.L2, and holding the next
+// block's row heads in registers -- both made the 2.5M-row fixpoint slower, 631 -> 720 us.)
+template <class Stage>
+__device__ __forceinline__ void stage_block(const LinDev &P, Stage &S, int lane, bool is_due, const RowHead h,
+                                            const int32_t *&gcol, const double *&gval)
+{
+  gcol = P.colx + h.beg; gval = P.val + h.beg;
+  const int e1 = __reduce_max_sync(kFullMask, is_due ? row_end(make_int2(h.beg, h.cnt)) : 0);
+  const int e0 = __reduce_min_sync(kFullMask, is_due ? h.beg : 0x7fffffff);
+  const int extent = e1 - e0;
+  if (extent <= 0 || extent > kStageEntries || __popc(__ballot_sync(kFullMask, is_due)) < 16) return;
+  int32_t *sc = S.stage_col();
+  double *sv = S.stage_val();
+  __syncwarp();
+  for (int o = lane * 4; o < extent; o += 128) {
+    const unsigned dc = (unsigned)__cvta_generic_to_shared(sc + o), dv = (unsigned)__cvta_generic_to_shared(sv + o);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dc), "l"(P.colx + e0 + o) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dv), "l"(P.val + e0 + o) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dv + 16), "l"(P.val + e0 + o + 2) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  gcol = sc + (h.beg - e0); gval = sv + (h.beg - e0);
+}
+
 // STREAMING form (rows not resident: large instances).  The due rows of [r0, r1): 32-row blocks (one word of the bit
 // set) in which at least kDenseRows rows are due are evaluated lane = row straight from the CSR (eval_resident with a
 // non-resident stage): in the dense rounds, which carry almost all the work of a large instance, that costs about two
@@ -438,7 +471,9 @@ __device__ __forceinline__ void eval_due_stream(const LinDev &P, const ReadPendi
         const RowHead h = load_head(P, bit ? row : -1);
         const bool is_due = bit && h.cnt >= 0;                     // deleted rows (term count < 0) are never evaluated
         if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
-        eval_resident<R>(P, rd, sink, S, lane, is_due, h, first);
+        const int32_t *gcol; const double *gval;
+        stage_block(P, S, lane, is_due, h, gcol, gval);
+        eval_resident<R>(P, rd, sink, S, lane, is_due, h, first, gcol, gval);
       }
     }
     drain_queue<R>(P, rd, sink, S, lane);
