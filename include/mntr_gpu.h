@@ -115,7 +115,8 @@ typedef struct {
   int64_t n_infeasible;  /* boxes with verdict != MNTR_FEASIBLE */
   int64_t n_changes;     /* (variable, round) pairs whose bounds moved (single-box path) */
   int32_t max_rounds;    /* largest number of rounds any box took */
-  int32_t reserved;
+  int32_t sparse_rounds; /* row-partitioned mode: rounds whose bounds were merged by the sparse exchange (changed
+                            candidates all-gathered) instead of the dense MAX/MIN all-reduce */
   double  kernel_ms;     /* device time of the tighten kernels (CUDA events) */
   double  h2d_ms, d2h_ms;
   double  comm_ms;       /* device time of the per-round NCCL bound all-reduces (row-partitioned mode) */

@@ -79,6 +79,10 @@ constexpr unsigned kCtlVarCross = 2u;    // a moved variable's bounds cross
 constexpr unsigned kCtlRowCross = 4u;    // a row's bounds cross
 constexpr unsigned kCtlInCross = 8u;     // the incoming bounds cross
 
+// one changed candidate of the sparse exchange; the header of a rank's message reuses the layout:
+// j = number of changed candidates (may exceed the capacity: overflow), lb = the rank's row-infeasible flag
+struct __align__(8) BoundMsg { double lb, ub; long long j; };
+
 // workspace of the per-round kernels (row-partitioned multi-GPU mode)
 struct RoundsWs {
   double2 *box;    // [n] {lb, ub} of the round start (replicated on every rank)
@@ -86,7 +90,14 @@ struct RoundsWs {
   double *nub;     // [n]   upper-bound candidates (all-reduced with MIN)
   uint32_t *bits;  // [(m+31)/32] this rank's due rows   (Constraint bFlag)
   int32_t *ctrl;   // [8] [0] changed [1] int moved [2] next list length [3] verdict [4] changed pairs
+                   //     [5] sparse exchange overflowed: the vars kernel did nothing, redo the merge densely
   unsigned long long *counters;  // [2] nnz_updates, rows evaluated (this rank)
+  // sparse bound exchange (row-partitioned mode, rounds with few moved bounds): this rank's changed candidates
+  // {count, row-infeasible flag | entries {lb, ub, j}} are all-gathered instead of all-reducing 16 bytes per variable
+  BoundMsg *xsend; // [1 + xcap]  header + entries of this rank
+  BoundMsg *xrecv; // [n_ranks][1 + xcap]
+  int32_t xcap;    // entries a rank can send (0: no sparse exchange)
+  int32_t n_ranks;
 };
 
 }  // namespace mntr

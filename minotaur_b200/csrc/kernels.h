@@ -20,6 +20,10 @@ cudaError_t launch_rounds_init(const LinDev &P, const RoundsWs &W, const double 
 cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per_row, bool directed,
                                int first, int sm_count, cudaStream_t stream);
 cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream);
+// sparse bound exchange: compact this rank's changed candidates into W.xsend; after the all-gather into W.xrecv,
+// merge the other ranks' candidates (or raise ctrl[5] if any rank's message overflowed)
+cudaError_t launch_rounds_compact(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream);
+cudaError_t launch_rounds_apply(const LinDev &P, const RoundsWs &W, int rank, int sm_count, cudaStream_t stream);
 cudaError_t launch_rounds_finish(const LinDev &P, const RoundsWs &W, double *lb_dev, double *ub_dev, int sm_count,
                                  cudaStream_t stream);
 

@@ -167,10 +167,64 @@ rounds_rows_kernel(LinDev P, RoundsWs W, int first)
   if (threadIdx.x == 0 && s_rows) { atomicAdd(&W.counters[0], s_nnz); atomicAdd(&W.counters[1], s_rows); }
 }
 
-// ctrl: [0] changed  [1] int moved  [3] verdict  [4] changed (var,round) pairs
+// ---- sparse bound exchange: rounds in which few bounds move need not all-reduce 16 bytes per variable ----
+// this rank's changed candidates (nlb / nub differ from the replicated box) -> W.xsend; entry 0 is the header
+__global__ void __launch_bounds__(kRoundsThreads)
+rounds_compact_kernel(LinDev P, RoundsWs W)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  unsigned long long *count = reinterpret_cast<unsigned long long *>(&W.xsend[0].j);     // zeroed by the host
+  if (tid == 0) W.xsend[0].lb = W.nlb[P.n];                                              // row-infeasible flag
+  for (int j0 = (tid >> 5) * 32; j0 < P.n; j0 += (nthreads >> 5) * 32) {
+    const int j = j0 + lane;
+    bool ch = false;
+    double l = 0.0, u = 0.0;
+    if (j < P.n) {
+      const double2 o = W.box[j];
+      l = W.nlb[j]; u = W.nub[j];
+      ch = l != o.x || u != o.y;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ch);
+    if (m == 0u) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));                // one atomic per warp
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ch) {
+      const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+      if (at < (unsigned long long)W.xcap) W.xsend[1 + at] = BoundMsg{l, u, (long long)j};
+    }
+  }
+}
+
+// merge the other ranks' candidates into nlb / nub (exact max / min: the result does not depend on the order);
+// any message longer than the capacity: raise ctrl[5] and leave nlb / nub alone (the host redoes the merge densely)
+__global__ void __launch_bounds__(kRoundsThreads)
+rounds_apply_kernel(LinDev P, RoundsWs W, int rank)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const size_t stride = (size_t)W.xcap + 1;
+  bool overflow = false;
+  for (int r = 0; r < W.n_ranks; ++r) overflow |= W.xrecv[r * stride].j > (long long)W.xcap;
+  if (overflow) { if (tid == 0) W.ctrl[5] = 1; return; }
+  for (int r = 0; r < W.n_ranks; ++r) {
+    if (r == rank) continue;
+    const BoundMsg *msg = W.xrecv + r * stride;
+    const long long cnt = msg[0].j;
+    if (tid == 0 && msg[0].lb > 0.0) W.nlb[P.n] = msg[0].lb;
+    for (long long k = tid; k < cnt; k += nthreads) {
+      const BoundMsg e = msg[1 + k];
+      atomic_max_f64(&W.nlb[e.j], e.lb);
+      atomic_min_f64(&W.nub[e.j], e.ub);
+    }
+  }
+}
+
+// ctrl: [0] changed  [1] int moved  [3] verdict  [4] changed (var,round) pairs  [5] sparse exchange overflowed
 __global__ void __launch_bounds__(kRoundsThreads)
 rounds_vars_kernel(LinDev P, RoundsWs W)
 {
+  if (W.ctrl[5] != 0) return;        // the sparse exchange overflowed: the host redoes the merge, then calls again
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int warp_g = tid >> 5, n_warps = nthreads >> 5;
@@ -278,6 +332,18 @@ cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per
 cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream)
 {
   rounds_vars_kernel<<<grid_for(P.n, sm_count), kRoundsThreads, 0, stream>>>(P, W);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rounds_compact(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream)
+{
+  rounds_compact_kernel<<<grid_for(P.n, sm_count), kRoundsThreads, 0, stream>>>(P, W);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rounds_apply(const LinDev &P, const RoundsWs &W, int rank, int sm_count, cudaStream_t stream)
+{
+  rounds_apply_kernel<<<grid_for((long long)W.xcap, sm_count), kRoundsThreads, 0, stream>>>(P, W, rank);
   return cudaGetLastError();
 }
 

@@ -96,6 +96,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -113,10 +114,11 @@ NcclApi &nccl_api()
   api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
   api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
   api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
   api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
   api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
   api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GroupStart &&
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GroupStart &&
            api.GroupEnd && api.GetErrorString;
   return api;
 }
@@ -284,6 +286,8 @@ void mntr_gpu_destroy(mntr_gpu_ctx *ctx)
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  if (ctx->rws.xsend) cudaFree(ctx->rws.xsend);
+  if (ctx->rws.xrecv) cudaFree(ctx->rws.xrecv);
   if (ctx->h_ctrl) { cudaFreeHost(ctx->h_ctrl); ctx->h_ctrl = nullptr; }
   if (ctx->h_single) { cudaFreeHost(ctx->h_single); ctx->h_single = nullptr; }
   free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->nl_allocs); free_all(ctx->single_allocs);
@@ -643,6 +647,7 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
   CU(cudaMemsetAsync(W.ctrl, 0, 64, ctx->stream));
   CU(launch_rounds_init(P, W, lb_dev, ub_dev, ctx->sm_count, ctx->stream));
   int round = 0, verd = 0;
+  long long last_changed = 0, changed_total = 0;     // variables moved in the last round / so far (same on every rank)
   double rows_ms = 0, comm_ms = 0, vars_ms = 0;
   CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -652,11 +657,26 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     CU(launch_rounds_rows(P, W, ctx->lanes_per_row, directed, round == 1, ctx->sm_count, ctx->stream));
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (ctx->comm) {
+    auto dense_merge = [&]() -> int {
       NC(nc.GroupStart());
       NC(nc.AllReduce(W.nlb, W.nlb, (size_t)P.n + 1, ncclDouble, ncclMax, ctx->comm, ctx->stream));
       NC(nc.AllReduce(W.nub, W.nub, (size_t)P.n, ncclDouble, ncclMin, ctx->comm, ctx->stream));
       NC(nc.GroupEnd());
+      return MNTR_OK;
+    };
+    // Few bounds moved in the previous round (every rank saw the same count): exchange only the changed
+    // candidates -- compact, all-gather of fixed-size messages, merge.  A message that does not fit raises
+    // ctrl[5]: the vars kernel then does nothing and the merge is redone densely below.
+    const bool sparse = ctx->comm && W.xcap > 0 && round > 1 && last_changed <= W.xcap / 2;
+    if (ctx->comm) {
+      int rc2;
+      if (sparse) {
+        CU(cudaMemsetAsync(W.xsend, 0, sizeof(BoundMsg), ctx->stream));
+        CU(launch_rounds_compact(P, W, ctx->sm_count, ctx->stream));
+        NC(nc.AllGather(W.xsend, W.xrecv, sizeof(BoundMsg) * ((size_t)W.xcap + 1), ncclChar, ctx->comm, ctx->stream));
+        CU(launch_rounds_apply(P, W, ctx->rank, ctx->sm_count, ctx->stream));
+        ++ctx->stats.sparse_rounds;
+      } else if ((rc2 = dense_merge())) return rc2;
     }
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
     CU(cudaMemsetAsync(W.ctrl, 0, 12, ctx->stream));          // changed, int moved, next list length
@@ -667,6 +687,22 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
     rows_ms += elapsed(ctx->ev[2], ctx->ev[3]);
     comm_ms += elapsed(ctx->ev[3], ctx->ev[4]);
     vars_ms += elapsed(ctx->ev[4], ctx->ev[5]);
+    if (sparse && ctx->h_ctrl[5]) {       // overflow: nothing was merged or finished; all ranks see it alike
+      int rc2;
+      --ctx->stats.sparse_rounds;
+      CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+      CU(cudaMemsetAsync(W.ctrl + 5, 0, 4, ctx->stream));
+      if ((rc2 = dense_merge())) return rc2;
+      CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+      CU(launch_rounds_vars(P, W, ctx->sm_count, ctx->stream));
+      CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+      CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      comm_ms += elapsed(ctx->ev[3], ctx->ev[4]);
+      vars_ms += elapsed(ctx->ev[4], ctx->ev[5]);
+    }
+    last_changed = (long long)ctx->h_ctrl[4] - changed_total;
+    changed_total = ctx->h_ctrl[4];
     verd = ctx->h_ctrl[3];
     const int changed = ctx->h_ctrl[0], int_moved = ctx->h_ctrl[1];
     if (verd != 0 || !changed) break;
@@ -1127,6 +1163,13 @@ int mntr_gpu_nccl_unique_id(void *id128)
   return MNTR_OK;
 }
 
+static void free_xchg(mntr_gpu_ctx *ctx)
+{
+  if (ctx->rws.xsend) cudaFree(ctx->rws.xsend);
+  if (ctx->rws.xrecv) cudaFree(ctx->rws.xrecv);
+  ctx->rws.xsend = nullptr; ctx->rws.xrecv = nullptr; ctx->rws.xcap = 0; ctx->rws.n_ranks = 1;
+}
+
 int mntr_gpu_comm_init(mntr_gpu_ctx *ctx, int32_t n_ranks, int32_t rank, const void *id128)
 {
   if (!ctx) return MNTR_E_ARG;
@@ -1139,6 +1182,17 @@ int mntr_gpu_comm_init(mntr_gpu_ctx *ctx, int32_t n_ranks, int32_t rank, const v
   memcpy(&id, id128, sizeof(id));
   NC(nc.CommInitRank(&ctx->comm, n_ranks, id, rank));
   ctx->n_ranks = n_ranks; ctx->rank = rank;
+  // buffers of the sparse bound exchange (MNTR_GPU_SPARSE_XCHG=0 switches it off, =<entries> sets the capacity)
+  free_xchg(ctx);
+  int cap = 65536;
+  if (const char *e = getenv("MNTR_GPU_SPARSE_XCHG")) cap = atoi(e);
+  if (cap > 0 && n_ranks > 1) {
+    const size_t msg = sizeof(BoundMsg) * ((size_t)cap + 1);
+    CU(cudaMalloc((void **)&ctx->rws.xsend, msg));
+    CU(cudaMalloc((void **)&ctx->rws.xrecv, msg * (size_t)n_ranks));
+    ctx->rws.xcap = cap;
+  }
+  ctx->rws.n_ranks = n_ranks;
   return MNTR_OK;
 }
 
@@ -1147,6 +1201,7 @@ int mntr_gpu_comm_destroy(mntr_gpu_ctx *ctx)
   if (!ctx) return MNTR_E_ARG;
   if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
   ctx->n_ranks = 1; ctx->rank = 0;
+  free_xchg(ctx);
   return MNTR_OK;
 }
 

@@ -54,7 +54,7 @@ class GpuOptions(C.Structure):
 
 class GpuStats(C.Structure):
     _fields_ = [("nnz_updates", C.c_int64), ("rows_evaluated", C.c_int64), ("n_infeasible", C.c_int64),
-                ("n_changes", C.c_int64), ("max_rounds", C.c_int32), ("reserved", C.c_int32), ("kernel_ms", C.c_double),
+                ("n_changes", C.c_int64), ("max_rounds", C.c_int32), ("sparse_rounds", C.c_int32), ("kernel_ms", C.c_double),
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("comm_ms", C.c_double), ("rows_ms", C.c_double),
                 ("vars_ms", C.c_double)]
 

@@ -41,10 +41,15 @@ def _n_devices():
     return E.load_library().mntr_gpu_device_count()
 
 
+@pytest.mark.parametrize("xchg", ["65536", "0", "48"], ids=["sparse", "dense", "tiny-cap"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_row_partition_nccl_bitwise_independent_of_ranks(engine, world):
+def test_row_partition_nccl_bitwise_independent_of_ranks(engine, world, xchg, monkeypatch):
+    """Row-partitioned mode over NCCL.  The per-round merge is either the dense MAX/MIN all-reduce of the candidate
+    bounds or, after a round that moved few bounds, the sparse exchange (changed candidates all-gathered); a capacity of
+    48 entries makes messages overflow, which must fall back to the dense merge.  Same bits in every case."""
     if _n_devices() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("MNTR_GPU_SPARSE_XCHG", xchg)      # read by mntr_gpu_comm_init
     inst = make_sparse_milp(20_000, 15_000, 9, seed=77, real_data=True, inf_frac=(0.02, 0.02, 0.0))
     engine.load_linear(inst)
     lbs, ubs = branch_boxes(inst.lb, inst.ub, inst.var_type, 3, seed=5, max_depth=10)
@@ -52,14 +57,17 @@ def test_row_partition_nccl_bitwise_independent_of_ranks(engine, world):
     ref = [engine.tighten(lbs[b], ubs[b], order=E.ORDER_JACOBI, flags=E.FLAG_PER_ROUND_KERNELS) for b in range(3)]
     blocks = partition_rows(inst, world)
     uid = E.GpuBoundEngine.nccl_unique_id()
-    out, errs = [None] * world, []
+    out, errs, sparse = [None] * world, [], [0] * world
 
     def run(rank):
         try:
             eng = E.GpuBoundEngine(rank)
             eng.load_linear(blocks[rank])
             eng.comm_init(world, rank, uid)
-            out[rank] = [eng.tighten(lbs[b], ubs[b], order=E.ORDER_JACOBI) for b in range(3)]
+            out[rank] = []
+            for b in range(3):
+                out[rank].append(eng.tighten(lbs[b], ubs[b], order=E.ORDER_JACOBI))
+                sparse[rank] += eng.stats().sparse_rounds
             eng.comm_destroy()
             eng.close()
         except Exception as ex:   # surface worker failures in the main thread
@@ -79,3 +87,7 @@ def test_row_partition_nccl_bitwise_independent_of_ranks(engine, world):
                 assert np.array_equal(got.lb, ref[b].lb) and np.array_equal(got.ub, ref[b].ub), (b, rank)
                 assert got.rounds[0] == ref[b].rounds[0]
                 assert got.nnz_updates[0] == ref[b].nnz_updates[0]     # summed over the ranks
+    if xchg == "65536":
+        assert min(sparse) > 0, "the sparse exchange never ran: the test is vacuous"
+    if xchg == "0":
+        assert max(sparse) == 0

@@ -29,6 +29,10 @@ def test_partition_covers_rows_and_balances_nnz():
     assert shard_boxes(10, 4, 0) == (0, 3) and shard_boxes(10, 4, 3) == (9, 10) and shard_boxes(2, 4, 3) == (2, 2)
 
 
+# (seed, real data, capacity of a sparse-exchange message: 0 = always the dense all-reduce, 6 = overflows often)
+CASES = ((1, False, 0), (2, True, 0), (1, False, 4096), (2, True, 4096), (2, True, 6))
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -39,29 +43,53 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     orc = Oracle()
     out = []
-    for seed, real in ((1, False), (2, True)):
+    for seed, real, cap in CASES:
         inst = make_sparse_milp(400, 350, 6, seed=seed, real_data=real, inf_frac=(0.05, 0.05, 0.0))
         block = partition_rows(inst, world)[rank]
         lb, ub = inst.lb.copy(), inst.ub.copy()
-        rounds, verdict = 0, 0
+        rounds, verdict, last_changed, sparse_rounds = 0, 0, 0, 0
         while True:
             rounds += 1
             nl, nu, inf = orc.lin_jacobi_round_rows(block, lb, ub)
-            # the merge: MAX on lower candidates (+ the row-infeasible flag in an extra slot), MIN on upper
-            tl = torch.from_numpy(np.concatenate([nl, [float(inf)]]))
-            tu = torch.from_numpy(nu.copy())
-            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tu, op=dist.ReduceOp.MIN)
+            merged = False
+            if cap > 0 and rounds > 1 and last_changed <= cap // 2:
+                # the sparse exchange (mntr_gpu.cu run_rounds_dev): fixed-size messages {count, flag | (j, lb, ub)...} of
+                # the changed candidates are all-gathered and merged with max / min; a message that does not fit makes
+                # every rank fall back to the dense merge
+                idx = np.flatnonzero((nl != lb) | (nu != ub))
+                msg = np.zeros((cap + 1, 3))
+                msg[0] = (len(idx), float(inf), 0.0)
+                k = min(len(idx), cap)
+                msg[1:k + 1, 0] = idx[:k]; msg[1:k + 1, 1] = nl[idx[:k]]; msg[1:k + 1, 2] = nu[idx[:k]]
+                got = [torch.zeros(cap + 1, 3, dtype=torch.float64) for _ in range(world)]
+                dist.all_gather(got, torch.from_numpy(msg))
+                if all(int(g[0, 0]) <= cap for g in got):
+                    ml, mu, flag = nl.copy(), nu.copy(), float(inf)
+                    for g in got:
+                        c = int(g[0, 0]); flag = max(flag, float(g[0, 1]))
+                        j = g[1:c + 1, 0].numpy().astype(np.int64)
+                        np.maximum.at(ml, j, g[1:c + 1, 1].numpy()); np.minimum.at(mu, j, g[1:c + 1, 2].numpy())
+                    tl = torch.from_numpy(np.concatenate([ml, [flag]])); tu = torch.from_numpy(mu)
+                    merged = True
+                    sparse_rounds += 1
+            if not merged:
+                # the dense merge: MAX on lower candidates (+ the row-infeasible flag in an extra slot), MIN on upper
+                tl = torch.from_numpy(np.concatenate([nl, [float(inf)]]))
+                tu = torch.from_numpy(nu.copy())
+                dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tu, op=dist.ReduceOp.MIN)
             if tl[-1].item() > 0:
                 verdict = 2
                 break
-            lb, ub, bad, changed = orc.lin_jacobi_round_vars(inst, lb, ub, tl[:-1].numpy(), tu.numpy())
+            new_lb, new_ub, bad, changed = orc.lin_jacobi_round_vars(inst, lb, ub, tl[:-1].numpy(), tu.numpy())
+            last_changed = int(np.count_nonzero((new_lb != lb) | (new_ub != ub)))
+            lb, ub = new_lb, new_ub
             if bad:
                 verdict = 1
                 break
             if not changed:
                 break
-        out.append((lb, ub, verdict, rounds))
+        out.append((lb, ub, verdict, rounds, sparse_rounds))
     q.put((rank, out))
     dist.destroy_process_group()
 
@@ -79,11 +107,12 @@ def test_merge_protocol_world2_gloo(oracle):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for k, (seed, real) in enumerate(((1, False), (2, True))):
+    for k, (seed, real, cap) in enumerate(CASES):
         inst = make_sparse_milp(400, 350, 6, seed=seed, real_data=real, inf_frac=(0.05, 0.05, 0.0))
         jl, ju, jr = oracle.lin_fixpoint_jacobi(inst, inst.lb, inst.ub)
         for rank in (0, 1):
-            lb, ub, verdict, rounds = results[rank][k]
+            lb, ub, verdict, rounds, sparse_rounds = results[rank][k]
+            assert (sparse_rounds > 0) == (cap == 4096 and jr["rounds"] > 1) or cap == 6
             assert (verdict != 0) == (jr["verdict"] != 0)
             if jr["verdict"] == 0:
                 assert np.array_equal(lb, jl) and np.array_equal(ub, ju), (seed, rank)
