@@ -224,12 +224,18 @@ rounds_apply_kernel(LinDev P, RoundsWs W, int rank)
 __global__ void __launch_bounds__(kRoundsThreads)
 rounds_vars_kernel(LinDev P, RoundsWs W)
 {
-  if (W.ctrl[5] != 0) return;        // the sparse exchange overflowed: the host redoes the merge, then calls again
+  // two device-wide words, read by ONE thread per block: thousands of warps asking for the same L2 line at kernel start
+  // are served one after the other (measured: 20 us per launch)
+  __shared__ int s_skip;
+  __shared__ double s_inf;
+  if (threadIdx.x == 0) { s_skip = W.xcap > 0 ? W.ctrl[5] : 0; s_inf = W.nlb[P.n]; }
+  __syncthreads();
+  if (s_skip != 0) return;           // the sparse exchange overflowed: the host redoes the merge, then calls again
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int warp_g = tid >> 5, n_warps = nthreads >> 5;
   int changed = 0, int_moved = 0, bad = 0, n_changed = 0;
-  const bool row_inf = W.nlb[P.n] > 0.0;          // merged flag: some rank found an activity-infeasible row
+  const bool row_inf = s_inf > 0.0;               // merged flag: some rank found an activity-infeasible row
   if (!row_inf) {
     for (int j0 = warp_g * 32; j0 < P.n; j0 += n_warps * 32) {
       const int j = j0 + lane;
