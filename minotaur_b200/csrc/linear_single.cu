@@ -142,17 +142,17 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
   // ---- phase 0: both boxes = incoming box; round 1's rows all due; moved-variable bit sets empty, except that
   //      integer variables whose INCOMING bounds are fractional move in round 1 by rounding alone: they are
   //      marked in touched[0], which round 1's fix-up scans ----
+  //      The incoming box may live in pinned HOST memory (zero-copy end-to-end call): its loads are issued first and
+  //      consumed last, so the trips over PCIe overlap everything else this phase does.
   {
     int cross0 = 0;
-    for (int j0 = gtid - lane; j0 < P.n; j0 += nthreads) {     // warp-uniform trip count: lanes = 32 consecutive j
-      const int j = j0 + lane;
+    auto take = [&](int j0, int j, bool in, double2 b, uint8_t ty) {
       bool frac = false;
-      if (j < P.n) {
-        const double2 b = make_double2(lb_io[j], ub_io[j]);
+      if (in) {
         W.box[0][j] = b;
         W.box[1][j] = b;
         double2 r = b;
-        if (is_int_type(__ldg(P.var_type + j))) {
+        if (is_int_type(ty)) {
           tighten_int_bounds(r.x, r.y);
           frac = r.x != b.x || r.y != b.y;
         }
@@ -160,20 +160,37 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
       }
       const unsigned fm = __ballot_sync(kFullMask, frac);
       if (lane == 0) { W.touched[0][j0 >> 5] = fm; W.touched[1][j0 >> 5] = 0u; W.ever[j0 >> 5] = 0u; }
-    }
+    };
+    // the first (for n <= threads of the grid: the only) trip of the box sweep: loads now
+    const int jf0 = gtid - lane, jf = jf0 + lane;
+    const bool inf = jf < P.n;
+    double2 bf = make_double2(0.0, 0.0);
+    uint8_t tyf = 4;
+    if (inf) { bf = make_double2(lb_io[jf], ub_io[jf]); tyf = __ldg(P.var_type + jf); }
     // round 1 takes every row without looking at its bit set (:1618-1622)
     const int nw_rows = (P.m + 31) / 32;
     for (int w = gtid; w < nw_rows; w += nthreads) { W.due[0][w] = 0u; W.due[1][w] = 0u; }
-    if (cross0) atomicOr(W.sync + 3, kCtlInCross);
     // the CSC lists (rows to flag when a variable moves) are first needed at the end of round 1, on its critical
-    // path: pull them into L2 now
-    const char *cp = reinterpret_cast<const char *>(P.csc_ptr), *cr = reinterpret_cast<const char *>(P.csc_row);
-    for (long long o = (long long)gtid * 128; o < (long long)(P.n + 1) * 4; o += (long long)nthreads * 128)
-      asm volatile("prefetch.global.L2 [%0];" :: "l"(cp + o));
-    for (long long o = (long long)gtid * 128; o < (long long)P.csc_nnz * 4; o += (long long)nthreads * 128)
-      asm volatile("prefetch.global.L2 [%0];" :: "l"(cr + o));
+    // path: pull them into L2 now (when they are small enough to stay there)
+    if ((long long)P.csc_nnz + P.n < (8ll << 20)) {
+      const char *cp = reinterpret_cast<const char *>(P.csc_ptr), *cr = reinterpret_cast<const char *>(P.csc_row);
+      for (long long o = (long long)gtid * 128; o < (long long)(P.n + 1) * 4; o += (long long)nthreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(cp + o));
+      for (long long o = (long long)gtid * 128; o < (long long)P.csc_nnz * 4; o += (long long)nthreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(cr + o));
+    }
+    if constexpr (RES) resident_fill(P, S, lane, head);
+    if (jf0 < P.n) take(jf0, jf, inf, bf, tyf);
+    for (int j0 = jf0 + nthreads; j0 < P.n; j0 += nthreads) {     // warp-uniform trip count: lanes = 32 consecutive j
+      const int j = j0 + lane;
+      const bool in = j < P.n;
+      double2 b = make_double2(0.0, 0.0);
+      uint8_t ty = 4;
+      if (in) { b = make_double2(lb_io[j], ub_io[j]); ty = __ldg(P.var_type + j); }
+      take(j0, j, in, b, ty);
+    }
+    if (cross0) atomicOr(W.sync + 3, kCtlInCross);
   }
-  if constexpr (RES) resident_fill(P, S, lane, head);
   MNTR_TRACE();
   grid_barrier(W.sync, gridDim.x, bar_target, s_ctl, nullptr);
   MNTR_TRACE();
