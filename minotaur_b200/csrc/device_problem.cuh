@@ -20,6 +20,7 @@ struct LinDev {
   const int32_t *csc_ptr;   // [n+1]
   const int32_t *csc_row;   // [nnz]
   int32_t csc_nnz;          // length of csc_row
+  int32_t nnz_pad;          // length of col / colx / val (rows padded to kRowPad entries)
   // wavefront schedule of the reference's index-ordered in-place sweep
   int32_t n_levels;
   const int32_t *level_ptr; // [n_levels+1] ranges of STORED rows (rows are stored in level order)

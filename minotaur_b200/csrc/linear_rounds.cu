@@ -31,8 +31,13 @@ struct __align__(16) StreamStage {
   int tcount;
   int pad_[3];                     // [1] length of the candidate queue
   static constexpr bool kSlab = false;
+  static constexpr bool kL2Hints = false;    // (measured: the hints slow this kernel down, 0.65 -> 0.85 ms at 2.5M rows)
   __device__ __forceinline__ double *stage_val() { return sval; }
   __device__ __forceinline__ int32_t *stage_col() { return scol; }
+  // (row heads staged ahead: never used here -- blocks are interleaved over the warps, no block has an adjacent next
+  //  one -- and kept out of the slice: three blocks of 62 KB leave the SM 32 KB of L1, which this kernel needs)
+  __device__ __forceinline__ int2 *stage_info() { return nullptr; }
+  __device__ __forceinline__ double2 *stage_bnd() { return nullptr; }
   __device__ __forceinline__ uint16_t *work_list() { return reinterpret_cast<uint16_t *>(q); }
   __device__ __forceinline__ CandItem *queue() { return q; }
 };

@@ -411,6 +411,7 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if ((rc = dev_upload(ctx, ctx->lin_allocs, cptr.data(), (size_t)n + 1, &L.csc_ptr))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, crow.data(), (size_t)nnz, &L.csc_row))) return rc;
   L.csc_nnz = (int32_t)nnz;
+  L.nnz_pad = (int32_t)pcol.size();
   if ((rc = dev_upload(ctx, ctx->lin_allocs, lptr.data(), (size_t)n_levels + 1, &L.level_ptr))) return rc;
 
   // ---- single-box workspace ----

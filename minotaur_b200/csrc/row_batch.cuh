@@ -56,12 +56,18 @@ struct __align__(16) WarpStage {
   // candidates in the second half of phi[]; the work list of a block with more candidates than the queue holds
   // overwrites the staged values (they have been consumed by then).
   static constexpr bool kSlab = false;
+  static constexpr bool kL2Hints = true;     // matrix stream evict-first, box gathers evict-last (common.cuh)
   static constexpr int kQueueCap = 48;
   __device__ __forceinline__ double *stage_val() { return plo; }
   __device__ __forceinline__ int32_t *stage_col() { return reinterpret_cast<int32_t *>(phi); }
   __device__ __forceinline__ CandItem *queue() { return reinterpret_cast<CandItem *>(phi + kCap / 2); }
   __device__ __forceinline__ uint16_t *work_list() { return reinterpret_cast<uint16_t *>(plo); }
+  // row heads of the NEXT 32-row block, staged ahead together with its entries (slot[] / flag[] are only used by the
+  // staged batches, which run after the dense blocks)
+  __device__ __forceinline__ int2 *stage_info() { return reinterpret_cast<int2 *>(slot); }
+  __device__ __forceinline__ double2 *stage_bnd() { return reinterpret_cast<double2 *>(slot + 256); }
 };
+static_assert(2 * kCap >= 32 * (sizeof(int2) + sizeof(double2)), "staged row heads fit slot[] + flag[]");
 static_assert(kCap >= kStageEntries && sizeof(double) * (kCap / 2) >= sizeof(int32_t) * kStageEntries, "staged block fits");
 static_assert(sizeof(double) * (kCap / 2) >= sizeof(CandItem) * WarpStage::kQueueCap, "the candidate queue fits phi[]");
 static_assert(sizeof(double) * kCap >= sizeof(uint16_t) * 32 * 32, "the work list of a 32-row block fits plo[]");

@@ -43,6 +43,7 @@ struct __align__(16) ResidentStage {
   int items[kListCap];
   uint16_t work[32 * kLaneMax];     // (row lane | entry << 5) of the entries whose exact candidates are due
   static constexpr bool kSlab = true;
+  static constexpr bool kL2Hints = false;
   __device__ __forceinline__ int *list() { return items; }
   __device__ __forceinline__ uint16_t *work_list() { return work; }
   static constexpr int kQueueCap = 0;                                   // (resident rows take their candidates at once)
@@ -153,9 +154,12 @@ __device__ __noinline__ void drain_queue(const LinDev &P, const ReadPending &rd,
 template <class R, class Sink, class Stage>
 __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending &rd, const Sink &sink, Stage &S,
                                               int lane, bool due, const RowHead h, bool first,
-                                              const int32_t *gcol = nullptr, const double *gval = nullptr)
+                                              const int32_t *gcol = nullptr, const double *gval = nullptr,
+                                              int next_row0 = -1, int next_e0 = 0)
 {
-  // gcol / gval (streaming form): where the lane's row starts -- in the CSR, or in the block staged in shared memory
+  // gcol / gval (streaming form): where the lane's row starts -- in the CSR, or in the block staged in shared memory;
+  // next_row0 >= 0: the warp's next block starts at that row and at entry next_e0 -- its heads and entries are
+  // requested (cp.async) as soon as pass 1 has consumed this block's staged entries
   if (first && due && h.rl > h.ru + kETol) sink.row_bounds_cross();     // checkBounds_, rows part (:328-359)
   const bool mine = due && h.cnt <= kLaneMax;
   unsigned longm = __ballot_sync(kFullMask, due && h.cnt > kLaneMax);
@@ -164,6 +168,8 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
   sink.mark(S, lane); sink.phase(lane, 0);
 
   // ---- pass 1: activities, terms in ascending column order ----
+  [[maybe_unused]] unsigned long long keep = 0ull;
+  if constexpr (!Stage::kSlab) { if constexpr (Stage::kL2Hints) keep = l2_policy_evict_last(); }
   double ll = 0.0, uu = 0.0;
   unsigned need = 0u;
   double slb = INFINITY, sub = INFINITY;
@@ -203,7 +209,13 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
       for (int u = 0; u < kPassGroup; ++u) {
         const int t = g * kPassGroup + u;
         b[u] = make_double2(0.0, 0.0);
-        if (t < cnt) b[u] = __ldcg(rd.box + (cv[u] & kColMask));
+        if (t < cnt) {
+          bool hinted = false;
+          if constexpr (!Stage::kSlab) {
+            if constexpr (Stage::kL2Hints) { b[u] = ld_box_keep(rd.box + (cv[u] & kColMask), keep); hinted = true; }   // the box stays in L2
+          }
+          if (!hinted) b[u] = __ldcg(rd.box + (cv[u] & kColMask));
+        }
       }
 #pragma unroll
       for (int u = 0; u < kPassGroup; ++u) {
@@ -219,6 +231,9 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
           reach[t] = __double2float_ru(term_reach(a, b[u]));
         }
       }
+    }
+    if constexpr (!Stage::kSlab) {
+      if (next_row0 >= 0 && longm == 0u) stage_next_block(P, S, lane, next_row0, next_e0);     // (eval_long would reuse plo[])
     }
     for (int t = kRes; t < maxc; ++t) {         // tails of rows longer than the resident part (global CSR)
       if (t < cnt) {
@@ -291,7 +306,15 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
         __syncwarp();
         queued = true;
       } else if (total > 0) {
-        drain_queue<R>(P, rd, sink, S, lane);      // the work list below shares the queue's storage
+        // more candidates than the queue holds (rare): each lane takes its own, one per warp-uniform trip
+        drain_queue<R>(P, rd, sink, S, lane);
+        while (__any_sync(kFullMask, need != 0u)) {
+          double a = 0.0; int cx = 0;
+          const bool on = need != 0u;
+          if (on) { resident_entry(P, S, lane, h.beg, __ffs(need) - 1, a, cx); need &= need - 1; }
+          exact_and_flag<R>(P, rd, sink, S, lane, on, slb, sub, (int)sg, a, cx);
+        }
+        queued = true;
       }
     }
     if (total > 0 && !queued) {
@@ -424,16 +447,55 @@ __device__ __forceinline__ void stage_block(const LinDev &P, Stage &S, int lane,
   int32_t *sc = S.stage_col();
   double *sv = S.stage_val();
   __syncwarp();
-  for (int o = lane * 4; o < extent; o += 128) {
-    const unsigned dc = (unsigned)__cvta_generic_to_shared(sc + o), dv = (unsigned)__cvta_generic_to_shared(sv + o);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dc), "l"(P.colx + e0 + o) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dv), "l"(P.val + e0 + o) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dv + 16), "l"(P.val + e0 + o + 2) : "memory");
+  if constexpr (Stage::kL2Hints) {
+    const unsigned long long pol = l2_policy_evict_first();
+    for (int o = lane * 4; o < extent; o += 128) {
+      const unsigned dc = (unsigned)__cvta_generic_to_shared(sc + o), dv = (unsigned)__cvta_generic_to_shared(sv + o);
+      cp_async16_stream(dc, P.colx + e0 + o, pol);
+      cp_async16_stream(dv, P.val + e0 + o, pol);
+      cp_async16_stream(dv + 16, P.val + e0 + o + 2, pol);
+    }
+  } else {
+    for (int o = lane * 4; o < extent; o += 128) {
+      const unsigned dc = (unsigned)__cvta_generic_to_shared(sc + o), dv = (unsigned)__cvta_generic_to_shared(sv + o);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dc), "l"(P.colx + e0 + o) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dv), "l"(P.val + e0 + o) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dv + 16), "l"(P.val + e0 + o + 2) : "memory");
+    }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
   gcol = sc + (h.beg - e0); gval = sv + (h.beg - e0);
+}
+
+// ---- streaming form, staging AHEAD ----
+// The rows of a warp's range lie back to back in the CSR, so the next 32-row block's entries start where this block's
+// end -- known before the next heads are.  Right after pass 1 (the staged entries of the current block are consumed)
+// the next block's row heads AND a window of kStageEntries entries from that position are requested together with
+// cp.async: by the time the current block's product test and candidates are done they have landed, and the next block
+// starts with shared-memory reads instead of two dependent trips to DRAM (heads, then entries).
+template <class Stage>
+__device__ __forceinline__ void stage_next_block(const LinDev &P, Stage &S, int lane, int row0, int e0)
+{
+  __syncwarp();
+  {
+    const unsigned di = (unsigned)__cvta_generic_to_shared(S.stage_info() + lane);
+    const unsigned db = (unsigned)__cvta_generic_to_shared(S.stage_bnd() + lane);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(di), "l"(P.row_info + row0 + lane) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(db), "l"(P.row_bnd + row0 + lane) : "memory");
+  }
+  const int extent = min(kStageEntries, P.nnz_pad - e0);      // (a multiple of four: rows are padded)
+  int32_t *sc = S.stage_col();
+  double *sv = S.stage_val();
+  const unsigned long long pol = l2_policy_evict_first();
+  for (int o = lane * 4; o < extent; o += 128) {
+    const unsigned dc = (unsigned)__cvta_generic_to_shared(sc + o), dv = (unsigned)__cvta_generic_to_shared(sv + o);
+    cp_async16_stream(dc, P.colx + e0 + o, pol);
+    cp_async16_stream(dv, P.val + e0 + o, pol);
+    cp_async16_stream(dv + 16, P.val + e0 + o + 2, pol);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // STREAMING form (rows not resident: large instances).  The due rows of [r0, r1): 32-row blocks (one word of the bit
@@ -462,19 +524,52 @@ __device__ __forceinline__ void eval_due_stream(const LinDev &P, const ReadPendi
       if (dense && !first) atomicAnd(due + w, ~word);            // setBFlag(false), :513
       if (word != 0u && !dense) rest = true;
       unsigned dm = __ballot_sync(kFullMask, dense);
+      int spec_row0 = -1, spec_e0 = 0;         // the block staged ahead (first row, first entry of the window), if any
       while (dm) {
         const int k = __ffs(dm) - 1;
         dm &= dm - 1;
         const unsigned wk = __shfl_sync(kFullMask, word, k);
-        const int row = (wb + k) * 32 + lane;
+        const int row0 = (wb + k) * 32, row = row0 + lane;
         const bool bit = (wk >> lane) & 1u;
-        const RowHead h = load_head(P, bit ? row : -1);
+        // heads of ALL the block's rows (the end of its last row is where the next block's entries start)
+        RowHead h{0, -1, 0.0, 0.0};
+        const bool ahead = spec_row0 == row0;
+        if (ahead) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          const int2 info = S.stage_info()[lane];
+          const double2 bnd = S.stage_bnd()[lane];
+          h = RowHead{info.x, info.y, bnd.x, bnd.y};
+        } else if (row < P.m) {
+          h = load_head(P, row);
+        }
         const bool is_due = bit && h.cnt >= 0;                     // deleted rows (term count < 0) are never evaluated
         if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
+        // where the lane's row starts: in the window staged ahead if it covers the block's due rows, else staged now
+        // (one burst) or read from the CSR
         const int32_t *gcol; const double *gval;
-        stage_block(P, S, lane, is_due, h, gcol, gval);
-        eval_resident<R>(P, rd, sink, S, lane, is_due, h, first, gcol, gval);
+        const int d1 = __reduce_max_sync(kFullMask, is_due ? row_end(make_int2(h.beg, h.cnt)) : 0);
+        const int d0 = __reduce_min_sync(kFullMask, is_due ? h.beg : 0x7fffffff);
+        if (ahead && d0 >= spec_e0 && d1 <= spec_e0 + kStageEntries) {
+          gcol = S.stage_col() + (h.beg - spec_e0); gval = S.stage_val() + (h.beg - spec_e0);
+        } else {
+          stage_block(P, S, lane, is_due, h, gcol, gval);
+        }
+        // the next dense block is the adjacent one and this block has no deleted rows: stage it ahead
+        const bool whole = __all_sync(kFullMask, row < P.m && h.cnt >= 0);
+        const int blk_end = __shfl_sync(kFullMask, row_end(make_int2(h.beg, h.cnt < 0 ? 0 : h.cnt)), 31);
+#ifdef MNTR_K1_NOSPEC
+        const bool adj = false;
+#else
+        const bool adj = dm != 0u && __ffs(dm) - 1 == k + 1 && whole && row0 + 64 <= P.m && blk_end < P.nnz_pad;
+#endif
+        spec_row0 = adj ? row0 + 32 : -1;
+        spec_e0 = blk_end;
+        eval_resident<R>(P, rd, sink, S, lane, is_due, h, first, gcol, gval, spec_row0, spec_e0);
+        if (spec_row0 >= 0 && __ballot_sync(kFullMask, is_due && h.cnt > kLaneMax) != 0u) spec_row0 = -1;   // (not issued)
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
     }
     drain_queue<R>(P, rd, sink, S, lane);
     if (first || !__any_sync(kFullMask, rest)) return;
