@@ -364,3 +364,29 @@ class Reference:
         nnz = C.c_int64(0); ninf = C.c_int64(0)
         secs = self.lib().ref_time_boxes(self.h, mode, nb, _d(lbs), _d(ubs), C.byref(nnz), C.byref(ninf))
         return secs, nnz.value, ninf.value
+
+
+def ref_read_mps(path: str) -> dict:
+    """The reference's own Reader::readMps (Reader.cpp:42-473) on `path`, dumped flat (fixture generator of
+    minotaur_b200/mps_reader.py)."""
+    L = Reference.lib()
+    _u8 = C.POINTER(C.c_uint8)
+    L.ref_read_mps.argtypes = [C.c_char_p, _ip, _ip, _ip, _ip, _ip, _dp, _dp, _dp, _u8, _dp, _dp, _ip, _ip, _dp, _dp]
+    L.ref_read_mps.restype = C.c_int32
+    m, n, nnz, ok = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    oc = C.c_double(0.0)
+    null_i, null_d, null_u = _ip(), _dp(), _u8()
+    err = L.ref_read_mps(path.encode(), C.byref(m), C.byref(n), C.byref(nnz), null_i, null_i, null_d, null_d, null_d,
+                         null_u, null_d, null_d, C.byref(ok), null_i, null_d, C.byref(oc))
+    if err != 0:
+        raise RuntimeError(f"Reader::readMps failed with code {err}")
+    out = dict(row_ptr=np.zeros(m.value + 1, np.int32), col=np.zeros(nnz.value, np.int32), val=np.zeros(nnz.value),
+               row_lb=np.zeros(m.value), row_ub=np.zeros(m.value), var_type=np.zeros(n.value, np.uint8),
+               lb=np.zeros(n.value), ub=np.zeros(n.value), obj_col=np.zeros(ok.value, np.int32), obj_val=np.zeros(ok.value))
+    def ip(a): return a.ctypes.data_as(_ip)
+    def dp(a): return a.ctypes.data_as(_dp)
+    L.ref_read_mps(path.encode(), C.byref(m), C.byref(n), C.byref(nnz), ip(out["row_ptr"]), ip(out["col"]), dp(out["val"]),
+                   dp(out["row_lb"]), dp(out["row_ub"]), out["var_type"].ctypes.data_as(_u8), dp(out["lb"]), dp(out["ub"]),
+                   C.byref(ok), ip(out["obj_col"]), dp(out["obj_val"]), C.byref(oc))
+    out["obj_const"] = np.array([oc.value])
+    return out

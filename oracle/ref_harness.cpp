@@ -32,6 +32,7 @@
 #include "Objective.h"
 #include "Option.h"
 #include "Problem.h"
+#include "Reader.h"
 #include "SolutionPool.h"
 #include "Types.h"
 #include "VarBoundMod.h"
@@ -364,6 +365,56 @@ double ref_time_boxes(void *hv, int32_t mode, int32_t n_boxes, const double *lbs
     *nnz_total += nnz; *n_infeasible += inf;
   }
   return secs;
+}
+
+// ---- Reader::readMps (Reader.cpp:42-473): read an MPS file with the reference's own reader and dump the problem
+//      flat -- the fixture generator of minotaur_b200/mps_reader.py.  Two-call protocol: sizes first (arrays null),
+//      then the arrays.  Returns the reader's error code (0 = ok), or -1 if the file gave no problem.
+int32_t ref_read_mps(const char *path, int32_t *m, int32_t *n, int32_t *nnz, int32_t *row_ptr, int32_t *col,
+                     double *val, double *row_lb, double *row_ub, uint8_t *var_type, double *lb, double *ub,
+                     int32_t *obj_k, int32_t *obj_col, double *obj_val, double *obj_const)
+{
+  EnvPtr env = new Environment();
+  int err = 0;
+  env->getLogger()->setMaxLevel(LogNone);
+  env->startTimer(err);
+  Reader rd(env);
+  ProblemPtr p = rd.readMps(path, err);
+  if (!p) { delete env; return err ? err : -1; }
+  *m = (int32_t)p->getNumCons(); *n = (int32_t)p->getNumVars();
+  int32_t cnt = 0, k = 0;
+  if (row_ptr) row_ptr[0] = 0;
+  for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it, ++k) {
+    LinearFunctionPtr lf = (*it)->getLinearFunction();
+    if (lf) {
+      for (VariableGroupConstIterator t = lf->termsBegin(); t != lf->termsEnd(); ++t) {
+        if (col) { col[cnt] = (int32_t)t->first->getIndex(); val[cnt] = t->second; }
+        ++cnt;
+      }
+    }
+    if (row_ptr) { row_ptr[k + 1] = cnt; row_lb[k] = (*it)->getLb(); row_ub[k] = (*it)->getUb(); }
+  }
+  *nnz = cnt;
+  if (var_type) {
+    int j = 0;
+    for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it, ++j) {
+      var_type[j] = (uint8_t)(*it)->getType(); lb[j] = (*it)->getLb(); ub[j] = (*it)->getUb();
+    }
+  }
+  *obj_k = 0; *obj_const = 0.0;
+  if (p->getObjective()) {
+    *obj_const = p->getObjective()->getConstant();
+    LinearFunctionPtr lf = p->getObjective()->getLinearFunction();
+    if (lf) {
+      for (VariableGroupConstIterator t = lf->termsBegin(); t != lf->termsEnd(); ++t) {
+        if (obj_col) { obj_col[*obj_k] = (int32_t)t->first->getIndex(); obj_val[*obj_k] = t->second; }
+        ++*obj_k;
+      }
+    }
+  }
+  delete p;
+  delete env;
+  return err;
 }
 
 void ref_destroy(void *hv)

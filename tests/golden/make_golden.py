@@ -262,7 +262,20 @@ def tls4_cases():
     return out
 
 
+def mps_cases():
+    """tests/golden/mps/*.mps read by the reference's own Reader::readMps (Reader.cpp:42-473)."""
+    from oracle.pyoracle import ref_read_mps
+    out = {}
+    d = os.path.join(HERE, "mps")
+    for f in sorted(os.listdir(d)):
+        if f.endswith(".mps"):
+            for k, v in ref_read_mps(os.path.join(d, f)).items():
+                out[f"{f[:-4]}.{k}"] = v
+    return out
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "mps_cases.npz"), **mps_cases())
     t4 = tls4_cases()
     np.savez_compressed(os.path.join(HERE, "tls4_cases.npz"), **t4)
     print("tls4_cases.npz", os.path.getsize(os.path.join(HERE, "tls4_cases.npz")), "bytes")

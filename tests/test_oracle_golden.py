@@ -219,3 +219,19 @@ def test_nl_reader_reads_the_reference_instance():
     assert np.array_equal(P.lin.cut_col, z["tls4_inc.cut_col"]) and np.array_equal(P.lin.cut_val, z["tls4_inc.cut_val"])
     # Jacobian non-zeros of the header: linear rows + linear parts and variable leaves of the 4 nonlinear rows
     assert P.lin.nnz + int(P.tapes.lin_ptr[-1]) + int(np.sum(P.tapes.op == 34)) == 588
+
+
+@pytest.mark.parametrize("name", ["small_mixed", "knap"])
+def test_mps_reader_matches_reference_reader(name):
+    """minotaur_b200/mps_reader.py against the reference's own Reader::readMps (Reader.cpp:42-473) on
+    tests/golden/mps/*.mps -- fixture tests/golden/mps_cases.npz, generated by make_golden.py: rows in ROWS order,
+    variables by first appearance, added / cancelled duplicate coefficients, range rows (the reference's sign for a
+    negative range on an E row included), every bound type, the ignored second RHS / RANGES / BOUNDS sets, objective."""
+    from minotaur_b200.mps_reader import read_mps
+    z = np.load(os.path.join(GOLD, "mps_cases.npz"))
+    P = read_mps(os.path.join(GOLD, "mps", name + ".mps"))
+    P.validate()
+    for k in ("row_ptr", "col", "val", "row_lb", "row_ub", "var_type", "lb", "ub"):
+        assert np.array_equal(getattr(P, k), z[f"{name}.{k}"]), k
+    assert np.array_equal(P.cut_col, z[f"{name}.obj_col"]) and np.array_equal(P.cut_val, z[f"{name}.obj_val"])
+    assert P.obj_const == float(z[f"{name}.obj_const"][0])
