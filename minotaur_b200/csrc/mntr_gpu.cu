@@ -801,9 +801,12 @@ static int tighten_single_zero_copy(mntr_gpu_ctx *ctx, double *lb_map, double *u
                                     int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
 {
   int rc;
-  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  // device-side timing of the call (stats.kernel_ms) costs two event records on the critical path of a ~125 us call:
+  // only when asked for (MNTR_GPU_TIMING=1)
+  static const bool timing = [] { const char *e = getenv("MNTR_GPU_TIMING"); return e && e[0] == '1'; }();
+  if (timing) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   if ((rc = run_single_dev(ctx, lb_map, ub_map, o))) return rc;
-  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (timing) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   const SingleCtrl ctrl = *ctx->h_single;      // written by the kernel's last block
   ctx->ctrl_clean = true;
@@ -811,7 +814,7 @@ static int tighten_single_zero_copy(mntr_gpu_ctx *ctx, double *lb_map, double *u
   if (rounds) *rounds = ctrl.status[1];
   if (nnz_updates) *nnz_updates = (int64_t)ctrl.counters[0];
   account_single(ctx, ctrl);
-  ctx->stats.kernel_ms += elapsed(ctx->ev[1], ctx->ev[2]);       // includes the PCIe reads / writes of the box
+  if (timing) ctx->stats.kernel_ms += elapsed(ctx->ev[1], ctx->ev[2]);       // includes the PCIe reads / writes of the box
   return MNTR_OK;
 }
 
