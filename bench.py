@@ -13,7 +13,7 @@ box tightened to the fixpoint.  A "step" is one whole fixpoint call (all rounds)
   cpu_baseline: the reference's own LinearHandler sweeps (oracle/_ref, built from /root/reference) or,
            if that library is absent, the plain-C oracle port, timed on this host's cores
 
-N>1 (torchrun): every rank tightens its own C2-shaped instance (independent replicas, weak scaling, no
+N>1 (torchrun): every rank tightens its own copy of the C2 instance (independent replicas, weak scaling, no
 data-path collective); value = total nnz-updates / max-over-ranks time.  `extra.node_batch` reports the
 C3-shaped node batch (8192 boxes sharded by node across the ranks).
 
@@ -211,7 +211,9 @@ def main():
         return float(t.item())
 
     # ---------------- workload C2 (one replica per rank) ----------------
-    cfg = dict(C2); cfg["seed"] = C2["seed"] + rank
+    # every rank tightens its own copy of the SAME instance (replicas): per-GPU work is identical, so the job's value
+    # over N measures the machine, not the spread of round counts over differently seeded instances
+    cfg = dict(C2)
     inst = make_sparse_milp(**cfg)
     eng = E.GpuBoundEngine(local_rank)
     eng.load_linear(inst)

@@ -22,8 +22,9 @@ cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per
 cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream);
 // sparse bound exchange: compact this rank's changed candidates into W.xsend; after the all-gather into W.xrecv,
 // merge the other ranks' candidates (or raise ctrl[5] if any rank's message overflowed)
-cudaError_t launch_rounds_compact(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream);
-cudaError_t launch_rounds_apply(const LinDev &P, const RoundsWs &W, int rank, int sm_count, cudaStream_t stream);
+// cap: the capacity tier of this round's messages (<= W.xcap, the same on every rank)
+cudaError_t launch_rounds_compact(const LinDev &P, const RoundsWs &W, int cap, int sm_count, cudaStream_t stream);
+cudaError_t launch_rounds_apply(const LinDev &P, const RoundsWs &W, int rank, int cap, int sm_count, cudaStream_t stream);
 cudaError_t launch_rounds_finish(const LinDev &P, const RoundsWs &W, double *lb_dev, double *ub_dev, int sm_count,
                                  cudaStream_t stream);
 

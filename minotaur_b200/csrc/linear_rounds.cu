@@ -175,7 +175,7 @@ rounds_rows_kernel(LinDev P, RoundsWs W, int first)
 // ---- sparse bound exchange: rounds in which few bounds move need not all-reduce 16 bytes per variable ----
 // this rank's changed candidates (nlb / nub differ from the replicated box) -> W.xsend; entry 0 is the header
 __global__ void __launch_bounds__(kRoundsThreads)
-rounds_compact_kernel(LinDev P, RoundsWs W)
+rounds_compact_kernel(LinDev P, RoundsWs W, int cap)
 {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
@@ -197,7 +197,7 @@ rounds_compact_kernel(LinDev P, RoundsWs W)
     base = __shfl_sync(0xffffffffu, base, 0);
     if (ch) {
       const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
-      if (at < (unsigned long long)W.xcap) W.xsend[1 + at] = BoundMsg{l, u, (long long)j};
+      if (at < (unsigned long long)cap) W.xsend[1 + at] = BoundMsg{l, u, (long long)j};
     }
   }
 }
@@ -205,12 +205,12 @@ rounds_compact_kernel(LinDev P, RoundsWs W)
 // merge the other ranks' candidates into nlb / nub (exact max / min: the result does not depend on the order);
 // any message longer than the capacity: raise ctrl[5] and leave nlb / nub alone (the host redoes the merge densely)
 __global__ void __launch_bounds__(kRoundsThreads)
-rounds_apply_kernel(LinDev P, RoundsWs W, int rank)
+rounds_apply_kernel(LinDev P, RoundsWs W, int rank, int cap)
 {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  const size_t stride = (size_t)W.xcap + 1;
+  const size_t stride = (size_t)cap + 1;      // messages of this round's capacity tier, back to back
   bool overflow = false;
-  for (int r = 0; r < W.n_ranks; ++r) overflow |= W.xrecv[r * stride].j > (long long)W.xcap;
+  for (int r = 0; r < W.n_ranks; ++r) overflow |= W.xrecv[r * stride].j > (long long)cap;
   if (overflow) { if (tid == 0) W.ctrl[5] = 1; return; }
   for (int r = 0; r < W.n_ranks; ++r) {
     if (r == rank) continue;
@@ -346,15 +346,15 @@ cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count,
   return cudaGetLastError();
 }
 
-cudaError_t launch_rounds_compact(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream)
+cudaError_t launch_rounds_compact(const LinDev &P, const RoundsWs &W, int cap, int sm_count, cudaStream_t stream)
 {
-  rounds_compact_kernel<<<grid_for(P.n, sm_count), kRoundsThreads, 0, stream>>>(P, W);
+  rounds_compact_kernel<<<grid_for(P.n, sm_count), kRoundsThreads, 0, stream>>>(P, W, cap);
   return cudaGetLastError();
 }
 
-cudaError_t launch_rounds_apply(const LinDev &P, const RoundsWs &W, int rank, int sm_count, cudaStream_t stream)
+cudaError_t launch_rounds_apply(const LinDev &P, const RoundsWs &W, int rank, int cap, int sm_count, cudaStream_t stream)
 {
-  rounds_apply_kernel<<<grid_for((long long)W.xcap, sm_count), kRoundsThreads, 0, stream>>>(P, W, rank);
+  rounds_apply_kernel<<<grid_for((long long)cap, sm_count), kRoundsThreads, 0, stream>>>(P, W, rank, cap);
   return cudaGetLastError();
 }
 

@@ -77,6 +77,7 @@ struct mntr_gpu_ctx {
   SingleCtrl *h_single = nullptr;     // pinned, mapped: the fixpoint kernel's last block writes its control block here
   bool ctrl_clean = false;            // the device control block is zero (left so by the previous launch)
   bool force_rounds = false;          // MNTR_GPU_ROUNDS=1: per-round kernels even without a communicator
+  int xcap_small = 0, xcap_first = 0; // sparse bound exchange: small capacity tier; tier of the first round (0: dense)
 
   // ---- NCCL communicator (resolved at run time with dlopen: no link-time dependency) ----
   ncclComm_t comm = nullptr;
@@ -665,17 +666,26 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
       NC(nc.GroupEnd());
       return MNTR_OK;
     };
-    // Few bounds moved in the previous round (every rank saw the same count): exchange only the changed
-    // candidates -- compact, all-gather of fixed-size messages, merge.  A message that does not fit raises
-    // ctrl[5]: the vars kernel then does nothing and the merge is redone densely below.
-    const bool sparse = ctx->comm && W.xcap > 0 && round > 1 && last_changed <= W.xcap / 2;
+    // Exchange only the changed candidates when they are few -- compact, all-gather of fixed-size messages, merge.
+    // Two capacity tiers: the small one (xcap_small entries) after a round that moved few bounds, the large one
+    // (W.xcap) in the first round -- which typically moves a few per cent of the variables -- and after rounds that
+    // moved more; beyond that, or with the exchange switched off, the dense all-reduce.  Every rank saw the same
+    // count, so every rank picks the same tier.  A message that does not fit raises ctrl[5]: the vars kernel then
+    // does nothing and the merge is redone densely below.
+    int cap = 0;
+    if (ctx->comm && W.xcap > 0) {
+      if (round == 1) cap = ctx->xcap_first;
+      else if (last_changed <= ctx->xcap_small / 2) cap = std::min(ctx->xcap_small, W.xcap);
+      else if (last_changed <= W.xcap / 2) cap = W.xcap;
+    }
+    const bool sparse = cap > 0;
     if (ctx->comm) {
       int rc2;
       if (sparse) {
         CU(cudaMemsetAsync(W.xsend, 0, sizeof(BoundMsg), ctx->stream));
-        CU(launch_rounds_compact(P, W, ctx->sm_count, ctx->stream));
-        NC(nc.AllGather(W.xsend, W.xrecv, sizeof(BoundMsg) * ((size_t)W.xcap + 1), ncclChar, ctx->comm, ctx->stream));
-        CU(launch_rounds_apply(P, W, ctx->rank, ctx->sm_count, ctx->stream));
+        CU(launch_rounds_compact(P, W, cap, ctx->sm_count, ctx->stream));
+        NC(nc.AllGather(W.xsend, W.xrecv, sizeof(BoundMsg) * ((size_t)cap + 1), ncclChar, ctx->comm, ctx->stream));
+        CU(launch_rounds_apply(P, W, ctx->rank, cap, ctx->sm_count, ctx->stream));
         ++ctx->stats.sparse_rounds;
       } else if ((rc2 = dense_merge())) return rc2;
     }
@@ -1186,15 +1196,23 @@ int mntr_gpu_comm_init(mntr_gpu_ctx *ctx, int32_t n_ranks, int32_t rank, const v
   memcpy(&id, id128, sizeof(id));
   NC(nc.CommInitRank(&ctx->comm, n_ranks, id, rank));
   ctx->n_ranks = n_ranks; ctx->rank = rank;
-  // buffers of the sparse bound exchange (MNTR_GPU_SPARSE_XCHG=0 switches it off, =<entries> sets the capacity)
+  // buffers of the sparse bound exchange.  MNTR_GPU_SPARSE_XCHG=0 switches it off, =<entries> sets ONE capacity
+  // (small tier only, first round dense), =<small>,<large> both tiers; by default the small tier holds 65536 entries and the large one n/16 (at
+  // most 2M): eight messages of the large tier are a tenth of what the dense all-reduce of 16 bytes per variable moves.
   free_xchg(ctx);
-  int cap = 65536;
-  if (const char *e = getenv("MNTR_GPU_SPARSE_XCHG")) cap = atoi(e);
-  if (cap > 0 && n_ranks > 1) {
-    const size_t msg = sizeof(BoundMsg) * ((size_t)cap + 1);
+  int small = 65536, large = 0, first = 0;
+  if (const char *e = getenv("MNTR_GPU_SPARSE_XCHG")) {       // "<small>" or "<small>,<large>"
+    small = atoi(e); large = small;
+    if (const char *c = strchr(e, ',')) { large = std::max(small, atoi(c + 1)); first = large > small ? large : 0; }
+  }
+  else { large = (int)std::min<int64_t>((int64_t)2 << 20, std::max<int64_t>(small, (int64_t)ctx->n / 16)); first = large > small ? large : 0; }
+  if (small > 0 && n_ranks > 1) {
+    const size_t msg = sizeof(BoundMsg) * ((size_t)large + 1);
     CU(cudaMalloc((void **)&ctx->rws.xsend, msg));
     CU(cudaMalloc((void **)&ctx->rws.xrecv, msg * (size_t)n_ranks));
-    ctx->rws.xcap = cap;
+    ctx->rws.xcap = large;
+    ctx->xcap_small = small;
+    ctx->xcap_first = first;
   }
   ctx->rws.n_ranks = n_ranks;
   return MNTR_OK;

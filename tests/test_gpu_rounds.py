@@ -41,12 +41,13 @@ def _n_devices():
     return E.load_library().mntr_gpu_device_count()
 
 
-@pytest.mark.parametrize("xchg", ["65536", "0", "48"], ids=["sparse", "dense", "tiny-cap"])
+@pytest.mark.parametrize("xchg", ["65536", "0", "48", "48,4000"], ids=["sparse", "dense", "tiny-cap", "two-tiers"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_row_partition_nccl_bitwise_independent_of_ranks(engine, world, xchg, monkeypatch):
     """Row-partitioned mode over NCCL.  The per-round merge is either the dense MAX/MIN all-reduce of the candidate
     bounds or, after a round that moved few bounds, the sparse exchange (changed candidates all-gathered); a capacity of
-    48 entries makes messages overflow, which must fall back to the dense merge.  Same bits in every case."""
+    48 entries makes messages overflow, which must fall back to the dense merge; "48,4000" adds the large tier, which
+    also carries the first round.  Same bits in every case."""
     if _n_devices() < world:
         pytest.skip(f"needs {world} GPUs")
     monkeypatch.setenv("MNTR_GPU_SPARSE_XCHG", xchg)      # read by mntr_gpu_comm_init
@@ -87,7 +88,7 @@ def test_row_partition_nccl_bitwise_independent_of_ranks(engine, world, xchg, mo
                 assert np.array_equal(got.lb, ref[b].lb) and np.array_equal(got.ub, ref[b].ub), (b, rank)
                 assert got.rounds[0] == ref[b].rounds[0]
                 assert got.nnz_updates[0] == ref[b].nnz_updates[0]     # summed over the ranks
-    if xchg == "65536":
+    if xchg in ("65536", "48,4000"):
         assert min(sparse) > 0, "the sparse exchange never ran: the test is vacuous"
     if xchg == "0":
         assert max(sparse) == 0
