@@ -8,10 +8,9 @@
 //                  detection, work list of this rank's rows for the next round
 // Because candidates are merged with exact max/min and everything after the merge is replicated, all
 // ranks finish with bit-identical boxes and the result does not depend on the number of ranks.
-// The row evaluation is the throughput form in linear_row.cuh (sub-warp group per row, registers and shuffles only).
+// The row evaluation is the lane = row streaming form of row_resident.cuh.
 #include "device_problem.cuh"
 #include "kernels.h"
-#include "linear_row.cuh"
 #include "row_resident.cuh"
 
 namespace mntr {
@@ -63,20 +62,19 @@ struct SinkRounds {
 
 // The rows of one phase, in blocks of 32 (one word of the bit set -- the reference's Constraint bFlag): blocks
 // bk = warp, warp + n_warps, ...; the due words of 32 of them are fetched at once (lane l looks at the l-th) and
-// cleared with a fire-and-forget atomic [setBFlag(false), :513].  Blocks with at least kDenseRows due rows (all blocks
-// in the first round) are evaluated lane = row; the due rows of a sparse block are taken 32/G at a time by sub-warp
-// groups of G lanes (process_row of linear_row.cuh).
-template <int G, class R>
+// cleared with a fire-and-forget atomic [setBFlag(false), :513].  Every block with a due row is evaluated lane = row
+// (eval_resident, streaming form), rows longer than 32 entries and the cut-off row by the whole warp (eval_long):
+// how a row's terms are added depends on the row alone -- never on which rows share its block or on how many lanes a
+// rank gives its rows -- so a row yields the same candidates whichever rank owns it, and the merged result is bitwise
+// independent of the partition.  (An earlier version took the due rows of sparse blocks with sub-warp groups and a
+// butterfly sum: the 8-rank run then differed from the 1-rank run in the last bits.)
+template <class R>
 __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W, StreamStage &S, int warp_global, int n_warps,
                                               bool first, unsigned long long &my_nnz, unsigned long long &my_rows)
 {
-  constexpr int GPW = 32 / G;
   const int lane = threadIdx.x & 31;
-  const int lane_g = lane % G, g = lane / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lane_g));
   const ReadPending rd{W.box, P.colx, false};          // the vars kernel stores rounded integer bounds
   const SinkRounds sink{W.nlb, W.nub, P.n};
-  const SinkSplit split{W.nlb, W.nub, P.n};
   const int n_blk = (P.m + 31) / 32;
   for (int it0 = 0; warp_global + (long long)it0 * n_warps < n_blk; it0 += 32) {
     const long long bl = warp_global + (long long)(it0 + lane) * n_warps;
@@ -86,9 +84,7 @@ __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W
       if (P.m - (int)bl * 32 < 32) word &= (1u << (P.m - (int)bl * 32)) - 1u;
       if (!first && word) atomicAnd(W.bits + bl, ~word);
     }
-    const bool dense = first ? word != 0u : __popc(word) >= kDenseRows;
-    unsigned dm = __ballot_sync(kFullMask, dense);
-    unsigned sm = __ballot_sync(kFullMask, word != 0u && !dense);
+    unsigned dm = __ballot_sync(kFullMask, word != 0u);
     while (dm) {
       const int k = __ffs(dm) - 1;
       dm &= dm - 1;
@@ -102,29 +98,14 @@ __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W
       stage_block(P, S, lane, is_due, h, gcol, gval);
       eval_resident<R>(P, rd, sink, S, lane, is_due, h, false, gcol, gval);
     }
-    while (sm) {
-      const int k = __ffs(sm) - 1;
-      sm &= sm - 1;
-      const unsigned wk = __shfl_sync(kFullMask, word, k);
-      const int base = (warp_global + (it0 + k) * n_warps) * 32, nd = __popc(wk);
-      for (int x0 = 0; x0 < nd; x0 += GPW) {
-        const int x = x0 + g;
-        if (x >= nd) continue;                                        // group-uniform
-        const int i = base + (int)__fns(wk, 0, x + 1);
-        const int2 info = __ldg(P.row_info + i);
-        if (info.y < 0) continue;
-        process_row<G, R>(P, W.box, W.ctrl, split, i, info.x, info.y, lane_g, gmask, my_nnz, my_rows);
-      }
-      __syncwarp();
-    }
   }
   drain_queue<R>(P, rd, sink, S, lane);
   // the objective cut-off row is evaluated in every round (the reference loops it to its own fixpoint in every
-  // sweep, LinearHandler.cpp:1636-1640); one group takes it
-  if (P.cut_cnt > 0 && warp_global == 0 && g == 0) {
-    LinDev C = P;
-    C.col = P.cut_col; C.val = P.cut_val; C.row_bnd = P.cut_bnd;
-    process_row<G, R>(C, W.box, W.ctrl, split, 0, 0, P.cut_cnt, lane_g, gmask, my_nnz, my_rows);
+  // sweep, LinearHandler.cpp:1636-1640); one warp takes it
+  if (P.cut_cnt > 0 && warp_global == 0) {
+    const ReadPending rdc{W.box, P.cut_colx, false};
+    eval_long<R>(P.cut_val, rdc, sink, S, lane, 0, P.cut_cnt, -INFINITY, P.cut_rhs);
+    if (lane == 0) { my_nnz += (unsigned long long)P.cut_cnt; ++my_rows; }
   }
 }
 
@@ -147,7 +128,7 @@ __global__ void rounds_init_kernel(LinDev P, RoundsWs W, const double *lb_io, co
   if (bad) W.ctrl[3] = 1 /* MNTR_INFEAS_BOUNDS */;
 }
 
-template <int G, class R>
+template <class R>
 __global__ void __launch_bounds__(kRoundsThreads, 4)
 rounds_rows_kernel(LinDev P, RoundsWs W, int first)
 {
@@ -158,7 +139,7 @@ rounds_rows_kernel(LinDev P, RoundsWs W, int first)
   StreamStage &S = reinterpret_cast<StreamStage *>(smem_raw)[threadIdx.x >> 5];
   if (lane == 0) { S.tcount = 0; S.pad_[0] = 0; S.pad_[1] = 0; }
   __syncwarp();
-  rows_of_phase<G, R>(P, W, S, tid >> 5, nthreads >> 5, first != 0, my_nnz, my_rows);
+  rows_of_phase<R>(P, W, S, tid >> 5, nthreads >> 5, first != 0, my_nnz, my_rows);
   __shared__ unsigned long long s_nnz, s_rows;
   if (threadIdx.x == 0) { s_nnz = 0ull; s_rows = 0ull; }
   __syncthreads();
@@ -304,24 +285,16 @@ int grid_for(long long items, int sm_count)
 }
 
 template <class R>
-cudaError_t rows_r(int G, const LinDev &P, const RoundsWs &W, int first, int sm_count, cudaStream_t s)
+cudaError_t rows_r(const LinDev &P, const RoundsWs &W, int first, int sm_count, cudaStream_t s)
 {
-  if (P.m <= 0) return cudaSuccess;
-  const int blocks = grid_for((long long)P.m * G, sm_count);
+  if (P.m <= 0 && P.cut_cnt <= 0) return cudaSuccess;
+  const int blocks = grid_for((long long)((P.m + 31) / 32) * 32, sm_count);      // one warp per 32-row block
   const size_t smem = sizeof(StreamStage) * (kRoundsThreads / 32);
-  auto launch = [&](auto kern) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<blocks, kRoundsThreads, smem, s>>>(P, W, first);
-    return cudaGetLastError();
-  };
-  switch (G) {
-  case 2:  return launch(rounds_rows_kernel<2, R>);
-  case 4:  return launch(rounds_rows_kernel<4, R>);
-  case 8:  return launch(rounds_rows_kernel<8, R>);
-  case 16: return launch(rounds_rows_kernel<16, R>);
-  default: return launch(rounds_rows_kernel<32, R>);
-  }
+  auto kern = rounds_rows_kernel<R>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<blocks, kRoundsThreads, smem, s>>>(P, W, first);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -336,8 +309,9 @@ cudaError_t launch_rounds_init(const LinDev &P, const RoundsWs &W, const double 
 cudaError_t launch_rounds_rows(const LinDev &P, const RoundsWs &W, int lanes_per_row, bool directed,
                                int first, int sm_count, cudaStream_t stream)
 {
-  if (directed) return rows_r<RoundDirected>(lanes_per_row, P, W, first, sm_count, stream);
-  return rows_r<RoundNearest>(lanes_per_row, P, W, first, sm_count, stream);
+  (void)lanes_per_row;      // (rows are evaluated lane = row; kept in the signature for the callers)
+  if (directed) return rows_r<RoundDirected>(P, W, first, sm_count, stream);
+  return rows_r<RoundNearest>(P, W, first, sm_count, stream);
 }
 
 cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream)

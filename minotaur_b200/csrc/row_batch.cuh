@@ -15,7 +15,7 @@
 //
 // This is the LATENCY form, used by the single-launch fixpoint kernel (linear_single.cu): one staged batch per warp
 // per round, every load of the batch in flight at once.  The per-round kernels of the row-partitioned multi-GPU path
-// stream hundreds of rows per warp and use the register-only throughput form (linear_row.cuh).  How the box is read
+// stream hundreds of rows per warp and use the lane = row streaming form (row_resident.cuh).  How the box is read
 // (Reader) and where candidates go (Sink) are policies.
 #pragma once
 #include "device_problem.cuh"
