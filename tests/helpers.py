@@ -53,3 +53,31 @@ def never_tighter(got_lb, got_ub, ref_lb, ref_ub, rel_tol=REL_TOL):
         ok_l = (got_lb <= ref_lb + sl) | (got_lb == ref_lb)
         ok_u = (got_ub >= ref_ub - su) | (got_ub == ref_ub)
     return bool(np.all(ok_l) and np.all(ok_u))
+
+
+def ragged_rows(inst, seed, max_keep=None):
+    """A copy of a uniform-row instance (k entries per row) whose rows keep a random number 0..max_keep of their
+    entries (in column order), row bounds rebuilt around the planted point: ragged blocks for the row kernels."""
+    import copy
+    rng = np.random.default_rng(seed)
+    m = inst.m
+    k = inst.nnz // m
+    assert inst.nnz == m * k and inst.xstar is not None
+    keep = rng.integers(0, (max_keep or k) + 1, size=m)
+    # a few long rows next to many short ones
+    keep = np.where(rng.random(m) < 0.85, np.minimum(keep, rng.integers(0, 14, size=m)), keep)
+    mask = np.arange(k)[None, :] < keep[:, None]
+    col = inst.col.reshape(m, k)[mask].astype(np.int32)
+    val = inst.val.reshape(m, k)[mask]
+    row_ptr = np.concatenate([[0], np.cumsum(keep)]).astype(np.int32)
+    act = np.add.reduceat(np.concatenate([val * inst.xstar[col], [0.0]]), np.minimum(row_ptr[:-1], len(col)))[:m]
+    act = np.where(keep > 0, act, 0.0)
+    is_eq = inst.row_lb == inst.row_ub
+    slack = rng.integers(0, 4, size=m).astype(np.float64)
+    out = copy.copy(inst)
+    out.row_ptr, out.col, out.val = row_ptr, col, val
+    out.row_ub = np.where(is_eq, act, act + slack)
+    out.row_lb = np.where(is_eq, act, -np.inf)
+    out.name = inst.name + "-ragged"
+    out.validate()
+    return out
