@@ -44,6 +44,17 @@ def _n_devices():
 @pytest.mark.parametrize("xchg", [None, "0", "48"], ids=["sparse", "dense", "tiny-cap"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_row_partition_nccl_bitwise_independent_of_ranks(engine, world, xchg, monkeypatch):
+    _nccl_partition_case(engine, world, xchg, monkeypatch, ragged=False)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_row_partition_nccl_ragged_rows(engine, world, monkeypatch):
+    """The same with rows of 0..40 entries mixed in every block (short rows, tails beyond the 12 staged entries, rows
+    longer than a lane takes): whichever rank owns a row, and whatever shares its block, its candidates are the same."""
+    _nccl_partition_case(engine, world, None, monkeypatch, ragged=True)
+
+
+def _nccl_partition_case(engine, world, xchg, monkeypatch, ragged):
     """Row-partitioned mode over NCCL.  The per-round merge is the sparse exchange (changed candidates compacted, their
     counts all-gathered and read by the host, then right-sized messages all-gathered and merged with max / min) or,
     when the messages would not fit or not pay, the dense MAX/MIN all-reduce of the candidate bounds: "0" forces the
@@ -54,7 +65,11 @@ def test_row_partition_nccl_bitwise_independent_of_ranks(engine, world, xchg, mo
         monkeypatch.delenv("MNTR_GPU_SPARSE_XCHG", raising=False)
     else:
         monkeypatch.setenv("MNTR_GPU_SPARSE_XCHG", xchg)      # read by mntr_gpu_comm_init
-    inst = make_sparse_milp(20_000, 15_000, 9, seed=77, real_data=True, inf_frac=(0.02, 0.02, 0.0))
+    if ragged:
+        from helpers import ragged_rows
+        inst = ragged_rows(make_sparse_milp(20_000, 15_000, 40, seed=78, real_data=True), 78)
+    else:
+        inst = make_sparse_milp(20_000, 15_000, 9, seed=77, real_data=True, inf_frac=(0.02, 0.02, 0.0))
     engine.load_linear(inst)
     lbs, ubs = branch_boxes(inst.lb, inst.ub, inst.var_type, 3, seed=5, max_depth=10)
     lbs[0], ubs[0] = inst.lb, inst.ub
