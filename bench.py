@@ -1,23 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- FBBT throughput of the B200 engine on BASELINE.json's configurations.
 
-Headline workload (N=1): config C2 -- synthetic sparse MILP 100k rows x 100k cols, 1M nnz, a single
-box tightened to the fixpoint.  A "step" is one whole fixpoint call (all rounds) on the root box.
+One JSON line.  Its top-level keys are the headline; `configs` holds one block per BASELINE configuration, each
+measured at BASELINE size with its own `roofline`, `cpu_baseline`, `e2e` and an in-run `parity` verdict:
 
-  value  : nnz-updates/s with the box already resident in HBM (mntr_gpu_tighten_single_dev; CUDA events
-           on the engine's stream around the kernel; L2 flushed between steps)
-  e2e    : the same metric through the reference-facing C-ABI call mntr_gpu_tighten with PINNED HOST
-           buffers: host->device copy of the box, kernel, device->host copy of the result, per step
-  roofline: algorithmic HBM bytes of the fixpoint launch (SURVEY.md 8d formula) / launch duration,
-           against the measured copy bandwidth in MEASURED_PEAKS.json
-  cpu_baseline: the reference's own LinearHandler sweeps (oracle/_ref, built from /root/reference) or,
-           if that library is absent, the plain-C oracle port, timed on this host's cores
+  C1  tls4.nl (the reference's own CPU-runnable case): the flattened instance of tests/golden/tls4_cases.npz, node
+      presolve of the root box and 11 branched boxes, bit for bit against the reference's handlers' outputs
+  C2  synthetic sparse MILP 100k x 100k, 1M nnz, ONE box to the fixpoint (K1, one cooperative launch)
+  C3  8192 B&B node boxes on the 50k-row knapsack/set-cover instance (K3), sharded by node over the ranks
+  C4  20M x 20M, 200M nnz at 8 ranks (2.5M rows per rank otherwise), row-partitioned, per-round bound merge (K5)
+  C5  1M bilinear/quadratic CGraph constraints + 100k linear rows, 4096 node boxes (K3 + K4), sharded by node
 
-N>1 (torchrun): every rank tightens its own copy of the C2 instance (independent replicas, weak scaling, no
-data-path collective); value = total nnz-updates / max-over-ranks time.  `extra.node_batch` reports the
-C3-shaped node batch (8192 boxes sharded by node across the ranks).
+Headline: N = 1 -> C2 (the configuration the metric is quoted on, a single box: `scaling` "weak" is moot);
+N > 1 -> the C3 node batch sharded by node over the ranks, no collective in the data path (`scaling` "strong"; the
+block also carries the time of the whole batch on ONE GPU measured in the same run, `ms_1gpu_same_run`).
 
-`--impl reference` times the reference's CPU implementation on the same config.
+  value   : nnz-updates/s, inputs resident in HBM, CUDA events on the engine's stream, max over ranks
+  e2e     : the same metric through the reference-facing C-ABI call with HOST buffers (mntr_gpu_tighten for a single
+            box, mntr_gpu_tighten_nodes -- deltas in, VarBoundMod tuples out -- for a node batch)
+  roofline: algorithmic HBM bytes / launch duration against MEASURED_PEAKS.json
+  cpu_baseline: the reference's own LinearHandler / NlPresHandler (oracle/_ref, built from /root/reference) on this
+            host, both as the status-honouring fixpoint and as one raw simplePresolve (what B&B pays per node), 1 core
+            and -- for the node batches -- all cores (one Problem clone per thread)
+  parity  : computed in this run against oracle/ (the CHECKER; never on the timed path)
+
+`--impl reference` times the reference's CPU implementation on the headline configuration.
 """
 import argparse
 import json
@@ -34,8 +41,23 @@ sys.path.insert(0, ROOT)
 
 C2 = dict(m=100_000, n=100_000, nnz_per_row=10, seed=12345)
 C3 = dict(m=50_000, n=50_000, nnz_per_row=10, seed=2024)
+C3_BOXES, C3_DEPTH = 8192, 20
+C4_ROWS_PER_RANK, C4_SEED = 2_500_000, 777
+C5 = dict(n=1_000_000, n_cons=1_000_000, m_lin=100_000, seed=99)
+C5_BOXES, C5_DEPTH = 4096, 10
 METRIC = "fbbt_nnz_updates_per_sec"
 UNIT = "nnz-updates/s"
+WORKLOAD_C2 = "C2: synthetic sparse MILP 100k x 100k, 1M nnz, single box to fixpoint"
+WORKLOAD_C3 = "C3: 8192 B&B node boxes on the 50k-row knapsack/set-cover instance, reference-order sweeps to fixpoint"
+
+
+def headline_config(world):
+    """The `config` dict of the headline: identical in the repo arm and the reference arm."""
+    if world == 1:
+        return {"workload": WORKLOAD_C2, "seed": C2["seed"], "rounding": "directed", "order": "jacobi",
+                "l2": "flushed between steps (256 MB write)", "parallelism": "single GPU"}
+    return {"workload": WORKLOAD_C3, "seed": C3["seed"], "rounding": "directed", "order": "reference (wavefront levels)",
+            "l2": "inputs larger than L2 (6.5 GB of boxes)", "parallelism": f"node batch sharded over {world} GPUs"}
 
 
 def measured_hbm_peak():
@@ -46,6 +68,16 @@ def measured_hbm_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def static_traffic(key):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json) -- NOT measured in this run."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(tpath))
+        return t.get(key), t.get(key + "_source", "profiles/traffic.json")
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -94,18 +126,130 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline_c2(inst, budget_s=12.0):
-    """The reference's CPU FBBT on the same instance/box, on this host (1 core: the path is sequential)."""
+# ------------------------------------------------------------------------------------------------------------------
+# parity helpers (the oracle is the CHECKER: nothing here is on a timed GPU path)
+# ------------------------------------------------------------------------------------------------------------------
+
+def _canon_int(x):
+    r = np.round(x)
+    with np.errstate(invalid="ignore"):
+        return np.where(np.isfinite(x) & (np.abs(x - r) <= 1e-6), r, x)
+
+
+def box_parity(var_type, got_lb, got_ub, ref_lb, ref_ub, rel_tol=1e-9):
+    """north star: integer-variable bounds bit-exact (after the 1e-6 canonicalisation of SURVEY.md 7, hard part 2),
+    continuous within rel_tol and never tighter than the reference beyond it.  Returns (ok, worst relative diff)."""
+    isint = var_type <= 1
+    ok = np.array_equal(_canon_int(got_lb[isint]), _canon_int(ref_lb[isint])) and \
+        np.array_equal(_canon_int(got_ub[isint]), _canon_int(ref_ub[isint]))
+    c = ~isint
+    worst = 0.0
+    for g, r, sign in ((got_lb[c], ref_lb[c], 1.0), (got_ub[c], ref_ub[c], -1.0)):
+        with np.errstate(invalid="ignore"):
+            d = np.abs(g - r) / np.maximum(1.0, np.maximum(np.abs(g), np.abs(r)))
+            d = np.nan_to_num(np.where(g == r, 0.0, d), nan=np.inf)
+            tighter = sign * (g - r) > rel_tol * np.maximum(1.0, np.abs(r))
+        worst = max(worst, float(d.max(initial=0.0)))
+        ok = ok and not bool(np.any(tighter & (g != r)))
+    return bool(ok and worst <= rel_tol), worst
+
+
+def mods_to_box(lb0, ub0, var, up, val):
+    lb, ub = lb0.copy(), ub0.copy()
+    u = up.astype(bool)
+    ub[var[u]] = val[u]
+    lb[var[~u]] = val[~u]
+    return lb, ub
+
+
+def sample_boxes(total, k, seed):
+    rng = np.random.default_rng(seed)
+    k = min(k, total)
+    return np.sort(rng.choice(total, size=k, replace=False))
+
+
+def take_deltas(deltas, idx):
+    """The boxes `idx` of a delta batch as a batch of their own."""
+    ptr, var, up, val = deltas
+    cnt = (ptr[idx + 1] - ptr[idx]).astype(np.int64)
+    nptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    sel = np.concatenate([np.arange(ptr[b], ptr[b + 1]) for b in idx]) if len(idx) else np.zeros(0, np.int64)
+    sel = sel.astype(np.int64)
+    return nptr, var[sel], up[sel], val[sel]
+
+
+def batch_parity(E, eng, orc, inst, tapes, deltas, idx, mode, loop, threads):
+    """Sampled boxes `idx` of a node batch: the CUDA path in ROUND_NEAREST / reference order (the same kernel template
+    as the timed run, other rounding policy) must equal the oracle's in-place sweeps BIT FOR BIT -- verdicts, and for
+    feasible boxes every bound change.  Returns (record, oracle result) -- the oracle's all-core time doubles as the
+    'port' CPU baseline."""
+    sub = take_deltas(deltas, idx)
+    cap = 1 << 14
+    o = orc.batch_deltas(inst, tapes, mode, inst.lb, inst.ub, sub, n_threads=threads, mod_cap=cap)
+    v, r, mp, mv, mu, mx, total = eng.tighten_nodes(inst.lb, inst.ub, *sub, rounding=E.ROUND_NEAREST, loop=loop)
+    n_ok = n_cmp = n_skip = 0
+    for k in range(len(idx)):
+        if mode != 0 and v[k] == E.INFEAS_ROW:
+            n_skip += 1          # documented deviation 1: the reference's node mode drops this status (LinearHandler.cpp:1631)
+            continue
+        n_cmp += 1
+        same = (v[k] != 0) == (o["verdict"][k] != 0)
+        if same and v[k] == 0:
+            c = int(o["mod_cnt"][k])
+            a, b = int(mp[k]), int(mp[k + 1])
+            same = c <= cap and (b - a) == c and np.array_equal(mv[a:b], o["mod_var"][k, :c]) and \
+                np.array_equal(mu[a:b], o["mod_up"][k, :c]) and np.array_equal(mx[a:b], o["mod_val"][k, :c])
+        n_ok += bool(same)
+    rec = {"ok": bool(n_ok == n_cmp and n_cmp > 0), "boxes_compared": n_cmp, "boxes_equal": n_ok,
+           "skipped_row_infeasible": n_skip,
+           "criterion": "bitwise (verdict + every bound change) vs oracle in-place sweeps, ROUND_NEAREST / reference order"}
+    return rec, o
+
+
+def directed_parity(E, inst, deltas, idx, gpu, orc_res):
+    """The timed (directed-rounding) results of the sampled boxes against the oracle's: north-star tolerance."""
+    v, mp, mv, mu, mx = gpu
+    n_ok = n_cmp = 0
+    worst = 0.0
+    from minotaur_b200.instances import deltas_box
+    for k, b in enumerate(idx):
+        if v[b] != 0 or orc_res["verdict"][k] != 0:
+            continue
+        lb0, ub0 = deltas_box(inst.lb, inst.ub, deltas, int(b))
+        a, e = int(mp[b]), int(mp[b + 1])
+        gl, gu = mods_to_box(lb0, ub0, mv[a:e], mu[a:e], mx[a:e])
+        c = int(orc_res["mod_cnt"][k])
+        ol, ou = mods_to_box(lb0, ub0, orc_res["mod_var"][k, :c], orc_res["mod_up"][k, :c], orc_res["mod_val"][k, :c])
+        ok, w = box_parity(inst.var_type, gl, gu, ol, ou)
+        n_cmp += 1; n_ok += ok; worst = max(worst, w)
+    return {"boxes_compared": n_cmp, "boxes_within_tolerance": n_ok, "worst_rel_diff": worst,
+            "criterion": "directed rounding (timed run): integer bounds exact, continuous <= 1e-9 rel and never tighter"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baselines (rank 0, N = 1 only)
+# ------------------------------------------------------------------------------------------------------------------
+
+def cpu_single_box(inst, budget_s=8.0):
+    """The reference's LinearHandler on one box, one core (the path is sequential): (1) the status-honouring fixpoint
+    of SURVEY.md 8c, (2) one raw simplePresolve call (LinearHandler.cpp:1605-1653)."""
     from oracle import pyoracle
+    out = {"unit": UNIT, "cores": 1, "host_cores_available": os.cpu_count()}
     if pyoracle.have_reference():
         ref = pyoracle.Reference(inst)
-        secs, nnz, reps = 0.0, 0, 0
-        while secs < budget_s and reps < 40:
-            s, z, _ = ref.time_boxes(0, inst.lb[None, :], inst.ub[None, :])
-            secs += s; nnz += z; reps += 1
+        recs = {}
+        for mode, name in ((0, "fixpoint"), (1, "simple_presolve")):
+            secs, nnz, reps = 0.0, 0, 0
+            while secs < budget_s / 2 and reps < 40:
+                s, z, _ = ref.time_boxes(mode, inst.lb[None, :], inst.ub[None, :])
+                secs += s; nnz += z; reps += 1
+            recs[name] = (secs / reps, nnz / reps, reps)
         ref.close()
-        kind = "reference"
-        sample = f"{reps} x status-honouring fixpoint of the reference's LinearHandler sweeps on the C2 root box"
+        fix_s, fix_nnz, reps = recs["fixpoint"]
+        out.update(kind="reference", value=fix_nnz / fix_s, ms_per_call_fixpoint=1e3 * fix_s,
+                   ms_per_call_simple_presolve=1e3 * recs["simple_presolve"][0],
+                   sample=f"{reps} x status-honouring fixpoint + {recs['simple_presolve'][2]} x raw "
+                          "LinearHandler::simplePresolve of the reference on the root box")
     else:
         orc = pyoracle.Oracle()
         secs, nnz, reps = 0.0, 0, 0
@@ -113,46 +257,135 @@ def cpu_baseline_c2(inst, budget_s=12.0):
             t0 = time.perf_counter()
             _, _, r = orc.lin_fixpoint_inplace(inst, inst.lb, inst.ub)
             secs += time.perf_counter() - t0; nnz += r["nnz_updates"]; reps += 1
-        kind = "port"
-        sample = f"{reps} x in-place fixpoint of the C oracle on the C2 root box"
-    return {"value": nnz / secs, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
-            "host_cores_available": os.cpu_count()}, secs / reps
+        out.update(kind="port", value=nnz / secs, ms_per_call_fixpoint=1e3 * secs / reps,
+                   sample=f"{reps} x in-place fixpoint of the C oracle on the root box")
+    return out
 
+
+def cpu_node_batch(inst, tapes, deltas, modes, n_one, n_all, port=None):
+    """Reference handlers on sampled node boxes: one core, then all cores (one Problem clone per thread, boxes dealt
+    round-robin -- SURVEY.md 8d).  modes: list of (ref_time_boxes mode, name)."""
+    from oracle import pyoracle
+    from minotaur_b200.instances import slice_deltas
+    cores = os.cpu_count() or 1
+    out = {"unit": "boxes/s", "host_cores_available": cores}
+    if port is not None:
+        out["port_all_cores"] = port
+    if not pyoracle.have_reference():
+        out.update(kind="port", cores=port["cores"], value=port["boxes_per_s"], sample=port["sample"])
+        return out
+    t0 = time.perf_counter()
+    ref = pyoracle.Reference(inst, tapes)
+    build_s = time.perf_counter() - t0
+    one = {}
+    for mode, name in modes:
+        s, z, ninf = ref.time_deltas(mode, inst.lb, inst.ub, slice_deltas(deltas, 0, n_one))
+        one[name] = {"boxes_per_s": n_one / s, "ms_per_box": 1e3 * s / n_one, "nnz_updates_per_s": (z / s) if z else None}
+    out["one_core"] = one
+    out["reference_build_s"] = build_s
+    first = modes[0][1]
+    if n_all > 0 and cores > 1 and build_s * cores < 120:
+        clones = [ref] + [pyoracle.Reference(inst, tapes) for _ in range(cores - 1)]
+        per = max(1, n_all // cores)
+        res = [None] * cores
+
+        def work(k):
+            res[k] = clones[k].time_deltas(modes[0][0], inst.lb, inst.ub, slice_deltas(deltas, n_one + k * per, n_one + (k + 1) * per))
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(k,)) for k in range(cores)]
+        [t.start() for t in th]; [t.join() for t in th]
+        wall = time.perf_counter() - t0
+        for c in clones:
+            c.close()
+        out.update(kind="reference", cores=cores, value=per * cores / wall,
+                   sample=f"{per * cores} boxes dealt to {cores} threads (one Problem clone each), {first}; one-core figures "
+                          f"on {n_one} boxes")
+    else:
+        ref.close()
+        out.update(kind="reference", cores=1, value=one[first]["boxes_per_s"], sample=f"{n_one} boxes, {first}, one core")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------------------------
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    from minotaur_b200.instances import make_sparse_milp
     from oracle import pyoracle
-    inst = make_sparse_milp(**C2)
     have = pyoracle.have_reference()
-    if have:
-        ref = pyoracle.Reference(inst)
-        def step():
-            s, z, _ = ref.time_boxes(0, inst.lb[None, :], inst.ub[None, :])
-            return s, z
+    kind = "reference" if have else "port"
+    if world == 1:
+        from minotaur_b200.instances import make_sparse_milp
+        inst = make_sparse_milp(**C2)
+        if have:
+            ref = pyoracle.Reference(inst)
+            def step():
+                s, z, _ = ref.time_boxes(0, inst.lb[None, :], inst.ub[None, :])
+                return s, z
+        else:
+            orc = pyoracle.Oracle()
+            def step():
+                t0 = time.perf_counter()
+                _, _, r = orc.lin_fixpoint_inplace(inst, inst.lb, inst.ub)
+                return time.perf_counter() - t0, r["nnz_updates"]
+        cores = 1
+        sample = "one status-honouring fixpoint of the reference's LinearHandler sweeps on the C2 root box per step (1 core: the path is sequential)"
     else:
-        orc = pyoracle.Oracle()
-        def step():
-            t0 = time.perf_counter()
-            _, _, r = orc.lin_fixpoint_inplace(inst, inst.lb, inst.ub)
-            return time.perf_counter() - t0, r["nnz_updates"]
+        # the C3 node batch: every step tightens a bounded sample of the 8192 boxes on all host cores
+        from minotaur_b200.instances import branch_deltas, make_knapsack_setcover, slice_deltas
+        inst = make_knapsack_setcover(**C3)
+        deltas = branch_deltas(inst.lb, inst.ub, inst.var_type, C3_BOXES, seed=C3["seed"], max_depth=C3_DEPTH)
+        cores = os.cpu_count() or 1
+        per = 4
+        if have:
+            clones = [pyoracle.Reference(inst) for _ in range(cores)]
+            state = {"at": 0}
+            def step():
+                res = [None] * cores
+                base = state["at"]
+                def work(k):
+                    b0 = (base + k * per) % (C3_BOXES - per)
+                    res[k] = clones[k].time_deltas(0, inst.lb, inst.ub, slice_deltas(deltas, b0, b0 + per))
+                t0 = time.perf_counter()
+                th = [threading.Thread(target=work, args=(k,)) for k in range(cores)]
+                [t.start() for t in th]; [t.join() for t in th]
+                state["at"] += cores * per
+                return time.perf_counter() - t0, sum(r[1] for r in res)
+        else:
+            orc = pyoracle.Oracle()
+            state = {"at": 0}
+            def step():
+                b0 = state["at"] % (C3_BOXES - cores * per)
+                r = orc.batch_deltas(inst, None, 0, inst.lb, inst.ub, slice_deltas(deltas, b0, b0 + cores * per), n_threads=cores)
+                state["at"] += cores * per
+                return r["secs"], int(r["nnz"].sum())
+        sample = (f"{cores * per} of the 8192 C3 boxes per step, status-honouring fixpoint of the reference's LinearHandler sweeps, "
+                  f"{cores} threads (one Problem clone each)")
     for _ in range(args.warmup):
         step()
     secs, nnz = 0.0, 0
     for _ in range(args.steps):
         s, z = step(); secs += s; nnz += z
     val = nnz / secs
-    kind = "reference" if have else "port"
-    sample = "one status-honouring fixpoint of the reference's LinearHandler sweeps on the C2 root box per step"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: synthetic sparse MILP 100k x 100k, 1M nnz, single box to fixpoint", "seed": C2["seed"]},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak" if world == 1 else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": headline_config(world),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the repo arm
+# ------------------------------------------------------------------------------------------------------------------
+
+class Ctx:
+    """what every block needs"""
+    pass
 
 
 def main():
@@ -161,13 +394,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-extra", action="store_true", help="skip the C3 node-batch extra measurement")
+    ap.add_argument("--only", default="", help="comma-separated subset of blocks: C1,C2,C3,C4,C5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch-boxes", type=int, default=8192)
-    ap.add_argument("--profile", action="store_true", help="short run for ncu: no sustained pre-load loop")
-    ap.add_argument("--c4-rows-per-rank", type=int, default=2_500_000)
-    ap.add_argument("--c5-cons", type=int, default=200_000)
-    ap.add_argument("--c5-boxes", type=int, default=1024)
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle checks (profiling runs)")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: no sustained pre-load loop, one repetition")
+    ap.add_argument("--c3-boxes", type=int, default=C3_BOXES)
+    ap.add_argument("--c4-rows-per-rank", type=int, default=C4_ROWS_PER_RANK)
+    ap.add_argument("--c4-cpu-rows", type=int, default=2_000_000, help="rows of the 1/10-scale C4 CPU baseline")
+    ap.add_argument("--c5-cons", type=int, default=C5["n_cons"])
+    ap.add_argument("--c5-boxes", type=int, default=C5_BOXES)
+    ap.add_argument("--parity-boxes", type=int, default=256)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -182,7 +418,6 @@ def main():
     import torch
     import torch.distributed as dist
     from minotaur_b200 import engine as E
-    from minotaur_b200.instances import branch_boxes, make_knapsack_setcover, make_sparse_milp
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
@@ -191,31 +426,80 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    X = Ctx()
+    X.args, X.rank, X.world, X.dev, X.E, X.torch, X.dist = args, rank, world, dev, E, torch, dist
+    X.cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    X.parity = not args.no_parity
+    X.peak, X.peak_src = measured_hbm_peak()
+    X.launches = 0
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
+    X.barrier = barrier
+    X.max_over_ranks = lambda x: reduce(x, dist.ReduceOp.MAX)
+    X.sum_over_ranks = lambda x: reduce(x, dist.ReduceOp.SUM)
+    X.min_over_ranks = lambda x: reduce(x, dist.ReduceOp.MIN)
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    only = [s.strip().upper() for s in args.only.split(",") if s.strip()]
+    want = lambda name: not only or name in only
 
-    # ---------------- workload C2 (one replica per rank) ----------------
-    # every rank tightens its own copy of the SAME instance (replicas): per-GPU work is identical, so the job's value
-    # over N measures the machine, not the spread of round counts over differently seeded instances
-    cfg = dict(C2)
-    inst = make_sparse_milp(**cfg)
-    eng = E.GpuBoundEngine(local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_all = time.perf_counter()
+    blocks = {}
+    for name, fn in (("C2", block_c2), ("C3", block_c3), ("C1", block_c1), ("C4", block_c4), ("C5", block_c5)):
+        if not want(name):
+            continue
+        t0 = time.perf_counter()
+        try:
+            blocks[name] = fn(X)
+        except Exception as ex:   # a failing block must not take the other measurements down; it is reported as failed
+            import traceback
+            blocks[name] = {"error": repr(ex)[:400], "trace": traceback.format_exc()[-800:]}
+        if isinstance(blocks[name], dict):
+            blocks[name]["block_wall_s"] = round(time.perf_counter() - t0, 2)
+        barrier()
+        torch.cuda.empty_cache()
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        head = blocks.get("C2") if world == 1 else blocks.get("C3")
+        if head is None or "error" in head:
+            head = next((b for b in blocks.values() if b and "error" not in b), {"error": "no block ran"})
+        out = {
+            "metric": METRIC, "value": head.get("value"), "unit": UNIT, "n_gpus": world, "steps": head.get("steps", args.steps),
+            "warmup": head.get("warmup", args.warmup), "ms_per_step": head.get("ms_per_step"), "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": headline_config(world), "e2e": head.get("e2e"), "gpu_launches": head.get("gpu_launches"),
+            "roofline": head.get("roofline"), "clocks": clocks, "parity": head.get("parity"),
+            "configs": blocks, "wall_s": round(time.perf_counter() - t_all, 1),
+        }
+        if head.get("cpu_baseline") is not None:
+            out["cpu_baseline"] = head["cpu_baseline"]
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------- C2 ----------------------------------------------
+
+def block_c2(X):
+    """Single box to the fixpoint (K1).  N > 1: every rank tightens its own copy (replicas; the block is the same
+    measurement on every GPU, reported for rank-count 1 only in `value_per_gpu`)."""
+    from minotaur_b200.instances import make_sparse_milp
+    args, E, torch, dev = X.args, X.E, X.torch, X.dev
+    inst = make_sparse_milp(**C2)
+    eng = E.GpuBoundEngine(dev.index)
     eng.load_linear(inst)
     n = inst.n
     stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
@@ -232,190 +516,299 @@ def main():
         st = eng.stats()
         return st.kernel_ms, z, r, v, st
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     # sustained pre-load so the clock samples are taken under load, then the warm-up steps
     t_end = time.perf_counter() + (0.0 if args.profile else 1.5)
     while time.perf_counter() < t_end:
         dev_step()
     for _ in range(args.warmup):
         dev_step()
-    barrier()
-    t0 = time.perf_counter()
-    ker_ms, nnz_tot, st_last = 0.0, 0, None
+    X.barrier()
+    ker_ms, nnz_tot, st_last, rounds = 0.0, 0, None, 0
     for _ in range(args.steps):
         ms, z, r, v, st = dev_step()
-        ker_ms += ms; nnz_tot += z; st_last = st
+        ker_ms += ms; nnz_tot += z; st_last = st; rounds = r
         assert v == 0, "C2 root box must be feasible"
-    barrier()
-    wall_s = time.perf_counter() - t0
-    ker_ms_max = max_over_ranks(ker_ms)
-    nnz_all = sum_over_ranks(float(nnz_tot))
+    X.barrier()
+    ker_ms_max = X.max_over_ranks(ker_ms)
+    nnz_all = X.sum_over_ranks(float(nnz_tot))
     value = nnz_all / (ker_ms_max * 1e-3)
+    got_lb, got_ub = w_lb.cpu().numpy(), w_ub.cpu().numpy()
 
-    # ---------------- e2e: C-ABI call with pinned host buffers ----------------
-    h_lb = torch.empty(n, dtype=torch.float64).pin_memory(); h_ub = torch.empty(n, dtype=torch.float64).pin_memory()
+    # e2e: the C-ABI call with pinned host buffers (mntr_gpu_alloc_host, as the Minotaur-side handler holds its bounds)
+    h_lb = eng.alloc_host(n); h_ub = eng.alloc_host(n)
     opts = E.GpuOptions(E.ROUND_DIRECTED, E.ORDER_JACOBI, E.LOOP_FIXPOINT, 0, E.HANDLERS_ALL)
     vbuf = np.zeros(1, np.int32); rbuf = np.zeros(1, np.int32); zbuf = np.zeros(1, np.int64)
-    root_l_h, root_u_h = torch.from_numpy(inst.lb), torch.from_numpy(inst.ub)
 
     def e2e_step():
-        h_lb.copy_(root_l_h); h_ub.copy_(root_u_h)                      # host-side refill, not timed
+        h_lb[:] = inst.lb; h_ub[:] = inst.ub                            # host-side refill, not timed
         with torch.cuda.stream(stream):
             flush.zero_()
         torch.cuda.synchronize()
         t = time.perf_counter()
-        eng.tighten_raw(1, h_lb.data_ptr(), h_ub.data_ptr(), opts, vbuf.ctypes.data, rbuf.ctypes.data, zbuf.ctypes.data)
+        eng.tighten_raw(1, h_lb.ctypes.data, h_ub.ctypes.data, opts, vbuf.ctypes.data, rbuf.ctypes.data, zbuf.ctypes.data)
         return time.perf_counter() - t, int(zbuf[0])
 
     for _ in range(args.warmup):
         e2e_step()
-    barrier()
+    X.barrier()
     e2e_s, e2e_nnz = 0.0, 0
     for _ in range(args.steps):
         s, z = e2e_step(); e2e_s += s; e2e_nnz += z
-    barrier()
-    e2e_value = sum_over_ranks(float(e2e_nnz)) / max_over_ranks(e2e_s)
-    # bytes that cross PCIe per step: the kernel reads the whole pinned host box (zero-copy, one coalesced pass) and
-    # writes back {lb, ub} of the variables that moved, plus the 128-byte control block
-    moved = int(np.count_nonzero((h_lb.numpy() != inst.lb) | (h_ub.numpy() != inst.ub)))
+    X.barrier()
+    e2e_value = X.sum_over_ranks(float(e2e_nnz)) / X.max_over_ranks(e2e_s)
+    moved = int(np.count_nonzero((h_lb != inst.lb) | (h_ub != inst.ub)))
     zero_copy = not os.environ.get("MNTR_GPU_NO_ZEROCOPY")
     d2h_bytes = 16 * moved + 128 if zero_copy else 16 * n + 128
-    clocks = sampler.stop() if rank == 0 else None
+    e2e_ok = np.array_equal(h_lb, got_lb) and np.array_equal(h_ub, got_ub)
+    eng.free_host(h_lb); eng.free_host(h_ub)
 
-    # ---------------- roofline of the fixpoint launch ----------------
-    peak, peak_src = measured_hbm_peak()
     st = st_last
     algo_bytes = 28 * st.nnz_updates + 24 * st.rows_evaluated + 17 * n * st.max_rounds + 16 * st.n_changes
     launch_ms = ker_ms / args.steps
     achieved = algo_bytes / (launch_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("fbbt_single_jacobi_kernel_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "fbbt_single_jacobi_kernel", "algorithmic_bytes_per_launch": algo_bytes,
-                "launch_ms": launch_ms, "rounds": st.max_rounds, "peak_source": peak_src}
+    traffic, tsrc = static_traffic("fbbt_single_jacobi_kernel_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": X.peak, "unit": "GB/s", "frac": achieved / X.peak,
+                "traffic": traffic, "traffic_source": f"static, from the committed ncu capture ({tsrc}); not measured in this run",
+                "kernel": "fbbt_single_jacobi_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                "launch_ms": launch_ms, "rounds": st.max_rounds, "peak_source": X.peak_src,
+                "note": "17 MB instance: L2-resident after round 1, latency / barrier bound (DESIGN.md 7)"}
 
-    # ---------------- extra: C3-shaped node batch sharded by node ----------------
-    extra = {}
-    if not args.no_extra:
-        for key, fn in (("node_batch", node_batch_extra), ("large_single_box", large_single_extra),
-                        ("row_partition", row_partition_extra), ("minlp_batch", minlp_batch_extra)):
-            try:
-                extra[key] = fn(args, eng, E, torch, dev, stream, rank, world, barrier, max_over_ranks, sum_over_ranks)
-            except Exception as ex:  # an extra must never take the headline down
-                extra[key] = {"error": repr(ex)[:300]}
-            barrier()
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_baseline_c2(inst)
-
-    if rank == 0:
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ker_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: synthetic sparse MILP 100k x 100k, 1M nnz, single box to fixpoint",
-                       "seed": C2["seed"], "rounding": "directed", "order": "jacobi", "l2": "flushed between steps (256 MB write)",
-                       "parallelism": f"replicas x{world}" if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "mntr_gpu_tighten (C ABI), pinned host buffers",
-                    "transfer": ("zero-copy: the kernel reads the pinned host box over PCIe and writes back only the "
-                                 f"bounds that moved ({moved} variables)") if zero_copy else "staged: cudaMemcpyAsync both ways"},
-            "gpu_launches": args.steps, "roofline": roofline, "clocks": clocks,
-            "wall_s_timed_region": wall_s, "extra": extra,
-        }
-        if cpu is not None:
-            out["cpu_baseline"] = cpu
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    parity = None
+    if X.parity and X.rank == 0:
+        from oracle import pyoracle
+        orc = pyoracle.Oracle()
+        jl, ju, jr = orc.lin_fixpoint_jacobi(inst, inst.lb, inst.ub)
+        il, iu, ir = orc.lin_fixpoint_inplace(inst, inst.lb, inst.ub)
+        ok_j, w_j = box_parity(inst.var_type, got_lb, got_ub, jl, ju)
+        ok_i, w_i = box_parity(inst.var_type, got_lb, got_ub, il, iu)
+        parity = {"ok": bool(ok_j and ok_i and jr["verdict"] == 0 and jr["nnz_updates"] == st.nnz_updates and
+                             jr["rounds"] == st.max_rounds and e2e_ok),
+                  "vs_oracle_jacobi": {"ok": ok_j, "worst_rel_diff": w_j, "rounds_equal": jr["rounds"] == st.max_rounds,
+                                       "nnz_updates_equal": jr["nnz_updates"] == st.nnz_updates},
+                  "vs_reference_inplace_fixpoint": {"ok": ok_i, "worst_rel_diff": w_i},
+                  "e2e_box_equals_device_box": bool(e2e_ok),
+                  "criterion": "integer bounds exact, continuous <= 1e-9 rel and never tighter (directed rounding, Jacobi order)"}
+    cpu = cpu_single_box(inst) if X.cpu else None
+    eng.close()
+    out = {"workload": WORKLOAD_C2, "value": value, "unit": UNIT, "ms_per_step": ker_ms_max / args.steps, "steps": args.steps,
+           "warmup": args.warmup, "rounds": rounds, "gpu_launches": args.steps, "parallelism": "single GPU" if X.world == 1 else f"replicas x{X.world}",
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": d2h_bytes,
+                   "ms_per_step": 1e3 * e2e_s / args.steps, "api": "mntr_gpu_tighten (C ABI), host buffers from mntr_gpu_alloc_host",
+                   "transfer": ("zero-copy: the kernel reads the pinned host box over PCIe and writes back only the "
+                                f"bounds that moved ({moved} variables)") if zero_copy else "staged: cudaMemcpyAsync both ways"},
+           "roofline": roofline, "parity": parity}
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    return out
 
 
-def node_batch_extra(args, eng_c2, E, torch, dev, stream_unused, rank, world, barrier, max_over_ranks, sum_over_ranks):
-    """C3: 8192 branching-perturbed boxes on a 50k-row knapsack/set-cover instance, sharded by node."""
-    from minotaur_b200.instances import branch_boxes, make_knapsack_setcover
-    inst = make_knapsack_setcover(**C3)
-    total = args.batch_boxes
-    per = (total + world - 1) // world
-    b0, b1 = rank * per, min(total, (rank + 1) * per)
+# ---------------------------------------------------------------- C1 ----------------------------------------------
+
+def block_c1(X):
+    """tls4.nl as flattened by minotaur_b200/nl_reader.py (fixture: tests/golden/tls4_cases.npz, generated by the
+    reference's own handlers): node presolve of the root box and 11 branched boxes, bit for bit."""
+    if X.rank != 0:
+        return None
+    E = X.E
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_golden import GOLD, load_minlp
+    z = np.load(os.path.join(GOLD, "tls4_cases.npz"))
+    lin, t = load_minlp(z, "tls4")
+    lbs, ubs = z["tls4.lbs"], z["tls4.ubs"]
+    eng = E.GpuBoundEngine(X.dev.index)
+    eng.load_linear(lin); eng.load_cgraph(t)
+    res = eng.tighten(lbs, ubs, rounding=E.ROUND_NEAREST, order=E.ORDER_REFERENCE, loop=E.LOOP_SIMPLEPRESOLVE)
+    n_eq = n_cmp = 0
+    for b in range(lbs.shape[0]):
+        if res.verdict[b] == E.INFEAS_ROW:
+            continue
+        n_cmp += 1
+        same = (res.verdict[b] != 0) == (z["tls4.node_verdict"][b] != 0)
+        if same and res.verdict[b] == 0:
+            same = np.array_equal(res.lb[b], z["tls4.node_lb"][b]) and np.array_equal(res.ub[b], z["tls4.node_ub"][b])
+        n_eq += bool(same)
+    tight = int(np.count_nonzero(res.lb[0] != lbs[0]) + np.count_nonzero(res.ub[0] != ubs[0]))
+    chk = float(np.sum(np.where(np.isfinite(res.lb[0]), res.lb[0], 0.0)) + np.sum(np.where(np.isfinite(res.ub[0]), res.ub[0], 0.0)))
+    eng.close()
+    return {"workload": "C1: test_instances/tls4.nl (105 variables, 60 linear rows + 4 CGraph rows), one presolveNode pass "
+                        "(LinearHandler then NlPresHandler) on the root box and 11 branched boxes",
+            "root_box": {"rounds": int(res.rounds[0]), "tightenings": tight, "verdict": int(res.verdict[0]),
+                         "sum_of_finite_bounds": chk, "kernel_ms": res.kernel_ms},
+            "parity": {"ok": bool(n_eq == n_cmp and n_cmp > 0), "boxes_compared": n_cmp, "boxes_equal": n_eq,
+                       "criterion": "bitwise vs the reference's own LinearHandler + NlPresHandler outputs (golden fixture)"},
+            "note": "root presolve through Presolver::solve with GpuBoundHandler is exercised by handler_test "
+                    "(tests/test_gpu_handler.py)"}
+
+
+# ---------------------------------------------------------------- C3 ----------------------------------------------
+
+def node_batch(X, name, inst, tapes, deltas, loop, mode, workload, cons_per_box=0):
+    """Shared driver of the node-batch blocks (C3, C5): boxes sharded by node over the ranks."""
+    args, E, torch, dev = X.args, X.E, X.torch, X.dev
+    from minotaur_b200.instances import slice_deltas
+    total = len(deltas[0]) - 1
+    tiles = (total + 31) // 32
+    t0, t1 = tiles * X.rank // X.world, tiles * (X.rank + 1) // X.world
+    b0, b1 = min(total, t0 * 32), min(total, t1 * 32)
     nb = b1 - b0
-    # boxes are generated per rank (same seed stream, rank's slice)
-    lbs, ubs = branch_boxes(inst.lb, inst.ub, inst.var_type, total, seed=C3["seed"], max_depth=20)
-    lbs, ubs = lbs[b0:b1], ubs[b0:b1]
+    mine = slice_deltas(deltas, b0, b1)
     eng = E.GpuBoundEngine(dev.index)
     eng.load_linear(inst)
+    if tapes is not None:
+        eng.load_cgraph(tapes)
+    n, m = inst.n, inst.m
     ld = eng.box_ld(nb)
-    boxes = torch.empty((inst.n, ld, 2), dtype=torch.float64, device=dev)
+    boxes = torch.empty((n, ld, 2), dtype=torch.float64, device=dev)
     verdict = torch.zeros(ld, dtype=torch.int32, device=dev); rounds = torch.zeros(ld, dtype=torch.int32, device=dev)
     nnz = torch.zeros(ld, dtype=torch.int64, device=dev)
-    eng.boxes_upload(lbs, ubs, boxes.data_ptr())
-    pristine = boxes.clone()
-    ms_tot, reps = 0.0, 3
+    reps = 1 if args.profile else 3
+    ms_list = []
     for it in range(reps + 1):
-        boxes.copy_(pristine)
+        eng.boxes_from_deltas(inst.lb, inst.ub, *mine, boxes.data_ptr())      # untimed: rebuild the batch in HBM
         torch.cuda.synchronize()
-        barrier()
-        st = eng.tighten_dev(nb, boxes.data_ptr(), verdict.data_ptr(), rounds.data_ptr(), nnz.data_ptr())
+        X.barrier()
+        st = eng.tighten_dev(nb, boxes.data_ptr(), verdict.data_ptr(), rounds.data_ptr(), nnz.data_ptr(), loop=loop)
+        if it > 0 or reps == 1:
+            ms_list.append(st.kernel_ms)
+    ms_rank = float(np.mean(ms_list))
+    ms = X.max_over_ranks(ms_rank)
+    ms_min = X.min_over_ranks(ms_rank)
+    h_nnz = nnz[:nb].cpu().numpy(); h_rounds = rounds[:nb].cpu().numpy(); h_v = verdict[:nb].cpu().numpy()
+    nnz_sum = X.sum_over_ranks(float(h_nnz.sum()))
+    n_inf = X.sum_over_ranks(float((h_v != 0).sum()))
+    rounds_sum = X.sum_over_ranks(float(h_rounds.sum()))
+    # algorithmic bytes (SURVEY.md 8d, batched boxes): per box and sweep 16 B per visited nnz + 17 B per variable; the
+    # matrix (12 B per nnz + 24 B per row) once per tile of 32 boxes and sweep
+    tile_rounds = float(sum(h_rounds[k:k + 32].max(initial=0) for k in range(0, nb, 32)))
+    tile_rounds = X.sum_over_ranks(tile_rounds)
+    algo = 16.0 * nnz_sum + 17.0 * n * rounds_sum + (12.0 * inst.nnz + 24.0 * m) * tile_rounds
+    evals = None
+    if cons_per_box:
+        # CGraph part: per constraint evaluation 16 B per variable leaf (2 leaves + the linear term's) + tape bytes
+        # amortised over the tile; evaluations are counted on the device (nnz carries the linear rows only)
+        st_dev = eng.stats()
+        evals = X.sum_over_ranks(float(getattr(st_dev, "nl_evals", 0)))
+        algo += 16.0 * 2.5 * evals
+    del boxes
+    torch.cuda.empty_cache()
+
+    # e2e through the reference-facing call: host deltas in, VarBoundMod tuples out (output buffers page-locked, as a
+    # caller that owns them would allocate them: mntr_gpu_alloc_host)
+    cap = int(os.environ.get("MNTR_BENCH_MODCAP", "0")) or max(1 << 20, nb * 4096)
+    raw = [eng.alloc_host_bytes(4 * cap), eng.alloc_host_bytes(cap), eng.alloc_host_bytes(8 * cap)]
+    obuf = (raw[0].view(np.int32), raw[1], raw[2].view(np.float64))
+    e2e_times = []
+    for it in range(2 if args.profile else 3):
+        t_e = time.perf_counter()
+        v, r, mp, mv, mu, mx, total_mods = eng.tighten_nodes(inst.lb, inst.ub, *mine, loop=loop, mod_cap=cap, out=obuf)
         if it > 0:
-            ms_tot += st.kernel_ms
-    ms = max_over_ranks(ms_tot / reps)
-    nnz_sum = sum_over_ranks(float(nnz[:nb].sum().item()))
-    n_inf = sum_over_ranks(float((verdict[:nb] != 0).sum().item()))
+            e2e_times.append(time.perf_counter() - t_e)
+    e2e_s = float(np.mean(e2e_times))
+    st_e = eng.stats()
+    e2e_max = X.max_over_ranks(e2e_s)
+    e2e_nnz = X.sum_over_ranks(float(st_e.nnz_updates))
+    h2d = 16 * n + 8 * (nb + 1) + 13 * int(mine[0][-1])
+    d2h = 13 * min(total_mods, cap) + 16 * nb
+    same_as_dev = bool(np.array_equal(v, h_v) and np.array_equal(r, h_rounds))
+    mv, mu, mx = mv.copy(), mu.copy(), mx.copy()        # out of the pinned buffers (freed below)
+    for a in raw:
+        eng.free_host(a)
+
+    parity = None
+    port = None
+    if X.parity:
+        from oracle import pyoracle
+        orc = pyoracle.Oracle()
+        threads = max(1, (os.cpu_count() or 1) // max(1, min(X.world, 8)))
+        k = max(1, args.parity_boxes // X.world)
+        idx = sample_boxes(nb, k, seed=1000 + X.rank)
+        rec, ores = batch_parity(E, eng, orc, inst, tapes, mine, idx, mode, loop, threads)
+        rec["directed"] = directed_parity(E, inst, mine, idx, (v, mp, mv, mu, mx), ores) if total_mods <= cap else None
+        rec["e2e_verdicts_rounds_equal_device_run"] = same_as_dev
+        ok_all = X.min_over_ranks(1.0 if (rec["ok"] and same_as_dev) else 0.0) > 0.5
+        rec["boxes_compared"] = int(X.sum_over_ranks(float(rec["boxes_compared"])))
+        rec["boxes_equal"] = int(X.sum_over_ranks(float(rec["boxes_equal"])))
+        rec["ok"] = bool(ok_all)
+        parity = rec
+        port = {"boxes_per_s": len(idx) / ores["secs"], "cores": threads, "kind": "port",
+                "sample": f"{len(idx)} sampled boxes, C oracle (in-place sweeps), {threads} OpenMP threads"}
     eng.close()
-    return {"workload": f"C3: {total} boxes on 50k-row knapsack/set-cover, reference-order sweeps to fixpoint",
-            "boxes_per_s": total / (ms * 1e-3), "nnz_updates_per_s": nnz_sum / (ms * 1e-3), "ms": ms,
-            "infeasible_boxes": n_inf, "boxes_per_rank": per, "scaling": "strong"}
+    achieved = algo / (ms * 1e-3) / 1e9 / X.world           # per GPU
+    out = {"workload": workload, "value": nnz_sum / (ms * 1e-3), "unit": UNIT, "boxes_per_s": total / (ms * 1e-3),
+           "ms_per_step": ms, "ms_fastest_rank": ms_min, "steps": len(ms_list), "warmup": 1, "boxes": total, "boxes_per_rank": nb,
+           "infeasible_boxes": int(n_inf), "mean_rounds": rounds_sum / max(1, total), "gpu_launches": len(ms_list),
+           "scaling": "strong", "parallelism": f"boxes sharded by node over {X.world} GPU(s), no collective",
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": X.peak, "unit": "GB/s", "frac": achieved / X.peak,
+                        "traffic": None, "kernel": "fbbt_batch_reference_kernel", "algorithmic_bytes_per_launch": algo / X.world,
+                        "launch_ms": ms, "peak_source": X.peak_src, "per": "GPU"},
+           "e2e": {"value": e2e_nnz / e2e_max, "unit": UNIT, "boxes_per_s": total / e2e_max, "ms_per_step": 1e3 * e2e_max,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "mods_out": int(total_mods),
+                   "api": "mntr_gpu_tighten_nodes (C ABI): root box + branching deltas in, VarBoundMod tuples out",
+                   "device_ms": {"build_boxes": st_e.h2d_ms, "kernel": st_e.kernel_ms, "mods_out": st_e.d2h_ms}},
+           "parity": parity}
+    if evals is not None:
+        out["constraint_evaluations"] = evals
+        out["constraint_evals_per_s"] = evals / (ms * 1e-3)
+    return out, port
 
 
-def large_single_extra(args, eng_c2, E, torch, dev, stream_unused, rank, world, barrier, max_over_ranks,
-                       sum_over_ranks):
-    """One rank's share of C4 as ONE box on ONE GPU in a single cooperative launch: 2.5M rows x 10 nnz.  Far more rows
-    than the grid can keep resident, so K1 streams them from the CSR (dense 32-row blocks lane = row): the
-    bandwidth-bound regime of the same kernel whose latency-bound regime is the C2 headline."""
-    from minotaur_b200.instances import make_sparse_milp_block
-    m = args.c4_rows_per_rank
-    inst = make_sparse_milp_block(m, m, 10, seed=777, block=0)
-    eng = E.GpuBoundEngine(dev.index)
-    eng.load_linear(inst)
-    lb0 = torch.from_numpy(inst.lb).to(dev); ub0 = torch.from_numpy(inst.ub).to(dev)
-    lb = torch.empty_like(lb0); ub = torch.empty_like(ub0)
-    ms, reps, z, r, v = 0.0, 3, 0, 0, 0
-    for it in range(reps + 1):
-        lb.copy_(lb0); ub.copy_(ub0)
-        torch.cuda.synchronize(); barrier()
-        v, r, z = eng.tighten_single_dev(lb.data_ptr(), ub.data_ptr())
-        st = eng.stats()
-        if it > 0:
-            ms += st.kernel_ms
-    ms = max_over_ranks(ms / reps)
-    algo = 28.0 * st.nnz_updates + 24.0 * st.rows_evaluated + 17.0 * m * r + 16.0 * st.n_changes
-    peak, _ = measured_hbm_peak()
-    eng.close()
-    return {"workload": f"{m} rows x {m} cols, {10 * m} nnz, single box to fixpoint in one launch (rows streamed from the CSR)",
-            "nnz_updates_per_s": z / (ms * 1e-3), "ms": ms, "rounds": r, "verdict": v,
-            "algorithmic_GBps": algo / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": algo / (ms * 1e-3) / 1e9 / peak,
-            "scaling": "replicas"}
+def block_c3(X):
+    from minotaur_b200.instances import branch_deltas, make_knapsack_setcover
+    args = X.args
+    inst = make_knapsack_setcover(**C3)
+    deltas = branch_deltas(inst.lb, inst.ub, inst.var_type, args.c3_boxes, seed=C3["seed"], max_depth=C3_DEPTH)
+    out, port = node_batch(X, "C3", inst, None, deltas, X.E.LOOP_FIXPOINT, 0, WORKLOAD_C3)
+    traffic, tsrc = static_traffic("fbbt_batch_reference_kernel_c3_dram_bytes_per_launch")
+    out["roofline"]["traffic"] = traffic
+    out["roofline"]["traffic_source"] = f"static, from the committed ncu capture ({tsrc}); not measured in this run"
+    if X.world > 1:
+        # the whole batch on ONE GPU in the same run (rank 0 alone), so the strong-scaling base is measured here
+        X.barrier()
+        if X.rank == 0:
+            one = Ctx(); one.__dict__.update(X.__dict__)
+            one.world, one.parity = 1, False
+            one.barrier = X.torch.cuda.synchronize
+            one.max_over_ranks = one.sum_over_ranks = one.min_over_ranks = (lambda x: x)
+            solo, _ = node_batch(one, "C3", inst, None, deltas, X.E.LOOP_FIXPOINT, 0, WORKLOAD_C3)
+            out["ms_1gpu_same_run"] = solo["ms_per_step"]
+        X.barrier()
+    if X.cpu:
+        out["cpu_baseline"] = cpu_node_batch(inst, None, deltas, [(0, "fixpoint"), (1, "simple_presolve")], n_one=8,
+                                             n_all=8 * (os.cpu_count() or 1), port=port)
+    return out
 
 
-def row_partition_extra(args, eng_c2, E, torch, dev, stream_unused, rank, world, barrier, max_over_ranks,
-                        sum_over_ranks):
-    """C4 shape, weak-scaled: every rank owns a block of 2.5M rows x 10 nnz over n = 2.5M x world columns
-    (world = 8 is BASELINE config 4: 20M x 20M, 200M nnz), box replicated, per-round NCCL MAX/MIN all-reduce."""
+# ---------------------------------------------------------------- C5 ----------------------------------------------
+
+def block_c5(X):
+    from minotaur_b200.instances import branch_deltas, make_minlp_large
+    args = X.args
+    scale = args.c5_cons / C5["n_cons"]
+    lin, tapes = make_minlp_large(n=int(C5["n"] * scale), n_cons=args.c5_cons, m_lin=int(C5["m_lin"] * scale), seed=C5["seed"])
+    deltas = branch_deltas(lin.lb, lin.ub, lin.var_type, args.c5_boxes, seed=C5["seed"], max_depth=C5_DEPTH, continuous_too=True)
+    wl = (f"C5: {tapes.n_cons} bilinear/quadratic CGraph constraints + {lin.m} linear rows over {lin.n} variables, "
+          f"{args.c5_boxes} node boxes, one presolveNode pass per box (LinearHandler::simplePresolve then "
+          "NlPresHandler::simplePresolve, in-place order by wavefront levels)")
+    out, port = node_batch(X, "C5", lin, tapes, deltas, X.E.LOOP_SIMPLEPRESOLVE, 2, wl, cons_per_box=tapes.n_cons)
+    out["roofline"]["kernel"] = "fbbt_batch_reference_kernel<.., HAS_NL> (K3 + K4)"
+    out["roofline"]["note"] = "instruction-issue bound (interval arithmetic of the tapes), not HBM bound: see DESIGN.md"
+    if X.cpu:
+        out["cpu_baseline"] = cpu_node_batch(lin, tapes, deltas, [(2, "node_presolve")], n_one=2, n_all=0, port=port)
+    return out
+
+
+# ---------------------------------------------------------------- C4 ----------------------------------------------
+
+def c4_run(X, m_block, world, rank, comm, reps, sync, want_e2e=False):
+    """One rank's part of a C4-shaped row-partitioned fixpoint.  comm: attach the NCCL communicator (world > 1)."""
     import torch.distributed as dist
     from minotaur_b200.instances import make_sparse_milp_block
-    m_block = args.c4_rows_per_rank
+    E, torch, dev = X.E, X.torch, X.dev
     n = m_block * world
-    inst = make_sparse_milp_block(m_block, n, 10, seed=777, block=rank)
+    inst = make_sparse_milp_block(m_block, n, 10, seed=C4_SEED, block=rank)
     eng = E.GpuBoundEngine(dev.index)
     eng.load_linear(inst)
-    if world > 1:
+    if comm:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             uid = torch.frombuffer(bytearray(E.GpuBoundEngine.nccl_unique_id()), dtype=torch.uint8).to(dev)
@@ -424,69 +817,109 @@ def row_partition_extra(args, eng_c2, E, torch, dev, stream_unused, rank, world,
     lb0 = torch.from_numpy(inst.lb).to(dev); ub0 = torch.from_numpy(inst.ub).to(dev)
     lb = torch.empty_like(lb0); ub = torch.empty_like(ub0)
     best = None
-    for it in range(3):
+    for it in range(reps + 1):
         lb.copy_(lb0); ub.copy_(ub0)
-        torch.cuda.synchronize(); barrier()
-        t0 = time.perf_counter()
-        v, r, z = eng.tighten_single_dev(lb.data_ptr(), ub.data_ptr(),
-                                         flags=E.FLAG_PER_ROUND_KERNELS if world == 1 else 0)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
+        torch.cuda.synchronize(); sync()
+        v, r, z = eng.tighten_single_dev(lb.data_ptr(), ub.data_ptr(), flags=0 if comm else E.FLAG_PER_ROUND_KERNELS)
         st = eng.stats()
-        rec = dict(wall_ms=1e3 * wall, kernel_ms=st.kernel_ms, rows_ms=st.rows_ms, comm_ms=st.comm_ms,
-                   vars_ms=st.vars_ms, rounds=r, verdict=v, nnz=z)
+        rec = dict(kernel_ms=st.kernel_ms, rows_ms=st.rows_ms, comm_ms=st.comm_ms, vars_ms=st.vars_ms, rounds=r, verdict=v,
+                   nnz=z, sparse_rounds=st.sparse_rounds, changes=st.n_changes)
         if it > 0 and (best is None or rec["kernel_ms"] < best["kernel_ms"]):
             best = rec
-    ms = max_over_ranks(best["kernel_ms"])
-    nnz_total = best["nnz"] if world > 1 else best["nnz"]        # with a communicator nnz is already the job total
-    if world > 1:
+    e2e = None
+    if want_e2e:
+        # the reference-facing call with HOST boxes (page-locked: mntr_gpu_alloc_host); every rank hands in its replica
+        h_lb = eng.alloc_host(n); h_ub = eng.alloc_host(n)
+        opts = E.GpuOptions(E.ROUND_DIRECTED, E.ORDER_JACOBI, E.LOOP_FIXPOINT, 0, E.HANDLERS_ALL,
+                            0 if comm else E.FLAG_PER_ROUND_KERNELS)
+        zbuf = np.zeros(1, np.int64)
+        secs = []
+        for it in range(2):
+            h_lb[:] = inst.lb; h_ub[:] = inst.ub
+            torch.cuda.synchronize(); sync()
+            t0 = time.perf_counter()
+            eng.tighten_raw(1, h_lb.ctypes.data, h_ub.ctypes.data, opts, 0, 0, zbuf.ctypes.data)
+            secs.append(time.perf_counter() - t0)
+        e2e = {"secs": min(secs), "nnz": int(zbuf[0]), "box_equal": bool(np.array_equal(h_lb, lb.cpu().numpy()) and
+                                                                         np.array_equal(h_ub, ub.cpu().numpy()))}
+        eng.free_host(h_lb); eng.free_host(h_ub)
+    if comm:
         eng.comm_destroy()
     eng.close()
-    algo_bytes_rank = 28.0 * nnz_total / world + 17.0 * n * best["rounds"]
-    return {"workload": f"C4 shape: {m_block * world} rows x {n} cols, {10 * m_block * world} nnz, row-partitioned "
-                        f"over {world} GPU(s), single box to fixpoint (Jacobi)",
-            "nnz_updates_per_s": nnz_total / (ms * 1e-3), "ms": ms, "rounds": best["rounds"],
-            "per_round_ms": {"rows": best["rows_ms"] / best["rounds"], "allreduce": best["comm_ms"] / best["rounds"],
-                             "vars": best["vars_ms"] / best["rounds"]},
-            "verdict": best["verdict"], "algorithmic_GBps_per_gpu": algo_bytes_rank / (ms * 1e-3) / 1e9,
-            "scaling": "weak"}
+    return inst, lb.cpu().numpy(), ub.cpu().numpy(), best, e2e
 
 
-def minlp_batch_extra(args, eng_c2, E, torch, dev, stream_unused, rank, world, barrier, max_over_ranks,
-                      sum_over_ranks):
-    """C5 shape (scaled): bilinear/quadratic CGraph constraints + linear rows, node boxes sharded by node."""
-    from minotaur_b200.instances import branch_boxes, make_minlp
-    n, n_cons, m_lin, total = args.c5_cons, args.c5_cons, args.c5_cons // 10, args.c5_boxes
-    lin, tapes = make_minlp(n=n, n_cons=n_cons, m_lin=m_lin, seed=99)
-    per = (total + world - 1) // world
-    b0, b1 = rank * per, min(total, (rank + 1) * per)
-    nb = b1 - b0
-    lbs, ubs = branch_boxes(lin.lb, lin.ub, lin.var_type, total, seed=99, max_depth=10, continuous_too=True)
-    lbs, ubs = lbs[b0:b1], ubs[b0:b1]
-    eng = E.GpuBoundEngine(dev.index)
-    eng.load_linear(lin)
-    eng.load_cgraph(tapes)
-    ld = eng.box_ld(nb)
-    boxes = torch.empty((lin.n, ld, 2), dtype=torch.float64, device=dev)
-    verdict = torch.zeros(ld, dtype=torch.int32, device=dev); rounds = torch.zeros(ld, dtype=torch.int32, device=dev)
-    nnz = torch.zeros(ld, dtype=torch.int64, device=dev)
-    eng.boxes_upload(lbs, ubs, boxes.data_ptr())
-    pristine = boxes.clone()
-    ms_tot, reps = 0.0, 2
-    for it in range(reps + 1):
-        boxes.copy_(pristine)
-        torch.cuda.synchronize(); barrier()
-        st = eng.tighten_dev(nb, boxes.data_ptr(), verdict.data_ptr(), rounds.data_ptr(), nnz.data_ptr(),
-                             loop=E.LOOP_SIMPLEPRESOLVE)
-        if it > 0:
-            ms_tot += st.kernel_ms
-    ms = max_over_ranks(ms_tot / reps)
-    n_inf = sum_over_ranks(float((verdict[:nb] != 0).sum().item()))
-    eng.close()
-    return {"workload": f"C5 shape (scaled): {n_cons} CGraph constraints + {m_lin} linear rows over {n} variables, "
-                        f"{total} node boxes, one presolveNode pass (LinearHandler then NlPresHandler order)",
-            "boxes_per_s": total / (ms * 1e-3), "constraint_evals_per_s": 2.0 * total * n_cons / (ms * 1e-3),
-            "ms": ms, "infeasible_boxes": n_inf, "boxes_per_rank": per, "scaling": "strong"}
+def block_c4(X):
+    args, E, torch, dev, world, rank = X.args, X.E, X.torch, X.dev, X.world, X.rank
+    import hashlib
+    m_block = args.c4_rows_per_rank
+    n = m_block * world
+    inst, lb, ub, best, e2e = c4_run(X, m_block, world, rank, world > 1, 1 if args.profile else 2, X.barrier, want_e2e=True)
+    ms = X.max_over_ranks(best["kernel_ms"])
+    nnz_total = best["nnz"]                     # with a communicator the counters are already the job total
+    digest = hashlib.sha256(lb.tobytes() + ub.tobytes()).hexdigest()
+    # every rank must hold the same box
+    same = X.min_over_ranks(float(int(digest[:12], 16))) == X.max_over_ranks(float(int(digest[:12], 16)))
+    inside = bool(np.all(lb <= inst.xstar + 1e-6) and np.all(ub >= inst.xstar - 1e-6))
+    algo_rank = 28.0 * nnz_total / world + 24.0 * (nnz_total / 10.0) / world + 17.0 * n * best["rounds"] + 16.0 * best["changes"]
+    achieved = algo_rank / (ms * 1e-3) / 1e9
+    parity = None
+    if X.parity:
+        # bitwise independence of the rank count, at a size where one GPU holds the whole instance: the N-rank run
+        # of a (200k x N)-row instance against ONE rank running all N blocks with the same per-round kernels
+        m_small = 200_000
+        _, slb, sub, sb, _ = c4_run(X, m_small, world, rank, world > 1, 1, X.barrier)
+        rec = {"ranks_hold_identical_boxes": bool(same), "planted_point_inside_final_box": inside, "verdict": best["verdict"]}
+        if rank == 0:
+            from minotaur_b200.instances import make_sparse_milp_block
+            import copy
+            parts = [make_sparse_milp_block(m_small, m_small * world, 10, seed=C4_SEED, block=b) for b in range(world)]
+            whole = copy.copy(parts[0])
+            whole.m = m_small * world
+            whole.col = np.concatenate([p.col for p in parts]); whole.val = np.concatenate([p.val for p in parts])
+            whole.row_lb = np.concatenate([p.row_lb for p in parts]); whole.row_ub = np.concatenate([p.row_ub for p in parts])
+            whole.row_ptr = (np.arange(whole.m + 1, dtype=np.int64) * 10).astype(np.int32)
+            e1 = E.GpuBoundEngine(dev.index)
+            e1.load_linear(whole)
+            r1 = e1.tighten(whole.lb, whole.ub, flags=E.FLAG_PER_ROUND_KERNELS)
+            e1.close()
+            eq = bool(np.array_equal(r1.lb, slb) and np.array_equal(r1.ub, sub) and int(r1.rounds[0]) == sb["rounds"]
+                      and int(r1.nnz_updates[0]) == sb["nnz"])
+            rec["n_rank_box_bitwise_equals_1_rank_box"] = eq
+            rec["checked_at"] = f"{m_small * world} rows x {m_small * world} cols, {world} rank(s) vs 1 rank"
+            if world == 1:
+                # one rank: the per-round kernels against the oracle's Jacobi restatement
+                from oracle import pyoracle
+                jl, ju, jr = pyoracle.Oracle().lin_fixpoint_jacobi(whole, whole.lb, whole.ub)
+                okj, wj = box_parity(whole.var_type, slb, sub, jl, ju)
+                rec["vs_oracle_jacobi"] = {"ok": okj, "worst_rel_diff": wj, "rounds_equal": jr["rounds"] == sb["rounds"],
+                                           "nnz_updates_equal": jr["nnz_updates"] == sb["nnz"]}
+                eq = eq and okj and jr["nnz_updates"] == sb["nnz"]
+            rec["ok"] = bool(eq and same and inside and best["verdict"] == 0)
+        parity = rec if rank == 0 else None
+    out = {"workload": f"C4: {m_block * world} rows x {n} cols, {10 * m_block * world} nnz, row-partitioned over {world} GPU(s), "
+                       "single box to the Jacobi fixpoint, per-round bound merge",
+           "value": nnz_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": 2, "warmup": 1, "rounds": best["rounds"],
+           "per_round_ms": {"rows": best["rows_ms"] / best["rounds"], "merge": best["comm_ms"] / best["rounds"],
+                            "vars": best["vars_ms"] / best["rounds"]},
+           "sparse_merge_rounds": best["sparse_rounds"], "scaling": "weak", "gpu_launches": None,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": X.peak, "unit": "GB/s", "frac": achieved / X.peak, "traffic": None,
+                        "kernel": "rounds_rows_kernel + merge + rounds_vars_kernel", "algorithmic_bytes_per_launch": algo_rank,
+                        "launch_ms": ms, "peak_source": X.peak_src, "per": "GPU"},
+           "e2e": None, "parity": parity}
+    if e2e is not None:
+        e2e_s = X.max_over_ranks(e2e["secs"])
+        out["e2e"] = {"value": e2e["nnz"] / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s, "h2d_bytes_per_step": 16 * n,
+                      "d2h_bytes_per_step": 16 * n, "api": "mntr_gpu_tighten (C ABI), one box in page-locked host memory per rank "
+                      "(staged copies both ways)", "box_equals_device_run": bool(X.min_over_ranks(1.0 if e2e["box_equal"] else 0.0) > 0.5)}
+    if X.cpu:
+        from minotaur_b200.instances import make_sparse_milp
+        small = make_sparse_milp(args.c4_cpu_rows, args.c4_cpu_rows, 10, seed=C4_SEED)
+        cb = cpu_single_box(small, budget_s=4.0)
+        cb["sample"] = (f"1/10-scale instance ({args.c4_cpu_rows} rows x {args.c4_cpu_rows} cols, {10 * args.c4_cpu_rows} nnz; the "
+                        "reference's object graph needs ~200 B per nnz): " + cb["sample"])
+        out["cpu_baseline"] = cb
+    return out
 
 
 if __name__ == "__main__":

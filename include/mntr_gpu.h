@@ -121,6 +121,8 @@ typedef struct {
   double  h2d_ms, d2h_ms;
   double  comm_ms;       /* device time of the per-round NCCL bound all-reduces (row-partitioned mode) */
   double  rows_ms, vars_ms; /* per-round kernels of the row-partitioned mode */
+  int64_t nl_evals;      /* (constraint, box) evaluations of CGraph tapes, counted on the device: one per chkRed_
+                            check and one per varBoundMods call that actually ran (boxes that stop early stop counting) */
 } mntr_gpu_stats;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -225,6 +227,21 @@ int mntr_gpu_tighten_single_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_de
 /* the context's cudaStream_t, for callers that time or order work against it */
 void *mntr_gpu_stream(mntr_gpu_ctx *ctx);
 
+/* Node boxes in the engine's layout built on the device from a root box and branching deltas (the input form of
+ * mntr_gpu_tighten_nodes; host arrays in, boxes_dev [n][mntr_gpu_box_ld(n_boxes)] double2 out).  For callers
+ * that keep a batch resident in HBM -- a dense box-major host copy of config C5's batch would be 65 GB. */
+int mntr_gpu_boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *root_lb,
+                               const double *root_ub, const int64_t *delta_ptr, const int32_t *delta_var,
+                               const uint8_t *delta_is_upper, const double *delta_val, void *boxes_dev);
+
+/* Page-locked, device-mapped host memory for the caller's bound arrays.  mntr_gpu_tighten on a single box whose
+ * lb / ub live in such memory takes the zero-copy path: the kernel reads the box over PCIe and writes back only
+ * the bounds that moved -- no staging copies.  (Any cudaHostAlloc'ed / cudaHostRegister'ed memory qualifies; these
+ * two calls spare the Minotaur-side adapter a CUDA dependency.)  Replaces: nothing in the reference (its bounds
+ * live in Variable objects, Variable.h:164-191). */
+void *mntr_gpu_alloc_host(mntr_gpu_ctx *ctx, int64_t bytes);
+void mntr_gpu_free_host(mntr_gpu_ctx *ctx, void *p);
+
 /* statistics of the last tighten call */
 int mntr_gpu_get_stats(const mntr_gpu_ctx *ctx, mntr_gpu_stats *out);
 
@@ -232,15 +249,48 @@ int mntr_gpu_get_stats(const mntr_gpu_ctx *ctx, mntr_gpu_stats *out);
 
 /* Every rank loads ITS row block with mntr_gpu_load_linear (all n columns) and holds a
  * full replica of the box.  After this call mntr_gpu_tighten on a single box runs Jacobi
- * rounds whose candidate bounds are merged across ranks each round with an NCCL
- * all-reduce (MAX on lb, MIN on ub, riding as one MAX over [lb ; -ub]) plus the change /
- * infeasible flags; integer rounding and the bound check run replicated after the merge,
+ * rounds whose candidate bounds are merged across ranks each round: rounds that move few bounds
+ * exchange only the changed candidates (all-gathered, merged with exact max / min), the others take
+ * a grouped NCCL all-reduce (MAX on the lower-bound candidates, whose extra slot carries the
+ * row-infeasible flag, MIN on the upper-bound candidates); integer rounding and the bound check run
+ * replicated after the merge,
  * so every rank ends with bit-identical boxes, independent of the number of ranks.
  * nccl_unique_id: 128 bytes from mntr_gpu_nccl_unique_id on rank 0, broadcast by the
  * caller (MPI / torch.distributed / files). */
 int mntr_gpu_nccl_unique_id(void *id128);
 int mntr_gpu_comm_init(mntr_gpu_ctx *ctx, int32_t n_ranks, int32_t rank, const void *id128);
 int mntr_gpu_comm_destroy(mntr_gpu_ctx *ctx);
+
+/* ---- node batches over several GPUs of one box, from ONE process --------------------------------------- */
+
+/* A group holds one context per listed device; the problem is replicated on every member (the CSR / tapes are
+ * small next to the boxes), and mntr_gpu_group_tighten_nodes splits a node batch contiguously over the members,
+ * one host thread per device, no collective (north star: "independent node-box batches split across GPUs";
+ * "multi-GPU init taking a device list").  The single-process counterpart of the
+ * one-process-per-GPU split bench.py makes under torchrun; a B&B thread that owns a group hands all strong-
+ * branching candidates of a node to all GPUs at once.  Signatures mirror the single-context calls. */
+typedef struct mntr_gpu_group mntr_gpu_group;
+int mntr_gpu_group_create(int32_t n_devices, const int32_t *devices, mntr_gpu_group **out);
+void mntr_gpu_group_destroy(mntr_gpu_group *g);
+int32_t mntr_gpu_group_size(const mntr_gpu_group *g);
+mntr_gpu_ctx *mntr_gpu_group_member(mntr_gpu_group *g, int32_t i);
+const char *mntr_gpu_group_last_error(const mntr_gpu_group *g);
+int mntr_gpu_group_load_linear(mntr_gpu_group *g, int32_t m, int32_t n, const int32_t *row_ptr,
+                               const int32_t *col, const double *val, const double *row_lb,
+                               const double *row_ub, const uint8_t *var_type, const uint8_t *row_active);
+int mntr_gpu_group_load_cgraph(mntr_gpu_group *g, int32_t n_cons, const int32_t *tape_ptr, const uint8_t *op,
+                               const int32_t *arg0, const int32_t *arg1, const double *cnst,
+                               const int32_t *child, const int32_t *lin_ptr, const int32_t *lin_col,
+                               const double *lin_val, const double *c_lb, const double *c_ub);
+int mntr_gpu_group_set_cutoff(mntr_gpu_group *g, int32_t k, const int32_t *col, const double *val, double rhs);
+int mntr_gpu_group_set_incumbent(mntr_gpu_group *g, double best_value);
+int mntr_gpu_group_tighten_nodes(mntr_gpu_group *g, int32_t n_boxes, const double *root_lb,
+                                 const double *root_ub, const int64_t *delta_ptr,
+                                 const int32_t *delta_var, const uint8_t *delta_is_upper,
+                                 const double *delta_val, const mntr_gpu_options *opts,
+                                 int32_t *verdict, int32_t *rounds, int64_t *mod_ptr,
+                                 int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val,
+                                 int64_t mod_cap, int64_t *n_mods_out);
 
 #ifdef __cplusplus
 }

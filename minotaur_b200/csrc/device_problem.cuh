@@ -62,23 +62,28 @@ struct SingleWs {
   uint32_t *touched[2]; // [(n+31)/32] variable-moved-in-the-round bit sets
   uint32_t *ever;       // [(n+31)/32] variable moved in some round: the only entries the epilogue writes back
   // control block (128 bytes; zero when a launch starts: the previous launch's last block resets it)
-  unsigned *sync;  // [4]  ONE 16-byte line, read with one load by the barrier's poller:
+  unsigned *sync;  // [4]  ONE 16-byte line, read with one load by the barrier's poller.  Every word is ROUND-TAGGED and
+                   //      only ever grows (atomicMax / atomicOr), so a block that has already left barrier r and writes
+                   //      round r+1 state cannot change what a slower block, still taking its snapshot of barrier r,
+                   //      concludes about round r (a later tag means "round r went on", which implies the same decision):
                    //      [0] device-wide barrier arrive counter
-                   //      [1] last round in which a bound moved          (atomicMax; "changed" of that round)
-                   //      [2] last round in which a row moved an integer variable   (nintmods > 0, :1625-1627)
-                   //      [3] sticky flag bits kCtl*
+                   //      [1] 2 x (last round in which a bound moved) + (a row moved an integer variable in it,
+                   //          nintmods > 0, :1625-1627)
+                   //      [2] bits 0..28: last round whose fix-up found crossed bounds; kCtl* bits above
+                   //      [3] last round in which a row was activity-infeasible
   int32_t *status; // [8]  results: [1] rounds  [2] changed (variable, round) pairs  [6] verdict of the loop
   unsigned long long *counters;  // [2] [0] nnz_updates, [1] rows evaluated
   unsigned *done;  // blocks that have left the kernel: the last one publishes and resets the control block
   int32_t *result; // [kCtrlWords] pinned, mapped host copy of the control block, written by the last block
   unsigned long long *trace;     // [64] optional phase timestamps (globaltimer ns), or nullptr
+  unsigned stress_ns;            // test hook: block 1's barrier poller sleeps this long after arriving (0: off)
 };
 constexpr int kCtrlWords = 32;   // the control block: 128 bytes
-// sticky flags in sync[3]
-constexpr unsigned kCtlRowInf = 1u;      // a row is activity-infeasible
-constexpr unsigned kCtlVarCross = 2u;    // a moved variable's bounds cross
-constexpr unsigned kCtlRowCross = 4u;    // a row's bounds cross
-constexpr unsigned kCtlInCross = 8u;     // the incoming bounds cross
+// flag bits of sync[2] (above the round tag of the bound check)
+constexpr unsigned kCtlRoundMask = (1u << 29) - 1u;
+constexpr unsigned kCtlFinalCross = 1u << 29;  // the epilogue's bound check of the last round's moved variables failed
+constexpr unsigned kCtlRowCross = 1u << 30;    // a row's bounds cross        (raised in round 1 only)
+constexpr unsigned kCtlInCross = 1u << 31;     // the incoming bounds cross   (raised before round 1 only)
 
 // one changed candidate of the sparse exchange; the header of a rank's message reuses the layout:
 // j = number of changed candidates (may exceed the capacity: overflow), lb = the rank's row-infeasible flag

@@ -39,6 +39,7 @@ struct BatchIo {
   int32_t *rounds;       // [n_boxes]
   long long *nnz;        // [n_boxes]
   unsigned char *tstate; // [tiles][kTileStateBytes] per-tile control words (global: shared by a cluster)
+  unsigned long long *nl_evals;  // [1] (constraint, box) evaluations of CGraph tapes (chkRed_ and varBoundMods each count one)
 };
 constexpr int kTileStateBytes = 640;
 
@@ -62,10 +63,13 @@ cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub,
 cudaError_t launch_apply_deltas(const long long *delta_ptr, const int32_t *delta_var,
                                 const uint8_t *delta_is_upper, const double *delta_val,
                                 int32_t n_boxes, double2 *boxes, int64_t ld, cudaStream_t stream);
-cudaError_t launch_count_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n,
-                              int32_t n_boxes, long long *mod_count, cudaStream_t stream);
-cudaError_t launch_emit_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n,
-                             int32_t n_boxes, const long long *mod_ptr, long long *cursor, long long cap,
+// mods = final bounds that differ from the box's initial bounds (root + the box's deltas); no copy of the initial boxes
+cudaError_t launch_count_mods(const double2 *boxes, const double *root_lb, const double *root_ub, const long long *delta_ptr,
+                              const int32_t *delta_var, const uint8_t *delta_is_upper, const double *delta_val, int64_t ld,
+                              int32_t n, int32_t n_boxes, long long *mod_count, cudaStream_t stream);
+cudaError_t launch_emit_mods(const double2 *boxes, const double *root_lb, const double *root_ub, const long long *delta_ptr,
+                             const int32_t *delta_var, const uint8_t *delta_is_upper, const double *delta_val, int64_t ld,
+                             int32_t n, int32_t n_boxes, const long long *mod_ptr, long long *cursor, long long cap,
                              int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val, cudaStream_t stream);
 
 }  // namespace mntr

@@ -597,7 +597,7 @@ __device__ __noinline__ void fix_obj_bins(const LinDev &P, double2 *bx, int64_t 
 
 template <class R>
 __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N, double2 *bx, int64_t ld, TileShared &sh,
-                                                bool active, bool &any_change, BatchStage &TS)
+                                                bool active, bool &any_change, BatchStage &TS, unsigned &my_evals)
 {
   const int lane = threadIdx.x & 31;
   const TileTeam team = make_team();
@@ -627,6 +627,7 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
           const ConsView V = batch_constraint(N, TS, B, k, c0 + k);
           if (run && sh.verdict[lane] == 0) {
             const int st = nl_chk_red<R>(V, bx, ld, nlb, nub);
+            ++my_evals;
             if (st != 0) sh.verdict[lane] = st;
           }
         }
@@ -646,6 +647,7 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
           if (run && sh.verdict[lane] == 0) {
             int n_mods = 0; unsigned dummy = 0;
             const int st = nl_var_bound_mods<R>(V, bx, ld, nlb, nub, n_mods, dummy);
+            ++my_evals;
             if (st != 0) sh.verdict[lane] = st;
             else if (n_mods > 0) sh.changed[lane] = 1;
           }
@@ -713,6 +715,7 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
   team.sync();
 
   unsigned long long my_nnz = 0ull;
+  unsigned my_evals = 0u;
   int my_rounds = 0;
   for (int outer = 0;; ++outer) {
     bool lin_changed = false, nl_changed = false;
@@ -721,7 +724,7 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
                                         my_nnz, lin_changed, seg_phase);
     if constexpr (HAS_NL) {
       // the NL instantiation uses the dynamic shared memory for the tape batches (no TMA segments: use_tma == 0)
-      if (nl_enabled) my_rounds += nl_tile_presolve<R>(P, N, bx, ld, sh, active, nl_changed, reinterpret_cast<BatchStage *>(s_seg)[wl]);
+      if (nl_enabled) my_rounds += nl_tile_presolve<R>(P, N, bx, ld, sh, active, nl_changed, reinterpret_cast<BatchStage *>(s_seg)[wl], my_evals);
     }
     // fixpoint mode with both handlers: go round again while the nonlinear sweeps still move bounds
     const bool again = (loop_mode == 0) && lin_enabled && nl_enabled && nl_changed && sh.verdict[lane] == 0 &&
@@ -730,6 +733,10 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
   }
 
   // ---- per-box results ----
+  if constexpr (HAS_NL) {
+    const unsigned ev = __reduce_add_sync(kFull, my_evals);
+    if (lane == 0 && ev != 0u && io.nl_evals != nullptr) atomicAdd(io.nl_evals, (unsigned long long)ev);
+  }
   if (my_nnz) atomicAdd(&sh.nnz[lane], my_nnz);
   team.sync();
   if (warp == 0 && active) {
@@ -818,37 +825,72 @@ __global__ void apply_deltas_kernel(const long long *__restrict__ dptr, const in
   }
 }
 
-// mods of box b = every (variable, side) whose bound differs from the box's initial bound.  A block takes a strip
-// of variables for one tile of 32 boxes (lane = box: coalesced 512-byte segments).
-__global__ void count_mods_kernel(const double2 *__restrict__ boxes, const double2 *__restrict__ boxes0, int64_t ld,
-                                  int n, int n_boxes, long long *mod_count)
+// mods of box b = every (variable, side) whose bound differs from the box's INITIAL bound (root box + the box's
+// deltas, a later delta overriding an earlier one).  No copy of the initial boxes is kept: a block takes a strip of
+// variables for one tile of 32 boxes (lane = box: coalesced 512-byte segments) and compares with the ROOT bound,
+// which is the initial bound everywhere except at the box's own deltas; only where the final bound differs from
+// the root's is the box's (short) delta list searched.  The sides a delta set and the sweep left EQUAL to the
+// root's bound (possible only for a delta that loosens the root) are picked up by the *_delta kernels.
+struct DeltaLists { const long long *ptr; const int32_t *var; const uint8_t *up; const double *val; };
+
+__device__ __forceinline__ double2 initial_bounds(const DeltaLists &D, int b, int j, double2 root)
 {
-  const int b = blockIdx.y * 32 + (threadIdx.x & 31);
-  const int j0 = blockIdx.x * 256 + (threadIdx.x >> 5), j1 = min(n, (blockIdx.x + 1) * 256);
-  int cnt = 0;
-  if (b < n_boxes)
-    for (int j = j0; j < j1; j += blockDim.x >> 5) {
-      const double2 v = boxes[(int64_t)j * ld + b], o = boxes0[(int64_t)j * ld + b];
-      cnt += (v.x != o.x) + (v.y != o.y);
-    }
-  if (cnt) atomicAdd(reinterpret_cast<unsigned long long *>(mod_count + b), (unsigned long long)cnt);
+  double2 init = root;
+  for (long long q = D.ptr[b]; q < D.ptr[b + 1]; ++q)
+    if (D.var[q] == j) { if (D.up[q]) init.y = D.val[q]; else init.x = D.val[q]; }
+  return init;
 }
 
-__global__ void emit_mods_kernel(const double2 *__restrict__ boxes, const double2 *__restrict__ boxes0, int64_t ld,
-                                 int n, int n_boxes, const long long *__restrict__ mod_ptr, long long *cursor,
-                                 long long cap, int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val)
+template <bool EMIT>
+__global__ void mods_kernel(const double2 *__restrict__ boxes, const double *__restrict__ rl, const double *__restrict__ ru,
+                            DeltaLists D, int64_t ld, int n, int n_boxes, long long *mod_count,
+                            const long long *__restrict__ mod_ptr, long long *cursor, long long cap, int32_t *mod_var,
+                            uint8_t *mod_is_upper, double *mod_val)
 {
   const int b = blockIdx.y * 32 + (threadIdx.x & 31);
   const int j0 = blockIdx.x * 256 + (threadIdx.x >> 5), j1 = min(n, (blockIdx.x + 1) * 256);
   if (b >= n_boxes) return;
+  int cnt = 0;
   for (int j = j0; j < j1; j += blockDim.x >> 5) {
-    const double2 v = boxes[(int64_t)j * ld + b], o = boxes0[(int64_t)j * ld + b];
-    const int k = (v.x != o.x) + (v.y != o.y);
+    const double2 v = boxes[(int64_t)j * ld + b];
+    const double2 r = make_double2(__ldg(rl + j), __ldg(ru + j));
+    if (v.x == r.x && v.y == r.y) continue;
+    const double2 o = initial_bounds(D, b, j, r);
+    const bool dl = v.x != r.x && v.x != o.x, du = v.y != r.y && v.y != o.y;
+    const int k = (int)dl + (int)du;
     if (k == 0) continue;
+    if (!EMIT) { cnt += k; continue; }
     long long at = mod_ptr[b] + (long long)atomicAdd(reinterpret_cast<unsigned long long *>(cursor + b), (unsigned long long)k);
-    if (v.x != o.x) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 0; mod_val[at] = v.x; } ++at; }
-    if (v.y != o.y) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 1; mod_val[at] = v.y; } }
+    if (dl) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 0; mod_val[at] = v.x; } ++at; }
+    if (du) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 1; mod_val[at] = v.y; } }
   }
+  if (!EMIT && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(mod_count + b), (unsigned long long)cnt);
+}
+
+// one thread per box: the sides its deltas set whose final bound EQUALS the root's but not the initial one
+template <bool EMIT>
+__global__ void mods_delta_kernel(const double2 *__restrict__ boxes, const double *__restrict__ rl, const double *__restrict__ ru,
+                                  DeltaLists D, int64_t ld, int n_boxes, long long *mod_count,
+                                  const long long *__restrict__ mod_ptr, long long *cursor, long long cap, int32_t *mod_var,
+                                  uint8_t *mod_is_upper, double *mod_val)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_boxes) return;
+  int cnt = 0;
+  for (long long q = D.ptr[b]; q < D.ptr[b + 1]; ++q) {
+    const int j = D.var[q];
+    const bool up = D.up[q] != 0;
+    bool last = true;                 // only the last delta of a (variable, side) defines the initial bound
+    for (long long q2 = q + 1; q2 < D.ptr[b + 1]; ++q2) if (D.var[q2] == j && (D.up[q2] != 0) == up) { last = false; break; }
+    if (!last) continue;
+    const double2 v = boxes[(int64_t)j * ld + b];
+    const double fin = up ? v.y : v.x, root = up ? ru[j] : rl[j];
+    if (fin != root || fin == D.val[q]) continue;
+    if (!EMIT) { ++cnt; continue; }
+    const long long at = mod_ptr[b] + (long long)atomicAdd(reinterpret_cast<unsigned long long *>(cursor + b), 1ull);
+    if (at < cap) { mod_var[at] = j; mod_is_upper[at] = up ? 1 : 0; mod_val[at] = fin; }
+  }
+  if (!EMIT && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(mod_count + b), (unsigned long long)cnt);
 }
 
 }  // namespace
@@ -939,23 +981,32 @@ cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub,
   return cudaGetLastError();
 }
 
-cudaError_t launch_count_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n, int32_t n_boxes,
-                              long long *mod_count, cudaStream_t stream)
+cudaError_t launch_count_mods(const double2 *boxes, const double *root_lb, const double *root_ub, const long long *delta_ptr,
+                              const int32_t *delta_var, const uint8_t *delta_is_upper, const double *delta_val, int64_t ld,
+                              int32_t n, int32_t n_boxes, long long *mod_count, cudaStream_t stream)
 {
   if (n <= 0 || n_boxes <= 0) return cudaSuccess;
+  const DeltaLists D{delta_ptr, delta_var, delta_is_upper, delta_val};
   dim3 grid((n + 255) / 256, (n_boxes + 31) / 32);
-  count_mods_kernel<<<grid, 256, 0, stream>>>(boxes, boxes0, ld, n, n_boxes, mod_count);
+  mods_kernel<false><<<grid, 256, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n, n_boxes, mod_count, nullptr, nullptr, 0,
+                                               nullptr, nullptr, nullptr);
+  mods_delta_kernel<false><<<(n_boxes + 127) / 128, 128, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n_boxes, mod_count, nullptr,
+                                                                     nullptr, 0, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 
-cudaError_t launch_emit_mods(const double2 *boxes, const double2 *boxes0, int64_t ld, int32_t n, int32_t n_boxes,
-                             const long long *mod_ptr, long long *cursor, long long cap, int32_t *mod_var,
-                             uint8_t *mod_is_upper, double *mod_val, cudaStream_t stream)
+cudaError_t launch_emit_mods(const double2 *boxes, const double *root_lb, const double *root_ub, const long long *delta_ptr,
+                             const int32_t *delta_var, const uint8_t *delta_is_upper, const double *delta_val, int64_t ld,
+                             int32_t n, int32_t n_boxes, const long long *mod_ptr, long long *cursor, long long cap,
+                             int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val, cudaStream_t stream)
 {
   if (n <= 0 || n_boxes <= 0) return cudaSuccess;
+  const DeltaLists D{delta_ptr, delta_var, delta_is_upper, delta_val};
   dim3 grid((n + 255) / 256, (n_boxes + 31) / 32);
-  emit_mods_kernel<<<grid, 256, 0, stream>>>(boxes, boxes0, ld, n, n_boxes, mod_ptr, cursor, cap, mod_var, mod_is_upper,
-                                             mod_val);
+  mods_kernel<true><<<grid, 256, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n, n_boxes, nullptr, mod_ptr, cursor, cap, mod_var,
+                                              mod_is_upper, mod_val);
+  mods_delta_kernel<true><<<(n_boxes + 127) / 128, 128, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n_boxes, nullptr, mod_ptr,
+                                                                    cursor, cap, mod_var, mod_is_upper, mod_val);
   return cudaGetLastError();
 }
 

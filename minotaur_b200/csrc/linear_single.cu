@@ -56,7 +56,7 @@ __device__ __forceinline__ uint4 ld_acquire_gpu_v4(const unsigned *p)
   return v;
 }
 __device__ __forceinline__ void grid_barrier(unsigned *sync, unsigned n_blocks, unsigned &target, unsigned *s_ctl,
-                                             unsigned long long *arrive)
+                                             unsigned long long *arrive, unsigned stress_ns = 0u)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -64,6 +64,12 @@ __device__ __forceinline__ void grid_barrier(unsigned *sync, unsigned n_blocks, 
     target += n_blocks;
     __threadfence();
     atomicAdd(sync, 1u);
+    // test hook (MNTR_GPU_STRESS_BARRIER): one block takes its snapshot long after the others have gone on into the
+    // next round and written its state into the same line -- the round tags must make that harmless
+    if (stress_ns != 0u && blockIdx.x == 1) {
+      const unsigned long long t0 = globaltimer_ns();
+      while (globaltimer_ns() - t0 < stress_ns) __nanosleep(1000);
+    }
     uint4 v;
     do { v = ld_acquire_gpu_v4(sync); } while (v.x < target);
     *reinterpret_cast<uint4 *>(s_ctl) = v;
@@ -189,7 +195,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
       if (in) { b = make_double2(lb_io[j], ub_io[j]); ty = __ldg(P.var_type + j); }
       take(j0, j, in, b, ty);
     }
-    if (cross0) atomicOr(W.sync + 3, kCtlInCross);
+    if (cross0) atomicOr(W.sync + 2, kCtlInCross);
   }
   MNTR_TRACE();
   grid_barrier(W.sync, gridDim.x, bar_target, s_ctl, nullptr);
@@ -285,7 +291,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
           const unsigned word = wb == fw0 ? fw : ((w < fw1) ? __ldcg(Tp + w) : 0u);
           if (word) { Tp[w] = 0u; atomicOr(W.ever + w, word); }
           my_changes += __popc(word);
-          for_each_marked(word, wb, lane, [&](int j) { flag_rows_serial(P, j, W.due[0]); atomicMax(W.sync + 1, 1u); });
+          for_each_marked(word, wb, lane, [&](int j) { flag_rows_serial(P, j, W.due[0]); atomicMax(W.sync + 1, 2u); });
         }
       } else {
         if (fj >= 0) fix(fj, fv, fty);
@@ -300,28 +306,32 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
           for_each_marked(word, wb, lane, [&](int j) { fix(j, __ldcg(A + j), __ldg(P.var_type + j)); });
         }
       }
-      if (bad) atomicOr(W.sync + 3, kCtlVarCross);
+      if (bad) atomicMax(W.sync + 2, (unsigned)round);      // round-tagged: see SingleWs::sync
     }
     if (W.trace != nullptr && round < 16 && lane == 0) atomicMax(W.trace + kTraceBlk + (blockIdx.x * 16 + round) * 8 + 6, globaltimer_ns());
     MNTR_TRACE();
     grid_barrier(W.sync, gridDim.x, bar_target, s_ctl,
-                 (W.trace != nullptr && round < 16) ? W.trace + 64 + blockIdx.x * 16 + round : nullptr);
+                 (W.trace != nullptr && round < 16) ? W.trace + 64 + blockIdx.x * 16 + round : nullptr, W.stress_ns);
     MNTR_TRACE();
 
-    const unsigned ctl_flags = s_ctl[3];
-    if (ctl_flags & kCtlVarCross) {                      // the box this round read was already crossed: found after round-1
+    // Decisions about round `round` from the snapshot.  A faster block may already be in round + 1 and have written
+    // that round's tags into the line before this block's poller took the snapshot: every test below gives the same
+    // answer in that case (a later tag proves that the loop went on after this round).
+    const unsigned ctl_flags = s_ctl[2];
+    if ((ctl_flags & kCtlRoundMask) == (unsigned)round) {   // the box this round read was already crossed: found after round-1
       verdict = 1; rounds_out = round - 1; out_buf = cur; out_round = true;
       break;
     }
     rounds_out = round;
-    if (ctl_flags & kCtlRowInf) {                      // activity-infeasible row: the box of the round start is handed back
+    if (s_ctl[3] == (unsigned)round) {                 // activity-infeasible row: the box of the round start is handed back
       verdict = 2 /* MNTR_INFEAS_ROW */; out_buf = cur; out_round = round > 1;
       break;
     }
     out_buf = cur ^ 1; out_round = true;
     if (round == 1 && (ctl_flags & (kCtlRowCross | kCtlInCross))) { verdict = 1; break; }    // checkBounds_ after round 1
-    const bool any_changed = s_ctl[1] == (unsigned)round;
-    const bool any_int = s_ctl[2] == (unsigned)round;
+    const unsigned moved_tag = s_ctl[1];
+    const bool any_changed = (moved_tag >> 1) >= (unsigned)round;
+    const bool any_int = (moved_tag >> 1) > (unsigned)round || ((moved_tag >> 1) == (unsigned)round && (moved_tag & 1u));
     if (!any_changed) break;
     final_check = true;
     if (max_rounds > 0 && round >= max_rounds) break;
@@ -351,7 +361,7 @@ fbbt_single_jacobi_kernel(LinDev P, SingleWs W, double *lb_io, double *ub_io, in
         if (b.x > b.y + kETol) bad = 1;            // bound check of what the last round moved (no fix-up follows)
       });
     }
-    if (bad && final_check) atomicOr(W.sync + 3, kCtlVarCross);
+    if (bad && final_check) atomicOr(W.sync + 2, kCtlFinalCross);
   }
   __shared__ unsigned long long s_nnz, s_rows;
   __shared__ int s_changes;

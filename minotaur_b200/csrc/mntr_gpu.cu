@@ -6,7 +6,6 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -24,12 +23,22 @@
 
 using namespace mntr;
 
+// The handful of NCCL declarations this file needs, spelled out so that the module builds without NCCL's headers
+// (the library itself is bound at run time with dlopen, see nccl_api()).  Values are NCCL 2.x's stable ABI (nccl.h).
+extern "C" {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclChar = 0, ncclUint64 = 5, ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+}
+
 // host mirror of the single-box kernel's control block (SingleWs::ring/status/counters/bar)
 constexpr int kTraceWords = 64 + 256 * 16 + 256 * 16 * 8;   // MNTR_GPU_TRACE buffer: phases, one warp's passes, barrier arrivals
 struct SingleCtrl {
   unsigned sync[4]; int32_t status[8]; unsigned long long counters[2]; unsigned done; unsigned pad[15];
   // the loop's verdict, or MNTR_INFEAS_BOUNDS when the bound check of the last round's moved variables failed
-  int verdict() const { return status[6] ? status[6] : ((sync[3] & mntr::kCtlVarCross) ? 1 : 0); }
+  int verdict() const { return status[6] ? status[6] : ((sync[2] & mntr::kCtlFinalCross) ? 1 : 0); }
 };
 static_assert(sizeof(SingleCtrl) == 128, "control block layout");
 
@@ -68,6 +77,7 @@ struct mntr_gpu_ctx {
   unsigned char *d_tstate = nullptr;
   int32_t *d_verdict = nullptr, *d_rounds = nullptr;
   long long *d_nnzb = nullptr;
+  unsigned long long *d_nl_evals = nullptr;   // [1] CGraph evaluations of the last batch call
   double *d_stage_lb = nullptr, *d_stage_ub = nullptr;
   int64_t stage_boxes = 0;
 
@@ -177,7 +187,8 @@ void free_stage(mntr_gpu_ctx *c)
 void free_batch(mntr_gpu_ctx *c)
 {
   cudaFree(c->d_boxes); cudaFree(c->d_rowflag); cudaFree(c->d_varflag); cudaFree(c->d_tstate); cudaFree(c->d_verdict); cudaFree(c->d_rounds);
-  cudaFree(c->d_nnzb);
+  cudaFree(c->d_nnzb); cudaFree(c->d_nl_evals);
+  c->d_nl_evals = nullptr;
   c->d_boxes = nullptr; c->d_rowflag = nullptr; c->d_verdict = nullptr; c->d_rounds = nullptr;
   c->d_nnzb = nullptr; c->d_varflag = nullptr; c->d_tstate = nullptr;
   c->batch_ld = 0;
@@ -197,6 +208,7 @@ int ensure_batch(mntr_gpu_ctx *ctx, int32_t n_boxes, bool need_boxes)
   CU(cudaMalloc((void **)&ctx->d_verdict, sizeof(int32_t) * (size_t)ld));
   CU(cudaMalloc((void **)&ctx->d_rounds, sizeof(int32_t) * (size_t)ld));
   CU(cudaMalloc((void **)&ctx->d_nnzb, sizeof(long long) * (size_t)ld));
+  CU(cudaMalloc((void **)&ctx->d_nl_evals, sizeof(unsigned long long)));
   ctx->batch_ld = ld;
   return MNTR_OK;
 }
@@ -444,6 +456,8 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   }
   ctx->ctrl_clean = false;
   W.trace = nullptr;
+  W.stress_ns = 0u;
+  if (const char *sb = getenv("MNTR_GPU_STRESS_BARRIER")) W.stress_ns = (unsigned)atoi(sb);   // test hook, see grid_barrier
   if (const char *tr = getenv("MNTR_GPU_TRACE")) {
     if (tr[0] == '1') { if ((rc = dalloc((void **)&W.trace, kTraceWords * sizeof(unsigned long long)))) return rc; }
   }
@@ -952,6 +966,9 @@ int mntr_gpu_tighten_dev(mntr_gpu_ctx *ctx, int32_t n_boxes, void *boxes_dev, co
   const mntr_gpu_options o = resolve_opts(opts, n_boxes > 1 ? n_boxes : 2);
   if (o.order != MNTR_ORDER_REFERENCE)
     return fail(ctx, MNTR_E_UNSUPPORTED, "tighten_dev: device-resident boxes use MNTR_ORDER_REFERENCE");
+  if (o.rounding != MNTR_ROUND_DIRECTED && o.rounding != MNTR_ROUND_NEAREST) return fail(ctx, MNTR_E_ARG, "tighten_dev: bad rounding");
+  if (o.loop != MNTR_LOOP_FIXPOINT && o.loop != MNTR_LOOP_SIMPLEPRESOLVE) return fail(ctx, MNTR_E_ARG, "tighten_dev: bad loop mode");
+  if (o.handlers < 0 || o.handlers > 2) return fail(ctx, MNTR_E_ARG, "tighten_dev: bad handlers");
   const int64_t ld = mntr_gpu_box_ld(n_boxes);
   const int64_t tiles = ld / 32;
   // row flags are sized for the context's batch capacity
@@ -959,16 +976,20 @@ int mntr_gpu_tighten_dev(mntr_gpu_ctx *ctx, int32_t n_boxes, void *boxes_dev, co
   if (rc) return rc;
   BatchIo io;
   io.boxes = (double2 *)boxes_dev; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
-  io.verdict = verdict_dev; io.rounds = rounds_dev; io.nnz = (long long *)nnz_dev;
+  io.verdict = verdict_dev; io.rounds = rounds_dev; io.nnz = (long long *)nnz_dev; io.nl_evals = ctx->d_nl_evals;
   (void)tiles;
+  CU(cudaMemsetAsync(ctx->d_nl_evals, 0, sizeof(unsigned long long), ctx->stream));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
                             o.loop, o.max_rounds, o.handlers != MNTR_HANDLERS_NONLINEAR,
                             (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR) ? 1 : 0, ctx->sm_count, ctx->stream));
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  unsigned long long evals = 0;
+  CU(cudaMemcpyAsync(&evals, ctx->d_nl_evals, sizeof(evals), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->stats = mntr_gpu_stats{};
   ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  ctx->stats.nl_evals = (int64_t)evals;
   return MNTR_OK;
 }
 
@@ -1005,7 +1026,8 @@ int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
   if ((rc = mntr_gpu_boxes_upload(ctx, n_boxes, lb, ub, ctx->d_boxes))) return rc;
   BatchIo io;
   io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
-  io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb;
+  io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb; io.nl_evals = ctx->d_nl_evals;
+  CU(cudaMemsetAsync(ctx->d_nl_evals, 0, sizeof(unsigned long long), ctx->stream));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
                             o.loop, o.max_rounds, o.handlers != MNTR_HANDLERS_NONLINEAR,
@@ -1017,8 +1039,11 @@ int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
   CU(cudaMemcpyAsync(hv.data(), ctx->d_verdict, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(hr.data(), ctx->d_rounds, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(hn.data(), ctx->d_nnzb, sizeof(long long) * (size_t)n_boxes, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long evals = 0;
+  CU(cudaMemcpyAsync(&evals, ctx->d_nl_evals, sizeof(evals), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.nl_evals = (int64_t)evals;
   for (int32_t b = 0; b < n_boxes; ++b) {
     if (verdict) verdict[b] = hv[b];
     if (rounds) rounds[b] = hr[b];
@@ -1033,6 +1058,111 @@ int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
   return MNTR_OK;
 }
 
+// ---- node batches given as branching deltas on a common root box ----
+namespace {
+
+// device copies of a root box and the boxes' delta lists
+struct DeviceDeltas {
+  double *rl = nullptr, *ru = nullptr, *val = nullptr;
+  long long *ptr = nullptr;
+  int32_t *var = nullptr;
+  uint8_t *up = nullptr;
+};
+
+int check_deltas(mntr_gpu_ctx *ctx, const char *who, int32_t n_boxes, const double *root_lb, const double *root_ub,
+                 const int64_t *delta_ptr, const int32_t *delta_var, const uint8_t *delta_is_upper, const double *delta_val)
+{
+  if (n_boxes <= 0 || !root_lb || !root_ub || !delta_ptr) return fail(ctx, MNTR_E_ARG, "%s: bad argument", who);
+  const int64_t n_delta = delta_ptr[n_boxes];
+  if (delta_ptr[0] != 0 || n_delta < 0 || (n_delta > 0 && (!delta_var || !delta_is_upper || !delta_val)))
+    return fail(ctx, MNTR_E_ARG, "%s: bad delta lists", who);
+  for (int32_t b = 0; b < n_boxes; ++b)
+    if (delta_ptr[b + 1] < delta_ptr[b]) return fail(ctx, MNTR_E_ARG, "%s: delta_ptr not monotone at box %d", who, b);
+  for (int64_t q = 0; q < n_delta; ++q)
+    if (delta_var[q] < 0 || delta_var[q] >= ctx->n) return fail(ctx, MNTR_E_ARG, "%s: delta variable %d out of range", who, delta_var[q]);
+  return MNTR_OK;
+}
+
+// uploads root + deltas (device scratch appended to `scratch`) and builds the boxes in the engine's layout
+int boxes_from_deltas(mntr_gpu_ctx *ctx, std::vector<void *> &scratch, int32_t n_boxes, const double *root_lb,
+                      const double *root_ub, const int64_t *delta_ptr, const int32_t *delta_var,
+                      const uint8_t *delta_is_upper, const double *delta_val, double2 *boxes, DeviceDeltas &D)
+{
+  const int32_t n = ctx->n;
+  const int64_t n_delta = delta_ptr[n_boxes], ld = mntr_gpu_box_ld(n_boxes);
+  auto dalloc = [&](void **p, size_t bytes) -> int {
+    if (cudaMalloc(p, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return fail(ctx, MNTR_E_NOMEM, "node batch: out of device memory");
+    }
+    scratch.push_back(*p);
+    return MNTR_OK;
+  };
+  int rc;
+  if ((rc = dalloc((void **)&D.rl, sizeof(double) * (size_t)n))) return rc;
+  if ((rc = dalloc((void **)&D.ru, sizeof(double) * (size_t)n))) return rc;
+  if ((rc = dalloc((void **)&D.ptr, sizeof(long long) * ((size_t)n_boxes + 1)))) return rc;
+  if ((rc = dalloc((void **)&D.var, sizeof(int32_t) * (size_t)n_delta))) return rc;
+  if ((rc = dalloc((void **)&D.up, (size_t)n_delta))) return rc;
+  if ((rc = dalloc((void **)&D.val, sizeof(double) * (size_t)n_delta))) return rc;
+  static_assert(sizeof(long long) == sizeof(int64_t), "delta_ptr / mod_ptr are copied as long long");
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(D.rl, root_lb, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(D.ru, root_ub, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(D.ptr, delta_ptr, sizeof(long long) * ((size_t)n_boxes + 1), cudaMemcpyHostToDevice, s));
+  if (n_delta > 0) {
+    CU(cudaMemcpyAsync(D.var, delta_var, sizeof(int32_t) * (size_t)n_delta, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(D.up, delta_is_upper, (size_t)n_delta, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(D.val, delta_val, sizeof(double) * (size_t)n_delta, cudaMemcpyHostToDevice, s));
+  }
+  CU(launch_boxes_from_root(D.rl, D.ru, n, n_boxes, boxes, ld, s));
+  CU(launch_apply_deltas(D.ptr, D.var, D.up, D.val, n_boxes, boxes, ld, s));
+  return MNTR_OK;
+}
+
+}  // namespace
+
+int mntr_gpu_boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *root_lb, const double *root_ub,
+                               const int64_t *delta_ptr, const int32_t *delta_var, const uint8_t *delta_is_upper,
+                               const double *delta_val, void *boxes_dev)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "boxes_from_deltas: no problem loaded");
+  if (!boxes_dev) return fail(ctx, MNTR_E_ARG, "boxes_from_deltas: null boxes");
+  int rc = check_deltas(ctx, "boxes_from_deltas", n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  std::vector<void *> scratch;
+  DeviceDeltas D;
+  rc = boxes_from_deltas(ctx, scratch, n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val,
+                         (double2 *)boxes_dev, D);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  free_all(scratch);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, MNTR_E_CUDA, "boxes_from_deltas: %s", cudaGetErrorString(e));
+  return MNTR_OK;
+}
+
+void *mntr_gpu_alloc_host(mntr_gpu_ctx *ctx, int64_t bytes)
+{
+  if (!ctx || bytes <= 0) return nullptr;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    (void)cudaGetLastError();
+    fail(ctx, MNTR_E_NOMEM, "alloc_host: cudaHostAlloc of %lld bytes failed", (long long)bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+void mntr_gpu_free_host(mntr_gpu_ctx *ctx, void *p)
+{
+  if (!p) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (cudaFreeHost(p) != cudaSuccess) (void)cudaGetLastError();
+}
+
 // Node batch given as branching deltas on a common root box; results as the VarBoundMod tuples to emit.
 int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *root_lb, const double *root_ub,
                            const int64_t *delta_ptr, const int32_t *delta_var, const uint8_t *delta_is_upper,
@@ -1042,16 +1172,10 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
 {
   if (!ctx) return MNTR_E_ARG;
   if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "tighten_nodes: no problem loaded");
-  if (n_boxes <= 0 || !root_lb || !root_ub || !delta_ptr || !mod_ptr || mod_cap < 0 ||
-      (mod_cap > 0 && (!mod_var || !mod_is_upper || !mod_val)))
+  if (!mod_ptr || mod_cap < 0 || (mod_cap > 0 && (!mod_var || !mod_is_upper || !mod_val)))
     return fail(ctx, MNTR_E_ARG, "tighten_nodes: bad argument");
-  const int64_t n_delta = delta_ptr[n_boxes];
-  if (delta_ptr[0] != 0 || n_delta < 0 || (n_delta > 0 && (!delta_var || !delta_is_upper || !delta_val)))
-    return fail(ctx, MNTR_E_ARG, "tighten_nodes: bad delta lists");
-  for (int32_t b = 0; b < n_boxes; ++b)
-    if (delta_ptr[b + 1] < delta_ptr[b]) return fail(ctx, MNTR_E_ARG, "tighten_nodes: delta_ptr not monotone at box %d", b);
-  for (int64_t q = 0; q < n_delta; ++q)
-    if (delta_var[q] < 0 || delta_var[q] >= ctx->n) return fail(ctx, MNTR_E_ARG, "tighten_nodes: delta variable %d out of range", delta_var[q]);
+  int rc = check_deltas(ctx, "tighten_nodes", n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val);
+  if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
   mntr_gpu_options o = resolve_opts(opts, n_boxes);
   o.order = MNTR_ORDER_REFERENCE;      // a node batch always runs the reference-order kernel
@@ -1060,11 +1184,10 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
   if (o.handlers < 0 || o.handlers > 2) return fail(ctx, MNTR_E_ARG, "tighten_nodes: bad handlers");
   ctx->stats = mntr_gpu_stats{};
   const int32_t n = ctx->n;
-  int rc = ensure_batch(ctx, n_boxes, true);
-  if (rc) return rc;
+  if ((rc = ensure_batch(ctx, n_boxes, true))) return rc;
   const int64_t ld = mntr_gpu_box_ld(n_boxes);
 
-  // device scratch of this call: the initial boxes, root, deltas, mod counts / offsets / tuples
+  // device scratch of this call: root, deltas, mod counts / offsets / tuples
   std::vector<void *> scratch;
   auto dalloc = [&](void **p, size_t bytes) -> int {
     if (cudaMalloc(p, std::max<size_t>(bytes, 16)) != cudaSuccess) {
@@ -1074,41 +1197,26 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
     scratch.push_back(*p);
     return MNTR_OK;
   };
-  double2 *boxes0 = nullptr; double *d_rl = nullptr, *d_ru = nullptr, *d_dval = nullptr, *d_mval = nullptr;
-  long long *d_dptr = nullptr, *d_cnt = nullptr, *d_mptr = nullptr, *d_cur = nullptr;
-  int32_t *d_dvar = nullptr, *d_mvar = nullptr; uint8_t *d_dup = nullptr, *d_mup = nullptr;
-  if ((rc = dalloc((void **)&boxes0, sizeof(double2) * (size_t)n * (size_t)ld))) return rc;
-  if ((rc = dalloc((void **)&d_rl, sizeof(double) * (size_t)n))) return rc;
-  if ((rc = dalloc((void **)&d_ru, sizeof(double) * (size_t)n))) return rc;
-  if ((rc = dalloc((void **)&d_dptr, sizeof(long long) * ((size_t)n_boxes + 1)))) return rc;
-  if ((rc = dalloc((void **)&d_dvar, sizeof(int32_t) * (size_t)n_delta))) return rc;
-  if ((rc = dalloc((void **)&d_dup, (size_t)n_delta))) return rc;
-  if ((rc = dalloc((void **)&d_dval, sizeof(double) * (size_t)n_delta))) return rc;
+  auto done = [&](int code) { free_all(scratch); return code; };
+#define CUN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_all(scratch); return fail(ctx, MNTR_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  cudaStream_t s = ctx->stream;
+  CUN(cudaEventRecord(ctx->ev[0], s));
+  DeviceDeltas D;
+  if ((rc = boxes_from_deltas(ctx, scratch, n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val,
+                              ctx->d_boxes, D))) return done(rc);
+  double *d_mval = nullptr;
+  long long *d_cnt = nullptr, *d_mptr = nullptr, *d_cur = nullptr;
+  int32_t *d_mvar = nullptr; uint8_t *d_mup = nullptr;
   if ((rc = dalloc((void **)&d_cnt, sizeof(long long) * (size_t)n_boxes))) return rc;
   if ((rc = dalloc((void **)&d_mptr, sizeof(long long) * ((size_t)n_boxes + 1)))) return rc;
   if ((rc = dalloc((void **)&d_cur, sizeof(long long) * (size_t)n_boxes))) return rc;
   if ((rc = dalloc((void **)&d_mvar, sizeof(int32_t) * (size_t)mod_cap))) return rc;
   if ((rc = dalloc((void **)&d_mup, (size_t)mod_cap))) return rc;
   if ((rc = dalloc((void **)&d_mval, sizeof(double) * (size_t)mod_cap))) return rc;
-  auto done = [&](int code) { free_all(scratch); return code; };
-#define CUN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_all(scratch); return fail(ctx, MNTR_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
-  static_assert(sizeof(long long) == sizeof(int64_t), "delta_ptr / mod_ptr are copied as long long");
-  cudaStream_t s = ctx->stream;
-  CUN(cudaEventRecord(ctx->ev[0], s));
-  CUN(cudaMemcpyAsync(d_rl, root_lb, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
-  CUN(cudaMemcpyAsync(d_ru, root_ub, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
-  CUN(cudaMemcpyAsync(d_dptr, delta_ptr, sizeof(long long) * ((size_t)n_boxes + 1), cudaMemcpyHostToDevice, s));
-  if (n_delta > 0) {
-    CUN(cudaMemcpyAsync(d_dvar, delta_var, sizeof(int32_t) * (size_t)n_delta, cudaMemcpyHostToDevice, s));
-    CUN(cudaMemcpyAsync(d_dup, delta_is_upper, (size_t)n_delta, cudaMemcpyHostToDevice, s));
-    CUN(cudaMemcpyAsync(d_dval, delta_val, sizeof(double) * (size_t)n_delta, cudaMemcpyHostToDevice, s));
-  }
-  CUN(launch_boxes_from_root(d_rl, d_ru, n, n_boxes, ctx->d_boxes, ld, s));
-  CUN(launch_apply_deltas(d_dptr, d_dvar, d_dup, d_dval, n_boxes, ctx->d_boxes, ld, s));
-  CUN(cudaMemcpyAsync(boxes0, ctx->d_boxes, sizeof(double2) * (size_t)n * (size_t)ld, cudaMemcpyDeviceToDevice, s));
   BatchIo io;
   io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
-  io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb;
+  io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb; io.nl_evals = ctx->d_nl_evals;
+  CUN(cudaMemsetAsync(ctx->d_nl_evals, 0, sizeof(unsigned long long), s));
   CUN(cudaEventRecord(ctx->ev[1], s));
   CUN(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
                              o.loop, o.max_rounds, o.handlers != MNTR_HANDLERS_NONLINEAR,
@@ -1117,13 +1225,17 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
   // mods: count per box, offsets on the host (n_boxes numbers), then emit
   CUN(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * (size_t)n_boxes, s));
   CUN(cudaMemsetAsync(d_cur, 0, sizeof(long long) * (size_t)n_boxes, s));
-  CUN(launch_count_mods(ctx->d_boxes, boxes0, ld, n, n_boxes, d_cnt, s));
-  std::vector<long long> cnt((size_t)n_boxes), ptr((size_t)n_boxes + 1, 0);
+  CUN(launch_count_mods(ctx->d_boxes, D.rl, D.ru, D.ptr, D.var, D.up, D.val, ld, n, n_boxes, d_cnt, s));
+  std::vector<long long> cnt((size_t)n_boxes), ptr((size_t)n_boxes + 1, 0), hz((size_t)n_boxes);
   std::vector<int32_t> hv((size_t)n_boxes), hr((size_t)n_boxes);
   CUN(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(long long) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
   CUN(cudaMemcpyAsync(hv.data(), ctx->d_verdict, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
   CUN(cudaMemcpyAsync(hr.data(), ctx->d_rounds, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  CUN(cudaMemcpyAsync(hz.data(), ctx->d_nnzb, sizeof(long long) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  unsigned long long evals = 0;
+  CUN(cudaMemcpyAsync(&evals, ctx->d_nl_evals, sizeof(evals), cudaMemcpyDeviceToHost, s));
   CUN(cudaStreamSynchronize(s));
+  ctx->stats.nl_evals = (int64_t)evals;
   // an infeasible box reports no mods (the node is pruned; its box is not meaningful)
   for (int32_t b = 0; b < n_boxes; ++b) ptr[(size_t)b + 1] = ptr[(size_t)b] + (hv[(size_t)b] == MNTR_FEASIBLE ? cnt[(size_t)b] : 0);
   const long long total = ptr[(size_t)n_boxes];
@@ -1137,7 +1249,8 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
     for (int32_t b = 0; b < n_boxes; ++b) if (hv[(size_t)b] != MNTR_FEASIBLE) cur[(size_t)b] = (long long)1 << 60;
     CUN(cudaMemcpyAsync(d_cur, cur.data(), sizeof(long long) * (size_t)n_boxes, cudaMemcpyHostToDevice, s));
     CUN(cudaMemcpyAsync(d_mptr, ptr.data(), sizeof(long long) * ((size_t)n_boxes + 1), cudaMemcpyHostToDevice, s));
-    CUN(launch_emit_mods(ctx->d_boxes, boxes0, ld, n, n_boxes, d_mptr, d_cur, (long long)mod_cap, d_mvar, d_mup, d_mval, s));
+    CUN(launch_emit_mods(ctx->d_boxes, D.rl, D.ru, D.ptr, D.var, D.up, D.val, ld, n, n_boxes, d_mptr, d_cur, (long long)mod_cap,
+                         d_mvar, d_mup, d_mval, s));
     CUN(cudaMemcpyAsync(mod_var, d_mvar, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
     CUN(cudaMemcpyAsync(mod_is_upper, d_mup, (size_t)total, cudaMemcpyDeviceToHost, s));
     CUN(cudaMemcpyAsync(mod_val, d_mval, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, s));
@@ -1165,6 +1278,7 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
   ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
   ctx->stats.d2h_ms = elapsed(ctx->ev[2], ctx->ev[3]);
   for (int32_t b = 0; b < n_boxes; ++b) {
+    ctx->stats.nnz_updates += hz[(size_t)b];
     ctx->stats.n_infeasible += hv[(size_t)b] != MNTR_FEASIBLE;
     ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, hr[(size_t)b]);
   }

@@ -186,20 +186,22 @@ struct SinkFix {
   __device__ __forceinline__ void int_moved() const
   {
     FixRound *w = const_cast<FixRound *>(rc);
-    if (w->seen_int != round && atomicExch(&w->seen_int, round) != round) atomicMax(rc->sync + 2, round);
+    if (w->seen_int != round && atomicExch(&w->seen_int, round) != round) atomicMax(rc->sync + 1, 2u * round + 1u);
   }
   __device__ __forceinline__ void changed() const
   {
     FixRound *w = const_cast<FixRound *>(rc);
-    if (w->seen_changed != round && atomicExch(&w->seen_changed, round) != round) atomicMax(rc->sync + 1, round);
+    if (w->seen_changed != round && atomicExch(&w->seen_changed, round) != round) atomicMax(rc->sync + 1, 2u * round);
   }
   __device__ __forceinline__ void touch(int j, bool isint) const
   {
     atomicOr(rc->touched + (j >> 5), 1u << (j & 31));
     if (isint) int_moved();      // nintmods, :1070-1133
   }
-  __device__ __forceinline__ void row_infeasible() const { atomicOr(rc->sync + 3, kCtlRowInf); }
-  __device__ __forceinline__ void row_bounds_cross() const { atomicOr(rc->sync + 3, kCtlRowCross); }
+  // round-tagged (see SingleWs::sync): a block that is already in round r+1 can never make a block that is still
+  // taking its snapshot of barrier r believe that round r found an infeasible row
+  __device__ __forceinline__ void row_infeasible() const { atomicMax(rc->sync + 3, round); }
+  __device__ __forceinline__ void row_bounds_cross() const { atomicOr(rc->sync + 2, kCtlRowCross); }
   // no room for `room` more entries?
   template <class Stage> __device__ __forceinline__ bool near_full(const Stage &S, int room = 32) const { return S.tcount + room > Stage::kListCap; }
 

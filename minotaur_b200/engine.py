@@ -44,6 +44,10 @@ ABI_SYMBOLS = [
     "mntr_gpu_boxes_upload", "mntr_gpu_boxes_download", "mntr_gpu_get_stats",
     "mntr_gpu_tighten_single_dev", "mntr_gpu_stream",
     "mntr_gpu_nccl_unique_id", "mntr_gpu_comm_init", "mntr_gpu_comm_destroy",
+    "mntr_gpu_boxes_from_deltas", "mntr_gpu_alloc_host", "mntr_gpu_free_host",
+    "mntr_gpu_group_create", "mntr_gpu_group_destroy", "mntr_gpu_group_size", "mntr_gpu_group_member",
+    "mntr_gpu_group_last_error", "mntr_gpu_group_load_linear", "mntr_gpu_group_load_cgraph",
+    "mntr_gpu_group_set_cutoff", "mntr_gpu_group_set_incumbent", "mntr_gpu_group_tighten_nodes",
 ]
 
 
@@ -56,7 +60,7 @@ class GpuStats(C.Structure):
     _fields_ = [("nnz_updates", C.c_int64), ("rows_evaluated", C.c_int64), ("n_infeasible", C.c_int64),
                 ("n_changes", C.c_int64), ("max_rounds", C.c_int32), ("sparse_rounds", C.c_int32), ("kernel_ms", C.c_double),
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("comm_ms", C.c_double), ("rows_ms", C.c_double),
-                ("vars_ms", C.c_double)]
+                ("vars_ms", C.c_double), ("nl_evals", C.c_int64)]
 
 
 class EngineError(RuntimeError):
@@ -100,6 +104,25 @@ def load_library() -> C.CDLL:
     L.mntr_gpu_nccl_unique_id.argtypes = [vp]
     L.mntr_gpu_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.mntr_gpu_comm_destroy.argtypes = [vp]
+    L.mntr_gpu_boxes_from_deltas.argtypes = [vp, C.c_int32, _dp, _dp, _lp, _ip, _bp, _dp, vp]
+    L.mntr_gpu_alloc_host.argtypes = [vp, C.c_int64]
+    L.mntr_gpu_alloc_host.restype = vp
+    L.mntr_gpu_free_host.argtypes = [vp, vp]
+    L.mntr_gpu_free_host.restype = None
+    L.mntr_gpu_group_create.argtypes = [C.c_int32, _ip, C.POINTER(vp)]
+    L.mntr_gpu_group_destroy.argtypes = [vp]
+    L.mntr_gpu_group_destroy.restype = None
+    L.mntr_gpu_group_size.argtypes = [vp]
+    L.mntr_gpu_group_member.argtypes = [vp, C.c_int32]
+    L.mntr_gpu_group_member.restype = vp
+    L.mntr_gpu_group_last_error.argtypes = [vp]
+    L.mntr_gpu_group_last_error.restype = C.c_char_p
+    L.mntr_gpu_group_load_linear.argtypes = [vp, C.c_int32, C.c_int32, _ip, _ip, _dp, _dp, _dp, _bp, _bp]
+    L.mntr_gpu_group_load_cgraph.argtypes = [vp, C.c_int32, _ip, _bp, _ip, _ip, _dp, _ip, _ip, _ip, _dp, _dp, _dp]
+    L.mntr_gpu_group_set_cutoff.argtypes = [vp, C.c_int32, _ip, _dp, C.c_double]
+    L.mntr_gpu_group_set_incumbent.argtypes = [vp, C.c_double]
+    L.mntr_gpu_group_tighten_nodes.argtypes = [vp, C.c_int32, _dp, _dp, _lp, _ip, _bp, _dp, C.POINTER(GpuOptions),
+                                               _ip, _ip, _lp, _ip, _bp, _dp, C.c_int64, _lp]
     _lib = L
     return L
 
@@ -120,6 +143,33 @@ class TightenResult:
     kernel_ms: float = 0.0
     h2d_ms: float = 0.0
     d2h_ms: float = 0.0
+
+
+def _tighten_nodes(fn, handle, check, what, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val, rounding,
+                   loop, max_rounds, handlers, mod_cap, out=None):
+    rl = np.ascontiguousarray(root_lb, np.float64); ru = np.ascontiguousarray(root_ub, np.float64)
+    dp = np.ascontiguousarray(delta_ptr, np.int64); dv = np.ascontiguousarray(delta_var, np.int32)
+    du = np.ascontiguousarray(delta_is_upper, np.uint8); dx = np.ascontiguousarray(delta_val, np.float64)
+    nb = len(dp) - 1
+    if len(dv) == 0:
+        dv = np.zeros(1, np.int32); du = np.zeros(1, np.uint8); dx = np.zeros(1)
+    o = GpuOptions(rounding, ORDER_REFERENCE, loop, max_rounds, handlers)
+    v = np.zeros(nb, np.int32); r = np.zeros(nb, np.int32); mp = np.zeros(nb + 1, np.int64)
+    cap = int(mod_cap) if mod_cap is not None else max(1024, 4 * nb)
+    while True:
+        if out is not None:       # caller-owned (e.g. page-locked) output buffers of at least mod_cap entries
+            mv, mu, mx = out
+            assert mod_cap is not None and len(mv) >= cap and len(mu) >= cap and len(mx) >= cap
+        else:
+            mv = np.zeros(max(cap, 1), np.int32); mu = np.zeros(max(cap, 1), np.uint8); mx = np.zeros(max(cap, 1))
+        total = C.c_int64(0)
+        check(fn(handle, nb, _d(rl), _d(ru), _l(dp), _i(dv), _b(du), _d(dx), C.byref(o),
+                 _i(v), _i(r), _l(mp), _i(mv), _b(mu), _d(mx), cap, C.byref(total)), what)
+        if total.value <= cap or mod_cap is not None:
+            break
+        cap = int(total.value)             # the buffer was too small: call again (documented contract)
+    k = min(int(total.value), cap)
+    return v, r, mp, mv[:k], mu[:k], mx[:k], int(total.value)
 
 
 class GpuBoundEngine:
@@ -240,29 +290,41 @@ class GpuBoundEngine:
         return lb, ub
 
     def tighten_nodes(self, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val, rounding=ROUND_DIRECTED,
-                      loop=LOOP_FIXPOINT, max_rounds=0, handlers=HANDLERS_ALL, mod_cap=None):
+                      loop=LOOP_FIXPOINT, max_rounds=0, handlers=HANDLERS_ALL, mod_cap=None, out=None):
         """Node batch as branching deltas on a root box; returns (verdict, rounds, mod_ptr, mod_var, mod_is_upper,
         mod_val): the VarBoundMod tuples of every feasible box, ascending (variable, side) inside a box."""
+        return _tighten_nodes(self.L.mntr_gpu_tighten_nodes, self.h, self._check, "tighten_nodes", root_lb, root_ub,
+                              delta_ptr, delta_var, delta_is_upper, delta_val, rounding, loop, max_rounds, handlers, mod_cap,
+                              out)
+
+    def alloc_host_bytes(self, nbytes: int) -> np.ndarray:
+        """`nbytes` of page-locked, device-mapped host memory as a uint8 array (view it as any dtype)."""
+        p = self.L.mntr_gpu_alloc_host(self.h, int(nbytes))
+        if not p:
+            raise EngineError("mntr_gpu_alloc_host failed")
+        return np.ctypeslib.as_array(C.cast(p, _bp), shape=(int(nbytes),))
+
+    def boxes_from_deltas(self, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val, boxes_dev_ptr: int):
+        """Builds the node boxes (root + deltas) in the engine's layout on the device."""
         rl = np.ascontiguousarray(root_lb, np.float64); ru = np.ascontiguousarray(root_ub, np.float64)
         dp = np.ascontiguousarray(delta_ptr, np.int64); dv = np.ascontiguousarray(delta_var, np.int32)
         du = np.ascontiguousarray(delta_is_upper, np.uint8); dx = np.ascontiguousarray(delta_val, np.float64)
-        nb = len(dp) - 1
         if len(dv) == 0:
             dv = np.zeros(1, np.int32); du = np.zeros(1, np.uint8); dx = np.zeros(1)
-        o = GpuOptions(rounding, ORDER_REFERENCE, loop, max_rounds, handlers)
-        v = np.zeros(nb, np.int32); r = np.zeros(nb, np.int32); mp = np.zeros(nb + 1, np.int64)
-        cap = int(mod_cap) if mod_cap is not None else max(1024, 4 * nb)
-        while True:
-            mv = np.zeros(max(cap, 1), np.int32); mu = np.zeros(max(cap, 1), np.uint8); mx = np.zeros(max(cap, 1))
-            total = C.c_int64(0)
-            self._check(self.L.mntr_gpu_tighten_nodes(self.h, nb, _d(rl), _d(ru), _l(dp), _i(dv), _b(du), _d(dx), C.byref(o),
-                                                      _i(v), _i(r), _l(mp), _i(mv), _b(mu), _d(mx), cap, C.byref(total)),
-                        "tighten_nodes")
-            if total.value <= cap or mod_cap is not None:
-                break
-            cap = int(total.value)             # the buffer was too small: call again (documented contract)
-        k = min(int(total.value), cap)
-        return v, r, mp, mv[:k], mu[:k], mx[:k], int(total.value)
+        self._check(self.L.mntr_gpu_boxes_from_deltas(self.h, len(dp) - 1, _d(rl), _d(ru), _l(dp), _i(dv), _b(du), _d(dx),
+                                                      C.c_void_p(boxes_dev_ptr)), "boxes_from_deltas")
+
+    def alloc_host(self, count: int) -> np.ndarray:
+        """`count` float64 in page-locked, device-mapped host memory (mntr_gpu_alloc_host): a single-box tighten on
+        such arrays takes the zero-copy path.  Free with free_host()."""
+        p = self.L.mntr_gpu_alloc_host(self.h, 8 * int(count))
+        if not p:
+            raise EngineError("mntr_gpu_alloc_host failed")
+        a = np.ctypeslib.as_array(C.cast(p, _dp), shape=(int(count),))
+        return a
+
+    def free_host(self, a: np.ndarray):
+        self.L.mntr_gpu_free_host(self.h, C.c_void_p(a.ctypes.data))
 
     def tighten_dev(self, n_boxes: int, boxes_dev_ptr: int, verdict_ptr: int, rounds_ptr: int, nnz_ptr: int,
                     rounding=ROUND_DIRECTED, loop=LOOP_FIXPOINT, max_rounds=0, handlers=HANDLERS_ALL):
@@ -307,3 +369,74 @@ class GpuBoundEngine:
         s = GpuStats()
         self._check(self.L.mntr_gpu_get_stats(self.h, C.byref(s)), "get_stats")
         return s
+
+
+class GpuBoundGroup:
+    """Several GPUs of one box driven from ONE process (mntr_gpu_group_*): the problem is replicated, a node batch is
+    split contiguously over the devices."""
+
+    def __init__(self, devices):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        dv = np.ascontiguousarray(devices, np.int32)
+        rc = self.L.mntr_gpu_group_create(len(dv), _i(dv), C.byref(self.h))
+        if rc != 0:
+            raise EngineError(f"mntr_gpu_group_create({list(devices)}) failed with {rc} (there is no CPU fallback)")
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.mntr_gpu_group_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.L.mntr_gpu_group_last_error(self.h)
+            raise EngineError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    @property
+    def size(self) -> int:
+        return int(self.L.mntr_gpu_group_size(self.h))
+
+    def load_linear(self, inst: LinearRows):
+        rp = np.ascontiguousarray(inst.row_ptr, np.int32); col = np.ascontiguousarray(inst.col, np.int32)
+        val = np.ascontiguousarray(inst.val, np.float64)
+        rl = np.ascontiguousarray(inst.row_lb, np.float64); ru = np.ascontiguousarray(inst.row_ub, np.float64)
+        vt = np.ascontiguousarray(inst.var_type, np.uint8)
+        ra = None if inst.row_active is None else np.ascontiguousarray(inst.row_active, np.uint8)
+        self._check(self.L.mntr_gpu_group_load_linear(self.h, inst.m, inst.n, _i(rp), _i(col), _d(val), _d(rl), _d(ru),
+                                                      _b(vt), _b(ra) if ra is not None else None), "group_load_linear")
+        self.n = inst.n
+        if inst.cut_col is not None and len(inst.cut_col):
+            cc = np.ascontiguousarray(inst.cut_col, np.int32); cv = np.ascontiguousarray(inst.cut_val, np.float64)
+            self._check(self.L.mntr_gpu_group_set_cutoff(self.h, len(cc), _i(cc), _d(cv), float(inst.cut_rhs)), "group_set_cutoff")
+            self._check(self.L.mntr_gpu_group_set_incumbent(self.h, float(inst.cut_rhs + getattr(inst, "obj_const", 0.0))),
+                        "group_set_incumbent")
+
+    def load_cgraph(self, t: Tapes):
+        a = {k: np.ascontiguousarray(getattr(t, k), ty) for k, ty in (
+            ("tape_ptr", np.int32), ("op", np.uint8), ("arg0", np.int32), ("arg1", np.int32), ("cnst", np.float64),
+            ("child", np.int32), ("lin_ptr", np.int32), ("lin_col", np.int32), ("lin_val", np.float64),
+            ("c_lb", np.float64), ("c_ub", np.float64))}
+        self._check(self.L.mntr_gpu_group_load_cgraph(self.h, t.n_cons, _i(a["tape_ptr"]), _b(a["op"]), _i(a["arg0"]),
+                                                      _i(a["arg1"]), _d(a["cnst"]), _i(a["child"]), _i(a["lin_ptr"]),
+                                                      _i(a["lin_col"]), _d(a["lin_val"]), _d(a["c_lb"]), _d(a["c_ub"])),
+                    "group_load_cgraph")
+
+    def tighten_nodes(self, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val, rounding=ROUND_DIRECTED,
+                      loop=LOOP_FIXPOINT, max_rounds=0, handlers=HANDLERS_ALL, mod_cap=None):
+        return _tighten_nodes(self.L.mntr_gpu_group_tighten_nodes, self.h, self._check, "group_tighten_nodes", root_lb,
+                              root_ub, delta_ptr, delta_var, delta_is_upper, delta_val, rounding, loop, max_rounds, handlers,
+                              mod_cap)

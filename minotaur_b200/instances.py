@@ -491,3 +491,156 @@ def make_minlp(n: int, n_cons: int, m_lin: int, seed: int = 99, name: str = "min
                      row_ub=row_ub.astype(np.float64), var_type=var_type, lb=lo, ub=hi, name=name,
                      xstar=xstar)
     return lin, tapes
+
+
+# --------------------------------------------------------------------------------------
+# large-batch forms: node boxes as sparse deltas, vectorised MINLP generator (bench sizes)
+# --------------------------------------------------------------------------------------
+
+def branch_deltas(inst_lb: np.ndarray, inst_ub: np.ndarray, var_type: np.ndarray, n_boxes: int, seed: int = 2024,
+                  max_depth: int = 20, continuous_too: bool = False):
+    """The node boxes of ``branch_boxes`` -- the root box with d in {1..max_depth} random branching perturbations
+    (``ub := floor(v)`` or ``lb := ceil(v)`` on random integer variables, IntVarHandler::getBranches,
+    /root/reference/src/base/IntVarHandler.cpp:133-190) -- produced directly as sparse deltas, vectorised: the form
+    ``mntr_gpu_tighten_nodes`` takes, and the only one that fits in memory at config C5's size (4096 boxes x 1M
+    variables).  Own random stream (not box-for-box equal to ``branch_boxes``).  Returns
+    (delta_ptr int64 [n_boxes+1], delta_var int32, delta_is_upper uint8, delta_val float64)."""
+    rng = np.random.default_rng([seed, 7])
+    is_int = (var_type == INTEGER) | (var_type == BINARY)
+    cand = np.nonzero((is_int | continuous_too) & np.isfinite(inst_lb) & np.isfinite(inst_ub) & (inst_ub > inst_lb))[0]
+    if cand.size == 0:
+        return np.zeros(n_boxes + 1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0)
+    depth = rng.integers(1, max_depth + 1, size=n_boxes)
+    box = np.repeat(np.arange(n_boxes, dtype=np.int64), depth)
+    var = cand[rng.integers(0, cand.size, size=box.size)].astype(np.int64)
+    # one perturbation per (box, variable): drop repeated draws
+    key = box * (int(var_type.shape[0]) + 1) + var
+    _, first = np.unique(key, return_index=True)
+    first.sort()
+    box, var = box[first], var[first]
+    lo, hi = inst_lb[var], inst_ub[var]
+    keep = (hi - lo) >= 0.5
+    box, var, lo, hi = box[keep], var[keep], lo[keep], hi[keep]
+    v = lo + (hi - lo) * rng.random(box.size)
+    vi = is_int[var]
+    v = np.where(vi & (v == np.floor(v)), v + 0.5, v)
+    up = rng.random(box.size) < 0.5
+    val = np.where(vi, np.where(up, np.floor(v), np.ceil(v)), v)
+    order = np.argsort(box, kind="stable")
+    box, var, up, val = box[order], var[order], up[order], val[order]
+    ptr = np.zeros(n_boxes + 1, np.int64)
+    np.add.at(ptr, box + 1, 1)
+    ptr = np.cumsum(ptr)
+    return ptr, var.astype(np.int32), up.astype(np.uint8), val.astype(np.float64)
+
+
+def deltas_box(root_lb: np.ndarray, root_ub: np.ndarray, deltas, b: int):
+    """Dense (lb, ub) of box ``b`` of a delta batch."""
+    ptr, var, up, val = deltas
+    lb, ub = root_lb.copy(), root_ub.copy()
+    for q in range(int(ptr[b]), int(ptr[b + 1])):
+        if up[q]:
+            ub[var[q]] = val[q]
+        else:
+            lb[var[q]] = val[q]
+    return lb, ub
+
+
+def slice_deltas(deltas, b0: int, b1: int):
+    """Boxes [b0, b1) of a delta batch as a batch of their own."""
+    ptr, var, up, val = deltas
+    q0, q1 = int(ptr[b0]), int(ptr[b1])
+    return (ptr[b0:b1 + 1] - q0).astype(np.int64), var[q0:q1], up[q0:q1], val[q0:q1]
+
+
+def make_minlp_large(n: int, n_cons: int, m_lin: int, seed: int = 99, name: str = "minlp") -> Tuple[LinearRows, Tapes]:
+    """Config C5 at full size: the constraint families of ``make_minlp`` (50 % ``c_lb <= x_i*x_j + a*x_k <= c_ub`` as
+    tape Var,Var,Mult + linear part; 50 % ``x_i^2 + x_j^2 <= r`` as SumList(Sqr,Sqr); ``m_lin`` linear rows; planted
+    point), with the tapes written directly in the node order ``flatten_expr`` / ``CGraph::finalize`` produce (variable
+    nodes by ascending id, operators in post-order) -- vectorised, so 1M constraints take seconds.  Own random stream;
+    ``tests/test_instances.py`` checks the tapes against ``build_tapes`` on the same draws."""
+    rng = np.random.default_rng([seed, 11])
+    # boxes inside [-10, 10] that straddle zero, none with zero as an END POINT at the root: the reference's reverse
+    # rule of OpMult divides by an interval that merely touches zero as if zero were excluded (BoundsOnRecip,
+    # Operations.cpp:182-212: [0,u] -> [1/u, inf]) and then cuts off feasible points; with a million constraints that
+    # proves the ROOT box "infeasible" and every node box with it (measured with make_minlp's [-{0..10}, {1..10}] boxes)
+    lo = 0.0 - rng.integers(1, 11, size=n).astype(np.float64)
+    hi = rng.integers(1, 11, size=n).astype(np.float64)
+    is_int = rng.random(n) < 0.3
+    var_type = np.where(is_int, INTEGER, CONTINUOUS).astype(np.uint8)
+    xstar = lo + (hi - lo) * rng.random(n)
+    xstar = np.where(is_int, np.round(xstar), xstar).clip(lo, hi)
+    ijk = rng.integers(0, n, size=(n_cons, 3))
+    for _ in range(100):
+        bad = (ijk[:, 0] == ijk[:, 1]) | (ijk[:, 0] == ijk[:, 2]) | (ijk[:, 1] == ijk[:, 2])
+        if not bad.any():
+            break
+        ijk[bad] = rng.integers(0, n, size=(int(bad.sum()), 3))
+    tapes = minlp_tapes_from_draws(ijk, xstar, rng)
+    k = min(6, n)
+    if m_lin > 0:
+        col = _distinct_sorted_columns(rng, m_lin, n, k)
+        val = rng.integers(1, 10, size=(m_lin, k)).astype(np.float64) * np.where(rng.random((m_lin, k)) < 0.3, -1.0, 1.0)
+        act = (val * xstar[col]).sum(axis=1)
+        row_ub = act + rng.integers(0, 4, size=m_lin)
+        row_lb = np.where(rng.random(m_lin) < 0.3, act, -INF)
+        row_ub = np.where(np.isfinite(row_lb), act, row_ub)
+    else:
+        col = np.zeros((0, k), np.int32); val = np.zeros((0, k)); row_lb = np.zeros(0); row_ub = np.zeros(0)
+    row_ptr = (np.arange(m_lin + 1, dtype=np.int64) * k).astype(np.int32)
+    lin = LinearRows(m=m_lin, n=n, row_ptr=row_ptr, col=col.reshape(-1).astype(np.int32),
+                     val=val.reshape(-1).astype(np.float64), row_lb=row_lb.astype(np.float64),
+                     row_ub=row_ub.astype(np.float64), var_type=var_type, lb=lo, ub=hi, name=name, xstar=xstar)
+    return lin, tapes
+
+
+def minlp_tapes_from_draws(ijk: np.ndarray, xstar: np.ndarray, rng: np.random.Generator, return_cons: bool = False):
+    """Tapes of the two C5 constraint families for the variable triples ``ijk`` (even constraints bilinear + linear
+    term, odd ones sum of two squares).  With ``return_cons`` also the same constraints as (Expr, linear, lb, ub)
+    tuples for ``build_tapes`` (the check of the direct layout)."""
+    n_cons = ijk.shape[0]
+    i, j, kk = ijk[:, 0], ijk[:, 1], ijk[:, 2]
+    bil = (np.arange(n_cons) % 2) == 0
+    a = rng.integers(1, 6, size=n_cons).astype(np.float64) * np.where(rng.random(n_cons) < 0.5, 1.0, -1.0)
+    w = rng.integers(0, 4, size=n_cons).astype(np.float64)
+    two_sided = rng.random(n_cons) < 0.3
+    r_extra = rng.integers(0, 10, size=n_cons).astype(np.float64)
+    vb = xstar[i] * xstar[j] + a * xstar[kk]
+    c_lb = np.where(bil, np.where(two_sided, vb - 0.5 * w, -INF), -INF)
+    c_ub = np.where(bil, np.where(two_sided, vb + 0.5 * w, vb + w), xstar[i] ** 2 + xstar[j] ** 2 + r_extra)
+    nodes = np.where(bil, 3, 5)
+    tape_ptr = np.concatenate([[0], np.cumsum(nodes)]).astype(np.int64)
+    n_nodes = int(tape_ptr[-1])
+    op = np.zeros(n_nodes, np.uint8); a0 = np.full(n_nodes, -1, np.int32); a1 = np.full(n_nodes, -1, np.int32)
+    base = tape_ptr[:-1]
+    vlo, vhi = np.minimum(i, j), np.maximum(i, j)
+    idx_i = (i > j).astype(np.int32)            # local index of x_i's variable node (variable nodes ascend by id)
+    idx_j = 1 - idx_i
+    op[base] = OpVar; a0[base] = vlo
+    op[base + 1] = OpVar; a0[base + 1] = vhi
+    bb = base[bil]
+    op[bb + 2] = OpMult; a0[bb + 2] = idx_i[bil]; a1[bb + 2] = idx_j[bil]
+    sb = base[~bil]
+    op[sb + 2] = OpSqr; a0[sb + 2] = idx_i[~bil]
+    op[sb + 3] = OpSqr; a0[sb + 3] = idx_j[~bil]
+    n_sq = int((~bil).sum())
+    op[sb + 4] = OpSumList
+    a0[sb + 4] = 2 * np.arange(n_sq, dtype=np.int32)
+    a1[sb + 4] = 2 * np.arange(n_sq, dtype=np.int32) + 2
+    child = np.tile(np.array([2, 3], np.int32), n_sq) if n_sq else np.zeros(1, np.int32)
+    lin_cnt = bil.astype(np.int64)
+    lin_ptr = np.concatenate([[0], np.cumsum(lin_cnt)]).astype(np.int32)
+    lin_col = kk[bil].astype(np.int32); lin_val = a[bil]
+    tapes = Tapes(n_cons=n_cons, tape_ptr=tape_ptr.astype(np.int32), op=op, arg0=a0, arg1=a1,
+                  cnst=np.zeros(n_nodes), child=child, lin_ptr=lin_ptr,
+                  lin_col=lin_col if lin_col.size else np.zeros(1, np.int32),
+                  lin_val=lin_val if lin_val.size else np.zeros(1), c_lb=c_lb.astype(np.float64), c_ub=c_ub.astype(np.float64))
+    if not return_cons:
+        return tapes
+    cons = []
+    for c in range(n_cons):
+        if bil[c]:
+            cons.append((Expr.v(int(i[c])) * Expr.v(int(j[c])), [(int(kk[c]), float(a[c]))], float(c_lb[c]), float(c_ub[c])))
+        else:
+            cons.append((Expr.sumlist([Expr.v(int(i[c])).sqr(), Expr.v(int(j[c])).sqr()]), [], float(c_lb[c]), float(c_ub[c])))
+    return tapes, cons

@@ -852,3 +852,68 @@ void orc_node_presolve(const orc_lin_t *p, const orc_nl_t *g, double *lb, double
   res->rounds = a.rounds + b.rounds;
   res->nnz_updates = a.nnz_updates; res->n_mods = a.n_mods + b.n_mods;
 }
+
+/* --- batches of node boxes given as branching deltas on a root box ------------------------------------------
+ * TEST / BASELINE DRIVER (no reference counterpart: the reference tightens one node at a time).  Box b is the
+ * root box with deltas dptr[b] .. dptr[b+1) applied in order (a later delta overrides), exactly like
+ * mntr_gpu_tighten_nodes.  mode 0 = orc_lin_fixpoint_inplace, 1 = orc_lin_simple_presolve, 2 = orc_node_presolve.
+ * Boxes are dealt to n_threads OpenMP threads (each with its own dense box).  Per box: verdict, rounds,
+ * nnz-updates and the bound changes relative to the box's INITIAL bounds, ascending (variable, side), at most
+ * mod_cap of them in slot b of mod_var / mod_up / mod_val (mod_cnt[b] is the true count).  Returns the wall
+ * time of the parallel region in seconds. */
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+double orc_batch_deltas(const orc_lin_t *p, const orc_nl_t *g, int32_t mode, int32_t n_boxes,
+                        const double *root_lb, const double *root_ub, const int64_t *dptr,
+                        const int32_t *dvar, const uint8_t *dup, const double *dval, int32_t n_threads,
+                        int32_t *verdict, int32_t *rounds, int64_t *nnz, int32_t mod_cap, int32_t *mod_cnt,
+                        int32_t *mod_var, uint8_t *mod_up, double *mod_val)
+{
+  const int32_t n = p ? p->n : 0;
+  struct timespec t0, t1;
+  if (n_threads < 1) n_threads = 1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+#pragma omp parallel num_threads(n_threads)
+  {
+    double *lb = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double *ub = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double *l0 = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double *u0 = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+#pragma omp for schedule(dynamic, 1)
+    for (int32_t b = 0; b < n_boxes; ++b) {
+      memcpy(lb, root_lb, sizeof(double) * (size_t)n);
+      memcpy(ub, root_ub, sizeof(double) * (size_t)n);
+      for (int64_t q = dptr[b]; q < dptr[b + 1]; ++q) {
+        if (dup[q]) ub[dvar[q]] = dval[q]; else lb[dvar[q]] = dval[q];
+      }
+      memcpy(l0, lb, sizeof(double) * (size_t)n);
+      memcpy(u0, ub, sizeof(double) * (size_t)n);
+      orc_result_t r = {0, 0, 0, 0};
+      if (mode == 0) orc_lin_fixpoint_inplace(p, lb, ub, &r);
+      else if (mode == 1) orc_lin_simple_presolve(p, lb, ub, &r);
+      else orc_node_presolve((p && p->m > 0) ? p : NULL, g, lb, ub, &r);
+      if (verdict) verdict[b] = r.verdict;
+      if (rounds) rounds[b] = r.rounds;
+      if (nnz) nnz[b] = r.nnz_updates;
+      if (mod_cnt) {
+        int32_t cnt = 0;
+        for (int32_t j = 0; j < n; ++j) {
+          if (lb[j] != l0[j]) {
+            if (cnt < mod_cap) { mod_var[(size_t)b * mod_cap + cnt] = j; mod_up[(size_t)b * mod_cap + cnt] = 0; mod_val[(size_t)b * mod_cap + cnt] = lb[j]; }
+            ++cnt;
+          }
+          if (ub[j] != u0[j]) {
+            if (cnt < mod_cap) { mod_var[(size_t)b * mod_cap + cnt] = j; mod_up[(size_t)b * mod_cap + cnt] = 1; mod_val[(size_t)b * mod_cap + cnt] = ub[j]; }
+            ++cnt;
+          }
+        }
+        mod_cnt[b] = cnt;
+      }
+    }
+    free(lb); free(ub); free(l0); free(u0);
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

@@ -21,12 +21,23 @@ REF_SO = os.path.join(HERE, "_ref", "libminotaur_ref.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
 _bp = C.POINTER(C.c_uint8)
 
 
 def _d(a): return a.ctypes.data_as(_dp)
 def _i(a): return a.ctypes.data_as(_ip)
 def _b(a): return a.ctypes.data_as(_bp)
+def _l(a): return a.ctypes.data_as(_lp)
+
+
+def _delta_arrays(deltas):
+    ptr, var, up, val = deltas
+    ptr = np.ascontiguousarray(ptr, np.int64); var = np.ascontiguousarray(var, np.int32)
+    up = np.ascontiguousarray(up, np.uint8); val = np.ascontiguousarray(val, np.float64)
+    if var.size == 0:
+        var = np.zeros(1, np.int32); up = np.zeros(1, np.uint8); val = np.zeros(1)
+    return ptr, var, up, val
 
 
 class OrcLin(C.Structure):
@@ -119,6 +130,9 @@ class Oracle:
         L.orc_nl_sweep.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(C.c_int64)]
         L.orc_nl_sweep.restype = C.c_int32
         L.orc_node_presolve.argtypes = [C.POINTER(OrcLin), C.POINTER(OrcNl), _dp, _dp, C.POINTER(OrcResult)]
+        L.orc_batch_deltas.argtypes = [C.POINTER(OrcLin), C.POINTER(OrcNl), C.c_int32, C.c_int32, _dp, _dp, _lp, _ip, _bp,
+                                       _dp, C.c_int32, _ip, _ip, _lp, C.c_int32, _ip, _ip, _bp, _dp]
+        L.orc_batch_deltas.restype = C.c_double
         for f in ("orc_bounds_on_product",):
             getattr(L, f).argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp]
         L.orc_bounds_on_div.argtypes = [C.c_double] * 4 + [_dp, _dp]
@@ -208,6 +222,26 @@ class Oracle:
                                    _d(lb), _d(ub), C.byref(r))
         return lb, ub, dict(verdict=r.verdict, rounds=r.rounds, nnz_updates=r.nnz_updates, n_mods=r.n_mods)
 
+    def batch_deltas(self, inst, tapes, mode, root_lb, root_ub, deltas, n_threads=1, mod_cap=0):
+        """Node boxes given as branching deltas on a root box (the form of mntr_gpu_tighten_nodes), dealt to
+        ``n_threads`` OpenMP threads.  mode 0 = lin_fixpoint_inplace, 1 = lin_simple_presolve, 2 = node_presolve.
+        Returns dict(secs, verdict, rounds, nnz, mod_cnt, mod_var, mod_up, mod_val): the mods of box b are the
+        first min(mod_cnt[b], mod_cap) entries of row b, ascending (variable, side)."""
+        keep = {}
+        s = _lin_struct(inst, keep)
+        g = _nl_struct(tapes, keep) if tapes is not None else None
+        ptr, var, up, val = _delta_arrays(deltas)
+        nb = len(ptr) - 1
+        rl = np.ascontiguousarray(root_lb, np.float64); ru = np.ascontiguousarray(root_ub, np.float64)
+        v = np.zeros(nb, np.int32); r = np.zeros(nb, np.int32); z = np.zeros(nb, np.int64)
+        cap = int(mod_cap)
+        mc = np.zeros(nb, np.int32)
+        mv = np.zeros((nb, max(cap, 1)), np.int32); mu = np.zeros((nb, max(cap, 1)), np.uint8); mx = np.zeros((nb, max(cap, 1)))
+        secs = self.lib.orc_batch_deltas(C.byref(s), C.byref(g) if g is not None else None, int(mode), nb, _d(rl), _d(ru),
+                                         _l(ptr), _i(var), _b(up), _d(val), int(n_threads), _i(v), _i(r), _l(z),
+                                         cap, _i(mc) if cap > 0 else None, _i(mv), _b(mu), _d(mx))
+        return dict(secs=secs, verdict=v, rounds=r, nnz=z, mod_cnt=mc, mod_var=mv, mod_up=mu, mod_val=mx)
+
     def bounds_on_product(self, z, l0, u0, l1, u1):
         o = np.zeros(2); self.lib.orc_bounds_on_product(int(z), l0, u0, l1, u1, _d(o[0:1]), _d(o[1:2])); return tuple(o)
 
@@ -246,6 +280,11 @@ class Reference:
             L.ref_row_activity.argtypes = [C.c_void_p, C.c_int32, _dp]
             L.ref_time_boxes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
             L.ref_time_boxes.restype = C.c_double
+            L.ref_time_deltas.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, _lp, _ip, _bp, _dp,
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+            L.ref_time_deltas.restype = C.c_double
+            L.ref_add_nl_batch.argtypes = [C.c_void_p, C.c_int32, _ip, _bp, _ip, _ip, _dp, _ip, _ip, _ip, _dp, _dp, _dp]
+            L.ref_add_nl_batch.restype = C.c_int32
             L.ref_destroy.argtypes = [C.c_void_p]
             cls._lib = L
         return cls._lib
@@ -262,15 +301,10 @@ class Reference:
             raise ValueError("Reference harness: deleted rows are not supported; drop them from the CSR")
         self.h = L.ref_create(inst.m, inst.n, _i(rp), _i(col), _d(val), _d(rl), _d(ru), _b(vt), _d(lb), _d(ub))
         if tapes is not None:
-            for c in range(tapes.n_cons):
-                b, e = int(tapes.tape_ptr[c]), int(tapes.tape_ptr[c + 1])
-                op = np.ascontiguousarray(tapes.op[b:e]); a0 = np.ascontiguousarray(tapes.arg0[b:e])
-                a1 = np.ascontiguousarray(tapes.arg1[b:e]); cn = np.ascontiguousarray(tapes.cnst[b:e])
-                lbeg, lend = int(tapes.lin_ptr[c]), int(tapes.lin_ptr[c + 1])
-                lc = np.ascontiguousarray(tapes.lin_col[lbeg:lend] if lend > lbeg else np.zeros(1, np.int32))
-                lv = np.ascontiguousarray(tapes.lin_val[lbeg:lend] if lend > lbeg else np.zeros(1))
-                L.ref_add_nl(self.h, e - b, _b(op), _i(a0), _i(a1), _d(cn), _i(tapes.child), lend - lbeg,
-                             _i(lc), _d(lv), float(tapes.c_lb[c]), float(tapes.c_ub[c]))
+            keep = {}
+            g = _nl_struct(tapes, keep)
+            L.ref_add_nl_batch(self.h, tapes.n_cons, g.tape_ptr, g.op, g.arg0, g.arg1, g.cnst, g.child, g.lin_ptr,
+                               g.lin_col, g.lin_val, g.c_lb, g.c_ub)
         if inst.cut_col is not None and len(inst.cut_col):
             # the cut-off row c.x <= cut_rhs as the reference meets it: a linear objective c.x + obj_const and an
             # incumbent of value cut_rhs + obj_const in the solution pool (LinearHandler.cpp:1636-1640)
@@ -364,6 +398,19 @@ class Reference:
         nnz = C.c_int64(0); ninf = C.c_int64(0)
         secs = self.lib().ref_time_boxes(self.h, mode, nb, _d(lbs), _d(ubs), C.byref(nnz), C.byref(ninf))
         return secs, nnz.value, ninf.value
+
+
+def _ref_time_deltas(self, mode, root_lb, root_ub, deltas):
+    """ref_time_boxes for boxes given as branching deltas on a root box; returns (secs, nnz, n_infeasible)."""
+    ptr, var, up, val = _delta_arrays(deltas)
+    rl = np.ascontiguousarray(root_lb, np.float64); ru = np.ascontiguousarray(root_ub, np.float64)
+    nnz = C.c_int64(0); ninf = C.c_int64(0)
+    secs = self.lib().ref_time_deltas(self.h, int(mode), len(ptr) - 1, _d(rl), _d(ru), _l(ptr), _i(var), _b(up), _d(val),
+                                      C.byref(nnz), C.byref(ninf))
+    return secs, nnz.value, ninf.value
+
+
+Reference.time_deltas = _ref_time_deltas
 
 
 def ref_read_mps(path: str) -> dict:

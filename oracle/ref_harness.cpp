@@ -367,6 +367,46 @@ double ref_time_boxes(void *hv, int32_t mode, int32_t n_boxes, const double *lbs
   return secs;
 }
 
+/* all nonlinear constraints of a flat tape description at once (the Python loop over ref_add_nl costs 60 us per
+ * constraint, a minute for the 1M constraints of config C5) */
+int32_t ref_add_nl_batch(void *hv, int32_t n_cons, const int32_t *tape_ptr, const uint8_t *op, const int32_t *arg0,
+                         const int32_t *arg1, const double *cnst, const int32_t *child, const int32_t *lin_ptr,
+                         const int32_t *lin_col, const double *lin_val, const double *c_lb, const double *c_ub)
+{
+  for (int32_t c = 0; c < n_cons; ++c) {
+    const int32_t b = tape_ptr[c], lb = lin_ptr[c];
+    ref_add_nl(hv, tape_ptr[c + 1] - b, op + b, arg0 + b, arg1 + b, cnst + b, child, lin_ptr[c + 1] - lb,
+               lin_col + lb, lin_val + lb, c_lb[c], c_ub[c]);
+  }
+  return n_cons;
+}
+
+/* ref_time_boxes for boxes given as branching deltas on a root box (the form of mntr_gpu_tighten_nodes): box b is
+ * the root box with deltas dptr[b] .. dptr[b+1) applied in order.  Only the tighten calls are timed. */
+double ref_time_deltas(void *hv, int32_t mode, int32_t n_boxes, const double *root_lb, const double *root_ub,
+                       const int64_t *dptr, const int32_t *dvar, const uint8_t *dup, const double *dval,
+                       int64_t *nnz_total, int64_t *n_infeasible)
+{
+  RefProblem *h = (RefProblem *)hv;
+  double secs = 0; *nnz_total = 0; *n_infeasible = 0;
+  for (int32_t b = 0; b < n_boxes; ++b) {
+    ref_set_box(hv, root_lb, root_ub);
+    for (int64_t q = dptr[b]; q < dptr[b + 1]; ++q) {
+      VariablePtr v = h->vars[dvar[q]];
+      if (dup[q]) h->p->changeBound(v, Upper, dval[q]); else h->p->changeBound(v, Lower, dval[q]);
+    }
+    int32_t rounds = 0, inf = 0; int64_t nmods = 0, nnz = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    if (mode == 0) inf = h->lh->fixpointCounted(h->p, h->spool, &rounds, &nmods, &nnz, 0);
+    else if (mode == 1) inf = ref_lin_simple_presolve(hv, &nmods);
+    else inf = ref_node_presolve(hv, &nmods);
+    auto t1 = std::chrono::steady_clock::now();
+    secs += std::chrono::duration<double>(t1 - t0).count();
+    *nnz_total += nnz; *n_infeasible += inf;
+  }
+  return secs;
+}
+
 // ---- Reader::readMps (Reader.cpp:42-473): read an MPS file with the reference's own reader and dump the problem
 //      flat -- the fixture generator of minotaur_b200/mps_reader.py.  Two-call protocol: sizes first (arrays null),
 //      then the arrays.  Returns the reader's error code (0 = ok), or -1 if the file gave no problem.

@@ -76,9 +76,10 @@ def test_row_activities_bitwise(oracle, lin_gold):
 
 def test_jacobi_reaches_reference_fixpoint(oracle, lin_gold):
     """The Jacobi rule (what the single-box CUDA kernel implements) against the reference's in-place
-    fixpoint: same verdicts, integer bounds bit-exact, continuous within 1e-9 relative -- except where the
-    1e-8 acceptance threshold (LinearHandler.cpp:1070) makes the fixpoint order dependent, bounded here
-    by 5e-8 ("Jacobi vs in-place")."""
+    fixpoint: same verdicts, integer bounds bit-exact, continuous within 1e-9 relative (the north-star tolerance) on
+    every fixture.  The one fixture that comes close is 'intdata' (9.8e-10 on one slowly converging box: the 1e-8
+    acceptance threshold of LinearHandler.cpp:1070 makes the fixpoint order dependent at that scale, see DESIGN.md,
+    "Jacobi vs in-place"); all others agree to 1e-14."""
     from helpers import assert_box_parity
     z = lin_gold
     for name in z["names"]:
@@ -87,8 +88,7 @@ def test_jacobi_reaches_reference_fixpoint(oracle, lin_gold):
             l, u, r = oracle.lin_fixpoint_jacobi(inst, z[f"{name}.lbs"][b], z[f"{name}.ubs"][b])
             assert (r["verdict"] != 0) == (z[f"{name}.fix_verdict"][b] != 0), (name, b)
             if r["verdict"] == 0:
-                assert_box_parity(inst.var_type, l, u, z[f"{name}.fix_lb"][b], z[f"{name}.fix_ub"][b], rel_tol=5e-8,
-                                  what=f"{name}[{b}]")
+                assert_box_parity(inst.var_type, l, u, z[f"{name}.fix_lb"][b], z[f"{name}.fix_ub"][b], what=f"{name}[{b}]")
 
 
 def test_tape_order_matches_cgraph_finalize(nl_gold):
