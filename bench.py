@@ -140,17 +140,22 @@ def box_parity(var_type, got_lb, got_ub, ref_lb, ref_ub, rel_tol=1e-9):
     """north star: integer-variable bounds bit-exact (after the 1e-6 canonicalisation of SURVEY.md 7, hard part 2),
     continuous within rel_tol and never tighter than the reference beyond it.  Returns (ok, worst relative diff)."""
     isint = var_type <= 1
-    ok = np.array_equal(_canon_int(got_lb[isint]), _canon_int(ref_lb[isint])) and \
-        np.array_equal(_canon_int(got_ub[isint]), _canon_int(ref_ub[isint]))
-    c = ~isint
+    ok = True
     worst = 0.0
-    for g, r, sign in ((got_lb[c], ref_lb[c], 1.0), (got_ub[c], ref_ub[c], -1.0)):
+    for g, r, sign in ((got_lb, ref_lb, 1.0), (got_ub, ref_ub, -1.0)):
+        gi, ri = _canon_int(g[isint]), _canon_int(r[isint])
+        # integral bounds of integer variables: bit-exact.  (CGraph harvests leave NON-integral bounds on integer
+        # variables -- CGraph::varBoundMods does not round, SURVEY.md 8a N4 -- those are compared like continuous ones.)
         with np.errstate(invalid="ignore"):
-            d = np.abs(g - r) / np.maximum(1.0, np.maximum(np.abs(g), np.abs(r)))
-            d = np.nan_to_num(np.where(g == r, 0.0, d), nan=np.inf)
-            tighter = sign * (g - r) > rel_tol * np.maximum(1.0, np.abs(r))
+            integral = (gi == np.round(gi)) | (ri == np.round(ri)) | ~np.isfinite(gi) | ~np.isfinite(ri)
+        ok = ok and bool(np.array_equal(gi[integral], ri[integral]))
+        gc = np.concatenate([g[~isint], gi[~integral]]); rc = np.concatenate([r[~isint], ri[~integral]])
+        with np.errstate(invalid="ignore"):
+            d = np.abs(gc - rc) / np.maximum(1.0, np.maximum(np.abs(gc), np.abs(rc)))
+            d = np.nan_to_num(np.where(gc == rc, 0.0, d), nan=np.inf)
+            tighter = sign * (gc - rc) > rel_tol * np.maximum(1.0, np.abs(rc))
         worst = max(worst, float(d.max(initial=0.0)))
-        ok = ok and not bool(np.any(tighter & (g != r)))
+        ok = ok and not bool(np.any(tighter & (gc != rc)))
     return bool(ok and worst <= rel_tol), worst
 
 
@@ -178,13 +183,12 @@ def take_deltas(deltas, idx):
     return nptr, var[sel], up[sel], val[sel]
 
 
-def batch_parity(E, eng, orc, inst, tapes, deltas, idx, mode, loop, threads):
+def batch_parity(E, eng, orc, inst, tapes, deltas, idx, mode, loop, threads, cap=1 << 14):
     """Sampled boxes `idx` of a node batch: the CUDA path in ROUND_NEAREST / reference order (the same kernel template
     as the timed run, other rounding policy) must equal the oracle's in-place sweeps BIT FOR BIT -- verdicts, and for
     feasible boxes every bound change.  Returns (record, oracle result) -- the oracle's all-core time doubles as the
     'port' CPU baseline."""
     sub = take_deltas(deltas, idx)
-    cap = 1 << 14
     o = orc.batch_deltas(inst, tapes, mode, inst.lb, inst.ub, sub, n_threads=threads, mod_cap=cap)
     v, r, mp, mv, mu, mx, total = eng.tighten_nodes(inst.lb, inst.ub, *sub, rounding=E.ROUND_NEAREST, loop=loop)
     n_ok = n_cmp = n_skip = 0
@@ -642,7 +646,7 @@ def block_c1(X):
 
 # ---------------------------------------------------------------- C3 ----------------------------------------------
 
-def node_batch(X, name, inst, tapes, deltas, loop, mode, workload, cons_per_box=0):
+def node_batch(X, name, inst, tapes, deltas, loop, mode, workload, cons_per_box=0, mods_per_box=4096):
     """Shared driver of the node-batch blocks (C3, C5): boxes sharded by node over the ranks."""
     args, E, torch, dev = X.args, X.E, X.torch, X.dev
     from minotaur_b200.instances import slice_deltas
@@ -694,7 +698,7 @@ def node_batch(X, name, inst, tapes, deltas, loop, mode, workload, cons_per_box=
 
     # e2e through the reference-facing call: host deltas in, VarBoundMod tuples out (output buffers page-locked, as a
     # caller that owns them would allocate them: mntr_gpu_alloc_host)
-    cap = int(os.environ.get("MNTR_BENCH_MODCAP", "0")) or max(1 << 20, nb * 4096)
+    cap = int(os.environ.get("MNTR_BENCH_MODCAP", "0")) or max(1 << 20, nb * mods_per_box)
     raw = [eng.alloc_host_bytes(4 * cap), eng.alloc_host_bytes(cap), eng.alloc_host_bytes(8 * cap)]
     obuf = (raw[0].view(np.int32), raw[1], raw[2].view(np.float64))
     e2e_times = []
@@ -722,7 +726,7 @@ def node_batch(X, name, inst, tapes, deltas, loop, mode, workload, cons_per_box=
         threads = max(1, (os.cpu_count() or 1) // max(1, min(X.world, 8)))
         k = max(1, args.parity_boxes // X.world)
         idx = sample_boxes(nb, k, seed=1000 + X.rank)
-        rec, ores = batch_parity(E, eng, orc, inst, tapes, mine, idx, mode, loop, threads)
+        rec, ores = batch_parity(E, eng, orc, inst, tapes, mine, idx, mode, loop, threads, cap=4 * mods_per_box)
         rec["directed"] = directed_parity(E, inst, mine, idx, (v, mp, mv, mu, mx), ores) if total_mods <= cap else None
         rec["e2e_verdicts_rounds_equal_device_run"] = same_as_dev
         ok_all = X.min_over_ranks(1.0 if (rec["ok"] and same_as_dev) else 0.0) > 0.5
@@ -789,7 +793,8 @@ def block_c5(X):
     wl = (f"C5: {tapes.n_cons} bilinear/quadratic CGraph constraints + {lin.m} linear rows over {lin.n} variables, "
           f"{args.c5_boxes} node boxes, one presolveNode pass per box (LinearHandler::simplePresolve then "
           "NlPresHandler::simplePresolve, in-place order by wavefront levels)")
-    out, port = node_batch(X, "C5", lin, tapes, deltas, X.E.LOOP_SIMPLEPRESOLVE, 2, wl, cons_per_box=tapes.n_cons)
+    out, port = node_batch(X, "C5", lin, tapes, deltas, X.E.LOOP_SIMPLEPRESOLVE, 2, wl, cons_per_box=tapes.n_cons,
+                           mods_per_box=max(4096, int(32768 * scale)))
     out["roofline"]["kernel"] = "fbbt_batch_reference_kernel<.., HAS_NL> (K3 + K4)"
     out["roofline"]["note"] = "instruction-issue bound (interval arithmetic of the tapes), not HBM bound: see DESIGN.md"
     if X.cpu:

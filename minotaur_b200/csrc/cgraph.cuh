@@ -166,7 +166,13 @@ struct ConsView {
   int n_lin;
   int n_lead_vars;          // leading OpVar nodes (the tape starts with the variable nodes, ascending id)
   double c_lb, c_ub;
+  int shape;                // kShape*: tapes of the two dominant forms are evaluated by straight-line code
 };
+// tape shapes with a specialised evaluator (same operations in the same order as the interpreter, node intervals in
+// registers instead of local memory, no opcode dispatch)
+constexpr int kShapeGeneric = 0;
+constexpr int kShapeBilinear = 1;   // [Var, Var, Mult(a, b)]                              x_i * x_j (+ linear part)
+constexpr int kShapeSumSq = 2;      // [Var, Var, Sqr(a), Sqr(b), SumList(2, 3)]           x_i^2 + x_j^2
 
 struct BatchInfo {
   int n;                    // constraints staged (1..32)
@@ -248,6 +254,14 @@ __device__ __forceinline__ ConsView batch_constraint(const NlDev &N, const Batch
   int nv = 0;
   while (nv < V.t.nn && V.t.op[nv] == OpVar) ++nv;
   V.n_lead_vars = nv;
+  V.shape = kShapeGeneric;
+  const TapeView &t = V.t;
+  if (nv == 2 && t.nn == 3 && t.op[2] == OpMult && (unsigned)t.a0[2] < 2u && (unsigned)t.a1[2] < 2u && t.a0[2] != t.a1[2])
+    V.shape = kShapeBilinear;
+  else if (nv == 2 && t.nn == 5 && t.op[2] == OpSqr && t.op[3] == OpSqr && t.op[4] == OpSumList &&
+           (unsigned)t.a0[2] < 2u && (unsigned)t.a0[3] < 2u && t.a1[4] - t.a0[4] == 2 &&
+           t.child[t.a0[4]] == 2 && t.child[t.a0[4] + 1] == 3)
+    V.shape = kShapeSumSq;
   return V;
 }
 
@@ -485,12 +499,67 @@ __device__ __forceinline__ void tape_forward(const ConsView &V, double *nlb, dou
   for (int i = V.n_lead_vars; i < t.nn; ++i) node_forward<R>(t, i, nlb, nub, bx, ld, error);
 }
 
+// ---- straight-line evaluators of the two dominant tape shapes.  Every arithmetic operation, comparison and store is
+//      the interpreter's (node_forward / node_reverse / prop_child above), in the same order: results are bitwise the
+//      same; node intervals live in registers. ----
+__device__ __forceinline__ void clamp25(double &lb, double &ub)      // the clamp of CNode::updateBnd, :1898-1903
+{
+  if (lb < -kMinfty) lb = -INFINITY;
+  if (ub > kMinfty) ub = INFINITY;
+}
+// CNode::propBounds_ on an interval held in registers
+__device__ __forceinline__ void prop_reg(double lb, double ub, double &nl, double &nu, bool &is_inf, int &error)
+{
+  const double etol = 1e-7;
+  if (isnan(lb) || isnan(ub)) { error = 9999; return; }
+  if (lb < -kMinfty) lb = -INFINITY;
+  if (ub > kMinfty) ub = INFINITY;
+  if (lb > ub + etol || ub < nl - etol || lb > nu + etol) is_inf = true;
+  else { if (lb > nl) nl = lb; if (ub < nu) nu = ub; }
+}
+
+// forward sweep of [Var, Var, Mult]: leaves clamped, product of node a0 and node a1
+template <class R>
+__device__ __forceinline__ void bilinear_forward(const TapeView &t, double2 b0, double2 b1, double nl[2], double nu[2],
+                                                 double &ol, double &ou)
+{
+  nl[0] = (b0.x < -kMinfty) ? -INFINITY : b0.x; nu[0] = (b0.y > kMinfty) ? INFINITY : b0.y;
+  nl[1] = (b1.x < -kMinfty) ? -INFINITY : b1.x; nu[1] = (b1.y > kMinfty) ? INFINITY : b1.y;
+  const bool swap = t.a0[2] != 0;            // warp-uniform: which variable node is the left operand
+  bounds_on_product<R>(true, swap ? nl[1] : nl[0], swap ? nu[1] : nu[0], swap ? nl[0] : nl[1], swap ? nu[0] : nu[1], ol, ou);
+  clamp25(ol, ou);
+}
+
+template <class R>
+__device__ __forceinline__ void sumsq_forward(const TapeView &t, double2 b0, double2 b1, double nl[2], double nu[2],
+                                              double sl[2], double su[2], double &ol, double &ou)
+{
+  nl[0] = (b0.x < -kMinfty) ? -INFINITY : b0.x; nu[0] = (b0.y > kMinfty) ? INFINITY : b0.y;
+  nl[1] = (b1.x < -kMinfty) ? -INFINITY : b1.x; nu[1] = (b1.y > kMinfty) ? INFINITY : b1.y;
+  const bool s2 = t.a0[2] != 0, s3 = t.a0[3] != 0;
+  bounds_on_square<R>(s2 ? nl[1] : nl[0], s2 ? nu[1] : nu[0], sl[0], su[0]); clamp25(sl[0], su[0]);
+  bounds_on_square<R>(s3 ? nl[1] : nl[0], s3 ? nu[1] : nu[0], sl[1], su[1]); clamp25(sl[1], su[1]);
+  ol = R::add_lo(R::add_lo(0.0, sl[0]), sl[1]);
+  ou = R::add_hi(R::add_hi(0.0, su[0]), su[1]);
+  clamp25(ol, ou);
+}
+
 // NlPresHandler::chkRed_ for one constraint (NlPresHandler.cpp:101-208, nlf branch):
 // returns 0 ok, 3 infeasible, 4 evaluation error
 template <class R>
 __device__ __forceinline__ int nl_chk_red(const ConsView &V, const double2 *bx, int64_t ld, double *nlb, double *nub)
 {
   const TapeView &t = V.t;
+  if (V.shape != kShapeGeneric) {
+    const double2 b0 = bx[(int64_t)t.a0[0] * ld], b1 = bx[(int64_t)t.a0[1] * ld];     // both gathers in flight
+    double nl[2], nu[2], ol, ou;
+    if (V.shape == kShapeBilinear) bilinear_forward<R>(t, b0, b1, nl, nu, ol, ou);
+    else { double sl[2], su[2]; sumsq_forward<R>(t, b0, b1, nl, nu, sl, su, ol, ou); }
+    double lfl, lfu;
+    lin_part_bounds<R>(V, bx, ld, lfl, lfu);
+    const double impl_lb = R::add_lo(ol, lfl), impl_ub = R::add_hi(ou, lfu);
+    return (impl_ub + 1e-6 < V.c_lb || impl_lb - 1e-6 > V.c_ub) ? 3 : 0;
+  }
   int error = 0;
   tape_forward<R>(V, nlb, nub, bx, ld, error);
   if (error != 0) return 4;
@@ -514,6 +583,75 @@ __device__ __forceinline__ int nl_var_bound_mods(const ConsView &V, double2 *bx,
   lin_part_bounds<R>(V, bx, ld, lfl, lfu);
   const double ub_in = R::sub_hi(V.c_ub, lfl), lb_in = R::sub_lo(V.c_lb, lfu);
   int error = 0;
+  if (V.shape != kShapeGeneric) {
+    double2 *p0 = bx + (int64_t)t.a0[0] * ld, *p1 = bx + (int64_t)t.a0[1] * ld;
+    double2 b0 = *p0, b1 = *p1;
+    double nl[2], nu[2], ol, ou;
+    bool is_inf = false;
+    if (V.shape == kShapeBilinear) {
+      bilinear_forward<R>(t, b0, b1, nl, nu, ol, ou);
+      ol = fmax(lb_in, ol); ou = fmin(ub_in, ou);
+      // reverse rule of OpMult (CNode.cpp:1344-1349): left child from out / right, then right child from out / the
+      // ALREADY TIGHTENED left child
+      const bool swap = t.a0[2] != 0;            // warp-uniform: node 1 is the left operand
+      double Ll = swap ? nl[1] : nl[0], Lu = swap ? nu[1] : nu[0], Rl = swap ? nl[0] : nl[1], Ru = swap ? nu[0] : nu[1];
+      double lb, ub;
+      bounds_on_div<R>(ol, ou, Rl, Ru, lb, ub);
+      prop_reg(lb, ub, Ll, Lu, is_inf, error);
+      bounds_on_div<R>(ol, ou, Ll, Lu, lb, ub);
+      prop_reg(lb, ub, Rl, Ru, is_inf, error);
+      if (is_inf) return 3;
+      if (error > 0) return 4;
+      nl[0] = swap ? Rl : Ll; nu[0] = swap ? Ru : Lu; nl[1] = swap ? Ll : Rl; nu[1] = swap ? Lu : Ru;
+    } else {
+      double sl[2], su[2];
+      sumsq_forward<R>(t, b0, b1, nl, nu, sl, su, ol, ou);
+      ol = fmax(lb_in, ol); ou = fmin(ub_in, ou);
+      // reverse rule of OpSumList over the two squares (CNode.cpp:1413-1481, its tub = -inf defect included); the
+      // reverse rule of OpSqr is a no-op in the reference (:1399-1403), so the variable nodes never move
+      bool inf_lb = false, inf_ub = false;
+      double lb = 0.0, ub = 0.0;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (sl[c] > -INFINITY) lb = R::add_lo(lb, sl[c]); else if (inf_lb) { lb = -INFINITY; break; } else inf_lb = true;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (su[c] < INFINITY) ub = R::add_hi(ub, su[c]); else if (inf_ub) { ub = INFINITY; break; } else inf_ub = true;
+      }
+      if (lb > -INFINITY || ub < INFINITY) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          double tlb, tub;
+          if (ub < INFINITY) {
+            if (!inf_ub) tlb = R::sub_lo(ol, R::sub_hi(ub, su[c]));
+            else if (su[c] < INFINITY) tlb = -INFINITY;
+            else tlb = R::sub_lo(ol, ub);
+          } else tlb = -INFINITY;
+          if (lb > -INFINITY) {
+            if (!inf_lb) tub = R::sub_hi(ou, R::sub_lo(lb, sl[c]));
+            else if (sl[c] > -INFINITY) tub = INFINITY;
+            else tub = R::sub_hi(ou, lb);
+          } else tub = -INFINITY;
+          prop_reg(tlb, tub, sl[c], su[c], is_inf, error);
+          if (is_inf) break;
+        }
+      }
+      if (is_inf) return 3;
+      if (error > 0) return 4;
+    }
+    // harvest (CGraph.cpp:1627-1641): variable nodes in ascending id; both tests read the variable's bounds before
+    // any mod of this call is applied (the two variables are distinct)
+    bool ch0 = false, ch1 = false;
+    const double2 o0 = b0, o1 = b1;
+    if (nl[0] > o0.x + bslack10) { b0.x = nl[0] - bslack; ++n_mods; ch0 = true; }
+    if (nu[0] < o0.y - bslack10) { b0.y = nu[0] + bslack; ++n_mods; ch0 = true; }
+    if (ch0) *p0 = b0;
+    if (nl[1] > o1.x + bslack10) { b1.x = nl[1] - bslack; ++n_mods; ch1 = true; }
+    if (nu[1] < o1.y - bslack10) { b1.y = nu[1] + bslack; ++n_mods; ch1 = true; }
+    if (ch1) *p1 = b1;
+    return 0;
+  }
   tape_forward<R>(V, nlb, nub, bx, ld, error);
   if (error > 0) return 4;
   const int o = t.nn - 1;

@@ -95,15 +95,46 @@ struct RoundsWs {
   double *nlb;     // [n+1] lower-bound candidates (all-reduced with MAX); [n] = row-infeasible flag
   double *nub;     // [n]   upper-bound candidates (all-reduced with MIN)
   uint32_t *bits;  // [(m+31)/32] this rank's due rows   (Constraint bFlag)
-  int32_t *ctrl;   // [8] [0] changed [1] int moved [2] next list length [3] verdict [4] changed pairs
-                   //     [5] sparse exchange overflowed: the vars kernel did nothing, redo the merge densely
+  int32_t *ctrl;   // [16] see kRc*
   unsigned long long *counters;  // [2] nnz_updates, rows evaluated (this rank)
-  // sparse bound exchange (row-partitioned mode, rounds with few moved bounds): this rank's changed candidates
+  // Per-round work proportional to the CHANGES: a variable that receives a candidate (from this rank's rows or, after
+  // the exchange, from another rank's) goes on the round's touched list -- once: tbits says who is on it -- and the
+  // merge, the integer rounding, the bound check and the row flagging walk that list instead of all n variables.
+  uint32_t *tbits; // [(n+31)/32]
+  int32_t *tlist;  // [n]   (ctrl[kRcTouched] entries)
+  uint32_t *ebits; // [(n+31)/32] variable moved in some round of this call: the only ones the finish kernel writes back
+  int32_t *elist;  // [n]   (ctrl[kRcEver] entries)
+  int32_t *progress;  // [4] pinned, mapped host words {round finished, stop, verdict, changed}: the host polls them
+                      //     WITHOUT synchronising the stream and keeps enqueuing rounds while the loop goes on
+  // sparse bound exchange over NCCL (fallback when peer memory is unavailable): this rank's changed candidates
   // {count, row-infeasible flag | entries {lb, ub, j}} are all-gathered instead of all-reducing 16 bytes per variable
   BoundMsg *xsend; // [1 + xcap]  header + entries of this rank
   BoundMsg *xrecv; // [n_ranks][1 + xcap]
   int32_t xcap;    // entries a rank can send (0: no sparse exchange)
   int32_t n_ranks;
+  int32_t rank;
+  // bound exchange over NVLink peer memory (one process per GPU, buffers shared with CUDA IPC): every rank PUSHES its
+  // touched candidates into every peer's inbox and raises the peer's round tag; no host in the loop, no collective
+  // call.  Inboxes are double-buffered by round parity (a peer can be at most one round ahead).
+  int32_t p2p;               // 1: peer-memory exchange is set up
+  int64_t inbox_stride;      // entries per (parity, sender) slot: 1 header + capacity (= n: a message always fits)
+  BoundMsg *inbox;           // [2][n_ranks][inbox_stride]  this rank's inbox
+  unsigned *inbox_tag;       // [n_ranks] last round whose message from rank r is complete
+  BoundMsg *const *peer_inbox;   // [n_ranks] device array: peers' inbox base pointers (own entry unused)
+  unsigned *const *peer_tag;     // [n_ranks] peers' tag arrays
 };
+// ctrl words of the per-round kernels
+constexpr int kRcChanged = 0;   // a bound moved in this round
+constexpr int kRcIntMoved = 1;  // a row moved an integer variable in this round
+constexpr int kRcTouched = 2;   // length of tlist
+constexpr int kRcVerdict = 3;
+constexpr int kRcPairs = 4;     // changed (variable, round) pairs of the call
+constexpr int kRcOverflow = 5;  // NCCL sparse exchange overflowed: the vars kernel did nothing, redo the merge densely
+constexpr int kRcStop = 6;      // the loop is over: every later kernel of the call returns at once
+constexpr int kRcRound = 7;     // rounds finished
+constexpr int kRcEver = 8;      // length of elist
+constexpr int kRcDoneA = 9;     // blocks of the current push kernel that have finished
+constexpr int kRcDoneB = 10;    // ... of the current vars kernel
+constexpr int kRcWords = 16;
 
 }  // namespace mntr

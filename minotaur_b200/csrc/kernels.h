@@ -27,6 +27,14 @@ cudaError_t launch_rounds_compact(const LinDev &P, const RoundsWs &W, int cap, i
 cudaError_t launch_rounds_apply(const LinDev &P, const RoundsWs &W, int rank, int cap, int sm_count, cudaStream_t stream);
 cudaError_t launch_rounds_finish(const LinDev &P, const RoundsWs &W, double *lb_dev, double *ub_dev, int sm_count,
                                  cudaStream_t stream);
+// list-based phases: work proportional to the variables that received a candidate in the round
+cudaError_t launch_rounds_vars_list(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream);
+cudaError_t launch_rounds_finalize(const LinDev &P, const RoundsWs &W, int max_rounds, int loop_mode, cudaStream_t stream);
+cudaError_t launch_rounds_clear_list(const RoundsWs &W, int sm_count, cudaStream_t stream);
+// bound exchange over NVLink peer memory: push this rank's touched candidates into every peer's inbox and raise the
+// round tag there; wait for the peers' tags and merge their candidates
+cudaError_t launch_rounds_push(const LinDev &P, const RoundsWs &W, unsigned tag, int sm_count, cudaStream_t stream);
+cudaError_t launch_rounds_pull(const LinDev &P, const RoundsWs &W, unsigned tag, int sm_count, cudaStream_t stream);
 
 // per-box outputs / controls of the batched kernels
 struct BatchIo {
@@ -63,13 +71,18 @@ cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub,
 cudaError_t launch_apply_deltas(const long long *delta_ptr, const int32_t *delta_var,
                                 const uint8_t *delta_is_upper, const double *delta_val,
                                 int32_t n_boxes, double2 *boxes, int64_t ld, cudaStream_t stream);
-// mods = final bounds that differ from the box's initial bounds (root + the box's deltas); no copy of the initial boxes
+// mods = final bounds that differ from the box's initial bounds (root + the box's deltas); no copy of the initial boxes.
+// count: strip_cnt [ceil(n/256)][ld] receives, per box, the EXCLUSIVE offsets of the 256-variable strips, mod_count the
+// box's ordered mods, extra_count the unordered extras (deltas that loosen the root).  emit: ascending (variable, side)
+// at mod_ptr[b] + strip offset; the extras at extra_at[b] ...
 cudaError_t launch_count_mods(const double2 *boxes, const double *root_lb, const double *root_ub, const long long *delta_ptr,
                               const int32_t *delta_var, const uint8_t *delta_is_upper, const double *delta_val, int64_t ld,
-                              int32_t n, int32_t n_boxes, long long *mod_count, cudaStream_t stream);
+                              int32_t n, int32_t n_boxes, int32_t *strip_cnt, long long *mod_count, long long *extra_count,
+                              cudaStream_t stream);
 cudaError_t launch_emit_mods(const double2 *boxes, const double *root_lb, const double *root_ub, const long long *delta_ptr,
                              const int32_t *delta_var, const uint8_t *delta_is_upper, const double *delta_val, int64_t ld,
-                             int32_t n, int32_t n_boxes, const long long *mod_ptr, long long *cursor, long long cap,
-                             int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val, cudaStream_t stream);
+                             int32_t n, int32_t n_boxes, const int32_t *strip_off, const long long *mod_ptr,
+                             const long long *extra_at, long long cap, int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val,
+                             cudaStream_t stream);
 
 }  // namespace mntr

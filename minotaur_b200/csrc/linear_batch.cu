@@ -42,7 +42,8 @@ namespace mntr {
 
 namespace {
 
-constexpr int kBatchWarps = 16;
+constexpr int kBatchWarps = 12;         // warps per CTA of the instantiation with CGraph tapes (85 registers per thread at two CTAs per SM: the interval code spills at 64)
+constexpr int kLinWarps = 8;            // ... of the pure linear one (two 12 KB segment stages per warp, two CTAs per SM)
 constexpr int kBatchThreads = kBatchWarps * 32;
 constexpr int kGather = 4;             // independent 512-byte gathers a warp keeps in flight
 constexpr unsigned kFull = 0xffffffffu;
@@ -61,11 +62,13 @@ static_assert(sizeof(TileShared) == kTileStateBytes, "BatchIo::tstate stride");
 struct TileTeam {
   int gwarp, n_warps;       // this warp / warps in the cluster
   int cthread, n_threads;   // this thread / threads in the cluster
+  bool solo;                // the cluster is one CTA: the level barrier is a plain bar.sync
   // bounds written with ordinary stores in this phase are read by bulk async copies (async proxy) in the next
   __device__ __forceinline__ void sync() const
   {
     asm volatile("fence.proxy.async;" ::: "memory");
-    cg::this_cluster().sync();
+    if (solo) __syncthreads();
+    else cg::this_cluster().sync();
   }
 };
 __device__ __forceinline__ TileTeam make_team()
@@ -73,10 +76,12 @@ __device__ __forceinline__ TileTeam make_team()
   cg::cluster_group cl = cg::this_cluster();
   TileTeam t;
   const int nb = (int)cl.num_blocks(), rk = (int)cl.block_rank();
-  t.gwarp = rk * kBatchWarps + (threadIdx.x >> 5);
-  t.n_warps = nb * kBatchWarps;
-  t.cthread = rk * kBatchThreads + threadIdx.x;
-  t.n_threads = nb * kBatchThreads;
+  const int wpb = (int)(blockDim.x >> 5);
+  t.gwarp = rk * wpb + (threadIdx.x >> 5);
+  t.n_warps = nb * wpb;
+  t.cthread = rk * (int)blockDim.x + threadIdx.x;
+  t.n_threads = nb * (int)blockDim.x;
+  t.solo = nb == 1;
   return t;
 }
 
@@ -90,14 +95,34 @@ __device__ __forceinline__ TileTeam make_team()
 struct RowStage {
   double *val;    // [32] this warp's slice
   int *col;       // [32]
-  double2 *seg;   // [kSegEntries][32] {lb,ub} of the row's variables for the 32 boxes of the tile (TMA destination)
-  uint64_t *bar;  // mbarrier of the bulk copies into seg
+  double2 *seg;   // [2][kSegEntries][32] {lb,ub} of a row's variables for the 32 boxes of the tile (TMA destination),
+                  // two pipeline slots: the next row's segments are in flight while this row is evaluated
+  uint64_t *bar;  // [2] mbarriers of the bulk copies into the two slots
 };
 
 // ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared, completion on an mbarrier ----
 constexpr int kSegEntries = 12;                      // rows of up to this many terms are staged
 constexpr int kSegBytes = kTile * (int)sizeof(double2);   // 512 B: one variable, the 32 boxes of the tile
-constexpr int kSegSmemBytes = kBatchWarps * kSegEntries * kSegBytes;   // dynamic shared memory of a CTA
+constexpr int kSegSlotBytes = kSegEntries * kSegBytes;                 // one pipeline slot of one warp: 6 KB
+// dynamic shared memory of a warp of the pure linear instantiation: two segment slots, then per slot the row's
+// coefficients (16 doubles) and columns (16 ints).  Addressed through the symbol below, so that the compiler knows the
+// address space (LDS / STS with immediate offsets instead of generic loads with 64-bit address arithmetic).
+constexpr int kEntSlotBytes = 16 * 8 + 16 * 4;
+constexpr int kWarpSmemBytes = 2 * kSegSlotBytes + 2 * kEntSlotBytes;
+constexpr int kSegSmemBytes = kLinWarps * kWarpSmemBytes;              // dynamic shared memory of a (pure linear) CTA
+extern __shared__ __align__(128) unsigned char dyn_smem[];
+__device__ __forceinline__ double2 *slot_seg(int wl, int slot)
+{
+  return reinterpret_cast<double2 *>(dyn_smem + wl * kWarpSmemBytes + slot * kSegSlotBytes);
+}
+__device__ __forceinline__ double *slot_val(int wl, int slot)
+{
+  return reinterpret_cast<double *>(dyn_smem + wl * kWarpSmemBytes + 2 * kSegSlotBytes + slot * kEntSlotBytes);
+}
+__device__ __forceinline__ int *slot_col(int wl, int slot)
+{
+  return reinterpret_cast<int *>(dyn_smem + wl * kWarpSmemBytes + 2 * kSegSlotBytes + slot * kEntSlotBytes + 16 * 8);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -125,6 +150,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // a bulk async copy put into shared memory (one 512-byte segment per term), writes a changed bound into that copy
 // and through to global memory.
 struct BoxGlobal {
+  static constexpr bool kNeedsCol = true;
   static constexpr int kBatch = kGather;     // independent 512-byte gathers kept in flight
   double2 *bx; int64_t ld;
   __device__ __forceinline__ double2 load(int, int j) const { return bx[(int64_t)j * ld]; }
@@ -132,6 +158,7 @@ struct BoxGlobal {
   __device__ __forceinline__ void commit(int, int) const {}
 };
 struct BoxStaged {
+  static constexpr bool kNeedsCol = false;   // the staged copy is addressed by the term's position
   static constexpr int kBatch = 2;           // shared-memory reads: no need to batch deeply, keep registers free
   double2 *seg;            // this lane's column of the staged segments: entry t at seg[t * 32]
   double2 *bx; int64_t ld;
@@ -173,14 +200,22 @@ __device__ __forceinline__ void acc_term(double a, double2 b, double &ll, double
   ll = R::add_lo(ll, R::mul_lo(a, blo));
   uu = R::add_hi(uu, R::mul_hi(a, bhi));
 }
+// the largest reach |a| (ub - lb) of a row's terms (see row_update: a term whose reach is below the row's slack cannot
+// move a bound); an undefined width (inf - inf) counts as infinite
+__device__ __forceinline__ void acc_reach(double a, double2 b, double &wmax)
+{
+  const double d = b.y - b.x;
+  const double w = fabs(a) * d * 1.000000001;
+  wmax = fmax(wmax, (d == d) ? w : INFINITY);
+}
 
 // min / max activity of one row for this lane's box  [getLfBnds_].  Computed by every lane (lanes whose box
 // is not due simply discard the result): no predication in the loop.
 template <class R, class Box>
 __device__ __forceinline__ void row_activity(const LinDev &P, int beg, int cnt_row, const Box &box,
-                                             const RowStage &st, int lane, double &ll, double &uu)
+                                             const RowStage &st, int lane, double &ll, double &uu, double &wmax)
 {
-  ll = 0.0; uu = 0.0;
+  ll = 0.0; uu = 0.0; wmax = 0.0;
   for (int c0 = 0; c0 < cnt_row; c0 += 32) {
     const int cnt = next_chunk(P, beg, c0, cnt_row, st, lane);
     int t = 0;
@@ -188,11 +223,15 @@ __device__ __forceinline__ void row_activity(const LinDev &P, int beg, int cnt_r
     for (; t + kB <= cnt; t += kB) {
       double a[kB]; double2 b[kB];
 #pragma unroll
-      for (int u = 0; u < kB; ++u) { a[u] = st.val[t + u]; b[u] = box.load(t + u, st.col[t + u]); }
+      for (int u = 0; u < kB; ++u) { a[u] = st.val[t + u]; b[u] = box.load(t + u, Box::kNeedsCol ? st.col[t + u] : 0); }
 #pragma unroll
-      for (int u = 0; u < kB; ++u) acc_term<R>(a[u], b[u], ll, uu);
+      for (int u = 0; u < kB; ++u) { acc_term<R>(a[u], b[u], ll, uu); acc_reach(a[u], b[u], wmax); }
     }
-    for (; t < cnt; ++t) acc_term<R>(st.val[t], box.load(t, st.col[t]), ll, uu);
+    for (; t < cnt; ++t) {
+      const double a = st.val[t];
+      const double2 b = box.load(t, Box::kNeedsCol ? st.col[t] : 0);
+      acc_term<R>(a, b, ll, uu); acc_reach(a, b, wmax);
+    }
   }
 }
 
@@ -330,8 +369,8 @@ __device__ __forceinline__ void process_row(const LinDev &P, int2 info, double2 
 {
   const int beg = info.x, cnt = info.y, end = beg + cnt;
   const double rl = bnd.x, ru = bnd.y;
-  double ll, uu, sing_ll = -INFINITY, sing_uu = INFINITY;
-  row_activity<R>(P, beg, cnt, box, st, lane, ll, uu);
+  double ll, uu, wmax, sing_ll = -INFINITY, sing_uu = INFINITY;
+  row_activity<R>(P, beg, cnt, box, st, lane, ll, uu, wmax);
   bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
   if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
   if (mine) my_nnz += (unsigned long long)cnt;
@@ -346,14 +385,17 @@ __device__ __forceinline__ void process_row(const LinDev &P, int2 info, double2 
     else if (sing_uu < kInf20) { do_lb = true; s_lb = true; act = sing_uu; }
   }
   unsigned chg = 0;
-  if (__any_sync(kFull, do_lb))
+  // the whole pass is skipped when no box of the tile has a slack below the row's largest reach: no term of the row
+  // can move a bound then (the per-term test of row_update, taken once for the row; the common case)
+  if (__any_sync(kFull, do_lb && !(-R::sub_lo(rl, act) > wmax)))
     chg = row_update<R, true>(P, beg, cnt, box, st, do_lb, s_lb, rl, act, flags, varflag, sh, lane);
   // recompute activities when FromLb changed something (:1027-1032); lanes that did not
   // change would recompute identical values, so the decision is taken per warp
   if (chg) {
     const bool redo = mine && ((chg >> lane) & 1u);
-    double l2, u2;
-    row_activity<R>(P, beg, cnt, box, st, lane, l2, u2);
+    double l2, u2, w2;
+    row_activity<R>(P, beg, cnt, box, st, lane, l2, u2, w2);
+    wmax = w2;          // this lane's box as it is now (lanes that changed nothing recompute what they had)
     if (redo) { ll = l2; uu = u2; }
     need_sing = redo && (ll < -kInf20 || uu > kInf20);
     if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
@@ -364,7 +406,86 @@ __device__ __forceinline__ void process_row(const LinDev &P, int2 info, double2 
     if (ll > -kInf20) { do_ub = true; act = ll; }
     else if (sing_ll > -kInf20) { do_ub = true; s_ub = true; act = sing_ll; }
   }
-  if (__any_sync(kFull, do_ub))
+  if (__any_sync(kFull, do_ub && !(R::sub_hi(ru, act) > wmax)))
+    (void)row_update<R, false>(P, beg, cnt, box, st, do_ub, s_ub, ru, act, flags, varflag, sh, lane);
+}
+
+// One STAGED row (at most kSegEntries terms, its {lb,ub} segments and entries in pipeline slot `slot` of warp `wl`) for
+// the 32 boxes of the tile: process_row with the common case made cheap.  The activity pass reads shared memory through
+// the dyn_smem symbol; the sign of a coefficient is warp-uniform (posmask, one bit per term), so the min / max selection
+// is a uniform branch; and whether ANY term of the row can move a bound is decided once per row from
+// amax * (largest width) >= every term's reach |a| (ub - lb) -- a conservative form of row_update's per-term test.
+// Only rows that pass it run the update passes (through the generic code above).
+template <class R>
+__device__ __forceinline__ void staged_row(const LinDev &P, int2 info, double2 bnd, int wl, int slot, unsigned posmask,
+                                           double amax, double2 *bx, int64_t ld, bool mine, uint32_t *flags, uint32_t *varflag,
+                                           TileShared &sh, int lane, unsigned long long &my_nnz)
+{
+  const int cnt = info.y;
+  const double rl = bnd.x, ru = bnd.y;
+  const double2 *sg = slot_seg(wl, slot) + lane;
+  const double *sv = slot_val(wl, slot);
+  double ll = 0.0, uu = 0.0;
+  int dhi = 0;            // high word of the largest width (ub - lb) seen: negative widths and zero never win, an
+                          // infinite or undefined one makes the bound below infinite / NaN, i.e. "cannot skip"
+  // one term: the sign of the coefficient is warp-uniform (posmask, extracted into predicates several bits at a time)
+  auto term = [&](int t, double a, double2 b) {
+    const bool pos = (posmask >> t) & 1u;
+    const double blo = pos ? b.x : b.y, bhi = pos ? b.y : b.x;
+    ll = R::add_lo(ll, R::mul_lo(a, blo));
+    uu = R::add_hi(uu, R::mul_hi(a, bhi));
+    dhi = max(dhi, __double2hiint(b.y - b.x));
+  };
+  int t0 = 0;
+#pragma unroll
+  for (int c = 0; c < kSegEntries / 4; ++c) {                 // four terms' loads in flight together
+    if (t0 + 4 <= cnt) {
+      double a[4]; double2 b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u] = sv[c * 4 + u]; b[u] = sg[(c * 4 + u) * kTile]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) term(c * 4 + u, a[u], b[u]);
+      t0 += 4;
+    }
+  }
+  for (int t = t0; t < cnt; ++t) term(t, sv[t], sg[t * kTile]);
+  // >= every term's reach |a| (ub - lb) 1.000000001: amax >= |a|, and the width rounded up to the next high word
+  const double wmax = amax * __hiloint2double(dhi + 1, 0) * 1.000000001;
+  const RowStage st{slot_val(wl, slot), slot_col(wl, slot), nullptr, nullptr};
+  const BoxStaged box{slot_seg(wl, slot) + lane, bx, ld};
+  const int beg = info.x, end = beg + cnt;
+  double sing_ll = -INFINITY, sing_uu = INFINITY;
+  bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
+  if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
+  if (mine) my_nnz += (unsigned long long)cnt;
+  if (mine && (ll > ru + kETol || uu < rl - kETol)) {       // :994-1015
+    sh.verdict[lane] = 2;  /* MNTR_INFEAS_ROW */
+    mine = false;
+  }
+  bool do_lb = false, s_lb = false; double act = 0.0;        // row lb side  (:1017-1025)
+  if (mine && rl > -kInf20) {
+    if (uu < kInf20) { do_lb = true; act = uu; }
+    else if (sing_uu < kInf20) { do_lb = true; s_lb = true; act = sing_uu; }
+  }
+  unsigned chg = 0;
+  double w2 = wmax;
+  if (__any_sync(kFull, do_lb && !(-R::sub_lo(rl, act) > wmax))) {
+    chg = row_update<R, true>(P, beg, cnt, box, st, do_lb, s_lb, rl, act, flags, varflag, sh, lane);
+    if (chg) {                                                // :1027-1032
+      const bool redo = mine && ((chg >> lane) & 1u);
+      double l2, u2;
+      row_activity<R>(P, beg, cnt, box, st, lane, l2, u2, w2);
+      if (redo) { ll = l2; uu = u2; }
+      need_sing = redo && (ll < -kInf20 || uu > kInf20);
+      if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
+    }
+  }
+  bool do_ub = false, s_ub = false; act = 0.0;               // row ub side  (:1035-1043)
+  if (mine && ru < kInf20) {
+    if (ll > -kInf20) { do_ub = true; act = ll; }
+    else if (sing_ll > -kInf20) { do_ub = true; s_ub = true; act = sing_ll; }
+  }
+  if (__any_sync(kFull, do_ub && !(R::sub_hi(ru, act) > w2)))
     (void)row_update<R, false>(P, beg, cnt, box, st, do_ub, s_ub, ru, act, flags, varflag, sh, lane);
 }
 
@@ -385,7 +506,8 @@ __device__ __noinline__ void cutoff_row(const LinDev &P, double2 *bx, int64_t ld
     double ll, uu, sing_ll = INFINITY, sing_uu = INFINITY;
     const BoxGlobal box{bx, ld};
     stage_short(C, 0, cnt, st, lane);
-    row_activity<R>(C, 0, cnt, box, st, lane, ll, uu);
+    double wmax;
+    row_activity<R>(C, 0, cnt, box, st, lane, ll, uu, wmax);
     const bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
     if (__any_sync(kFull, need_sing)) row_sing_activity<R>(C, 0, cnt, bx, ld, need_sing, sing_ll, sing_uu);
     if (mine) my_nnz += (unsigned long long)cnt;
@@ -435,7 +557,7 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
                                                  int max_rounds, int bad_row, unsigned long long &my_nnz,
                                                  bool &any_change, unsigned &seg_phase)
 {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const double2 *tile_base = bx - lane;          // box 0 of the tile: + j*ld is variable j's 512-byte segment
   const TileTeam team = make_team();
   const int warp = team.gwarp;
@@ -481,29 +603,74 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
         int2 myinfo = make_int2(0, 0);
         double2 mybnd = make_double2(0.0, 0.0);
         if (fw != 0u) { myinfo = __ldg(P.row_info + q); mybnd = __ldg(P.row_bnd + q); }
-        while (rows) {
-          const int t = __ffs(rows) - 1;
-          rows &= rows - 1;
-          const int2 info = make_int2(__shfl_sync(kFull, myinfo.x, t), __shfl_sync(kFull, myinfo.y, t));
-          const double2 bnd = make_double2(__shfl_sync(kFull, mybnd.x, t), __shfl_sync(kFull, mybnd.y, t));
-          const uint32_t proc = __shfl_sync(kFull, fw, t);
-          if (lane == t) __stcg(flags + q, raw & ~proc);     // c_ptr->setBFlag(false), :513
-          stage_short(P, info.x, info.y, st, lane);
-          const bool mine = (proc >> lane) & 1u;
-          if (st.seg != nullptr && info.y <= kSegEntries) {
-            // TMA: one 512-byte bulk copy per term brings the {lb,ub} of that variable for the tile's 32 boxes into
-            // shared memory; all copies of the row are in flight at once and land on the warp's mbarrier
-            if (lane == 0) mbar_expect_tx(st.bar, (uint32_t)(info.y * kSegBytes));
-            __syncwarp();
-            if (lane < info.y) bulk_g2s(st.seg + lane * kTile, tile_base + (int64_t)st.col[lane] * ld, kSegBytes, st.bar);
-            mbar_wait(st.bar, seg_phase);
-            seg_phase ^= 1u;
-            const BoxStaged box{st.seg + lane, bx, ld};
-            process_row<R>(P, info, bnd, box, bx, ld, st, mine, flags, varflag, sh, lane, my_nnz);
-          } else {
+        if (fw != 0u) __stcg(flags + q, raw & ~fw);         // c_ptr->setBFlag(false), :513 (rows of a level share no variable,
+                                                            // so nothing sets a flag of this chunk while it is worked on)
+        if (st.seg == nullptr) {
+          while (rows) {
+            const int t = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const int2 info = make_int2(__shfl_sync(kFull, myinfo.x, t), __shfl_sync(kFull, myinfo.y, t));
+            const double2 bnd = make_double2(__shfl_sync(kFull, mybnd.x, t), __shfl_sync(kFull, mybnd.y, t));
+            const bool mine = (__shfl_sync(kFull, fw, t) >> lane) & 1u;
+            stage_short(P, info.x, info.y, st, lane);
             const BoxGlobal box{bx, ld};
             process_row<R>(P, info, bnd, box, bx, ld, st, mine, flags, varflag, sh, lane, my_nnz);
           }
+          continue;
+        }
+        // ---- software pipeline over the chunk's due rows, three stages deep:
+        //   A  entry t of the row after next is requested into registers (lane t),
+        //   B  the next row's entries go to its slot and one 512-byte TMA bulk copy per term brings the {lb,ub} of that
+        //      variable for the tile's 32 boxes into the slot's segments (all copies of the row in flight at once, landing
+        //      on the slot's mbarrier),
+        //   C  this row is evaluated from its slot.
+        // Rows of a level share no variable, so a row's segments may be fetched while earlier rows of the level still
+        // write bounds.  Rows longer than kSegEntries take no slot and gather straight from global memory.
+        auto pop = [](unsigned &m) { const int t = m ? __ffs(m) - 1 : -1; m &= m - 1; return t; };
+        auto entries = [&](int r, int &cnt, int &c, double &v) {        // stage A
+          const int beg = __shfl_sync(kFull, myinfo.x, r);
+          cnt = __shfl_sync(kFull, myinfo.y, r);
+          c = 0; v = 0.0;
+          if (cnt <= kSegEntries && lane < cnt) { c = __ldg(P.col + beg + lane); v = __ldg(P.val + beg + lane); }
+        };
+        // stage B; returns the row's sign mask (bit t: coefficient t positive) and largest |coefficient| (rounded up)
+        auto launch = [&](int slot, int cnt, int c, double v, unsigned &posmask, double &amax) {
+          posmask = __ballot_sync(kFull, v > 0.0);
+          amax = (double)__uint_as_float(__reduce_max_sync(kFull, __float_as_uint(__double2float_ru(fabs(v)))));
+          if (cnt > kSegEntries) return;
+          if (lane < cnt) { slot_col(wl, slot)[lane] = c; slot_val(wl, slot)[lane] = v; }
+          if (lane == 0) mbar_expect_tx(st.bar + slot, (uint32_t)(cnt * kSegBytes));
+          if (lane < cnt) bulk_g2s(slot_seg(wl, slot) + lane * kTile, tile_base + (int64_t)c * ld, kSegBytes, st.bar + slot);
+          __syncwarp();
+        };
+        unsigned todo = rows;
+        int rC = pop(todo), cntC, cA = 0, cntA = 0; double vA = 0.0;
+        unsigned posC = 0u, posB = 0u; double amaxC = 0.0, amaxB = 0.0;
+        int slot = 0;
+        { int c; double v; entries(rC, cntC, c, v); launch(slot, cntC, c, v, posC, amaxC); }
+        int rA = pop(todo);
+        if (rA >= 0) entries(rA, cntA, cA, vA);
+        while (rC >= 0) {
+          const int rB = rA, cntB = cntA;
+          if (rB >= 0) {
+            launch(slot ^ 1, cntB, cA, vA, posB, amaxB);
+            rA = pop(todo);
+            if (rA >= 0) entries(rA, cntA, cA, vA);
+          }
+          const int2 info = make_int2(__shfl_sync(kFull, myinfo.x, rC), cntC);
+          const double2 bnd = make_double2(__shfl_sync(kFull, mybnd.x, rC), __shfl_sync(kFull, mybnd.y, rC));
+          const bool mine = (__shfl_sync(kFull, fw, rC) >> lane) & 1u;
+          if (cntC <= kSegEntries) {
+            mbar_wait(st.bar + slot, (seg_phase >> slot) & 1u);
+            seg_phase ^= 1u << slot;
+            staged_row<R>(P, info, bnd, wl, slot, posC, amaxC, bx, ld, mine, flags, varflag, sh, lane, my_nnz);
+          } else {
+            stage_short(P, info.x, info.y, st, lane);                 // chunk staging of long rows
+            const BoxGlobal box{bx, ld};
+            process_row<R>(P, info, bnd, box, bx, ld, st, mine, flags, varflag, sh, lane, my_nnz);
+          }
+          __syncwarp();                                               // the slot may be refilled
+          rC = rB; cntC = cntB; posC = posB; amaxC = amaxB; slot ^= 1;
         }
       }
       team.sync();
@@ -674,20 +841,20 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
 // directly (use_tma == 0: no dynamic shared memory), which leaves the L1 to the interpreter's per-thread node
 // intervals, and stages the tapes instead.
 template <class R, bool HAS_NL>
-__global__ void __launch_bounds__(kBatchThreads, 2)
+__global__ void __launch_bounds__(HAS_NL ? kBatchThreads : kLinWarps * 32, 2)
 fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int max_rounds, int lin_enabled,
                             int nl_enabled_arg, int use_tma)
 {
+  constexpr int kWarps = HAS_NL ? kBatchWarps : kLinWarps;
   const int nl_enabled = HAS_NL ? nl_enabled_arg : 0;
-  __shared__ double s_val[kBatchWarps][32];
-  __shared__ int s_col[kBatchWarps][32];
-  __shared__ __align__(8) uint64_t s_bar[kBatchWarps];
-
-  extern __shared__ __align__(128) unsigned char s_seg[];       // [kBatchWarps][kSegEntries][32] double2: TMA destination
+  // per warp: chunk staging of long rows (and of the cut-off row), mbarriers of the two pipeline slots
+  __shared__ double s_val[kWarps][32];
+  __shared__ int s_col[kWarps][32];
+  __shared__ __align__(8) uint64_t s_bar[kWarps][2];
+  // dyn_smem: pure linear instantiation: kWarpSmemBytes per warp (segment slots + entries); with tapes: BatchStage per warp
   const int wl = threadIdx.x >> 5;
-  const RowStage st{s_val[wl], s_col[wl],
-                    use_tma ? reinterpret_cast<double2 *>(s_seg) + (size_t)wl * kSegEntries * kTile : nullptr, &s_bar[wl]};
-  if ((threadIdx.x & 31) == 0) mbar_init(st.bar, 1);
+  const RowStage st{s_val[wl], s_col[wl], use_tma ? slot_seg(wl, 0) : nullptr, s_bar[wl]};
+  if ((threadIdx.x & 31) == 0) { mbar_init(st.bar, 1); mbar_init(st.bar + 1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   unsigned seg_phase = 0u;
@@ -707,7 +874,7 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
   // checkBounds_ rows part is static: a row with lb > ub + eTol makes every box infeasible
   // (every CTA of the cluster scans all rows, so the flag is identical cluster-wide)
   int bad_row = 0;
-  for (int i = threadIdx.x; i < P.m; i += kBatchThreads) {
+  for (int i = threadIdx.x; i < P.m; i += (int)blockDim.x) {
     const double2 bnd = __ldg(P.row_bnd + i);
     if (__ldg(P.row_info + i).y >= 0 && bnd.x > bnd.y + kETol) bad_row = 1;
   }
@@ -724,7 +891,7 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
                                         my_nnz, lin_changed, seg_phase);
     if constexpr (HAS_NL) {
       // the NL instantiation uses the dynamic shared memory for the tape batches (no TMA segments: use_tma == 0)
-      if (nl_enabled) my_rounds += nl_tile_presolve<R>(P, N, bx, ld, sh, active, nl_changed, reinterpret_cast<BatchStage *>(s_seg)[wl], my_evals);
+      if (nl_enabled) my_rounds += nl_tile_presolve<R>(P, N, bx, ld, sh, active, nl_changed, reinterpret_cast<BatchStage *>(dyn_smem)[wl], my_evals);
     }
     // fixpoint mode with both handlers: go round again while the nonlinear sweeps still move bounds
     const bool again = (loop_mode == 0) && lin_enabled && nl_enabled && nl_changed && sh.verdict[lane] == 0 &&
@@ -841,42 +1008,79 @@ __device__ __forceinline__ double2 initial_bounds(const DeltaLists &D, int b, in
   return init;
 }
 
+// grid (strips of 256 variables, tiles of 32 boxes), 8 warps: warp w walks the variables [j0 + 32 w, j0 + 32 w + 32) in
+// ascending order, lane = box.  COUNT: the strip's count per box goes to strip_cnt[strip][box].  EMIT: the mods are
+// written in ascending (variable, side) order at mod_ptr[box] + strip_off[strip][box] + (the warps before this one).
 template <bool EMIT>
-__global__ void mods_kernel(const double2 *__restrict__ boxes, const double *__restrict__ rl, const double *__restrict__ ru,
-                            DeltaLists D, int64_t ld, int n, int n_boxes, long long *mod_count,
-                            const long long *__restrict__ mod_ptr, long long *cursor, long long cap, int32_t *mod_var,
-                            uint8_t *mod_is_upper, double *mod_val)
+__global__ void __launch_bounds__(256)
+mods_kernel(const double2 *__restrict__ boxes, const double *__restrict__ rl, const double *__restrict__ ru,
+            DeltaLists D, int64_t ld, int n, int n_boxes, int32_t *strip_cnt, const long long *__restrict__ mod_ptr,
+            long long cap, int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val)
 {
-  const int b = blockIdx.y * 32 + (threadIdx.x & 31);
-  const int j0 = blockIdx.x * 256 + (threadIdx.x >> 5), j1 = min(n, (blockIdx.x + 1) * 256);
-  if (b >= n_boxes) return;
+  __shared__ int s_cnt[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.y * 32 + lane;
+  const int j0 = blockIdx.x * 256 + w * 32, j1 = min(n, j0 + 32);
+  const bool live = b < n_boxes;
+  auto visit = [&](auto &&f) {
+    for (int j = j0; j < j1; ++j) {
+      const double2 v = boxes[(int64_t)j * ld + b];
+      const double2 r = make_double2(__ldg(rl + j), __ldg(ru + j));
+      if (v.x == r.x && v.y == r.y) continue;
+      const double2 o = initial_bounds(D, b, j, r);
+      const bool dl = v.x != r.x && v.x != o.x, du = v.y != r.y && v.y != o.y;
+      if (dl || du) f(j, v, dl, du);
+    }
+  };
   int cnt = 0;
-  for (int j = j0; j < j1; j += blockDim.x >> 5) {
-    const double2 v = boxes[(int64_t)j * ld + b];
-    const double2 r = make_double2(__ldg(rl + j), __ldg(ru + j));
-    if (v.x == r.x && v.y == r.y) continue;
-    const double2 o = initial_bounds(D, b, j, r);
-    const bool dl = v.x != r.x && v.x != o.x, du = v.y != r.y && v.y != o.y;
-    const int k = (int)dl + (int)du;
-    if (k == 0) continue;
-    if (!EMIT) { cnt += k; continue; }
-    long long at = mod_ptr[b] + (long long)atomicAdd(reinterpret_cast<unsigned long long *>(cursor + b), (unsigned long long)k);
-    if (dl) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 0; mod_val[at] = v.x; } ++at; }
-    if (du) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 1; mod_val[at] = v.y; } }
+  if (live) visit([&](int, double2, bool dl, bool du) { cnt += (int)dl + (int)du; });
+  s_cnt[w][lane] = cnt;
+  __syncthreads();
+  if (!EMIT) {
+    if (w == 0 && live) {
+      int tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += s_cnt[k][lane];
+      strip_cnt[(int64_t)blockIdx.x * ld + b] = tot;
+    }
+    return;
   }
-  if (!EMIT && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(mod_count + b), (unsigned long long)cnt);
+  if (!live || cnt == 0) return;
+  long long at = mod_ptr[b] + (long long)strip_cnt[(int64_t)blockIdx.x * ld + b];     // here: the strip's exclusive offset
+  for (int k = 0; k < w; ++k) at += s_cnt[k][lane];
+  visit([&](int j, double2 v, bool dl, bool du) {
+    if (dl) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 0; mod_val[at] = v.x; } ++at; }
+    if (du) { if (at < cap) { mod_var[at] = j; mod_is_upper[at] = 1; mod_val[at] = v.y; } ++at; }
+  });
 }
 
-// one thread per box: the sides its deltas set whose final bound EQUALS the root's but not the initial one
+// per box: exclusive scan of the strips' counts (in place) and the box's total
+__global__ void mods_scan_kernel(int32_t *strip_cnt, int n_strips, int64_t ld, int n_boxes, long long *mod_count)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_boxes) return;
+  int run = 0;
+  for (int s = 0; s < n_strips; ++s) {
+    const int c = strip_cnt[(int64_t)s * ld + b];
+    strip_cnt[(int64_t)s * ld + b] = run;
+    run += c;
+  }
+  mod_count[b] = (long long)run;
+}
+
+// one thread per box: the sides its deltas set whose final bound EQUALS the root's but not the initial one (only a
+// delta that LOOSENS the root bound can do that).  They are counted separately and emitted behind the box's ordered
+// mods; the host merges them in for the (rare) boxes that have any.
 template <bool EMIT>
 __global__ void mods_delta_kernel(const double2 *__restrict__ boxes, const double *__restrict__ rl, const double *__restrict__ ru,
-                                  DeltaLists D, int64_t ld, int n_boxes, long long *mod_count,
-                                  const long long *__restrict__ mod_ptr, long long *cursor, long long cap, int32_t *mod_var,
+                                  DeltaLists D, int64_t ld, int n_boxes, long long *extra_count,
+                                  const long long *__restrict__ extra_at, long long cap, int32_t *mod_var,
                                   uint8_t *mod_is_upper, double *mod_val)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_boxes) return;
   int cnt = 0;
+  long long at = EMIT ? extra_at[b] : 0;
   for (long long q = D.ptr[b]; q < D.ptr[b + 1]; ++q) {
     const int j = D.var[q];
     const bool up = D.up[q] != 0;
@@ -887,10 +1091,10 @@ __global__ void mods_delta_kernel(const double2 *__restrict__ boxes, const doubl
     const double fin = up ? v.y : v.x, root = up ? ru[j] : rl[j];
     if (fin != root || fin == D.val[q]) continue;
     if (!EMIT) { ++cnt; continue; }
-    const long long at = mod_ptr[b] + (long long)atomicAdd(reinterpret_cast<unsigned long long *>(cursor + b), 1ull);
     if (at < cap) { mod_var[at] = j; mod_is_upper[at] = up ? 1 : 0; mod_val[at] = fin; }
+    ++at;
   }
-  if (!EMIT && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(mod_count + b), (unsigned long long)cnt);
+  if (!EMIT) extra_count[b] = (long long)cnt;
 }
 
 }  // namespace
@@ -902,8 +1106,6 @@ cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, 
 {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(tiles * cluster));
-  cfg.blockDim = dim3(kBatchThreads);
-  cfg.dynamicSmemBytes = kSegSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -913,6 +1115,7 @@ cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (nl_enabled) {
+    cfg.blockDim = dim3(kBatchThreads);
     cfg.dynamicSmemBytes = kBatchWarps * sizeof(BatchStage);
     cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
@@ -920,6 +1123,8 @@ cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, 
     return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, true>, P, nl, io, loop_mode, max_rounds, lin_enabled,
                               nl_enabled, 0);
   }
+  cfg.blockDim = dim3(kLinWarps * 32);
+  cfg.dynamicSmemBytes = kSegSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSegSmemBytes);
   if (e != cudaSuccess) return e;
@@ -983,30 +1188,34 @@ cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub,
 
 cudaError_t launch_count_mods(const double2 *boxes, const double *root_lb, const double *root_ub, const long long *delta_ptr,
                               const int32_t *delta_var, const uint8_t *delta_is_upper, const double *delta_val, int64_t ld,
-                              int32_t n, int32_t n_boxes, long long *mod_count, cudaStream_t stream)
+                              int32_t n, int32_t n_boxes, int32_t *strip_cnt, long long *mod_count, long long *extra_count,
+                              cudaStream_t stream)
 {
   if (n <= 0 || n_boxes <= 0) return cudaSuccess;
   const DeltaLists D{delta_ptr, delta_var, delta_is_upper, delta_val};
-  dim3 grid((n + 255) / 256, (n_boxes + 31) / 32);
-  mods_kernel<false><<<grid, 256, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n, n_boxes, mod_count, nullptr, nullptr, 0,
-                                               nullptr, nullptr, nullptr);
-  mods_delta_kernel<false><<<(n_boxes + 127) / 128, 128, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n_boxes, mod_count, nullptr,
-                                                                     nullptr, 0, nullptr, nullptr, nullptr);
+  const int n_strips = (n + 255) / 256;
+  dim3 grid(n_strips, (n_boxes + 31) / 32);
+  mods_kernel<false><<<grid, 256, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n, n_boxes, strip_cnt, nullptr, 0, nullptr, nullptr,
+                                               nullptr);
+  mods_scan_kernel<<<(n_boxes + 127) / 128, 128, 0, stream>>>(strip_cnt, n_strips, ld, n_boxes, mod_count);
+  mods_delta_kernel<false><<<(n_boxes + 127) / 128, 128, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n_boxes, extra_count, nullptr,
+                                                                     0, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 
 cudaError_t launch_emit_mods(const double2 *boxes, const double *root_lb, const double *root_ub, const long long *delta_ptr,
                              const int32_t *delta_var, const uint8_t *delta_is_upper, const double *delta_val, int64_t ld,
-                             int32_t n, int32_t n_boxes, const long long *mod_ptr, long long *cursor, long long cap,
-                             int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val, cudaStream_t stream)
+                             int32_t n, int32_t n_boxes, const int32_t *strip_off, const long long *mod_ptr,
+                             const long long *extra_at, long long cap, int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val,
+                             cudaStream_t stream)
 {
   if (n <= 0 || n_boxes <= 0) return cudaSuccess;
   const DeltaLists D{delta_ptr, delta_var, delta_is_upper, delta_val};
   dim3 grid((n + 255) / 256, (n_boxes + 31) / 32);
-  mods_kernel<true><<<grid, 256, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n, n_boxes, nullptr, mod_ptr, cursor, cap, mod_var,
-                                              mod_is_upper, mod_val);
-  mods_delta_kernel<true><<<(n_boxes + 127) / 128, 128, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n_boxes, nullptr, mod_ptr,
-                                                                    cursor, cap, mod_var, mod_is_upper, mod_val);
+  mods_kernel<true><<<grid, 256, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n, n_boxes, const_cast<int32_t *>(strip_off), mod_ptr,
+                                              cap, mod_var, mod_is_upper, mod_val);
+  mods_delta_kernel<true><<<(n_boxes + 127) / 128, 128, 0, stream>>>(boxes, root_lb, root_ub, D, ld, n_boxes, nullptr, extra_at, cap,
+                                                                    mod_var, mod_is_upper, mod_val);
   return cudaGetLastError();
 }
 

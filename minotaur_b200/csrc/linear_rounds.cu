@@ -19,6 +19,21 @@ namespace {
 
 constexpr int kRoundsThreads = 256;
 
+// a variable goes on a list once: the bit set says who is on it already
+__device__ __forceinline__ void note_touched(uint32_t *bits, int32_t *list, int32_t *count, int j)
+{
+  const unsigned bit = 1u << (j & 31);
+  if (!(atomicOr(bits + (j >> 5), bit) & bit)) list[atomicAdd(count, 1)] = j;
+}
+// one thread per block reads the loop's stop word (every kernel enqueued after the loop has ended returns at once)
+__device__ __forceinline__ bool loop_stopped(const int32_t *ctrl)
+{
+  __shared__ int s_stop;
+  if (threadIdx.x == 0) s_stop = __ldcg(ctrl + kRcStop);
+  __syncthreads();
+  return s_stop != 0;
+}
+
 // ---- dense 32-row blocks: lane = row straight from the CSR (eval_resident of row_resident.cuh, streaming form) ----
 // one warp's slice of shared memory: the queue of deferred exact candidates and, for a block with more candidates
 // than the queue holds, the work list
@@ -48,12 +63,15 @@ struct SinkRounds {
   static constexpr bool kFlagsRows = false;
   double *nlb, *nub;
   int n;
+  uint32_t *tbits; int32_t *tlist; int32_t *tcount;
   template <class Stage> __device__ __forceinline__ void mark(Stage &, int) const {}
   __device__ __forceinline__ void phase(int, int) const {}
   template <class Stage> __device__ __forceinline__ void raise_lb(Stage &, int j, bool, double c) const { atomic_max_f64(&nlb[j], c); }
   template <class Stage> __device__ __forceinline__ void lower_ub(Stage &, int j, bool, double c) const { atomic_min_f64(&nub[j], c); }
-  template <class Stage> __device__ __forceinline__ void moved(Stage &, int, bool) const {}
-  __device__ __forceinline__ void touch(int, bool) const {}
+  // a variable that received a candidate goes on the round's touched list, once
+  __device__ __forceinline__ void note(int j) const { note_touched(tbits, tlist, tcount, j); }
+  template <class Stage> __device__ __forceinline__ void moved(Stage &, int j, bool) const { note(j); }
+  __device__ __forceinline__ void touch(int j, bool) const { note(j); }
   __device__ __forceinline__ void row_infeasible() const { nlb[n] = 2.0; }
   __device__ __forceinline__ void row_bounds_cross() const {}      // checked by the init kernel
   template <class Stage> __device__ __forceinline__ bool near_full(const Stage &, int = 32) const { return false; }
@@ -74,7 +92,7 @@ __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W
 {
   const int lane = threadIdx.x & 31;
   const ReadPending rd{W.box, P.colx, false};          // the vars kernel stores rounded integer bounds
-  const SinkRounds sink{W.nlb, W.nub, P.n};
+  const SinkRounds sink{W.nlb, W.nub, P.n, W.tbits, W.tlist, W.ctrl + kRcTouched};
   const int n_blk = (P.m + 31) / 32;
   for (int it0 = 0; warp_global + (long long)it0 * n_warps < n_blk; it0 += 32) {
     const long long bl = warp_global + (long long)(it0 + lane) * n_warps;
@@ -102,7 +120,7 @@ __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W
   drain_queue<R>(P, rd, sink, S, lane);
   // the objective cut-off row is evaluated in every round (the reference loops it to its own fixpoint in every
   // sweep, LinearHandler.cpp:1636-1640); one warp takes it
-  if (P.cut_cnt > 0 && warp_global == 0) {
+  if (P.cut_cnt > 0 && warp_global == 0 && W.rank == 0) {       // rank 0 alone: the row is replicated, its candidates too
     const ReadPending rdc{W.box, P.cut_colx, false};
     eval_long<R>(P.cut_val, rdc, sink, S, lane, 0, P.cut_cnt, -INFINITY, P.cut_rhs);
     if (lane == 0) { my_nnz += (unsigned long long)P.cut_cnt; ++my_rows; }
@@ -125,13 +143,15 @@ __global__ void rounds_init_kernel(LinDev P, RoundsWs W, const double *lb_io, co
     if (__ldg(P.row_info + i).y >= 0 && bnd.x > bnd.y + kETol) bad = 1;     // checkBounds_, rows part
   }
   for (int w = tid; w < (P.m + 31) / 32; w += nthreads) W.bits[w] = 0u;
-  if (bad) W.ctrl[3] = 1 /* MNTR_INFEAS_BOUNDS */;
+  for (int w = tid; w < (P.n + 31) / 32; w += nthreads) { W.tbits[w] = 0u; W.ebits[w] = 0u; }
+  if (bad) { W.ctrl[kRcVerdict] = 1 /* MNTR_INFEAS_BOUNDS */; W.ctrl[kRcStop] = 1; }
 }
 
 template <class R>
 __global__ void __launch_bounds__(kRoundsThreads, 4)
 rounds_rows_kernel(LinDev P, RoundsWs W, int first)
 {
+  if (loop_stopped(W.ctrl)) return;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   unsigned long long my_nnz = 0, my_rows = 0;
@@ -153,33 +173,18 @@ rounds_rows_kernel(LinDev P, RoundsWs W, int first)
   if (threadIdx.x == 0 && s_rows) { atomicAdd(&W.counters[0], s_nnz); atomicAdd(&W.counters[1], s_rows); }
 }
 
-// ---- sparse bound exchange: rounds in which few bounds move need not all-reduce 16 bytes per variable ----
-// this rank's changed candidates (nlb / nub differ from the replicated box) -> W.xsend; entry 0 is the header
+// ---- sparse bound exchange over NCCL (fallback without peer memory): rounds in which few bounds move need not
+//      all-reduce 16 bytes per variable ----
+// this rank's touched candidates -> W.xsend; entry 0 is the header {lb = row-infeasible flag, j = count}
 __global__ void __launch_bounds__(kRoundsThreads)
 rounds_compact_kernel(LinDev P, RoundsWs W, int cap)
 {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31;
-  unsigned long long *count = reinterpret_cast<unsigned long long *>(&W.xsend[0].j);     // zeroed by the host
-  if (tid == 0) W.xsend[0].lb = W.nlb[P.n];                                              // row-infeasible flag
-  for (int j0 = (tid >> 5) * 32; j0 < P.n; j0 += (nthreads >> 5) * 32) {
-    const int j = j0 + lane;
-    bool ch = false;
-    double l = 0.0, u = 0.0;
-    if (j < P.n) {
-      const double2 o = W.box[j];
-      l = W.nlb[j]; u = W.nub[j];
-      ch = l != o.x || u != o.y;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, ch);
-    if (m == 0u) continue;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));                // one atomic per warp
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (ch) {
-      const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
-      if (at < (unsigned long long)cap) W.xsend[1 + at] = BoundMsg{l, u, (long long)j};
-    }
+  const int cnt = W.ctrl[kRcTouched];
+  if (tid == 0) { W.xsend[0].lb = W.nlb[P.n]; W.xsend[0].ub = 0.0; W.xsend[0].j = (long long)cnt; }
+  for (int k = tid; k < cnt && k < cap; k += nthreads) {
+    const int j = W.tlist[k];
+    W.xsend[1 + k] = BoundMsg{W.nlb[j], W.nub[j], (long long)j};
   }
 }
 
@@ -192,7 +197,7 @@ rounds_apply_kernel(LinDev P, RoundsWs W, int rank, int cap)
   const size_t stride = (size_t)cap + 1;      // messages of this round's capacity tier, back to back
   bool overflow = false;
   for (int r = 0; r < W.n_ranks; ++r) overflow |= W.xrecv[r * stride].j > (long long)cap;
-  if (overflow) { if (tid == 0) W.ctrl[5] = 1; return; }
+  if (overflow) { if (tid == 0) W.ctrl[kRcOverflow] = 1; return; }
   for (int r = 0; r < W.n_ranks; ++r) {
     if (r == rank) continue;
     const BoundMsg *msg = W.xrecv + r * stride;
@@ -202,8 +207,165 @@ rounds_apply_kernel(LinDev P, RoundsWs W, int rank, int cap)
       const BoundMsg e = msg[1 + k];
       atomic_max_f64(&W.nlb[e.j], e.lb);
       atomic_min_f64(&W.nub[e.j], e.ub);
+      note_touched(W.tbits, W.tlist, W.ctrl + kRcTouched, (int)e.j);
     }
   }
+}
+
+// ---- bound exchange over NVLink peer memory: push, then wait + merge ----
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// Every rank writes its touched candidates {lb, ub, j} straight into the inbox of every peer (slot [tag parity][this
+// rank]: plain stores over NVLink, 24 bytes per entry and peer), header first entry {row-infeasible flag, count}; the
+// last block to finish raises this rank's round tag in every peer's tag array.
+__global__ void __launch_bounds__(kRoundsThreads)
+rounds_push_kernel(LinDev P, RoundsWs W, unsigned tag)
+{
+  if (loop_stopped(W.ctrl)) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int cnt = W.ctrl[kRcTouched];
+  const int64_t slot = ((int64_t)(tag & 1u) * W.n_ranks + W.rank) * W.inbox_stride;
+  for (int k = tid; k < cnt; k += nthreads) {
+    const int j = W.tlist[k];
+    const BoundMsg e{W.nlb[j], W.nub[j], (long long)j};
+    for (int r = 0; r < W.n_ranks; ++r)
+      if (r != W.rank) W.peer_inbox[r][slot + 1 + k] = e;
+  }
+  if (tid == 0) {
+    const BoundMsg h{W.nlb[P.n], 0.0, (long long)cnt};
+    for (int r = 0; r < W.n_ranks; ++r)
+      if (r != W.rank) W.peer_inbox[r][slot] = h;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(W.ctrl + kRcDoneA, 1);
+    if (done == (int)gridDim.x - 1) {
+      __threadfence_system();
+      for (int r = 0; r < W.n_ranks; ++r)
+        if (r != W.rank) st_release_sys(W.peer_tag[r] + W.rank, tag);
+      W.ctrl[kRcDoneA] = 0;
+    }
+  }
+}
+
+// Waits until every peer's message of this round is complete, then merges the peers' candidates (exact max / min:
+// the order does not matter) and puts their variables on the touched list.
+__global__ void __launch_bounds__(kRoundsThreads)
+rounds_pull_kernel(LinDev P, RoundsWs W, unsigned tag)
+{
+  if (loop_stopped(W.ctrl)) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  if (threadIdx.x < W.n_ranks && threadIdx.x != W.rank)
+    while ((int)(ld_acquire_sys(W.inbox_tag + threadIdx.x) - tag) < 0) __nanosleep(200);
+  __syncthreads();
+  for (int r = 0; r < W.n_ranks; ++r) {
+    if (r == W.rank) continue;
+    const BoundMsg *msg = W.inbox + ((int64_t)(tag & 1u) * W.n_ranks + r) * W.inbox_stride;
+    const long long cnt = msg[0].j;
+    if (tid == 0 && msg[0].lb > 0.0) W.nlb[P.n] = msg[0].lb;
+    for (long long k = tid; k < cnt; k += nthreads) {
+      const BoundMsg e = msg[1 + k];
+      atomic_max_f64(&W.nlb[e.j], e.lb);
+      atomic_min_f64(&W.nub[e.j], e.ub);
+      note_touched(W.tbits, W.tlist, W.ctrl + kRcTouched, (int)e.j);
+    }
+  }
+}
+
+// The touched variables of the round (this rank's and, after the exchange, everybody's -- the same set on every rank):
+// integer rounding [tightenInts_], bound check [checkBounds_], commit to the box, flag this rank's rows of every
+// variable that moved [changeBFlag_], remember it for the write-back.  Replicated on every rank over identical data.
+__global__ void __launch_bounds__(kRoundsThreads)
+rounds_vars_list_kernel(LinDev P, RoundsWs W)
+{
+  if (loop_stopped(W.ctrl)) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int cnt = W.ctrl[kRcTouched];
+  __shared__ double s_inf;
+  if (threadIdx.x == 0) s_inf = W.nlb[P.n];
+  __syncthreads();
+  int changed = 0, int_moved = 0, bad = 0, n_changed = 0;
+  const bool row_inf = s_inf > 0.0;               // merged flag: some rank found an activity-infeasible row
+  for (int k = tid; k < cnt; k += nthreads) {
+    const int j = W.tlist[k];
+    atomicAnd(W.tbits + (j >> 5), ~(1u << (j & 31)));
+    const double2 o = W.box[j];
+    double2 v = make_double2(W.nlb[j], W.nub[j]);
+    if (row_inf) { W.nlb[j] = o.x; W.nub[j] = o.y; continue; }      // the box of the round start is handed back
+    if (is_int_type(__ldg(P.var_type + j))) {
+      if (v.x != o.x || v.y != o.y) int_moved = 1;
+      tighten_int_bounds(v.x, v.y);
+    }
+    if (v.x > v.y + kETol) bad = 1;
+    if (v.x != o.x || v.y != o.y) {
+      changed = 1; ++n_changed;
+      W.box[j] = v; W.nlb[j] = v.x; W.nub[j] = v.y;
+      note_touched(W.ebits, W.elist, W.ctrl + kRcEver, j);
+      const int qb = __ldg(P.csc_ptr + j), qe = __ldg(P.csc_ptr + j + 1);
+      for (int q = qb; q < qe; ++q) {                 // fire-and-forget OR into this rank's row bit set
+        const int row = __ldg(P.csc_row + q);
+        atomicOr(W.bits + (row >> 5), 1u << (row & 31));
+      }
+    }
+  }
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  n_changed = __reduce_add_sync(0xffffffffu, n_changed);
+  if ((threadIdx.x & 31) == 0 && n_changed) atomicAdd(&s_count, n_changed);
+  changed = __syncthreads_or(changed);
+  int_moved = __syncthreads_or(int_moved);
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) {
+    if (s_count) atomicAdd(&W.ctrl[kRcPairs], s_count);
+    if (changed) W.ctrl[kRcChanged] = 1;
+    if (int_moved) W.ctrl[kRcIntMoved] = 1;
+    if (bad) atomicMax(&W.ctrl[kRcVerdict], 1 /* MNTR_INFEAS_BOUNDS */);
+  }
+}
+
+// End of a round (one warp): verdict, loop decision [simplePresolve :1625-1627], progress words for the host (which
+// polls them without synchronising the stream), per-round words reset.
+__global__ void rounds_finalize_kernel(LinDev P, RoundsWs W, int max_rounds, int loop_mode)
+{
+  if (threadIdx.x != 0) return;
+  int32_t *c = W.ctrl;
+  volatile int32_t *pr = W.progress;
+  if (c[kRcStop] != 0) {                           // stopped before (e.g. crossed row bounds found by the init kernel)
+    pr[2] = c[kRcVerdict]; pr[1] = 1;
+    __threadfence_system();
+    return;
+  }
+  const int round = ++c[kRcRound];
+  if (W.nlb[P.n] > 0.0) c[kRcVerdict] = 2 /* MNTR_INFEAS_ROW */;
+  const int verdict = c[kRcVerdict], changed = c[kRcChanged], int_moved = c[kRcIntMoved];
+  int stop = verdict != 0 || !changed;
+  if (max_rounds > 0 && round >= max_rounds) stop = 1;
+  if (loop_mode == 1 && (round >= 10 || (round >= 2 && !int_moved))) stop = 1;
+  c[kRcStop] = stop;
+  c[kRcChanged] = 0; c[kRcIntMoved] = 0; c[kRcTouched] = 0;
+  pr[2] = verdict; pr[3] = changed; pr[1] = stop;
+  __threadfence_system();
+  pr[0] = round;
+  __threadfence_system();
+}
+
+// dense (all-reduce) rounds of the NCCL fallback leave this rank's touched list behind: clear it
+__global__ void rounds_clear_list_kernel(RoundsWs W)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int cnt = W.ctrl[kRcTouched];
+  for (int k = tid; k < cnt; k += nthreads) { const int j = W.tlist[k]; atomicAnd(W.tbits + (j >> 5), ~(1u << (j & 31))); }
 }
 
 // ctrl: [0] changed  [1] int moved  [3] verdict  [4] changed (var,round) pairs  [5] sparse exchange overflowed
@@ -214,7 +376,7 @@ rounds_vars_kernel(LinDev P, RoundsWs W)
   // are served one after the other (measured: 20 us per launch)
   __shared__ int s_skip;
   __shared__ double s_inf;
-  if (threadIdx.x == 0) { s_skip = W.xcap > 0 ? W.ctrl[5] : 0; s_inf = W.nlb[P.n]; }
+  if (threadIdx.x == 0) { s_skip = (W.xcap > 0 ? W.ctrl[kRcOverflow] : 0) | W.ctrl[kRcStop]; s_inf = W.nlb[P.n]; }
   __syncthreads();
   if (s_skip != 0) return;           // the sparse exchange overflowed: the host redoes the merge, then calls again
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
@@ -234,7 +396,10 @@ rounds_vars_kernel(LinDev P, RoundsWs W)
           tighten_int_bounds(v.x, v.y);
         }
         if (v.x > v.y + kETol) bad = 1;
-        if (v.x != o.x || v.y != o.y) { ch = true; W.box[j] = v; W.nlb[j] = v.x; W.nub[j] = v.y; }
+        if (v.x != o.x || v.y != o.y) {
+          ch = true; W.box[j] = v; W.nlb[j] = v.x; W.nub[j] = v.y;
+          note_touched(W.ebits, W.elist, W.ctrl + kRcEver, j);
+        }
       }
       unsigned chm = __ballot_sync(0xffffffffu, ch);
       if (ch) { changed = 1; ++n_changed; }
@@ -258,18 +423,20 @@ rounds_vars_kernel(LinDev P, RoundsWs W)
   int_moved = __syncthreads_or(int_moved);
   bad = __syncthreads_or(bad);
   if (threadIdx.x == 0) {
-    if (s_count) atomicAdd(&W.ctrl[4], s_count);
-    if (changed) W.ctrl[0] = 1;
-    if (int_moved) W.ctrl[1] = 1;
-    if (row_inf) W.ctrl[3] = 2 /* MNTR_INFEAS_ROW */;
-    else if (bad) W.ctrl[3] = 1 /* MNTR_INFEAS_BOUNDS */;
+    if (s_count) atomicAdd(&W.ctrl[kRcPairs], s_count);
+    if (changed) W.ctrl[kRcChanged] = 1;
+    if (int_moved) W.ctrl[kRcIntMoved] = 1;
+    if (bad && !row_inf) atomicMax(&W.ctrl[kRcVerdict], 1 /* MNTR_INFEAS_BOUNDS */);
   }
 }
 
+// hands the box back: lb_io / ub_io still hold the bounds of every variable that never moved
 __global__ void rounds_finish_kernel(LinDev P, RoundsWs W, double *lb_io, double *ub_io)
 {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  for (int j = tid; j < P.n; j += nthreads) {
+  const int cnt = W.ctrl[kRcEver];
+  for (int k = tid; k < cnt; k += nthreads) {
+    const int j = W.elist[k];
     const double2 b = W.box[j];
     lb_io[j] = b.x;
     ub_io[j] = b.y;
@@ -322,7 +489,7 @@ cudaError_t launch_rounds_vars(const LinDev &P, const RoundsWs &W, int sm_count,
 
 cudaError_t launch_rounds_compact(const LinDev &P, const RoundsWs &W, int cap, int sm_count, cudaStream_t stream)
 {
-  rounds_compact_kernel<<<grid_for(P.n, sm_count), kRoundsThreads, 0, stream>>>(P, W, cap);
+  rounds_compact_kernel<<<sm_count * 2, kRoundsThreads, 0, stream>>>(P, W, cap);
   return cudaGetLastError();
 }
 
@@ -335,7 +502,37 @@ cudaError_t launch_rounds_apply(const LinDev &P, const RoundsWs &W, int rank, in
 cudaError_t launch_rounds_finish(const LinDev &P, const RoundsWs &W, double *lb_dev, double *ub_dev, int sm_count,
                                  cudaStream_t stream)
 {
-  rounds_finish_kernel<<<grid_for(P.n, sm_count), kRoundsThreads, 0, stream>>>(P, W, lb_dev, ub_dev);
+  rounds_finish_kernel<<<sm_count * 4, kRoundsThreads, 0, stream>>>(P, W, lb_dev, ub_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rounds_push(const LinDev &P, const RoundsWs &W, unsigned tag, int sm_count, cudaStream_t stream)
+{
+  rounds_push_kernel<<<sm_count, kRoundsThreads, 0, stream>>>(P, W, tag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rounds_pull(const LinDev &P, const RoundsWs &W, unsigned tag, int sm_count, cudaStream_t stream)
+{
+  rounds_pull_kernel<<<sm_count * 2, kRoundsThreads, 0, stream>>>(P, W, tag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rounds_vars_list(const LinDev &P, const RoundsWs &W, int sm_count, cudaStream_t stream)
+{
+  rounds_vars_list_kernel<<<sm_count * 2, kRoundsThreads, 0, stream>>>(P, W);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rounds_finalize(const LinDev &P, const RoundsWs &W, int max_rounds, int loop_mode, cudaStream_t stream)
+{
+  rounds_finalize_kernel<<<1, 32, 0, stream>>>(P, W, max_rounds, loop_mode);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rounds_clear_list(const RoundsWs &W, int sm_count, cudaStream_t stream)
+{
+  rounds_clear_list_kernel<<<sm_count, kRoundsThreads, 0, stream>>>(W);
   return cudaGetLastError();
 }
 

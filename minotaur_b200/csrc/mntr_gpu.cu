@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -88,6 +89,15 @@ struct mntr_gpu_ctx {
   bool ctrl_clean = false;            // the device control block is zero (left so by the previous launch)
   bool force_rounds = false;          // MNTR_GPU_ROUNDS=1: per-round kernels even without a communicator
   BoundMsg *h_xhdr = nullptr;         // pinned: the ranks' message headers of the sparse bound exchange
+  int32_t *h_progress = nullptr;      // pinned, mapped: {round finished, stop, verdict, changed} written by rounds_finalize_kernel
+  std::vector<cudaEvent_t> round_ev;  // 4 events per timed round (rows / exchange / vars boundaries)
+  // bound exchange over NVLink peer memory (CUDA IPC between the ranks' processes)
+  void *p2p_region = nullptr;         // this rank's inbox + tags (exported to the peers)
+  std::vector<void *> p2p_peers;      // peers' regions as mapped into this process (own entry nullptr)
+  void *p2p_dev_tables = nullptr;     // device arrays: peers' inbox / tag pointers
+  int64_t p2p_n = -1;                 // number of variables the region was sized for
+  bool p2p_failed = false;            // IPC is unavailable: NCCL exchange
+  unsigned p2p_tag = 0;               // rounds exchanged so far (tags are monotone over the calls)
 
   // ---- NCCL communicator (resolved at run time with dlopen: no link-time dependency) ----
   ncclComm_t comm = nullptr;
@@ -176,6 +186,18 @@ void free_all(std::vector<void *> &v)
 {
   for (void *p : v) cudaFree(p);
   v.clear();
+}
+
+// closes the peers' regions and frees this rank's (collective in effect: every rank does it before the region is reused)
+void p2p_teardown(mntr_gpu_ctx *c)
+{
+  for (void *p : c->p2p_peers) if (p) cudaIpcCloseMemHandle(p);
+  c->p2p_peers.clear();
+  if (c->p2p_region) cudaFree(c->p2p_region);
+  if (c->p2p_dev_tables) cudaFree(c->p2p_dev_tables);
+  c->p2p_region = nullptr; c->p2p_dev_tables = nullptr; c->p2p_n = -1;
+  c->rws.p2p = 0; c->rws.inbox = nullptr; c->rws.inbox_tag = nullptr; c->rws.peer_inbox = nullptr; c->rws.peer_tag = nullptr;
+  (void)cudaGetLastError();
 }
 
 void free_stage(mntr_gpu_ctx *c)
@@ -303,6 +325,10 @@ void mntr_gpu_destroy(mntr_gpu_ctx *ctx)
   if (ctx->rws.xrecv) cudaFree(ctx->rws.xrecv);
   if (ctx->h_xhdr) cudaFreeHost(ctx->h_xhdr);
   if (ctx->h_ctrl) { cudaFreeHost(ctx->h_ctrl); ctx->h_ctrl = nullptr; }
+  if (ctx->h_progress) { cudaFreeHost(ctx->h_progress); ctx->h_progress = nullptr; }
+  for (cudaEvent_t e : ctx->round_ev) cudaEventDestroy(e);
+  ctx->round_ev.clear();
+  p2p_teardown(ctx);
   if (ctx->h_single) { cudaFreeHost(ctx->h_single); ctx->h_single = nullptr; }
   free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->nl_allocs); free_all(ctx->single_allocs);
   free_batch(ctx); free_stage(ctx);
@@ -467,9 +493,20 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   RW.box = W.box[0]; RW.bits = W.due[0];
   if ((rc = dalloc((void **)&RW.nlb, sizeof(double) * ((size_t)n + 1)))) return rc;
   if ((rc = dalloc((void **)&RW.nub, sizeof(double) * ((size_t)n + 1)))) return rc;
-  if ((rc = dalloc((void **)&RW.ctrl, 64))) return rc;
-  RW.counters = (unsigned long long *)((char *)RW.ctrl + 32);
-  if (!ctx->h_ctrl) CU(cudaMallocHost((void **)&ctx->h_ctrl, 64));
+  if ((rc = dalloc((void **)&RW.ctrl, 128))) return rc;
+  RW.counters = (unsigned long long *)((char *)RW.ctrl + 64);
+  if ((rc = dalloc((void **)&RW.tbits, sizeof(uint32_t) * (size_t)((n + 31) / 32 + 1)))) return rc;
+  if ((rc = dalloc((void **)&RW.ebits, sizeof(uint32_t) * (size_t)((n + 31) / 32 + 1)))) return rc;
+  if ((rc = dalloc((void **)&RW.tlist, sizeof(int32_t) * (size_t)std::max(n, 1)))) return rc;
+  if ((rc = dalloc((void **)&RW.elist, sizeof(int32_t) * (size_t)std::max(n, 1)))) return rc;
+  if (!ctx->h_ctrl) CU(cudaMallocHost((void **)&ctx->h_ctrl, 128));
+  if (!ctx->h_progress) CU(cudaHostAlloc((void **)&ctx->h_progress, 64, cudaHostAllocMapped));
+  {
+    void *mapped = nullptr;
+    CU(cudaHostGetDevicePointer(&mapped, ctx->h_progress, 0));
+    RW.progress = (int32_t *)mapped;
+  }
+  RW.rank = ctx->rank; RW.n_ranks = ctx->n_ranks;
   if (const char *fr = getenv("MNTR_GPU_ROUNDS")) ctx->force_rounds = fr[0] == '1';
   if (const char *zc = getenv("MNTR_GPU_NO_ZEROCOPY")) ctx->no_zero_copy = zc[0] == '1';
 
@@ -652,50 +689,178 @@ static void account_single(mntr_gpu_ctx *ctx, const SingleCtrl &ctrl)
   ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, ctrl.status[1]);
 }
 
-// Jacobi rounds as separate launches with the bound merge between rows and vars kernels: the
-// row-partitioned multi-GPU path (and, with MNTR_GPU_ROUNDS=1, the same kernels on one GPU).
+// Peer-memory exchange of the row-partitioned mode: every rank exports ONE region (round tags + a double-buffered inbox
+// with a slot per sender, each large enough for n candidates -- a message always fits, no overflow path) with CUDA IPC;
+// the handles travel through one NCCL all-gather.  Collective: every rank calls it at the same point of its first
+// tighten call after comm_init / load_linear.  Any failure (IPC unavailable, peers not reachable) leaves the NCCL
+// exchange in place -- consistently on all ranks, because the outcome is all-reduced.
+static int p2p_setup(mntr_gpu_ctx *ctx)
+{
+  NcclApi &nc = nccl_api();
+  const int R = ctx->n_ranks;
+  const int64_t n = ctx->n;
+  const int64_t stride = n + 1;
+  const size_t tag_bytes = 256;
+  const size_t inbox_bytes = sizeof(BoundMsg) * (size_t)(2 * R) * (size_t)stride;
+  int ok = 1;
+  if (const char *e = getenv("MNTR_GPU_P2P")) ok = e[0] != '0';
+  if (getenv("MNTR_GPU_SPARSE_XCHG")) ok = 0;        // the NCCL exchange was asked for explicitly (capacity / dense)
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaMalloc(&ctx->p2p_region, tag_bytes + inbox_bytes) != cudaSuccess) { (void)cudaGetLastError(); ctx->p2p_region = nullptr; ok = 0; }
+  if (ok && cudaMemsetAsync(ctx->p2p_region, 0, tag_bytes, ctx->stream) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, ctx->p2p_region) != cudaSuccess) { (void)cudaGetLastError(); ok = 0; }
+  // all-gather {ok, handle}
+  // ranks that are threads of ONE process (one context per device) cannot open each other's IPC handles: they take the
+  // raw pointer and enable peer access instead
+  struct Card { int ok; int device; long long pid; void *ptr; cudaIpcMemHandle_t h; };
+  Card card; card.ok = ok; card.device = ctx->device; card.pid = (long long)getpid(); card.ptr = ctx->p2p_region; card.h = mine;
+  Card *d_cards = nullptr;
+  std::vector<Card> cards((size_t)R);
+  CU(cudaMalloc((void **)&d_cards, sizeof(Card) * (size_t)(R + 1)));
+  CU(cudaMemcpyAsync(d_cards + R, &card, sizeof(Card), cudaMemcpyHostToDevice, ctx->stream));
+  NC(nc.AllGather(d_cards + R, d_cards, sizeof(Card), ncclChar, ctx->comm, ctx->stream));
+  CU(cudaMemcpyAsync(cards.data(), d_cards, sizeof(Card) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < R; ++r) ok = ok && cards[(size_t)r].ok;
+  ctx->p2p_peers.assign((size_t)R, nullptr);
+  std::vector<void *> same_process((size_t)R, nullptr);
+  if (ok) {
+    for (int r = 0; r < R && ok; ++r) {
+      if (r == ctx->rank) continue;
+      const Card &c = cards[(size_t)r];
+      if (c.pid == (long long)getpid()) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, ctx->device, c.device) != cudaSuccess || !can) { (void)cudaGetLastError(); ok = 0; continue; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(c.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+        (void)cudaGetLastError();
+        same_process[(size_t)r] = c.ptr;
+        continue;
+      }
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, c.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); ok = 0; }
+      else ctx->p2p_peers[(size_t)r] = p;
+    }
+  }
+  // everybody must have opened everybody: agree on the outcome
+  double okd = ok ? 1.0 : 0.0, *d_okd = (double *)(d_cards + R);
+  CU(cudaMemcpyAsync(d_okd, &okd, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  NC(nc.AllReduce(d_okd, d_okd, 1, ncclDouble, ncclMin, ctx->comm, ctx->stream));
+  CU(cudaMemcpyAsync(&okd, d_okd, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_cards);
+  if (okd < 0.5) {
+    p2p_teardown(ctx);
+    ctx->p2p_failed = true;
+    return MNTR_OK;
+  }
+  // device tables of the peers' inbox / tag pointers
+  std::vector<void *> tab((size_t)(2 * R), nullptr);
+  for (int r = 0; r < R; ++r) {
+    char *base = (char *)(r == ctx->rank ? ctx->p2p_region : (same_process[(size_t)r] ? same_process[(size_t)r] : ctx->p2p_peers[(size_t)r]));
+    tab[(size_t)r] = base + tag_bytes;         // inbox
+    tab[(size_t)(R + r)] = base;               // tags
+  }
+  CU(cudaMalloc(&ctx->p2p_dev_tables, sizeof(void *) * (size_t)(2 * R)));
+  CU(cudaMemcpy(ctx->p2p_dev_tables, tab.data(), sizeof(void *) * (size_t)(2 * R), cudaMemcpyHostToDevice));
+  RoundsWs &W = ctx->rws;
+  W.p2p = 1; W.inbox_stride = stride;
+  W.inbox = (BoundMsg *)((char *)ctx->p2p_region + tag_bytes);
+  W.inbox_tag = (unsigned *)ctx->p2p_region;
+  W.peer_inbox = (BoundMsg *const *)ctx->p2p_dev_tables;
+  W.peer_tag = (unsigned *const *)((void **)ctx->p2p_dev_tables + R);
+  ctx->p2p_n = n;
+  ctx->p2p_tag = 0;
+  return MNTR_OK;
+}
+
+// Jacobi rounds as separate launches with the bound merge between the rows phase and the variables phase: the
+// row-partitioned multi-GPU path (and, with MNTR_FLAG_PER_ROUND_KERNELS, the same kernels on one GPU).
+// The loop runs on the DEVICE: a one-warp kernel ends every round (verdict, stop decision, progress words in mapped
+// host memory) and every kernel enqueued after the stop returns at once; the host only keeps the stream fed -- it
+// enqueues a round as soon as the round before the previous one has reported, polling the progress words without ever
+// synchronising the stream.  Per-round work is proportional to the CHANGES (touched lists), not to n.
 static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, const mntr_gpu_options &o,
                           int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
 {
   const LinDev &P = ctx->lin;
-  const RoundsWs &W = ctx->rws;
   const bool directed = o.rounding == MNTR_ROUND_DIRECTED;
   NcclApi &nc = nccl_api();
-  CU(cudaMemsetAsync(W.ctrl, 0, 64, ctx->stream));
-  CU(launch_rounds_init(P, W, lb_dev, ub_dev, ctx->sm_count, ctx->stream));
-  int round = 0, verd = 0;
-  double rows_ms = 0, comm_ms = 0, vars_ms = 0;
-  CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  verd = ctx->h_ctrl[3];
-  while (verd == 0) {
-    ++round;
-    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CU(launch_rounds_rows(P, W, ctx->lanes_per_row, directed, round == 1, ctx->sm_count, ctx->stream));
-    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  cudaStream_t s = ctx->stream;
+  ctx->rws.rank = ctx->rank; ctx->rws.n_ranks = ctx->n_ranks;
+  if (ctx->comm && ctx->n_ranks > 1 && !ctx->p2p_failed && ctx->p2p_n != (int64_t)ctx->n) {
+    if (ctx->p2p_region) p2p_teardown(ctx);
+    int rc = p2p_setup(ctx);
+    if (rc) return rc;
+  }
+  const RoundsWs &W = ctx->rws;
+  const bool p2p = ctx->comm && W.p2p;
+  volatile int32_t *prog = ctx->h_progress;
+  prog[0] = 0; prog[1] = 0; prog[2] = 0; prog[3] = 0;
+  CU(cudaMemsetAsync(W.ctrl, 0, 128, s));
+  CU(launch_rounds_init(P, W, lb_dev, ub_dev, ctx->sm_count, s));
+  const int kTimed = 64;                      // rounds with per-phase device timing
+  while ((int)ctx->round_ev.size() < 4 * kTimed) {
+    cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->round_ev.push_back(e);
+  }
+  int enq = 0;                                // rounds enqueued
+  auto enqueue_round = [&](int round) -> int {
+    cudaEvent_t *ev = round <= kTimed ? &ctx->round_ev[(size_t)(4 * (round - 1))] : nullptr;
+    if (ev) CU(cudaEventRecord(ev[0], s));
+    CU(launch_rounds_rows(P, W, ctx->lanes_per_row, directed, round == 1, ctx->sm_count, s));
+    if (ev) CU(cudaEventRecord(ev[1], s));
+    if (p2p) {
+      const unsigned tag = ctx->p2p_tag + (unsigned)round;
+      CU(launch_rounds_push(P, W, tag, ctx->sm_count, s));
+      CU(launch_rounds_pull(P, W, tag, ctx->sm_count, s));
+    }
+    if (ev) CU(cudaEventRecord(ev[2], s));
+    CU(launch_rounds_vars_list(P, W, ctx->sm_count, s));
+    CU(launch_rounds_finalize(P, W, o.max_rounds, o.loop, s));
+    if (ev) CU(cudaEventRecord(ev[3], s));
+    return MNTR_OK;
+  };
+  int finished = 0, stop = 0;
+  if (!ctx->comm || p2p) {
+    // ---- device-driven loop ----
+    for (unsigned spins = 0;; ++spins) {
+      finished = prog[0]; stop = prog[1];
+      if (stop) break;
+      if (enq - finished < 2) {
+        int rc = enqueue_round(++enq);
+        if (rc) return rc;
+        continue;
+      }
+      if ((spins & 1023u) == 1023u) {           // a failed launch would never report: look at the stream now and then
+        const cudaError_t q = cudaStreamQuery(s);
+        if (q != cudaSuccess && q != cudaErrorNotReady)
+          return fail(ctx, MNTR_E_CUDA, "per-round kernels: %s", cudaGetErrorString(q));
+      }
+    }
+    // rounds enqueued beyond the stop are no-ops on every rank alike
+  } else {
+    // ---- NCCL fallback (no peer memory): the host reads the message sizes and chooses sparse all-gather / dense
+    //      all-reduce per round (one host round trip per round) ----
     auto dense_merge = [&]() -> int {
       NC(nc.GroupStart());
-      NC(nc.AllReduce(W.nlb, W.nlb, (size_t)P.n + 1, ncclDouble, ncclMax, ctx->comm, ctx->stream));
-      NC(nc.AllReduce(W.nub, W.nub, (size_t)P.n, ncclDouble, ncclMin, ctx->comm, ctx->stream));
+      NC(nc.AllReduce(W.nlb, W.nlb, (size_t)P.n + 1, ncclDouble, ncclMax, ctx->comm, s));
+      NC(nc.AllReduce(W.nub, W.nub, (size_t)P.n, ncclDouble, ncclMin, ctx->comm, s));
       NC(nc.GroupEnd());
       return MNTR_OK;
     };
-    // Exchange only the changed candidates: compact them behind a {count, flag} header, all-gather the HEADERS (24
-    // bytes per rank) and read them on the host -- every rank sees the same counts and takes the same decision --
-    // then all-gather messages of the smallest power-of-two capacity that holds the longest one, and merge.  If the
-    // longest message does not fit the buffers, or the messages together would move more than half of what the
-    // dense all-reduce moves, the merge is the dense all-reduce.  (Costs one extra host round trip per round, ~20 us,
-    // against all-reduces of 16 bytes per variable: 0.2 ms at n = 5M on 2 GPUs, 1.4 ms at n = 20M on 8.)
-    bool sparse = false;
-    if (ctx->comm) {
-      int rc2;
-      int cap = 0;
+    while (!stop) {
+      const int round = ++enq;
+      cudaEvent_t *ev = round <= kTimed ? &ctx->round_ev[(size_t)(4 * (round - 1))] : nullptr;
+      if (ev) CU(cudaEventRecord(ev[0], s));
+      CU(launch_rounds_rows(P, W, ctx->lanes_per_row, directed, round == 1, ctx->sm_count, s));
+      if (ev) CU(cudaEventRecord(ev[1], s));
+      int cap = 0, rc2;
       if (W.xcap > 0) {
-        CU(cudaMemsetAsync(W.xsend, 0, sizeof(BoundMsg), ctx->stream));
-        CU(launch_rounds_compact(P, W, W.xcap, ctx->sm_count, ctx->stream));
-        NC(nc.AllGather(W.xsend, W.xrecv, sizeof(BoundMsg), ncclChar, ctx->comm, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->h_xhdr, W.xrecv, sizeof(BoundMsg) * (size_t)ctx->n_ranks, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(launch_rounds_compact(P, W, W.xcap, ctx->sm_count, s));
+        NC(nc.AllGather(W.xsend, W.xrecv, sizeof(BoundMsg), ncclChar, ctx->comm, s));
+        CU(cudaMemcpyAsync(ctx->h_xhdr, W.xrecv, sizeof(BoundMsg) * (size_t)ctx->n_ranks, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
         long long maxc = 0;
         for (int r = 0; r < ctx->n_ranks; ++r) maxc = std::max(maxc, ctx->h_xhdr[r].j);
         long long c2 = 64;
@@ -705,61 +870,49 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
         if (maxc <= W.xcap && sparse_bytes <= 0.5 * 16.0 * (double)P.n) cap = (int)c2;
       }
       if (cap > 0) {
-        NC(nc.AllGather(W.xsend, W.xrecv, sizeof(BoundMsg) * ((size_t)cap + 1), ncclChar, ctx->comm, ctx->stream));
-        CU(launch_rounds_apply(P, W, ctx->rank, cap, ctx->sm_count, ctx->stream));
+        NC(nc.AllGather(W.xsend, W.xrecv, sizeof(BoundMsg) * ((size_t)cap + 1), ncclChar, ctx->comm, s));
+        CU(launch_rounds_apply(P, W, ctx->rank, cap, ctx->sm_count, s));
+        if (ev) CU(cudaEventRecord(ev[2], s));
+        CU(launch_rounds_vars_list(P, W, ctx->sm_count, s));
         ++ctx->stats.sparse_rounds;
-        sparse = true;
-      } else if ((rc2 = dense_merge())) return rc2;
-    }
-    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
-    CU(cudaMemsetAsync(W.ctrl, 0, 12, ctx->stream));          // changed, int moved, next list length
-    CU(launch_rounds_vars(P, W, ctx->sm_count, ctx->stream));
-    CU(cudaEventRecord(ctx->ev[5], ctx->stream));
-    CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    rows_ms += elapsed(ctx->ev[2], ctx->ev[3]);
-    comm_ms += elapsed(ctx->ev[3], ctx->ev[4]);
-    vars_ms += elapsed(ctx->ev[4], ctx->ev[5]);
-    if (sparse && ctx->h_ctrl[5]) {       // overflow: nothing was merged or finished; all ranks see it alike
-      int rc2;
-      --ctx->stats.sparse_rounds;
-      CU(cudaEventRecord(ctx->ev[3], ctx->stream));
-      CU(cudaMemsetAsync(W.ctrl + 5, 0, 4, ctx->stream));
-      if ((rc2 = dense_merge())) return rc2;
-      CU(cudaEventRecord(ctx->ev[4], ctx->stream));
-      CU(launch_rounds_vars(P, W, ctx->sm_count, ctx->stream));
-      CU(cudaEventRecord(ctx->ev[5], ctx->stream));
-      CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 64, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-      comm_ms += elapsed(ctx->ev[3], ctx->ev[4]);
-      vars_ms += elapsed(ctx->ev[4], ctx->ev[5]);
-    }
-    verd = ctx->h_ctrl[3];
-    const int changed = ctx->h_ctrl[0], int_moved = ctx->h_ctrl[1];
-    if (verd != 0 || !changed) break;
-    if (o.max_rounds > 0 && round >= o.max_rounds) break;
-    if (o.loop == MNTR_LOOP_SIMPLEPRESOLVE) {       // LinearHandler.cpp:1625-1627
-      if (round >= 10) break;
-      if (round >= 2 && !int_moved) break;
+      } else {
+        CU(launch_rounds_clear_list(W, ctx->sm_count, s));
+        if ((rc2 = dense_merge())) return rc2;
+        if (ev) CU(cudaEventRecord(ev[2], s));
+        CU(launch_rounds_vars(P, W, ctx->sm_count, s));
+      }
+      CU(launch_rounds_finalize(P, W, o.max_rounds, o.loop, s));
+      if (ev) CU(cudaEventRecord(ev[3], s));
+      CU(cudaStreamSynchronize(s));
+      stop = prog[1];
     }
   }
-  CU(launch_rounds_finish(P, W, lb_dev, ub_dev, ctx->sm_count, ctx->stream));
+  CU(launch_rounds_finish(P, W, lb_dev, ub_dev, ctx->sm_count, s));
+  CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 128, cudaMemcpyDeviceToHost, s));
   unsigned long long cnt[2];
-  memcpy(cnt, (char *)ctx->h_ctrl + 32, sizeof(cnt));
   if (ctx->comm) {     // nnz-updates / rows are per rank: sum them so every rank reports the job total
-    NC(nc.AllReduce(W.counters, W.counters, 2, ncclUint64, ncclSum, ctx->comm, ctx->stream));
-    CU(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    NC(nc.AllReduce(W.counters, W.counters, 2, ncclUint64, ncclSum, ctx->comm, s));
+    CU(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, s));
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(s));
+  if (!ctx->comm) memcpy(cnt, (char *)ctx->h_ctrl + 64, sizeof(cnt));
+  const int round = ctx->h_ctrl[kRcRound], verd = ctx->h_ctrl[kRcVerdict];
+  if (p2p) ctx->p2p_tag += (unsigned)round;
+  double rows_ms = 0, comm_ms = 0, vars_ms = 0;
+  for (int r = 0; r < round && r < kTimed; ++r) {
+    cudaEvent_t *ev = &ctx->round_ev[(size_t)(4 * r)];
+    rows_ms += elapsed(ev[0], ev[1]); comm_ms += elapsed(ev[1], ev[2]); vars_ms += elapsed(ev[2], ev[3]);
+  }
   if (verdict) *verdict = verd;
   if (rounds) *rounds = round;
   if (nnz_updates) *nnz_updates = (int64_t)cnt[0];
   ctx->stats.nnz_updates += (int64_t)cnt[0];
   ctx->stats.rows_evaluated += (int64_t)cnt[1];
-  ctx->stats.n_changes += ctx->h_ctrl[4];
+  ctx->stats.n_changes += ctx->h_ctrl[kRcPairs];
   ctx->stats.n_infeasible += verd != 0;
   ctx->stats.max_rounds = std::max(ctx->stats.max_rounds, round);
   ctx->stats.rows_ms += rows_ms; ctx->stats.comm_ms += comm_ms; ctx->stats.vars_ms += vars_ms;
+  if (p2p) ctx->stats.sparse_rounds += round;
   return MNTR_OK;
 }
 
@@ -1205,11 +1358,14 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
   if ((rc = boxes_from_deltas(ctx, scratch, n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val,
                               ctx->d_boxes, D))) return done(rc);
   double *d_mval = nullptr;
-  long long *d_cnt = nullptr, *d_mptr = nullptr, *d_cur = nullptr;
-  int32_t *d_mvar = nullptr; uint8_t *d_mup = nullptr;
+  long long *d_cnt = nullptr, *d_mptr = nullptr, *d_xcnt = nullptr, *d_xat = nullptr;
+  int32_t *d_mvar = nullptr, *d_strip = nullptr; uint8_t *d_mup = nullptr;
+  const int64_t n_strips = ((int64_t)n + 255) / 256;
   if ((rc = dalloc((void **)&d_cnt, sizeof(long long) * (size_t)n_boxes))) return rc;
+  if ((rc = dalloc((void **)&d_xcnt, sizeof(long long) * (size_t)n_boxes))) return rc;
   if ((rc = dalloc((void **)&d_mptr, sizeof(long long) * ((size_t)n_boxes + 1)))) return rc;
-  if ((rc = dalloc((void **)&d_cur, sizeof(long long) * (size_t)n_boxes))) return rc;
+  if ((rc = dalloc((void **)&d_xat, sizeof(long long) * (size_t)n_boxes))) return rc;
+  if ((rc = dalloc((void **)&d_strip, sizeof(int32_t) * (size_t)(n_strips * ld)))) return rc;
   if ((rc = dalloc((void **)&d_mvar, sizeof(int32_t) * (size_t)mod_cap))) return rc;
   if ((rc = dalloc((void **)&d_mup, (size_t)mod_cap))) return rc;
   if ((rc = dalloc((void **)&d_mval, sizeof(double) * (size_t)mod_cap))) return rc;
@@ -1222,13 +1378,13 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
                              o.loop, o.max_rounds, o.handlers != MNTR_HANDLERS_NONLINEAR,
                              (ctx->nl_loaded && o.handlers != MNTR_HANDLERS_LINEAR) ? 1 : 0, ctx->sm_count, s));
   CUN(cudaEventRecord(ctx->ev[2], s));
-  // mods: count per box, offsets on the host (n_boxes numbers), then emit
-  CUN(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * (size_t)n_boxes, s));
-  CUN(cudaMemsetAsync(d_cur, 0, sizeof(long long) * (size_t)n_boxes, s));
-  CUN(launch_count_mods(ctx->d_boxes, D.rl, D.ru, D.ptr, D.var, D.up, D.val, ld, n, n_boxes, d_cnt, s));
-  std::vector<long long> cnt((size_t)n_boxes), ptr((size_t)n_boxes + 1, 0), hz((size_t)n_boxes);
+  // mods: per box the ordered count (strip offsets stay on the device) and the extras; offsets on the host (n_boxes
+  // numbers), then emit in ascending (variable, side) order
+  CUN(launch_count_mods(ctx->d_boxes, D.rl, D.ru, D.ptr, D.var, D.up, D.val, ld, n, n_boxes, d_strip, d_cnt, d_xcnt, s));
+  std::vector<long long> cnt((size_t)n_boxes), xcnt((size_t)n_boxes), ptr((size_t)n_boxes + 1, 0), xat((size_t)n_boxes), hz((size_t)n_boxes);
   std::vector<int32_t> hv((size_t)n_boxes), hr((size_t)n_boxes);
   CUN(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(long long) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  CUN(cudaMemcpyAsync(xcnt.data(), d_xcnt, sizeof(long long) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
   CUN(cudaMemcpyAsync(hv.data(), ctx->d_verdict, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
   CUN(cudaMemcpyAsync(hr.data(), ctx->d_rounds, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
   CUN(cudaMemcpyAsync(hz.data(), ctx->d_nnzb, sizeof(long long) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
@@ -1236,21 +1392,27 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
   CUN(cudaMemcpyAsync(&evals, ctx->d_nl_evals, sizeof(evals), cudaMemcpyDeviceToHost, s));
   CUN(cudaStreamSynchronize(s));
   ctx->stats.nl_evals = (int64_t)evals;
-  // an infeasible box reports no mods (the node is pruned; its box is not meaningful)
-  for (int32_t b = 0; b < n_boxes; ++b) ptr[(size_t)b + 1] = ptr[(size_t)b] + (hv[(size_t)b] == MNTR_FEASIBLE ? cnt[(size_t)b] : 0);
+  // an infeasible box reports no mods (the node is pruned; its box is not meaningful): it gets an empty range and a
+  // start that is already past any capacity
+  bool any_extra = false;
+  for (int32_t b = 0; b < n_boxes; ++b) {
+    const bool feas = hv[(size_t)b] == MNTR_FEASIBLE;
+    ptr[(size_t)b + 1] = ptr[(size_t)b] + (feas ? cnt[(size_t)b] + xcnt[(size_t)b] : 0);
+    xat[(size_t)b] = feas ? ptr[(size_t)b] + cnt[(size_t)b] : ((long long)1 << 60);
+    any_extra = any_extra || (feas && xcnt[(size_t)b] > 0);
+  }
   const long long total = ptr[(size_t)n_boxes];
   if (n_mods_out) *n_mods_out = (int64_t)total;
   for (int32_t b = 0; b <= n_boxes; ++b) mod_ptr[b] = (int64_t)ptr[(size_t)b];
   if (verdict) memcpy(verdict, hv.data(), sizeof(int32_t) * (size_t)n_boxes);
   if (rounds) memcpy(rounds, hr.data(), sizeof(int32_t) * (size_t)n_boxes);
   if (total > 0 && total <= mod_cap) {
-    // boxes that are infeasible get an empty range [ptr, ptr): give them a cursor that is already past any capacity
-    std::vector<long long> cur((size_t)n_boxes, 0);
-    for (int32_t b = 0; b < n_boxes; ++b) if (hv[(size_t)b] != MNTR_FEASIBLE) cur[(size_t)b] = (long long)1 << 60;
-    CUN(cudaMemcpyAsync(d_cur, cur.data(), sizeof(long long) * (size_t)n_boxes, cudaMemcpyHostToDevice, s));
-    CUN(cudaMemcpyAsync(d_mptr, ptr.data(), sizeof(long long) * ((size_t)n_boxes + 1), cudaMemcpyHostToDevice, s));
-    CUN(launch_emit_mods(ctx->d_boxes, D.rl, D.ru, D.ptr, D.var, D.up, D.val, ld, n, n_boxes, d_mptr, d_cur, (long long)mod_cap,
-                         d_mvar, d_mup, d_mval, s));
+    std::vector<long long> start(ptr.begin(), ptr.end() - 1);
+    for (int32_t b = 0; b < n_boxes; ++b) if (hv[(size_t)b] != MNTR_FEASIBLE) start[(size_t)b] = (long long)1 << 60;
+    CUN(cudaMemcpyAsync(d_mptr, start.data(), sizeof(long long) * (size_t)n_boxes, cudaMemcpyHostToDevice, s));
+    CUN(cudaMemcpyAsync(d_xat, xat.data(), sizeof(long long) * (size_t)n_boxes, cudaMemcpyHostToDevice, s));
+    CUN(launch_emit_mods(ctx->d_boxes, D.rl, D.ru, D.ptr, D.var, D.up, D.val, ld, n, n_boxes, d_strip, d_mptr, d_xat,
+                         (long long)mod_cap, d_mvar, d_mup, d_mval, s));
     CUN(cudaMemcpyAsync(mod_var, d_mvar, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
     CUN(cudaMemcpyAsync(mod_is_upper, d_mup, (size_t)total, cudaMemcpyDeviceToHost, s));
     CUN(cudaMemcpyAsync(mod_val, d_mval, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, s));
@@ -1258,13 +1420,14 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
   CUN(cudaEventRecord(ctx->ev[3], s));
   CUN(cudaStreamSynchronize(s));
 #undef CUN
-  // deterministic order inside a box: ascending (variable, side)
-  if (total > 0 && total <= mod_cap) {
+  // the device emits a box's mods in ascending (variable, side) order; only boxes with extras (a delta that loosened
+  // the root bound) need their few extras merged in
+  if (any_extra && total > 0 && total <= mod_cap) {
     std::vector<size_t> idx;
     std::vector<int32_t> tv; std::vector<uint8_t> tu; std::vector<double> tx;
     for (int32_t b = 0; b < n_boxes; ++b) {
+      if (hv[(size_t)b] != MNTR_FEASIBLE || xcnt[(size_t)b] == 0) continue;
       const size_t lo = (size_t)ptr[(size_t)b], hi = (size_t)ptr[(size_t)b + 1];
-      if (hi - lo < 2) continue;
       idx.resize(hi - lo);
       for (size_t k = 0; k < idx.size(); ++k) idx[k] = lo + k;
       std::sort(idx.begin(), idx.end(), [&](size_t x, size_t y) {
@@ -1331,13 +1494,19 @@ int mntr_gpu_comm_init(mntr_gpu_ctx *ctx, int32_t n_ranks, int32_t rank, const v
     CU(cudaMallocHost((void **)&ctx->h_xhdr, sizeof(BoundMsg) * (size_t)n_ranks));
     ctx->rws.xcap = (int32_t)cap;
   }
-  ctx->rws.n_ranks = n_ranks;
+  ctx->rws.n_ranks = n_ranks; ctx->rws.rank = rank;
+  p2p_teardown(ctx);
+  ctx->p2p_failed = false;
   return MNTR_OK;
 }
 
 int mntr_gpu_comm_destroy(mntr_gpu_ctx *ctx)
 {
   if (!ctx) return MNTR_E_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->stream) CU(cudaStreamSynchronize(ctx->stream));
+  p2p_teardown(ctx);
+  ctx->rws.rank = 0;
   if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
   ctx->n_ranks = 1; ctx->rank = 0;
   free_xchg(ctx);

@@ -41,7 +41,7 @@ def _n_devices():
     return E.load_library().mntr_gpu_device_count()
 
 
-@pytest.mark.parametrize("xchg", [None, "0", "48"], ids=["sparse", "dense", "tiny-cap"])
+@pytest.mark.parametrize("xchg", [None, "nccl", "0", "48"], ids=["peer-memory", "nccl-sparse", "dense", "tiny-cap"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_row_partition_nccl_bitwise_independent_of_ranks(engine, world, xchg, monkeypatch):
     _nccl_partition_case(engine, world, xchg, monkeypatch, ragged=False)
@@ -55,15 +55,19 @@ def test_row_partition_nccl_ragged_rows(engine, world, monkeypatch):
 
 
 def _nccl_partition_case(engine, world, xchg, monkeypatch, ragged):
-    """Row-partitioned mode over NCCL.  The per-round merge is the sparse exchange (changed candidates compacted, their
-    counts all-gathered and read by the host, then right-sized messages all-gathered and merged with max / min) or,
-    when the messages would not fit or not pay, the dense MAX/MIN all-reduce of the candidate bounds: "0" forces the
-    dense merge, a capacity of 48 entries makes most rounds fall back to it.  Same bits in every case."""
+    """Row-partitioned mode.  The per-round merge of the candidate bounds is, by default, the exchange over NVLink peer
+    memory (every rank pushes its touched candidates into the peers' inboxes; the loop runs on the device); with
+    MNTR_GPU_P2P=0 the NCCL sparse exchange (counts all-gathered and read by the host, then right-sized messages
+    all-gathered and merged with max / min) or, when the messages would not fit or not pay, the dense MAX/MIN
+    all-reduce: MNTR_GPU_SPARSE_XCHG "0" forces the dense merge, a capacity of 48 entries makes most rounds fall back
+    to it.  Same bits in every case."""
     if _n_devices() < world:
         pytest.skip(f"needs {world} GPUs")
-    if xchg is None:
-        monkeypatch.delenv("MNTR_GPU_SPARSE_XCHG", raising=False)
-    else:
+    monkeypatch.delenv("MNTR_GPU_SPARSE_XCHG", raising=False)
+    monkeypatch.delenv("MNTR_GPU_P2P", raising=False)
+    if xchg == "nccl":
+        monkeypatch.setenv("MNTR_GPU_P2P", "0")
+    elif xchg is not None:
         monkeypatch.setenv("MNTR_GPU_SPARSE_XCHG", xchg)      # read by mntr_gpu_comm_init
     if ragged:
         from helpers import ragged_rows
@@ -106,7 +110,7 @@ def _nccl_partition_case(engine, world, xchg, monkeypatch, ragged):
                 assert np.array_equal(got.lb, ref[b].lb) and np.array_equal(got.ub, ref[b].ub), (b, rank)
                 assert got.rounds[0] == ref[b].rounds[0]
                 assert got.nnz_updates[0] == ref[b].nnz_updates[0]     # summed over the ranks
-    if xchg is None:
+    if xchg in (None, "nccl"):
         assert min(sparse) > 0, "the sparse exchange never ran: the test is vacuous"
     if xchg == "0":
         assert max(sparse) == 0
