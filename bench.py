@@ -419,6 +419,10 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # stdout carries ONE JSON line: whatever libraries print there meanwhile (NCCL's version banner ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from minotaur_b200 import engine as E
@@ -490,7 +494,8 @@ def main():
         }
         if head.get("cpu_baseline") is not None:
             out["cpu_baseline"] = head["cpu_baseline"]
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -32,6 +32,8 @@ extern "C" {
 #endif
 
 #define MNTR_GPU_ABI_VERSION 1
+/* longest CGraph tape (nodes of one constraint) mntr_gpu_load_cgraph accepts; callers leave longer ones to NlPresHandler */
+#define MNTR_GPU_MAX_TAPE 48
 
 typedef struct mntr_gpu_ctx mntr_gpu_ctx;
 
@@ -160,6 +162,11 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
                          const double *cnst, const int32_t *child, const int32_t *lin_ptr,
                          const int32_t *lin_col, const double *lin_val, const double *c_lb,
                          const double *c_ub);
+
+/* New bounds for the linear rows already on the device (same rows, same order as the mntr_gpu_load_linear call):
+ * what a ConBoundMod or LinearHandler's row-bound tightening changes.  m doubles each way instead of re-flattening the
+ * whole problem.  Replaces: Constraint::lb_/ub_ being read live by linBndTighten_ (LinearHandler.cpp:952-1045). */
+int mntr_gpu_update_row_bounds(mntr_gpu_ctx *ctx, int32_t m, const double *row_lb, const double *row_ub);
 
 /* Objective cut-off row  c.x <= rhs  (rhs = incumbent value - objective constant);
  * k = 0 removes it.  Replaces: LinearHandler::varBndsFromObj_ (LinearHandler.cpp:544-597). */

@@ -135,6 +135,12 @@ __device__ __forceinline__ double pow_chk(double x, double y, int &error)
   return r;
 }
 
+// tape shapes with a specialised evaluator (same operations in the same order as the interpreter, node intervals in
+// registers instead of local memory, no opcode dispatch)
+constexpr int kShapeGeneric = 0;
+constexpr int kShapeBilinear = 1;   // [Var, Var, Mult(a, b)]                              x_i * x_j (+ linear part)
+constexpr int kShapeSumSq = 2;      // [Var, Var, Sqr(a), Sqr(b), SumList(2, 3)]           x_i^2 + x_j^2
+
 struct TapeView {
   const uint8_t *op; const int32_t *a0; const int32_t *a1; const double *cn; const int32_t *child;
   int nn;
@@ -157,6 +163,7 @@ struct BatchStage {
   int32_t lin_col[kStageLin];
   int32_t tape_off[33], lin_off[33];     // offsets of the batch's constraints inside the staged arrays
   uint8_t op[kStageNodes];
+  uint8_t shape[32], nlead[32];          // per staged constraint: kShape*, leading OpVar nodes (classified once per batch)
 };
 
 // a staged constraint: tape view (pointers into the BatchStage), linear part, bounds
@@ -168,11 +175,7 @@ struct ConsView {
   double c_lb, c_ub;
   int shape;                // kShape*: tapes of the two dominant forms are evaluated by straight-line code
 };
-// tape shapes with a specialised evaluator (same operations in the same order as the interpreter, node intervals in
-// registers instead of local memory, no opcode dispatch)
-constexpr int kShapeGeneric = 0;
-constexpr int kShapeBilinear = 1;   // [Var, Var, Mult(a, b)]                              x_i * x_j (+ linear part)
-constexpr int kShapeSumSq = 2;      // [Var, Var, Sqr(a), Sqr(b), SumList(2, 3)]           x_i^2 + x_j^2
+
 
 struct BatchInfo {
   int n;                    // constraints staged (1..32)
@@ -237,6 +240,22 @@ __device__ __forceinline__ BatchInfo stage_batch(const NlDev &N, int c0, int c_e
     B.child = S.child - clo;
   }
   __syncwarp();
+  // classify the staged tapes, one constraint per lane (every lane would otherwise repeat this for every constraint)
+  if (lane < n) {
+    const int o = S.tape_off[lane], nn = S.tape_off[lane + 1] - o;
+    const uint8_t *op = S.op + o; const int32_t *a0 = S.a0 + o, *a1 = S.a1 + o;
+    int nv = 0;
+    while (nv < nn && op[nv] == OpVar) ++nv;
+    int shape = kShapeGeneric;
+    if (nv == 2 && nn == 3 && op[2] == OpMult && (unsigned)a0[2] < 2u && (unsigned)a1[2] < 2u && a0[2] != a1[2])
+      shape = kShapeBilinear;
+    else if (nv == 2 && nn == 5 && op[2] == OpSqr && op[3] == OpSqr && op[4] == OpSumList &&
+             (unsigned)a0[2] < 2u && (unsigned)a0[3] < 2u && a1[4] - a0[4] == 2 &&
+             B.child[a0[4]] == 2 && B.child[a0[4] + 1] == 3)
+      shape = kShapeSumSq;
+    S.shape[lane] = (uint8_t)shape; S.nlead[lane] = (uint8_t)nv;
+  }
+  __syncwarp();
   return B;
 }
 
@@ -251,17 +270,8 @@ __device__ __forceinline__ ConsView batch_constraint(const NlDev &N, const Batch
   if (B.lin_col == S.lin_col) { V.lin_col = S.lin_col + S.lin_off[k]; V.lin_val = S.lin_val + S.lin_off[k]; }
   else { const int q0 = __ldg(N.lin_ptr + c); V.lin_col = N.lin_col + q0; V.lin_val = N.lin_val + q0; }
   V.c_lb = S.c_lb[k]; V.c_ub = S.c_ub[k];
-  int nv = 0;
-  while (nv < V.t.nn && V.t.op[nv] == OpVar) ++nv;
-  V.n_lead_vars = nv;
-  V.shape = kShapeGeneric;
-  const TapeView &t = V.t;
-  if (nv == 2 && t.nn == 3 && t.op[2] == OpMult && (unsigned)t.a0[2] < 2u && (unsigned)t.a1[2] < 2u && t.a0[2] != t.a1[2])
-    V.shape = kShapeBilinear;
-  else if (nv == 2 && t.nn == 5 && t.op[2] == OpSqr && t.op[3] == OpSqr && t.op[4] == OpSumList &&
-           (unsigned)t.a0[2] < 2u && (unsigned)t.a0[3] < 2u && t.a1[4] - t.a0[4] == 2 &&
-           t.child[t.a0[4]] == 2 && t.child[t.a0[4] + 1] == 3)
-    V.shape = kShapeSumSq;
+  V.n_lead_vars = S.nlead[k];
+  V.shape = S.shape[k];
   return V;
 }
 

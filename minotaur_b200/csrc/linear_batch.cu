@@ -451,42 +451,20 @@ __device__ __forceinline__ void staged_row(const LinDev &P, int2 info, double2 b
   for (int t = t0; t < cnt; ++t) term(t, sv[t], sg[t * kTile]);
   // >= every term's reach |a| (ub - lb) 1.000000001: amax >= |a|, and the width rounded up to the next high word
   const double wmax = amax * __hiloint2double(dhi + 1, 0) * 1.000000001;
+  // SCREEN: does any box of the tile need more than the activity?  A box does when its row is activity-infeasible
+  // (:994-1015), needs the singleton-infinity sums (:970-972), or has a side whose slack is within the row's largest
+  // reach (only then can a term move a bound).  The common answer is no: one vote, and the row is done.  Otherwise
+  // the row goes through process_row from the start (it recomputes the same activities from the staged segments).
+  const double slack_lb = -R::sub_lo(rl, uu), slack_ub = R::sub_hi(ru, ll);       // as row_update forms them
+  const bool more = mine && ((ll < -kInf20) | (uu > kInf20) | (ll > ru + kETol) | (uu < rl - kETol) |
+                             ((rl > -kInf20) & !(slack_lb > wmax)) | ((ru < kInf20) & !(slack_ub > wmax)));
+  if (!__any_sync(kFull, more)) {
+    if (mine) my_nnz += (unsigned long long)cnt;
+    return;
+  }
   const RowStage st{slot_val(wl, slot), slot_col(wl, slot), nullptr, nullptr};
   const BoxStaged box{slot_seg(wl, slot) + lane, bx, ld};
-  const int beg = info.x, end = beg + cnt;
-  double sing_ll = -INFINITY, sing_uu = INFINITY;
-  bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
-  if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
-  if (mine) my_nnz += (unsigned long long)cnt;
-  if (mine && (ll > ru + kETol || uu < rl - kETol)) {       // :994-1015
-    sh.verdict[lane] = 2;  /* MNTR_INFEAS_ROW */
-    mine = false;
-  }
-  bool do_lb = false, s_lb = false; double act = 0.0;        // row lb side  (:1017-1025)
-  if (mine && rl > -kInf20) {
-    if (uu < kInf20) { do_lb = true; act = uu; }
-    else if (sing_uu < kInf20) { do_lb = true; s_lb = true; act = sing_uu; }
-  }
-  unsigned chg = 0;
-  double w2 = wmax;
-  if (__any_sync(kFull, do_lb && !(-R::sub_lo(rl, act) > wmax))) {
-    chg = row_update<R, true>(P, beg, cnt, box, st, do_lb, s_lb, rl, act, flags, varflag, sh, lane);
-    if (chg) {                                                // :1027-1032
-      const bool redo = mine && ((chg >> lane) & 1u);
-      double l2, u2;
-      row_activity<R>(P, beg, cnt, box, st, lane, l2, u2, w2);
-      if (redo) { ll = l2; uu = u2; }
-      need_sing = redo && (ll < -kInf20 || uu > kInf20);
-      if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
-    }
-  }
-  bool do_ub = false, s_ub = false; act = 0.0;               // row ub side  (:1035-1043)
-  if (mine && ru < kInf20) {
-    if (ll > -kInf20) { do_ub = true; act = ll; }
-    else if (sing_ll > -kInf20) { do_ub = true; s_ub = true; act = sing_ll; }
-  }
-  if (__any_sync(kFull, do_ub && !(R::sub_hi(ru, act) > w2)))
-    (void)row_update<R, false>(P, beg, cnt, box, st, do_ub, s_ub, ru, act, flags, varflag, sh, lane);
+  process_row<R>(P, info, bnd, box, bx, ld, st, mine, flags, varflag, sh, lane, my_nnz);
 }
 
 // Objective cut-off row  c.x <= rhs  for the 32 boxes of the tile  [varBndsFromObj_, :544-597]: evaluated after

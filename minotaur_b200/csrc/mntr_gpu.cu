@@ -42,6 +42,7 @@ struct SingleCtrl {
   int verdict() const { return status[6] ? status[6] : ((sync[2] & mntr::kCtlFinalCross) ? 1 : 0); }
 };
 static_assert(sizeof(SingleCtrl) == 128, "control block layout");
+static_assert(MNTR_GPU_MAX_TAPE == mntr::kMaxTape, "include/mntr_gpu.h and cgraph.cuh disagree on the longest tape");
 
 struct mntr_gpu_ctx {
   int device = 0;
@@ -55,6 +56,7 @@ struct mntr_gpu_ctx {
   int32_t m = 0, n = 0;
   int64_t nnz = 0, nnz_padded = 0;
   std::vector<uint8_t> h_var_type;   // host copy: integer bit of the stored columns
+  std::vector<int32_t> h_perm;       // stored row -> caller's row (rows are stored in wavefront-level order)
   int lanes_per_row = 8;             // sub-warp group size of the per-round kernels
   bool no_zero_copy = false;         // MNTR_GPU_NO_ZEROCOPY=1: always stage pinned host boxes through device copies
   LinDev lin{};
@@ -128,8 +130,11 @@ NcclApi &nccl_api()
 {
   static NcclApi api;
   if (api.handle) return api;
+  // an NCCL the process has already loaded (e.g. PyTorch's bundled one) is reused; otherwise the system's is loaded
+  // with RTLD_LOCAL, so that its symbols cannot shadow those of a different NCCL a later import brings along
   const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
-  for (int k = 0; names[k] && !api.handle; ++k) api.handle = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
+  for (int k = 0; names[k] && !api.handle; ++k) api.handle = dlopen(names[k], RTLD_NOW | RTLD_NOLOAD);
+  for (int k = 0; names[k] && !api.handle; ++k) api.handle = dlopen(names[k], RTLD_NOW | RTLD_LOCAL);
   if (!api.handle) return api;
   api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
   api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
@@ -446,6 +451,7 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
     if ((rc = dev_upload(ctx, ctx->lin_allocs, pcolx.data(), pcolx.size(), &L.colx))) return rc;
   }
   ctx->h_var_type.assign(var_type, var_type + n);
+  ctx->h_perm.assign(perm.begin(), perm.begin() + m);
   if ((rc = dev_upload(ctx, ctx->lin_allocs, pval.data(), pval.size(), &L.val))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, var_type, (size_t)n, &L.var_type))) return rc;
   if ((rc = dev_upload(ctx, ctx->lin_allocs, cptr.data(), (size_t)n + 1, &L.csc_ptr))) return rc;
@@ -622,6 +628,20 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
   if ((rc = dev_upload(ctx, ctx->nl_allocs, lptr.data(), (size_t)n_levels + 1, &N.level_ptr))) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->nl_loaded = true;
+  return MNTR_OK;
+}
+
+int mntr_gpu_update_row_bounds(mntr_gpu_ctx *ctx, int32_t m, const double *row_lb, const double *row_ub)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "update_row_bounds: call load_linear first");
+  if (m != ctx->m || (m > 0 && (!row_lb || !row_ub))) return fail(ctx, MNTR_E_ARG, "update_row_bounds: row count differs from the loaded problem");
+  if (m == 0) return MNTR_OK;
+  CU(cudaSetDevice(ctx->device));
+  std::vector<double2> pbnd((size_t)m);
+  for (int32_t q = 0; q < m; ++q) pbnd[(size_t)q] = make_double2(row_lb[ctx->h_perm[(size_t)q]], row_ub[ctx->h_perm[(size_t)q]]);
+  CU(cudaMemcpyAsync(const_cast<double2 *>(ctx->lin.row_bnd), pbnd.data(), sizeof(double2) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return MNTR_OK;
 }
 

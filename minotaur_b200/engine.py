@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "mntr_gpu_boxes_upload", "mntr_gpu_boxes_download", "mntr_gpu_get_stats",
     "mntr_gpu_tighten_single_dev", "mntr_gpu_stream",
     "mntr_gpu_nccl_unique_id", "mntr_gpu_comm_init", "mntr_gpu_comm_destroy",
-    "mntr_gpu_boxes_from_deltas", "mntr_gpu_alloc_host", "mntr_gpu_free_host",
+    "mntr_gpu_boxes_from_deltas", "mntr_gpu_alloc_host", "mntr_gpu_free_host", "mntr_gpu_update_row_bounds",
     "mntr_gpu_group_create", "mntr_gpu_group_destroy", "mntr_gpu_group_size", "mntr_gpu_group_member",
     "mntr_gpu_group_last_error", "mntr_gpu_group_load_linear", "mntr_gpu_group_load_cgraph",
     "mntr_gpu_group_set_cutoff", "mntr_gpu_group_set_incumbent", "mntr_gpu_group_tighten_nodes",
@@ -105,6 +105,7 @@ def load_library() -> C.CDLL:
     L.mntr_gpu_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.mntr_gpu_comm_destroy.argtypes = [vp]
     L.mntr_gpu_boxes_from_deltas.argtypes = [vp, C.c_int32, _dp, _dp, _lp, _ip, _bp, _dp, vp]
+    L.mntr_gpu_update_row_bounds.argtypes = [vp, C.c_int32, _dp, _dp]
     L.mntr_gpu_alloc_host.argtypes = [vp, C.c_int64]
     L.mntr_gpu_alloc_host.restype = vp
     L.mntr_gpu_free_host.argtypes = [vp, vp]
@@ -232,6 +233,11 @@ class GpuBoundEngine:
                                                 _i(a["arg1"]), _d(a["cnst"]), _i(a["child"]), _i(a["lin_ptr"]),
                                                 _i(a["lin_col"]), _d(a["lin_val"]), _d(a["c_lb"]), _d(a["c_ub"])),
                     "load_cgraph")
+
+    def update_row_bounds(self, row_lb, row_ub):
+        """New bounds for the loaded rows (same order as load_linear): m doubles each way, no re-flattening."""
+        rl = np.ascontiguousarray(row_lb, np.float64); ru = np.ascontiguousarray(row_ub, np.float64)
+        self._check(self.L.mntr_gpu_update_row_bounds(self.h, len(rl), _d(rl), _d(ru)), "update_row_bounds")
 
     def set_cutoff(self, col, val, rhs: float):
         col = np.ascontiguousarray(col, np.int32); val = np.ascontiguousarray(val, np.float64)

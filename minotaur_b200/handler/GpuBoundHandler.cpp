@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <iostream>
 #include <map>
+#include <cstring>
 #include <stdexcept>
 
 #include "MinotaurConfig.h"
@@ -39,17 +40,36 @@ using namespace Minotaur;
 const std::string GpuBoundHandler::me_ = "GpuBoundHandler: ";
 
 GpuBoundHandler::GpuBoundHandler(EnvPtr env, ProblemPtr problem, int device)
-  : env_(env), problem_(problem), ctx_(0), mode_(FastFixpoint), roundNearest_(false), loadedFor_(0),
-    loadedVars_(0), loadedCons_(0), cutoffOn_(false)
+  : env_(env), problem_(problem), ctx_(0), group_(0), mode_(FastFixpoint), roundNearest_(false), checkStructure_(true),
+    loadedFor_(0), loadedVars_(0), loadedCons_(0), cutoffOn_(false), sigStruct_(0), sigBounds_(0), lb_(0), ub_(0), boxCap_(0)
 {
-  logger_ = env->getLogger();
+  init_(std::vector<int>(1, device));
+}
+
+GpuBoundHandler::GpuBoundHandler(EnvPtr env, ProblemPtr problem, const std::vector<int> &devices)
+  : env_(env), problem_(problem), ctx_(0), group_(0), mode_(FastFixpoint), roundNearest_(false), checkStructure_(true),
+    loadedFor_(0), loadedVars_(0), loadedCons_(0), cutoffOn_(false), sigStruct_(0), sigBounds_(0), lb_(0), ub_(0), boxCap_(0)
+{
+  init_(devices);
+}
+
+void GpuBoundHandler::init_(const std::vector<int> &devices)
+{
+  logger_ = env_->getLogger();
   stats_.calls = stats_.uploads = stats_.nMods = stats_.nInf = 0;
+  stats_.rowBoundUpdates = stats_.skippedCons = stats_.engineErrors = 0;
   stats_.nnzUpdates = 0;
   stats_.timeHost = stats_.timeDevice = 0.;
-  int rc = mntr_gpu_create(device, &ctx_);
-  if (rc != MNTR_OK) {
-    ctx_ = 0;
-    // the reference's convention for unusable components is an assert / exception at set-up time
+  int rc;
+  if (devices.size() > 1) {
+    rc = mntr_gpu_group_create((int)devices.size(), &devices[0], &group_);
+    if (rc == MNTR_OK) ctx_ = mntr_gpu_group_member(group_, 0);
+  } else {
+    rc = mntr_gpu_create(devices.empty() ? 0 : devices[0], &ctx_);
+  }
+  if (rc != MNTR_OK || !ctx_) {
+    ctx_ = 0; group_ = 0;
+    // the reference's convention for unusable components is an assert / exception at set-up time (never later)
     throw std::runtime_error("GpuBoundHandler: no usable CUDA device (mntr_gpu_create failed); "
                              "use LinearHandler/NlPresHandler instead");
   }
@@ -57,7 +77,18 @@ GpuBoundHandler::GpuBoundHandler(EnvPtr env, ProblemPtr problem, int device)
 
 GpuBoundHandler::~GpuBoundHandler()
 {
-  if (ctx_) mntr_gpu_destroy(ctx_);
+  if (ctx_) { mntr_gpu_free_host(ctx_, lb_); mntr_gpu_free_host(ctx_, ub_); }
+  if (group_) mntr_gpu_group_destroy(group_);
+  else if (ctx_) mntr_gpu_destroy(ctx_);
+}
+
+// an engine call failed: say so once per call site, count it, and let the caller carry on without tightening
+void GpuBoundHandler::engineFailed_(const char *where)
+{
+  ++stats_.engineErrors;
+  logger_->errStream() << me_ << where << ": " << (ctx_ ? mntr_gpu_last_error(ctx_) : "no context")
+                       << " -- no bound tightening from this call" << std::endl;
+  loadedFor_ = 0;
 }
 
 std::string GpuBoundHandler::getName() const { return "GpuBoundHandler (FBBT on B200)"; }
@@ -124,6 +155,62 @@ bool flattenCGraph(CGraph *cg, std::vector<unsigned char> &op, std::vector<int> 
 
 }  // namespace
 
+// FNV-1a over the words that decide whether the device copy is current
+static inline void fnv(unsigned long long &h, unsigned long long x)
+{
+  for (int k = 0; k < 8; ++k) { h ^= (x >> (8 * k)) & 0xffull; h *= 1099511628211ull; }
+}
+
+void GpuBoundHandler::signature_(ProblemPtr p, unsigned long long &structure, unsigned long long &bounds) const
+{
+  structure = 1469598103934665603ull; bounds = 1469598103934665603ull;
+  fnv(structure, p->getNumVars()); fnv(structure, p->getNumCons());
+  for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it) {
+    ConstraintPtr c = *it;
+    LinearFunctionPtr lf = c->getLinearFunction();
+    fnv(structure, (unsigned long long)c->getState() * 8u + (unsigned long long)c->getFunctionType());
+    fnv(structure, lf ? lf->getNumTerms() : 0u);
+    fnv(structure, (unsigned long long)(size_t)c->getNonlinearFunction());
+    double lb = c->getLb(), ub = c->getUb();
+    unsigned long long bl, bu;
+    memcpy(&bl, &lb, 8); memcpy(&bu, &ub, 8);
+    fnv(bounds, bl); fnv(bounds, bu);
+  }
+  for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) fnv(structure, (unsigned long long)(*it)->getType());
+}
+
+void GpuBoundHandler::sync_(ProblemPtr p)
+{
+  if (loadedFor_ != p || loadedVars_ != p->getNumVars() || loadedCons_ != p->getNumCons()) { upload_(p); return; }
+  if (!checkStructure_) return;
+  unsigned long long st, bd;
+  signature_(p, st, bd);
+  if (st != sigStruct_) { upload_(p); return; }
+  if (bd != sigBounds_) {
+    // same rows, new row bounds (a ConBoundMod, LinearHandler's row-bound tightening): refresh them alone.  The CGraph
+    // constraints' bounds live with their tapes: those re-flatten.
+    bool nlChanged = false;
+    std::vector<double> rl, ru;
+    for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it) {
+      ConstraintPtr c = *it;
+      if (DeletedCons == c->getState()) continue;
+      if (c->getFunctionType() == Linear && c->getQuadraticFunction() == 0 && c->getNonlinearFunction() == 0) {
+        rl.push_back(c->getLb()); ru.push_back(c->getUb());
+      } else if (c->getNonlinearFunction()) nlChanged = true;      // cannot tell which moved: be safe
+    }
+    int rc = MNTR_OK;
+    if (!nlChanged) {
+      const int k = group_ ? mntr_gpu_group_size(group_) : 1;
+      for (int i = 0; i < k && rc == MNTR_OK; ++i)
+        rc = mntr_gpu_update_row_bounds(group_ ? mntr_gpu_group_member(group_, i) : ctx_, (int)rl.size(),
+                                        rl.empty() ? 0 : &rl[0], ru.empty() ? 0 : &ru[0]);
+    }
+    if (nlChanged || rc != MNTR_OK) { upload_(p); return; }
+    sigBounds_ = bd;
+    ++stats_.rowBoundUpdates;
+  }
+}
+
 void GpuBoundHandler::upload_(ProblemPtr p)
 {
   const UInt n = p->getNumVars();
@@ -132,6 +219,7 @@ void GpuBoundHandler::upload_(ProblemPtr p)
   std::vector<unsigned char> vtype(n), op;
   for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it)
     vtype[(*it)->getIndex()] = (unsigned char)(*it)->getType();
+  stats_.skippedCons = 0;
 
   for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it) {
     ConstraintPtr c = *it;
@@ -148,9 +236,16 @@ void GpuBoundHandler::upload_(ProblemPtr p)
       rowLb.push_back(c->getLb());
       rowUb.push_back(c->getUb());
     } else if (c->getFunctionType() != Constant && c->getNonlinearFunction() && !c->getQuadraticFunction()) {
-      // NlPresHandler::varBndsFromCons_ nlf branch, NlPresHandler.cpp:1771-1778 (native CGraph only)
+      // NlPresHandler::varBndsFromCons_ nlf branch, NlPresHandler.cpp:1771-1778 (native CGraph only).  A constraint
+      // the engine cannot take -- a tape longer than MNTR_GPU_MAX_TAPE nodes, a non-CGraph function -- is SKIPPED
+      // and counted: skipping a constraint only loses tightening, it never makes a derived bound invalid.
       CGraph *cg = dynamic_cast<CGraph *>(c->getNonlinearFunction());
-      if (!cg || !flattenCGraph(cg, op, a0, a1, cn, child)) continue;
+      const size_t keep = op.size(), keepChild = child.size();
+      if (!cg || !flattenCGraph(cg, op, a0, a1, cn, child) || op.size() - keep > (size_t)MNTR_GPU_MAX_TAPE) {
+        op.resize(keep); a0.resize(keep); a1.resize(keep); cn.resize(keep); child.resize(keepChild);
+        ++stats_.skippedCons;
+        continue;
+      }
       tapePtr.push_back((int)op.size());
       if (lf)
         for (VariableGroupConstIterator t = lf->termsBegin(); t != lf->termsEnd(); ++t) {
@@ -160,6 +255,8 @@ void GpuBoundHandler::upload_(ProblemPtr p)
       linPtr.push_back((int)linCol.size());
       cLb.push_back(c->getLb());
       cUb.push_back(c->getUb());
+    } else if (c->getFunctionType() != Constant && c->getFunctionType() != Linear) {
+      ++stats_.skippedCons;        // QuadraticFunction constraints: QuadHandler's
     }
   }
   // CSR columns must ascend by variable INDEX; LinearFunction orders by id, which equals the index unless
@@ -175,22 +272,41 @@ void GpuBoundHandler::upload_(ProblemPtr p)
     }
   }
   const int m = (int)rowPtr.size() - 1;
-  int rc = mntr_gpu_load_linear(ctx_, m, (int)n, &rowPtr[0], col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0],
-                                rowLb.empty() ? 0 : &rowLb[0], rowUb.empty() ? 0 : &rowUb[0],
-                                vtype.empty() ? 0 : &vtype[0], 0);
-  if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
   const int nc = (int)tapePtr.size() - 1;
-  if (nc > 0) {
-    if (child.empty()) child.push_back(0);
-    if (linCol.empty()) { linCol.push_back(0); linVal.push_back(0.); }
-    rc = mntr_gpu_load_cgraph(ctx_, nc, &tapePtr[0], &op[0], &a0[0], &a1[0], &cn[0], &child[0], &linPtr[0],
-                              &linCol[0], &linVal[0], &cLb[0], &cUb[0]);
-    if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+  if (child.empty()) child.push_back(0);
+  if (linCol.empty()) { linCol.push_back(0); linVal.push_back(0.); }
+  int rc;
+  if (group_) {
+    rc = mntr_gpu_group_load_linear(group_, m, (int)n, &rowPtr[0], col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0],
+                                    rowLb.empty() ? 0 : &rowLb[0], rowUb.empty() ? 0 : &rowUb[0], vtype.empty() ? 0 : &vtype[0], 0);
+    if (rc == MNTR_OK && nc > 0)
+      rc = mntr_gpu_group_load_cgraph(group_, nc, &tapePtr[0], &op[0], &a0[0], &a1[0], &cn[0], &child[0], &linPtr[0],
+                                      &linCol[0], &linVal[0], &cLb[0], &cUb[0]);
+  } else {
+    rc = mntr_gpu_load_linear(ctx_, m, (int)n, &rowPtr[0], col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0],
+                              rowLb.empty() ? 0 : &rowLb[0], rowUb.empty() ? 0 : &rowUb[0], vtype.empty() ? 0 : &vtype[0], 0);
+    if (rc == MNTR_OK && nc > 0)
+      rc = mntr_gpu_load_cgraph(ctx_, nc, &tapePtr[0], &op[0], &a0[0], &a1[0], &cn[0], &child[0], &linPtr[0],
+                                &linCol[0], &linVal[0], &cLb[0], &cUb[0]);
   }
+  if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + (group_ ? mntr_gpu_group_last_error(group_) : mntr_gpu_last_error(ctx_)));
   loadedFor_ = p;
   loadedVars_ = p->getNumVars();
   loadedCons_ = p->getNumCons();
-  lb_.resize(n); ub_.resize(n); lb0_.resize(n); ub0_.resize(n);
+  signature_(p, sigStruct_, sigBounds_);
+  cutoffOn_ = false;
+  if (n > boxCap_) {
+    mntr_gpu_free_host(ctx_, lb_); mntr_gpu_free_host(ctx_, ub_);
+    lb_ = (double *)mntr_gpu_alloc_host(ctx_, (long long)sizeof(double) * std::max<UInt>(n, 1));
+    ub_ = (double *)mntr_gpu_alloc_host(ctx_, (long long)sizeof(double) * std::max<UInt>(n, 1));
+    if (!lb_ || !ub_) throw std::runtime_error(std::string(me_) + "mntr_gpu_alloc_host failed");
+    boxCap_ = n;
+  }
+  lb0_.resize(n); ub0_.resize(n);
+  if (stats_.skippedCons > 0)
+    logger_->msgStream(LogInfo) << me_ << stats_.skippedCons << " constraint(s) are not taken by the GPU engine (tape longer than "
+                                << MNTR_GPU_MAX_TAPE << " nodes, quadratic or non-CGraph function); they stay with NlPresHandler / QuadHandler"
+                                << std::endl;
   ++stats_.uploads;
 }
 
@@ -203,7 +319,8 @@ void GpuBoundHandler::setCutoff_(ProblemPtr p, SolutionPoolPtr spool)
   const bool on = spool && spool->getNumSols() > 0 && lf && o->getFunctionType() == Linear;
   if (!on) {
     if (cutoffOn_) {
-      if (mntr_gpu_set_cutoff(ctx_, 0, 0, 0, 0.0) != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+      const int rc0 = group_ ? mntr_gpu_group_set_cutoff(group_, 0, 0, 0, 0.0) : mntr_gpu_set_cutoff(ctx_, 0, 0, 0, 0.0);
+      if (rc0 != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
       cutoffOn_ = false;
     }
     return;
@@ -216,18 +333,27 @@ void GpuBoundHandler::setCutoff_(ProblemPtr p, SolutionPoolPtr spool)
   std::vector<double> val(terms.size());
   for (size_t t = 0; t < terms.size(); ++t) { col[t] = terms[t].first; val[t] = terms[t].second; }
   const double rhs = spool->getBestSolutionValue() - o->getConstant();
-  if (mntr_gpu_set_cutoff(ctx_, (int)col.size(), col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0], rhs) != MNTR_OK)
-    throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+  const int rc1 = group_ ? mntr_gpu_group_set_cutoff(group_, (int)col.size(), col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0], rhs)
+                         : mntr_gpu_set_cutoff(ctx_, (int)col.size(), col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0], rhs);
+  if (rc1 != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
   cutoffOn_ = !col.empty();
   // NlPresHandler::fixObjBins_ compares against the raw pool value (NlPresHandler.cpp:1030)
-  if (mntr_gpu_set_incumbent(ctx_, spool->getBestSolutionValue()) != MNTR_OK)
-    throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+  const int rc2 = group_ ? mntr_gpu_group_set_incumbent(group_, spool->getBestSolutionValue())
+                         : mntr_gpu_set_incumbent(ctx_, spool->getBestSolutionValue());
+  if (rc2 != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
 }
 
 bool GpuBoundHandler::tighten_(ProblemPtr p, SolutionPoolPtr spool, ModVector &mods, bool truncated)
 {
-  if (loadedFor_ != p || loadedVars_ != p->getNumVars() || loadedCons_ != p->getNumCons()) { upload_(p); cutoffOn_ = false; }
-  setCutoff_(p, spool);
+  // Nothing on this path may abort the solve (no exceptions on the node path): an engine failure is
+  // logged and counted, and the call reports "no tightening".
+  try {
+    sync_(p);
+    setCutoff_(p, spool);
+  } catch (const std::exception &) {
+    engineFailed_("upload");
+    return false;
+  }
   const UInt n = p->getNumVars();
   for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) {
     const UInt j = (*it)->getIndex();
@@ -244,13 +370,13 @@ bool GpuBoundHandler::tighten_(ProblemPtr p, SolutionPoolPtr spool, ModVector &m
   o.reserved[0] = o.reserved[1] = 0;
   int verdict = 0, rounds = 0;
   long long nnz = 0;
-  int rc = mntr_gpu_tighten(ctx_, 1, n ? &lb_[0] : 0, n ? &ub_[0] : 0, &o, &verdict, &rounds, (int64_t *)&nnz);
+  int rc = mntr_gpu_tighten(ctx_, 1, lb_, ub_, &o, &verdict, &rounds, (int64_t *)&nnz);
   if (rc == MNTR_E_UNSUPPORTED && o.order == MNTR_ORDER_JACOBI) {
     // CGraph constraints are evaluated by the reference-order kernel
     o.order = MNTR_ORDER_REFERENCE;
-    rc = mntr_gpu_tighten(ctx_, 1, &lb_[0], &ub_[0], &o, &verdict, &rounds, (int64_t *)&nnz);
+    rc = mntr_gpu_tighten(ctx_, 1, lb_, ub_, &o, &verdict, &rounds, (int64_t *)&nnz);
   }
-  if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+  if (rc != MNTR_OK) { engineFailed_("tighten"); return false; }
   mntr_gpu_stats st;
   mntr_gpu_get_stats(ctx_, &st);
   stats_.timeDevice += st.kernel_ms + st.h2d_ms + st.d2h_ms;
@@ -283,12 +409,17 @@ void GpuBoundHandler::tightenCandidates(RelaxationPtr rel, SolutionPoolPtr spool
                                         std::vector<BoxOutcome> &out)
 {
   ProblemPtr p = rel;
-  if (loadedFor_ != p || loadedVars_ != p->getNumVars() || loadedCons_ != p->getNumCons()) { upload_(p); cutoffOn_ = false; }
-  setCutoff_(p, spool);
-  const UInt n = p->getNumVars();
   const int nb = (int)deltas.size();
   out.assign(deltas.size(), BoxOutcome());
   if (nb == 0) return;
+  try {
+    sync_(p);
+    setCutoff_(p, spool);
+  } catch (const std::exception &) {
+    engineFailed_("upload");
+    return;                          // every outcome: feasible, no changes
+  }
+  const UInt n = p->getNumVars();
   for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) {
     const UInt j = (*it)->getIndex();
     lb_[j] = (*it)->getLb();
@@ -323,9 +454,12 @@ void GpuBoundHandler::tightenCandidates(RelaxationPtr rel, SolutionPoolPtr spool
   std::vector<double> mval;
   for (int attempt = 0; attempt < 2; ++attempt) {          // second trip only when the tuple buffer was too small
     mvar.assign((size_t)cap, 0); mup.assign((size_t)cap, 0); mval.assign((size_t)cap, 0.);
-    const int rc = mntr_gpu_tighten_nodes(ctx_, nb, n ? &lb_[0] : 0, n ? &ub_[0] : 0, &dptr[0], &dvar[0], &dup[0], &dval[0],
-                                          &o, &verdict[0], &rounds[0], &mptr[0], &mvar[0], &mup[0], &mval[0], cap, &total);
-    if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + mntr_gpu_last_error(ctx_));
+    const int rc = group_
+        ? mntr_gpu_group_tighten_nodes(group_, nb, lb_, ub_, &dptr[0], &dvar[0], &dup[0], &dval[0], &o, &verdict[0],
+                                       &rounds[0], &mptr[0], &mvar[0], &mup[0], &mval[0], cap, &total)
+        : mntr_gpu_tighten_nodes(ctx_, nb, lb_, ub_, &dptr[0], &dvar[0], &dup[0], &dval[0], &o, &verdict[0], &rounds[0],
+                                 &mptr[0], &mvar[0], &mup[0], &mval[0], cap, &total);
+    if (rc != MNTR_OK) { engineFailed_("tighten_nodes"); return; }
     if (total <= cap) break;
     cap = total;
   }
@@ -390,6 +524,7 @@ SolveStatus GpuBoundHandler::presolve(PreModQ *, bool *changed, Solution **)
   ModVector mods;
   Timer *timer = env_->getNewTimer();
   timer->start();
+  invalidate();       // LinearHandler::presolve edits coefficients and rows in place between the calls (coeffImp_, dupRows_)
   const bool inf = tighten_(problem_, SolutionPoolPtr(), mods, false);     // root presolve: no incumbent yet
   if (!mods.empty()) *changed = true;
   // root mode keeps no undo information: the mods are already applied (LinearHandler deletes them too,
@@ -405,6 +540,9 @@ void GpuBoundHandler::writeStats(std::ostream &out) const
   out << me_ << "Statistics for GPU bound tightening:" << std::endl
       << me_ << "Calls                        = " << stats_.calls << std::endl
       << me_ << "Structure uploads            = " << stats_.uploads << std::endl
+      << me_ << "Row-bound refreshes          = " << stats_.rowBoundUpdates << std::endl
+      << me_ << "Constraints left to others   = " << stats_.skippedCons << std::endl
+      << me_ << "Engine errors                = " << stats_.engineErrors << std::endl
       << me_ << "Bound modifications          = " << stats_.nMods << std::endl
       << me_ << "Times infeasibility detected = " << stats_.nInf << std::endl
       << me_ << "nnz-updates                  = " << stats_.nnzUpdates << std::endl

@@ -26,6 +26,7 @@
 #include "Handler.h"
 
 struct mntr_gpu_ctx;
+struct mntr_gpu_group;
 
 namespace Minotaur {
 
@@ -35,6 +36,9 @@ struct GpuBoundStats {
   int uploads;        ///< times the problem structure was (re)flattened and uploaded
   int nMods;          ///< VarBoundMods emitted
   int nInf;           ///< calls that proved infeasibility
+  int rowBoundUpdates; ///< times only the row bounds were refreshed on the device (structure unchanged)
+  int skippedCons;    ///< constraints of the last upload the engine does not take (left to NlPresHandler / QuadHandler)
+  int engineErrors;   ///< engine calls that failed (the call then reports "no tightening", it never aborts the solve)
   long long nnzUpdates;
   double timeHost;    ///< host seconds in flatten + gather + mod emission
   double timeDevice;  ///< device milliseconds reported by the engine
@@ -49,6 +53,9 @@ public:
   };
 
   GpuBoundHandler(EnvPtr env, ProblemPtr problem, int device = 0);
+  /// Several GPUs of the box: node boxes (presolveNode, simplePresolve) run on devices[0]; tightenCandidates splits
+  /// its batch over all of them (mntr_gpu_group_*: one process, one host thread per device, no collective).
+  GpuBoundHandler(EnvPtr env, ProblemPtr problem, const std::vector<int> &devices);
   ~GpuBoundHandler();
 
   // ---- Handler interface: does nothing, like NlPresHandler ----
@@ -98,6 +105,17 @@ public:
   void setMode(Mode m) { mode_ = m; }
   /// Reproduce the reference's round-to-nearest arithmetic instead of outward rounding.
   void setRoundNearest(bool b) { roundNearest_ = b; }
+  /**
+   * Before every call the handler compares a signature of the problem's rows (state, bounds, number of terms of every
+   * constraint: one pass over the constraints, no pass over the terms) with the one of the device copy: changed row
+   * BOUNDS alone are refreshed (mntr_gpu_update_row_bounds), anything else re-flattens the problem.  Coefficients
+   * edited in place with the term count unchanged (LinearHandler::coeffImp_) are not seen by the signature: root
+   * presolve() therefore always re-flattens, and callers that edit coefficients between node calls call invalidate().
+   * A caller that guarantees a static structure may switch the check off.
+   */
+  void setStructureCheck(bool b) { checkStructure_ = b; }
+  /// Forget the device copy: the next call re-flattens and uploads the problem.
+  void invalidate() { loadedFor_ = 0; }
   const GpuBoundStats *getStats() const { return &stats_; }
   /// False when no CUDA device / library is usable; every call then reports "no tightening" is NOT done:
   /// the handler throws at construction instead (there is no CPU fallback).
@@ -108,8 +126,10 @@ private:
   ProblemPtr problem_;
   LoggerPtr logger_;
   mntr_gpu_ctx *ctx_;
+  mntr_gpu_group *group_;   // non-null with several devices; ctx_ is then its first member
   Mode mode_;
   bool roundNearest_;
+  bool checkStructure_;
   GpuBoundStats stats_;
   static const std::string me_;
 
@@ -117,10 +137,20 @@ private:
   const Problem *loadedFor_;
   UInt loadedVars_, loadedCons_;
   bool cutoffOn_;      // an objective cut-off row is installed on the device
-  std::vector<double> lb_, ub_, lb0_, ub0_;
+  unsigned long long sigStruct_, sigBounds_;   // signature of the uploaded rows: structure / row bounds
+  // the box that travels: page-locked, device-mapped host memory (mntr_gpu_alloc_host), so that a single-box call is
+  // ONE kernel launch that reads the bounds over PCIe and writes back only those that moved
+  double *lb_, *ub_;
+  UInt boxCap_;
+  std::vector<double> lb0_, ub0_;
 
   /// Flatten p (linear rows -> CSR, CGraph constraints -> tapes) and upload it.
   void upload_(ProblemPtr p);
+  /// Make the device copy current for p (signature check, see setStructureCheck).
+  void sync_(ProblemPtr p);
+  void signature_(ProblemPtr p, unsigned long long &structure, unsigned long long &bounds) const;
+  void init_(const std::vector<int> &devices);
+  void engineFailed_(const char *where);
   /// One tighten call on the current bounds of p; emits applied VarBoundMods.  Returns infeasible?
   bool tighten_(ProblemPtr p, SolutionPoolPtr spool, ModVector &mods, bool truncated);
   void setCutoff_(ProblemPtr p, SolutionPoolPtr spool);

@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <string>
 #include <vector>
 
 #include "MinotaurConfig.h"
@@ -19,6 +21,7 @@
 #include "LinearHandler.h"
 #include "NlPresHandler.h"
 #include "Objective.h"
+#include "Presolver.h"
 #include "Problem.h"
 #include "Relaxation.h"
 #include "SolutionPool.h"
@@ -99,7 +102,92 @@ static int failures = 0;
 #define CHECK(cond, ...) do { if (!(cond)) { ++failures; fprintf(stderr, "FAIL %s:%d: ", __FILE__, __LINE__); \
                               fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
 
-int main()
+// tests/golden/tls4_flat.txt (written by tests/golden/make_tls4_flat.py): test_instances/tls4.nl as Minotaur objects
+static ProblemPtr readFlat(EnvPtr env, const char *path)
+{
+  std::ifstream in(path);
+  if (!in) return 0;
+  auto num = [&]() { std::string t; in >> t; return t == "inf" ? INFINITY : (t == "-inf" ? -INFINITY : atof(t.c_str())); };
+  int n, m, nc;
+  in >> n >> m >> nc;
+  ProblemPtr p = (ProblemPtr) new Problem(env);
+  std::vector<VariablePtr> v(n);
+  for (int j = 0; j < n; ++j) { int ty; in >> ty; const double lb = num(), ub = num(); v[j] = p->newVariable(lb, ub, (VariableType)ty); }
+  for (int i = 0; i < m; ++i) {
+    const double lb = num(), ub = num(); int k; in >> k;
+    LinearFunctionPtr lf = (LinearFunctionPtr) new LinearFunction();
+    for (int t = 0; t < k; ++t) { int c; in >> c; lf->addTerm(v[c], num()); }
+    p->newConstraint((FunctionPtr) new Function(lf), lb, ub);
+  }
+  for (int c = 0; c < nc; ++c) {
+    const double clb = num(), cub = num(); int nn, klin, nchild; in >> nn >> klin >> nchild;
+    std::vector<int> op(nn), a0(nn), a1(nn); std::vector<double> cn(nn);
+    for (int i = 0; i < nn; ++i) { in >> op[i] >> a0[i] >> a1[i]; cn[i] = num(); }
+    std::vector<std::pair<int, double> > lin;
+    if (klin == 0) { std::string dash; in >> dash; }
+    for (int t = 0; t < klin; ++t) { int col; in >> col; lin.push_back(std::make_pair(col, num())); }
+    std::vector<int> child(nchild);
+    if (nchild == 0) { std::string dash; in >> dash; }
+    for (int t = 0; t < nchild; ++t) in >> child[t];
+    CGraph *cg = new CGraph();
+    std::vector<CNode *> nodes(nn, (CNode *)0);
+    for (int i = 0; i < nn; ++i) {
+      const OpCode o = (OpCode)op[i];
+      if (o == OpVar) nodes[i] = cg->newNode(v[a0[i]]);
+      else if (o == OpNum) nodes[i] = cg->newNode(cn[i]);
+      else if (o == OpInt) nodes[i] = cg->newNode((int)cn[i]);
+      else if (o == OpSumList) {
+        std::vector<CNode *> ch;
+        for (int q = a0[i]; q < a1[i]; ++q) ch.push_back(nodes[child[q]]);
+        nodes[i] = cg->newNode(OpSumList, &ch[0], (UInt)ch.size());
+      } else nodes[i] = cg->newNode(o, nodes[a0[i]], a1[i] >= 0 ? nodes[a1[i]] : (CNode *)0);
+    }
+    cg->setOut(nodes[nn - 1]);
+    cg->finalize();
+    LinearFunctionPtr lf = 0;
+    if (klin > 0) { lf = (LinearFunctionPtr) new LinearFunction(); for (int t = 0; t < klin; ++t) lf->addTerm(v[lin[t].first], lin[t].second); }
+    p->newConstraint((FunctionPtr) new Function(lf, (NonlinearFunctionPtr)cg), clb, cub);
+  }
+  int k; in >> k; const double oc = num();
+  LinearFunctionPtr of = (LinearFunctionPtr) new LinearFunction();
+  for (int t = 0; t < k; ++t) { int c; in >> c; of->addTerm(v[c], num()); }
+  p->newObjective((FunctionPtr) new Function(of), oc, Minimize);
+  p->calculateSize();
+  return p;
+}
+
+// Root presolve through Presolver::solve (Presolver.cpp:91-182): the reference pair LinearHandler + NlPresHandler on one
+// copy of the problem, LinearHandler + GpuBoundHandler (reference order, round to nearest) on another.  Returns the
+// number of bounds that differ; prints what each run did.
+static int rootPresolve(EnvPtr env, ProblemPtr pA, ProblemPtr pB, const char *what, int *tightA, int *tightB)
+{
+  std::vector<double> l0, u0;
+  for (VariableConstIterator it = pA->varsBegin(); it != pA->varsEnd(); ++it) { l0.push_back((*it)->getLb()); u0.push_back((*it)->getUb()); }
+  HandlerVector hA, hB;
+  LinearHandler *lhA = new LinearHandler(env, pA); NlPresHandler *nhA = new NlPresHandler(env, pA);
+  hA.push_back(lhA); hA.push_back(nhA);
+  LinearHandler *lhB = new LinearHandler(env, pB); GpuBoundHandler *ghB = new GpuBoundHandler(env, pB, 0);
+  ghB->setMode(GpuBoundHandler::ReferenceOrder); ghB->setRoundNearest(true);
+  hB.push_back(lhB); hB.push_back(ghB);
+  Presolver prA(pA, env, hA), prB(pB, env, hB);
+  const SolveStatus sA = prA.solve(), sB = prB.solve();
+  int diff = 0; *tightA = 0; *tightB = 0;
+  const UInt n = pA->getNumVars();
+  if (pB->getNumVars() != n) { printf("root presolve %s: variable counts differ (%u vs %u)\n", what, n, pB->getNumVars()); return -1; }
+  VariableConstIterator ia = pA->varsBegin(), ib = pB->varsBegin();
+  for (UInt j = 0; j < n; ++j, ++ia, ++ib) {
+    if ((*ia)->getLb() != (*ib)->getLb() || (*ia)->getUb() != (*ib)->getUb()) ++diff;
+  }
+  printf("root presolve %s: reference pair status %d, %u vars %u cons left; with GpuBoundHandler status %d, %u vars %u cons left; "
+         "%d of %u variables end with different bounds; GPU handler: %d calls, %d uploads, %d mods\n", what, (int)sA,
+         pA->getNumVars(), pA->getNumCons(), (int)sB, pB->getNumVars(), pB->getNumCons(), diff, n, ghB->getStats()->calls,
+         ghB->getStats()->uploads, ghB->getStats()->nMods);
+  (void)l0; (void)u0;
+  delete lhA; delete nhA; delete lhB; delete ghB;
+  return (sA == sB && pA->getNumCons() == pB->getNumCons()) ? diff : -1;
+}
+
+int main(int argc, char **argv)
 {
   EnvPtr env = (EnvPtr) new Environment();
   int err = 0;
@@ -239,6 +327,106 @@ int main()
     delete rel;
     delete p;
   }
+  // ---- the device copy follows the problem: a row bound changed between two calls (ConBoundMod, a cut tightened) ----
+  int n_stale = 0;
+  {
+    std::vector<double> xstar;
+    const uint64_t keep = rng_state;
+    ProblemPtr pA = makeProblem(env, 300, 320, 6, 20, xstar);
+    rng_state = keep;
+    ProblemPtr pB = makeProblem(env, 300, 320, 6, 20, xstar);
+    RelaxationPtr relA = (RelaxationPtr) new Relaxation(pA, env), relB = (RelaxationPtr) new Relaxation(pB, env);
+    relA->calculateSize(); relB->calculateSize();
+    GpuBoundHandler gh(env, pB, 0);
+    gh.setMode(GpuBoundHandler::ReferenceOrder); gh.setRoundNearest(true);
+    ModVector pm;
+    for (int step = 0; step < 3; ++step) {
+      if (step > 0) {
+        // tighten the upper bound of a few linear rows by one (the planted point may be cut off: fine, both sides see
+        // the same rows) -- same change on both copies
+        for (int k = 0; k < 12; ++k) {
+          const int i = irand(0, 319);
+          ConstraintPtr ca = relA->getConstraint(i), cb = relB->getConstraint(i);
+          if (ca->getUb() < 1e20) { relA->changeBound(ca, Upper, ca->getUb() - 1.0); relB->changeBound(cb, Upper, cb->getUb() - 1.0); }
+        }
+      }
+      LinearHandler lh(env, pA); NlPresHandler nh(env, pA);
+      ModVector rmA, rmB;
+      bool infA = lh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pm, rmA);
+      if (!infA) infA = nh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pm, rmA);
+      const bool infB = gh.presolveNode(relB, (NodePtr)0, (SolutionPoolPtr)0, pm, rmB);
+      ++n_stale;
+      if (!(infB && !infA)) {
+        CHECK(infA == infB, "stale step %d: verdict ref %d gpu %d", step, (int)infA, (int)infB);
+        for (int j = 0; j < 300 && !infA; ++j)
+          CHECK(relA->getVariable(j)->getLb() == relB->getVariable(j)->getLb() && relA->getVariable(j)->getUb() == relB->getVariable(j)->getUb(),
+                "stale step %d var %d: ref [%.17g,%.17g] gpu [%.17g,%.17g]", step, j, relA->getVariable(j)->getLb(),
+                relA->getVariable(j)->getUb(), relB->getVariable(j)->getLb(), relB->getVariable(j)->getUb());
+      }
+      for (ModVector::reverse_iterator it = rmA.rbegin(); it != rmA.rend(); ++it) { (*it)->undoToProblem(relA); delete *it; }
+      for (ModVector::reverse_iterator it = rmB.rbegin(); it != rmB.rend(); ++it) { (*it)->undoToProblem(relB); delete *it; }
+    }
+    CHECK(gh.getStats()->uploads == 1 && gh.getStats()->rowBoundUpdates == 2,
+          "row-bound changes: %d uploads, %d row-bound refreshes (expected 1 and 2)", gh.getStats()->uploads, gh.getStats()->rowBoundUpdates);
+    delete relA; delete relB; delete pA; delete pB;
+  }
+  // ---- setModFlags(true, true): the bounds found on the relaxation are mirrored into the original problem as p_mods
+  //      (LinearHandler::copyBndsFromRel_, LinearHandler.cpp:108-132) ----
+  int n_pmods = 0;
+  {
+    std::vector<double> xstar;
+    const uint64_t keep = rng_state;
+    ProblemPtr pA = makeProblem(env, 260, 300, 6, 0, xstar);
+    rng_state = keep;
+    ProblemPtr pB = makeProblem(env, 260, 300, 6, 0, xstar);
+    RelaxationPtr relA = (RelaxationPtr) new Relaxation(pA, env), relB = (RelaxationPtr) new Relaxation(pB, env);
+    relA->calculateSize(); relB->calculateSize();
+    const uint64_t keep2 = rng_state;
+    branch(relA, 6); rng_state = keep2; branch(relB, 6);
+    LinearHandler lh(env, pA);
+    lh.setModFlags(true, true);
+    GpuBoundHandler gh(env, pB, 0);
+    gh.setMode(GpuBoundHandler::ReferenceOrder); gh.setRoundNearest(true);
+    gh.setModFlags(true, true);
+    ModVector pmA, pmB, rmA, rmB;
+    const bool infA = lh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pmA, rmA);
+    const bool infB = gh.presolveNode(relB, (NodePtr)0, (SolutionPoolPtr)0, pmB, rmB);
+    CHECK(infA == infB || (infB && !infA), "modProb: verdicts differ");
+    if (!infA && !infB) {
+      CHECK(pmA.size() == pmB.size(), "modProb: %d p_mods from LinearHandler, %d from GpuBoundHandler", (int)pmA.size(), (int)pmB.size());
+      for (int j = 0; j < 260; ++j)
+        CHECK(pA->getVariable(j)->getLb() == pB->getVariable(j)->getLb() && pA->getVariable(j)->getUb() == pB->getVariable(j)->getUb(),
+              "modProb var %d: original problem bounds differ", j);
+      n_pmods = (int)pmB.size();
+    }
+    for (ModVector::iterator it = pmA.begin(); it != pmA.end(); ++it) delete *it;
+    for (ModVector::iterator it = pmB.begin(); it != pmB.end(); ++it) delete *it;
+    for (ModVector::iterator it = rmA.begin(); it != rmA.end(); ++it) delete *it;
+    for (ModVector::iterator it = rmB.begin(); it != rmB.end(); ++it) delete *it;
+    delete relA; delete relB; delete pA; delete pB;
+  }
+  // ---- root: Presolver::solve with LinearHandler + GpuBoundHandler against the reference pair ----
+  {
+    std::vector<double> xstar;
+    const uint64_t keep = rng_state;
+    ProblemPtr pA = makeProblem(env, 300, 320, 6, 30, xstar);
+    rng_state = keep;
+    ProblemPtr pB = makeProblem(env, 300, 320, 6, 30, xstar);
+    int ta, tb;
+    const int d = rootPresolve(env, pA, pB, "random MINLP (300 variables, 320 rows, 30 bilinear constraints)", &ta, &tb);
+    CHECK(d == 0, "root presolve (random MINLP): %d variables end with different bounds", d);
+    delete pA; delete pB;
+    if (argc > 1) {
+      ProblemPtr tA = readFlat(env, argv[1]), tB = readFlat(env, argv[1]);
+      CHECK(tA && tB, "cannot read %s", argv[1]);
+      if (tA && tB) {
+        const int dt = rootPresolve(env, tA, tB, "tls4 (BASELINE config 1)", &ta, &tb);
+        CHECK(dt == 0, "root presolve (tls4): %d variables end with different bounds", dt);
+      }
+      delete tA; delete tB;
+    }
+  }
+  printf("handler_test: %d calls with row bounds changed in between, %d p_mods mirrored into the original problem\n", n_stale, n_pmods);
   printf("handler_test: %d comparisons (%d with an incumbent cut-off), %d infeasible, %d mods emitted; "
          "%d strong-branching candidates in one batch (%d infeasible); %d failures\n",
          n_cmp, n_cut, n_inf, n_mods, n_cand, n_cand_inf, failures);

@@ -15,7 +15,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 def test_handler_matches_reference_handlers():
     if not os.path.exists(BIN):
         pytest.skip("oracle/_ref/handler_test not built (needs /root/reference at build time)")
-    res = subprocess.run([BIN], capture_output=True, text=True, timeout=500)
+    res = subprocess.run([BIN, os.path.join(ROOT, "tests", "golden", "tls4_flat.txt")], capture_output=True, text=True, timeout=500)
     print(res.stdout[-2000:], res.stderr[-4000:])
     assert res.returncode == 0, res.stderr[-4000:]
     assert "0 failures" in res.stdout
