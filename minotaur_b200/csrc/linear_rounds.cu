@@ -18,6 +18,9 @@ namespace mntr {
 namespace {
 
 constexpr int kRoundsThreads = 256;
+// gathers a lane of the rows kernel keeps in flight: the whole resident part of a row at once (one trip to L2 / DRAM
+// per 32-row block instead of three; 128 registers per thread, two blocks per SM)
+constexpr int kRoundsGathers = kRes;
 
 // a variable goes on a list once: the bit set says who is on it already
 __device__ __forceinline__ void note_touched(uint32_t *bits, int32_t *list, int32_t *count, int j)
@@ -114,7 +117,7 @@ __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W
       if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
       const int32_t *gcol; const double *gval;
       stage_block(P, S, lane, is_due, h, gcol, gval);
-      eval_resident<R>(P, rd, sink, S, lane, is_due, h, false, gcol, gval);
+      eval_resident<R, kRoundsGathers>(P, rd, sink, S, lane, is_due, h, false, gcol, gval);
     }
   }
   drain_queue<R>(P, rd, sink, S, lane);
@@ -148,7 +151,7 @@ __global__ void rounds_init_kernel(LinDev P, RoundsWs W, const double *lb_io, co
 }
 
 template <class R>
-__global__ void __launch_bounds__(kRoundsThreads, 4)
+__global__ void __launch_bounds__(kRoundsThreads, kRoundsGathers > 4 ? 2 : 4)
 rounds_rows_kernel(LinDev P, RoundsWs W, int first)
 {
   if (loop_stopped(W.ctrl)) return;

@@ -81,6 +81,10 @@ struct mntr_gpu_ctx {
   int32_t *d_verdict = nullptr, *d_rounds = nullptr;
   long long *d_nnzb = nullptr;
   unsigned long long *d_nl_evals = nullptr;   // [1] CGraph evaluations of the last batch call
+  // grow-only device scratch of the node-batch calls (root, deltas, mod counts / offsets / tuples): allocating and
+  // freeing hundreds of MB per call costs tens of milliseconds on the host, unpredictably
+  struct DevBuf { void *p = nullptr; size_t cap = 0; };
+  DevBuf nb_buf[16];
   double *d_stage_lb = nullptr, *d_stage_ub = nullptr;
   int64_t stage_boxes = 0;
 
@@ -211,6 +215,31 @@ void free_stage(mntr_gpu_ctx *c)
   c->d_stage_lb = nullptr; c->d_stage_ub = nullptr; c->stage_boxes = 0;
 }
 
+// grow-only scratch slot k of at least `bytes`
+int scratch(mntr_gpu_ctx *ctx, int k, size_t bytes, void **out)
+{
+  mntr_gpu_ctx::DevBuf &b = ctx->nb_buf[k];
+  bytes = std::max<size_t>(bytes, 16);
+  if (b.cap < bytes) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    const size_t want = bytes + bytes / 4;            // headroom: batches of similar size do not reallocate
+    if (cudaMalloc(&b.p, want) != cudaSuccess) {
+      (void)cudaGetLastError();
+      b.p = nullptr;
+      return fail(ctx, MNTR_E_NOMEM, "node batch: out of device memory (%zu bytes)", want);
+    }
+    b.cap = want;
+  }
+  *out = b.p;
+  return MNTR_OK;
+}
+
+void free_scratch(mntr_gpu_ctx *c)
+{
+  for (auto &b : c->nb_buf) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+}
+
 void free_batch(mntr_gpu_ctx *c)
 {
   cudaFree(c->d_boxes); cudaFree(c->d_rowflag); cudaFree(c->d_varflag); cudaFree(c->d_tstate); cudaFree(c->d_verdict); cudaFree(c->d_rounds);
@@ -336,7 +365,7 @@ void mntr_gpu_destroy(mntr_gpu_ctx *ctx)
   p2p_teardown(ctx);
   if (ctx->h_single) { cudaFreeHost(ctx->h_single); ctx->h_single = nullptr; }
   free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->nl_allocs); free_all(ctx->single_allocs);
-  free_batch(ctx); free_stage(ctx);
+  free_batch(ctx); free_stage(ctx); free_scratch(ctx);
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1256,28 +1285,20 @@ int check_deltas(mntr_gpu_ctx *ctx, const char *who, int32_t n_boxes, const doub
   return MNTR_OK;
 }
 
-// uploads root + deltas (device scratch appended to `scratch`) and builds the boxes in the engine's layout
-int boxes_from_deltas(mntr_gpu_ctx *ctx, std::vector<void *> &scratch, int32_t n_boxes, const double *root_lb,
+// uploads root + deltas (the context's grow-only scratch) and builds the boxes in the engine's layout
+int boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *root_lb,
                       const double *root_ub, const int64_t *delta_ptr, const int32_t *delta_var,
                       const uint8_t *delta_is_upper, const double *delta_val, double2 *boxes, DeviceDeltas &D)
 {
   const int32_t n = ctx->n;
   const int64_t n_delta = delta_ptr[n_boxes], ld = mntr_gpu_box_ld(n_boxes);
-  auto dalloc = [&](void **p, size_t bytes) -> int {
-    if (cudaMalloc(p, std::max<size_t>(bytes, 16)) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return fail(ctx, MNTR_E_NOMEM, "node batch: out of device memory");
-    }
-    scratch.push_back(*p);
-    return MNTR_OK;
-  };
   int rc;
-  if ((rc = dalloc((void **)&D.rl, sizeof(double) * (size_t)n))) return rc;
-  if ((rc = dalloc((void **)&D.ru, sizeof(double) * (size_t)n))) return rc;
-  if ((rc = dalloc((void **)&D.ptr, sizeof(long long) * ((size_t)n_boxes + 1)))) return rc;
-  if ((rc = dalloc((void **)&D.var, sizeof(int32_t) * (size_t)n_delta))) return rc;
-  if ((rc = dalloc((void **)&D.up, (size_t)n_delta))) return rc;
-  if ((rc = dalloc((void **)&D.val, sizeof(double) * (size_t)n_delta))) return rc;
+  if ((rc = scratch(ctx, 0, sizeof(double) * (size_t)n, (void **)&D.rl))) return rc;
+  if ((rc = scratch(ctx, 1, sizeof(double) * (size_t)n, (void **)&D.ru))) return rc;
+  if ((rc = scratch(ctx, 2, sizeof(long long) * ((size_t)n_boxes + 1), (void **)&D.ptr))) return rc;
+  if ((rc = scratch(ctx, 3, sizeof(int32_t) * (size_t)n_delta, (void **)&D.var))) return rc;
+  if ((rc = scratch(ctx, 4, (size_t)n_delta, (void **)&D.up))) return rc;
+  if ((rc = scratch(ctx, 5, sizeof(double) * (size_t)n_delta, (void **)&D.val))) return rc;
   static_assert(sizeof(long long) == sizeof(int64_t), "delta_ptr / mod_ptr are copied as long long");
   cudaStream_t s = ctx->stream;
   CU(cudaMemcpyAsync(D.rl, root_lb, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
@@ -1305,12 +1326,10 @@ int mntr_gpu_boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double 
   int rc = check_deltas(ctx, "boxes_from_deltas", n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
-  std::vector<void *> scratch;
   DeviceDeltas D;
-  rc = boxes_from_deltas(ctx, scratch, n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val,
+  rc = boxes_from_deltas(ctx, n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val,
                          (double2 *)boxes_dev, D);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  free_all(scratch);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(ctx, MNTR_E_CUDA, "boxes_from_deltas: %s", cudaGetErrorString(e));
   return MNTR_OK;
@@ -1360,35 +1379,26 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
   if ((rc = ensure_batch(ctx, n_boxes, true))) return rc;
   const int64_t ld = mntr_gpu_box_ld(n_boxes);
 
-  // device scratch of this call: root, deltas, mod counts / offsets / tuples
-  std::vector<void *> scratch;
-  auto dalloc = [&](void **p, size_t bytes) -> int {
-    if (cudaMalloc(p, std::max<size_t>(bytes, 16)) != cudaSuccess) {
-      (void)cudaGetLastError(); free_all(scratch);
-      return fail(ctx, MNTR_E_NOMEM, "tighten_nodes: out of device memory");
-    }
-    scratch.push_back(*p);
-    return MNTR_OK;
-  };
-  auto done = [&](int code) { free_all(scratch); return code; };
-#define CUN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_all(scratch); return fail(ctx, MNTR_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  // device scratch (grow-only, kept by the context): root, deltas, mod counts / offsets / tuples
+  auto done = [&](int code) { return code; };
+#define CUN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { return fail(ctx, MNTR_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
   cudaStream_t s = ctx->stream;
   CUN(cudaEventRecord(ctx->ev[0], s));
   DeviceDeltas D;
-  if ((rc = boxes_from_deltas(ctx, scratch, n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val,
-                              ctx->d_boxes, D))) return done(rc);
+  if ((rc = boxes_from_deltas(ctx, n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val,
+                              ctx->d_boxes, D))) return rc;
   double *d_mval = nullptr;
   long long *d_cnt = nullptr, *d_mptr = nullptr, *d_xcnt = nullptr, *d_xat = nullptr;
   int32_t *d_mvar = nullptr, *d_strip = nullptr; uint8_t *d_mup = nullptr;
   const int64_t n_strips = ((int64_t)n + 255) / 256;
-  if ((rc = dalloc((void **)&d_cnt, sizeof(long long) * (size_t)n_boxes))) return rc;
-  if ((rc = dalloc((void **)&d_xcnt, sizeof(long long) * (size_t)n_boxes))) return rc;
-  if ((rc = dalloc((void **)&d_mptr, sizeof(long long) * ((size_t)n_boxes + 1)))) return rc;
-  if ((rc = dalloc((void **)&d_xat, sizeof(long long) * (size_t)n_boxes))) return rc;
-  if ((rc = dalloc((void **)&d_strip, sizeof(int32_t) * (size_t)(n_strips * ld)))) return rc;
-  if ((rc = dalloc((void **)&d_mvar, sizeof(int32_t) * (size_t)mod_cap))) return rc;
-  if ((rc = dalloc((void **)&d_mup, (size_t)mod_cap))) return rc;
-  if ((rc = dalloc((void **)&d_mval, sizeof(double) * (size_t)mod_cap))) return rc;
+  if ((rc = scratch(ctx, 6, sizeof(long long) * (size_t)n_boxes, (void **)&d_cnt))) return rc;
+  if ((rc = scratch(ctx, 7, sizeof(long long) * (size_t)n_boxes, (void **)&d_xcnt))) return rc;
+  if ((rc = scratch(ctx, 8, sizeof(long long) * ((size_t)n_boxes + 1), (void **)&d_mptr))) return rc;
+  if ((rc = scratch(ctx, 9, sizeof(long long) * (size_t)n_boxes, (void **)&d_xat))) return rc;
+  if ((rc = scratch(ctx, 10, sizeof(int32_t) * (size_t)(n_strips * ld), (void **)&d_strip))) return rc;
+  if ((rc = scratch(ctx, 11, sizeof(int32_t) * (size_t)mod_cap, (void **)&d_mvar))) return rc;
+  if ((rc = scratch(ctx, 12, (size_t)mod_cap, (void **)&d_mup))) return rc;
+  if ((rc = scratch(ctx, 13, sizeof(double) * (size_t)mod_cap, (void **)&d_mval))) return rc;
   BatchIo io;
   io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
   io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb; io.nl_evals = ctx->d_nl_evals;

@@ -151,7 +151,8 @@ __device__ __noinline__ void drain_queue(const LinDev &P, const ReadPending &rd,
 // With a stage that does not keep rows resident (Stage::kSlab false: the streaming form of large instances) the lane
 // reads its row's entries from the CSR, four at a time with 128-bit loads (rows start at and are padded to a multiple
 // of four entries); the lines are shared by neighbouring lanes and consecutive groups through L1.
-template <class R, class Sink, class Stage>
+// G: gathers a lane keeps in flight in pass 1 (a multiple of four; kRes: the whole resident part at once)
+template <class R, int G = kPassGroup, class Sink, class Stage>
 __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending &rd, const Sink &sink, Stage &S,
                                               int lane, bool due, const RowHead h, bool first,
                                               const int32_t *gcol = nullptr, const double *gval = nullptr,
@@ -176,38 +177,42 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
   uint8_t sg = 0;
   {
     float reach[kRes];
+    static_assert(G % 4 == 0 && kRes % G == 0, "pass 1 runs in groups of G entries");
 #pragma unroll
-    for (int g = 0; g < kRes / kPassGroup; ++g) {
-      if (g * kPassGroup >= maxc) {            // warp-uniform: no row of the warp reaches this group
+    for (int g = 0; g < kRes / G; ++g) {
+      if (g * G >= maxc) {            // warp-uniform: no row of the warp reaches this group
 #pragma unroll
-        for (int u = 0; u < kPassGroup; ++u) reach[g * kPassGroup + u] = 0.f;
+        for (int u = 0; u < G; ++u) reach[g * G + u] = 0.f;
         continue;
       }
-      double2 b[kPassGroup];
-      double av[kPassGroup];
-      int cv[kPassGroup];
+      double2 b[G];
+      double av[G];
+      int cv[G];
       if constexpr (Stage::kSlab) {
 #pragma unroll
-        for (int u = 0; u < kPassGroup; ++u) {
-          const int t = g * kPassGroup + u;
+        for (int u = 0; u < G; ++u) {
+          const int t = g * G + u;
           av[u] = 0.0; cv[u] = 0;
           if (t < cnt) { av[u] = S.val[t][lane]; cv[u] = S.colx[t][lane]; }
         }
       } else {
-        static_assert(kPassGroup == 4, "one 128-bit column load and two 128-bit value loads per group");
-        int4 c = make_int4(0, 0, 0, 0);
-        double2 v0 = make_double2(0.0, 0.0), v1 = v0;
-        if (g * kPassGroup < cnt) {
-          c = *reinterpret_cast<const int4 *>(gcol + g * kPassGroup);
-          v0 = *reinterpret_cast<const double2 *>(gval + g * kPassGroup);
-          v1 = *reinterpret_cast<const double2 *>(gval + g * kPassGroup + 2);
+        // one 128-bit column load and two 128-bit value loads per four entries
+#pragma unroll
+        for (int q = 0; q < G; q += 4) {
+          int4 c = make_int4(0, 0, 0, 0);
+          double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+          if (g * G + q < cnt) {
+            c = *reinterpret_cast<const int4 *>(gcol + g * G + q);
+            v0 = *reinterpret_cast<const double2 *>(gval + g * G + q);
+            v1 = *reinterpret_cast<const double2 *>(gval + g * G + q + 2);
+          }
+          cv[q] = c.x; cv[q + 1] = c.y; cv[q + 2] = c.z; cv[q + 3] = c.w;
+          av[q] = v0.x; av[q + 1] = v0.y; av[q + 2] = v1.x; av[q + 3] = v1.y;
         }
-        cv[0] = c.x; cv[1] = c.y; cv[2] = c.z; cv[3] = c.w;
-        av[0] = v0.x; av[1] = v0.y; av[2] = v1.x; av[3] = v1.y;
       }
 #pragma unroll
-      for (int u = 0; u < kPassGroup; ++u) {
-        const int t = g * kPassGroup + u;
+      for (int u = 0; u < G; ++u) {
+        const int t = g * G + u;
         b[u] = make_double2(0.0, 0.0);
         if (t < cnt) {
           bool hinted = false;
@@ -218,8 +223,8 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
         }
       }
 #pragma unroll
-      for (int u = 0; u < kPassGroup; ++u) {
-        const int t = g * kPassGroup + u;
+      for (int u = 0; u < G; ++u) {
+        const int t = g * G + u;
         reach[t] = 0.f;
         if (t < cnt) {
           const double a = av[u];

@@ -174,7 +174,9 @@ void GpuBoundHandler::signature_(ProblemPtr p, unsigned long long &structure, un
     double lb = c->getLb(), ub = c->getUb();
     unsigned long long bl, bu;
     memcpy(&bl, &lb, 8); memcpy(&bu, &ub, 8);
-    fnv(bounds, bl); fnv(bounds, bu);
+    // the bounds of the linear rows can be refreshed alone; those of CGraph constraints travel with their tapes
+    if (c->getNonlinearFunction() || c->getQuadraticFunction()) { fnv(structure, bl); fnv(structure, bu); }
+    else { fnv(bounds, bl); fnv(bounds, bu); }
   }
   for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) fnv(structure, (unsigned long long)(*it)->getType());
 }
@@ -187,25 +189,22 @@ void GpuBoundHandler::sync_(ProblemPtr p)
   signature_(p, st, bd);
   if (st != sigStruct_) { upload_(p); return; }
   if (bd != sigBounds_) {
-    // same rows, new row bounds (a ConBoundMod, LinearHandler's row-bound tightening): refresh them alone.  The CGraph
-    // constraints' bounds live with their tapes: those re-flatten.
-    bool nlChanged = false;
+    // same rows, new bounds of LINEAR rows (a ConBoundMod, LinearHandler's row-bound tightening): refresh them alone
+    // (the bounds of CGraph constraints are part of the structure signature: they re-flatten)
     std::vector<double> rl, ru;
     for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it) {
       ConstraintPtr c = *it;
       if (DeletedCons == c->getState()) continue;
       if (c->getFunctionType() == Linear && c->getQuadraticFunction() == 0 && c->getNonlinearFunction() == 0) {
         rl.push_back(c->getLb()); ru.push_back(c->getUb());
-      } else if (c->getNonlinearFunction()) nlChanged = true;      // cannot tell which moved: be safe
+      }
     }
     int rc = MNTR_OK;
-    if (!nlChanged) {
-      const int k = group_ ? mntr_gpu_group_size(group_) : 1;
-      for (int i = 0; i < k && rc == MNTR_OK; ++i)
-        rc = mntr_gpu_update_row_bounds(group_ ? mntr_gpu_group_member(group_, i) : ctx_, (int)rl.size(),
-                                        rl.empty() ? 0 : &rl[0], ru.empty() ? 0 : &ru[0]);
-    }
-    if (nlChanged || rc != MNTR_OK) { upload_(p); return; }
+    const int k = group_ ? mntr_gpu_group_size(group_) : 1;
+    for (int i = 0; i < k && rc == MNTR_OK; ++i)
+      rc = mntr_gpu_update_row_bounds(group_ ? mntr_gpu_group_member(group_, i) : ctx_, (int)rl.size(),
+                                      rl.empty() ? 0 : &rl[0], ru.empty() ? 0 : &ru[0]);
+    if (rc != MNTR_OK) { upload_(p); return; }
     sigBounds_ = bd;
     ++stats_.rowBoundUpdates;
   }
