@@ -86,6 +86,82 @@ class Tapes:
         return int(self.tape_ptr[-1])
 
 
+@dataclass
+class QuadCons:
+    """Constraints with a QuadraticFunction:  q_lb <= sum_k coef_k x_{v1_k} x_{v2_k} + lin . x <= q_ub.  Terms are kept
+    in the order of the reference's VariablePairGroup (by (v1, v2) with v1 <= v2,
+    /root/reference/src/base/Types.cpp CompareVariablePair); NlPresHandler::chkRed_ checks them with
+    QuadraticFunction::computeBounds (QuadraticFunction.cpp:156-180)."""
+    n_quad: int
+    q_ptr: np.ndarray      # int32 [n_quad+1]
+    v1: np.ndarray         # int32
+    v2: np.ndarray         # int32
+    coef: np.ndarray       # float64
+    lin_ptr: np.ndarray    # int32 [n_quad+1]
+    lin_col: np.ndarray    # int32
+    lin_val: np.ndarray    # float64
+    q_lb: np.ndarray       # float64 [n_quad]
+    q_ub: np.ndarray       # float64 [n_quad]
+
+
+def build_quad(cons) -> QuadCons:
+    """cons: list of ([(i, j, coef) ...], [(col, coef) ...], lb, ub).  Terms are merged per variable pair and sorted the
+    way QuadraticFunction keeps them (a std::map keyed by the ordered pair; coefficients below 1e-8 are dropped,
+    QuadraticFunction.cpp addTerm)."""
+    qp, lp = [0], [0]
+    v1, v2, cf, lc, lv, lo, hi = [], [], [], [], [], [], []
+    for terms, lin, l, u in cons:
+        seen = {}
+        for i, j, c in terms:
+            key = (min(i, j), max(i, j))
+            if abs(c) >= 1e-8 and key not in seen:       # std::map::insert keeps the first weight of a pair
+                seen[key] = c
+        for key in sorted(seen):
+            v1.append(key[0]); v2.append(key[1]); cf.append(seen[key])
+        qp.append(len(v1))
+        lin = sorted(lin)
+        lc += [j for j, _ in lin]; lv += [a for _, a in lin]
+        lp.append(len(lc))
+        lo.append(l); hi.append(u)
+    return QuadCons(n_quad=len(cons), q_ptr=np.asarray(qp, np.int32), v1=np.asarray(v1 or [0], np.int32),
+                    v2=np.asarray(v2 or [0], np.int32), coef=np.asarray(cf or [0.0], np.float64),
+                    lin_ptr=np.asarray(lp, np.int32), lin_col=np.asarray(lc or [0], np.int32),
+                    lin_val=np.asarray(lv or [0.0], np.float64), q_lb=np.asarray(lo, np.float64), q_ub=np.asarray(hi, np.float64))
+
+
+def make_quad_cons(n: int, n_quad: int, xstar: np.ndarray, seed: int = 7, terms: int = 4) -> QuadCons:
+    """Random quadratic constraints around a planted point: a few bilinear / square terms with coefficients in +-{1..4},
+    one or two linear terms, bounds x*'s value plus a small slack (a third two-sided)."""
+    rng = np.random.default_rng([seed, 13])
+    cons = []
+    for _ in range(n_quad):
+        k = int(rng.integers(1, terms + 1))
+        tt = []
+        val = 0.0
+        for _ in range(k):
+            i, j = int(rng.integers(0, n)), int(rng.integers(0, n))
+            c = float(rng.integers(1, 5)) * (1.0 if rng.random() < 0.6 else -1.0)
+            tt.append((i, j, c))
+        merged = {}
+        for i, j, c in tt:
+            merged.setdefault((min(i, j), max(i, j)), c)
+        for (i, j), c in merged.items():
+            val += c * xstar[i] * xstar[j]
+        lin = []
+        for _ in range(int(rng.integers(0, 3))):
+            j = int(rng.integers(0, n)); a = float(rng.integers(1, 6)) * (1.0 if rng.random() < 0.5 else -1.0)
+            if all(j != jj for jj, _ in lin):
+                lin.append((j, a)); val += a * xstar[j]
+        w = float(rng.integers(0, 4))
+        if rng.random() < 0.33:
+            cons.append((tt, lin, val - 0.5 * w, val + 0.5 * w))
+        elif rng.random() < 0.5:
+            cons.append((tt, lin, -INF, val + w))
+        else:
+            cons.append((tt, lin, val - w, INF))
+    return build_quad(cons)
+
+
 # --------------------------------------------------------------------------------------
 # expression -> tape (mirrors the node order of CGraph::finalize)
 # --------------------------------------------------------------------------------------

@@ -757,9 +757,36 @@ int32_t orc_nl_var_bound_mods(const orc_nl_t *g, int32_t c, double lb_in, double
   return ORC_OK;
 }
 
-/* ref: NlPresHandler.cpp:101-208 chkRed_ (nlf branch), tolerance eTol_ = 1e-6 (:72) */
+/* ref: QuadraticFunction.cpp:156-180 computeBounds: per term the four corner products (coef*x1)*x2 -- evaluated left to
+ * right -- their min added to the lower, their max to the upper bound; std::min / std::max as called there */
+void orc_quad_compute_bounds(const orc_nl_t *g, int32_t q, const double *lbv, const double *ubv, double *out_lb, double *out_ub)
+{
+  double lb = 0, ub = 0;
+  for (int32_t t = g->q_ptr[q]; t < g->q_ptr[q + 1]; ++t) {
+    const double w = g->q_coef[t];
+    const double l1 = lbv[g->q_v1[t]], u1 = ubv[g->q_v1[t]], l2 = lbv[g->q_v2[t]], u2 = ubv[g->q_v2[t]];
+    const double a = w * l1 * l2, b = w * l1 * u2, c = w * u1 * l2, d = w * u1 * u2;
+    double m = (b < a) ? b : a; m = (c < m) ? c : m; m = (d < m) ? d : m;
+    lb += m;
+    m = (a < b) ? b : a; m = (m < c) ? c : m; m = (m < d) ? d : m;
+    ub += m;
+  }
+  *out_lb = lb; *out_ub = ub;
+}
+
+/* ref: NlPresHandler.cpp:101-208 chkRed_ (nlf branch, and the qf branch for QuadraticFunction constraints),
+ * tolerance eTol_ = 1e-6 (:72).  The reference walks the constraints in index order and stops at the first
+ * infeasible one: only the verdict is observable, so the two families are checked one after the other. */
 int32_t orc_nl_chk_red(const orc_nl_t *g, const double *lb, const double *ub)
 {
+  for (int32_t q = 0; q < g->n_quad; ++q) {
+    double lfl = 0, lfu = 0, ql = 0, qu = 0;
+    int32_t b = g->q_lin_ptr[q], k = g->q_lin_ptr[q + 1] - b;
+    if (k > 0) lf_bnds(k, g->q_lin_col + b, g->q_lin_val + b, lb, ub, &lfl, &lfu);
+    orc_quad_compute_bounds(g, q, lb, ub, &ql, &qu);
+    double impl_lb = ql + lfl, impl_ub = qu + lfu;
+    if (impl_ub + 1e-6 < g->q_lb[q] || impl_lb - 1e-6 > g->q_ub[q]) return ORC_INFEASIBLE;
+  }
   for (int32_t c = 0; c < g->n_cons; ++c) {
     double lfl = 0, lfu = 0, nl = 0, nu = 0;
     int32_t b = g->lin_ptr[c], k = g->lin_ptr[c + 1] - b;

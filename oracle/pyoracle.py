@@ -50,7 +50,9 @@ class OrcLin(C.Structure):
 class OrcNl(C.Structure):
     _fields_ = [("n_cons", C.c_int32), ("tape_ptr", _ip), ("op", _bp), ("arg0", _ip), ("arg1", _ip),
                 ("cnst", _dp), ("child", _ip), ("lin_ptr", _ip), ("lin_col", _ip), ("lin_val", _dp),
-                ("c_lb", _dp), ("c_ub", _dp)]
+                ("c_lb", _dp), ("c_ub", _dp),
+                ("n_quad", C.c_int32), ("q_ptr", _ip), ("q_v1", _ip), ("q_v2", _ip), ("q_coef", _dp), ("q_lin_ptr", _ip),
+                ("q_lin_col", _ip), ("q_lin_val", _dp), ("q_lb", _dp), ("q_ub", _dp)]
 
 
 class OrcResult(C.Structure):
@@ -92,15 +94,34 @@ def _lin_struct(inst, keep):
     return s
 
 
-def _nl_struct(t, keep):
+def _nl_struct(t, keep, quad=None):
+    """t: Tapes or None; quad: QuadCons or None (constraints with a QuadraticFunction, checked by chkRed_ only)."""
     s = OrcNl()
-    s.n_cons = t.n_cons
-    for name, typ in (("tape_ptr", np.int32), ("op", np.uint8), ("arg0", np.int32), ("arg1", np.int32),
-                      ("cnst", np.float64), ("child", np.int32), ("lin_ptr", np.int32), ("lin_col", np.int32),
-                      ("lin_val", np.float64), ("c_lb", np.float64), ("c_ub", np.float64)):
-        a = np.ascontiguousarray(getattr(t, name), typ)
-        keep["nl_" + name] = a
-        setattr(s, name, {np.int32: _i, np.uint8: _b, np.float64: _d}[typ](a))
+    conv = {np.int32: _i, np.uint8: _b, np.float64: _d}
+    if t is None:
+        s.n_cons = 0
+        z = np.zeros(1, np.int32); keep["nl_zero"] = z
+        s.tape_ptr = _i(z); s.lin_ptr = _i(z)
+    else:
+        s.n_cons = t.n_cons
+        for name, typ in (("tape_ptr", np.int32), ("op", np.uint8), ("arg0", np.int32), ("arg1", np.int32),
+                          ("cnst", np.float64), ("child", np.int32), ("lin_ptr", np.int32), ("lin_col", np.int32),
+                          ("lin_val", np.float64), ("c_lb", np.float64), ("c_ub", np.float64)):
+            a = np.ascontiguousarray(getattr(t, name), typ)
+            keep["nl_" + name] = a
+            setattr(s, name, conv[typ](a))
+    if quad is None:
+        quad = getattr(t, "quad", None)
+    s.n_quad = 0
+    if quad is not None and quad.n_quad > 0:
+        s.n_quad = quad.n_quad
+        for dst, src, typ in (("q_ptr", "q_ptr", np.int32), ("q_v1", "v1", np.int32), ("q_v2", "v2", np.int32),
+                              ("q_coef", "coef", np.float64), ("q_lin_ptr", "lin_ptr", np.int32),
+                              ("q_lin_col", "lin_col", np.int32), ("q_lin_val", "lin_val", np.float64),
+                              ("q_lb", "q_lb", np.float64), ("q_ub", "q_ub", np.float64)):
+            a = np.ascontiguousarray(getattr(quad, src), typ)
+            keep["q_" + dst] = a
+            setattr(s, dst, conv[typ](a))
     return s
 
 
@@ -127,6 +148,8 @@ class Oracle:
         L.orc_nl_simple_presolve_obj.argtypes = [C.POINTER(OrcNl), C.POINTER(OrcLin), _dp, _dp, C.POINTER(OrcResult)]
         L.orc_nl_chk_red.argtypes = [C.POINTER(OrcNl), _dp, _dp]
         L.orc_nl_chk_red.restype = C.c_int32
+        L.orc_quad_compute_bounds.argtypes = [C.POINTER(OrcNl), C.c_int32, _dp, _dp, _dp, _dp]
+        L.orc_quad_compute_bounds.restype = None
         L.orc_nl_sweep.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(C.c_int64)]
         L.orc_nl_sweep.restype = C.c_int32
         L.orc_node_presolve.argtypes = [C.POINTER(OrcLin), C.POINTER(OrcNl), _dp, _dp, C.POINTER(OrcResult)]
@@ -200,9 +223,22 @@ class Oracle:
         st = self.lib.orc_nl_var_bound_mods(C.byref(s), c, lb_in, ub_in, _d(lb), _d(ub), _i(nm))
         return lb, ub, st, int(nm[0])
 
-    def nl_simple_presolve(self, tapes, lb, ub, obj=None):
+    def nl_chk_red(self, tapes, lb, ub, quad=None):
+        """NlPresHandler::chkRed_ over the CGraph constraints and the QuadraticFunction constraints: 0 ok, 1 infeasible."""
+        keep = {}; s = _nl_struct(tapes, keep, quad)
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        return int(self.lib.orc_nl_chk_red(C.byref(s), _d(lb), _d(ub)))
+
+    def quad_compute_bounds(self, quad, q, lb, ub):
+        keep = {}; s = _nl_struct(None, keep, quad)
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        o = np.zeros(2)
+        self.lib.orc_quad_compute_bounds(C.byref(s), int(q), _d(lb), _d(ub), _d(o[0:1]), _d(o[1:2]))
+        return o[0], o[1]
+
+    def nl_simple_presolve(self, tapes, lb, ub, obj=None, quad=None):
         """obj: a LinearRows whose cut-off row is the (linear) objective, with an incumbent -> fixObjBins_ runs."""
-        keep = {}; s = _nl_struct(tapes, keep)
+        keep = {}; s = _nl_struct(tapes, keep, quad)
         lb = np.array(lb, np.float64, copy=True); ub = np.array(ub, np.float64, copy=True)
         r = OrcResult()
         if obj is not None:
@@ -212,10 +248,10 @@ class Oracle:
             self.lib.orc_nl_simple_presolve(C.byref(s), _d(lb), _d(ub), C.byref(r))
         return lb, ub, dict(verdict=r.verdict, rounds=r.rounds, n_mods=r.n_mods)
 
-    def node_presolve(self, inst, tapes, lb, ub):
+    def node_presolve(self, inst, tapes, lb, ub, quad=None):
         keep = {}
         s = _lin_struct(inst, keep) if inst is not None and inst.m > 0 else None
-        g = _nl_struct(tapes, keep) if tapes is not None else None
+        g = _nl_struct(tapes, keep, quad) if (tapes is not None or quad is not None) else None
         lb = np.array(lb, np.float64, copy=True); ub = np.array(ub, np.float64, copy=True)
         r = OrcResult()
         self.lib.orc_node_presolve(C.byref(s) if s is not None else None, C.byref(g) if g is not None else None,
@@ -285,11 +321,16 @@ class Reference:
             L.ref_time_deltas.restype = C.c_double
             L.ref_add_nl_batch.argtypes = [C.c_void_p, C.c_int32, _ip, _bp, _ip, _ip, _dp, _ip, _ip, _ip, _dp, _dp, _dp]
             L.ref_add_nl_batch.restype = C.c_int32
+            L.ref_add_quad.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _dp, C.c_int32, _ip, _dp, C.c_double, C.c_double]
+            L.ref_add_quad.restype = C.c_int32
+            L.ref_nl_chk_red.argtypes = [C.c_void_p]
+            L.ref_nl_chk_red.restype = C.c_int32
+            L.ref_quad_compute_bounds.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
             L.ref_destroy.argtypes = [C.c_void_p]
             cls._lib = L
         return cls._lib
 
-    def __init__(self, inst, tapes=None):
+    def __init__(self, inst, tapes=None, quad=None):
         L = self.lib()
         self.n = inst.n
         rp = np.ascontiguousarray(inst.row_ptr, np.int32); col = np.ascontiguousarray(inst.col, np.int32)
@@ -305,6 +346,16 @@ class Reference:
             g = _nl_struct(tapes, keep)
             L.ref_add_nl_batch(self.h, tapes.n_cons, g.tape_ptr, g.op, g.arg0, g.arg1, g.cnst, g.child, g.lin_ptr,
                                g.lin_col, g.lin_val, g.c_lb, g.c_ub)
+        if quad is not None:
+            for q in range(quad.n_quad):
+                b, e = int(quad.q_ptr[q]), int(quad.q_ptr[q + 1])
+                lb_, le_ = int(quad.lin_ptr[q]), int(quad.lin_ptr[q + 1])
+                a1 = np.ascontiguousarray(quad.v1[b:e], np.int32); a2 = np.ascontiguousarray(quad.v2[b:e], np.int32)
+                cf = np.ascontiguousarray(quad.coef[b:e], np.float64)
+                lc = np.ascontiguousarray(quad.lin_col[lb_:le_] if le_ > lb_ else np.zeros(1, np.int32), np.int32)
+                lv = np.ascontiguousarray(quad.lin_val[lb_:le_] if le_ > lb_ else np.zeros(1), np.float64)
+                L.ref_add_quad(self.h, e - b, _i(a1), _i(a2), _d(cf), le_ - lb_, _i(lc), _d(lv), float(quad.q_lb[q]),
+                               float(quad.q_ub[q]))
         if inst.cut_col is not None and len(inst.cut_col):
             # the cut-off row c.x <= cut_rhs as the reference meets it: a linear objective c.x + obj_const and an
             # incumbent of value cut_rhs + obj_const in the solution pool (LinearHandler.cpp:1636-1640)
@@ -380,6 +431,17 @@ class Reference:
         st = self.lib().ref_nl_var_bound_mods(self.h, c, lb_in, ub_in, _i(nm))
         l, u = self.get_box()
         return l, u, int(st), int(nm[0])
+
+    def nl_chk_red(self, lb, ub):
+        """NlPresHandler::chkRed_ alone on the box: 1 = infeasible."""
+        self.set_box(lb, ub)
+        return int(self.lib().ref_nl_chk_red(self.h))
+
+    def quad_compute_bounds(self, q, lb, ub):
+        self.set_box(lb, ub)
+        o = np.zeros(2)
+        self.lib().ref_quad_compute_bounds(self.h, int(q), _d(o[0:1]), _d(o[1:2]))
+        return o[0], o[1]
 
     def nl_dq_ops(self, c):
         ops = np.zeros(4096, np.int32)

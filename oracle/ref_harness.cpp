@@ -12,6 +12,14 @@
  */
 #include "MinotaurConfig.h"
 
+// NlPresHandler::chkRed_ is private (NlPresHandler.h:226); the harness calls it directly to pin the oracle's
+// QuadraticFunction check in isolation (the handler's public simplePresolve also runs the qf branch of varBndsFromCons_,
+// which writes to the ORIGINAL problem -- a reference defect).  The objects were compiled from the
+// untouched headers: access specifiers do not change the layout.
+#define private public
+#include "NlPresHandler.h"
+#undef private
+
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -32,6 +40,7 @@
 #include "Objective.h"
 #include "Option.h"
 #include "Problem.h"
+#include "QuadraticFunction.h"
 #include "Reader.h"
 #include "SolutionPool.h"
 #include "Types.h"
@@ -146,6 +155,7 @@ struct RefProblem {
   std::vector<VariablePtr> vars;
   std::vector<ConstraintPtr> lin_rows;
   std::vector<ConstraintPtr> nl_rows;
+  std::vector<ConstraintPtr> quad_rows;
   std::vector<CGraph *> graphs;
 };
 
@@ -215,6 +225,39 @@ int32_t ref_add_nl(void *hv, int32_t n_nodes, const uint8_t *op, const int32_t *
   h->nl_rows.push_back(h->p->newConstraint(f, c_lb, c_ub));
   h->graphs.push_back(cg);
   return (int32_t)h->nl_rows.size() - 1;
+}
+
+/* one constraint  lb <= sum_k coef_k x_{v1_k} x_{v2_k} + lin.x <= ub  with a QuadraticFunction */
+int32_t ref_add_quad(void *hv, int32_t k, const int32_t *v1, const int32_t *v2, const double *coef, int32_t lin_k,
+                     const int32_t *lin_col, const double *lin_val, double lb, double ub)
+{
+  RefProblem *h = (RefProblem *)hv;
+  QuadraticFunctionPtr qf = (QuadraticFunctionPtr) new QuadraticFunction();
+  for (int32_t t = 0; t < k; ++t) qf->addTerm(h->vars[v1[t]], h->vars[v2[t]], coef[t]);
+  LinearFunctionPtr lf = 0;
+  if (lin_k > 0) {
+    lf = (LinearFunctionPtr) new LinearFunction();
+    for (int32_t t = 0; t < lin_k; ++t) lf->addTerm(h->vars[lin_col[t]], lin_val[t]);
+  }
+  FunctionPtr f = (FunctionPtr) new Function(lf, qf, (NonlinearFunctionPtr)0);
+  h->quad_rows.push_back(h->p->newConstraint(f, lb, ub));
+  return (int32_t)h->quad_rows.size() - 1;
+}
+
+/* NlPresHandler::chkRed_ alone (NlPresHandler.cpp:101-208) on the current box: 1 = infeasible */
+int32_t ref_nl_chk_red(void *hv)
+{
+  RefProblem *h = (RefProblem *)hv;
+  bool changed = false; ModQ mods; SolveStatus st = Started;
+  h->nh->chkRed_(h->p, false, &changed, &mods, st);
+  return st == SolvedInfeasible ? 1 : 0;
+}
+
+/* QuadraticFunction::computeBounds of quadratic constraint q on the current box */
+void ref_quad_compute_bounds(void *hv, int32_t q, double *lb, double *ub)
+{
+  RefProblem *h = (RefProblem *)hv;
+  h->quad_rows[q]->getFunction()->getQuadraticFunction()->computeBounds(lb, ub);
 }
 
 /* linear objective  min c.x + constant  (the cut-off row of LinearHandler::varBndsFromObj_) */

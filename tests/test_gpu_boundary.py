@@ -8,6 +8,11 @@ import sys
 import numpy as np
 import pytest
 
+try:            # before anything loads an NCCL: PyTorch must find ITS bundled libnccl.so.2 first (the engine then reuses it)
+    import torch  # noqa: F401
+except Exception:   # pragma: no cover
+    torch = None
+
 from minotaur_b200 import engine as E
 from minotaur_b200.instances import (branch_deltas, deltas_box, make_knapsack_setcover, make_minlp_large, make_sparse_milp,
                                      slice_deltas)
@@ -25,7 +30,6 @@ def _apply(lb, ub, mv, mu, mx):
 
 
 def test_boxes_from_deltas_matches_dense_upload(engine):
-    import torch
     inst = make_knapsack_setcover(3000, 2500, 8, seed=5)
     engine.load_linear(inst)
     nb = 77
