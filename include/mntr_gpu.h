@@ -163,6 +163,18 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
                          const int32_t *lin_col, const double *lin_val, const double *c_lb,
                          const double *c_ub);
 
+/* Constraints whose nonlinear part is a QuadraticFunction:  q_lb <= sum_k coef_k x_{v1_k} x_{v2_k} + lin.x <= q_ub.
+ * Terms of a constraint in the order of the reference's VariablePairGroup (ascending (v1, v2), v1 <= v2;
+ * Types.cpp CompareVariablePair); terms with |coef| < 1e-8 are dropped as QuadraticFunction::addTerm drops them.
+ * NlPresHandler only CHECKS these constraints: chkRed_ (NlPresHandler.cpp:101-208) with
+ * QuadraticFunction::computeBounds (QuadraticFunction.cpp:156-180) -- an infeasible one gives verdict MNTR_INFEAS_NL;
+ * no bound is derived from them (the qf branch of NlPresHandler::varBndsFromCons_ is a reference defect, SURVEY.md 8a
+ * N5).  Requires a previous mntr_gpu_load_linear; n_quad = 0 removes them.  Flattens: QuadraticFunction. */
+int mntr_gpu_load_quad(mntr_gpu_ctx *ctx, int32_t n_quad, const int32_t *q_ptr, const int32_t *v1,
+                       const int32_t *v2, const double *coef, const int32_t *lin_ptr,
+                       const int32_t *lin_col, const double *lin_val, const double *q_lb,
+                       const double *q_ub);
+
 /* New bounds for the linear rows already on the device (same rows, same order as the mntr_gpu_load_linear call):
  * what a ConBoundMod or LinearHandler's row-bound tightening changes.  m doubles each way instead of re-flattening the
  * whole problem.  Replaces: Constraint::lb_/ub_ being read live by linBndTighten_ (LinearHandler.cpp:952-1045). */
@@ -249,6 +261,26 @@ int mntr_gpu_boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double 
 void *mntr_gpu_alloc_host(mntr_gpu_ctx *ctx, int64_t bytes);
 void mntr_gpu_free_host(mntr_gpu_ctx *ctx, void *p);
 
+/* ---- root presolve: row operations of LinearHandler::presolve over the rows on the device ------------------ */
+
+/* Duplicate-row CANDIDATES as LinearHandler::dupRows_ finds them (LinearHandler.cpp:882-949): every loaded row is
+ * hashed with the two random vectors r1, r2 [n] (the caller draws them the way the reference does: rand()/RAND_MAX*10),
+ * all pairs i < j are compared, and the pairs that pass the reference's tests are returned sorted by (i, j):
+ * kind 1 = |h1j - h1i| < 1e-10 or |h1j + h1i| < 1e-10 (treatDupRows_ with mult 1.0), kind 2 = |h1i/h1j - h2i/h2j| <
+ * 1e-10 (mult h1i / h1j).  Row indices are the caller's (the order of mntr_gpu_load_linear).  h1_out / h2_out [m]
+ * receive the hashes (may be NULL).  The O(m^2) compare runs on the GPU; merging / deleting rows (treatDupRows_,
+ * :1322-1395) mutates Minotaur's object graph and stays with the caller, who walks the list in order and skips pairs
+ * whose row was deleted by an earlier pair -- exactly the reference's loop.  *n_pairs_out may exceed cap. */
+int mntr_gpu_root_dup_rows(mntr_gpu_ctx *ctx, const double *r1, const double *r2, double *h1_out,
+                           double *h2_out, int64_t cap, int32_t *pair_i, int32_t *pair_j,
+                           uint8_t *pair_kind, int64_t *n_pairs_out);
+
+/* Rows that are redundant on the box (lb, ub): the activity range of getLfBnds_ lies inside the row bounds,
+ * ll >= row_lb - 1e-8 && uu <= row_ub + 1e-8 -- the test of linBndTighten_ in root mode (LinearHandler.cpp:974-985).
+ * redundant [m] (caller's row order) receives 0 / 1.  Round-to-nearest, the reference's operation order: bit-exact. */
+int mntr_gpu_root_redundant_rows(mntr_gpu_ctx *ctx, const double *lb, const double *ub, uint8_t *redundant,
+                                 int64_t *n_redundant);
+
 /* statistics of the last tighten call */
 int mntr_gpu_get_stats(const mntr_gpu_ctx *ctx, mntr_gpu_stats *out);
 
@@ -289,6 +321,10 @@ int mntr_gpu_group_load_cgraph(mntr_gpu_group *g, int32_t n_cons, const int32_t 
                                const int32_t *arg0, const int32_t *arg1, const double *cnst,
                                const int32_t *child, const int32_t *lin_ptr, const int32_t *lin_col,
                                const double *lin_val, const double *c_lb, const double *c_ub);
+int mntr_gpu_group_load_quad(mntr_gpu_group *g, int32_t n_quad, const int32_t *q_ptr, const int32_t *v1,
+                             const int32_t *v2, const double *coef, const int32_t *lin_ptr,
+                             const int32_t *lin_col, const double *lin_val, const double *q_lb,
+                             const double *q_ub);
 int mntr_gpu_group_set_cutoff(mntr_gpu_group *g, int32_t k, const int32_t *col, const double *val, double rhs);
 int mntr_gpu_group_set_incumbent(mntr_gpu_group *g, double best_value);
 int mntr_gpu_group_tighten_nodes(mntr_gpu_group *g, int32_t n_boxes, const double *root_lb,

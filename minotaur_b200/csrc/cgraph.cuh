@@ -580,6 +580,41 @@ __device__ __forceinline__ int nl_chk_red(const ConsView &V, const double2 *bx, 
   return 0;
 }
 
+// NlPresHandler::chkRed_ for one QuadraticFunction constraint (NlPresHandler.cpp:127-150): QuadraticFunction::computeBounds
+// (QuadraticFunction.cpp:156-180) -- per term the four corner products (coef * x1) * x2, evaluated left to right, their min
+// added to the lower and their max to the upper bound -- plus the linear part.  With RoundNearest these are the
+// reference's operations in the reference's order; with RoundDirected every corner is an interval product, so the lower
+// bound only errs downward and the upper bound only upward.  returns 0 ok, 3 infeasible
+template <class R>
+__device__ __forceinline__ int quad_chk_red(const NlDev &N, int q, const double2 *bx, int64_t ld)
+{
+  double lb = 0.0, ub = 0.0;
+  const int tb = __ldg(N.q_ptr + q), te = __ldg(N.q_ptr + q + 1);
+  for (int t = tb; t < te; ++t) {
+    const double w = __ldg(N.q_coef + t);
+    const double2 b1 = bx[(int64_t)__ldg(N.q_v1 + t) * ld], b2 = bx[(int64_t)__ldg(N.q_v2 + t) * ld];
+    // (w * x1) as an interval per end point of x1, then times the end points of x2
+    const double wl_lo = R::mul_lo(w, b1.x), wl_hi = R::mul_hi(w, b1.x), wu_lo = R::mul_lo(w, b1.y), wu_hi = R::mul_hi(w, b1.y);
+    const double a_lo = std_min(R::mul_lo(wl_lo, b2.x), R::mul_lo(wl_hi, b2.x)), a_hi = std_max(R::mul_hi(wl_lo, b2.x), R::mul_hi(wl_hi, b2.x));
+    const double b_lo = std_min(R::mul_lo(wl_lo, b2.y), R::mul_lo(wl_hi, b2.y)), b_hi = std_max(R::mul_hi(wl_lo, b2.y), R::mul_hi(wl_hi, b2.y));
+    const double c_lo = std_min(R::mul_lo(wu_lo, b2.x), R::mul_lo(wu_hi, b2.x)), c_hi = std_max(R::mul_hi(wu_lo, b2.x), R::mul_hi(wu_hi, b2.x));
+    const double d_lo = std_min(R::mul_lo(wu_lo, b2.y), R::mul_lo(wu_hi, b2.y)), d_hi = std_max(R::mul_hi(wu_lo, b2.y), R::mul_hi(wu_hi, b2.y));
+    double m = std_min(a_lo, b_lo); m = std_min(m, c_lo); m = std_min(m, d_lo);
+    lb = R::add_lo(lb, m);
+    m = std_max(a_hi, b_hi); m = std_max(m, c_hi); m = std_max(m, d_hi);
+    ub = R::add_hi(ub, m);
+  }
+  double lfl = 0.0, lfu = 0.0;
+  for (int k = __ldg(N.q_lin_ptr + q); k < __ldg(N.q_lin_ptr + q + 1); ++k) {      // LinearFunction::computeBounds
+    const double a = __ldg(N.q_lin_val + k);
+    const double2 b = bx[(int64_t)__ldg(N.q_lin_col + k) * ld];
+    if (a > 0) { lfl = R::add_lo(lfl, R::mul_lo(a, b.x)); lfu = R::add_hi(lfu, R::mul_hi(a, b.y)); }
+    else       { lfl = R::add_lo(lfl, R::mul_lo(a, b.y)); lfu = R::add_hi(lfu, R::mul_hi(a, b.x)); }
+  }
+  const double impl_lb = R::add_lo(lb, lfl), impl_ub = R::add_hi(ub, lfu);
+  return (impl_ub + 1e-6 < __ldg(N.q_lb + q) || impl_lb - 1e-6 > __ldg(N.q_ub + q)) ? 3 : 0;
+}
+
 // NlPresHandler::varBndsFromCons_ for one constraint (NlPresHandler.cpp:1771-1803) = lf bounds +
 // CGraph::varBoundMods + in-place application of the mods.  returns 0 ok, 3 infeasible, 4 error;
 // n_mods receives the number of bound changes.

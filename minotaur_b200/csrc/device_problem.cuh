@@ -52,6 +52,15 @@ struct NlDev {
   int32_t max_nodes;        // longest tape
   int32_t n_levels;
   const int32_t *level_ptr; // [n_levels+1] ranges of STORED constraints (stored in level order)
+  // constraints with a QuadraticFunction  q_lb <= sum_k coef_k x_{v1_k} x_{v2_k} + lin.x <= q_ub: only checked
+  // (NlPresHandler::chkRed_ with QuadraticFunction::computeBounds, QuadraticFunction.cpp:156-180)
+  int32_t n_quad;
+  const int32_t *q_ptr;     // [n_quad+1]
+  const int32_t *q_v1, *q_v2;
+  const double  *q_coef;
+  const int32_t *q_lin_ptr, *q_lin_col;
+  const double  *q_lin_val;
+  const double  *q_lb, *q_ub;
 };
 
 // workspace of the single-box Jacobi fixpoint kernel (linear_single.cu).  Everything is double-buffered by round

@@ -85,4 +85,12 @@ cudaError_t launch_emit_mods(const double2 *boxes, const double *root_lb, const 
                              const long long *extra_at, long long cap, int32_t *mod_var, uint8_t *mod_is_upper, double *mod_val,
                              cudaStream_t stream);
 
+// root-presolve row operations (root_rows.cu): duplicate-row candidates and redundant rows of LinearHandler::presolve
+cudaError_t launch_row_hash(const LinDev &P, const int32_t *perm, const double *r1, const double *r2, double *h1, double *h2,
+                            cudaStream_t stream);
+cudaError_t launch_dup_pairs(int m, const double *h1, const double *h2, long long cap, int32_t *pair_i, int32_t *pair_j,
+                             uint8_t *pair_kind, unsigned long long *count, cudaStream_t stream);
+cudaError_t launch_redundant_rows(const LinDev &P, const int32_t *perm, const double *lb, const double *ub, uint8_t *flag,
+                                  unsigned long long *count, cudaStream_t stream);
+
 }  // namespace mntr

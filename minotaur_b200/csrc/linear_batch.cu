@@ -807,6 +807,18 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
         c0 += B.n;
       }
     }
+    // ... and every QuadraticFunction constraint (the qf branch of chkRed_; these are only ever checked)
+    if (N.n_quad > 0) {
+      const int per = (N.n_quad + team.n_warps - 1) / team.n_warps;
+      const int q_lo = min(N.n_quad, warp * per), q_hi = min(N.n_quad, q_lo + per);
+      for (int q = q_lo; q < q_hi; ++q) {
+        if (run && sh.verdict[lane] == 0) {
+          const int st = quad_chk_red<R>(N, q, bx, ld);
+          ++my_evals;
+          if (st != 0) sh.verdict[lane] = st;
+        }
+      }
+    }
     team.sync();
     // varBndsFromCons_: constraints of one level touch disjoint variables
     for (int lev = 0; lev < N.n_levels; ++lev) {

@@ -63,9 +63,10 @@ struct mntr_gpu_ctx {
   std::vector<void *> lin_allocs, cut_allocs;
 
   // ---- cgraph tapes ----
-  bool nl_loaded = false;
+  bool nl_loaded = false;            // tapes and / or QuadraticFunction constraints are on the device
+  bool tapes_loaded = false, quad_loaded = false;
   NlDev nl{};
-  std::vector<void *> nl_allocs;
+  std::vector<void *> nl_allocs, quad_allocs;
 
   // ---- single-box workspace ----
   SingleWs sws{};
@@ -364,7 +365,7 @@ void mntr_gpu_destroy(mntr_gpu_ctx *ctx)
   ctx->round_ev.clear();
   p2p_teardown(ctx);
   if (ctx->h_single) { cudaFreeHost(ctx->h_single); ctx->h_single = nullptr; }
-  free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->nl_allocs); free_all(ctx->single_allocs);
+  free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->nl_allocs); free_all(ctx->quad_allocs); free_all(ctx->single_allocs);
   free_batch(ctx); free_stage(ctx); free_scratch(ctx);
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -390,7 +391,9 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if (row_ptr[0] != 0) return fail(ctx, MNTR_E_ARG, "load_linear: row_ptr[0] != 0");
   CU(cudaSetDevice(ctx->device));
   free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->single_allocs); free_batch(ctx); free_stage(ctx);
-  free_all(ctx->nl_allocs); ctx->nl_loaded = false;
+  free_all(ctx->nl_allocs); free_all(ctx->quad_allocs);
+  ctx->nl_loaded = ctx->tapes_loaded = ctx->quad_loaded = false;
+  ctx->nl = NlDev{};
   ctx->lin_loaded = false;
 
   // ---- host flattening: drop |a| <= 1e-9 (LinearFunction.cpp:89-95) ----
@@ -566,7 +569,17 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
   if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "load_cgraph: call load_linear first (m may be 0)");
   CU(cudaSetDevice(ctx->device));
   free_all(ctx->nl_allocs);
-  ctx->nl_loaded = false;
+  const NlDev keep_quad = ctx->nl;        // the QuadraticFunction constraints are loaded separately and stay
+  auto restore_quad = [&](NlDev &N) {
+    N.n_quad = ctx->quad_loaded ? keep_quad.n_quad : 0;
+    N.q_ptr = keep_quad.q_ptr; N.q_v1 = keep_quad.q_v1; N.q_v2 = keep_quad.q_v2; N.q_coef = keep_quad.q_coef;
+    N.q_lin_ptr = keep_quad.q_lin_ptr; N.q_lin_col = keep_quad.q_lin_col; N.q_lin_val = keep_quad.q_lin_val;
+    N.q_lb = keep_quad.q_lb; N.q_ub = keep_quad.q_ub;
+  };
+  ctx->tapes_loaded = false;
+  ctx->nl = NlDev{};
+  restore_quad(ctx->nl);
+  ctx->nl_loaded = ctx->quad_loaded;
   if (n_cons == 0) return MNTR_OK;
   if (n_cons < 0 || !tape_ptr || !op || !arg0 || !arg1 || !cnst || !lin_ptr || !c_lb || !c_ub)
     return fail(ctx, MNTR_E_ARG, "load_cgraph: null or negative argument");
@@ -641,6 +654,7 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
 
   NlDev &N = ctx->nl;
   N = NlDev{};
+  restore_quad(N);
   N.n_cons = n_cons; N.max_nodes = max_nodes; N.n_levels = n_levels;
   int rc;
   if ((rc = dev_upload(ctx, ctx->nl_allocs, tp.data(), tp.size(), &N.tape_ptr))) return rc;
@@ -656,6 +670,58 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
   if ((rc = dev_upload(ctx, ctx->nl_allocs, cub.data(), cub.size(), &N.c_ub))) return rc;
   if ((rc = dev_upload(ctx, ctx->nl_allocs, lptr.data(), (size_t)n_levels + 1, &N.level_ptr))) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->tapes_loaded = true;
+  ctx->nl_loaded = true;
+  return MNTR_OK;
+}
+
+int mntr_gpu_load_quad(mntr_gpu_ctx *ctx, int32_t n_quad, const int32_t *q_ptr, const int32_t *v1, const int32_t *v2,
+                       const double *coef, const int32_t *lin_ptr, const int32_t *lin_col, const double *lin_val,
+                       const double *q_lb, const double *q_ub)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "load_quad: call load_linear first (m may be 0)");
+  CU(cudaSetDevice(ctx->device));
+  free_all(ctx->quad_allocs);
+  ctx->quad_loaded = false;
+  ctx->nl.n_quad = 0;
+  ctx->nl_loaded = ctx->tapes_loaded;
+  if (n_quad == 0) return MNTR_OK;
+  if (n_quad < 0 || !q_ptr || !v1 || !v2 || !coef || !lin_ptr || !q_lb || !q_ub || q_ptr[0] != 0 || lin_ptr[0] != 0)
+    return fail(ctx, MNTR_E_ARG, "load_quad: null or negative argument");
+  const int32_t n = ctx->n;
+  std::vector<int32_t> qp(1, 0), a1, a2;
+  std::vector<double> cf;
+  for (int32_t q = 0; q < n_quad; ++q) {
+    if (q_ptr[q + 1] < q_ptr[q] || lin_ptr[q + 1] < lin_ptr[q]) return fail(ctx, MNTR_E_ARG, "load_quad: offsets not monotone at constraint %d", q);
+    long long prev = -1;
+    for (int32_t t = q_ptr[q]; t < q_ptr[q + 1]; ++t) {
+      if (v1[t] < 0 || v2[t] >= n || v1[t] > v2[t]) return fail(ctx, MNTR_E_ARG, "load_quad: bad variable pair in constraint %d (need 0 <= v1 <= v2 < n)", q);
+      const long long key = (long long)v1[t] * n + v2[t];
+      if (key <= prev) return fail(ctx, MNTR_E_ARG, "load_quad: pairs not strictly ascending in constraint %d", q);
+      prev = key;
+      if (!(std::fabs(coef[t]) >= 1e-8)) continue;            // QuadraticFunction::addTerm, etol_
+      a1.push_back(v1[t]); a2.push_back(v2[t]); cf.push_back(coef[t]);
+    }
+    qp.push_back((int32_t)a1.size());
+    for (int32_t k = lin_ptr[q]; k < lin_ptr[q + 1]; ++k)
+      if (!lin_col || !lin_val || lin_col[k] < 0 || lin_col[k] >= n) return fail(ctx, MNTR_E_ARG, "load_quad: bad linear term in constraint %d", q);
+  }
+  NlDev &N = ctx->nl;
+  int rc;
+  const int32_t n_lin = lin_ptr[n_quad];
+  if ((rc = dev_upload(ctx, ctx->quad_allocs, qp.data(), qp.size(), &N.q_ptr))) return rc;
+  if ((rc = dev_upload(ctx, ctx->quad_allocs, a1.data(), a1.size(), &N.q_v1))) return rc;
+  if ((rc = dev_upload(ctx, ctx->quad_allocs, a2.data(), a2.size(), &N.q_v2))) return rc;
+  if ((rc = dev_upload(ctx, ctx->quad_allocs, cf.data(), cf.size(), &N.q_coef))) return rc;
+  if ((rc = dev_upload(ctx, ctx->quad_allocs, lin_ptr, (size_t)n_quad + 1, &N.q_lin_ptr))) return rc;
+  if ((rc = dev_upload(ctx, ctx->quad_allocs, lin_col, (size_t)n_lin, &N.q_lin_col))) return rc;
+  if ((rc = dev_upload(ctx, ctx->quad_allocs, lin_val, (size_t)n_lin, &N.q_lin_val))) return rc;
+  if ((rc = dev_upload(ctx, ctx->quad_allocs, q_lb, (size_t)n_quad, &N.q_lb))) return rc;
+  if ((rc = dev_upload(ctx, ctx->quad_allocs, q_ub, (size_t)n_quad, &N.q_ub))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  N.n_quad = n_quad;
+  ctx->quad_loaded = true;
   ctx->nl_loaded = true;
   return MNTR_OK;
 }
@@ -1332,6 +1398,102 @@ int mntr_gpu_boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double 
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(ctx, MNTR_E_CUDA, "boxes_from_deltas: %s", cudaGetErrorString(e));
+  return MNTR_OK;
+}
+
+// ---- root presolve row operations ----
+static int upload_perm(mntr_gpu_ctx *ctx, int32_t **d_perm)
+{
+  int rc = scratch(ctx, 14, sizeof(int32_t) * (size_t)std::max(ctx->m, 1), (void **)d_perm);
+  if (rc) return rc;
+  if (ctx->m > 0) CU(cudaMemcpyAsync(*d_perm, ctx->h_perm.data(), sizeof(int32_t) * (size_t)ctx->m, cudaMemcpyHostToDevice, ctx->stream));
+  return MNTR_OK;
+}
+
+int mntr_gpu_root_dup_rows(mntr_gpu_ctx *ctx, const double *r1, const double *r2, double *h1_out, double *h2_out,
+                           int64_t cap, int32_t *pair_i, int32_t *pair_j, uint8_t *pair_kind, int64_t *n_pairs_out)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "root_dup_rows: no problem loaded");
+  if (!r1 || !r2 || cap < 0 || !n_pairs_out || (cap > 0 && (!pair_i || !pair_j || !pair_kind)))
+    return fail(ctx, MNTR_E_ARG, "root_dup_rows: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  const int32_t m = ctx->m, n = ctx->n;
+  *n_pairs_out = 0;
+  if (m <= 0) return MNTR_OK;
+  int rc;
+  int32_t *d_perm = nullptr, *d_pi = nullptr, *d_pj = nullptr; uint8_t *d_pk = nullptr;
+  double *d_r1 = nullptr, *d_r2 = nullptr, *d_h1 = nullptr, *d_h2 = nullptr;
+  unsigned long long *d_cnt = nullptr;
+  if ((rc = upload_perm(ctx, &d_perm))) return rc;
+  if ((rc = scratch(ctx, 0, sizeof(double) * (size_t)n, (void **)&d_r1))) return rc;
+  if ((rc = scratch(ctx, 1, sizeof(double) * (size_t)n, (void **)&d_r2))) return rc;
+  if ((rc = scratch(ctx, 5, sizeof(double) * (size_t)m, (void **)&d_h1))) return rc;
+  if ((rc = scratch(ctx, 13, sizeof(double) * (size_t)m, (void **)&d_h2))) return rc;
+  if ((rc = scratch(ctx, 3, sizeof(int32_t) * (size_t)cap, (void **)&d_pi))) return rc;
+  if ((rc = scratch(ctx, 11, sizeof(int32_t) * (size_t)cap, (void **)&d_pj))) return rc;
+  if ((rc = scratch(ctx, 12, (size_t)cap, (void **)&d_pk))) return rc;
+  if ((rc = scratch(ctx, 6, sizeof(unsigned long long), (void **)&d_cnt))) return rc;
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(d_r1, r1, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_r2, r2, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+  CU(cudaEventRecord(ctx->ev[1], s));
+  CU(launch_row_hash(ctx->lin, d_perm, d_r1, d_r2, d_h1, d_h2, s));
+  CU(launch_dup_pairs(m, d_h1, d_h2, (long long)cap, d_pi, d_pj, d_pk, d_cnt, s));
+  CU(cudaEventRecord(ctx->ev[2], s));
+  unsigned long long cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  if (h1_out) CU(cudaMemcpyAsync(h1_out, d_h1, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, s));
+  if (h2_out) CU(cudaMemcpyAsync(h2_out, d_h2, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  *n_pairs_out = (int64_t)cnt;
+  const size_t k = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)cap);
+  if (k > 0) {
+    std::vector<int32_t> pi(k), pj(k); std::vector<uint8_t> pk(k);
+    CU(cudaMemcpy(pi.data(), d_pi, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(pj.data(), d_pj, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(pk.data(), d_pk, k, cudaMemcpyDeviceToHost));
+    std::vector<size_t> idx(k);
+    for (size_t q = 0; q < k; ++q) idx[q] = q;
+    std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return pi[a] != pi[b] ? pi[a] < pi[b] : pj[a] < pj[b]; });
+    for (size_t q = 0; q < k; ++q) { pair_i[q] = pi[idx[q]]; pair_j[q] = pj[idx[q]]; pair_kind[q] = pk[idx[q]]; }
+  }
+  ctx->stats = mntr_gpu_stats{};
+  ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  return MNTR_OK;
+}
+
+int mntr_gpu_root_redundant_rows(mntr_gpu_ctx *ctx, const double *lb, const double *ub, uint8_t *redundant, int64_t *n_redundant)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "root_redundant_rows: no problem loaded");
+  if (!lb || !ub || (ctx->m > 0 && !redundant)) return fail(ctx, MNTR_E_ARG, "root_redundant_rows: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  const int32_t m = ctx->m, n = ctx->n;
+  if (n_redundant) *n_redundant = 0;
+  if (m <= 0) return MNTR_OK;
+  int rc;
+  int32_t *d_perm = nullptr; double *d_lb = nullptr, *d_ub = nullptr; uint8_t *d_flag = nullptr; unsigned long long *d_cnt = nullptr;
+  if ((rc = upload_perm(ctx, &d_perm))) return rc;
+  if ((rc = scratch(ctx, 0, sizeof(double) * (size_t)n, (void **)&d_lb))) return rc;
+  if ((rc = scratch(ctx, 1, sizeof(double) * (size_t)n, (void **)&d_ub))) return rc;
+  if ((rc = scratch(ctx, 12, (size_t)m, (void **)&d_flag))) return rc;
+  if ((rc = scratch(ctx, 6, sizeof(unsigned long long), (void **)&d_cnt))) return rc;
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(d_lb, lb, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_ub, ub, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+  CU(cudaEventRecord(ctx->ev[1], s));
+  CU(launch_redundant_rows(ctx->lin, d_perm, d_lb, d_ub, d_flag, d_cnt, s));
+  CU(cudaEventRecord(ctx->ev[2], s));
+  unsigned long long cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(redundant, d_flag, (size_t)m, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (n_redundant) *n_redundant = (int64_t)cnt;
+  ctx->stats = mntr_gpu_stats{};
+  ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
   return MNTR_OK;
 }
 

@@ -102,6 +102,15 @@ int mntr_gpu_group_load_cgraph(mntr_gpu_group *g, int32_t n_cons, const int32_t 
                                 c_lb, c_ub); });
 }
 
+int mntr_gpu_group_load_quad(mntr_gpu_group *g, int32_t n_quad, const int32_t *q_ptr, const int32_t *v1, const int32_t *v2,
+                             const double *coef, const int32_t *lin_ptr, const int32_t *lin_col, const double *lin_val,
+                             const double *q_lb, const double *q_ub)
+{
+  if (!g) return MNTR_E_ARG;
+  return for_each_member(g, "group_load_quad", [&](int i) {
+    return mntr_gpu_load_quad(g->members[(size_t)i], n_quad, q_ptr, v1, v2, coef, lin_ptr, lin_col, lin_val, q_lb, q_ub); });
+}
+
 int mntr_gpu_group_set_cutoff(mntr_gpu_group *g, int32_t k, const int32_t *col, const double *val, double rhs)
 {
   if (!g) return MNTR_E_ARG;

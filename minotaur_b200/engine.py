@@ -45,6 +45,7 @@ ABI_SYMBOLS = [
     "mntr_gpu_tighten_single_dev", "mntr_gpu_stream",
     "mntr_gpu_nccl_unique_id", "mntr_gpu_comm_init", "mntr_gpu_comm_destroy",
     "mntr_gpu_boxes_from_deltas", "mntr_gpu_alloc_host", "mntr_gpu_free_host", "mntr_gpu_update_row_bounds",
+    "mntr_gpu_load_quad", "mntr_gpu_group_load_quad", "mntr_gpu_root_dup_rows", "mntr_gpu_root_redundant_rows",
     "mntr_gpu_group_create", "mntr_gpu_group_destroy", "mntr_gpu_group_size", "mntr_gpu_group_member",
     "mntr_gpu_group_last_error", "mntr_gpu_group_load_linear", "mntr_gpu_group_load_cgraph",
     "mntr_gpu_group_set_cutoff", "mntr_gpu_group_set_incumbent", "mntr_gpu_group_tighten_nodes",
@@ -106,6 +107,10 @@ def load_library() -> C.CDLL:
     L.mntr_gpu_comm_destroy.argtypes = [vp]
     L.mntr_gpu_boxes_from_deltas.argtypes = [vp, C.c_int32, _dp, _dp, _lp, _ip, _bp, _dp, vp]
     L.mntr_gpu_update_row_bounds.argtypes = [vp, C.c_int32, _dp, _dp]
+    L.mntr_gpu_load_quad.argtypes = [vp, C.c_int32, _ip, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp]
+    L.mntr_gpu_root_dup_rows.argtypes = [vp, _dp, _dp, _dp, _dp, C.c_int64, _ip, _ip, _bp, _lp]
+    L.mntr_gpu_root_redundant_rows.argtypes = [vp, _dp, _dp, _bp, _lp]
+    L.mntr_gpu_group_load_quad.argtypes = [vp, C.c_int32, _ip, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp]
     L.mntr_gpu_alloc_host.argtypes = [vp, C.c_int64]
     L.mntr_gpu_alloc_host.restype = vp
     L.mntr_gpu_free_host.argtypes = [vp, vp]
@@ -233,6 +238,41 @@ class GpuBoundEngine:
                                                 _i(a["arg1"]), _d(a["cnst"]), _i(a["child"]), _i(a["lin_ptr"]),
                                                 _i(a["lin_col"]), _d(a["lin_val"]), _d(a["c_lb"]), _d(a["c_ub"])),
                     "load_cgraph")
+
+    def load_quad(self, q):
+        """QuadraticFunction constraints (instances.QuadCons); None or an empty set removes them."""
+        if q is None or q.n_quad == 0:
+            self._check(self.L.mntr_gpu_load_quad(self.h, 0, None, None, None, None, None, None, None, None, None), "load_quad")
+            return
+        a = {k: np.ascontiguousarray(getattr(q, k), ty) for k, ty in (
+            ("q_ptr", np.int32), ("v1", np.int32), ("v2", np.int32), ("coef", np.float64), ("lin_ptr", np.int32),
+            ("lin_col", np.int32), ("lin_val", np.float64), ("q_lb", np.float64), ("q_ub", np.float64))}
+        self._check(self.L.mntr_gpu_load_quad(self.h, q.n_quad, _i(a["q_ptr"]), _i(a["v1"]), _i(a["v2"]), _d(a["coef"]),
+                                              _i(a["lin_ptr"]), _i(a["lin_col"]), _d(a["lin_val"]), _d(a["q_lb"]), _d(a["q_ub"])),
+                    "load_quad")
+
+    def root_dup_rows(self, r1, r2, cap=1 << 16):
+        """Duplicate-row candidates of LinearHandler::dupRows_: returns (h1, h2, pairs) with pairs an int array [k, 3]
+        of (i, j, kind) sorted by (i, j)."""
+        r1 = np.ascontiguousarray(r1, np.float64); r2 = np.ascontiguousarray(r2, np.float64)
+        h1 = np.zeros(max(self.m, 1)); h2 = np.zeros(max(self.m, 1))
+        while True:
+            pi = np.zeros(max(cap, 1), np.int32); pj = np.zeros(max(cap, 1), np.int32); pk = np.zeros(max(cap, 1), np.uint8)
+            total = C.c_int64(0)
+            self._check(self.L.mntr_gpu_root_dup_rows(self.h, _d(r1), _d(r2), _d(h1), _d(h2), cap, _i(pi), _i(pj), _b(pk),
+                                                      C.byref(total)), "root_dup_rows")
+            if total.value <= cap:
+                break
+            cap = int(total.value)
+        k = int(total.value)
+        return h1[:self.m], h2[:self.m], np.stack([pi[:k], pj[:k], pk[:k].astype(np.int32)], axis=1)
+
+    def root_redundant_rows(self, lb, ub):
+        """Rows whose activity range lies inside their bounds on the box (linBndTighten_ root mode, :974-985)."""
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        out = np.zeros(max(self.m, 1), np.uint8); cnt = C.c_int64(0)
+        self._check(self.L.mntr_gpu_root_redundant_rows(self.h, _d(lb), _d(ub), _b(out), C.byref(cnt)), "root_redundant_rows")
+        return out[:self.m].astype(bool)
 
     def update_row_bounds(self, row_lb, row_ub):
         """New bounds for the loaded rows (same order as load_linear): m doubles each way, no re-flattening."""

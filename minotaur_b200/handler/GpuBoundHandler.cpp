@@ -28,6 +28,7 @@
 #include "NonlinearFunction.h"
 #include "Objective.h"
 #include "Problem.h"
+#include "QuadraticFunction.h"
 #include "Relaxation.h"
 #include "SolutionPool.h"
 #include "Timer.h"
@@ -216,6 +217,8 @@ void GpuBoundHandler::upload_(ProblemPtr p)
   std::vector<int> rowPtr(1, 0), col, tapePtr(1, 0), a0, a1, child, linPtr(1, 0), linCol;
   std::vector<double> val, rowLb, rowUb, cn, linVal, cLb, cUb;
   std::vector<unsigned char> vtype(n), op;
+  std::vector<int> qPtr(1, 0), qV1, qV2, qLinPtr(1, 0), qLinCol;
+  std::vector<double> qCoef, qLinVal, qLb, qUb;
   for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it)
     vtype[(*it)->getIndex()] = (unsigned char)(*it)->getType();
   stats_.skippedCons = 0;
@@ -254,8 +257,26 @@ void GpuBoundHandler::upload_(ProblemPtr p)
       linPtr.push_back((int)linCol.size());
       cLb.push_back(c->getLb());
       cUb.push_back(c->getUb());
+    } else if (c->getFunctionType() != Constant && c->getQuadraticFunction()) {
+      // QuadraticFunction constraints are only CHECKED by NlPresHandler (chkRed_, NlPresHandler.cpp:127-150: the qf
+      // bounds take precedence over an nlf part, which chkRed_ then ignores); terms in VariablePairGroup order
+      QuadraticFunctionPtr qf = c->getQuadraticFunction();
+      for (VariablePairGroupConstIterator t = qf->begin(); t != qf->end(); ++t) {
+        qV1.push_back((int)t->first.first->getIndex());
+        qV2.push_back((int)t->first.second->getIndex());
+        qCoef.push_back(t->second);
+      }
+      qPtr.push_back((int)qV1.size());
+      if (lf)
+        for (VariableGroupConstIterator t = lf->termsBegin(); t != lf->termsEnd(); ++t) {
+          qLinCol.push_back((int)t->first->getIndex());
+          qLinVal.push_back(t->second);
+        }
+      qLinPtr.push_back((int)qLinCol.size());
+      qLb.push_back(c->getLb());
+      qUb.push_back(c->getUb());
     } else if (c->getFunctionType() != Constant && c->getFunctionType() != Linear) {
-      ++stats_.skippedCons;        // QuadraticFunction constraints: QuadHandler's
+      ++stats_.skippedCons;
     }
   }
   // CSR columns must ascend by variable INDEX; LinearFunction orders by id, which equals the index unless
@@ -274,6 +295,9 @@ void GpuBoundHandler::upload_(ProblemPtr p)
   const int nc = (int)tapePtr.size() - 1;
   if (child.empty()) child.push_back(0);
   if (linCol.empty()) { linCol.push_back(0); linVal.push_back(0.); }
+  const int nq = (int)qPtr.size() - 1;
+  if (qV1.empty()) { qV1.push_back(0); qV2.push_back(0); qCoef.push_back(0.); }
+  if (qLinCol.empty()) { qLinCol.push_back(0); qLinVal.push_back(0.); }
   int rc;
   if (group_) {
     rc = mntr_gpu_group_load_linear(group_, m, (int)n, &rowPtr[0], col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0],
@@ -281,12 +305,17 @@ void GpuBoundHandler::upload_(ProblemPtr p)
     if (rc == MNTR_OK && nc > 0)
       rc = mntr_gpu_group_load_cgraph(group_, nc, &tapePtr[0], &op[0], &a0[0], &a1[0], &cn[0], &child[0], &linPtr[0],
                                       &linCol[0], &linVal[0], &cLb[0], &cUb[0]);
+    if (rc == MNTR_OK && nq > 0)
+      rc = mntr_gpu_group_load_quad(group_, nq, &qPtr[0], &qV1[0], &qV2[0], &qCoef[0], &qLinPtr[0], &qLinCol[0], &qLinVal[0],
+                                    &qLb[0], &qUb[0]);
   } else {
     rc = mntr_gpu_load_linear(ctx_, m, (int)n, &rowPtr[0], col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0],
                               rowLb.empty() ? 0 : &rowLb[0], rowUb.empty() ? 0 : &rowUb[0], vtype.empty() ? 0 : &vtype[0], 0);
     if (rc == MNTR_OK && nc > 0)
       rc = mntr_gpu_load_cgraph(ctx_, nc, &tapePtr[0], &op[0], &a0[0], &a1[0], &cn[0], &child[0], &linPtr[0],
                                 &linCol[0], &linVal[0], &cLb[0], &cUb[0]);
+    if (rc == MNTR_OK && nq > 0)
+      rc = mntr_gpu_load_quad(ctx_, nq, &qPtr[0], &qV1[0], &qV2[0], &qCoef[0], &qLinPtr[0], &qLinCol[0], &qLinVal[0], &qLb[0], &qUb[0]);
   }
   if (rc != MNTR_OK) throw std::runtime_error(std::string(me_) + (group_ ? mntr_gpu_group_last_error(group_) : mntr_gpu_last_error(ctx_)));
   loadedFor_ = p;

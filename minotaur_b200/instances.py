@@ -720,3 +720,36 @@ def minlp_tapes_from_draws(ijk: np.ndarray, xstar: np.ndarray, rng: np.random.Ge
         else:
             cons.append((Expr.sumlist([Expr.v(int(i[c])).sqr(), Expr.v(int(j[c])).sqr()]), [], float(c_lb[c]), float(c_ub[c])))
     return tapes, cons
+
+
+def plant_duplicate_rows(inst: LinearRows, n_dups: int, seed: int) -> LinearRows:
+    """A copy of a uniform-row instance in which ``n_dups`` rows are overwritten by a copy, the negative, or a multiple
+    (2.5x, -0.5x) of another row, some with shifted bounds: what LinearHandler::dupRows_
+    (/root/reference/src/base/LinearHandler.cpp:882-949) looks for."""
+    import copy
+    m = inst.m
+    k = inst.nnz // m
+    assert inst.nnz == m * k
+    rng = np.random.default_rng([seed, 17])
+    col = inst.col.reshape(m, k).copy(); val = inst.val.reshape(m, k).copy()
+    rl = inst.row_lb.copy(); ru = inst.row_ub.copy()
+    for t in range(n_dups):
+        i, j = (int(x) for x in rng.integers(0, m, 2))
+        if i == j:
+            continue
+        col[j] = col[i]
+        kind = t % 4
+        if kind == 0:
+            val[j] = val[i]
+        elif kind == 1:
+            val[j] = -val[i]; rl[j], ru[j] = -ru[j], -rl[j]
+        elif kind == 2:
+            val[j] = val[i] * 2.5
+        else:
+            val[j] = val[i] * (-0.5)
+        if np.isfinite(ru[j]):
+            ru[j] = ru[j] + float(rng.integers(-2, 3))
+    out = copy.copy(inst)
+    out.col, out.val, out.row_lb, out.row_ub = col.reshape(-1), val.reshape(-1), rl, ru
+    out.name = inst.name + "-dups"
+    return out

@@ -944,3 +944,56 @@ double orc_batch_deltas(const orc_lin_t *p, const orc_nl_t *g, int32_t mode, int
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* --- root presolve row operations (LinearHandler::presolve) ------------------------------------------------------ */
+
+/* ref: LinearHandler.cpp:882-949 dupRows_, the detection part: row hashes h = Constraint::getActivity(r) (terms in
+ * ascending variable id, value += x * coef, LinearFunction.cpp:151-158) for two random vectors, then every pair i < j
+ * through the reference's tests.  Returns the number of candidate pairs (stored up to cap, in (i, j) order -- the order
+ * of the reference's double loop).  kind 1: treatDupRows_ is called with mult 1.0, kind 2: with h1i / h1j.
+ * The reference also skips rows deleted earlier in the same loop; that depends on treatDupRows_ (the object graph) and
+ * is applied by the caller while walking the list. */
+int64_t orc_root_dup_rows(const orc_lin_t *p, const double *r1, const double *r2, double *h1, double *h2, int64_t cap,
+                          int32_t *pair_i, int32_t *pair_j, uint8_t *pair_kind)
+{
+  const int32_t m = p->m;
+  for (int32_t i = 0; i < m; ++i) {
+    if (p->row_active && !p->row_active[i]) { h1[i] = h2[i] = 1e30; continue; }
+    double a = 0, b = 0;
+    for (int32_t t = p->row_ptr[i]; t < p->row_ptr[i + 1]; ++t) {
+      if (fabs(p->val[t]) <= 1e-9) continue;                 /* LinearFunction::addTerm drops these */
+      a += r1[p->col[t]] * p->val[t];
+      b += r2[p->col[t]] * p->val[t];
+    }
+    h1[i] = a; h2[i] = b;
+  }
+  int64_t k = 0;
+  for (int32_t i = 0; i < m; ++i) {
+    if (!(h1[i] < 1e29)) continue;
+    for (int32_t j = i + 1; j < m; ++j) {
+      int kind = 0;
+      if (fabs(h1[j] - h1[i]) < 1e-10 || fabs(h1[j] + h1[i]) < 1e-10) kind = 1;
+      else if (h1[j] < 1e29 && fabs(h1[i] / h1[j] - h2[i] / h2[j]) < 1e-10) kind = 2;
+      if (kind) {
+        if (k < cap) { pair_i[k] = i; pair_j[k] = j; pair_kind[k] = (uint8_t)kind; }
+        ++k;
+      }
+    }
+  }
+  return k;
+}
+
+/* ref: LinearHandler.cpp:974-985: a row is redundant on a box when getLfBnds_ gives ll >= lb - eTol && uu <= ub + eTol */
+int64_t orc_root_redundant_rows(const orc_lin_t *p, const double *lb, const double *ub, uint8_t *redundant)
+{
+  int64_t k = 0;
+  for (int32_t i = 0; i < p->m; ++i) {
+    redundant[i] = 0;
+    if (p->row_active && !p->row_active[i]) continue;
+    double ll, uu;
+    int32_t b = p->row_ptr[i];
+    lf_bnds(p->row_ptr[i + 1] - b, p->col + b, p->val + b, lb, ub, &ll, &uu);
+    if (ll >= p->row_lb[i] - E_TOL && uu <= p->row_ub[i] + E_TOL) { redundant[i] = 1; ++k; }
+  }
+  return k;
+}

@@ -150,6 +150,10 @@ class Oracle:
         L.orc_nl_chk_red.restype = C.c_int32
         L.orc_quad_compute_bounds.argtypes = [C.POINTER(OrcNl), C.c_int32, _dp, _dp, _dp, _dp]
         L.orc_quad_compute_bounds.restype = None
+        L.orc_root_dup_rows.argtypes = [C.POINTER(OrcLin), _dp, _dp, _dp, _dp, C.c_int64, _ip, _ip, _bp]
+        L.orc_root_dup_rows.restype = C.c_int64
+        L.orc_root_redundant_rows.argtypes = [C.POINTER(OrcLin), _dp, _dp, _bp]
+        L.orc_root_redundant_rows.restype = C.c_int64
         L.orc_nl_sweep.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(C.c_int64)]
         L.orc_nl_sweep.restype = C.c_int32
         L.orc_node_presolve.argtypes = [C.POINTER(OrcLin), C.POINTER(OrcNl), _dp, _dp, C.POINTER(OrcResult)]
@@ -207,6 +211,24 @@ class Oracle:
         lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
         self.lib.orc_lin_row_activity(C.byref(s), row, _d(lb), _d(ub), _d(out))
         return out
+
+    # ---- root presolve row operations ----
+    def root_dup_rows(self, inst, r1, r2, cap=1 << 16):
+        """Duplicate-row candidates of LinearHandler::dupRows_: (h1, h2, pairs [k, 3] = (i, j, kind))."""
+        keep = {}; s = _lin_struct(inst, keep)
+        r1 = np.ascontiguousarray(r1, np.float64); r2 = np.ascontiguousarray(r2, np.float64)
+        h1 = np.zeros(max(inst.m, 1)); h2 = np.zeros(max(inst.m, 1))
+        pi = np.zeros(cap, np.int32); pj = np.zeros(cap, np.int32); pk = np.zeros(cap, np.uint8)
+        k = int(self.lib.orc_root_dup_rows(C.byref(s), _d(r1), _d(r2), _d(h1), _d(h2), cap, _i(pi), _i(pj), _b(pk)))
+        assert k <= cap
+        return h1[:inst.m], h2[:inst.m], np.stack([pi[:k], pj[:k], pk[:k].astype(np.int32)], axis=1)
+
+    def root_redundant_rows(self, inst, lb, ub):
+        keep = {}; s = _lin_struct(inst, keep)
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        out = np.zeros(max(inst.m, 1), np.uint8)
+        self.lib.orc_root_redundant_rows(C.byref(s), _d(lb), _d(ub), _b(out))
+        return out[:inst.m].astype(bool)
 
     # ---- nonlinear ----
     def nl_compute_bounds(self, tapes, c, lb, ub):
@@ -326,6 +348,10 @@ class Reference:
             L.ref_nl_chk_red.argtypes = [C.c_void_p]
             L.ref_nl_chk_red.restype = C.c_int32
             L.ref_quad_compute_bounds.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
+            L.ref_draw_dup_vectors.argtypes = [C.c_void_p, C.c_uint32, _dp, _dp]
+            L.ref_dup_rows.argtypes = [C.c_void_p, C.c_uint32, _bp, _dp, _dp]
+            L.ref_dup_rows_replay.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _bp, _dp, _bp, _dp, _dp]
+            L.ref_redundant_rows.argtypes = [C.c_void_p, _bp]
             L.ref_destroy.argtypes = [C.c_void_p]
             cls._lib = L
         return cls._lib
@@ -431,6 +457,34 @@ class Reference:
         st = self.lib().ref_nl_var_bound_mods(self.h, c, lb_in, ub_in, _i(nm))
         l, u = self.get_box()
         return l, u, int(st), int(nm[0])
+
+    def draw_dup_vectors(self, seed):
+        """The two random vectors LinearHandler::dupRows_ draws after srand(seed)."""
+        r1 = np.zeros(self.n); r2 = np.zeros(self.n)
+        self.lib().ref_draw_dup_vectors(self.h, int(seed), _d(r1), _d(r2))
+        return r1, r2
+
+    def dup_rows(self, seed, m):
+        """The reference's own dupRows_ (generator seeded): (deleted [m], row_lb, row_ub).  Modifies the problem."""
+        d = np.zeros(max(m, 1), np.uint8); rl = np.zeros(max(m, 1)); ru = np.zeros(max(m, 1))
+        self.lib().ref_dup_rows(self.h, int(seed), _b(d), _d(rl), _d(ru))
+        return d[:m].astype(bool), rl[:m], ru[:m]
+
+    def dup_rows_replay(self, pairs, h1, m):
+        """dupRows_'s loop driven by an external candidate list (treatDupRows_ is the reference's).  Modifies the problem."""
+        pi = np.ascontiguousarray(pairs[:, 0], np.int32); pj = np.ascontiguousarray(pairs[:, 1], np.int32)
+        pk = np.ascontiguousarray(pairs[:, 2], np.uint8); h1 = np.ascontiguousarray(h1, np.float64)
+        if len(pi) == 0:
+            pi = np.zeros(1, np.int32); pj = np.zeros(1, np.int32); pk = np.zeros(1, np.uint8)
+        d = np.zeros(max(m, 1), np.uint8); rl = np.zeros(max(m, 1)); ru = np.zeros(max(m, 1))
+        self.lib().ref_dup_rows_replay(self.h, len(pairs), _i(pi), _i(pj), _b(pk), _d(h1), _b(d), _d(rl), _d(ru))
+        return d[:m].astype(bool), rl[:m], ru[:m]
+
+    def redundant_rows(self, lb, ub, m):
+        self.set_box(lb, ub)
+        out = np.zeros(max(m, 1), np.uint8)
+        self.lib().ref_redundant_rows(self.h, _b(out))
+        return out[:m].astype(bool)
 
     def nl_chk_red(self, lb, ub):
         """NlPresHandler::chkRed_ alone on the box: 1 = infeasible."""

@@ -137,6 +137,17 @@ public:
     return inf;
   }
 
+  /* LinearHandler::dupRows_ itself (protected, :882-949).  It draws its two random vectors with rand(): the caller
+   * seeds the generator, so that the same vectors can be drawn again outside (drawDupVectors). */
+  void dupRows(bool *changed) { dupRows_(changed); }
+  bool treatDup(ConstraintPtr c1, ConstraintPtr c2, double mult, bool *changed) { return treatDupRows_(c1, c2, mult, changed); }
+  bool redundantOnBox(ConstraintPtr c)
+  {
+    double ll, uu;
+    getLfBnds_(c->getLinearFunction(), &ll, &uu);
+    return ll >= c->getLb() - 1e-8 && uu <= c->getUb() + 1e-8;       /* :974 */
+  }
+
   void rowActivity(ConstraintPtr c, double out[4])
   {
     LinearFunctionPtr lf = c->getLinearFunction();
@@ -258,6 +269,63 @@ void ref_quad_compute_bounds(void *hv, int32_t q, double *lb, double *ub)
 {
   RefProblem *h = (RefProblem *)hv;
   h->quad_rows[q]->getFunction()->getQuadraticFunction()->computeBounds(lb, ub);
+}
+
+/* the two random vectors LinearHandler::dupRows_ draws after srand(seed): r1[i], r2[i] alternately (:904-907) */
+void ref_draw_dup_vectors(void *hv, uint32_t seed, double *r1, double *r2)
+{
+  RefProblem *h = (RefProblem *)hv;
+  srand(seed);
+  for (size_t i = 0; i < h->vars.size(); ++i) {
+    r1[i] = (double)rand() / (RAND_MAX) * 10.0;
+    r2[i] = (double)rand() / (RAND_MAX) * 10.0;
+  }
+}
+
+static void dumpRows(RefProblem *h, uint8_t *deleted, double *row_lb, double *row_ub)
+{
+  for (size_t i = 0; i < h->lin_rows.size(); ++i) {
+    deleted[i] = h->p->isMarkedDel(h->lin_rows[i]) ? 1 : 0;
+    row_lb[i] = h->lin_rows[i]->getLb(); row_ub[i] = h->lin_rows[i]->getUb();
+  }
+}
+
+/* the reference's own LinearHandler::dupRows_ with the generator seeded: which rows it marks deleted, the row bounds
+ * it leaves (the problem is modified: use a fresh handle per call) */
+int32_t ref_dup_rows(void *hv, uint32_t seed, uint8_t *deleted, double *row_lb, double *row_ub)
+{
+  RefProblem *h = (RefProblem *)hv;
+  bool changed = false;
+  srand(seed);
+  h->lh->dupRows(&changed);
+  dumpRows(h, deleted, row_lb, row_ub);
+  return changed ? 1 : 0;
+}
+
+/* the same loop driven by an externally computed candidate list (mntr_gpu_root_dup_rows / orc_root_dup_rows): pairs in
+ * (i, j) order; a pair is skipped when one of its rows was deleted by an earlier pair, exactly what overwriting
+ * h1[j] = 1e30 does in the reference (:934-947); treatDupRows_ is the reference's own */
+int32_t ref_dup_rows_replay(void *hv, int64_t n_pairs, const int32_t *pair_i, const int32_t *pair_j, const uint8_t *pair_kind,
+                            const double *h1, uint8_t *deleted, double *row_lb, double *row_ub)
+{
+  RefProblem *h = (RefProblem *)hv;
+  bool changed = false;
+  std::vector<char> gone(h->lin_rows.size(), 0);
+  for (int64_t k = 0; k < n_pairs; ++k) {
+    const int32_t i = pair_i[k], j = pair_j[k];
+    if (gone[i] || gone[j]) continue;
+    const double mult = pair_kind[k] == 1 ? 1.0 : h1[i] / h1[j];
+    if (h->lh->treatDup(h->lin_rows[i], h->lin_rows[j], mult, &changed)) gone[j] = 1;
+  }
+  dumpRows(h, deleted, row_lb, row_ub);
+  return changed ? 1 : 0;
+}
+
+/* rows that the reference's root-mode linBndTighten_ would find redundant on the current box (:974) */
+void ref_redundant_rows(void *hv, uint8_t *redundant)
+{
+  RefProblem *h = (RefProblem *)hv;
+  for (size_t i = 0; i < h->lin_rows.size(); ++i) redundant[i] = h->lh->redundantOnBox(h->lin_rows[i]) ? 1 : 0;
 }
 
 /* linear objective  min c.x + constant  (the cut-off row of LinearHandler::varBndsFromObj_) */
