@@ -42,14 +42,16 @@ const std::string GpuBoundHandler::me_ = "GpuBoundHandler: ";
 
 GpuBoundHandler::GpuBoundHandler(EnvPtr env, ProblemPtr problem, int device)
   : env_(env), problem_(problem), ctx_(0), group_(0), mode_(FastFixpoint), roundNearest_(false), checkStructure_(true),
-    loadedFor_(0), loadedVars_(0), loadedCons_(0), cutoffOn_(false), sigStruct_(0), sigBounds_(0), lb_(0), ub_(0), boxCap_(0)
+    loadedFor_(0), loadedVars_(0), loadedCons_(0), cutoffOn_(false), sigStruct_(0), sigBounds_(0), lb_(0), ub_(0), boxCap_(0),
+    cacheFor_(0)
 {
   init_(std::vector<int>(1, device));
 }
 
 GpuBoundHandler::GpuBoundHandler(EnvPtr env, ProblemPtr problem, const std::vector<int> &devices)
   : env_(env), problem_(problem), ctx_(0), group_(0), mode_(FastFixpoint), roundNearest_(false), checkStructure_(true),
-    loadedFor_(0), loadedVars_(0), loadedCons_(0), cutoffOn_(false), sigStruct_(0), sigBounds_(0), lb_(0), ub_(0), boxCap_(0)
+    loadedFor_(0), loadedVars_(0), loadedCons_(0), cutoffOn_(false), sigStruct_(0), sigBounds_(0), lb_(0), ub_(0), boxCap_(0),
+    cacheFor_(0)
 {
   init_(devices);
 }
@@ -58,7 +60,7 @@ void GpuBoundHandler::init_(const std::vector<int> &devices)
 {
   logger_ = env_->getLogger();
   stats_.calls = stats_.uploads = stats_.nMods = stats_.nInf = 0;
-  stats_.rowBoundUpdates = stats_.skippedCons = stats_.engineErrors = 0;
+  stats_.rowBoundUpdates = stats_.skippedCons = stats_.engineErrors = stats_.cacheHits = 0;
   stats_.nnzUpdates = 0;
   stats_.timeHost = stats_.timeDevice = 0.;
   int rc;
@@ -507,10 +509,87 @@ void GpuBoundHandler::tightenCandidates(RelaxationPtr rel, SolutionPoolPtr spool
   }
 }
 
+void GpuBoundHandler::prefetchCandidates(RelaxationPtr rel, SolutionPoolPtr spool,
+                                         const std::vector<std::vector<BoundChange> > &deltas)
+{
+  clearCandidates();
+  if (deltas.empty()) return;
+  tightenCandidates(rel, spool, deltas, cacheOut_);
+  if (cacheOut_.size() != deltas.size()) { cacheOut_.clear(); return; }
+  ProblemPtr p = rel;
+  const UInt n = p->getNumVars();
+  cacheLb_.resize(n); cacheUb_.resize(n);
+  for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) {
+    cacheLb_[(*it)->getIndex()] = (*it)->getLb();
+    cacheUb_[(*it)->getIndex()] = (*it)->getUb();
+  }
+  cacheDeltas_ = deltas;
+  cacheFor_ = p;
+}
+
+void GpuBoundHandler::clearCandidates()
+{
+  cacheFor_ = 0;
+  cacheDeltas_.clear(); cacheOut_.clear();
+}
+
+int GpuBoundHandler::findCached_(ProblemPtr p) const
+{
+  if (cacheFor_ != p || cacheLb_.size() != p->getNumVars()) return -1;
+  // the bounds that differ from the cached base box
+  std::vector<BoundChange> diff;
+  for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) {
+    const UInt j = (*it)->getIndex();
+    if ((*it)->getLb() != cacheLb_[j]) { BoundChange c = { j, Lower, (*it)->getLb() }; diff.push_back(c); }
+    if ((*it)->getUb() != cacheUb_[j]) { BoundChange c = { j, Upper, (*it)->getUb() }; diff.push_back(c); }
+    if (diff.size() > 8) return -1;
+  }
+  if (diff.empty()) return -1;
+  for (size_t b = 0; b < cacheDeltas_.size(); ++b) {
+    const std::vector<BoundChange> &d = cacheDeltas_[b];
+    if (d.size() != diff.size()) continue;
+    bool same = true;
+    for (size_t k = 0; k < d.size() && same; ++k) {
+      bool found = false;
+      for (size_t q = 0; q < diff.size(); ++q)
+        if (diff[q].var == d[k].var && diff[q].lu == d[k].lu && diff[q].val == d[k].val) { found = true; break; }
+      same = found;
+    }
+    if (same) return (int)b;
+  }
+  return -1;
+}
+
 void GpuBoundHandler::simplePresolve(ProblemPtr p, SolutionPoolPtr spool, ModVector &t_mods, SolveStatus &status)
 {
   Timer *timer = env_->getNewTimer();
   timer->start();
+  if (cacheFor_) {
+    const int b = findCached_(p);
+    if (b >= 0) {
+      // the outcome mntr_gpu_tighten_nodes computed for exactly this box: emit it as applied VarBoundMods
+      ++stats_.cacheHits; ++stats_.calls;
+      if (cacheOut_[(size_t)b].infeasible) { ++stats_.nInf; status = SolvedInfeasible; }
+      else
+        for (size_t k = 0; k < cacheOut_[(size_t)b].changes.size(); ++k) {
+          const BoundChange &c = cacheOut_[(size_t)b].changes[k];
+          VarBoundModPtr mod = (VarBoundModPtr) new VarBoundMod(p->getVariable(c.var), c.lu, c.val);
+          mod->applyToProblem(p);
+          t_mods.push_back(mod);
+          ++stats_.nMods;
+        }
+      stats_.timeHost += timer->query();
+      delete timer;
+      return;
+    }
+    if (cacheFor_ == p) {
+      // `p` is neither the base box nor one of the candidates: the outcomes are stale
+      bool isBase = true;
+      for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd() && isBase; ++it)
+        isBase = (*it)->getLb() == cacheLb_[(*it)->getIndex()] && (*it)->getUb() == cacheUb_[(*it)->getIndex()];
+      if (!isBase) clearCandidates();
+    }
+  }
   const bool inf = tighten_(p, spool, t_mods, true);
   if (inf) status = SolvedInfeasible;
   stats_.timeHost += timer->query();
@@ -571,6 +650,7 @@ void GpuBoundHandler::writeStats(std::ostream &out) const
       << me_ << "Row-bound refreshes          = " << stats_.rowBoundUpdates << std::endl
       << me_ << "Constraints left to others   = " << stats_.skippedCons << std::endl
       << me_ << "Engine errors                = " << stats_.engineErrors << std::endl
+      << me_ << "Answered from prefetched set = " << stats_.cacheHits << std::endl
       << me_ << "Bound modifications          = " << stats_.nMods << std::endl
       << me_ << "Times infeasibility detected = " << stats_.nInf << std::endl
       << me_ << "nnz-updates                  = " << stats_.nnzUpdates << std::endl

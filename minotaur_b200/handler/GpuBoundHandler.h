@@ -39,6 +39,7 @@ struct GpuBoundStats {
   int rowBoundUpdates; ///< times only the row bounds were refreshed on the device (structure unchanged)
   int skippedCons;    ///< constraints of the last upload the engine does not take (left to NlPresHandler / QuadHandler)
   int engineErrors;   ///< engine calls that failed (the call then reports "no tightening", it never aborts the solve)
+  int cacheHits;      ///< presolveNode calls answered from prefetched candidate outcomes (no device call)
   long long nnzUpdates;
   double timeHost;    ///< host seconds in flatten + gather + mod emission
   double timeDevice;  ///< device milliseconds reported by the engine
@@ -98,6 +99,18 @@ public:
   void tightenCandidates(RelaxationPtr rel, SolutionPoolPtr spool,
                          const std::vector<std::vector<BoundChange> > &deltas, std::vector<BoxOutcome> &out);
 
+  /**
+   * The same, for callers that cannot consume a batch at once: StrongBrancher / WeakBrancher tighten one candidate
+   * box after the other through Handler::getStrongerMods -> presolveNode (StrongBrancher.cpp:499-585,
+   * WeakBrancher.cpp:300-350).  Called once before such a loop with the branching modifications of ALL candidates
+   * (Handler::getBrMod for DownBranch and UpBranch), this tightens all their boxes in one device call and keeps the
+   * outcomes; every presolveNode that follows on `rel` with exactly one of those modifications applied is answered
+   * from them (same VarBoundMods, same verdict, no device call).  The outcomes are dropped by clearCandidates(), by the
+   * next prefetch, and whenever a presolveNode finds the relaxation in a state it does not know.
+   */
+  void prefetchCandidates(RelaxationPtr rel, SolutionPoolPtr spool, const std::vector<std::vector<BoundChange> > &deltas);
+  void clearCandidates();
+
   std::string getName() const;
   void writeStats(std::ostream &out) const;
 
@@ -143,6 +156,13 @@ private:
   double *lb_, *ub_;
   UInt boxCap_;
   std::vector<double> lb0_, ub0_;
+  // prefetched candidate outcomes (prefetchCandidates): the box they were computed from and, per candidate, its deltas
+  const Problem *cacheFor_;
+  std::vector<double> cacheLb_, cacheUb_;
+  std::vector<std::vector<BoundChange> > cacheDeltas_;
+  std::vector<BoxOutcome> cacheOut_;
+  /// the candidate whose deltas are exactly the difference between p's bounds and the cached base box, or -1
+  int findCached_(ProblemPtr p) const;
 
   /// Flatten p (linear rows -> CSR, CGraph constraints -> tapes) and upload it.
   void upload_(ProblemPtr p);

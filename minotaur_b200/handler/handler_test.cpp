@@ -325,6 +325,44 @@ int main(int argc, char **argv)
       for (ModVector::reverse_iterator it = rm.rbegin(); it != rm.rend(); ++it) { (*it)->undoToProblem(rel); delete *it; }
       br.undoToProblem(rel);
     }
+    // ---- the same loop the way StrongBrancher runs it with strong_brancher_prefetch.patch: one prefetch, then every
+    //      getStrongerMods -> presolveNode is answered from the prefetched outcomes (no device call per candidate) ----
+    {
+      GpuBoundHandler g2(env, p, 0);
+      g2.setMode(GpuBoundHandler::ReferenceOrder);
+      g2.setRoundNearest(true);
+      g2.prefetchCandidates(rel, (SolutionPoolPtr)0, deltas);
+      int hits = 0;
+      for (size_t b = 0; b < deltas.size(); ++b) {
+        VariablePtr bv = rel->getVariable(deltas[b][0].var);
+        VarBoundMod br(bv, deltas[b][0].lu, deltas[b][0].val);
+        br.applyToProblem(rel);
+        std::vector<double> l0(n), u0(n);
+        for (int j = 0; j < n; ++j) { l0[j] = rel->getVariable(j)->getLb(); u0[j] = rel->getVariable(j)->getUb(); }
+        ModVector rm;
+        const bool inf = g2.presolveNode(rel, (NodePtr)0, (SolutionPoolPtr)0, pm, rm);
+        CHECK(inf == outc[b].infeasible, "prefetched candidate %d: verdict %d, batch %d", (int)b, (int)inf, (int)outc[b].infeasible);
+        if (!inf) {
+          std::vector<double> l(l0), u(u0);
+          for (size_t k = 0; k < outc[b].changes.size(); ++k)
+            (outc[b].changes[k].lu == Upper ? u : l)[outc[b].changes[k].var] = outc[b].changes[k].val;
+          for (int j = 0; j < n; ++j)
+            CHECK(rel->getVariable(j)->getLb() == l[j] && rel->getVariable(j)->getUb() == u[j],
+                  "prefetched candidate %d var %d differs from the batch outcome", (int)b, j);
+        }
+        for (ModVector::reverse_iterator it = rm.rbegin(); it != rm.rend(); ++it) { (*it)->undoToProblem(rel); delete *it; }
+        br.undoToProblem(rel);
+      }
+      hits = g2.getStats()->cacheHits;
+      CHECK(hits == (int)deltas.size(), "prefetch: %d of %d candidate calls were answered from the prefetched outcomes", hits, (int)deltas.size());
+      // a box that is not one of the candidates drops the outcomes and takes the device path again
+      branch(rel, 3);
+      ModVector rm;
+      (void)g2.presolveNode(rel, (NodePtr)0, (SolutionPoolPtr)0, pm, rm);
+      CHECK(g2.getStats()->cacheHits == hits, "prefetch: a foreign box was answered from the cache");
+      for (ModVector::iterator it = rm.begin(); it != rm.end(); ++it) delete *it;
+      printf("handler_test: prefetch of %d candidate boxes, %d presolveNode calls answered without a device call\n", (int)deltas.size(), hits);
+    }
     delete rel;
     delete p;
   }
