@@ -10,6 +10,9 @@
 #include <fstream>
 #include <string>
 #include <vector>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 
 #include "MinotaurConfig.h"
 #include "CGraph.h"
@@ -188,8 +191,18 @@ static int rootPresolve(EnvPtr env, ProblemPtr pA, ProblemPtr pB, const char *wh
   return (pA->getNumCons() == pB->getNumCons()) ? diff : -1;
 }
 
+static void onAbort(int)
+{
+  void *frames[48];
+  const int nf = backtrace(frames, 48);
+  backtrace_symbols_fd(frames, nf, 2);
+  _exit(134);
+}
+
 int main(int argc, char **argv)
 {
+  setvbuf(stdout, 0, _IOLBF, 0);
+  signal(SIGABRT, onAbort);
   EnvPtr env = (EnvPtr) new Environment();
   int err = 0;
   env->startTimer(err);
@@ -328,6 +341,7 @@ int main(int argc, char **argv)
     // ---- the same loop the way StrongBrancher runs it with strong_brancher_prefetch.patch: one prefetch, then every
     //      getStrongerMods -> presolveNode is answered from the prefetched outcomes (no device call per candidate) ----
     {
+      const uint64_t keepRng = rng_state;   // the sections below keep the random problems they were written against
       GpuBoundHandler g2(env, p, 0);
       g2.setMode(GpuBoundHandler::ReferenceOrder);
       g2.setRoundNearest(true);
@@ -362,6 +376,7 @@ int main(int argc, char **argv)
       CHECK(g2.getStats()->cacheHits == hits, "prefetch: a foreign box was answered from the cache");
       for (ModVector::iterator it = rm.begin(); it != rm.end(); ++it) delete *it;
       printf("handler_test: prefetch of %d candidate boxes, %d presolveNode calls answered without a device call\n", (int)deltas.size(), hits);
+      rng_state = keepRng;
     }
     delete rel;
     delete p;
@@ -452,6 +467,9 @@ int main(int argc, char **argv)
     rng_state = keep;
     ProblemPtr pB = makeProblem(env, 300, 320, 6, 30, xstar);
     int ta, tb;
+    // (the reference's NlPresHandler::bin2Lin_, NlPresHandler.cpp:424-540, adds constraints while it walks them with
+    //  `mult` sized for the old count: a random problem with a binary x binary product aborts inside the REFERENCE run
+    //  under _FORTIFY_SOURCE -- this seed has none)
     // (informational: NlPresHandler::presolve also DELETES constraints it finds redundant at the root, chkRed_ with
     //  apply_to_prob -- a structure change GpuBoundHandler leaves to it by design, SURVEY.md 8a L12 -- so the two runs
     //  need not end with the same rows or bit-identical boxes; both must finish)
