@@ -9,6 +9,7 @@
 // Because candidates are merged with exact max/min and everything after the merge is replicated, all
 // ranks finish with bit-identical boxes and the result does not depend on the number of ranks.
 // The row evaluation is the lane = row streaming form of row_resident.cuh.
+#include <cstdlib>
 #include "device_problem.cuh"
 #include "kernels.h"
 #include "row_resident.cuh"
@@ -43,7 +44,11 @@ __device__ __forceinline__ bool loop_stopped(const int32_t *ctrl)
 struct __align__(16) StreamStage {
   double sval[kStageEntries];      // the block's entries, staged by cp.async
   int32_t scol[kStageEntries];
-  static constexpr int kQueueCap = 96;
+  int2 sinfo[32];                  // the next block's row heads, staged ahead (round 1)
+  double2 sbnd[32];
+  // (the slice is kept below 8 KB: two blocks of 8 warps then leave the SM 124 KB of L1, which the later rounds -- lanes
+  //  reading their rows straight from the CSR -- need: with 28 KB of L1 round 2 took 0.30 ms instead of 0.14)
+  static constexpr int kQueueCap = 48;
   CandItem q[kQueueCap];           // (the work list is only used with an empty queue and shares its storage)
   int tcount;
   int pad_[3];                     // [1] length of the candidate queue
@@ -51,14 +56,11 @@ struct __align__(16) StreamStage {
   static constexpr bool kL2Hints = false;    // (measured: the hints slow this kernel down, 0.65 -> 0.85 ms at 2.5M rows)
   __device__ __forceinline__ double *stage_val() { return sval; }
   __device__ __forceinline__ int32_t *stage_col() { return scol; }
-  // (row heads staged ahead: never used here -- blocks are interleaved over the warps, no block has an adjacent next
-  //  one -- and kept out of the slice: three blocks of 62 KB leave the SM 32 KB of L1, which this kernel needs)
-  __device__ __forceinline__ int2 *stage_info() { return nullptr; }
-  __device__ __forceinline__ double2 *stage_bnd() { return nullptr; }
-  __device__ __forceinline__ uint16_t *work_list() { return reinterpret_cast<uint16_t *>(q); }
+  __device__ __forceinline__ int2 *stage_info() { return sinfo; }
+  __device__ __forceinline__ double2 *stage_bnd() { return sbnd; }
   __device__ __forceinline__ CandItem *queue() { return q; }
 };
-static_assert(sizeof(CandItem) * StreamStage::kQueueCap >= sizeof(uint16_t) * 32 * kLaneMax, "work list fits the queue's storage");
+static_assert(sizeof(StreamStage) * (kRoundsThreads / 32) + 1024 <= 66 * 1024, "two blocks fit the 132 KB shared-memory carve-out");
 
 // candidates go into the split arrays nlb / nub; moved variables are found, rounded and their rows flagged by the vars
 // kernel after the cross-GPU merge, so nothing is marked here
@@ -89,7 +91,58 @@ struct SinkRounds {
 // rank gives its rows -- so a row yields the same candidates whichever rank owns it, and the merged result is bitwise
 // independent of the partition.  (An earlier version took the due rows of sparse blocks with sub-warp groups and a
 // butterfly sum: the 8-rank run then differed from the 1-rank run in the last bits.)
-template <class R>
+// ROUND 1: every row is due, so a warp knows its whole sequence of blocks before it starts.  It takes a CONTIGUOUS range
+// of 32-row blocks: the next block's entries start where this block's end, so right after pass 1 has consumed the
+// staged entries of block b the row heads of block b+1 and a window of entries from that position are requested
+// (stage_next_block, cp.async): they land while block b's product test and candidates run, and block b+1 starts from
+// shared memory instead of with two dependent trips to DRAM (heads, then entries).
+template <class R, int G>
+__device__ __forceinline__ void rows_first_round(const LinDev &P, const RoundsWs &W, StreamStage &S, int warp_global, int n_warps,
+                                                 unsigned long long &my_nnz, unsigned long long &my_rows)
+{
+  const int lane = threadIdx.x & 31;
+  const ReadPending rd{W.box, P.colx, false};
+  const SinkRounds sink{W.nlb, W.nub, P.n, W.tbits, W.tlist, W.ctrl + kRcTouched};
+  const int n_blk = (P.m + 31) / 32;
+  const int per = (n_blk + n_warps - 1) / n_warps;
+  const int b0 = warp_global * per, b1 = min(n_blk, b0 + per);
+  int spec_row0 = -1, spec_e0 = 0;           // the block staged ahead (first row, first entry of the window), if any
+  for (int b = b0; b < b1; ++b) {
+    const int row0 = b * 32, row = row0 + lane;
+    RowHead h{0, -1, 0.0, 0.0};
+    const bool ahead = spec_row0 == row0;
+    if (ahead) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      const int2 info = S.sinfo[lane];
+      const double2 bnd = S.sbnd[lane];
+      h = RowHead{info.x, info.y, bnd.x, bnd.y};
+    } else if (row < P.m) {
+      h = load_head(P, row);
+    }
+    const bool is_due = h.cnt >= 0;                            // deleted rows are never evaluated
+    if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
+    const int32_t *gcol; const double *gval;
+    const int d1 = __reduce_max_sync(kFullMask, is_due ? row_end(make_int2(h.beg, h.cnt)) : 0);
+    const int d0 = __reduce_min_sync(kFullMask, is_due ? h.beg : 0x7fffffff);
+    if (ahead && d0 >= spec_e0 && d1 <= spec_e0 + kStageEntries) {
+      gcol = S.scol + (h.beg - spec_e0); gval = S.sval + (h.beg - spec_e0);
+    } else {
+      stage_block(P, S, lane, is_due, h, gcol, gval);
+    }
+    const bool whole = __all_sync(kFullMask, row < P.m && h.cnt >= 0);
+    const int blk_end = __shfl_sync(kFullMask, row_end(make_int2(h.beg, h.cnt < 0 ? 0 : h.cnt)), 31);
+    const bool adj = b + 1 < b1 && whole && row0 + 64 <= P.m && blk_end < P.nnz_pad &&
+                     __ballot_sync(kFullMask, is_due && h.cnt > kLaneMax) == 0u;      // (eval_resident stages only then)
+    spec_row0 = adj ? row0 + 32 : -1;
+    spec_e0 = blk_end;
+    eval_resident<R, G>(P, rd, sink, S, lane, is_due, h, false, gcol, gval, spec_row0, spec_e0);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+
+template <class R, int G>
 __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W, StreamStage &S, int warp_global, int n_warps,
                                               bool first, unsigned long long &my_nnz, unsigned long long &my_rows)
 {
@@ -97,15 +150,22 @@ __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W
   const ReadPending rd{W.box, P.colx, false};          // the vars kernel stores rounded integer bounds
   const SinkRounds sink{W.nlb, W.nub, P.n, W.tbits, W.tlist, W.ctrl + kRcTouched};
   const int n_blk = (P.m + 31) / 32;
-  for (int it0 = 0; warp_global + (long long)it0 * n_warps < n_blk; it0 += 32) {
+  if (first) rows_first_round<R, G>(P, W, S, warp_global, n_warps, my_nnz, my_rows);
+  for (int it0 = 0; !first && warp_global + (long long)it0 * n_warps < n_blk; it0 += 32) {
     const long long bl = warp_global + (long long)(it0 + lane) * n_warps;
     unsigned word = 0u;
     if (bl < n_blk) {
-      word = first ? kFullMask : __ldcg(W.bits + bl);                 // bits are set by L2 atomics: bypass L1
+      word = __ldcg(W.bits + bl);                                     // bits are set by L2 atomics: bypass L1
       if (P.m - (int)bl * 32 < 32) word &= (1u << (P.m - (int)bl * 32)) - 1u;
-      if (!first && word) atomicAnd(W.bits + bl, ~word);
+      if (word) atomicAnd(W.bits + bl, ~word);
     }
-    unsigned dm = __ballot_sync(kFullMask, word != 0u);
+    // Blocks with at least half of their rows due are taken as they lie (their entries are staged in one burst).  The
+    // due rows of all other blocks of the 32 are laid end to end over the lanes, 32 at a time: in a late round (a few
+    // due rows in every block) the warp makes one trip per 32 DUE rows instead of one per block with a due row.  A
+    // row's evaluation does not depend on its lane, so the result is the same bit for bit.
+    const int pc = __popc(word);
+    const bool dense = pc >= 16;
+    unsigned dm = __ballot_sync(kFullMask, dense);
     while (dm) {
       const int k = __ffs(dm) - 1;
       dm &= dm - 1;
@@ -117,7 +177,33 @@ __device__ __forceinline__ void rows_of_phase(const LinDev &P, const RoundsWs &W
       if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
       const int32_t *gcol; const double *gval;
       stage_block(P, S, lane, is_due, h, gcol, gval);
-      eval_resident<R, kRoundsGathers>(P, rd, sink, S, lane, is_due, h, false, gcol, gval);
+      eval_resident<R, G>(P, rd, sink, S, lane, is_due, h, false, gcol, gval);
+    }
+    int incl = dense ? 0 : pc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(kFullMask, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(kFullMask, incl, 31);
+    const int excl = incl - (dense ? 0 : pc);
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      const int e = c0 + lane;
+      int k = 0;                                   // the block of due row e: first lane whose inclusive count exceeds e
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(kFullMask, incl, k + step - 1);
+        if (v <= e) k += step;
+      }
+      const unsigned wk = __shfl_sync(kFullMask, word, k);
+      const int ek = e - __shfl_sync(kFullMask, excl, k);
+      const bool on = e < total;
+      int row = -1;
+      if (on) row = (warp_global + (it0 + k) * n_warps) * 32 + (int)__fns(wk, 0u, ek + 1);
+      const RowHead h = load_head(P, row);
+      const bool is_due = on && h.cnt >= 0;
+      if (is_due) { my_nnz += (unsigned long long)h.cnt; ++my_rows; }
+      eval_resident<R, G>(P, rd, sink, S, lane, is_due, h, false, P.colx + h.beg, P.val + h.beg);
     }
   }
   drain_queue<R>(P, rd, sink, S, lane);
@@ -150,8 +236,8 @@ __global__ void rounds_init_kernel(LinDev P, RoundsWs W, const double *lb_io, co
   if (bad) { W.ctrl[kRcVerdict] = 1 /* MNTR_INFEAS_BOUNDS */; W.ctrl[kRcStop] = 1; }
 }
 
-template <class R>
-__global__ void __launch_bounds__(kRoundsThreads, kRoundsGathers > 4 ? 2 : 4)
+template <class R, int G>
+__global__ void __launch_bounds__(kRoundsThreads, G > 4 ? 2 : 4)
 rounds_rows_kernel(LinDev P, RoundsWs W, int first)
 {
   if (loop_stopped(W.ctrl)) return;
@@ -162,7 +248,7 @@ rounds_rows_kernel(LinDev P, RoundsWs W, int first)
   StreamStage &S = reinterpret_cast<StreamStage *>(smem_raw)[threadIdx.x >> 5];
   if (lane == 0) { S.tcount = 0; S.pad_[0] = 0; S.pad_[1] = 0; }
   __syncwarp();
-  rows_of_phase<R>(P, W, S, tid >> 5, nthreads >> 5, first != 0, my_nnz, my_rows);
+  rows_of_phase<R, G>(P, W, S, tid >> 5, nthreads >> 5, first != 0, my_nnz, my_rows);
   __shared__ unsigned long long s_nnz, s_rows;
   if (threadIdx.x == 0) { s_nnz = 0ull; s_rows = 0ull; }
   __syncthreads();
@@ -454,17 +540,30 @@ int grid_for(long long items, int sm_count)
   return blocks < 1 ? 1 : (int)blocks;
 }
 
+template <class R, int G>
+cudaError_t rows_rg(const LinDev &P, const RoundsWs &W, int first, int sm_count, cudaStream_t s)
+{
+  // a persistent grid, as many blocks as stay resident: a warp takes its 32-row blocks one after the other, the queue
+  // of exact candidates is drained when it is full (not once per short-lived block), and the kernel has ONE tail
+  const int per_sm = G > 4 ? 2 : 4;
+  long long blocks = ((long long)((P.m + 31) / 32) * 32 + kRoundsThreads - 1) / kRoundsThreads;      // one warp per 32-row block
+  if (blocks > (long long)sm_count * per_sm) blocks = (long long)sm_count * per_sm;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = sizeof(StreamStage) * (kRoundsThreads / 32);
+  auto kern = rounds_rows_kernel<R, G>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<(int)blocks, kRoundsThreads, smem, s>>>(P, W, first);
+  return cudaGetLastError();
+}
+
 template <class R>
 cudaError_t rows_r(const LinDev &P, const RoundsWs &W, int first, int sm_count, cudaStream_t s)
 {
   if (P.m <= 0 && P.cut_cnt <= 0) return cudaSuccess;
-  const int blocks = grid_for((long long)((P.m + 31) / 32) * 32, sm_count);      // one warp per 32-row block
-  const size_t smem = sizeof(StreamStage) * (kRoundsThreads / 32);
-  auto kern = rounds_rows_kernel<R>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<blocks, kRoundsThreads, smem, s>>>(P, W, first);
-  return cudaGetLastError();
+  static const int g = getenv("MNTR_K5_G") ? atoi(getenv("MNTR_K5_G")) : kRoundsGathers;      // (experiments)
+  if (g == 4) return rows_rg<R, 4>(P, W, first, sm_count, s);
+  return rows_rg<R, kRoundsGathers>(P, W, first, sm_count, s);
 }
 
 }  // namespace

@@ -1014,9 +1014,14 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
   const int round = ctx->h_ctrl[kRcRound], verd = ctx->h_ctrl[kRcVerdict];
   if (p2p) ctx->p2p_tag += (unsigned)round;
   double rows_ms = 0, comm_ms = 0, vars_ms = 0;
+  static const bool trace_rounds = getenv("MNTR_GPU_TRACE_ROUNDS") != nullptr;
   for (int r = 0; r < round && r < kTimed; ++r) {
     cudaEvent_t *ev = &ctx->round_ev[(size_t)(4 * r)];
     rows_ms += elapsed(ev[0], ev[1]); comm_ms += elapsed(ev[1], ev[2]); vars_ms += elapsed(ev[2], ev[3]);
+    if (trace_rounds)
+      fprintf(stderr, "[mntr rounds] rank %d round %d: rows %.4f ms, merge %.4f ms, vars %.4f ms, gap to next %.4f ms\n", ctx->rank,
+              r + 1, elapsed(ev[0], ev[1]), elapsed(ev[1], ev[2]), elapsed(ev[2], ev[3]),
+              r + 1 < round && r + 1 < kTimed ? elapsed(ev[3], ev[4]) : 0.0);
   }
   if (verdict) *verdict = verd;
   if (rounds) *rounds = round;

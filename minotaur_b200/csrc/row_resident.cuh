@@ -322,7 +322,7 @@ __device__ __forceinline__ void eval_resident(const LinDev &P, const ReadPending
         queued = true;
       }
     }
-    if (total > 0 && !queued) {
+    if constexpr (Stage::kSlab) if (total > 0 && !queued) {
       int pos = incl - mine_n;
       for (unsigned nd = need; nd; nd &= nd - 1) S.work_list()[pos++] = (uint16_t)(lane | ((__ffs(nd) - 1) << 5));
       __syncwarp();

@@ -21,7 +21,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(src.splitlines()))
 h = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
 if h:
-    hdr = rows[h[0]]; data = rows[h[0] + 1:]
+    hdr = rows[h[0]]; data = [r for r in rows[h[0] + 1:(h[1] if len(h) > 1 else len(rows))] if len(r) == len(hdr)]
     si = hdr.index("# Samples"); so = hdr.index("Source"); ie = hdr.index("Instructions Executed")
     tot = sum(int(r[si]) for r in data if len(r) > si and r[si].isdigit())
     toti = sum(int(r[ie]) for r in data if len(r) > ie and r[ie].isdigit())
