@@ -897,8 +897,11 @@ static int p2p_setup(mntr_gpu_ctx *ctx)
 // enqueues a round as soon as the round before the previous one has reported, polling the progress words without ever
 // synchronising the stream.  Per-round work is proportional to the CHANGES (touched lists), not to n.
 static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, const mntr_gpu_options &o,
-                          int32_t *verdict, int32_t *rounds, int64_t *nnz_updates)
+                          int32_t *verdict, int32_t *rounds, int64_t *nnz_updates, double *lb_out = nullptr, double *ub_out = nullptr)
 {
+  // lb_out / ub_out: where the bounds that moved are written (default: in place)
+  if (!lb_out) lb_out = lb_dev;
+  if (!ub_out) ub_out = ub_dev;
   const LinDev &P = ctx->lin;
   const bool directed = o.rounding == MNTR_ROUND_DIRECTED;
   NcclApi &nc = nccl_api();
@@ -1002,7 +1005,7 @@ static int run_rounds_dev(mntr_gpu_ctx *ctx, double *lb_dev, double *ub_dev, con
       stop = prog[1];
     }
   }
-  CU(launch_rounds_finish(P, W, lb_dev, ub_dev, ctx->sm_count, s));
+  CU(launch_rounds_finish(P, W, lb_out, ub_out, ctx->sm_count, s));
   CU(cudaMemcpyAsync(ctx->h_ctrl, W.ctrl, 128, cudaMemcpyDeviceToHost, s));
   unsigned long long cnt[2];
   if (ctx->comm) {     // nnz-updates / rows are per rank: sum them so every rank reports the job total
@@ -1050,9 +1053,18 @@ static int tighten_single(mntr_gpu_ctx *ctx, double *lb, double *ub, const mntr_
 {
   const size_t bytes = sizeof(double) * (size_t)ctx->n;
   int rc;
-  if (!use_rounds(ctx, o) && !ctx->no_zero_copy) {
+  if (!ctx->no_zero_copy) {
     double *lb_map = mapped_host_ptr(lb), *ub_map = mapped_host_ptr(ub);
-    if (lb_map && ub_map) return tighten_single_zero_copy(ctx, lb_map, ub_map, o, verdict, rounds, nnz_updates);
+    if (lb_map && ub_map && !use_rounds(ctx, o)) return tighten_single_zero_copy(ctx, lb_map, ub_map, o, verdict, rounds, nnz_updates);
+    if (lb_map && ub_map) {
+      // per-round kernels on a page-locked, mapped box: the box comes in with the copy engine (55 GB/s; a kernel reading
+      // mapped memory gets 42), the finish kernel writes only the bounds that moved straight back to the host box
+      CU(cudaMemcpyAsync(ctx->d_lb, lb, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->d_ub, ub, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      if ((rc = run_rounds_dev(ctx, ctx->d_lb, ctx->d_ub, o, verdict, rounds, nnz_updates, lb_map, ub_map))) return rc;
+      ctx->stats.kernel_ms += ctx->stats.rows_ms + ctx->stats.comm_ms + ctx->stats.vars_ms;
+      return MNTR_OK;
+    }
   }
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_lb, lb, bytes, cudaMemcpyHostToDevice, ctx->stream));
