@@ -50,12 +50,12 @@ def test_product_never_imports_oracle():
 
 
 def test_reference_side_patch_applies_and_compiles():
-    """minotaur_b200/handler/strong_brancher_prefetch.patch (all strong-branching candidates of a node in
-    one device call) applies to the reference's StrongBrancher.cpp as it is and compiles against the reference's headers
+    """minotaur_b200/handler/{strong,weak}_brancher_prefetch.patch (all strong-branching candidates of a node
+    in one device call) apply to the reference's StrongBrancher.cpp / WeakBrancher.cpp as they are and compiles against the reference's headers
     and GpuBoundHandler.h.  Only where the reference tree is present."""
     import subprocess
     if not os.path.exists("/root/reference/src/base/StrongBrancher.cpp"):
         pytest.skip("reference sources not present")
     res = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "patch_check"], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "applies" in res.stdout
+    assert "strong_brancher_prefetch.patch applies" in res.stdout and "weak_brancher_prefetch.patch applies" in res.stdout
