@@ -768,6 +768,8 @@ def block_c3(X):
     deltas = branch_deltas(inst.lb, inst.ub, inst.var_type, args.c3_boxes, seed=C3["seed"], max_depth=C3_DEPTH)
     out, port = node_batch(X, "C3", inst, None, deltas, X.E.LOOP_FIXPOINT, 0, WORKLOAD_C3)
     traffic, tsrc = static_traffic("fbbt_batch_reference_kernel_c3_dram_bytes_per_launch")
+    if X.world > 1 or args.c3_boxes != C3_BOXES:
+        traffic = None                    # the capture is of the whole batch on one GPU
     out["roofline"]["traffic"] = traffic
     out["roofline"]["traffic_source"] = f"static, from the committed ncu capture ({tsrc}); not measured in this run"
     if X.world > 1:

@@ -17,6 +17,15 @@ for vals in rows[2:]:
     for w in want:
         if w in hdr:
             i = hdr.index(w); print(f"  {w:70s} {vals[i]:>18s} {units[i]}")
+    # warps stalled per issue-active cycle, by reason
+    st = []
+    for i, h in enumerate(hdr):
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") or \
+           h.startswith("smsp__average_warp_latency_issue_stalled_") and h.endswith(".ratio"):
+            try: st.append((float(vals[i]), h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "").replace(".ratio", "")))
+            except ValueError: pass
+    st.sort(reverse=True)
+    if st: print("  stalled warps per issue-active cycle: " + ", ".join(f"{n} {v:.2f}" for v, n in st[:8]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 h = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
