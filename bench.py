@@ -416,7 +416,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        # (launched without torchrun, --gpus still names the configuration the arm is compared on)
+        run_reference_arm(args, rank, world if world > 1 else max(1, args.gpus))
         return
 
     # stdout carries ONE JSON line: whatever libraries print there meanwhile (NCCL's version banner ...) goes to stderr
