@@ -281,6 +281,23 @@ int mntr_gpu_root_dup_rows(mntr_gpu_ctx *ctx, const double *r1, const double *r2
 int mntr_gpu_root_redundant_rows(mntr_gpu_ctx *ctx, const double *lb, const double *ub, uint8_t *redundant,
                                  int64_t *n_redundant);
 
+/* LinearHandler::coeffImp_ (LinearHandler.cpp:600-704) with its implications computeImpBounds_ (:707-783), for the
+ * problem given here in the caller's row order (CSR as in mntr_gpu_load_linear; no problem needs to be loaded) on the box
+ * (lb, ub).  For every one-sided row with at least two terms the first binary (Binary / ImplBin, not fixed) whose
+ * coefficient the reference would improve is reported: out_row, out_var, out_coef = the NEW coefficient (0: the term
+ * is erased, LinearFunction::incTerm :133-142), out_side = which row bound moves with it (0 none, 1 lower, 2 upper)
+ * and out_bnd its new value; sorted by row.  The reference's pass is sequential through the 2-term rows its
+ * implications read (a row sees the improved version of those before it): rows run in dependency levels
+ * (*n_levels_out launches), so the result is the reference's, bit for bit.  Applying the changes (incTerm,
+ * changeBound, bFlags) mutates Minotaur's object graph and stays with the caller.  *n_erased_out counts improvements
+ * that erased a term: the set of 2-term rows changed under the pass, the caller re-runs after applying them.
+ * *n_out may exceed cap. */
+int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col,
+                            const double *val, const double *row_lb, const double *row_ub, const uint8_t *var_type,
+                            const double *lb, const double *ub, int64_t cap, int32_t *out_row, int32_t *out_var,
+                            double *out_coef, int32_t *out_side, double *out_bnd, int64_t *n_out, int32_t *n_levels_out,
+                            int32_t *n_erased_out);
+
 /* statistics of the last tighten call */
 int mntr_gpu_get_stats(const mntr_gpu_ctx *ctx, mntr_gpu_stats *out);
 

@@ -93,4 +93,22 @@ cudaError_t launch_dup_pairs(int m, const double *h1, const double *h2, long lon
 cudaError_t launch_redundant_rows(const LinDev &P, const int32_t *perm, const double *lb, const double *ub, uint8_t *flag,
                                   unsigned long long *count, cudaStream_t stream);
 
+
+// LinearHandler::coeffImp_ (LinearHandler.cpp:600-704) for the rows of one dependency level (root_rows.cu).  Rows are in
+// the CALLER's order (the pass is sequential in row index: a row's implications read 2-term rows, and see the improved
+// version of those with a smaller index, the original of the others).
+struct CoeffProb {
+  int32_t m, n;
+  const int32_t *row_ptr, *col;
+  const double *val0, *rlb0, *rub0;     // the problem as it came
+  double *val, *rlb, *rub;              // ... as the pass has changed it so far
+  const uint8_t *var_type;
+  const double *lb, *ub;
+  const int32_t *cptr, *crow;           // rows of a variable
+  const uint8_t *is2;                   // the row has exactly two terms
+};
+cudaError_t launch_coeff_imp(const CoeffProb &Q, const int32_t *rows, int32_t n_rows, long long cap, int32_t *out_row,
+                             int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd,
+                             unsigned long long *count, int32_t *n_erased, cudaStream_t stream);
+
 }  // namespace mntr

@@ -1514,6 +1514,142 @@ int mntr_gpu_root_redundant_rows(mntr_gpu_ctx *ctx, const double *lb, const doub
   return MNTR_OK;
 }
 
+// LinearHandler::coeffImp_ on the device.  The pass is sequential in row index only through the 2-term rows that the
+// implications (computeImpBounds_) read: a row sees the improved version of those with a smaller index.  Rows are
+// therefore scheduled in dependency levels (level = 1 + the highest level of an earlier 2-term row the row's
+// implications can read), one launch per level, one thread per row; a level reads the coefficients and row bounds as
+// the lower levels left them.
+int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col,
+                            const double *val, const double *row_lb, const double *row_ub, const uint8_t *var_type,
+                            const double *lb, const double *ub, int64_t cap, int32_t *out_row, int32_t *out_var,
+                            double *out_coef, int32_t *out_side, double *out_bnd, int64_t *n_out, int32_t *n_levels_out,
+                            int32_t *n_erased_out)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (m < 0 || n < 0 || !row_ptr || !n_out || cap < 0) return fail(ctx, MNTR_E_ARG, "root_coeff_imp: bad argument");
+  if (cap > 0 && (!out_row || !out_var || !out_coef || !out_side || !out_bnd)) return fail(ctx, MNTR_E_ARG, "root_coeff_imp: null output");
+  *n_out = 0;
+  if (n_levels_out) *n_levels_out = 0;
+  if (n_erased_out) *n_erased_out = 0;
+  if (m == 0) return MNTR_OK;
+  if (!col || !val || !row_lb || !row_ub || !var_type || !lb || !ub) return fail(ctx, MNTR_E_ARG, "root_coeff_imp: null input");
+  CU(cudaSetDevice(ctx->device));
+  const int64_t nnz = row_ptr[m];
+  auto is_term = [](double a) { return std::fabs(a) > 1e-9; };
+  auto is_bin = [&](int32_t j) { return (var_type[j] == 0 || var_type[j] == 2) && ub[j] > lb[j] + 0.5; };
+  // ---- host: CSC, 2-term rows, candidate rows and their dependency levels ----
+  std::vector<int32_t> cptr((size_t)n + 2, 0), crow((size_t)std::max<int64_t>(nnz, 1)), nterms((size_t)m, 0);
+  for (int32_t i = 0; i < m; ++i)
+    for (int32_t t = row_ptr[i]; t < row_ptr[i + 1]; ++t) {
+      if (col[t] < 0 || col[t] >= n) return fail(ctx, MNTR_E_ARG, "root_coeff_imp: column out of range in row %d", i);
+      cptr[(size_t)col[t] + 2]++;
+      nterms[(size_t)i] += is_term(val[t]);
+    }
+  for (int32_t j = 0; j < n; ++j) cptr[(size_t)j + 2] += cptr[(size_t)j + 1];
+  for (int32_t i = 0; i < m; ++i)
+    for (int32_t t = row_ptr[i]; t < row_ptr[i + 1]; ++t) crow[(size_t)cptr[(size_t)col[t] + 1]++] = i;
+  std::vector<uint8_t> is2((size_t)m, 0);
+  for (int32_t i = 0; i < m; ++i) is2[(size_t)i] = nterms[(size_t)i] == 2;
+  std::vector<int32_t> level((size_t)m, -1);
+  int32_t n_levels = 0;
+  for (int32_t c = 0; c < m; ++c) {
+    if (!(row_lb[c] <= -INFINITY || row_ub[c] >= INFINITY) || nterms[(size_t)c] < 2) continue;     // :620-627
+    bool has_bin = false;
+    int32_t lev = 0;
+    for (int32_t t = row_ptr[c]; t < row_ptr[c + 1]; ++t) {
+      const int32_t z = col[t];
+      if (!is_term(val[t]) || !is_bin(z)) continue;
+      has_bin = true;
+      if (nterms[(size_t)c] >= 50) continue;          // no implications (:625-629)
+      // 2-term rows with z and another variable of c, earlier in the pass
+      for (int32_t q = cptr[(size_t)z]; q < cptr[(size_t)z + 1]; ++q) {
+        const int32_t c2 = crow[(size_t)q];
+        if (c2 >= c) break;                           // (rows of a variable ascend)
+        if (!is2[(size_t)c2] || level[(size_t)c2] < 0) continue;      // never improved: reads as it came
+        int32_t other = -1;
+        for (int32_t t2 = row_ptr[c2]; t2 < row_ptr[c2 + 1]; ++t2) if (is_term(val[t2]) && col[t2] != z) other = col[t2];
+        if (other < 0) continue;
+        const int32_t *b = col + row_ptr[c], *e = col + row_ptr[c + 1];
+        if (std::find(b, e, other) != e) lev = std::max(lev, level[(size_t)c2] + 1);
+      }
+    }
+    if (!has_bin) continue;
+    level[(size_t)c] = lev;
+    n_levels = std::max(n_levels, lev + 1);
+  }
+  std::vector<int32_t> lptr((size_t)n_levels + 1, 0), lrows;
+  for (int32_t c = 0; c < m; ++c) if (level[(size_t)c] >= 0) lptr[(size_t)level[(size_t)c] + 1]++;
+  for (int32_t l = 0; l < n_levels; ++l) lptr[(size_t)l + 1] += lptr[(size_t)l];
+  lrows.resize((size_t)std::max(lptr[(size_t)n_levels], 1));
+  {
+    std::vector<int32_t> pos(lptr.begin(), lptr.end());
+    for (int32_t c = 0; c < m; ++c) if (level[(size_t)c] >= 0) lrows[(size_t)pos[(size_t)level[(size_t)c]]++] = c;
+  }
+  if (n_levels_out) *n_levels_out = n_levels;
+  if (n_levels == 0) return MNTR_OK;
+  // ---- device ----
+  std::vector<void *> owned;
+  struct Free { std::vector<void *> &v; ~Free() { for (void *p : v) cudaFree(p); } } guard{owned};
+  CoeffProb Q{};
+  Q.m = m; Q.n = n;
+  int rc;
+  if ((rc = dev_upload(ctx, owned, row_ptr, (size_t)m + 1, &Q.row_ptr))) return rc;
+  if ((rc = dev_upload(ctx, owned, col, (size_t)nnz, &Q.col))) return rc;
+  if ((rc = dev_upload(ctx, owned, val, (size_t)nnz, &Q.val0))) return rc;
+  if ((rc = dev_upload(ctx, owned, row_lb, (size_t)m, &Q.rlb0))) return rc;
+  if ((rc = dev_upload(ctx, owned, row_ub, (size_t)m, &Q.rub0))) return rc;
+  { const double *p; if ((rc = dev_upload(ctx, owned, val, (size_t)nnz, &p))) return rc; Q.val = const_cast<double *>(p); }
+  { const double *p; if ((rc = dev_upload(ctx, owned, row_lb, (size_t)m, &p))) return rc; Q.rlb = const_cast<double *>(p); }
+  { const double *p; if ((rc = dev_upload(ctx, owned, row_ub, (size_t)m, &p))) return rc; Q.rub = const_cast<double *>(p); }
+  if ((rc = dev_upload(ctx, owned, var_type, (size_t)n, &Q.var_type))) return rc;
+  if ((rc = dev_upload(ctx, owned, lb, (size_t)n, &Q.lb))) return rc;
+  if ((rc = dev_upload(ctx, owned, ub, (size_t)n, &Q.ub))) return rc;
+  if ((rc = dev_upload(ctx, owned, cptr.data(), (size_t)n + 1, &Q.cptr))) return rc;
+  if ((rc = dev_upload(ctx, owned, crow.data(), (size_t)nnz, &Q.crow))) return rc;
+  if ((rc = dev_upload(ctx, owned, is2.data(), (size_t)m, &Q.is2))) return rc;
+  const int32_t *d_rows;
+  if ((rc = dev_upload(ctx, owned, lrows.data(), lrows.size(), &d_rows))) return rc;
+  const size_t capz = (size_t)std::max<int64_t>(cap, 1);
+  int32_t *d_orow, *d_ovar, *d_oside, *d_erased; double *d_ocoef, *d_obnd; unsigned long long *d_cnt;
+  auto dalloc = [&](void **p, size_t bytes) -> int { CU(cudaMalloc(p, std::max<size_t>(bytes, 16))); owned.push_back(*p); return MNTR_OK; };
+  if ((rc = dalloc((void **)&d_orow, 4 * capz)) || (rc = dalloc((void **)&d_ovar, 4 * capz)) || (rc = dalloc((void **)&d_oside, 4 * capz)) ||
+      (rc = dalloc((void **)&d_ocoef, 8 * capz)) || (rc = dalloc((void **)&d_obnd, 8 * capz)) || (rc = dalloc((void **)&d_cnt, 16)) ||
+      (rc = dalloc((void **)&d_erased, 16))) return rc;
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemsetAsync(d_cnt, 0, 16, s));
+  CU(cudaMemsetAsync(d_erased, 0, 16, s));
+  CU(cudaEventRecord(ctx->ev[1], s));
+  for (int32_t l = 0; l < n_levels; ++l)
+    CU(launch_coeff_imp(Q, d_rows + lptr[(size_t)l], lptr[(size_t)l + 1] - lptr[(size_t)l], (long long)cap, d_orow, d_ovar, d_ocoef,
+                        d_oside, d_obnd, d_cnt, d_erased, s));
+  CU(cudaEventRecord(ctx->ev[2], s));
+  unsigned long long cnt = 0; int32_t erased = 0;
+  CU(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(&erased, d_erased, sizeof(erased), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  const size_t k = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)cap);
+  if (k) {
+    std::vector<int32_t> r(k), v(k), sd(k); std::vector<double> cf(k), bd(k);
+    CU(cudaMemcpyAsync(r.data(), d_orow, 4 * k, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(v.data(), d_ovar, 4 * k, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(sd.data(), d_oside, 4 * k, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(cf.data(), d_ocoef, 8 * k, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(bd.data(), d_obnd, 8 * k, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    std::vector<size_t> ord(k);
+    for (size_t i = 0; i < k; ++i) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return r[a] < r[b]; });      // the reference's order: by row
+    for (size_t i = 0; i < k; ++i) {
+      out_row[i] = r[ord[i]]; out_var[i] = v[ord[i]]; out_coef[i] = cf[ord[i]]; out_side[i] = sd[ord[i]]; out_bnd[i] = bd[ord[i]];
+    }
+  }
+  *n_out = (int64_t)cnt;
+  if (n_erased_out) *n_erased_out = erased;
+  ctx->stats = mntr_gpu_stats{};
+  ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  return MNTR_OK;
+}
+
 void *mntr_gpu_alloc_host(mntr_gpu_ctx *ctx, int64_t bytes)
 {
   if (!ctx || bytes <= 0) return nullptr;

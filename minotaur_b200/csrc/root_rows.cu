@@ -106,6 +106,119 @@ __global__ void redundant_rows_kernel(LinDev P, const int32_t *__restrict__ perm
   if (f) atomicAdd(count, 1ull);
 }
 
+
+// ---- LinearHandler::coeffImp_ (LinearHandler.cpp:600-704) + computeImpBounds_ (:707-783) -----------------------
+// One thread per row of the level: the row's work is the reference's, term by term in variable order, the first
+// binary that can be improved ends the row.  Terms with |a| <= 1e-9 do not exist (LinearFunction::addTerm :89-95).
+constexpr int kImplicTerms = 50;       // rows with fewer terms use the implications (:625-629)
+__device__ __forceinline__ bool ci_term(double a) { return fabs(a) > 1e-9; }
+
+// weights of z and v in the 2-term row c2 (0: absent); the version of c2 the row c may see
+__device__ __forceinline__ void ci_pair(const CoeffProb &Q, int c, int c2, int z, int v, double &b2, double &a2, double &clb, double &cub)
+{
+  const bool cur = c2 < c;             // improved earlier in the pass: its current state; else as it came
+  const double *V = cur ? Q.val : Q.val0;
+  b2 = 0.0; a2 = 0.0;
+  for (int t = Q.row_ptr[c2]; t < Q.row_ptr[c2 + 1]; ++t) {
+    const double a = V[t];
+    if (!ci_term(a)) continue;
+    const int j = Q.col[t];
+    if (j == z) b2 = a; else if (j == v) a2 = a;
+  }
+  clb = cur ? Q.rlb[c2] : Q.rlb0[c2];
+  cub = cur ? Q.rub[c2] : Q.rub0[c2];
+}
+
+// computeImpBounds_: activity of row c with z at zval and every other variable tightened by the 2-term rows it shares
+// with z; then LinearFunction::computeBounds (LinearFunction.cpp:178-195)
+__device__ void ci_imp_bounds(const CoeffProb &Q, int c, int z, double zval, double &out_l, double &out_u)
+{
+  double lo = 0.0, up = 0.0;
+  for (int t = Q.row_ptr[c]; t < Q.row_ptr[c + 1]; ++t) {
+    const double a = Q.val[t];
+    if (!ci_term(a)) continue;
+    const int v = Q.col[t];
+    double l1 = Q.lb[v], u1 = Q.ub[v];
+    if (v == z) {
+      if (zval < 0.5) u1 = 0.0; else l1 = 1.0;
+    } else {
+      const double vl = l1, vu = u1;
+      for (int q = Q.cptr[v]; q < Q.cptr[v + 1]; ++q) {
+        const int c2 = Q.crow[q];
+        if (!Q.is2[c2]) continue;
+        double b2, a2, clb, cub;
+        ci_pair(Q, c, c2, z, v, b2, a2, clb, cub);
+        if (b2 == 0.0 || a2 == 0.0) continue;
+        if (a2 > 0 && (cub - zval * b2) / a2 < u1) u1 = (cub - zval * b2) / a2;
+        if (a2 < 0 && (cub - zval * b2) / a2 > l1) l1 = (cub - zval * b2) / a2;
+        if (a2 > 0 && (clb - zval * b2) / a2 > l1) l1 = (clb - zval * b2) / a2;
+        if (a2 < 0 && (clb - zval * b2) / a2 < u1) u1 = (clb - zval * b2) / a2;
+      }
+      if (!(l1 > vl)) l1 = vl;
+      if (!(u1 < vu)) u1 = vu;
+    }
+    if (a > 0) { lo += a * l1; up += a * u1; }
+    else       { lo += a * u1; up += a * l1; }
+  }
+  out_l = lo; out_u = up;
+}
+
+__global__ void coeff_imp_kernel(CoeffProb Q, const int32_t *rows, int32_t n_rows, long long cap, int32_t *out_row,
+                                 int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd,
+                                 unsigned long long *count, int32_t *n_erased)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int c = rows[i];
+  const double coeftol = 1e-4, bslack = 1e-4;
+  const double lb = Q.rlb[c], ub = Q.rub[c];
+  int nt = 0;
+  double ll = 0.0, uu = 0.0;                        // getLfBnds_ :1237-1258
+  for (int t = Q.row_ptr[c]; t < Q.row_ptr[c + 1]; ++t) {
+    const double a = Q.val[t];
+    if (!ci_term(a)) continue;
+    ++nt;
+    const int j = Q.col[t];
+    if (a > 0) { ll += a * Q.lb[j]; uu += a * Q.ub[j]; }
+    else       { ll += a * Q.ub[j]; uu += a * Q.lb[j]; }
+  }
+  if (nt < 2) return;
+  const bool implic = nt < kImplicTerms;
+  for (int t = Q.row_ptr[c]; t < Q.row_ptr[c + 1]; ++t) {
+    const double a0 = Q.val[t];
+    if (!ci_term(a0)) continue;
+    const int v = Q.col[t];
+    const int ty = Q.var_type[v];
+    if (!((ty == 0 || ty == 2) && Q.ub[v] > Q.lb[v] + 0.5)) continue;      // Binary / ImplBin, not fixed (:635-637)
+    double delta = 0.0, nb = 0.0;
+    int side = 0;
+    bool hit = false;
+    if (implic) {
+      ci_imp_bounds(Q, c, v, 1.0, ll, uu);
+      ll -= bslack; uu += bslack;
+      if (a0 > 0) ll -= a0; else uu -= a0;
+    }
+    if (uu + a0 < ub - coeftol && uu >= ub) { delta = ub - uu - a0; hit = true; }
+    else if (ll + a0 > lb + coeftol && ll <= lb) { delta = lb - ll - a0; hit = true; }
+    if (!hit) {
+      if (implic) {
+        ci_imp_bounds(Q, c, v, 0.0, ll, uu);
+        if (a0 > 0) uu += a0; else ll += a0;
+      }
+      if (uu - a0 < ub - coeftol && uu >= ub) { delta = uu - a0 - ub; side = 2; nb = uu - a0; hit = true; }
+      else if (ll - a0 > lb + coeftol && ll <= lb) { delta = ll - a0 - lb; side = 1; nb = ll - a0; hit = true; }
+    }
+    if (!hit) continue;
+    double nv = a0;                                  // LinearFunction::incTerm :133-142
+    if (fabs(delta) > 1e-9) { nv = a0 + delta; if (fabs(nv) < 1e-9) { nv = 0.0; atomicAdd(n_erased, 1); } }
+    Q.val[t] = nv;
+    if (side == 2) Q.rub[c] = nb; else if (side == 1) Q.rlb[c] = nb;
+    const unsigned long long k = atomicAdd(count, 1ull);
+    if ((long long)k < cap) { out_row[k] = c; out_var[k] = v; out_coef[k] = nv; out_side[k] = side; out_bnd[k] = nb; }
+    return;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_row_hash(const LinDev &P, const int32_t *perm, const double *r1, const double *r2, double *h1, double *h2,
@@ -129,6 +242,16 @@ cudaError_t launch_redundant_rows(const LinDev &P, const int32_t *perm, const do
 {
   if (P.m <= 0) return cudaSuccess;
   redundant_rows_kernel<<<(P.m + 255) / 256, 256, 0, stream>>>(P, perm, lb, ub, flag, count);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_coeff_imp(const CoeffProb &Q, const int32_t *rows, int32_t n_rows, long long cap, int32_t *out_row,
+                             int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd,
+                             unsigned long long *count, int32_t *n_erased, cudaStream_t stream)
+{
+  if (n_rows <= 0) return cudaSuccess;
+  coeff_imp_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(Q, rows, n_rows, cap, out_row, out_var, out_coef, out_side, out_bnd,
+                                                             count, n_erased);
   return cudaGetLastError();
 }
 

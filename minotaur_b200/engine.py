@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "mntr_gpu_tighten_single_dev", "mntr_gpu_stream",
     "mntr_gpu_nccl_unique_id", "mntr_gpu_comm_init", "mntr_gpu_comm_destroy",
     "mntr_gpu_boxes_from_deltas", "mntr_gpu_alloc_host", "mntr_gpu_free_host", "mntr_gpu_update_row_bounds",
-    "mntr_gpu_load_quad", "mntr_gpu_group_load_quad", "mntr_gpu_root_dup_rows", "mntr_gpu_root_redundant_rows",
+    "mntr_gpu_load_quad", "mntr_gpu_group_load_quad", "mntr_gpu_root_dup_rows", "mntr_gpu_root_redundant_rows", "mntr_gpu_root_coeff_imp",
     "mntr_gpu_group_create", "mntr_gpu_group_destroy", "mntr_gpu_group_size", "mntr_gpu_group_member",
     "mntr_gpu_group_last_error", "mntr_gpu_group_load_linear", "mntr_gpu_group_load_cgraph",
     "mntr_gpu_group_set_cutoff", "mntr_gpu_group_set_incumbent", "mntr_gpu_group_tighten_nodes",
@@ -110,6 +110,8 @@ def load_library() -> C.CDLL:
     L.mntr_gpu_load_quad.argtypes = [vp, C.c_int32, _ip, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp]
     L.mntr_gpu_root_dup_rows.argtypes = [vp, _dp, _dp, _dp, _dp, C.c_int64, _ip, _ip, _bp, _lp]
     L.mntr_gpu_root_redundant_rows.argtypes = [vp, _dp, _dp, _bp, _lp]
+    L.mntr_gpu_root_coeff_imp.argtypes = [vp, C.c_int32, C.c_int32, _ip, _ip, _dp, _dp, _dp, _bp, _dp, _dp, C.c_int64, _ip, _ip, _dp,
+                                          _ip, _dp, _lp, _ip, _ip]
     L.mntr_gpu_group_load_quad.argtypes = [vp, C.c_int32, _ip, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp]
     L.mntr_gpu_alloc_host.argtypes = [vp, C.c_int64]
     L.mntr_gpu_alloc_host.restype = vp
@@ -273,6 +275,25 @@ class GpuBoundEngine:
         out = np.zeros(max(self.m, 1), np.uint8); cnt = C.c_int64(0)
         self._check(self.L.mntr_gpu_root_redundant_rows(self.h, _d(lb), _d(ub), _b(out), C.byref(cnt)), "root_redundant_rows")
         return out[:self.m].astype(bool)
+
+    def root_coeff_imp(self, inst, lb, ub, cap=1 << 20):
+        """LinearHandler::coeffImp_ (LinearHandler.cpp:600-704) on the device for the rows of ``inst`` (caller's order; nothing
+        needs to be loaded): (row, var, new coefficient, side, new row bound) arrays sorted by row, plus
+        {'levels', 'erased', 'kernel_ms'}."""
+        rp = np.ascontiguousarray(inst.row_ptr, np.int32); col = np.ascontiguousarray(inst.col, np.int32)
+        val = np.ascontiguousarray(inst.val, np.float64)
+        rl = np.ascontiguousarray(inst.row_lb, np.float64); ru = np.ascontiguousarray(inst.row_ub, np.float64)
+        vt = np.ascontiguousarray(inst.var_type, np.uint8)
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        row = np.zeros(max(cap, 1), np.int32); var = np.zeros(max(cap, 1), np.int32); coef = np.zeros(max(cap, 1))
+        side = np.zeros(max(cap, 1), np.int32); bnd = np.zeros(max(cap, 1))
+        cnt = C.c_int64(0); lev = C.c_int32(0); er = C.c_int32(0)
+        self._check(self.L.mntr_gpu_root_coeff_imp(self.h, inst.m, inst.n, _i(rp), _i(col), _d(val), _d(rl), _d(ru), _b(vt), _d(lb),
+                                                   _d(ub), cap, _i(row), _i(var), _d(coef), _i(side), _d(bnd), C.byref(cnt),
+                                                   C.byref(lev), C.byref(er)), "root_coeff_imp")
+        k = min(int(cnt.value), cap)
+        info = {"levels": int(lev.value), "erased": int(er.value), "count": int(cnt.value), "kernel_ms": self.stats().kernel_ms}
+        return row[:k], var[:k], coef[:k], side[:k], bnd[:k], info
 
     def update_row_bounds(self, row_lb, row_ub):
         """New bounds for the loaded rows (same order as load_linear): m doubles each way, no re-flattening."""

@@ -753,3 +753,63 @@ def plant_duplicate_rows(inst: LinearRows, n_dups: int, seed: int) -> LinearRows
     out.col, out.val, out.row_lb, out.row_ub = col.reshape(-1), val.reshape(-1), rl, ru
     out.name = inst.name + "-dups"
     return out
+
+
+def make_bigm_instance(n_bin: int, n_cont: int, n_rows: int, seed: int) -> LinearRows:
+    """Rows of the kind LinearHandler::coeffImp_ (/root/reference/src/base/LinearHandler.cpp:600-704) improves: variable
+    upper / lower bound rows  x - M z <= 0,  x - m z >= 0  with loose big-M coefficients (2-term rows: the implications
+    computeImpBounds_ reads, :707-783), one-sided rows mixing continuous variables and binaries with big-M style
+    coefficients, and some two-sided rows (never touched).  Variables: binaries first, then continuous in [l, u]."""
+    rng = np.random.default_rng([seed, 31])
+    n = n_bin + n_cont
+    var_type = np.full(n, 4, np.uint8); var_type[:n_bin] = 0
+    if n_bin > 4:
+        var_type[rng.choice(n_bin, n_bin // 8, replace=False)] = 2          # some ImplBin
+    lb = np.zeros(n); ub = np.ones(n)
+    lb[n_bin:] = rng.integers(-3, 2, n_cont).astype(np.float64)
+    ub[n_bin:] = lb[n_bin:] + rng.integers(1, 12, n_cont)
+    if n_bin > 6:
+        fixed = rng.choice(n_bin, n_bin // 10, replace=False)               # some binaries fixed (skipped by :637)
+        lb[fixed] = ub[fixed] = rng.integers(0, 2, len(fixed))
+    rows = []
+    # variable bound rows
+    for j in range(n_bin, n):
+        if rng.random() < 0.6:
+            z = int(rng.integers(0, n_bin))
+            big = float(ub[j] + rng.integers(0, 6))                          # M >= u, often loose
+            rows.append(([(z, -big), (j, 1.0)], -INF, 0.0))                  # x - M z <= 0
+        if rng.random() < 0.3:
+            z = int(rng.integers(0, n_bin))
+            sm = float(rng.integers(0, 3))
+            rows.append(([(z, -sm), (j, 1.0)], 0.0, INF))                    # x - m z >= 0
+    # mixed one-sided / two-sided rows
+    while len(rows) < n_rows:
+        k = int(rng.integers(2, 9))
+        cols = np.sort(rng.choice(n, k, replace=False))
+        terms = []
+        for c in cols:
+            if c < n_bin:
+                a = float(rng.integers(1, 30)) * (1.0 if rng.random() < 0.5 else -1.0)
+            else:
+                a = float(rng.integers(1, 6)) * (1.0 if rng.random() < 0.6 else -1.0)
+            terms.append((int(c), a))
+        lo = sum(a * (lb[c] if a > 0 else ub[c]) for c, a in terms)
+        hi = sum(a * (ub[c] if a > 0 else lb[c]) for c, a in terms)
+        r = rng.random()
+        if r < 0.45:
+            rows.append((terms, -INF, float(np.floor(lo + (hi - lo) * rng.uniform(0.3, 1.1)))))
+        elif r < 0.9:
+            rows.append((terms, float(np.ceil(lo + (hi - lo) * rng.uniform(-0.1, 0.7))), INF))
+        else:
+            mid = lo + (hi - lo) * 0.5
+            rows.append((terms, float(np.floor(mid - 2)), float(np.ceil(mid + 2))))
+    order = rng.permutation(len(rows))                                       # VUB rows before AND after their users
+    rows = [rows[i] for i in order]
+    row_ptr = [0]; col = []; val = []; rl = []; ru = []
+    for terms, a, b in rows:
+        terms = sorted(terms)
+        col += [t[0] for t in terms]; val += [t[1] for t in terms]
+        row_ptr.append(len(col)); rl.append(a); ru.append(b)
+    return LinearRows(m=len(rows), n=n, row_ptr=np.array(row_ptr, np.int32), col=np.array(col, np.int32),
+                      val=np.array(val, np.float64), row_lb=np.array(rl), row_ub=np.array(ru), var_type=var_type,
+                      lb=lb, ub=ub, name=f"bigm-{seed}")

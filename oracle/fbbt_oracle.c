@@ -997,3 +997,159 @@ int64_t orc_root_redundant_rows(const orc_lin_t *p, const double *lb, const doub
   }
   return k;
 }
+
+
+/* ---- LinearHandler::coeffImp_ (LinearHandler.cpp:600-704) with its implications computeImpBounds_ (:707-783) ----
+ * Sequential, in the reference's order: rows by index, the terms of a row by variable id, the first binary that can
+ * be improved ends the row (`break`).  Works on private copies of the coefficients and row bounds, which it edits as
+ * the reference edits the problem (LinearFunction::incTerm :133-142: a change of at most 1e-9 is ignored, a result
+ * below 1e-9 erases the term; Problem::changeBound on the row), so later rows see earlier improvements through the
+ * 2-term rows their implications read.  Terms with |a| <= 1e-9 do not exist (LinearFunction::addTerm :89-95).
+ * Output per improved row: the row, the variable, the NEW coefficient, which row bound moved (0 none, 1 lower,
+ * 2 upper) and its new value.  Returns the number of improved rows (counted beyond cap too). */
+static int ci_is_term(double a) { return fabs(a) > 1e-9; }
+
+typedef struct {
+  const orc_lin_t *p;
+  double *val, *rlb, *rub;      /* edited copies */
+  const int32_t *cptr, *crow, *cpos;   /* CSC: rows of a variable and the entry's position in the row */
+  double *lb, *ub;              /* variable bounds (edited temporarily by the implications) */
+} ci_state;
+
+static int ci_num_terms(const ci_state *s, int32_t r)
+{
+  int k = 0;
+  for (int32_t t = s->p->row_ptr[r]; t < s->p->row_ptr[r + 1]; ++t) k += ci_is_term(s->val[t]);
+  return k;
+}
+
+/* weight of variable j in row r (0 when absent) */
+static double ci_weight(const ci_state *s, int32_t r, int32_t j)
+{
+  for (int32_t t = s->p->row_ptr[r]; t < s->p->row_ptr[r + 1]; ++t)
+    if (s->p->col[t] == j) return ci_is_term(s->val[t]) ? s->val[t] : 0.0;
+  return 0.0;
+}
+
+static void ci_lf_bounds(const ci_state *s, int32_t r, double *l, double *u)     /* LinearFunction::computeBounds :178-195 */
+{
+  double lo = 0.0, up = 0.0;
+  for (int32_t t = s->p->row_ptr[r]; t < s->p->row_ptr[r + 1]; ++t) {
+    const double a = s->val[t];
+    if (!ci_is_term(a)) continue;
+    const int32_t j = s->p->col[t];
+    if (a > 0) { lo += a * s->lb[j]; up += a * s->ub[j]; }
+    else       { lo += a * s->ub[j]; up += a * s->lb[j]; }
+  }
+  *l = lo; *u = up;
+}
+
+/* computeImpBounds_ :707-783: activity of row c with z fixed at zval and every other variable of the row tightened
+ * by the 2-term rows it shares with z */
+static void ci_imp_bounds(ci_state *s, int32_t c, int32_t z, double zval, double *out_l, double *out_u)
+{
+  const orc_lin_t *p = s->p;
+  const double zl0 = s->lb[z], zu0 = s->ub[z];
+  if (zval < 0.5) s->ub[z] = 0.0; else s->lb[z] = 1.0;
+  /* the other variables: their tightened bounds are applied after each is computed; a variable's implied bounds
+   * depend on its own bounds and on z alone, so the order does not matter */
+  const int32_t b = p->row_ptr[c], e = p->row_ptr[c + 1];
+  double *sl = (double *)malloc(sizeof(double) * (size_t)(e - b + 1)), *su = (double *)malloc(sizeof(double) * (size_t)(e - b + 1));
+  for (int32_t t = b; t < e; ++t) {
+    const int32_t v = p->col[t];
+    sl[t - b] = s->lb[v]; su[t - b] = s->ub[v];
+    if (!ci_is_term(s->val[t]) || v == z) continue;
+    double l1 = s->lb[v], u1 = s->ub[v];
+    for (int32_t q = s->cptr[v]; q < s->cptr[v + 1]; ++q) {
+      const int32_t c2 = s->crow[q];
+      if (p->row_active && !p->row_active[c2]) continue;
+      if (ci_num_terms(s, c2) != 2) continue;
+      const double b2 = ci_weight(s, c2, z);
+      if (b2 == 0.0) continue;                       /* lf2->hasVar(z) */
+      const double a2 = ci_weight(s, c2, v);
+      if (a2 == 0.0) continue;
+      const double cub = s->rub[c2], clb = s->rlb[c2];
+      if (a2 > 0 && (cub - zval * b2) / a2 < u1) u1 = (cub - zval * b2) / a2;
+      if (a2 < 0 && (cub - zval * b2) / a2 > l1) l1 = (cub - zval * b2) / a2;
+      if (a2 > 0 && (clb - zval * b2) / a2 > l1) l1 = (clb - zval * b2) / a2;
+      if (a2 < 0 && (clb - zval * b2) / a2 < u1) u1 = (clb - zval * b2) / a2;
+    }
+    if (l1 > s->lb[v]) s->lb[v] = l1;
+    if (u1 < s->ub[v]) s->ub[v] = u1;
+  }
+  ci_lf_bounds(s, c, out_l, out_u);
+  for (int32_t t = b; t < e; ++t) { s->lb[p->col[t]] = sl[t - b]; s->ub[p->col[t]] = su[t - b]; }
+  s->lb[z] = zl0; s->ub[z] = zu0;
+  free(sl); free(su);
+}
+
+int64_t orc_root_coeff_imp(const orc_lin_t *p, const double *lb_in, const double *ub_in, int64_t cap, int32_t *out_row,
+                           int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd)
+{
+  const int32_t m = p->m, n = p->n;
+  const int64_t nnz = p->row_ptr[m];
+  const double coeftol = 1e-4, bslack = 1e-4;
+  ci_state s;
+  s.p = p;
+  s.val = (double *)malloc(sizeof(double) * (size_t)(nnz + 1));
+  s.rlb = (double *)malloc(sizeof(double) * (size_t)(m + 1)); s.rub = (double *)malloc(sizeof(double) * (size_t)(m + 1));
+  s.lb = (double *)malloc(sizeof(double) * (size_t)(n + 1)); s.ub = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+  memcpy(s.val, p->val, sizeof(double) * (size_t)nnz);
+  memcpy(s.rlb, p->row_lb, sizeof(double) * (size_t)m); memcpy(s.rub, p->row_ub, sizeof(double) * (size_t)m);
+  memcpy(s.lb, lb_in, sizeof(double) * (size_t)n); memcpy(s.ub, ub_in, sizeof(double) * (size_t)n);
+  int32_t *cptr = (int32_t *)calloc((size_t)n + 2, sizeof(int32_t)), *crow = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz + 1)),
+          *cpos = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz + 1));
+  for (int64_t t = 0; t < nnz; ++t) cptr[p->col[t] + 2]++;
+  for (int32_t j = 0; j < n; ++j) cptr[j + 2] += cptr[j + 1];
+  for (int32_t i = 0; i < m; ++i)
+    for (int32_t t = p->row_ptr[i]; t < p->row_ptr[i + 1]; ++t) { const int32_t q = cptr[p->col[t] + 1]++; crow[q] = i; cpos[q] = t; }
+  s.cptr = cptr; s.crow = crow; s.cpos = cpos;
+
+  int64_t k = 0;
+  for (int32_t c = 0; c < m; ++c) {
+    if (p->row_active && !p->row_active[c]) continue;
+    if (!(s.rlb[c] <= -INFINITY || s.rub[c] >= INFINITY)) continue;
+    const int nt = ci_num_terms(&s, c);
+    if (nt < 2) continue;
+    const int implic = nt < 50;
+    const double lb = s.rlb[c], ub = s.rub[c];
+    double ll, uu;
+    ci_lf_bounds(&s, c, &ll, &uu);                  /* getLfBnds_ :1237-1258: the same sums */
+    for (int32_t t = p->row_ptr[c]; t < p->row_ptr[c + 1]; ++t) {
+      const double a0 = s.val[t];
+      if (!ci_is_term(a0)) continue;
+      const int32_t v = p->col[t];
+      const int ty = p->var_type[v];
+      if (!((ty == ORC_BINARY || ty == ORC_IMPLBIN) && s.ub[v] > s.lb[v] + 0.5)) continue;
+      double delta = 0.0, nb = 0.0; int side = 0, hit = 0;
+      if (implic) {
+        ll = uu = 0;
+        ci_imp_bounds(&s, c, v, 1.0, &ll, &uu);
+        ll -= bslack; uu += bslack;
+        if (a0 > 0) ll -= a0; else uu -= a0;
+      }
+      if (uu + a0 < ub - coeftol && uu >= ub) { delta = ub - uu - a0; hit = 1; }
+      else if (ll + a0 > lb + coeftol && ll <= lb) { delta = lb - ll - a0; hit = 1; }
+      if (!hit) {
+        if (implic) {
+          ll = uu = 0;
+          ci_imp_bounds(&s, c, v, 0.0, &ll, &uu);
+          if (a0 > 0) uu += a0; else ll += a0;
+        }
+        if (uu - a0 < ub - coeftol && uu >= ub) { delta = uu - a0 - ub; side = 2; nb = uu - a0; hit = 1; }
+        else if (ll - a0 > lb + coeftol && ll <= lb) { delta = ll - a0 - lb; side = 1; nb = ll - a0; hit = 1; }
+      }
+      if (!hit) continue;
+      /* lf->incTerm(v, delta) */
+      double nv = a0;
+      if (fabs(delta) > 1e-9) { nv = a0 + delta; if (fabs(nv) < 1e-9) nv = 0.0; }
+      s.val[t] = nv;
+      if (side == 2) s.rub[c] = nb; else if (side == 1) s.rlb[c] = nb;
+      if (k < cap) { out_row[k] = c; out_var[k] = v; out_coef[k] = nv; out_side[k] = side; out_bnd[k] = nb; }
+      ++k;
+      break;
+    }
+  }
+  free(s.val); free(s.rlb); free(s.rub); free(s.lb); free(s.ub); free(cptr); free(crow); free(cpos);
+  return k;
+}

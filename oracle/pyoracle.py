@@ -154,6 +154,8 @@ class Oracle:
         L.orc_root_dup_rows.restype = C.c_int64
         L.orc_root_redundant_rows.argtypes = [C.POINTER(OrcLin), _dp, _dp, _bp]
         L.orc_root_redundant_rows.restype = C.c_int64
+        L.orc_root_coeff_imp.argtypes = [C.POINTER(OrcLin), _dp, _dp, C.c_int64, _ip, _ip, _dp, _ip, _dp]
+        L.orc_root_coeff_imp.restype = C.c_int64
         L.orc_nl_sweep.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(C.c_int64)]
         L.orc_nl_sweep.restype = C.c_int32
         L.orc_node_presolve.argtypes = [C.POINTER(OrcLin), C.POINTER(OrcNl), _dp, _dp, C.POINTER(OrcResult)]
@@ -229,6 +231,16 @@ class Oracle:
         out = np.zeros(max(inst.m, 1), np.uint8)
         self.lib.orc_root_redundant_rows(C.byref(s), _d(lb), _d(ub), _b(out))
         return out[:inst.m].astype(bool)
+
+    def root_coeff_imp(self, inst, lb, ub, cap=1 << 20):
+        """LinearHandler::coeffImp_ restated: (row, var, new coefficient, side, new row bound) arrays."""
+        keep = {}; s = _lin_struct(inst, keep)
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        row = np.zeros(cap, np.int32); var = np.zeros(cap, np.int32); coef = np.zeros(cap); side = np.zeros(cap, np.int32)
+        bnd = np.zeros(cap)
+        k = int(self.lib.orc_root_coeff_imp(C.byref(s), _d(lb), _d(ub), cap, _i(row), _i(var), _d(coef), _i(side), _d(bnd)))
+        assert k <= cap
+        return row[:k], var[:k], coef[:k], side[:k], bnd[:k]
 
     # ---- nonlinear ----
     def nl_compute_bounds(self, tapes, c, lb, ub):
@@ -352,6 +364,8 @@ class Reference:
             L.ref_dup_rows.argtypes = [C.c_void_p, C.c_uint32, _bp, _dp, _dp]
             L.ref_dup_rows_replay.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _bp, _dp, _bp, _dp, _dp]
             L.ref_redundant_rows.argtypes = [C.c_void_p, _bp]
+            L.ref_coeff_imp.restype = C.c_int64
+            L.ref_coeff_imp.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _dp, _ip, _dp]
             L.ref_destroy.argtypes = [C.c_void_p]
             cls._lib = L
         return cls._lib
@@ -479,6 +493,16 @@ class Reference:
         d = np.zeros(max(m, 1), np.uint8); rl = np.zeros(max(m, 1)); ru = np.zeros(max(m, 1))
         self.lib().ref_dup_rows_replay(self.h, len(pairs), _i(pi), _i(pj), _b(pk), _d(h1), _b(d), _d(rl), _d(ru))
         return d[:m].astype(bool), rl[:m], ru[:m]
+
+    def coeff_imp(self, lb, ub, cap=1 << 20):
+        """The reference's own LinearHandler::coeffImp_ on the box.  Modifies the problem (use a fresh Reference).
+        Returns (row, var, new coefficient, side, new row bound) arrays."""
+        self.set_box(lb, ub)
+        row = np.zeros(cap, np.int32); var = np.zeros(cap, np.int32); coef = np.zeros(cap); side = np.zeros(cap, np.int32)
+        bnd = np.zeros(cap)
+        k = int(self.lib().ref_coeff_imp(self.h, cap, _i(row), _i(var), _d(coef), _i(side), _d(bnd)))
+        assert k <= cap
+        return row[:k], var[:k], coef[:k], side[:k], bnd[:k]
 
     def redundant_rows(self, lb, ub, m):
         self.set_box(lb, ub)

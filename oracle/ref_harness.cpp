@@ -141,6 +141,7 @@ public:
    * seeds the generator, so that the same vectors can be drawn again outside (drawDupVectors). */
   void dupRows(bool *changed) { dupRows_(changed); }
   bool treatDup(ConstraintPtr c1, ConstraintPtr c2, double mult, bool *changed) { return treatDupRows_(c1, c2, mult, changed); }
+  void coeffImp(bool *changed) { coeffImp_(changed); }
   bool redundantOnBox(ConstraintPtr c)
   {
     double ll, uu;
@@ -326,6 +327,44 @@ void ref_redundant_rows(void *hv, uint8_t *redundant)
 {
   RefProblem *h = (RefProblem *)hv;
   for (size_t i = 0; i < h->lin_rows.size(); ++i) redundant[i] = h->lh->redundantOnBox(h->lin_rows[i]) ? 1 : 0;
+}
+
+/* The reference's own LinearHandler::coeffImp_ (LinearHandler.cpp:600-704) on the current box.  MODIFIES the problem
+ * (coefficients and row bounds); what it changed is found by comparing every linear row before and after: per changed
+ * row the variable, its new coefficient (0: the term was erased), which row bound moved (0 none / 1 lower / 2 upper)
+ * and its new value.  Returns the number of changed rows. */
+int64_t ref_coeff_imp(void *hv, int64_t cap, int32_t *out_row, int32_t *out_var, double *out_coef, int32_t *out_side,
+                      double *out_bnd)
+{
+  RefProblem *h = (RefProblem *)hv;
+  const size_t m = h->lin_rows.size();
+  std::vector<std::vector<std::pair<int, double> > > before(m);
+  std::vector<double> lb0(m), ub0(m);
+  for (size_t i = 0; i < m; ++i) {
+    LinearFunctionPtr lf = h->lin_rows[i]->getLinearFunction();
+    if (lf) for (VariableGroupConstIterator it = lf->termsBegin(); it != lf->termsEnd(); ++it)
+      before[i].push_back(std::make_pair((int)it->first->getIndex(), it->second));
+    lb0[i] = h->lin_rows[i]->getLb(); ub0[i] = h->lin_rows[i]->getUb();
+  }
+  bool changed = false;
+  h->lh->coeffImp(&changed);
+  int64_t k = 0;
+  for (size_t i = 0; i < m; ++i) {
+    ConstraintPtr c = h->lin_rows[i];
+    LinearFunctionPtr lf = c->getLinearFunction();
+    int var = -1; double coef = 0.0;
+    for (size_t t = 0; t < before[i].size(); ++t) {
+      const double w = lf->getWeight(h->vars[(size_t)before[i][t].first]);
+      if (w != before[i][t].second) { var = before[i][t].first; coef = w; }
+    }
+    int side = 0; double nb = 0.0;
+    if (c->getLb() != lb0[i]) { side = 1; nb = c->getLb(); }
+    if (c->getUb() != ub0[i]) { side = 2; nb = c->getUb(); }
+    if (var < 0 && side == 0) continue;
+    if (k < cap) { out_row[k] = (int32_t)i; out_var[k] = var; out_coef[k] = coef; out_side[k] = side; out_bnd[k] = nb; }
+    ++k;
+  }
+  return k;
 }
 
 /* linear objective  min c.x + constant  (the cut-off row of LinearHandler::varBndsFromObj_) */

@@ -83,3 +83,41 @@ def test_gpu_dup_rows_at_c2_size(engine):
     assert np.all(i < j) and np.all(same | mult)
     assert np.all((pairs[:, 2] == 1) == same)
     print(f"dupRows_ all-pairs compare of 100k rows: {st.kernel_ms:.2f} ms on the device, {len(pairs)} candidates")
+
+
+# ---- LinearHandler::coeffImp_ (LinearHandler.cpp:600-704) ----
+
+def _same_improvements(a, b):
+    return all(len(x) == len(y) and np.array_equal(x, y) for x, y in zip(a[:5], b[:5]))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_coeff_imp_matches_reference(oracle, have_ref, seed):
+    """The restatement against the reference's own coeffImp_ (called through the LinearHandler subclass of the harness) on
+    big-M instances: every improved row, the variable, the new coefficient (bitwise), the row bound that moved."""
+    from minotaur_b200.instances import make_bigm_instance
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import pyoracle
+    inst = make_bigm_instance(40, 120, 400, seed)
+    o = oracle.root_coeff_imp(inst, inst.lb, inst.ub)
+    r = pyoracle.Reference(inst).coeff_imp(inst.lb, inst.ub)
+    assert len(o[0]) > 50 and set(np.unique(o[3])) == {0, 1, 2}          # all four cases of :645-694 occur
+    assert _same_improvements(o, r)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,sizes", [(0, (40, 120, 400)), (1, (10, 30, 90)), (2, (300, 900, 4000)), (3, (2000, 6000, 30000))])
+def test_gpu_coeff_imp_vs_oracle(oracle, seed, sizes):
+    """mntr_gpu_root_coeff_imp against the oracle: same rows, variables, coefficients (bitwise) and row bounds; the rows
+    that read 2-term rows improved before them run in a later dependency level."""
+    from minotaur_b200 import engine as E
+    from minotaur_b200.instances import make_bigm_instance
+    inst = make_bigm_instance(*sizes, seed)
+    eng = E.GpuBoundEngine(0)
+    g = eng.root_coeff_imp(inst, inst.lb, inst.ub)
+    eng.close()
+    o = oracle.root_coeff_imp(inst, inst.lb, inst.ub)
+    assert len(o[0]) > 10
+    assert g[5]["levels"] >= 2 and g[5]["count"] == len(o[0])
+    assert _same_improvements(g, o)
