@@ -298,6 +298,21 @@ int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32
                             double *out_coef, int32_t *out_side, double *out_bnd, int64_t *n_out, int32_t *n_levels_out,
                             int32_t *n_erased_out);
 
+/* QuadHandler::simplePresolve (QuadHandler.cpp:1146-1201), the (f)-4 slice: the relations the handler holds after the
+ * reformulation -- y = x^2 (QuadHandler::x2Funs_: one per x, given ascending in x) and y = x0 * x1 (x0x1Funs_: given
+ * ascending in (x0, x1), x0 < x1; LinBil.cpp:26-35, 57-68) -- for the variables of the loaded problem (load_linear
+ * first; m may be 0).  n_sq = n_bil = 0 removes them. */
+int mntr_gpu_load_quad_relations(mntr_gpu_ctx *ctx, int32_t n_sq, const int32_t *sq_x, const int32_t *sq_y,
+                                 int32_t n_bil, const int32_t *b_x0, const int32_t *b_x1, const int32_t *b_y);
+/* ONE in-place sweep over the squares, then the products, on each of n_boxes boxes (lb / ub box-major [n_boxes][n],
+ * updated in place): BoundsOnSquare / the square-root rule / BoundsOnProduct / BoundsOnDiv, every step through
+ * updatePBounds_ (:3218-3246: integer rounding, tolerances 1e-8 / 1e-6 absolute and 1e-7 relative).  n_mods [n_boxes]
+ * receives the bound changes per box.  The reference overwrites its status with Finished (:1200), so no box is ever
+ * reported infeasible; n_inconsistent [n_boxes] (may be NULL) counts the steps that found crossing bounds.  With
+ * MNTR_ROUND_NEAREST the result is the reference's bit for bit; MNTR_ROUND_DIRECTED rounds outward. */
+int mntr_gpu_quad_simple_presolve(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub, int32_t rounding,
+                                  int32_t *n_mods, int32_t *n_inconsistent);
+
 /* statistics of the last tighten call */
 int mntr_gpu_get_stats(const mntr_gpu_ctx *ctx, mntr_gpu_stats *out);
 

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmntr_gpu.so")
 OBJ = os.path.join(HERE, "build")
 
-SOURCES = ["linear_single.cu", "linear_batch.cu", "linear_rounds.cu", "root_rows.cu", "mntr_gpu.cu", "mntr_group.cu"]
+SOURCES = ["linear_single.cu", "linear_batch.cu", "linear_rounds.cu", "root_rows.cu", "quad_relations.cu", "mntr_gpu.cu", "mntr_group.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--fmad=false",        # never contract a*b+c: the reference builds without FMA
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]

@@ -111,4 +111,17 @@ cudaError_t launch_coeff_imp(const CoeffProb &Q, const int32_t *rows, int32_t n_
                              int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd,
                              unsigned long long *count, int32_t *n_erased, cudaStream_t stream);
 
+
+// QuadHandler::simplePresolve (quad_relations.cu): the relations y = x^2 (b < 0) / y = a * b, stored in wavefront-level
+// order of the handler's sweep (squares by x, then products by (x0, x1))
+struct QRelDev {
+  int32_t n_rel;
+  const int32_t *a, *b, *y;
+  int32_t n_levels;
+  const int32_t *level_ptr;
+  const uint8_t *var_type;
+};
+cudaError_t launch_quad_relations(const QRelDev &Q, double2 *boxes, int64_t ld, int32_t n_boxes, bool directed, int32_t *n_mods,
+                                  int32_t *n_bad, cudaStream_t stream);
+
 }  // namespace mntr

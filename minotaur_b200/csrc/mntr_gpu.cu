@@ -60,7 +60,9 @@ struct mntr_gpu_ctx {
   int lanes_per_row = 8;             // sub-warp group size of the per-round kernels
   bool no_zero_copy = false;         // MNTR_GPU_NO_ZEROCOPY=1: always stage pinned host boxes through device copies
   LinDev lin{};
-  std::vector<void *> lin_allocs, cut_allocs;
+  std::vector<void *> lin_allocs, cut_allocs, qrel_allocs;
+  QRelDev qrel{};                    // QuadHandler relations (mntr_gpu_load_quad_relations)
+  bool qrel_loaded = false;
 
   // ---- cgraph tapes ----
   bool nl_loaded = false;            // tapes and / or QuadraticFunction constraints are on the device
@@ -366,6 +368,7 @@ void mntr_gpu_destroy(mntr_gpu_ctx *ctx)
   p2p_teardown(ctx);
   if (ctx->h_single) { cudaFreeHost(ctx->h_single); ctx->h_single = nullptr; }
   free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->nl_allocs); free_all(ctx->quad_allocs); free_all(ctx->single_allocs);
+  free_all(ctx->qrel_allocs);
   free_batch(ctx); free_stage(ctx); free_scratch(ctx);
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -391,6 +394,7 @@ int mntr_gpu_load_linear(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t 
   if (row_ptr[0] != 0) return fail(ctx, MNTR_E_ARG, "load_linear: row_ptr[0] != 0");
   CU(cudaSetDevice(ctx->device));
   free_all(ctx->lin_allocs); free_all(ctx->cut_allocs); free_all(ctx->single_allocs); free_batch(ctx); free_stage(ctx);
+  free_all(ctx->qrel_allocs); ctx->qrel_loaded = false; ctx->qrel = QRelDev{};
   free_all(ctx->nl_allocs); free_all(ctx->quad_allocs);
   ctx->nl_loaded = ctx->tapes_loaded = ctx->quad_loaded = false;
   ctx->nl = NlDev{};
@@ -1645,6 +1649,100 @@ int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32
   }
   *n_out = (int64_t)cnt;
   if (n_erased_out) *n_erased_out = erased;
+  ctx->stats = mntr_gpu_stats{};
+  ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  return MNTR_OK;
+}
+
+// ---- QuadHandler::simplePresolve (QuadHandler.cpp:1146-1201) ------------------------------------------------------
+int mntr_gpu_load_quad_relations(mntr_gpu_ctx *ctx, int32_t n_sq, const int32_t *sq_x, const int32_t *sq_y, int32_t n_bil,
+                                 const int32_t *b_x0, const int32_t *b_x1, const int32_t *b_y)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "load_quad_relations: call load_linear first (m may be 0)");
+  CU(cudaSetDevice(ctx->device));
+  free_all(ctx->qrel_allocs);
+  ctx->qrel_loaded = false;
+  ctx->qrel = QRelDev{};
+  if (n_sq < 0 || n_bil < 0 || (n_sq > 0 && (!sq_x || !sq_y)) || (n_bil > 0 && (!b_x0 || !b_x1 || !b_y)))
+    return fail(ctx, MNTR_E_ARG, "load_quad_relations: null or negative argument");
+  const int32_t n = ctx->n, n_rel = n_sq + n_bil;
+  if (n_rel == 0) return MNTR_OK;
+  // the handler's container order: squares ascending in x, one per x (a map); products ascending in (x0, x1), x0 < x1
+  for (int32_t k = 0; k < n_sq; ++k) {
+    if (sq_x[k] < 0 || sq_x[k] >= n || sq_y[k] < 0 || sq_y[k] >= n) return fail(ctx, MNTR_E_ARG, "load_quad_relations: variable out of range in square %d", k);
+    if (k > 0 && sq_x[k] <= sq_x[k - 1]) return fail(ctx, MNTR_E_ARG, "load_quad_relations: squares not strictly ascending in x at %d", k);
+  }
+  for (int32_t k = 0; k < n_bil; ++k) {
+    if (b_x0[k] < 0 || b_x1[k] >= n || b_x0[k] >= b_x1[k] || b_y[k] < 0 || b_y[k] >= n)
+      return fail(ctx, MNTR_E_ARG, "load_quad_relations: bad product %d (need 0 <= x0 < x1 < n)", k);
+    if (k > 0 && (b_x0[k] < b_x0[k - 1] || (b_x0[k] == b_x0[k - 1] && b_x1[k] <= b_x1[k - 1])))
+      return fail(ctx, MNTR_E_ARG, "load_quad_relations: products not strictly ascending in (x0, x1) at %d", k);
+  }
+  // wavefront levels of the sequential sweep: a relation reads and may write all of its variables
+  std::vector<int32_t> last((size_t)std::max(n, 1), -1), level((size_t)n_rel);
+  int32_t n_levels = 0;
+  auto vars_of = [&](int32_t r, int32_t v[3]) {
+    if (r < n_sq) { v[0] = sq_x[r]; v[1] = sq_y[r]; v[2] = sq_y[r]; }
+    else { v[0] = b_x0[r - n_sq]; v[1] = b_x1[r - n_sq]; v[2] = b_y[r - n_sq]; }
+  };
+  for (int32_t r = 0; r < n_rel; ++r) {
+    int32_t v[3]; vars_of(r, v);
+    int32_t lev = 0;
+    for (int t = 0; t < 3; ++t) lev = std::max(lev, last[(size_t)v[t]] + 1);
+    level[(size_t)r] = lev;
+    for (int t = 0; t < 3; ++t) last[(size_t)v[t]] = lev;
+    n_levels = std::max(n_levels, lev + 1);
+  }
+  std::vector<int32_t> lptr((size_t)n_levels + 1, 0), a((size_t)n_rel), b((size_t)n_rel), y((size_t)n_rel);
+  for (int32_t r = 0; r < n_rel; ++r) lptr[(size_t)level[(size_t)r] + 1]++;
+  for (int32_t l = 0; l < n_levels; ++l) lptr[(size_t)l + 1] += lptr[(size_t)l];
+  {
+    std::vector<int32_t> pos(lptr.begin(), lptr.end());
+    for (int32_t r = 0; r < n_rel; ++r) {
+      const int32_t q = pos[(size_t)level[(size_t)r]]++;
+      if (r < n_sq) { a[(size_t)q] = sq_x[r]; b[(size_t)q] = -1; y[(size_t)q] = sq_y[r]; }
+      else { a[(size_t)q] = b_x0[r - n_sq]; b[(size_t)q] = b_x1[r - n_sq]; y[(size_t)q] = b_y[r - n_sq]; }
+    }
+  }
+  QRelDev &Q = ctx->qrel;
+  int rc;
+  if ((rc = dev_upload(ctx, ctx->qrel_allocs, a.data(), a.size(), &Q.a))) return rc;
+  if ((rc = dev_upload(ctx, ctx->qrel_allocs, b.data(), b.size(), &Q.b))) return rc;
+  if ((rc = dev_upload(ctx, ctx->qrel_allocs, y.data(), y.size(), &Q.y))) return rc;
+  if ((rc = dev_upload(ctx, ctx->qrel_allocs, lptr.data(), lptr.size(), &Q.level_ptr))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  Q.n_rel = n_rel; Q.n_levels = n_levels; Q.var_type = ctx->lin.var_type;
+  ctx->qrel_loaded = true;
+  return MNTR_OK;
+}
+
+int mntr_gpu_quad_simple_presolve(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub, int32_t rounding,
+                                  int32_t *n_mods, int32_t *n_inconsistent)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "quad_simple_presolve: no problem loaded");
+  if (n_boxes <= 0 || !lb || !ub) return fail(ctx, MNTR_E_ARG, "quad_simple_presolve: bad argument");
+  if (rounding != MNTR_ROUND_DIRECTED && rounding != MNTR_ROUND_NEAREST) return fail(ctx, MNTR_E_ARG, "quad_simple_presolve: bad rounding");
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_batch(ctx, n_boxes, true))) return rc;
+  if ((rc = mntr_gpu_boxes_upload(ctx, n_boxes, lb, ub, ctx->d_boxes))) return rc;
+  const int64_t ld = mntr_gpu_box_ld(n_boxes);
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemsetAsync(ctx->d_verdict, 0, sizeof(int32_t) * (size_t)ld, s));
+  CU(cudaMemsetAsync(ctx->d_rounds, 0, sizeof(int32_t) * (size_t)ld, s));
+  CU(cudaEventRecord(ctx->ev[1], s));
+  if (ctx->qrel_loaded) {
+    QRelDev Q = ctx->qrel;
+    Q.var_type = ctx->lin.var_type;
+    CU(launch_quad_relations(Q, ctx->d_boxes, ld, n_boxes, rounding == MNTR_ROUND_DIRECTED, ctx->d_rounds, ctx->d_verdict, s));
+  }
+  CU(cudaEventRecord(ctx->ev[2], s));
+  if (n_mods) CU(cudaMemcpyAsync(n_mods, ctx->d_rounds, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  if (n_inconsistent) CU(cudaMemcpyAsync(n_inconsistent, ctx->d_verdict, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if ((rc = mntr_gpu_boxes_download(ctx, n_boxes, ctx->d_boxes, lb, ub))) return rc;
   ctx->stats = mntr_gpu_stats{};
   ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
   return MNTR_OK;

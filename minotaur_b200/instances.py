@@ -813,3 +813,66 @@ def make_bigm_instance(n_bin: int, n_cont: int, n_rows: int, seed: int) -> Linea
     return LinearRows(m=len(rows), n=n, row_ptr=np.array(row_ptr, np.int32), col=np.array(col, np.int32),
                       val=np.array(val, np.float64), row_lb=np.array(rl), row_ub=np.array(ru), var_type=var_type,
                       lb=lb, ub=ub, name=f"bigm-{seed}")
+
+
+@dataclass
+class QuadRelations:
+    """The relations a QuadHandler holds after the reformulation (/root/reference/src/base/QuadHandler.cpp:127-179):
+    y = x^2 (x2Funs_: one per x, ascending x) and y = x0 * x1 (x0x1Funs_: ascending (x0, x1), x0 < x1, one per pair)."""
+    sq_x: np.ndarray    # int32
+    sq_y: np.ndarray
+    b_x0: np.ndarray
+    b_x1: np.ndarray
+    b_y: np.ndarray
+
+
+def make_quad_relations(n_x: int, n_sq: int, n_bil: int, seed: int):
+    """n_x original variables (a mix of continuous, integer and binary), one auxiliary y per relation.  Returns
+    (QuadRelations, var_type, lb, ub).  Boxes avoid what makes the REFERENCE assert or divide badly: the auxiliary of a
+    square has lb >= 0 (QuadHandler.cpp:1165 asserts it), and factors of a
+    product straddle zero or stay away from it (BoundsOnRecip, Operations.cpp:182-212)."""
+    rng = np.random.default_rng([seed, 53])
+    n = n_x + n_sq + n_bil
+    var_type = np.full(n, 4, np.uint8)
+    kinds = rng.random(n_x)
+    var_type[:n_x][kinds < 0.25] = 1
+    var_type[:n_x][kinds < 0.1] = 0
+    lb = np.zeros(n); ub = np.zeros(n)
+    for j in range(n_x):
+        if var_type[j] == 0:
+            lb[j], ub[j] = 0.0, 1.0
+        else:
+            r = rng.random()
+            if r < 0.4:
+                lb[j] = -float(rng.integers(1, 8)); ub[j] = float(rng.integers(1, 8))          # straddles zero
+            elif r < 0.7:
+                lb[j] = float(rng.integers(1, 5)); ub[j] = lb[j] + float(rng.integers(1, 8))
+            else:
+                ub[j] = -float(rng.integers(1, 5)); lb[j] = ub[j] - float(rng.integers(1, 8))
+            if var_type[j] == 4:
+                lb[j] += 0.25 * float(rng.integers(0, 3)) * (1 if lb[j] > 0 else 0); ub[j] += 0.5 * float(rng.integers(0, 2))
+    sq_x = np.sort(rng.choice(n_x, n_sq, replace=False)).astype(np.int32)
+    sq_y = (n_x + np.arange(n_sq)).astype(np.int32)
+    pairs = set()
+    while len(pairs) < n_bil:
+        a, b = rng.choice(n_x, 2, replace=False)
+        pairs.add((int(min(a, b)), int(max(a, b))))
+    pairs = sorted(pairs)
+    b_x0 = np.array([p[0] for p in pairs], np.int32); b_x1 = np.array([p[1] for p in pairs], np.int32)
+    b_y = (n_x + n_sq + np.arange(n_bil)).astype(np.int32)
+    # auxiliaries: some free, some bounded so that the reverse rules bite
+    for k, y in enumerate(sq_y):
+        x = sq_x[k]
+        hi = max(lb[x] ** 2, ub[x] ** 2)
+        lb[y] = 0.0 if rng.random() < 0.6 else float(rng.integers(0, 3))        # (never negative: the reference asserts it)
+        ub[y] = INF if rng.random() < 0.3 else float(np.ceil(hi * rng.uniform(0.2, 1.2))) + 1.0
+    for k, y in enumerate(b_y):
+        c = [lb[b_x0[k]] * lb[b_x1[k]], lb[b_x0[k]] * ub[b_x1[k]], ub[b_x0[k]] * lb[b_x1[k]], ub[b_x0[k]] * ub[b_x1[k]]]
+        lo, hi = min(c), max(c)
+        r = rng.random()
+        if r < 0.3:
+            lb[y], ub[y] = -INF, INF
+        else:
+            lb[y] = float(np.floor(lo + (hi - lo) * rng.uniform(0.0, 0.4))) - 0.5
+            ub[y] = float(np.ceil(lo + (hi - lo) * rng.uniform(0.6, 1.0))) + 0.5
+    return QuadRelations(sq_x, sq_y, b_x0, b_x1, b_y), var_type, lb, ub

@@ -1153,3 +1153,56 @@ int64_t orc_root_coeff_imp(const orc_lin_t *p, const double *lb_in, const double
   free(s.val); free(s.rlb); free(s.rub); free(s.lb); free(s.ub); free(cptr); free(crow); free(cpos);
   return k;
 }
+
+
+/* ---- QuadHandler::simplePresolve (QuadHandler.cpp:1146-1201): ONE in-place sweep over the relations y = x^2 (x2Funs_,
+ *      a map keyed by x: ascending variable id) and then y = x0 * x1 (x0x1Funs_, ordered by (x0, x1), x0 < x1 by
+ *      index: LinBil.cpp:26-35, 57-68), every step through updatePBounds_ (QuadHandler.cpp:3218-3246).  The status the
+ *      reference computes is overwritten with Finished at the end (:1200): nothing is ever reported infeasible; the
+ *      number of steps that found inconsistent bounds is returned in *n_inconsistent for information. ---- */
+static int qh_update(const uint8_t *var_type, double *lbv, double *ubv, int32_t v, double lb, double ub, int64_t *n_mods)
+{
+  const double aTol = 1e-6, bTol = 1e-8, rTol = 1e-7;
+  const int ty = var_type[v];
+  if (ty == ORC_BINARY || ty == ORC_IMPLBIN || ty == ORC_INTEGER || ty == ORC_IMPLINT) { ub = floor(ub); lb = ceil(lb); }
+  if (ub < lbv[v] - bTol || lb > ubv[v] + bTol) return -1;
+  if (ub < ubv[v] - bTol && (ubv[v] == INFINITY || ub < ubv[v] - fabs(ubv[v]) * rTol)) { ubv[v] = ub; ++*n_mods; }
+  if (lb > lbv[v] + aTol && (lbv[v] == -INFINITY || lb > lbv[v] + fabs(lbv[v]) * rTol)) { lbv[v] = lb; ++*n_mods; }
+  return 0;
+}
+
+int64_t orc_quad_simple_presolve(int32_t n_sq, const int32_t *sq_x, const int32_t *sq_y, int32_t n_bil, const int32_t *b_x0,
+                                 const int32_t *b_x1, const int32_t *b_y, const uint8_t *var_type, double *lbv, double *ubv,
+                                 int64_t *n_inconsistent)
+{
+  const double bTol = 1e-8;
+  int64_t n_mods = 0, bad = 0;
+  for (int32_t k = 0; k < n_sq; ++k) {
+    const int32_t x = sq_x[k], y = sq_y[k];
+    double lb, ub;
+    orc_bounds_on_square(lbv[x], ubv[x], &lb, &ub);
+    if (qh_update(var_type, lbv, ubv, y, lb, ub, &n_mods) < 0) ++bad;
+    if (ubv[y] > bTol) {
+      ub = sqrt(ubv[y]);
+      lb = -ub;
+      if (lbv[x] > -sqrt(lbv[y]) + bTol) lb = sqrt(lbv[y]);
+      if (qh_update(var_type, lbv, ubv, x, lb, ub, &n_mods) < 0) ++bad;
+    } else if (ubv[y] < -bTol) {
+      ++bad;
+    } else {
+      if (qh_update(var_type, lbv, ubv, x, 0.0, 0.0, &n_mods) < 0) ++bad;
+    }
+  }
+  for (int32_t k = 0; k < n_bil; ++k) {
+    const int32_t x1 = b_x0[k], x2 = b_x1[k], y = b_y[k];
+    double lb, ub;
+    orc_bounds_on_product(1, lbv[x1], ubv[x1], lbv[x2], ubv[x2], &lb, &ub);
+    if (qh_update(var_type, lbv, ubv, y, lb, ub, &n_mods) < 0) ++bad;
+    orc_bounds_on_div(lbv[y], ubv[y], lbv[x1], ubv[x1], &lb, &ub);
+    if (qh_update(var_type, lbv, ubv, x2, lb, ub, &n_mods) < 0) ++bad;
+    orc_bounds_on_div(lbv[y], ubv[y], lbv[x2], ubv[x2], &lb, &ub);
+    if (qh_update(var_type, lbv, ubv, x1, lb, ub, &n_mods) < 0) ++bad;
+  }
+  if (n_inconsistent) *n_inconsistent = bad;
+  return n_mods;
+}

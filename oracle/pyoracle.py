@@ -156,6 +156,8 @@ class Oracle:
         L.orc_root_redundant_rows.restype = C.c_int64
         L.orc_root_coeff_imp.argtypes = [C.POINTER(OrcLin), _dp, _dp, C.c_int64, _ip, _ip, _dp, _ip, _dp]
         L.orc_root_coeff_imp.restype = C.c_int64
+        L.orc_quad_simple_presolve.argtypes = [C.c_int32, _ip, _ip, C.c_int32, _ip, _ip, _ip, _bp, _dp, _dp, _lp]
+        L.orc_quad_simple_presolve.restype = C.c_int64
         L.orc_nl_sweep.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(C.c_int64)]
         L.orc_nl_sweep.restype = C.c_int32
         L.orc_node_presolve.argtypes = [C.POINTER(OrcLin), C.POINTER(OrcNl), _dp, _dp, C.POINTER(OrcResult)]
@@ -241,6 +243,17 @@ class Oracle:
         k = int(self.lib.orc_root_coeff_imp(C.byref(s), _d(lb), _d(ub), cap, _i(row), _i(var), _d(coef), _i(side), _d(bnd)))
         assert k <= cap
         return row[:k], var[:k], coef[:k], side[:k], bnd[:k]
+
+    def quad_simple_presolve(self, rel, var_type, lb, ub):
+        """QuadHandler::simplePresolve restated: one in-place sweep over the relations ``rel`` (instances.QuadRelations, in
+        the handler's container order).  Returns (lb, ub, n_mods, n_inconsistent)."""
+        lb = np.array(lb, np.float64); ub = np.array(ub, np.float64)
+        vt = np.ascontiguousarray(var_type, np.uint8)
+        bad = np.zeros(1, np.int64)
+        a = [np.ascontiguousarray(x if len(x) else np.zeros(1), np.int32) for x in (rel.sq_x, rel.sq_y, rel.b_x0, rel.b_x1, rel.b_y)]
+        k = int(self.lib.orc_quad_simple_presolve(len(rel.sq_x), _i(a[0]), _i(a[1]), len(rel.b_x0), _i(a[2]), _i(a[3]), _i(a[4]),
+                                                  _b(vt), _d(lb), _d(ub), bad.ctypes.data_as(_lp)))
+        return lb, ub, k, int(bad[0])
 
     # ---- nonlinear ----
     def nl_compute_bounds(self, tapes, c, lb, ub):
@@ -365,6 +378,8 @@ class Reference:
             L.ref_dup_rows_replay.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _bp, _dp, _bp, _dp, _dp]
             L.ref_redundant_rows.argtypes = [C.c_void_p, _bp]
             L.ref_coeff_imp.restype = C.c_int64
+            L.ref_quad_simple_presolve.restype = C.c_int64
+            L.ref_quad_simple_presolve.argtypes = [C.c_int32, _bp, _dp, _dp, C.c_int32, _ip, _ip, C.c_int32, _ip, _ip, _ip]
             L.ref_coeff_imp.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _dp, _ip, _dp]
             L.ref_destroy.argtypes = [C.c_void_p]
             cls._lib = L
@@ -493,6 +508,16 @@ class Reference:
         d = np.zeros(max(m, 1), np.uint8); rl = np.zeros(max(m, 1)); ru = np.zeros(max(m, 1))
         self.lib().ref_dup_rows_replay(self.h, len(pairs), _i(pi), _i(pj), _b(pk), _d(h1), _b(d), _d(rl), _d(ru))
         return d[:m].astype(bool), rl[:m], ru[:m]
+
+    @classmethod
+    def quad_simple_presolve(cls, rel, var_type, lb, ub):
+        """The reference's own QuadHandler::simplePresolve on a fresh problem holding the relations.  (lb, ub, n_mods)"""
+        lb = np.array(lb, np.float64); ub = np.array(ub, np.float64)
+        vt = np.ascontiguousarray(var_type, np.uint8)
+        a = [np.ascontiguousarray(x if len(x) else np.zeros(1), np.int32) for x in (rel.sq_x, rel.sq_y, rel.b_x0, rel.b_x1, rel.b_y)]
+        k = int(cls.lib().ref_quad_simple_presolve(len(lb), _b(vt), _d(lb), _d(ub), len(rel.sq_x), _i(a[0]), _i(a[1]),
+                                                   len(rel.b_x0), _i(a[2]), _i(a[3]), _i(a[4])))
+        return lb, ub, k
 
     def coeff_imp(self, lb, ub, cap=1 << 20):
         """The reference's own LinearHandler::coeffImp_ on the box.  Modifies the problem (use a fresh Reference).

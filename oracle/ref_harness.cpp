@@ -18,6 +18,7 @@
 // untouched headers: access specifiers do not change the layout.
 #define private public
 #include "NlPresHandler.h"
+#include "QuadHandler.h"
 #undef private
 
 #include <chrono>
@@ -254,6 +255,44 @@ int32_t ref_add_quad(void *hv, int32_t k, const int32_t *v1, const int32_t *v2, 
   FunctionPtr f = (FunctionPtr) new Function(lf, qf, (NonlinearFunctionPtr)0);
   h->quad_rows.push_back(h->p->newConstraint(f, lb, ub));
   return (int32_t)h->quad_rows.size() - 1;
+}
+
+/* The reference's own QuadHandler::simplePresolve (QuadHandler.cpp:1146-1201) on a fresh problem of n variables with
+ * the given types and box: the relations y = x^2 and y = x0 x1 are handed to QuadHandler::addConstraint (:127-179) as
+ * constraints  y - x0 x1 = 0  (one linear term, one quadratic term); the handler orders them itself (x2Funs_ by x,
+ * x0x1Funs_ by (x0, x1)).  lb / ub are updated in place; returns the number of modifications. */
+int64_t ref_quad_simple_presolve(int32_t n, const uint8_t *var_type, double *lb, double *ub, int32_t n_sq, const int32_t *sq_x,
+                                 const int32_t *sq_y, int32_t n_bil, const int32_t *b_x0, const int32_t *b_x1, const int32_t *b_y)
+{
+  EnvPtr env = (EnvPtr) new Environment();
+  int err = 0;
+  env->startTimer(err);
+  env->setLogLevel(LogNone);
+  ProblemPtr p = (ProblemPtr) new Problem(env);
+  std::vector<VariablePtr> vars;
+  for (int32_t j = 0; j < n; ++j) vars.push_back(p->newVariable(lb[j], ub[j], (VariableType)var_type[j]));
+  QuadHandler *qh = new QuadHandler(env, p);
+  for (int32_t k = 0; k < n_sq + n_bil; ++k) {
+    const bool sq = k < n_sq;
+    VariablePtr y = vars[sq ? sq_y[k] : b_y[k - n_sq]];
+    VariablePtr x0 = vars[sq ? sq_x[k] : b_x0[k - n_sq]], x1 = vars[sq ? sq_x[k] : b_x1[k - n_sq]];
+    LinearFunctionPtr lf = (LinearFunctionPtr) new LinearFunction();
+    lf->addTerm(y, 1.0);
+    QuadraticFunctionPtr qf = (QuadraticFunctionPtr) new QuadraticFunction();
+    qf->addTerm(x0, x1, -1.0);
+    FunctionPtr f = (FunctionPtr) new Function(lf, qf, (NonlinearFunctionPtr)0);
+    qh->addConstraint(p->newConstraint(f, 0.0, 0.0));
+  }
+  ModVector mods;
+  SolveStatus status = Started;
+  qh->simplePresolve(p, (SolutionPoolPtr)0, mods, status);
+  const int64_t n_mods = (int64_t)mods.size();
+  for (int32_t j = 0; j < n; ++j) { lb[j] = vars[j]->getLb(); ub[j] = vars[j]->getUb(); }
+  freeMods(mods);
+  delete qh;
+  delete p;
+  delete env;
+  return n_mods;
 }
 
 /* NlPresHandler::chkRed_ alone (NlPresHandler.cpp:101-208) on the current box: 1 = infeasible */
