@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--only", default="", help="comma-separated subset of blocks: C1,C2,C3,C4,C5")
+    ap.add_argument("--only", default="", help="comma-separated subset of blocks: C1,C2,C3,C4,C5,F (F: the SURVEY 8(f) rows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle checks (profiling runs)")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no sustained pre-load loop, one repetition")
@@ -466,9 +466,11 @@ def main():
         sampler.start()
     t_all = time.perf_counter()
     blocks = {}
-    for name, fn in (("C2", block_c2), ("C3", block_c3), ("C1", block_c1), ("C4", block_c4), ("C5", block_c5)):
+    for name, fn in (("C2", block_c2), ("C3", block_c3), ("C1", block_c1), ("C4", block_c4), ("C5", block_c5), ("F", block_next)):
         if not want(name):
             continue
+        if name == "F" and (world > 1 or args.profile):
+            continue                            # the (f) rows: one GPU
         t0 = time.perf_counter()
         try:
             blocks[name] = fn(X)
@@ -499,6 +501,12 @@ def main():
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        # a block that failed, or whose in-run parity check failed, fails the run (the line above is printed all the same)
+        bad = [k for k, b in blocks.items() if isinstance(b, dict) and ("error" in b or (b.get("parity") or {}).get("ok") is False)]
+        if bad:
+            print("bench.py: failed blocks / parity checks: " + ", ".join(bad), file=sys.stderr)
+            sys.exit(3)
 
 
 # ---------------------------------------------------------------- C2 ----------------------------------------------
@@ -611,6 +619,106 @@ def block_c2(X):
         out["cpu_baseline"] = cpu
     return out
 
+
+
+# ---------------------------------------------------------------- (f) rows ----------------------------------------
+
+def block_next(X):
+    """The SURVEY 8(f) rows that run on the device -- root-presolve row operations ((f)-3) and QuadHandler::simplePresolve
+    ((f)-4) -- each timed on the GPU with the reference's own routine timed beside it on one host core, and checked
+    against the oracle in the run.  One GPU, rank 0."""
+    E, torch = X.E, X.torch
+    from minotaur_b200.instances import (LinearRows, make_bigm_instance, make_quad_relations, make_sparse_milp,
+                                          plant_duplicate_rows)
+    from oracle import pyoracle
+    orc = pyoracle.Oracle() if X.parity else None
+    have_ref = pyoracle.have_reference() and X.cpu
+    out = {}
+    eng = E.GpuBoundEngine(X.dev.index)
+
+    # ---- dupRows_ + redundancy on 20k rows (the reference's scan is O(m^2): 100k rows would take minutes) ----
+    inst = plant_duplicate_rows(make_sparse_milp(20_000, 20_000, 10, seed=4242), 400, 11)
+    eng.load_linear(inst)
+    rng = np.random.default_rng(5)
+    r1, r2 = rng.random(inst.n) * 10.0, rng.random(inst.n) * 10.0
+    ms = []
+    for it in range(4):
+        h1, h2, pairs = eng.root_dup_rows(r1, r2)
+        if it: ms.append(eng.stats().kernel_ms)
+    d = {"workload": "LinearHandler::dupRows_ candidates, 20000 rows x 10 nnz with 400 planted duplicates (all-pairs hash compare)",
+         "ms": float(np.mean(ms)), "candidates": int(len(pairs))}
+    if orc is not None:
+        o1, o2, opairs = orc.root_dup_rows(inst, r1, r2, cap=1 << 18)
+        d["parity"] = {"ok": bool(np.array_equal(h1, o1) and np.array_equal(h2, o2) and np.array_equal(pairs, opairs)),
+                       "criterion": "hashes and candidate list bitwise vs the oracle"}
+    if have_ref:
+        ref = pyoracle.Reference(inst)
+        t0 = time.perf_counter(); ref.dup_rows(4321, inst.m); d["cpu_reference_ms"] = 1e3 * (time.perf_counter() - t0)
+        ref.close()
+    out["dup_rows"] = d
+    ms = []
+    for it in range(4):
+        red = eng.root_redundant_rows(inst.lb, inst.ub)
+        if it: ms.append(eng.stats().kernel_ms)
+    d = {"workload": "redundancy test of linBndTighten_ (root mode) on the same rows", "ms": float(np.mean(ms)), "redundant": int(red.sum())}
+    if orc is not None:
+        d["parity"] = {"ok": bool(np.array_equal(red, orc.root_redundant_rows(inst, inst.lb, inst.ub))), "criterion": "flags bitwise vs the oracle"}
+    out["redundant_rows"] = d
+
+    # ---- coeffImp_ on 300k big-M rows ----
+    inst = make_bigm_instance(20_000, 60_000, 300_000, 7)
+    ms = []
+    for it in range(3):
+        g = eng.root_coeff_imp(inst, inst.lb, inst.ub)
+        if it: ms.append(g[5]["kernel_ms"])
+    d = {"workload": f"LinearHandler::coeffImp_ with implications, {inst.m} big-M rows, {inst.nnz} nnz", "ms": float(np.mean(ms)),
+         "improvements": g[5]["count"], "dependency_levels": g[5]["levels"]}
+    if orc is not None:
+        t0 = time.perf_counter(); o = orc.root_coeff_imp(inst, inst.lb, inst.ub); d["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+        d["parity"] = {"ok": bool(all(len(a) == len(b) and np.array_equal(a, b) for a, b in zip(g[:5], o))),
+                       "criterion": "rows, variables, new coefficients and row bounds bitwise vs the oracle"}
+    if have_ref:
+        ref = pyoracle.Reference(inst)
+        t0 = time.perf_counter(); ref.coeff_imp(inst.lb, inst.ub); d["cpu_reference_ms"] = 1e3 * (time.perf_counter() - t0)
+        ref.close()
+    out["coeff_imp"] = d
+
+    # ---- QuadHandler::simplePresolve: 50k relations x 1024 boxes ----
+    rel, vt, lb, ub = make_quad_relations(30_000, 10_000, 40_000, 5)
+    n = len(lb)
+    empty = LinearRows(m=0, n=n, row_ptr=np.zeros(1, np.int32), col=np.zeros(0, np.int32), val=np.zeros(0), row_lb=np.zeros(0),
+                       row_ub=np.zeros(0), var_type=vt, lb=lb, ub=ub)
+    eng.load_linear(empty)
+    eng.load_quad_relations(rel)
+    nb = 1024
+    L = np.tile(lb, (nb, 1)); U = np.tile(ub, (nb, 1))
+    rngb = np.random.default_rng(9)
+    for b in range(1, nb):                      # every box a different perturbation of a few positive-range variables
+        js = rngb.choice(30_000, 8, replace=False)
+        for j in js:
+            if L[b, j] > 0 and U[b, j] - L[b, j] >= 2: L[b, j] += 1.0
+    ms = []
+    for it in range(3):
+        gl, gu, nm, bad, kms = eng.quad_simple_presolve(L, U, rounding=E.ROUND_NEAREST)
+        if it: ms.append(kms)
+    d = {"workload": f"QuadHandler::simplePresolve, {len(rel.sq_x)} squares + {len(rel.b_x0)} products, {nb} boxes (round to nearest)",
+         "ms": float(np.mean(ms)), "boxes_per_s": nb / (1e-3 * float(np.mean(ms))), "mods": int(nm.sum())}
+    if orc is not None:
+        ok = True
+        t0 = time.perf_counter()
+        for b in range(0, nb, 64):
+            ol, ou, k, obad = orc.quad_simple_presolve(rel, vt, L[b], U[b])
+            ok = ok and np.array_equal(gl[b], ol) and np.array_equal(gu[b], ou) and nm[b] == k
+        d["cpu_port_ms_per_box"] = 1e3 * (time.perf_counter() - t0) / len(range(0, nb, 64))
+        d["parity"] = {"ok": bool(ok), "criterion": "16 of the boxes bitwise vs the oracle (bounds and modification counts)"}
+    if have_ref:
+        t0 = time.perf_counter(); pyoracle.Reference.quad_simple_presolve(rel, vt, L[0], U[0])
+        d["cpu_reference_ms_per_box"] = 1e3 * (time.perf_counter() - t0)
+        d["cpu_reference_note"] = "includes building the reference's Problem and QuadHandler for the box"
+    out["quad_handler_simple_presolve"] = d
+    eng.close()
+    out["parity"] = {"ok": all(v.get("parity", {}).get("ok", True) for v in out.values() if isinstance(v, dict))}
+    return out
 
 # ---------------------------------------------------------------- C1 ----------------------------------------------
 
