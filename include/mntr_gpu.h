@@ -286,7 +286,8 @@ int mntr_gpu_root_redundant_rows(mntr_gpu_ctx *ctx, const double *lb, const doub
  * (lb, ub).  For every one-sided row with at least two terms the first binary (Binary / ImplBin, not fixed) whose
  * coefficient the reference would improve is reported: out_row, out_var, out_coef = the NEW coefficient (0: the term
  * is erased, LinearFunction::incTerm :133-142), out_side = which row bound moves with it (0 none, 1 lower, 2 upper)
- * and out_bnd its new value; sorted by row.  The reference's pass is sequential through the 2-term rows its
+ * and out_bnd its new value; out_delta (may be NULL) = the argument the reference passes to
+ * LinearFunction::incTerm, so that a caller applying the change gets the very same coefficient; sorted by row.  The reference's pass is sequential through the 2-term rows its
  * implications read (a row sees the improved version of those before it): rows run in dependency levels
  * (*n_levels_out launches), so the result is the reference's, bit for bit.  Applying the changes (incTerm,
  * changeBound, bFlags) mutates Minotaur's object graph and stays with the caller.  *n_erased_out counts improvements
@@ -295,8 +296,8 @@ int mntr_gpu_root_redundant_rows(mntr_gpu_ctx *ctx, const double *lb, const doub
 int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col,
                             const double *val, const double *row_lb, const double *row_ub, const uint8_t *var_type,
                             const double *lb, const double *ub, int64_t cap, int32_t *out_row, int32_t *out_var,
-                            double *out_coef, int32_t *out_side, double *out_bnd, int64_t *n_out, int32_t *n_levels_out,
-                            int32_t *n_erased_out);
+                            double *out_coef, int32_t *out_side, double *out_bnd, double *out_delta, int64_t *n_out,
+                            int32_t *n_levels_out, int32_t *n_erased_out);
 
 /* QuadHandler::simplePresolve (QuadHandler.cpp:1146-1201), the (f)-4 slice: the relations the handler holds after the
  * reformulation -- y = x^2 (QuadHandler::x2Funs_: one per x, given ascending in x) and y = x0 * x1 (x0x1Funs_: given

@@ -108,7 +108,7 @@ struct CoeffProb {
   const uint8_t *is2;                   // the row has exactly two terms
 };
 cudaError_t launch_coeff_imp(const CoeffProb &Q, const int32_t *rows, int32_t n_rows, long long cap, int32_t *out_row,
-                             int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd,
+                             int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd, double *out_delta,
                              unsigned long long *count, int32_t *n_erased, cudaStream_t stream);
 
 

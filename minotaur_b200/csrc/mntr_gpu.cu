@@ -1526,8 +1526,8 @@ int mntr_gpu_root_redundant_rows(mntr_gpu_ctx *ctx, const double *lb, const doub
 int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col,
                             const double *val, const double *row_lb, const double *row_ub, const uint8_t *var_type,
                             const double *lb, const double *ub, int64_t cap, int32_t *out_row, int32_t *out_var,
-                            double *out_coef, int32_t *out_side, double *out_bnd, int64_t *n_out, int32_t *n_levels_out,
-                            int32_t *n_erased_out)
+                            double *out_coef, int32_t *out_side, double *out_bnd, double *out_delta, int64_t *n_out,
+                            int32_t *n_levels_out, int32_t *n_erased_out)
 {
   if (!ctx) return MNTR_E_ARG;
   if (m < 0 || n < 0 || !row_ptr || !n_out || cap < 0) return fail(ctx, MNTR_E_ARG, "root_coeff_imp: bad argument");
@@ -1614,10 +1614,11 @@ int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32
   const int32_t *d_rows;
   if ((rc = dev_upload(ctx, owned, lrows.data(), lrows.size(), &d_rows))) return rc;
   const size_t capz = (size_t)std::max<int64_t>(cap, 1);
-  int32_t *d_orow, *d_ovar, *d_oside, *d_erased; double *d_ocoef, *d_obnd; unsigned long long *d_cnt;
+  int32_t *d_orow, *d_ovar, *d_oside, *d_erased; double *d_ocoef, *d_obnd, *d_odelta; unsigned long long *d_cnt;
   auto dalloc = [&](void **p, size_t bytes) -> int { CU(cudaMalloc(p, std::max<size_t>(bytes, 16))); owned.push_back(*p); return MNTR_OK; };
   if ((rc = dalloc((void **)&d_orow, 4 * capz)) || (rc = dalloc((void **)&d_ovar, 4 * capz)) || (rc = dalloc((void **)&d_oside, 4 * capz)) ||
-      (rc = dalloc((void **)&d_ocoef, 8 * capz)) || (rc = dalloc((void **)&d_obnd, 8 * capz)) || (rc = dalloc((void **)&d_cnt, 16)) ||
+      (rc = dalloc((void **)&d_ocoef, 8 * capz)) || (rc = dalloc((void **)&d_obnd, 8 * capz)) || (rc = dalloc((void **)&d_odelta, 8 * capz)) ||
+      (rc = dalloc((void **)&d_cnt, 16)) ||
       (rc = dalloc((void **)&d_erased, 16))) return rc;
   cudaStream_t s = ctx->stream;
   CU(cudaMemsetAsync(d_cnt, 0, 16, s));
@@ -1625,7 +1626,7 @@ int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32
   CU(cudaEventRecord(ctx->ev[1], s));
   for (int32_t l = 0; l < n_levels; ++l)
     CU(launch_coeff_imp(Q, d_rows + lptr[(size_t)l], lptr[(size_t)l + 1] - lptr[(size_t)l], (long long)cap, d_orow, d_ovar, d_ocoef,
-                        d_oside, d_obnd, d_cnt, d_erased, s));
+                        d_oside, d_obnd, d_odelta, d_cnt, d_erased, s));
   CU(cudaEventRecord(ctx->ev[2], s));
   unsigned long long cnt = 0; int32_t erased = 0;
   CU(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
@@ -1633,7 +1634,8 @@ int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32
   CU(cudaStreamSynchronize(s));
   const size_t k = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)cap);
   if (k) {
-    std::vector<int32_t> r(k), v(k), sd(k); std::vector<double> cf(k), bd(k);
+    std::vector<int32_t> r(k), v(k), sd(k); std::vector<double> cf(k), bd(k), dl(k);
+    CU(cudaMemcpyAsync(dl.data(), d_odelta, 8 * k, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(r.data(), d_orow, 4 * k, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(v.data(), d_ovar, 4 * k, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(sd.data(), d_oside, 4 * k, cudaMemcpyDeviceToHost, s));
@@ -1645,6 +1647,7 @@ int mntr_gpu_root_coeff_imp(mntr_gpu_ctx *ctx, int32_t m, int32_t n, const int32
     std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return r[a] < r[b]; });      // the reference's order: by row
     for (size_t i = 0; i < k; ++i) {
       out_row[i] = r[ord[i]]; out_var[i] = v[ord[i]]; out_coef[i] = cf[ord[i]]; out_side[i] = sd[ord[i]]; out_bnd[i] = bd[ord[i]];
+      if (out_delta) out_delta[i] = dl[ord[i]];
     }
   }
   *n_out = (int64_t)cnt;

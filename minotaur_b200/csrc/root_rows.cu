@@ -164,7 +164,7 @@ __device__ void ci_imp_bounds(const CoeffProb &Q, int c, int z, double zval, dou
 }
 
 __global__ void coeff_imp_kernel(CoeffProb Q, const int32_t *rows, int32_t n_rows, long long cap, int32_t *out_row,
-                                 int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd,
+                                 int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd, double *out_delta,
                                  unsigned long long *count, int32_t *n_erased)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,7 +214,7 @@ __global__ void coeff_imp_kernel(CoeffProb Q, const int32_t *rows, int32_t n_row
     Q.val[t] = nv;
     if (side == 2) Q.rub[c] = nb; else if (side == 1) Q.rlb[c] = nb;
     const unsigned long long k = atomicAdd(count, 1ull);
-    if ((long long)k < cap) { out_row[k] = c; out_var[k] = v; out_coef[k] = nv; out_side[k] = side; out_bnd[k] = nb; }
+    if ((long long)k < cap) { out_row[k] = c; out_var[k] = v; out_coef[k] = nv; out_side[k] = side; out_bnd[k] = nb; out_delta[k] = delta; }
     return;
   }
 }
@@ -246,12 +246,12 @@ cudaError_t launch_redundant_rows(const LinDev &P, const int32_t *perm, const do
 }
 
 cudaError_t launch_coeff_imp(const CoeffProb &Q, const int32_t *rows, int32_t n_rows, long long cap, int32_t *out_row,
-                             int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd,
+                             int32_t *out_var, double *out_coef, int32_t *out_side, double *out_bnd, double *out_delta,
                              unsigned long long *count, int32_t *n_erased, cudaStream_t stream)
 {
   if (n_rows <= 0) return cudaSuccess;
   coeff_imp_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(Q, rows, n_rows, cap, out_row, out_var, out_coef, out_side, out_bnd,
-                                                             count, n_erased);
+                                                             out_delta, count, n_erased);
   return cudaGetLastError();
 }
 

@@ -113,7 +113,7 @@ def load_library() -> C.CDLL:
     L.mntr_gpu_load_quad_relations.argtypes = [vp, C.c_int32, _ip, _ip, C.c_int32, _ip, _ip, _ip]
     L.mntr_gpu_quad_simple_presolve.argtypes = [vp, C.c_int32, _dp, _dp, C.c_int32, _ip, _ip]
     L.mntr_gpu_root_coeff_imp.argtypes = [vp, C.c_int32, C.c_int32, _ip, _ip, _dp, _dp, _dp, _bp, _dp, _dp, C.c_int64, _ip, _ip, _dp,
-                                          _ip, _dp, _lp, _ip, _ip]
+                                          _ip, _dp, _dp, _lp, _ip, _ip]
     L.mntr_gpu_group_load_quad.argtypes = [vp, C.c_int32, _ip, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp]
     L.mntr_gpu_alloc_host.argtypes = [vp, C.c_int64]
     L.mntr_gpu_alloc_host.restype = vp
@@ -291,7 +291,7 @@ class GpuBoundEngine:
         side = np.zeros(max(cap, 1), np.int32); bnd = np.zeros(max(cap, 1))
         cnt = C.c_int64(0); lev = C.c_int32(0); er = C.c_int32(0)
         self._check(self.L.mntr_gpu_root_coeff_imp(self.h, inst.m, inst.n, _i(rp), _i(col), _d(val), _d(rl), _d(ru), _b(vt), _d(lb),
-                                                   _d(ub), cap, _i(row), _i(var), _d(coef), _i(side), _d(bnd), C.byref(cnt),
+                                                   _d(ub), cap, _i(row), _i(var), _d(coef), _i(side), _d(bnd), None, C.byref(cnt),
                                                    C.byref(lev), C.byref(er)), "root_coeff_imp")
         k = min(int(cnt.value), cap)
         info = {"levels": int(lev.value), "erased": int(er.value), "count": int(cnt.value), "kernel_ms": self.stats().kernel_ms}

@@ -59,6 +59,10 @@ GpuBoundHandler::GpuBoundHandler(EnvPtr env, ProblemPtr problem, const std::vect
 void GpuBoundHandler::init_(const std::vector<int> &devices)
 {
   logger_ = env_->getLogger();
+  // Handler leaves modProb_ / modRel_ uninitialised (Handler.h:380-383; LinearHandler's constructor does not set them
+  // either): start from what Bnb sets for the node handlers (setModFlags(false, true), Bnb.cpp:111,121)
+  modProb_ = false;
+  modRel_ = true;
   stats_.calls = stats_.uploads = stats_.nMods = stats_.nInf = 0;
   stats_.rowBoundUpdates = stats_.skippedCons = stats_.engineErrors = stats_.cacheHits = 0;
   stats_.nnzUpdates = 0;
@@ -92,6 +96,56 @@ void GpuBoundHandler::engineFailed_(const char *where)
   logger_->errStream() << me_ << where << ": " << (ctx_ ? mntr_gpu_last_error(ctx_) : "no context")
                        << " -- no bound tightening from this call" << std::endl;
   loadedFor_ = 0;
+}
+
+int GpuBoundHandler::coeffImprove(bool *changed)
+{
+  ProblemPtr p = problem_;
+  const UInt n = p->getNumVars();
+  std::vector<int> rowPtr(1, 0), col;
+  std::vector<double> val, rowLb, rowUb, lb(n), ub(n);
+  std::vector<unsigned char> vtype(n);
+  std::vector<ConstraintPtr> rows;
+  for (VariableConstIterator it = p->varsBegin(); it != p->varsEnd(); ++it) {
+    const UInt j = (*it)->getIndex();
+    vtype[j] = (unsigned char)(*it)->getType(); lb[j] = (*it)->getLb(); ub[j] = (*it)->getUb();
+  }
+  // the rows coeffImp_ and computeImpBounds_ look at: Linear constraints, in index order (:616-620, :739-742)
+  for (ConstraintConstIterator it = p->consBegin(); it != p->consEnd(); ++it) {
+    ConstraintPtr c = *it;
+    if (p->isMarkedDel(c) || c->getFunctionType() != Linear) continue;
+    LinearFunctionPtr lf = c->getLinearFunction();
+    if (!lf) continue;
+    for (VariableGroupConstIterator t = lf->termsBegin(); t != lf->termsEnd(); ++t) {
+      col.push_back((int)t->first->getIndex());
+      val.push_back(t->second);
+    }
+    rowPtr.push_back((int)col.size());
+    rowLb.push_back(c->getLb()); rowUb.push_back(c->getUb());
+    rows.push_back(c);
+  }
+  const int m = (int)rows.size();
+  if (m == 0) return 0;
+  const long long cap = m;
+  std::vector<int> oRow((size_t)cap), oVar((size_t)cap), oSide((size_t)cap);
+  std::vector<double> oCoef((size_t)cap), oBnd((size_t)cap), oDelta((size_t)cap);
+  long long cnt = 0;
+  int levels = 0, erased = 0;
+  if (mntr_gpu_root_coeff_imp(ctx_, m, (int)n, &rowPtr[0], col.empty() ? 0 : &col[0], val.empty() ? 0 : &val[0], &rowLb[0],
+                              &rowUb[0], &vtype[0], &lb[0], &ub[0], cap, &oRow[0], &oVar[0], &oCoef[0], &oSide[0], &oBnd[0],
+                              &oDelta[0], (int64_t *)&cnt, &levels, &erased) != 0) {
+    engineFailed_("coeffImprove");
+    return 0;
+  }
+  for (long long k = 0; k < cnt; ++k) {
+    ConstraintPtr c = rows[(size_t)oRow[(size_t)k]];
+    c->getLinearFunction()->incTerm(p->getVariable((UInt)oVar[(size_t)k]), oDelta[(size_t)k]);     // :652, :660, :680, :689
+    if (oSide[(size_t)k] == 2) p->changeBound(c, Upper, oBnd[(size_t)k]);
+    else if (oSide[(size_t)k] == 1) p->changeBound(c, Lower, oBnd[(size_t)k]);
+    c->setBFlag(true);
+  }
+  if (cnt > 0) { if (changed) *changed = true; invalidate(); }
+  return (int)cnt;
 }
 
 std::string GpuBoundHandler::getName() const { return "GpuBoundHandler (FBBT on B200)"; }

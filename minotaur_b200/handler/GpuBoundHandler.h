@@ -111,6 +111,16 @@ public:
   void prefetchCandidates(RelaxationPtr rel, SolutionPoolPtr spool, const std::vector<std::vector<BoundChange> > &deltas);
   void clearCandidates();
 
+  /**
+   * LinearHandler::coeffImp_ (LinearHandler.cpp:600-704) for problem_, the detection on the device
+   * (mntr_gpu_root_coeff_imp: the reference's sequential semantics through dependency levels), the changes applied
+   * here exactly as the reference applies them: LinearFunction::incTerm with the same argument,
+   * Problem::changeBound on the row, Constraint::setBFlag(true).  Returns the number of improved rows; *changed is
+   * set when there is one.  Meant for a root presolve loop that runs this step on the GPU handler instead of in
+   * LinearHandler (setPreOptCoeffImp(false) there).
+   */
+  int coeffImprove(bool *changed);
+
   std::string getName() const;
   void writeStats(std::ostream &out) const;
 

@@ -159,6 +159,53 @@ static ProblemPtr readFlat(EnvPtr env, const char *path)
   return p;
 }
 
+// LinearHandler::coeffImp_ is protected: a probe
+struct CoeffProbe : public LinearHandler {
+  CoeffProbe(EnvPtr env, ProblemPtr p) : LinearHandler(env, p) {}
+  void run(bool *changed) { coeffImp_(changed); }
+};
+
+// variable upper / lower bound rows with loose big-M coefficients plus mixed one-sided rows (what coeffImp_ improves)
+static ProblemPtr makeBigM(EnvPtr env, int nBin, int nCont, int nRows)
+{
+  ProblemPtr p = (ProblemPtr) new Problem(env);
+  std::vector<VariablePtr> v;
+  for (int j = 0; j < nBin; ++j) v.push_back(p->newVariable(0.0, 1.0, Binary));
+  for (int j = 0; j < nCont; ++j) {
+    const double l = (double)((int)(urand() * 5) - 3);
+    v.push_back(p->newVariable(l, l + 1.0 + (int)(urand() * 11), Continuous));
+  }
+  int made = 0;
+  for (int j = nBin; j < nBin + nCont && made < nRows; ++j) {
+    if (urand() < 0.6) {
+      LinearFunctionPtr lf = (LinearFunctionPtr) new LinearFunction();
+      lf->addTerm(v[(size_t)(urand() * nBin)], -(v[(size_t)j]->getUb() + (int)(urand() * 6)));
+      lf->addTerm(v[(size_t)j], 1.0);
+      p->newConstraint((FunctionPtr) new Function(lf), -INFINITY, 0.0);
+      ++made;
+    }
+  }
+  while (made < nRows) {
+    LinearFunctionPtr lf = (LinearFunctionPtr) new LinearFunction();
+    const int k = 2 + (int)(urand() * 7);
+    double lo = 0.0, hi = 0.0;
+    for (int t = 0; t < k; ++t) {
+      const size_t j = (size_t)(urand() * (nBin + nCont));
+      if (lf->hasVar(v[j])) continue;
+      const double a = (j < (size_t)nBin ? 1.0 + (int)(urand() * 29) : 1.0 + (int)(urand() * 5)) * (urand() < 0.5 ? 1.0 : -1.0);
+      lf->addTerm(v[j], a);
+      lo += a > 0 ? a * v[j]->getLb() : a * v[j]->getUb();
+      hi += a > 0 ? a * v[j]->getUb() : a * v[j]->getLb();
+    }
+    if (lf->getNumTerms() < 2) { delete lf; continue; }
+    if (urand() < 0.5) p->newConstraint((FunctionPtr) new Function(lf), -INFINITY, std::floor(lo + (hi - lo) * (0.3 + 0.8 * urand())));
+    else p->newConstraint((FunctionPtr) new Function(lf), std::ceil(lo + (hi - lo) * (-0.1 + 0.8 * urand())), INFINITY);
+    ++made;
+  }
+  p->calculateSize();
+  return p;
+}
+
 // Root presolve through Presolver::solve (Presolver.cpp:91-182): the reference pair LinearHandler + NlPresHandler on one
 // copy of the problem, LinearHandler + GpuBoundHandler (reference order, round to nearest) on another.  Returns the
 // number of bounds that differ; prints what each run did.
@@ -168,8 +215,10 @@ static int rootPresolve(EnvPtr env, ProblemPtr pA, ProblemPtr pB, const char *wh
   for (VariableConstIterator it = pA->varsBegin(); it != pA->varsEnd(); ++it) { l0.push_back((*it)->getLb()); u0.push_back((*it)->getUb()); }
   HandlerVector hA, hB;
   LinearHandler *lhA = new LinearHandler(env, pA); NlPresHandler *nhA = new NlPresHandler(env, pA);
+  lhA->setModFlags(false, true); nhA->setModFlags(false, true);
   hA.push_back(lhA); hA.push_back(nhA);
   LinearHandler *lhB = new LinearHandler(env, pB); GpuBoundHandler *ghB = new GpuBoundHandler(env, pB, 0);
+  lhB->setModFlags(false, true);
   ghB->setMode(GpuBoundHandler::ReferenceOrder); ghB->setRoundNearest(true);
   hB.push_back(lhB); hB.push_back(ghB);
   Presolver prA(pA, env, hA), prB(pB, env, hB);
@@ -236,6 +285,10 @@ int main(int argc, char **argv)
       // reference: LinearHandler then NlPresHandler, one PCBProcessor::presolveNode_ pass
       LinearHandler lh(env, p);
       NlPresHandler nh(env, p);
+      // (Handler::modProb_ / modRel_ are uninitialised until set -- Handler.h:380-383 -- and a LinearHandler that finds
+      //  garbage `true` in modProb_ mirrors the relaxation's bounds into p: the solver mains always set them, Bnb.cpp:111,121)
+      lh.setModFlags(false, true);
+      nh.setModFlags(false, true);
       ModVector pm, rmA;
       bool infA = lh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)spool, pm, rmA);
       if (!infA && n_nl) infA = nh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)spool, pm, rmA);
@@ -265,6 +318,9 @@ int main(int argc, char **argv)
         } else ++n_inf;
       }
       n_mods += (int)rmB.size();
+      if (getenv("HANDLER_TEST_VERBOSE"))
+        printf("trial %d box %d: ref inf %d (%d mods), gpu inf %d (%d mods), cutoff %d\n", trial, box, (int)infA, (int)rmA.size(),
+               (int)infB, (int)rmB.size(), spool ? 1 : 0);
       // undo in reverse order restores the incoming box (Node.cpp:318-340)
       for (ModVector::reverse_iterator it = rmB.rbegin(); it != rmB.rend(); ++it) (*it)->undoToProblem(relB);
       for (int j = 0; j < n; ++j)
@@ -405,6 +461,7 @@ int main(int argc, char **argv)
         }
       }
       LinearHandler lh(env, pA); NlPresHandler nh(env, pA);
+      lh.setModFlags(false, true); nh.setModFlags(false, true);
       ModVector rmA, rmB;
       bool infA = lh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pm, rmA);
       if (!infA) infA = nh.presolveNode(relA, (NodePtr)0, (SolutionPoolPtr)0, pm, rmA);
@@ -485,6 +542,38 @@ int main(int argc, char **argv)
       }
       delete tA; delete tB;
     }
+  }
+  // ---- root step: coefficient improvement (LinearHandler::coeffImp_) through GpuBoundHandler::coeffImprove ----
+  {
+    int n_imp = 0;
+    for (int trial = 0; trial < 3; ++trial) {
+      const uint64_t keep = rng_state;
+      ProblemPtr pA = makeBigM(env, 30, 90, 300), pB = 0;
+      rng_state = keep;
+      pB = makeBigM(env, 30, 90, 300);
+      CoeffProbe lhA(env, pA);
+      bool chA = false, chB = false;
+      lhA.run(&chA);
+      GpuBoundHandler gB(env, pB, 0);
+      const int k = gB.coeffImprove(&chB);
+      CHECK(chA == chB, "coeffImprove: changed flags differ");
+      CHECK(pA->getNumCons() == pB->getNumCons(), "coeffImprove: constraint counts differ");
+      ConstraintConstIterator ia = pA->consBegin(), ib = pB->consBegin();
+      int diff = 0;
+      for (; ia != pA->consEnd() && ib != pB->consEnd(); ++ia, ++ib) {
+        if ((*ia)->getLb() != (*ib)->getLb() || (*ia)->getUb() != (*ib)->getUb()) ++diff;
+        LinearFunctionPtr la = (*ia)->getLinearFunction(), lb2 = (*ib)->getLinearFunction();
+        if (la->getNumTerms() != lb2->getNumTerms()) { ++diff; continue; }
+        VariableGroupConstIterator ta = la->termsBegin(), tb = lb2->termsBegin();
+        for (; ta != la->termsEnd(); ++ta, ++tb)
+          if (ta->first->getIndex() != tb->first->getIndex() || ta->second != tb->second) { ++diff; break; }
+      }
+      CHECK(diff == 0, "coeffImprove: %d rows differ from LinearHandler::coeffImp_", diff);
+      CHECK(k > 10, "coeffImprove: only %d rows improved", k);
+      n_imp += k;
+      delete pA; delete pB;
+    }
+    printf("handler_test: coeffImprove = LinearHandler::coeffImp_ on 3 big-M problems (%d improved rows, coefficients and row bounds bit for bit)\n", n_imp);
   }
   printf("handler_test: %d calls with row bounds changed in between, %d p_mods mirrored into the original problem\n", n_stale, n_pmods);
   printf("handler_test: %d comparisons (%d with an incumbent cut-off), %d infeasible, %d mods emitted; "
