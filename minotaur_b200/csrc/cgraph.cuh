@@ -556,11 +556,14 @@ __device__ __forceinline__ void sumsq_forward(const TapeView &t, double2 b0, dou
 
 // NlPresHandler::chkRed_ for one constraint (NlPresHandler.cpp:101-208, nlf branch):
 // returns 0 ok, 3 infeasible, 4 evaluation error
-template <class R>
+// SHAPED: every tape of the problem has one of the two straight-line shapes (classified at load time): the interpreter
+// and its per-thread node arrays are not compiled in (fewer registers, no spills: 12-warp CTAs at 80 registers spill
+// 400 bytes with the interpreter)
+template <class R, bool SHAPED = false>
 __device__ __forceinline__ int nl_chk_red(const ConsView &V, const double2 *bx, int64_t ld, double *nlb, double *nub)
 {
   const TapeView &t = V.t;
-  if (V.shape != kShapeGeneric) {
+  if (SHAPED || V.shape != kShapeGeneric) {
     const double2 b0 = bx[(int64_t)t.a0[0] * ld], b1 = bx[(int64_t)t.a0[1] * ld];     // both gathers in flight
     double nl[2], nu[2], ol, ou;
     if (V.shape == kShapeBilinear) bilinear_forward<R>(t, b0, b1, nl, nu, ol, ou);
@@ -570,6 +573,7 @@ __device__ __forceinline__ int nl_chk_red(const ConsView &V, const double2 *bx, 
     const double impl_lb = R::add_lo(ol, lfl), impl_ub = R::add_hi(ou, lfu);
     return (impl_ub + 1e-6 < V.c_lb || impl_lb - 1e-6 > V.c_ub) ? 3 : 0;
   }
+  if constexpr (SHAPED) return 4;
   int error = 0;
   tape_forward<R>(V, nlb, nub, bx, ld, error);
   if (error != 0) return 4;
@@ -618,7 +622,7 @@ __device__ __forceinline__ int quad_chk_red(const NlDev &N, int q, const double2
 // NlPresHandler::varBndsFromCons_ for one constraint (NlPresHandler.cpp:1771-1803) = lf bounds +
 // CGraph::varBoundMods + in-place application of the mods.  returns 0 ok, 3 infeasible, 4 error;
 // n_mods receives the number of bound changes.
-template <class R>
+template <class R, bool SHAPED = false>
 __device__ __forceinline__ int nl_var_bound_mods(const ConsView &V, double2 *bx, int64_t ld, double *nlb,
                                                  double *nub, int &n_mods, unsigned &moved_int)
 {
@@ -628,7 +632,7 @@ __device__ __forceinline__ int nl_var_bound_mods(const ConsView &V, double2 *bx,
   lin_part_bounds<R>(V, bx, ld, lfl, lfu);
   const double ub_in = R::sub_hi(V.c_ub, lfl), lb_in = R::sub_lo(V.c_lb, lfu);
   int error = 0;
-  if (V.shape != kShapeGeneric) {
+  if (SHAPED || V.shape != kShapeGeneric) {
     double2 *p0 = bx + (int64_t)t.a0[0] * ld, *p1 = bx + (int64_t)t.a0[1] * ld;
     double2 b0 = *p0, b1 = *p1;
     double nl[2], nu[2], ol, ou;
@@ -697,6 +701,7 @@ __device__ __forceinline__ int nl_var_bound_mods(const ConsView &V, double2 *bx,
     if (ch1) *p1 = b1;
     return 0;
   }
+  if constexpr (SHAPED) return 4;
   tape_forward<R>(V, nlb, nub, bx, ld, error);
   if (error > 0) return 4;
   const int o = t.nn - 1;

@@ -41,6 +41,7 @@ __host__ __device__ __forceinline__ int row_end(int2 info) { return info.x + ((i
 // CGraph tapes (see include/mntr_gpu.h for the node order contract)
 struct NlDev {
   int32_t n_cons;
+  int32_t all_shaped;       // every tape has one of the two straight-line shapes of cgraph.cuh (classified at load time)
   const int32_t *tape_ptr;  // [n_cons+1]
   const uint8_t *op;
   const int32_t *arg0, *arg1;

@@ -768,7 +768,7 @@ __device__ __noinline__ void fix_obj_bins(const LinDev &P, double2 *bx, int64_t 
   }
 }
 
-template <class R>
+template <class R, bool SHAPED>
 __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N, double2 *bx, int64_t ld, TileShared &sh,
                                                 bool active, bool &any_change, BatchStage &TS, unsigned &my_evals)
 {
@@ -776,7 +776,7 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
   const TileTeam team = make_team();
   const int warp = team.gwarp;
   const double2 *tile_base = bx - lane;
-  double nlb[kMaxTape], nub[kMaxTape];
+  double nlb[SHAPED ? 1 : kMaxTape], nub[SHAPED ? 1 : kMaxTape];      // the interpreter's node intervals
   if (warp == 0) sh.changed[lane] = 1;
   team.sync();
   int iters = 1, my_rounds = 0;
@@ -799,7 +799,7 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
         for (int k = 0; k < B.n; ++k) {
           const ConsView V = batch_constraint(N, TS, B, k, c0 + k);
           if (run && sh.verdict[lane] == 0) {
-            const int st = nl_chk_red<R>(V, bx, ld, nlb, nub);
+            const int st = nl_chk_red<R, SHAPED>(V, bx, ld, nlb, nub);
             ++my_evals;
             if (st != 0) sh.verdict[lane] = st;
           }
@@ -831,7 +831,7 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
           const ConsView V = batch_constraint(N, TS, B, k, c0 + k);
           if (run && sh.verdict[lane] == 0) {
             int n_mods = 0; unsigned dummy = 0;
-            const int st = nl_var_bound_mods<R>(V, bx, ld, nlb, nub, n_mods, dummy);
+            const int st = nl_var_bound_mods<R, SHAPED>(V, bx, ld, nlb, nub, n_mods, dummy);
             ++my_evals;
             if (st != 0) sh.verdict[lane] = st;
             else if (n_mods > 0) sh.changed[lane] = 1;
@@ -858,7 +858,7 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
 // dynamic shared memory per CTA) and carries no tape interpreter.  HAS_NL = true gathers the linear rows' bounds
 // directly (use_tma == 0: no dynamic shared memory), which leaves the L1 to the interpreter's per-thread node
 // intervals, and stages the tapes instead.
-template <class R, bool HAS_NL>
+template <class R, bool HAS_NL, bool SHAPED = false>
 __global__ void __launch_bounds__(HAS_NL ? kBatchThreads : kLinWarps * 32, 2)
 fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int max_rounds, int lin_enabled,
                             int nl_enabled_arg, int use_tma)
@@ -909,7 +909,7 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
                                         my_nnz, lin_changed, seg_phase);
     if constexpr (HAS_NL) {
       // the NL instantiation uses the dynamic shared memory for the tape batches (no TMA segments: use_tma == 0)
-      if (nl_enabled) my_rounds += nl_tile_presolve<R>(P, N, bx, ld, sh, active, nl_changed, reinterpret_cast<BatchStage *>(dyn_smem)[wl], my_evals);
+      if (nl_enabled) my_rounds += nl_tile_presolve<R, SHAPED>(P, N, bx, ld, sh, active, nl_changed, reinterpret_cast<BatchStage *>(dyn_smem)[wl], my_evals);
     }
     // fixpoint mode with both handlers: go round again while the nonlinear sweeps still move bounds
     const bool again = (loop_mode == 0) && lin_enabled && nl_enabled && nl_changed && sh.verdict[lane] == 0 &&
@@ -1135,6 +1135,13 @@ cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, 
   if (nl_enabled) {
     cfg.blockDim = dim3(kBatchThreads);
     cfg.dynamicSmemBytes = kBatchWarps * sizeof(BatchStage);
+    if (nl.all_shaped) {              // every tape is [Var,Var,Mult] or [Var,Var,Sqr,Sqr,SumList]: no interpreter
+      cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, true, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+      if (e != cudaSuccess) return e;
+      return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, true, true>, P, nl, io, loop_mode, max_rounds, lin_enabled,
+                                nl_enabled, 0);
+    }
     cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
     if (e != cudaSuccess) return e;

@@ -640,8 +640,18 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
   std::vector<int32_t> tp(n_cons + 1, 0), lp(n_cons + 1, 0), a0v, a1v, chv, lcv;
   std::vector<uint8_t> opv;
   std::vector<double> cnv, lvv, clb(n_cons), cub(n_cons);
+  bool all_shaped = true;         // every tape is [Var,Var,Mult] or [Var,Var,Sqr,Sqr,SumList(2,3)] (the rule of stage_batch, cgraph.cuh)
   for (int32_t q = 0; q < n_cons; ++q) {
     const int32_t c = perm[q], b = tape_ptr[c], nn = tape_ptr[c + 1] - b;
+    {
+      const uint8_t *o = op + b; const int32_t *x0 = arg0 + b, *x1 = arg1 + b;
+      int nv = 0;
+      while (nv < nn && o[nv] == OpVar) ++nv;
+      const bool bil = nv == 2 && nn == 3 && o[2] == OpMult && (unsigned)x0[2] < 2u && (unsigned)x1[2] < 2u && x0[2] != x1[2];
+      const bool ssq = nv == 2 && nn == 5 && o[2] == OpSqr && o[3] == OpSqr && o[4] == OpSumList && (unsigned)x0[2] < 2u &&
+                       (unsigned)x0[3] < 2u && x1[4] - x0[4] == 2 && child[x0[4]] == 2 && child[x0[4] + 1] == 3;
+      all_shaped = all_shaped && (bil || ssq);
+    }
     for (int32_t i = 0; i < nn; ++i) {
       opv.push_back(op[b + i]); cnv.push_back(cnst[b + i]);
       if (op[b + i] == OpSumList) {
@@ -660,6 +670,8 @@ int mntr_gpu_load_cgraph(mntr_gpu_ctx *ctx, int32_t n_cons, const int32_t *tape_
   N = NlDev{};
   restore_quad(N);
   N.n_cons = n_cons; N.max_nodes = max_nodes; N.n_levels = n_levels;
+  N.all_shaped = all_shaped ? 1 : 0;
+  if (const char *e = getenv("MNTR_GPU_NO_SHAPED_KERNEL")) if (e[0] == '1') N.all_shaped = 0;
   int rc;
   if ((rc = dev_upload(ctx, ctx->nl_allocs, tp.data(), tp.size(), &N.tape_ptr))) return rc;
   if ((rc = dev_upload(ctx, ctx->nl_allocs, opv.data(), opv.size(), &N.op))) return rc;
