@@ -884,7 +884,8 @@ def block_c3(X):
     if X.world > 1 or args.c3_boxes != C3_BOXES:
         traffic = None                    # the capture is of the whole batch on one GPU
     out["roofline"]["traffic"] = traffic
-    out["roofline"]["traffic_source"] = f"static, from the committed ncu capture ({tsrc}); not measured in this run"
+    out["roofline"]["traffic_source"] = (f"static, from the committed ncu capture ({tsrc}); not measured in this run" if traffic is not None
+                                         else "none: the committed capture is of the whole batch on one GPU")
     if X.world > 1:
         # the whole batch on ONE GPU in the same run (rank 0 alone), so the strong-scaling base is measured here
         X.barrier()
