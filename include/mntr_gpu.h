@@ -314,6 +314,20 @@ int mntr_gpu_load_quad_relations(mntr_gpu_ctx *ctx, int32_t n_sq, const int32_t 
 int mntr_gpu_quad_simple_presolve(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub, int32_t rounding,
                                   int32_t *n_mods, int32_t *n_inconsistent);
 
+/* The propagation loop of QuadHandler::presolveNode (QuadHandler.cpp:1204-1239) over the loaded relations, on each of
+ * n_boxes boxes (lb / ub box-major [n_boxes][n], updated in place): the sweep { propSqrBnds_ (:1361-1395) over the
+ * squares, propBilBnds_ (:1271-1301) over the products } repeated while it moves a bound, every step through the
+ * relaxation-aware updatePBounds_ (:3248-3320: integer rounding; a side moves when it improves by more than 1e-8
+ * absolute and 1e-7 relative).  verdict [n_boxes]: 1 = a step found inconsistent bounds (the reference returns
+ * "infeasible" there; the bounds of such a box are not a result), else 0.  n_mods (may be NULL): Modification objects
+ * the reference would push to p_mods (one per step that moves a variable, whether one side or both).  n_sweeps (may
+ * be NULL): sweeps run (pStats_.iters).  max_sweeps <= 0: no cap, like the reference.  Not included, because they
+ * change structure or belong to another algorithm: tightenQuad_ of a handler's first node (:1241-1250) and the refresh
+ * of the McCormick rows (upSqCon_ / upBilCon_, :1252-1257) -- the caller runs the latter on the boxes it keeps.
+ * MNTR_ROUND_NEAREST: the reference's result bit for bit; MNTR_ROUND_DIRECTED: rounded outward. */
+int mntr_gpu_quad_presolve_node(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub, int32_t rounding,
+                                int32_t max_sweeps, int32_t *verdict, int32_t *n_mods, int32_t *n_sweeps);
+
 /* statistics of the last tighten call */
 int mntr_gpu_get_stats(const mntr_gpu_ctx *ctx, mntr_gpu_stats *out);
 

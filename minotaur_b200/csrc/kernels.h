@@ -123,5 +123,8 @@ struct QRelDev {
 };
 cudaError_t launch_quad_relations(const QRelDev &Q, double2 *boxes, int64_t ld, int32_t n_boxes, bool directed, int32_t *n_mods,
                                   int32_t *n_bad, cudaStream_t stream);
+// the propagation loop of QuadHandler::presolveNode over the same relations: verdict 1 = infeasible, Modification count, sweeps
+cudaError_t launch_quad_node(const QRelDev &Q, double2 *boxes, int64_t ld, int32_t n_boxes, bool directed, int32_t max_sweeps,
+                             int32_t *verdict, int32_t *n_mods, int32_t *n_sweeps, cudaStream_t stream);
 
 }  // namespace mntr

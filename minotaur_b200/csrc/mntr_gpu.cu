@@ -1763,6 +1763,41 @@ int mntr_gpu_quad_simple_presolve(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb
   return MNTR_OK;
 }
 
+int mntr_gpu_quad_presolve_node(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub, int32_t rounding, int32_t max_sweeps,
+                                int32_t *verdict, int32_t *n_mods, int32_t *n_sweeps)
+{
+  if (!ctx) return MNTR_E_ARG;
+  if (!ctx->lin_loaded) return fail(ctx, MNTR_E_STATE, "quad_presolve_node: no problem loaded");
+  if (n_boxes <= 0 || !lb || !ub || !verdict) return fail(ctx, MNTR_E_ARG, "quad_presolve_node: bad argument");
+  if (rounding != MNTR_ROUND_DIRECTED && rounding != MNTR_ROUND_NEAREST) return fail(ctx, MNTR_E_ARG, "quad_presolve_node: bad rounding");
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_batch(ctx, n_boxes, true))) return rc;
+  if ((rc = mntr_gpu_boxes_upload(ctx, n_boxes, lb, ub, ctx->d_boxes))) return rc;
+  const int64_t ld = mntr_gpu_box_ld(n_boxes);
+  cudaStream_t s = ctx->stream;
+  int32_t *d_sweeps = (int32_t *)ctx->d_nnzb;                  // [ld] long long: room for ld int32
+  CU(cudaMemsetAsync(ctx->d_verdict, 0, sizeof(int32_t) * (size_t)ld, s));
+  CU(cudaMemsetAsync(ctx->d_rounds, 0, sizeof(int32_t) * (size_t)ld, s));
+  CU(cudaMemsetAsync(d_sweeps, 0, sizeof(int32_t) * (size_t)ld, s));
+  CU(cudaEventRecord(ctx->ev[1], s));
+  if (ctx->qrel_loaded) {
+    QRelDev Q = ctx->qrel;
+    Q.var_type = ctx->lin.var_type;
+    CU(launch_quad_node(Q, ctx->d_boxes, ld, n_boxes, rounding == MNTR_ROUND_DIRECTED, max_sweeps, ctx->d_verdict, ctx->d_rounds,
+                        d_sweeps, s));
+  }
+  CU(cudaEventRecord(ctx->ev[2], s));
+  CU(cudaMemcpyAsync(verdict, ctx->d_verdict, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  if (n_mods) CU(cudaMemcpyAsync(n_mods, ctx->d_rounds, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  if (n_sweeps) CU(cudaMemcpyAsync(n_sweeps, d_sweeps, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if ((rc = mntr_gpu_boxes_download(ctx, n_boxes, ctx->d_boxes, lb, ub))) return rc;
+  ctx->stats = mntr_gpu_stats{};
+  ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  return MNTR_OK;
+}
+
 void *mntr_gpu_alloc_host(mntr_gpu_ctx *ctx, int64_t bytes)
 {
   if (!ctx || bytes <= 0) return nullptr;

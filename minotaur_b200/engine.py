@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "mntr_gpu_tighten_single_dev", "mntr_gpu_stream",
     "mntr_gpu_nccl_unique_id", "mntr_gpu_comm_init", "mntr_gpu_comm_destroy",
     "mntr_gpu_boxes_from_deltas", "mntr_gpu_alloc_host", "mntr_gpu_free_host", "mntr_gpu_update_row_bounds",
-    "mntr_gpu_load_quad", "mntr_gpu_group_load_quad", "mntr_gpu_root_dup_rows", "mntr_gpu_root_redundant_rows", "mntr_gpu_root_coeff_imp", "mntr_gpu_load_quad_relations", "mntr_gpu_quad_simple_presolve",
+    "mntr_gpu_load_quad", "mntr_gpu_group_load_quad", "mntr_gpu_root_dup_rows", "mntr_gpu_root_redundant_rows", "mntr_gpu_root_coeff_imp", "mntr_gpu_load_quad_relations", "mntr_gpu_quad_simple_presolve", "mntr_gpu_quad_presolve_node",
     "mntr_gpu_group_create", "mntr_gpu_group_destroy", "mntr_gpu_group_size", "mntr_gpu_group_member",
     "mntr_gpu_group_last_error", "mntr_gpu_group_load_linear", "mntr_gpu_group_load_cgraph",
     "mntr_gpu_group_set_cutoff", "mntr_gpu_group_set_incumbent", "mntr_gpu_group_tighten_nodes",
@@ -112,6 +112,7 @@ def load_library() -> C.CDLL:
     L.mntr_gpu_root_redundant_rows.argtypes = [vp, _dp, _dp, _bp, _lp]
     L.mntr_gpu_load_quad_relations.argtypes = [vp, C.c_int32, _ip, _ip, C.c_int32, _ip, _ip, _ip]
     L.mntr_gpu_quad_simple_presolve.argtypes = [vp, C.c_int32, _dp, _dp, C.c_int32, _ip, _ip]
+    L.mntr_gpu_quad_presolve_node.argtypes = [vp, C.c_int32, _dp, _dp, C.c_int32, C.c_int32, _ip, _ip, _ip]
     L.mntr_gpu_root_coeff_imp.argtypes = [vp, C.c_int32, C.c_int32, _ip, _ip, _dp, _dp, _dp, _bp, _dp, _dp, C.c_int64, _ip, _ip, _dp,
                                           _ip, _dp, _dp, _lp, _ip, _ip]
     L.mntr_gpu_group_load_quad.argtypes = [vp, C.c_int32, _ip, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp]
@@ -310,6 +311,16 @@ class GpuBoundEngine:
         nm = np.zeros(nb, np.int32); bad = np.zeros(nb, np.int32)
         self._check(self.L.mntr_gpu_quad_simple_presolve(self.h, nb, _d(lb), _d(ub), rounding, _i(nm), _i(bad)), "quad_simple_presolve")
         return lb, ub, nm, bad, self.stats().kernel_ms
+
+    def quad_presolve_node(self, lb, ub, rounding=ROUND_NEAREST, max_sweeps=0):
+        """The propagation loop of QuadHandler::presolveNode on boxes [n_boxes][n]:
+        (lb, ub, verdict, n_mods, n_sweeps, kernel_ms)."""
+        lb = np.array(np.atleast_2d(lb), np.float64, order="C"); ub = np.array(np.atleast_2d(ub), np.float64, order="C")
+        nb = lb.shape[0]
+        v = np.zeros(nb, np.int32); nm = np.zeros(nb, np.int32); ns = np.zeros(nb, np.int32)
+        self._check(self.L.mntr_gpu_quad_presolve_node(self.h, nb, _d(lb), _d(ub), rounding, max_sweeps, _i(v), _i(nm), _i(ns)),
+                    "quad_presolve_node")
+        return lb, ub, v, nm, ns, self.stats().kernel_ms
 
     def update_row_bounds(self, row_lb, row_ub):
         """New bounds for the loaded rows (same order as load_linear): m doubles each way, no re-flattening."""

@@ -876,3 +876,51 @@ def make_quad_relations(n_x: int, n_sq: int, n_bil: int, seed: int):
             lb[y] = float(np.floor(lo + (hi - lo) * rng.uniform(0.0, 0.4))) - 0.5
             ub[y] = float(np.ceil(lo + (hi - lo) * rng.uniform(0.6, 1.0))) + 0.5
     return QuadRelations(sq_x, sq_y, b_x0, b_x1, b_y), var_type, lb, ub
+
+
+def make_quad_relations_planted(n_x: int, n_sq: int, n_bil: int, seed: int):
+    """make_quad_relations with a planted point: x* inside the box (integral for integer variables), y* = x*^2 or
+    x0* x1*, and every auxiliary's bounds widened to contain y* -- so the ROOT box is consistent and the propagation loop
+    of QuadHandler::presolveNode (/root/reference/src/base/QuadHandler.cpp:1214-1239) runs to its fixpoint instead of
+    stopping at the first relation.  Returns (QuadRelations, var_type, lb, ub, xstar)."""
+    rel, var_type, lb, ub = make_quad_relations(n_x, n_sq, n_bil, seed)
+    rng = np.random.default_rng([seed, 59])
+    n = len(lb)
+    xs = np.zeros(n)
+    u = rng.random(n_x)
+    xs[:n_x] = lb[:n_x] + u * (ub[:n_x] - lb[:n_x])
+    isint = var_type[:n_x] != 4
+    xs[:n_x][isint] = np.clip(np.round(xs[:n_x][isint]), np.ceil(lb[:n_x][isint]), np.floor(ub[:n_x][isint]))
+    xs[rel.sq_y] = xs[rel.sq_x] ** 2
+    xs[rel.b_y] = xs[rel.b_x0] * xs[rel.b_x1]
+    for y in np.concatenate([rel.sq_y, rel.b_y]):
+        lb[y] = min(lb[y], np.floor(xs[y]) - 0.5)
+        ub[y] = max(ub[y], np.ceil(xs[y]) + 0.5)
+    lb[rel.sq_y] = np.maximum(lb[rel.sq_y], 0.0)           # the reference asserts y.lb >= 0 for a square (:1376)
+    return rel, var_type, lb, ub, xs
+
+
+def quad_node_boxes(lb, ub, n_x: int, nb: int, seed: int, xstar=None, keep: float = 0.7):
+    """nb node boxes on the root box (lb, ub): box 0 is the root; the others move a few original variables' bounds
+    inward by one unit (a branching), a fraction ``keep`` of them only where the planted point stays inside (those boxes
+    cannot be infeasible), the rest blindly and with a few variables fixed at an end of their range (some of those
+    boxes are infeasible)."""
+    rng = np.random.default_rng([seed, 61])
+    L = np.tile(lb, (nb, 1)); U = np.tile(ub, (nb, 1))
+    for b in range(1, nb):
+        safe = xstar is not None and rng.random() < keep
+        for j in rng.choice(n_x, 6, replace=False):
+            if not (np.isfinite(L[b, j]) and np.isfinite(U[b, j])) or U[b, j] - L[b, j] < 2:
+                continue
+            if L[b, j] < 0 < U[b, j]:
+                continue                                   # keep straddling factors straddling (BoundsOnRecip's zero end points)
+            if rng.random() < 0.5:
+                if not safe or xstar[j] >= L[b, j] + 1.0: L[b, j] += 1.0
+            else:
+                if not safe or xstar[j] <= U[b, j] - 1.0: U[b, j] -= 1.0
+        if not safe:                                       # ... and a few variables fixed at an end of their range
+            for j in rng.choice(n_x, 8, replace=False):
+                if np.isfinite(L[b, j]) and np.isfinite(U[b, j]) and not (L[b, j] < 0 < U[b, j]):
+                    if rng.random() < 0.5: U[b, j] = L[b, j]
+                    else: L[b, j] = U[b, j]
+    return L, U

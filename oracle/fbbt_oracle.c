@@ -1206,3 +1206,76 @@ int64_t orc_quad_simple_presolve(int32_t n_sq, const int32_t *sq_x, const int32_
   if (n_inconsistent) *n_inconsistent = bad;
   return n_mods;
 }
+
+
+/* ---- QuadHandler::presolveNode's propagation loop (QuadHandler.cpp:1214-1239): sweeps { propSqrBnds_ over x2Funs_
+ *      (:1361-1395), propBilBnds_ over x0x1Funs_ (:1271-1301) } in place, repeated while a sweep changed a bound; the
+ *      first inconsistent step ends the call with "infeasible" (:1224, :1233).  Every step goes through the
+ *      relaxation-aware updatePBounds_ (:3248-3320): integer rounding, consistency test with bTol, then
+ *        both sides move   if each side improves by more than bTol AND by more than rTol relative   (one VarBoundMod2),
+ *        else the lower    if it does                                                                (one VarBoundMod),
+ *        else the upper    if it does                                                                (one VarBoundMod)
+ *      -- i.e. each side moves exactly when its own two tests pass; the three-way split only decides how many
+ *      Modification objects are pushed.  (The Problem-side variant of simplePresolve uses aTol = 1e-6 for the lower
+ *      bound; this one uses bTol = 1e-8 for both.)  What follows the loop in presolveNode -- tightenQuad_ on the first
+ *      call (:1241-1250) and the McCormick row refresh upSqCon_/upBilCon_ (:1252-1257) -- is not part of this path.
+ *      Returns 1 when infeasible (the box is then undefined: the reference stops mid-sweep), else 0;
+ *      *n_mods = Modification objects pushed, *n_sweeps = pStats_.iters increments.  max_sweeps <= 0: no cap. ---- */
+static int qh_update_node(const uint8_t *var_type, double *lbv, double *ubv, int32_t v, double lb, double ub, int64_t *n_mods,
+                          int *changed)
+{
+  const double bTol = 1e-8, rTol = 1e-7;
+  const int ty = var_type[v];
+  if (ty == ORC_BINARY || ty == ORC_IMPLBIN || ty == ORC_INTEGER || ty == ORC_IMPLINT) { ub = floor(ub); lb = ceil(lb); }
+  if (lb > ubv[v] + bTol || ub < lbv[v] - bTol) return -1;
+  const int lo = lb > lbv[v] + bTol && (lbv[v] == -INFINITY || lb > lbv[v] + rTol * fabs(lbv[v]));
+  const int up = ub < ubv[v] - bTol && (ubv[v] == INFINITY || ub < ubv[v] - rTol * fabs(ubv[v]));
+  if (lo && up) { lbv[v] = lb; ubv[v] = ub; }
+  else if (lo) lbv[v] = lb;
+  else if (up) ubv[v] = ub;
+  if (lo || up) { ++*n_mods; *changed = 1; }
+  return 0;
+}
+
+int32_t orc_quad_presolve_node(int32_t n_sq, const int32_t *sq_x, const int32_t *sq_y, int32_t n_bil, const int32_t *b_x0,
+                               const int32_t *b_x1, const int32_t *b_y, const uint8_t *var_type, double *lbv, double *ubv,
+                               int32_t max_sweeps, int64_t *n_mods_out, int32_t *n_sweeps_out)
+{
+  const double bTol = 1e-8;
+  int64_t n_mods = 0;
+  int32_t sweeps = 0, inf = 0;
+  int changed = 1;
+  while (changed && !inf && (max_sweeps <= 0 || sweeps < max_sweeps)) {
+    ++sweeps;
+    changed = 0;
+    for (int32_t k = 0; k < n_sq && !inf; ++k) {                                       /* propSqrBnds_ :1361-1395 */
+      const int32_t x = sq_x[k], y = sq_y[k];
+      double lb, ub;
+      orc_bounds_on_square(lbv[x], ubv[x], &lb, &ub);
+      if (qh_update_node(var_type, lbv, ubv, y, lb, ub, &n_mods, &changed) < 0) { inf = 1; break; }
+      if (ubv[y] > bTol) {
+        ub = sqrt(ubv[y]);
+        lb = -ub;
+        if (lbv[x] > -sqrt(lbv[y]) + bTol) lb = sqrt(lbv[y]);
+        if (qh_update_node(var_type, lbv, ubv, x, lb, ub, &n_mods, &changed) < 0) inf = 1;
+      } else if (ubv[y] < -bTol) {
+        inf = 1;
+      } else {
+        if (qh_update_node(var_type, lbv, ubv, x, 0.0, 0.0, &n_mods, &changed) < 0) inf = 1;
+      }
+    }
+    for (int32_t k = 0; k < n_bil && !inf; ++k) {                                      /* propBilBnds_ :1271-1301 */
+      const int32_t x0 = b_x0[k], x1 = b_x1[k], y = b_y[k];
+      double lb, ub;
+      orc_bounds_on_product(1, lbv[x0], ubv[x0], lbv[x1], ubv[x1], &lb, &ub);
+      if (qh_update_node(var_type, lbv, ubv, y, lb, ub, &n_mods, &changed) < 0) { inf = 1; break; }
+      orc_bounds_on_div(lbv[y], ubv[y], lbv[x0], ubv[x0], &lb, &ub);
+      if (qh_update_node(var_type, lbv, ubv, x1, lb, ub, &n_mods, &changed) < 0) { inf = 1; break; }
+      orc_bounds_on_div(lbv[y], ubv[y], lbv[x1], ubv[x1], &lb, &ub);
+      if (qh_update_node(var_type, lbv, ubv, x0, lb, ub, &n_mods, &changed) < 0) inf = 1;
+    }
+  }
+  if (n_mods_out) *n_mods_out = n_mods;
+  if (n_sweeps_out) *n_sweeps_out = sweeps;
+  return inf;
+}

@@ -158,6 +158,8 @@ class Oracle:
         L.orc_root_coeff_imp.restype = C.c_int64
         L.orc_quad_simple_presolve.argtypes = [C.c_int32, _ip, _ip, C.c_int32, _ip, _ip, _ip, _bp, _dp, _dp, _lp]
         L.orc_quad_simple_presolve.restype = C.c_int64
+        L.orc_quad_presolve_node.argtypes = [C.c_int32, _ip, _ip, C.c_int32, _ip, _ip, _ip, _bp, _dp, _dp, C.c_int32, _lp, _ip]
+        L.orc_quad_presolve_node.restype = C.c_int32
         L.orc_nl_sweep.argtypes = [C.POINTER(OrcNl), _dp, _dp, C.POINTER(C.c_int64)]
         L.orc_nl_sweep.restype = C.c_int32
         L.orc_node_presolve.argtypes = [C.POINTER(OrcLin), C.POINTER(OrcNl), _dp, _dp, C.POINTER(OrcResult)]
@@ -254,6 +256,17 @@ class Oracle:
         k = int(self.lib.orc_quad_simple_presolve(len(rel.sq_x), _i(a[0]), _i(a[1]), len(rel.b_x0), _i(a[2]), _i(a[3]), _i(a[4]),
                                                   _b(vt), _d(lb), _d(ub), bad.ctypes.data_as(_lp)))
         return lb, ub, k, int(bad[0])
+
+    def quad_presolve_node(self, rel, var_type, lb, ub, max_sweeps=0):
+        """The propagation loop of QuadHandler::presolveNode restated (sweeps to the fixpoint, first inconsistency ends
+        it).  Returns (lb, ub, infeasible, n_mods, n_sweeps)."""
+        lb = np.array(lb, np.float64); ub = np.array(ub, np.float64)
+        vt = np.ascontiguousarray(var_type, np.uint8)
+        nm = np.zeros(1, np.int64); ns = np.zeros(1, np.int32)
+        a = [np.ascontiguousarray(x if len(x) else np.zeros(1), np.int32) for x in (rel.sq_x, rel.sq_y, rel.b_x0, rel.b_x1, rel.b_y)]
+        inf = int(self.lib.orc_quad_presolve_node(len(rel.sq_x), _i(a[0]), _i(a[1]), len(rel.b_x0), _i(a[2]), _i(a[3]), _i(a[4]),
+                                                  _b(vt), _d(lb), _d(ub), max_sweeps, nm.ctypes.data_as(_lp), _i(ns)))
+        return lb, ub, inf, int(nm[0]), int(ns[0])
 
     # ---- nonlinear ----
     def nl_compute_bounds(self, tapes, c, lb, ub):
@@ -381,6 +394,8 @@ class Reference:
             L.ref_quad_simple_presolve.restype = C.c_int64
             L.ref_quad_simple_presolve.argtypes = [C.c_int32, _bp, _dp, _dp, C.c_int32, _ip, _ip, C.c_int32, _ip, _ip, _ip]
             L.ref_coeff_imp.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _dp, _ip, _dp]
+            L.ref_quad_presolve_node.argtypes = [C.c_int32, _bp, _dp, _dp, C.c_int32, _ip, _ip, C.c_int32, _ip, _ip, _ip, C.c_int32,
+                                                 _dp, _dp, _ip, _lp]
             L.ref_destroy.argtypes = [C.c_void_p]
             cls._lib = L
         return cls._lib
@@ -518,6 +533,20 @@ class Reference:
         k = int(cls.lib().ref_quad_simple_presolve(len(lb), _b(vt), _d(lb), _d(ub), len(rel.sq_x), _i(a[0]), _i(a[1]),
                                                    len(rel.b_x0), _i(a[2]), _i(a[3]), _i(a[4])))
         return lb, ub, k
+
+    @classmethod
+    def quad_presolve_node(cls, rel, var_type, root_lb, root_ub, L, U):
+        """The reference's own QuadHandler::presolveNode (as at every node after the first: no tightenQuad_) on the boxes
+        L, U [n_boxes][n] of a problem built on the root box.  Returns (lb, ub, verdict, n_mods)."""
+        L = np.array(L, np.float64, ndmin=2); U = np.array(U, np.float64, ndmin=2)
+        nb, n = L.shape
+        vt = np.ascontiguousarray(var_type, np.uint8)
+        rl = np.ascontiguousarray(root_lb, np.float64); ru = np.ascontiguousarray(root_ub, np.float64)
+        a = [np.ascontiguousarray(x if len(x) else np.zeros(1), np.int32) for x in (rel.sq_x, rel.sq_y, rel.b_x0, rel.b_x1, rel.b_y)]
+        verdict = np.zeros(nb, np.int32); nm = np.zeros(nb, np.int64)
+        cls.lib().ref_quad_presolve_node(n, _b(vt), _d(rl), _d(ru), len(rel.sq_x), _i(a[0]), _i(a[1]), len(rel.b_x0), _i(a[2]),
+                                         _i(a[3]), _i(a[4]), nb, _d(L), _d(U), _i(verdict), nm.ctypes.data_as(_lp))
+        return L, U, verdict, nm
 
     def coeff_imp(self, lb, ub, cap=1 << 20):
         """The reference's own LinearHandler::coeffImp_ on the box.  Modifies the problem (use a fresh Reference).

@@ -43,6 +43,7 @@
 #include "Problem.h"
 #include "QuadraticFunction.h"
 #include "Reader.h"
+#include "Relaxation.h"
 #include "SolutionPool.h"
 #include "Types.h"
 #include "VarBoundMod.h"
@@ -293,6 +294,68 @@ int64_t ref_quad_simple_presolve(int32_t n, const uint8_t *var_type, double *lb,
   delete p;
   delete env;
   return n_mods;
+}
+
+/* The reference's own QuadHandler::presolveNode (QuadHandler.cpp:1204-1269) on a batch of boxes.  A problem of n
+ * variables with the ROOT box (root_lb, root_ub) receives the relations through QuadHandler::addConstraint; the
+ * relaxation is built the way NodeIncRelaxer does for this handler (variables cloned, then QuadHandler::relaxInitInc:
+ * the McCormick rows).  For every box the bounds of the problem's and the relaxation's variables are set and
+ * presolveNode is called with setModFlags(false, true), Bnb's setting.  bStats_.niters is preset to 1: the handler
+ * behaves as at every node after the first, i.e. without tightenQuad_ (:1241, doQT_ is false by default), so the call
+ * is the propagation loop plus the refresh of the McCormick rows (upSqCon_/upBilCon_, which do not touch variable
+ * bounds).  lb/ub [n_boxes][n] are updated in place; verdict[b] = 1 when presolveNode returned true (infeasible: the
+ * box is then whatever the reference had reached); n_mods[b] = p_mods.size(). */
+int32_t ref_quad_presolve_node(int32_t n, const uint8_t *var_type, const double *root_lb, const double *root_ub, int32_t n_sq,
+                               const int32_t *sq_x, const int32_t *sq_y, int32_t n_bil, const int32_t *b_x0, const int32_t *b_x1,
+                               const int32_t *b_y, int32_t n_boxes, double *lb, double *ub, int32_t *verdict, int64_t *n_mods)
+{
+  EnvPtr env = (EnvPtr) new Environment();
+  int err = 0;
+  env->startTimer(err);
+  env->setLogLevel(LogNone);
+  ProblemPtr p = (ProblemPtr) new Problem(env);
+  std::vector<VariablePtr> vars;
+  for (int32_t j = 0; j < n; ++j) vars.push_back(p->newVariable(root_lb[j], root_ub[j], (VariableType)var_type[j]));
+  QuadHandler *qh = new QuadHandler(env, p);
+  for (int32_t k = 0; k < n_sq + n_bil; ++k) {
+    const bool sq = k < n_sq;
+    VariablePtr y = vars[sq ? sq_y[k] : b_y[k - n_sq]];
+    VariablePtr x0 = vars[sq ? sq_x[k] : b_x0[k - n_sq]], x1 = vars[sq ? sq_x[k] : b_x1[k - n_sq]];
+    LinearFunctionPtr lf = (LinearFunctionPtr) new LinearFunction();
+    lf->addTerm(y, 1.0);
+    QuadraticFunctionPtr qf = (QuadraticFunctionPtr) new QuadraticFunction();
+    qf->addTerm(x0, x1, -1.0);
+    FunctionPtr f = (FunctionPtr) new Function(lf, qf, (NonlinearFunctionPtr)0);
+    qh->addConstraint(p->newConstraint(f, 0.0, 0.0));
+  }
+  qh->setModFlags(false, true);
+  RelaxationPtr rel = (RelaxationPtr) new Relaxation(env);
+  rel->setProblem(p);
+  for (int32_t j = 0; j < n; ++j) rel->newVariable(root_lb[j], root_ub[j], (VariableType)var_type[j], vars[j]->getName(), vars[j]->getSrcType());
+  bool is_inf = false;
+  qh->relaxInitInc(rel, &is_inf);
+  SolutionPoolPtr pool = (SolutionPoolPtr) new SolutionPool(env, p, 1);
+  for (int32_t b = 0; b < n_boxes; ++b) {
+    double *bl = lb + (size_t)b * n, *bu = ub + (size_t)b * n;
+    for (int32_t j = 0; j < n; ++j) {
+      p->changeBound(vars[j], bl[j], bu[j]);
+      rel->changeBound(rel->getRelaxationVar(vars[j]), bl[j], bu[j]);
+    }
+    qh->bStats_.niters = 1;
+    ModVector p_mods, r_mods;
+    const bool inf = qh->presolveNode(rel, (NodePtr)0, pool, p_mods, r_mods);
+    verdict[b] = inf ? 1 : 0;
+    n_mods[b] = (int64_t)p_mods.size();
+    for (int32_t j = 0; j < n; ++j) { bl[j] = vars[j]->getLb(); bu[j] = vars[j]->getUb(); }
+    freeMods(p_mods);
+    freeMods(r_mods);
+  }
+  delete pool;
+  delete qh;
+  delete rel;
+  delete p;
+  delete env;
+  return 0;
 }
 
 /* NlPresHandler::chkRed_ alone (NlPresHandler.cpp:101-208) on the current box: 1 = infeasible */
