@@ -716,6 +716,36 @@ def block_next(X):
         d["cpu_reference_ms_per_box"] = 1e3 * (time.perf_counter() - t0)
         d["cpu_reference_note"] = "includes building the reference's Problem and QuadHandler for the box"
     out["quad_handler_simple_presolve"] = d
+
+    # ---- the propagation loop of QuadHandler::presolveNode: 50k relations x 1024 boxes, to the fixpoint ----
+    from minotaur_b200.instances import make_quad_relations_planted, quad_node_boxes
+    rel, vt, lb, ub, xs = make_quad_relations_planted(30_000, 10_000, 40_000, 6)
+    empty = LinearRows(m=0, n=len(lb), row_ptr=np.zeros(1, np.int32), col=np.zeros(0, np.int32), val=np.zeros(0), row_lb=np.zeros(0),
+                       row_ub=np.zeros(0), var_type=vt, lb=lb, ub=ub)
+    eng.load_linear(empty)
+    eng.load_quad_relations(rel)
+    L, U = quad_node_boxes(lb, ub, 30_000, nb, 6, xs)
+    ms = []
+    for it in range(3):
+        gl, gu, gv, gnm, gns, kms = eng.quad_presolve_node(L, U, rounding=E.ROUND_NEAREST)
+        if it: ms.append(kms)
+    d = {"workload": f"QuadHandler::presolveNode propagation loop, {len(rel.sq_x)} squares + {len(rel.b_x0)} products, {nb} boxes "
+                     "(round to nearest, to the fixpoint)",
+         "ms": float(np.mean(ms)), "boxes_per_s": nb / (1e-3 * float(np.mean(ms))), "mods": int(gnm[gv == 0].sum()),
+         "infeasible_boxes": int(gv.sum()), "mean_sweeps": float(gns[gv == 0].mean()) if np.any(gv == 0) else 0.0}
+    if orc is not None:
+        ok = True
+        t0 = time.perf_counter()
+        for b in range(0, nb, 64):
+            ol, ou, inf, k, ns = orc.quad_presolve_node(rel, vt, L[b], U[b])
+            ok = ok and inf == gv[b] and (inf or (np.array_equal(gl[b], ol) and np.array_equal(gu[b], ou) and gnm[b] == k and gns[b] == ns))
+        d["cpu_port_ms_per_box"] = 1e3 * (time.perf_counter() - t0) / len(range(0, nb, 64))
+        d["parity"] = {"ok": bool(ok), "criterion": "16 of the boxes vs the oracle: verdict; bounds, Modification count and sweeps bitwise"}
+    if have_ref:
+        t0 = time.perf_counter(); pyoracle.Reference.quad_presolve_node(rel, vt, lb, ub, L[:4], U[:4])
+        d["cpu_reference_ms_per_box"] = 1e3 * (time.perf_counter() - t0) / 4
+        d["cpu_reference_note"] = "the reference's own QuadHandler::presolveNode on 4 boxes, incl. building its Problem, handler and relaxation once"
+    out["quad_handler_presolve_node"] = d
     eng.close()
     out["parity"] = {"ok": all(v.get("parity", {}).get("ok", True) for v in out.values() if isinstance(v, dict))}
     return out
