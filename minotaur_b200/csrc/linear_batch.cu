@@ -560,7 +560,7 @@ template <class R>
 __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, int64_t ld, const RowStage &st,
                                                  uint32_t *flags, uint32_t *varflag, TileShared &sh, bool active, int loop_mode,
                                                  int max_rounds, int bad_row, unsigned long long &my_nnz,
-                                                 bool &any_change, unsigned &seg_phase)
+                                                 bool &any_change, unsigned &seg_phase, bool prepared)
 {
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const double2 *tile_base = bx - lane;          // box 0 of the tile: + j*ld is variable j's 512-byte segment
@@ -568,7 +568,8 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
   const int warp = team.gwarp;
   // every row flagged for every box of the tile  (simplePresolve :1618-1622)
   for (int i = team.cthread; i < P.m; i += team.n_threads) __stcg(flags + i, __ldg(P.row_info + i).y >= 0 ? kFull : 0u);
-  for (int j = team.cthread; j < P.n; j += team.n_threads) __stcg(varflag + j, 0u);
+  // (a PREPARED batch arrives with the variables its deltas set already flagged, see BatchIo::prepared)
+  if (!prepared) for (int j = team.cthread; j < P.n; j += team.n_threads) __stcg(varflag + j, 0u);
   if (warp == 0) { sh.changed[lane] = 1; sh.nint[lane] = 0; }
   team.sync();
 
@@ -689,8 +690,11 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
     }
 
     // ---- integer rounding + bound check ----
-    if (first_sweep) {
+    if (first_sweep && !prepared) {
       // every variable once: the incoming box may hold fractional integer bounds or crossed bounds
+      // (not for a prepared batch: its builder has checked the root box and flagged the variables the deltas set, so
+      // rounding and the bound check are no-ops everywhere else and the flag-driven pass below visits the same set of
+      // variables that can change or cross -- those, and the ones the rows of this sweep moved)
       for (int j0 = warp * kGather; j0 < P.n; j0 += team.n_warps * kGather) {
         double2 b[kGather];
         const bool want = run && sh.verdict[lane] != 2;     // row-infeasible boxes are frozen
@@ -902,11 +906,12 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
   unsigned long long my_nnz = 0ull;
   unsigned my_evals = 0u;
   int my_rounds = 0;
+  const bool prepared = io.prepared != nullptr && __ldg(io.prepared) == 0;
   for (int outer = 0;; ++outer) {
     bool lin_changed = false, nl_changed = false;
     if (lin_enabled)
       my_rounds += lin_tile_presolve<R>(P, bx, ld, st, flags, varflag, sh, active, loop_mode, max_rounds, bad_row,
-                                        my_nnz, lin_changed, seg_phase);
+                                        my_nnz, lin_changed, seg_phase, prepared && outer == 0);
     if constexpr (HAS_NL) {
       // the NL instantiation uses the dynamic shared memory for the tape batches (no TMA segments: use_tma == 0)
       if (nl_enabled) my_rounds += nl_tile_presolve<R, SHAPED>(P, N, bx, ld, sh, active, nl_changed, reinterpret_cast<BatchStage *>(dyn_smem)[wl], my_evals);
@@ -988,25 +993,37 @@ __global__ void boxes_pad_kernel(double2 *boxes, int64_t ld, int n, int n_boxes)
   }
 }
 
+// every box = the root box.  With `dirty` (a prepared batch, BatchIo::prepared): *dirty is raised when the root box is
+// not a fixed point of tightenInts_ + checkBounds_ (an integer variable with a fractional bound, or crossed bounds) --
+// the batch kernel then runs its all-variables pass in the first sweep as for any other batch.
 __global__ void boxes_from_root_kernel(const double *__restrict__ rl, const double *__restrict__ ru, int n,
-                                       double2 *__restrict__ boxes, int64_t ld)
+                                       double2 *__restrict__ boxes, int64_t ld, const uint8_t *__restrict__ var_type,
+                                       int32_t *dirty)
 {
   const int64_t total = (int64_t)n * ld;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = k / ld;
-    boxes[k] = make_double2(rl[j], ru[j]);
+    const double2 b = make_double2(rl[j], ru[j]);
+    boxes[k] = b;
+    if (dirty != nullptr && k == j * ld) {
+      double l = b.x, u = b.y;
+      if (is_int_type(var_type[j])) tighten_int_bounds(l, u);
+      if (l != b.x || u != b.y || b.x > b.y + kETol) *dirty = 1;
+    }
   }
 }
 
 __global__ void apply_deltas_kernel(const long long *__restrict__ dptr, const int32_t *__restrict__ dvar,
                                     const uint8_t *__restrict__ dup, const double *__restrict__ dval,
-                                    int n_boxes, double2 *boxes, int64_t ld)
+                                    int n_boxes, double2 *boxes, int64_t ld, uint32_t *varflag, int n)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_boxes) return;
   for (long long q = dptr[b]; q < dptr[b + 1]; ++q) {      // in order: a later delta overrides
     double2 *p = boxes + (int64_t)dvar[q] * ld + b;
     if (dup[q]) p->y = dval[q]; else p->x = dval[q];
+    // prepared batch: the variable goes through integer rounding + bound check in this box's first sweep
+    if (varflag != nullptr) atomicOr(varflag + (int64_t)(b >> 5) * n + dvar[q], 1u << (b & 31));
   }
 }
 
@@ -1203,11 +1220,11 @@ cudaError_t launch_boxes_pad(double2 *boxes, int64_t ld, int32_t n, int32_t n_bo
 }
 
 cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub, int32_t n, int32_t n_boxes,
-                                   double2 *boxes, int64_t ld, cudaStream_t stream)
+                                   double2 *boxes, int64_t ld, const uint8_t *var_type, int32_t *dirty, cudaStream_t stream)
 {
   (void)n_boxes;
   if (n <= 0) return cudaSuccess;
-  boxes_from_root_kernel<<<148 * 8, 256, 0, stream>>>(root_lb, root_ub, n, boxes, ld);
+  boxes_from_root_kernel<<<148 * 8, 256, 0, stream>>>(root_lb, root_ub, n, boxes, ld, var_type, dirty);
   return cudaGetLastError();
 }
 
@@ -1246,11 +1263,11 @@ cudaError_t launch_emit_mods(const double2 *boxes, const double *root_lb, const 
 
 cudaError_t launch_apply_deltas(const long long *delta_ptr, const int32_t *delta_var,
                                 const uint8_t *delta_is_upper, const double *delta_val, int32_t n_boxes,
-                                double2 *boxes, int64_t ld, cudaStream_t stream)
+                                double2 *boxes, int64_t ld, uint32_t *varflag, int32_t n, cudaStream_t stream)
 {
   if (n_boxes <= 0) return cudaSuccess;
   apply_deltas_kernel<<<(n_boxes + 127) / 128, 128, 0, stream>>>(delta_ptr, delta_var, delta_is_upper,
-                                                                 delta_val, n_boxes, boxes, ld);
+                                                                 delta_val, n_boxes, boxes, ld, varflag, n);
   return cudaGetLastError();
 }
 

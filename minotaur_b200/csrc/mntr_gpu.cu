@@ -80,6 +80,9 @@ struct mntr_gpu_ctx {
   int64_t batch_ld = 0;        // capacity in boxes (multiple of 32)
   double2 *d_boxes = nullptr;
   uint32_t *d_rowflag = nullptr, *d_varflag = nullptr;
+  int32_t *d_prepared = nullptr;                // [1] BatchIo::prepared word of the batch built last (0 = root box clean)
+  const void *prepared_boxes = nullptr;         // the batch boxes_from_deltas built and nobody has touched since
+  int32_t prepared_n = 0;
   unsigned char *d_tstate = nullptr;
   int32_t *d_verdict = nullptr, *d_rounds = nullptr;
   long long *d_nnzb = nullptr;
@@ -246,7 +249,8 @@ void free_scratch(mntr_gpu_ctx *c)
 void free_batch(mntr_gpu_ctx *c)
 {
   cudaFree(c->d_boxes); cudaFree(c->d_rowflag); cudaFree(c->d_varflag); cudaFree(c->d_tstate); cudaFree(c->d_verdict); cudaFree(c->d_rounds);
-  cudaFree(c->d_nnzb); cudaFree(c->d_nl_evals);
+  cudaFree(c->d_nnzb); cudaFree(c->d_nl_evals); cudaFree(c->d_prepared);
+  c->d_prepared = nullptr; c->prepared_boxes = nullptr; c->prepared_n = 0;
   c->d_nl_evals = nullptr;
   c->d_boxes = nullptr; c->d_rowflag = nullptr; c->d_verdict = nullptr; c->d_rounds = nullptr;
   c->d_nnzb = nullptr; c->d_varflag = nullptr; c->d_tstate = nullptr;
@@ -268,6 +272,7 @@ int ensure_batch(mntr_gpu_ctx *ctx, int32_t n_boxes, bool need_boxes)
   CU(cudaMalloc((void **)&ctx->d_rounds, sizeof(int32_t) * (size_t)ld));
   CU(cudaMalloc((void **)&ctx->d_nnzb, sizeof(long long) * (size_t)ld));
   CU(cudaMalloc((void **)&ctx->d_nl_evals, sizeof(unsigned long long)));
+  CU(cudaMalloc((void **)&ctx->d_prepared, sizeof(int32_t)));
   ctx->batch_ld = ld;
   return MNTR_OK;
 }
@@ -1278,6 +1283,8 @@ int mntr_gpu_tighten_dev(mntr_gpu_ctx *ctx, int32_t n_boxes, void *boxes_dev, co
   BatchIo io;
   io.boxes = (double2 *)boxes_dev; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
   io.verdict = verdict_dev; io.rounds = rounds_dev; io.nnz = (long long *)nnz_dev; io.nl_evals = ctx->d_nl_evals;
+  io.prepared = (ctx->prepared_boxes == boxes_dev && ctx->prepared_n == n_boxes) ? ctx->d_prepared : nullptr;
+  ctx->prepared_boxes = nullptr;                   // consumed: the boxes are tightened in place
   (void)tiles;
   CU(cudaMemsetAsync(ctx->d_nl_evals, 0, sizeof(unsigned long long), ctx->stream));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -1328,6 +1335,7 @@ int mntr_gpu_tighten(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, double *ub,
   BatchIo io;
   io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
   io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb; io.nl_evals = ctx->d_nl_evals;
+  ctx->prepared_boxes = nullptr;                   // (uploaded boxes: nothing is known about them)
   CU(cudaMemsetAsync(ctx->d_nl_evals, 0, sizeof(unsigned long long), ctx->stream));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   CU(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,
@@ -1408,8 +1416,17 @@ int boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *root_lb,
     CU(cudaMemcpyAsync(D.up, delta_is_upper, (size_t)n_delta, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(D.val, delta_val, sizeof(double) * (size_t)n_delta, cudaMemcpyHostToDevice, s));
   }
-  CU(launch_boxes_from_root(D.rl, D.ru, n, n_boxes, boxes, ld, s));
-  CU(launch_apply_deltas(D.ptr, D.var, D.up, D.val, n_boxes, boxes, ld, s));
+  // the batch is PREPARED (BatchIo::prepared): root box checked on the device, the deltas' variables flagged -- the
+  // next batch call on these boxes skips the all-variables rounding pass of its first sweep
+  ctx->prepared_boxes = nullptr;
+  const bool prep = ctx->d_varflag != nullptr && ld <= ctx->batch_ld && !getenv("MNTR_GPU_NO_PREPARED");
+  if (prep) {
+    CU(cudaMemsetAsync(ctx->d_varflag, 0, sizeof(uint32_t) * (size_t)n * (size_t)(ld / 32), s));
+    CU(cudaMemsetAsync(ctx->d_prepared, 0, sizeof(int32_t), s));
+  }
+  CU(launch_boxes_from_root(D.rl, D.ru, n, n_boxes, boxes, ld, ctx->lin.var_type, prep ? ctx->d_prepared : nullptr, s));
+  CU(launch_apply_deltas(D.ptr, D.var, D.up, D.val, n_boxes, boxes, ld, prep ? ctx->d_varflag : nullptr, n, s));
+  if (prep) { ctx->prepared_boxes = boxes; ctx->prepared_n = n_boxes; }
   return MNTR_OK;
 }
 
@@ -1425,6 +1442,7 @@ int mntr_gpu_boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double 
   int rc = check_deltas(ctx, "boxes_from_deltas", n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
+  if ((rc = ensure_batch(ctx, n_boxes, false))) return rc;         // (the flag words of the prepared batch)
   DeviceDeltas D;
   rc = boxes_from_deltas(ctx, n_boxes, root_lb, root_ub, delta_ptr, delta_var, delta_is_upper, delta_val,
                          (double2 *)boxes_dev, D);
@@ -1865,6 +1883,8 @@ int mntr_gpu_tighten_nodes(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *roo
   BatchIo io;
   io.boxes = ctx->d_boxes; io.ld = ld; io.n_boxes = n_boxes; io.rowflag = ctx->d_rowflag; io.varflag = ctx->d_varflag; io.tstate = ctx->d_tstate;
   io.verdict = ctx->d_verdict; io.rounds = ctx->d_rounds; io.nnz = ctx->d_nnzb; io.nl_evals = ctx->d_nl_evals;
+  io.prepared = (ctx->prepared_boxes == (const void *)ctx->d_boxes && ctx->prepared_n == n_boxes) ? ctx->d_prepared : nullptr;
+  ctx->prepared_boxes = nullptr;
   CUN(cudaMemsetAsync(ctx->d_nl_evals, 0, sizeof(unsigned long long), s));
   CUN(cudaEventRecord(ctx->ev[1], s));
   CUN(launch_batch_reference(ctx->lin, ctx->nl_loaded ? &ctx->nl : nullptr, io, o.rounding == MNTR_ROUND_DIRECTED,

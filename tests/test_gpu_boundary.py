@@ -84,6 +84,55 @@ def test_tighten_nodes_mods_without_initial_copy(engine, oracle, loosen):
     assert n_feas > nb // 4
 
 
+@pytest.mark.parametrize("dirty_root", [False, True])
+def test_prepared_batch_equals_uploaded_batch(engine, oracle, dirty_root):
+    """A batch built on the device from root + deltas is PREPARED (BatchIo::prepared): the first sweep's integer rounding
+    and bound check visit only the variables the deltas set and the ones the rows moved.  The result must be the
+    uploaded-boxes path's (which runs the all-variables pass) and the oracle's, bit for bit -- with deltas that put
+    FRACTIONAL bounds on integer variables, deltas that CROSS a variable's bounds (checkBounds_ must report them), and,
+    for `dirty_root`, a root box that itself holds fractional integer bounds (the prepared path must step aside)."""
+    inst = make_knapsack_setcover(1200, 1000, 8, seed=11)
+    engine.load_linear(inst)
+    root_lb, root_ub = inst.lb.copy(), inst.ub.copy()
+    isint = np.nonzero(inst.var_type <= 1)[0]
+    if dirty_root:
+        root_ub[isint[::7]] += 0.5                      # ub of an integer variable = k + 0.5: tightenInts_ floors it
+    nb = 70
+    ptr, var, up, val = branch_deltas(root_lb, root_ub, inst.var_type, nb, seed=4, max_depth=8)
+    rng = np.random.default_rng(12)
+    val = val.copy()
+    frac = rng.random(len(val)) < 0.25
+    val[frac] += np.where(up[frac] == 1, 0.5, -0.5)       # fractional, looser by half a unit: rounding restores the integer
+    # two boxes whose deltas cross a variable's bounds outright
+    crossed = []
+    for b in (5, 40):
+        q = int(ptr[b])
+        if ptr[b + 1] > q:
+            j = var[q]
+            val[q] = root_lb[j] - 3.0 if up[q] == 1 else root_ub[j] + 3.0
+            if not np.any(var[q + 1:ptr[b + 1]] == j): crossed.append(b)
+    d = (ptr, var, up, val)
+    v, r, mp, mv, mu, mx, total = engine.tighten_nodes(root_lb, root_ub, *d, rounding=E.ROUND_NEAREST)
+    L = np.empty((nb, inst.n)); U = np.empty((nb, inst.n))
+    for b in range(nb):
+        L[b], U[b] = deltas_box(root_lb, root_ub, d, b)
+    up_res = engine.tighten(L, U, rounding=E.ROUND_NEAREST, order=E.ORDER_REFERENCE)
+    assert np.array_equal(v != 0, up_res.verdict != 0)
+    assert np.array_equal(r, up_res.rounds)
+    n_feas = 0
+    for b in range(nb):
+        ol, ou, ro = oracle.lin_fixpoint_inplace(inst, L[b], U[b])
+        assert (v[b] != 0) == (ro["verdict"] != 0), b
+        if v[b] != 0:
+            continue
+        n_feas += 1
+        a, e = int(mp[b]), int(mp[b + 1])
+        gl, gu = _apply(L[b], U[b], mv[a:e], mu[a:e], mx[a:e])
+        assert np.array_equal(gl, up_res.lb[b]) and np.array_equal(gu, up_res.ub[b]), b
+        assert np.array_equal(gl, ol) and np.array_equal(gu, ou), b
+    assert crossed and all(v[b] != 0 for b in crossed) and n_feas > nb // 4
+
+
 def test_zero_copy_call_on_alloc_host_buffers(engine, oracle):
     inst = make_sparse_milp(5000, 5000, 8, seed=21)
     engine.load_linear(inst)
