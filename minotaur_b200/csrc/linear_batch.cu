@@ -455,7 +455,14 @@ __device__ __forceinline__ void staged_row(const LinDev &P, int2 info, double2 b
   double ll = 0.0, uu = 0.0;
   int dhi = 0;            // high word of the largest width (ub - lb) seen: negative widths and zero never win, an
                           // infinite or undefined one makes the bound below infinite / NaN, i.e. "cannot skip"
-  // one term: the sign of the coefficient is warp-uniform (posmask, extracted into predicates several bits at a time)
+  // one term: the sign of the coefficient is warp-uniform (posmask).  Rows whose coefficients are ALL positive
+  // (knapsack, covering, packing rows: the common case) take a loop without the selection; the sums are the same
+  // operations in the same order either way.
+  auto term_pos = [&](double a, double2 b) {
+    ll = R::add_lo(ll, R::mul_lo(a, b.x));
+    uu = R::add_hi(uu, R::mul_hi(a, b.y));
+    dhi = max(dhi, __double2hiint(b.y - b.x));
+  };
   auto term = [&](int t, double a, double2 b) {
     const bool pos = (posmask >> t) & 1u;
     const double blo = pos ? b.x : b.y, bhi = pos ? b.y : b.x;
@@ -463,19 +470,30 @@ __device__ __forceinline__ void staged_row(const LinDev &P, int2 info, double2 b
     uu = R::add_hi(uu, R::mul_hi(a, bhi));
     dhi = max(dhi, __double2hiint(b.y - b.x));
   };
-  int t0 = 0;
+  // four terms' loads in flight together; the remainder (0..3 terms) as a pair and a single one, straight-line
+  auto sweep_terms = [&](auto &&one) {
+    int t0 = 0;
 #pragma unroll
-  for (int c = 0; c < kSegEntries / 4; ++c) {                 // four terms' loads in flight together
-    if (t0 + 4 <= cnt) {
-      double a[4]; double2 b[4];
+    for (int c = 0; c < kSegEntries / 4; ++c) {
+      if (t0 + 4 <= cnt) {
+        double a[4]; double2 b[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { a[u] = sv[c * 4 + u]; b[u] = sg[(c * 4 + u) * kTile]; }
+        for (int u = 0; u < 4; ++u) { a[u] = sv[c * 4 + u]; b[u] = sg[(c * 4 + u) * kTile]; }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) term(c * 4 + u, a[u], b[u]);
-      t0 += 4;
+        for (int u = 0; u < 4; ++u) one(c * 4 + u, a[u], b[u]);
+        t0 += 4;
+      }
     }
-  }
-  for (int t = t0; t < cnt; ++t) term(t, sv[t], sg[t * kTile]);
+    const double *rv = sv + t0; const double2 *rg = sg + t0 * kTile;
+    if (cnt - t0 >= 2) {
+      const double a0 = rv[0], a1 = rv[1]; const double2 b0 = rg[0], b1 = rg[kTile];
+      one(t0, a0, b0); one(t0 + 1, a1, b1);
+      rv += 2; rg += 2 * kTile; t0 += 2;
+    }
+    if (t0 < cnt) one(t0, rv[0], rg[0]);
+  };
+  if (posmask == (cnt >= 32 ? kFull : ((1u << cnt) - 1u))) sweep_terms([&](int, double a, double2 b) { term_pos(a, b); });
+  else sweep_terms(term);
   // >= every term's reach |a| (ub - lb) 1.000000001: amax >= |a|, and the width rounded up to the next high word
   const double wmax = amax * __hiloint2double(dhi + 1, 0) * 1.000000001;
   // SCREEN: does any box of the tile need more than the activity?  A box does when its row is activity-infeasible
