@@ -517,10 +517,14 @@ __device__ __forceinline__ void staged_row(const LinDev &P, int2 info, double2 b
 // Its modifications of integer variables do not count towards nintmods (the reference counts them into a local
 // it never reads, :554), and an infeasible cut-off stops the box like an activity-infeasible row.
 template <class R>
-__device__ __noinline__ void cutoff_row(const LinDev &P, double2 *bx, int64_t ld, const RowStage &st, bool run,
-                                        uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane,
-                                        unsigned long long &my_nnz)
+// (P and st BY VALUE: a reference would force the caller's copies of the kernel parameters into local memory, and the
+// hot row loop would then read P.col / st.bar through the stack instead of the constant bank / registers)
+// returns the nonzeros this lane's box visited (by value for the same reason: a reference to the caller's counter would
+// put the counter of the hot row loop into local memory)
+__device__ __noinline__ unsigned long long cutoff_row(const LinDev P, double2 *bx, int64_t ld, const RowStage st, bool run,
+                                                      uint32_t *flags, uint32_t *varflag, TileShared &sh, int lane)
 {
+  unsigned long long my_nnz = 0ull;
   LinDev C = P;
   C.col = P.cut_col; C.val = P.cut_val;
   const int cnt = P.cut_cnt;
@@ -546,6 +550,7 @@ __device__ __noinline__ void cutoff_row(const LinDev &P, double2 *bx, int64_t ld
       chg = row_update<R, false>(C, 0, cnt, box, st, doit, sing, P.cut_rhs, act, flags, varflag, sh, lane, false);
     mine = mine && ((chg >> lane) & 1u);
   }
+  return my_nnz;
 }
 
 // integer rounding [tightenInts_] + lb>ub check [checkBounds_] of variable j for the lanes in `want`
@@ -703,7 +708,7 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
 
     // ---- objective cut-off row (only with an incumbent), :1636-1640 ----
     if (P.cut_cnt > 0) {
-      if (warp == 0) cutoff_row<R>(P, bx, ld, st, run, flags, varflag, sh, lane, my_nnz);
+      if (warp == 0) my_nnz += cutoff_row<R>(P, bx, ld, st, run, flags, varflag, sh, lane);
       team.sync();
     }
 
@@ -763,7 +768,7 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
 // objective's lower bound over the box (LinearFunction::computeBounds, taken once), a binary with coefficient a0
 // is fixed to 0 if a0>0 && olb+a0>ub, to 1 if a0<0 && olb-a0>ub; ub is the RAW incumbent value.  One warp per tile.
 template <class R>
-__device__ __noinline__ void fix_obj_bins(const LinDev &P, double2 *bx, int64_t ld, bool run, TileShared &sh, int lane)
+__device__ __noinline__ void fix_obj_bins(const LinDev P, double2 *bx, int64_t ld, bool run, TileShared &sh, int lane)
 {
   const bool mine = run && sh.verdict[lane] == 0;
   if (!__any_sync(kFull, mine)) return;
