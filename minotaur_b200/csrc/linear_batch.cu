@@ -823,12 +823,17 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
       const int c_lo = min(N.n_cons, warp * per), c_hi = min(N.n_cons, c_lo + per);
       for (int c0 = c_lo; c0 < c_hi;) {
         const BatchInfo B = stage_batch(N, c0, c_hi, TS, tile_base, ld, lane);
+        // The box's verdict word lives in L2 (a cluster may share the tile): it is sampled once per staged batch, not
+        // once per constraint -- a volatile load in front of every evaluation put a full L2 round trip before the
+        // evaluation's own loads.  A finding of THIS warp stops its lane at once; another warp's finding is seen at
+        // the next batch (the evaluations in between are of a box whose result is already discarded).
+        bool alive = run && sh.verdict[lane] == 0;
         for (int k = 0; k < B.n; ++k) {
           const ConsView V = batch_constraint(N, TS, B, k, c0 + k);
-          if (run && sh.verdict[lane] == 0) {
+          if (alive) {
             const int st = nl_chk_red<R, SHAPED>(V, bx, ld, nlb, nub);
             ++my_evals;
-            if (st != 0) sh.verdict[lane] = st;
+            if (st != 0) { sh.verdict[lane] = st; alive = false; }
           }
         }
         c0 += B.n;
@@ -838,34 +843,38 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
     if (N.n_quad > 0) {
       const int per = (N.n_quad + team.n_warps - 1) / team.n_warps;
       const int q_lo = min(N.n_quad, warp * per), q_hi = min(N.n_quad, q_lo + per);
+      bool alive = run && sh.verdict[lane] == 0;
       for (int q = q_lo; q < q_hi; ++q) {
-        if (run && sh.verdict[lane] == 0) {
+        if (alive) {
           const int st = quad_chk_red<R>(N, q, bx, ld);
           ++my_evals;
-          if (st != 0) sh.verdict[lane] = st;
+          if (st != 0) { sh.verdict[lane] = st; alive = false; }
         }
       }
     }
     team.sync();
     // varBndsFromCons_: constraints of one level touch disjoint variables
+    bool moved = false;                                   // this lane's box changed in this sweep (published once, below)
     for (int lev = 0; lev < N.n_levels; ++lev) {
       const int qb = __ldg(N.level_ptr + lev), qe = __ldg(N.level_ptr + lev + 1);
       const int per = (qe - qb + team.n_warps - 1) / team.n_warps;
       const int c_lo = min(qe, qb + warp * per), c_hi = min(qe, c_lo + per);
       for (int c0 = c_lo; c0 < c_hi;) {
         const BatchInfo B = stage_batch(N, c0, c_hi, TS, tile_base, ld, lane);
+        bool alive = run && sh.verdict[lane] == 0;         // (sampled per batch, see chkRed_ above)
         for (int k = 0; k < B.n; ++k) {
           const ConsView V = batch_constraint(N, TS, B, k, c0 + k);
-          if (run && sh.verdict[lane] == 0) {
+          if (alive) {
             int n_mods = 0; unsigned dummy = 0;
             const int st = nl_var_bound_mods<R, SHAPED>(V, bx, ld, nlb, nub, n_mods, dummy);
             ++my_evals;
-            if (st != 0) sh.verdict[lane] = st;
-            else if (n_mods > 0) sh.changed[lane] = 1;
+            if (st != 0) { sh.verdict[lane] = st; alive = false; }
+            else if (n_mods > 0) moved = true;
           }
         }
         c0 += B.n;
       }
+      if (lev + 1 == N.n_levels && moved) sh.changed[lane] = 1;
       team.sync();
     }
     // fixObjBins_: only with an incumbent and a linear objective (:1045-1050)
