@@ -30,6 +30,8 @@
 // Deviation, deliberate: an activity-infeasible row yields verdict MNTR_INFEAS_ROW and stops
 // that box; the reference's node mode drops that status (:1631).
 #include <cooperative_groups.h>
+#include <cuda.h>
+#include <cstdint>
 #include <cstdlib>
 
 #include "cgraph.cuh"
@@ -98,6 +100,8 @@ struct RowStage {
   double2 *seg;   // [2][kSegEntries][32] {lb,ub} of a row's variables for the 32 boxes of the tile (TMA destination),
                   // two pipeline slots: the next row's segments are in flight while this row is evaluated
   uint64_t *bar;  // [2] mbarriers of the bulk copies into the two slots
+  const void *tmap = nullptr;   // tensor map over the batch [n][2 ld] doubles (TMA gather4: four variables' segments per copy)
+  int tile_x = 0;               // first double of this tile inside a variable's row: 64 * tile
 };
 
 // ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared, completion on an mbarrier ----
@@ -111,6 +115,8 @@ constexpr int kEntSlotBytes = 16 * 8 + 16 * 4;
 constexpr int kWarpSmemBytes = 2 * kSegSlotBytes + 2 * kEntSlotBytes;
 constexpr int kSegSmemBytes = kLinWarps * kWarpSmemBytes;              // dynamic shared memory of a (pure linear) CTA
 extern __shared__ __align__(128) unsigned char dyn_smem[];
+// a CUtensorMap (128 opaque bytes, 64-byte aligned), passed to the kernel as a __grid_constant__ parameter
+struct alignas(64) BoxTensorMap { unsigned long long opaque[16]; };
 __device__ __forceinline__ double2 *slot_seg(int wl, int slot)
 {
   return reinterpret_cast<double2 *>(dyn_smem + wl * kWarpSmemBytes + slot * kSegSlotBytes);
@@ -140,6 +146,16 @@ __device__ __forceinline__ void bulk_g2s_stream(void *dst, const void *src, uint
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+// TMA tile::gather4 (sm_100): ONE copy brings the 512-byte segments of FOUR variables (rows j0..j3 of the tensor
+// [n][2 ld] doubles, 64 doubles starting at column x) into four consecutive 512-byte pieces of shared memory
+__device__ __forceinline__ void tma_gather4_stream(void *dst, const void *tmap, int x, int j0, int j1, int j2, int j3,
+                                                   uint64_t *bar, unsigned long long policy)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+               " [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;"
+               ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(j0), "r"(j1), "r"(j2), "r"(j3), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
 }
 __device__ __forceinline__ int ldg_keep_i32(const int32_t *p, unsigned long long policy)
 {
@@ -670,6 +686,17 @@ __device__ __forceinline__ int lin_tile_presolve(const LinDev &P, double2 *bx, i
           if (cnt > kSegEntries) return;
           if (lane < cnt) { slot_col(wl, slot)[lane] = c; slot_val(wl, slot)[lane] = v; }
           if (lane == 0) mbar_expect_tx(st.bar + slot, (uint32_t)(cnt * kSegBytes));
+          if (st.tmap != nullptr) {
+            // groups of four terms with one gather4 each (issued by lane g for terms 4g .. 4g+3), the 0..3 terms left
+            // over with a bulk copy each
+            const int j0 = __shfl_sync(kFull, c, (4 * lane) & 31), j1 = __shfl_sync(kFull, c, (4 * lane + 1) & 31),
+                      j2 = __shfl_sync(kFull, c, (4 * lane + 2) & 31), j3 = __shfl_sync(kFull, c, (4 * lane + 3) & 31);
+            const int full = cnt & ~3;
+            if (4 * lane < full)
+              tma_gather4_stream(slot_seg(wl, slot) + 4 * lane * kTile, st.tmap, st.tile_x, j0, j1, j2, j3, st.bar + slot, pol_stream);
+            if (lane >= full && lane < cnt)
+              bulk_g2s_stream(slot_seg(wl, slot) + lane * kTile, tile_base + (int64_t)c * ld, kSegBytes, st.bar + slot, pol_stream);
+          } else
           if (lane < cnt) bulk_g2s_stream(slot_seg(wl, slot) + lane * kTile, tile_base + (int64_t)c * ld, kSegBytes, st.bar + slot, pol_stream);
           __syncwarp();
         };
@@ -897,7 +924,7 @@ __device__ __forceinline__ int nl_tile_presolve(const LinDev &P, const NlDev &N,
 template <class R, bool HAS_NL, bool SHAPED = false>
 __global__ void __launch_bounds__(HAS_NL ? kBatchThreads : kLinWarps * 32, 2)
 fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int max_rounds, int lin_enabled,
-                            int nl_enabled_arg, int use_tma)
+                            int nl_enabled_arg, int use_tma, const __grid_constant__ BoxTensorMap tmap)
 {
   constexpr int kWarps = HAS_NL ? kBatchWarps : kLinWarps;
   const int nl_enabled = HAS_NL ? nl_enabled_arg : 0;
@@ -907,7 +934,9 @@ fbbt_batch_reference_kernel(LinDev P, NlDev N, BatchIo io, int loop_mode, int ma
   __shared__ __align__(8) uint64_t s_bar[kWarps][2];
   // dyn_smem: pure linear instantiation: kWarpSmemBytes per warp (segment slots + entries); with tapes: BatchStage per warp
   const int wl = threadIdx.x >> 5;
-  const RowStage st{s_val[wl], s_col[wl], use_tma ? slot_seg(wl, 0) : nullptr, s_bar[wl]};
+  const RowStage st{s_val[wl], s_col[wl], use_tma ? slot_seg(wl, 0) : nullptr, s_bar[wl],
+                    use_tma == 2 ? (const void *)&tmap : nullptr,
+                    64 * (int)(blockIdx.x / cg::this_cluster().num_blocks())};
   if ((threadIdx.x & 31) == 0) { mbar_init(st.bar, 1); mbar_init(st.bar + 1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -1167,10 +1196,39 @@ __global__ void mods_delta_kernel(const double2 *__restrict__ boxes, const doubl
 }  // namespace
 
 namespace {
+// Tensor map over the batch for TMA gather4: a 2-D tensor of doubles, [n rows][2 ld], row stride 16 ld bytes, box
+// {64 doubles = one tile's 512-byte segment, 1 row}: tile::gather4 takes four row indices per copy.  The driver entry
+// point is fetched through the runtime (no link-time dependency on libcuda).  false: not available -> bulk copies.
+bool encode_box_tensor_map(BoxTensorMap *out, const double2 *boxes, int64_t ld, int32_t n)
+{
+  static_assert(sizeof(BoxTensorMap) == sizeof(CUtensorMap), "CUtensorMap is 128 bytes");
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (encode_fn)p;
+    else (void)cudaGetLastError();
+  }
+  if (fn == nullptr || n <= 0 || (reinterpret_cast<uintptr_t>(boxes) & 15u) != 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)(2 * ld), (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)(16 * ld)};
+  const cuuint32_t box[2] = {64u, 1u}, estr[2] = {1u, 1u};
+  return fn(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)boxes, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class R>
 cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, int loop_mode, int max_rounds,
                            int lin_enabled, int nl_enabled, int tiles, int cluster, cudaStream_t stream)
 {
+  BoxTensorMap tmap{};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(tiles * cluster));
   cfg.stream = stream;
@@ -1189,21 +1247,25 @@ cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, 
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
       if (e != cudaSuccess) return e;
       return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, true, true>, P, nl, io, loop_mode, max_rounds, lin_enabled,
-                                nl_enabled, 0);
+                                nl_enabled, 0, tmap);
     }
     cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
     if (e != cudaSuccess) return e;
     return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, true>, P, nl, io, loop_mode, max_rounds, lin_enabled,
-                              nl_enabled, 0);
+                              nl_enabled, 0, tmap);
   }
   cfg.blockDim = dim3(kLinWarps * 32);
   cfg.dynamicSmemBytes = kSegSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSegSmemBytes);
   if (e != cudaSuccess) return e;
+  // segments by TMA: gather4 over a tensor map of the batch (default), else one bulk copy per term
+  int use_tma = 1;
+  const char *g4 = getenv("MNTR_GPU_GATHER4");
+  if (!(g4 && atoi(g4) == 0) && encode_box_tensor_map(&tmap, io.boxes, io.ld, P.n)) use_tma = 2;
   return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, false>, P, nl, io, loop_mode, max_rounds, lin_enabled,
-                            nl_enabled, 1);
+                            nl_enabled, use_tma, tmap);
 }
 }  // namespace
 
