@@ -1230,42 +1230,44 @@ cudaError_t launch_cluster(const LinDev &P, const NlDev &nl, const BatchIo &io, 
 {
   BoxTensorMap tmap{};
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(tiles * cluster));
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (nl_enabled) {
-    cfg.blockDim = dim3(kBatchThreads);
-    cfg.dynamicSmemBytes = kBatchWarps * sizeof(BatchStage);
-    if (nl.all_shaped) {              // every tape is [Var,Var,Mult] or [Var,Var,Sqr,Sqr,SumList]: no interpreter
-      cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, true, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-      if (e != cudaSuccess) return e;
-      return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, true, true>, P, nl, io, loop_mode, max_rounds, lin_enabled,
-                                nl_enabled, 0, tmap);
-    }
-    cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+  // one launch of `kernel` with `smem` bytes of dynamic shared memory.  A cluster of 16 CTAs is beyond the portable
+  // size: the kernel opts in, and where that is refused or 16 CTAs of this shape do not fit a GPC the tile gets 8.
+  auto launch = [&](auto kernel, unsigned threads, size_t smem, int use_tma) -> cudaError_t {
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, true>, P, nl, io, loop_mode, max_rounds, lin_enabled,
-                              nl_enabled, 0, tmap);
+    int c = cluster;
+    for (;;) {
+      cfg.gridDim = dim3((unsigned)(tiles * c));
+      attr[0].val.clusterDim.x = (unsigned)c;
+      if (c <= 8) break;
+      int n_clusters = 0;
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+          cudaOccupancyMaxActiveClusters(&n_clusters, kernel, &cfg) == cudaSuccess && n_clusters >= 1) break;
+      (void)cudaGetLastError();
+      c = 8;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, P, nl, io, loop_mode, max_rounds, lin_enabled, nl_enabled, use_tma, tmap);
+  };
+  if (nl_enabled) {
+    const size_t smem = kBatchWarps * sizeof(BatchStage);
+    if (nl.all_shaped)                // every tape is [Var,Var,Mult] or [Var,Var,Sqr,Sqr,SumList]: no interpreter
+      return launch(fbbt_batch_reference_kernel<R, true, true>, kBatchThreads, smem, 0);
+    return launch(fbbt_batch_reference_kernel<R, true>, kBatchThreads, smem, 0);
   }
-  cfg.blockDim = dim3(kLinWarps * 32);
-  cfg.dynamicSmemBytes = kSegSmemBytes;
-  cudaError_t e = cudaFuncSetAttribute(fbbt_batch_reference_kernel<R, false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSegSmemBytes);
-  if (e != cudaSuccess) return e;
   // segments by TMA: gather4 over a tensor map of the batch (default), else one bulk copy per term
   int use_tma = 1;
   const char *g4 = getenv("MNTR_GPU_GATHER4");
   if (!(g4 && atoi(g4) == 0) && encode_box_tensor_map(&tmap, io.boxes, io.ld, P.n)) use_tma = 2;
-  return cudaLaunchKernelEx(&cfg, fbbt_batch_reference_kernel<R, false>, P, nl, io, loop_mode, max_rounds, lin_enabled,
-                            nl_enabled, use_tma, tmap);
+  return launch(fbbt_batch_reference_kernel<R, false>, kLinWarps * 32, kSegSmemBytes, use_tma);
 }
 }  // namespace
 
@@ -1282,8 +1284,14 @@ cudaError_t launch_batch_reference(const LinDev &P, const NlDev *N, const BatchI
   // level barrier.  Two CTAs of this kernel fit on an SM.
   int cluster = 1;
   const int slots = 2 * sm_count;
-  while (cluster < 8 && tiles * cluster * 2 <= slots) cluster *= 2;
-  if (const char *e = getenv("MNTR_GPU_CLUSTER")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8) cluster = c; }
+  // Up to 8 CTAs per tile for the pure linear kernel; up to 16 -- beyond the portable cluster size, opted into at the
+  // launch -- with CGraph tapes, where a level is more work per barrier (measured on 512 boxes = 16 tiles: C5 73.5 ->
+  // 68.8 ms with 16, but the linear kernel on C3's rows 4.55 -> 6.70 ms: the barrier over 16 CTAs costs it more than
+  // the halved shares give).  MNTR_GPU_CLUSTER_MAX overrides the limit.
+  int cmax = nl_enabled ? 16 : 8;
+  if (const char *e = getenv("MNTR_GPU_CLUSTER_MAX")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) cmax = c; }
+  while (cluster < cmax && tiles * cluster * 2 <= slots) cluster *= 2;
+  if (const char *e = getenv("MNTR_GPU_CLUSTER")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) cluster = c; }
   return directed ? launch_cluster<RoundDirected>(P, nl, io, loop_mode, max_rounds, lin_enabled, nl_enabled, tiles, cluster, stream)
                   : launch_cluster<RoundNearest>(P, nl, io, loop_mode, max_rounds, lin_enabled, nl_enabled, tiles, cluster, stream);
 }
