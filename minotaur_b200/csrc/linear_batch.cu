@@ -278,6 +278,27 @@ __device__ __forceinline__ void row_activity(const LinDev &P, int beg, int cnt_r
   }
 }
 
+// the largest reach alone (the activities of a staged row are already known to its caller)
+template <class Box>
+__device__ __forceinline__ double row_reach(const LinDev &P, int beg, int cnt_row, const Box &box, const RowStage &st, int lane)
+{
+  double wmax = 0.0;
+  for (int c0 = 0; c0 < cnt_row; c0 += 32) {
+    const int cnt = next_chunk(P, beg, c0, cnt_row, st, lane);
+    int t = 0;
+    constexpr int kB = Box::kBatch;
+    for (; t + kB <= cnt; t += kB) {
+      double a[kB]; double2 b[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) { a[u] = st.val[t + u]; b[u] = box.load(t + u, Box::kNeedsCol ? st.col[t + u] : 0); }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) acc_reach(a[u], b[u], wmax);
+    }
+    for (; t < cnt; ++t) acc_reach(st.val[t], box.load(t, Box::kNeedsCol ? st.col[t] : 0), wmax);
+  }
+  return wmax;
+}
+
 // singleton-infinity activity [getSingLfBnds_], state machine as coded in the reference (rare path)
 template <class R>
 __device__ __forceinline__ void row_sing_activity(const LinDev &P, int beg, int end, const double2 *bx,
@@ -405,15 +426,19 @@ __device__ __forceinline__ unsigned row_update(const LinDev &P, int beg, int cnt
 
 // one linear row for the 32 boxes of the tile  [linBndTighten_ with apply_to_prob == false]
 // (rows of at most 32 entries have been staged by the caller; `box` says where their {lb,ub} are)
-template <class R, class Box>
+// PRE: the caller (staged_row) has already added up the row's activities -- the same operations in the same order as
+// row_activity -- and passes them in; only the largest reach is still to be taken.
+template <class R, class Box, bool PRE = false>
 __device__ __forceinline__ void process_row(const LinDev &P, int2 info, double2 bnd, const Box &box, double2 *bx,
                                             int64_t ld, const RowStage &st, bool mine, uint32_t *flags,
-                                            uint32_t *varflag, TileShared &sh, int lane, unsigned long long &my_nnz)
+                                            uint32_t *varflag, TileShared &sh, int lane, unsigned long long &my_nnz,
+                                            double pre_ll = 0.0, double pre_uu = 0.0)
 {
   const int beg = info.x, cnt = info.y, end = beg + cnt;
   const double rl = bnd.x, ru = bnd.y;
   double ll, uu, wmax, sing_ll = -INFINITY, sing_uu = INFINITY;
-  row_activity<R>(P, beg, cnt, box, st, lane, ll, uu, wmax);
+  if constexpr (PRE) { ll = pre_ll; uu = pre_uu; wmax = row_reach(P, beg, cnt, box, st, lane); }
+  else row_activity<R>(P, beg, cnt, box, st, lane, ll, uu, wmax);
   bool need_sing = mine && (ll < -kInf20 || uu > kInf20);
   if (__any_sync(kFull, need_sing)) row_sing_activity<R>(P, beg, end, bx, ld, need_sing, sing_ll, sing_uu);
   if (mine) my_nnz += (unsigned long long)cnt;
@@ -525,7 +550,7 @@ __device__ __forceinline__ void staged_row(const LinDev &P, int2 info, double2 b
   }
   const RowStage st{slot_val(wl, slot), slot_col(wl, slot), nullptr, nullptr};
   const BoxStaged box{slot_seg(wl, slot) + lane, bx, ld};
-  process_row<R>(P, info, bnd, box, bx, ld, st, mine, flags, varflag, sh, lane, my_nnz);
+  process_row<R, BoxStaged, true>(P, info, bnd, box, bx, ld, st, mine, flags, varflag, sh, lane, my_nnz, ll, uu);
 }
 
 // Objective cut-off row  c.x <= rhs  for the 32 boxes of the tile  [varBndsFromObj_, :544-597]: evaluated after
