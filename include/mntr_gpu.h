@@ -249,13 +249,13 @@ void *mntr_gpu_stream(mntr_gpu_ctx *ctx);
 /* Node boxes in the engine's layout built on the device from a root box and branching deltas (the input form of
  * mntr_gpu_tighten_nodes; host arrays in, boxes_dev [n][mntr_gpu_box_ld(n_boxes)] double2 out).  For callers
  * that keep a batch resident in HBM -- a dense box-major host copy of config C5's batch would be 65 GB.
- * The batch is PREPARED: the call also checks on the device that the root box is a fixed point of
- * LinearHandler::tightenInts_ / checkBounds_ (LinearHandler.cpp:415-490, 328-359: no integer variable with a fractional
- * bound, no crossed bounds) and remembers which variables the deltas set, so the next mntr_gpu_tighten_dev on exactly
- * these boxes (same pointer, same n_boxes) applies integer rounding and the bound check of its first sweep only where
- * they can do anything -- at the deltas' variables and the variables the rows move -- instead of at all n variables of
- * every box.  Results are the same bit for bit.  The caller must not write to the boxes between the two calls; any
- * other batch call on the context in between, or a root box that fails the check, falls back to the full pass.
+ * The batch is PREPARED: the call also notes on the device which variables are not at a fixed point of
+ * LinearHandler::tightenInts_ / checkBounds_ (LinearHandler.cpp:415-490, 328-359) -- root variables with a fractional
+ * integer bound or crossed bounds, for every box, and the variables a box's deltas set -- so the next
+ * mntr_gpu_tighten_dev on exactly these boxes (same pointer, same n_boxes) applies integer rounding and the bound check
+ * of its first sweep only where they can do anything -- there and at the variables the rows move -- instead of at all n
+ * variables of every box.  Results are the same bit for bit.  The caller must not write to the boxes between the two
+ * calls; any other batch call on the context in between falls back to the full pass.
  * MNTR_GPU_NO_PREPARED=1 in the environment switches the shortcut off. */
 int mntr_gpu_boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *root_lb,
                                const double *root_ub, const int64_t *delta_ptr, const int32_t *delta_var,

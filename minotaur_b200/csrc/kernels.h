@@ -49,9 +49,10 @@ struct BatchIo {
   unsigned char *tstate; // [tiles][kTileStateBytes] per-tile control words (global: shared by a cluster)
   unsigned long long *nl_evals;  // [1] (constraint, box) evaluations of CGraph tapes (chkRed_ and varBoundMods each count one)
   // PREPARED batch (built by boxes_from_root + apply_deltas in this context, untouched since): non-null and *prepared == 0
-  // say that every box is the root box -- checked to be a fixed point of tightenInts_ / checkBounds_ -- except at the
-  // variables its deltas set, whose bits are already up in varflag.  The first sweep's integer rounding / bound check
-  // then visits flagged variables only instead of all n (LinearHandler.cpp:415-490, 328-359 are no-ops elsewhere).
+  // say that every variable whose bounds are not a fixed point of tightenInts_ / checkBounds_ in some box -- a root
+  // variable with a fractional integer bound or crossed bounds, a variable one of the box's deltas set -- has its bit up
+  // in varflag already.  The first sweep's integer rounding / bound check then visits flagged variables only instead of
+  // all n (LinearHandler.cpp:415-490, 328-359 are no-ops elsewhere).
   const int32_t *prepared = nullptr;
 };
 constexpr int kTileStateBytes = 640;
@@ -71,9 +72,10 @@ cudaError_t launch_boxes_unpack(const double2 *boxes, int64_t ld, int32_t n, int
 cudaError_t launch_boxes_pad(double2 *boxes, int64_t ld, int32_t n, int32_t n_boxes, cudaStream_t stream);
 
 // node form: boxes from root + deltas, and extraction of the resulting mods
-// (var_type + dirty: the root box is checked for BatchIo::prepared; varflag [tiles][n]: the deltas' variables are flagged)
+// (varflag [tiles][n], zeroed by the caller, for BatchIo::prepared: root variables that need rounding / the bound check are
+// flagged for every box, then the deltas' variables for their boxes)
 cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub, int32_t n,
-                                   int32_t n_boxes, double2 *boxes, int64_t ld, const uint8_t *var_type, int32_t *dirty,
+                                   int32_t n_boxes, double2 *boxes, int64_t ld, const uint8_t *var_type, uint32_t *varflag,
                                    cudaStream_t stream);
 cudaError_t launch_apply_deltas(const long long *delta_ptr, const int32_t *delta_var,
                                 const uint8_t *delta_is_upper, const double *delta_val,

@@ -1079,22 +1079,24 @@ __global__ void boxes_pad_kernel(double2 *boxes, int64_t ld, int n, int n_boxes)
   }
 }
 
-// every box = the root box.  With `dirty` (a prepared batch, BatchIo::prepared): *dirty is raised when the root box is
-// not a fixed point of tightenInts_ + checkBounds_ (an integer variable with a fractional bound, or crossed bounds) --
-// the batch kernel then runs its all-variables pass in the first sweep as for any other batch.
+// every box = the root box.  With `varflag` (a prepared batch, BatchIo::prepared): a variable whose ROOT bounds are not a
+// fixed point of tightenInts_ + checkBounds_ (an integer variable with a fractional bound -- NlPresHandler leaves such
+// bounds behind, CGraph.cpp:1627-1641 -- or crossed bounds) is flagged for every box of every tile, so the first sweep's
+// flag-driven pass rounds / checks it like the variables the deltas set.
 __global__ void boxes_from_root_kernel(const double *__restrict__ rl, const double *__restrict__ ru, int n,
                                        double2 *__restrict__ boxes, int64_t ld, const uint8_t *__restrict__ var_type,
-                                       int32_t *dirty)
+                                       uint32_t *varflag)
 {
   const int64_t total = (int64_t)n * ld;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = k / ld;
     const double2 b = make_double2(rl[j], ru[j]);
     boxes[k] = b;
-    if (dirty != nullptr && k == j * ld) {
+    if (varflag != nullptr && k == j * ld) {
       double l = b.x, u = b.y;
       if (is_int_type(var_type[j])) tighten_int_bounds(l, u);
-      if (l != b.x || u != b.y || b.x > b.y + kETol) *dirty = 1;
+      if (l != b.x || u != b.y || b.x > b.y + kETol)
+        for (int64_t t = 0; t < ld / 32; ++t) varflag[t * n + j] = kFull;
     }
   }
 }
@@ -1347,11 +1349,11 @@ cudaError_t launch_boxes_pad(double2 *boxes, int64_t ld, int32_t n, int32_t n_bo
 }
 
 cudaError_t launch_boxes_from_root(const double *root_lb, const double *root_ub, int32_t n, int32_t n_boxes,
-                                   double2 *boxes, int64_t ld, const uint8_t *var_type, int32_t *dirty, cudaStream_t stream)
+                                   double2 *boxes, int64_t ld, const uint8_t *var_type, uint32_t *varflag, cudaStream_t stream)
 {
   (void)n_boxes;
   if (n <= 0) return cudaSuccess;
-  boxes_from_root_kernel<<<148 * 8, 256, 0, stream>>>(root_lb, root_ub, n, boxes, ld, var_type, dirty);
+  boxes_from_root_kernel<<<148 * 8, 256, 0, stream>>>(root_lb, root_ub, n, boxes, ld, var_type, varflag);
   return cudaGetLastError();
 }
 

@@ -1416,15 +1416,15 @@ int boxes_from_deltas(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *root_lb,
     CU(cudaMemcpyAsync(D.up, delta_is_upper, (size_t)n_delta, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(D.val, delta_val, sizeof(double) * (size_t)n_delta, cudaMemcpyHostToDevice, s));
   }
-  // the batch is PREPARED (BatchIo::prepared): root box checked on the device, the deltas' variables flagged -- the
-  // next batch call on these boxes skips the all-variables rounding pass of its first sweep
+  // the batch is PREPARED (BatchIo::prepared): the root variables that need rounding or the bound check and the deltas'
+  // variables are flagged on the device -- the next batch call on these boxes skips the all-variables pass of its first sweep
   ctx->prepared_boxes = nullptr;
   const bool prep = ctx->d_varflag != nullptr && ld <= ctx->batch_ld && !getenv("MNTR_GPU_NO_PREPARED");
   if (prep) {
     CU(cudaMemsetAsync(ctx->d_varflag, 0, sizeof(uint32_t) * (size_t)n * (size_t)(ld / 32), s));
     CU(cudaMemsetAsync(ctx->d_prepared, 0, sizeof(int32_t), s));
   }
-  CU(launch_boxes_from_root(D.rl, D.ru, n, n_boxes, boxes, ld, ctx->lin.var_type, prep ? ctx->d_prepared : nullptr, s));
+  CU(launch_boxes_from_root(D.rl, D.ru, n, n_boxes, boxes, ld, ctx->lin.var_type, prep ? ctx->d_varflag : nullptr, s));
   CU(launch_apply_deltas(D.ptr, D.var, D.up, D.val, n_boxes, boxes, ld, prep ? ctx->d_varflag : nullptr, n, s));
   if (prep) { ctx->prepared_boxes = boxes; ctx->prepared_n = n_boxes; }
   return MNTR_OK;
