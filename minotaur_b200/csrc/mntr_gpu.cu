@@ -1228,6 +1228,7 @@ int mntr_gpu_boxes_upload(mntr_gpu_ctx *ctx, int32_t n_boxes, const double *lb, 
 {
   if (!ctx || !ctx->lin_loaded || n_boxes <= 0 || !lb || !ub || !boxes_dev) return fail(ctx, MNTR_E_ARG, "boxes_upload: bad argument");
   CU(cudaSetDevice(ctx->device));
+  if (ctx->prepared_boxes == boxes_dev) ctx->prepared_boxes = nullptr;      // uploaded boxes: nothing is known about them
   int rc = ensure_stage(ctx);
   if (rc) return rc;
   const int64_t ld = mntr_gpu_box_ld(n_boxes);
