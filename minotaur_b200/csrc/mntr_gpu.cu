@@ -1811,6 +1811,8 @@ int mntr_gpu_quad_presolve_node(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb, 
   if (n_mods) CU(cudaMemcpyAsync(n_mods, ctx->d_rounds, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
   if (n_sweeps) CU(cudaMemcpyAsync(n_sweeps, d_sweeps, sizeof(int32_t) * (size_t)n_boxes, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  if (!ctx->qrel_loaded && n_sweeps)                       // no relations: the reference's loop still runs once (:1215-1217)
+    for (int32_t b = 0; b < n_boxes; ++b) n_sweeps[b] = 1;
   if ((rc = mntr_gpu_boxes_download(ctx, n_boxes, ctx->d_boxes, lb, ub))) return rc;
   ctx->stats = mntr_gpu_stats{};
   ctx->stats.kernel_ms = elapsed(ctx->ev[1], ctx->ev[2]);
