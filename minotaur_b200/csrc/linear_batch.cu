@@ -1232,16 +1232,14 @@ bool encode_box_tensor_map(BoxTensorMap *out, const double2 *boxes, int64_t ld, 
   typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const encode_fn fn = []() -> encode_fn {          // (initialised once, thread-safe: the device group calls from several threads)
     void *p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (encode_fn)p;
-    else (void)cudaGetLastError();
-  }
+      return (encode_fn)p;
+    (void)cudaGetLastError();
+    return nullptr;
+  }();
   if (fn == nullptr || n <= 0 || (reinterpret_cast<uintptr_t>(boxes) & 15u) != 0) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)(2 * ld), (cuuint64_t)n};
   const cuuint64_t strides[1] = {(cuuint64_t)(16 * ld)};
