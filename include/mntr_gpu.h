@@ -329,7 +329,9 @@ int mntr_gpu_quad_simple_presolve(mntr_gpu_ctx *ctx, int32_t n_boxes, double *lb
  * absolute and 1e-7 relative).  verdict [n_boxes]: 1 = a step found inconsistent bounds (the reference returns
  * "infeasible" there; the bounds of such a box are not a result), else 0.  n_mods (may be NULL): Modification objects
  * the reference would push to p_mods (one per step that moves a variable, whether one side or both).  n_sweeps (may
- * be NULL): sweeps run (pStats_.iters).  max_sweeps <= 0: no cap, like the reference.  Not included, because they
+ * be NULL): sweeps run (pStats_.iters).  max_sweeps <= 0: no cap, like the reference -- whose loop, like this one, ends
+ * only because an accepted step improves a bound by more than 1e-8 + 1e-7 |bound|; a caller that cannot rule out slowly
+ * contracting relations passes a cap (a box cut short is valid, just not at the fixpoint; n_sweeps tells).  Not included, because they
  * change structure or belong to another algorithm: tightenQuad_ of a handler's first node (:1241-1250) and the refresh
  * of the McCormick rows (upSqCon_ / upBilCon_, :1252-1257) -- the caller runs the latter on the boxes it keeps.
  * MNTR_ROUND_NEAREST: the reference's result bit for bit; MNTR_ROUND_DIRECTED: rounded outward. */
