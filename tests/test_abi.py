@@ -59,3 +59,4 @@ def test_reference_side_patch_applies_and_compiles():
     res = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "patch_check"], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "strong_brancher_prefetch.patch applies" in res.stdout and "weak_brancher_prefetch.patch applies" in res.stdout
+    assert "quad_handler_gpu.patch applies" in res.stdout
